@@ -1,0 +1,352 @@
+// Batch-norm family on NHWC bf16 activations (fp32/fp64 statistics).
+// Replaces modeling/sync_batchnorm/batchnorm.py:48-125 (_SynchronizedBatchNorm.forward,
+// _compute_mean_std) and the F.batch_norm fallback at :50-53 of the reference, fused
+// with the ReLU/ReLU6 that always follows (mobilenet.py:12-13,41-42,51-56; assp.py:19-21;
+// decoder.py:35-37), the residual add (mobilenet.py:65) and Dropout (assp.py:78,
+// decoder.py:25,29; domian.py:18,22).
+//
+// Two-phase structure: channel sums (this rank) -> [host: all-reduce across ranks] ->
+// finalize (mean / inv-std / running stats / scale+shift) -> apply.  All kernels are
+// HBM-bound: 16-byte vector of 8 channels per thread, channel-group fastest so a warp
+// touches contiguous memory.
+#include "common.cuh"
+#include "../../include/s2r_b200.h"
+
+namespace {
+
+// Launch geometry for kernels that reduce over the pixel axis of a [P][C] tensor.
+struct RowReduceCfg {
+  int cg;       // channel groups of 8
+  int rows;     // rows handled concurrently by one CTA
+  int threads;  // cg * rows
+  int grid;
+};
+
+inline RowReduceCfg row_reduce_cfg(long long P, int C) {
+  RowReduceCfg c;
+  c.cg = C / 8;
+  c.rows = 256 / c.cg;
+  if (c.rows < 1) c.rows = 1;
+  c.threads = c.cg * c.rows;
+  long long blocks = (P + (long long)c.rows * 32 - 1) / ((long long)c.rows * 32);  // >= 32 rows per thread
+  long long cap = (long long)s2r_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  c.grid = (int)blocks;
+  return c;
+}
+
+// sums[0][c] += sum_p x[p][c], sums[1][c] += sum_p x[p][c]^2
+__global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int pitch,
+                                    int coff, int rows, double* __restrict__ sums) {
+  extern __shared__ float sm[];  // [rows][cg][16]
+  const int cg = C / 8;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+    float f[8];
+    bf16x8_to_float(ldg16(x + p * pitch + coff + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+  }
+  float* mine = sm + ((size_t)r * cg + g) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  __syncthreads();
+  // one thread per (channel-group, value) column sums over the rows
+  for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
+    const int gg = t / 16, k = t % 16;
+    double acc = 0;
+    for (int rr = 0; rr < rows; ++rr) acc += (double)sm[((size_t)rr * cg + gg) * 16 + k];
+    const int ch = gg * 8 + (k & 7);
+    atomicAdd(&sums[(k >> 3) * C + ch], acc);
+  }
+}
+
+// mean/inv-std from the (already cross-rank reduced) sums; running-stat update;
+// scale = gamma * invstd, shift = beta - mean * scale.
+// clamp_mode 0: invstd = (var + eps)^-1/2   (F.batch_norm, batchnorm.py:50-53)
+// clamp_mode 1: invstd = max(var, eps)^-1/2 (sync branch, batchnorm.py:125)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, int clamp_mode, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_invstd, float* __restrict__ scale_shift,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double sumvar = sums[C + c] - sums[c] * mean;  // batchnorm.py:117-118
+  if (sumvar < 0) sumvar = 0;
+  const double var = sumvar / count;
+  const double invstd = clamp_mode ? 1.0 / sqrt(var > (double)eps ? var : (double)eps)
+                                   : 1.0 / sqrt(var + (double)eps);
+  if (running_mean) {
+    const double unbiased = count > 1 ? sumvar / (count - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = (float)(g * invstd);
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = (float)invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = (float)(b - mean * (double)sc);
+}
+
+// eval mode: statistics are the running buffers
+__global__ void bn_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                               float* __restrict__ mean_invstd, float* __restrict__ scale_shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  mean_invstd[c] = rm[c];
+  mean_invstd[C + c] = invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = b - rm[c] * sc;
+}
+
+// y = dropout(act(x * scale + shift)) + residual
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
+                const float* __restrict__ scale_shift, int act,
+                const __nv_bfloat16* __restrict__ residual, float drop_p, unsigned long long seed,
+                __nv_bfloat16* __restrict__ y, int ypitch, int yoff) {
+  const int cg = C / 8;
+  const long long total = P * cg;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long p = t / cg;
+    const int g = (int)(t - p * cg);
+    float f[8], sc[8], sh[8];
+    bf16x8_to_float(ldg16(x + p * xpitch + xoff + g * 8), f);
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8) + 1);
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8) + 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = apply_act(fmaf(f[i], sc[i], sh[i]), act, 0.f);
+    if (drop_p > 0.f) {
+      float m[8];
+      dropout_scale8(seed, (unsigned long long)t, drop_p, m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] *= m[i];
+    }
+    if (residual) {
+      float r[8];
+      bf16x8_to_float(ldg16(residual + p * C + g * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(f);
+  }
+}
+
+// effective upstream gradient through dropout and the activation:
+// dy' = dY * dropout_mask * act'(x * scale + shift)
+__device__ __forceinline__ void bn_bwd_load(const __nv_bfloat16* dy, const __nv_bfloat16* x,
+                                            const float* scale_shift, const float* mean_invstd, int C,
+                                            int g, int act, float drop_p, unsigned long long seed,
+                                            long long t, float* gdy, float* xhat) {
+  float f[8], sc[8], sh[8], mu[8], is[8];
+  bf16x8_to_float(ldg16(dy), gdy);
+  bf16x8_to_float(ldg16(x), f);
+  *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8));
+  *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8) + 1);
+  *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8));
+  *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8) + 1);
+  *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean_invstd + g * 8));
+  *reinterpret_cast<float4*>(mu + 4) = __ldg(reinterpret_cast<const float4*>(mean_invstd + g * 8) + 1);
+  *reinterpret_cast<float4*>(is) = __ldg(reinterpret_cast<const float4*>(mean_invstd + C + g * 8));
+  *reinterpret_cast<float4*>(is + 4) = __ldg(reinterpret_cast<const float4*>(mean_invstd + C + g * 8) + 1);
+  float m[8];
+  if (drop_p > 0.f) dropout_scale8(seed, (unsigned long long)t, drop_p, m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float pre = fmaf(f[i], sc[i], sh[i]);
+    float gd = gdy[i] * act_grad(pre, act, 0.f);
+    if (drop_p > 0.f) gd *= m[i];
+    gdy[i] = gd;
+    xhat[i] = (f[i] - mu[i]) * is[i];
+  }
+}
+
+// dsums[0][c] += sum_p dy', dsums[1][c] += sum_p dy' * xhat
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
+                                     const __nv_bfloat16* __restrict__ x, int xpitch, int xoff,
+                                     const float* __restrict__ mean_invstd,
+                                     const float* __restrict__ scale_shift, int act, float drop_p,
+                                     unsigned long long seed, long long P, int C, int rows,
+                                     double* __restrict__ dsums) {
+  extern __shared__ float sm[];
+  const int cg = C / 8;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+    float gdy[8], xh[8];
+    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
+                mean_invstd, C, g, act, drop_p, seed, p * cg + g, gdy, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += gdy[i]; q[i] += gdy[i] * xh[i]; }
+  }
+  float* mine = sm + ((size_t)r * cg + g) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
+    const int gg = t / 16, k = t % 16;
+    double acc = 0;
+    for (int rr = 0; rr < rows; ++rr) acc += (double)sm[((size_t)rr * cg + gg) * 16 + k];
+    atomicAdd(&dsums[(k >> 3) * C + gg * 8 + (k & 7)], acc);
+  }
+}
+
+// dx = scale * (dy' - mean(dy') - xhat * mean(dy' xhat));  count <= 0: frozen stats, dx = scale * dy'
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
+                    const __nv_bfloat16* __restrict__ x, int xpitch, int xoff,
+                    const float* __restrict__ mean_invstd, const float* __restrict__ scale_shift,
+                    int act, float drop_p, unsigned long long seed,
+                    const double* __restrict__ dsums, double count, long long P, int C,
+                    __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff) {
+  const int cg = C / 8;
+  const long long total = P * cg;
+  const float inv_n = count > 0 ? (float)(1.0 / count) : 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long p = t / cg;
+    const int g = (int)(t - p * cg);
+    float gdy[8], xh[8], o[8];
+    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
+                mean_invstd, C, g, act, drop_p, seed, t, gdy, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      const float sc = __ldg(scale_shift + c);
+      float m1 = 0.f, m2 = 0.f;
+      if (count > 0) {
+        m1 = (float)dsums[c] * inv_n;
+        m2 = (float)dsums[C + c] * inv_n;
+      }
+      o[i] = sc * (gdy[i] - m1 - xh[i] * m2);
+    }
+    *reinterpret_cast<uint4*>(dx + p * dxpitch + dxoff + g * 8) = float_to_bf16x8(o);
+  }
+}
+
+// dgamma = sum dy' xhat, dbeta = sum dy'
+__global__ void bn_param_grad_kernel(const double* __restrict__ dsums, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)dsums[c];
+  if (dgamma) dgamma[c] = (float)dsums[C + c];
+}
+
+inline bool vec_ok(const void* p, int pitch, int off) {
+  return ((uintptr_t)p % 16 == 0) && (pitch % 8 == 0) && (off % 8 == 0);
+}
+
+}  // namespace
+
+extern "C" int s2r_channel_sums_bf16(const void* x, int64_t P, int C, int pitch, int coff,
+                                     double* sums, s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 4096, S2R_ERR_SHAPE, "channel_sums: C=%d must be a multiple of 8 in [8,4096]", C);
+  S2R_REQUIRE(vec_ok(x, pitch, coff) && pitch >= C + coff, S2R_ERR_SHAPE, "channel_sums: bad pitch/offset/alignment");
+  if (P == 0) return S2R_OK;
+  RowReduceCfg cfg = row_reduce_cfg(P, C);
+  size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
+  channel_sums_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, P, C, pitch, coff, cfg.rows, sums);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
+                               float eps, int clamp_mode, float momentum, float* running_mean,
+                               float* running_var, float* mean_invstd, float* scale_shift, int C,
+                               s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 1, S2R_ERR_SHAPE, "bn_finalize: C=%d", C);
+  // batchnorm.py:116 -- the statistics need more than one value per channel
+  S2R_REQUIRE(count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+  bn_finalize_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sums, count, gamma, beta, eps, clamp_mode, momentum, running_mean, running_var, mean_invstd,
+      scale_shift, C);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean,
+                                       const float* running_var, float eps, float* mean_invstd,
+                                       float* scale_shift, int C, s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 1, S2R_ERR_SHAPE, "bn_eval: C=%d", C);
+  bn_eval_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      gamma, beta, running_mean, running_var, eps, mean_invstd, scale_shift, C);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
+                                const float* scale_shift, int act, const void* residual,
+                                float drop_p, uint64_t seed, void* y, int ypitch, int yoff,
+                                s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8", C);
+  S2R_REQUIRE(vec_ok(x, xpitch, xoff) && vec_ok(y, ypitch, yoff) && vec_ok(residual, 8, 0) &&
+                  ((uintptr_t)scale_shift % 16 == 0),
+              S2R_ERR_SHAPE, "bn_apply: bad pitch/offset/alignment");
+  S2R_REQUIRE(drop_p >= 0.f && drop_p < 1.f, S2R_ERR_SHAPE, "bn_apply: dropout p=%f", drop_p);
+  if (P == 0) return S2R_OK;
+  const long long total = (long long)P * (C / 8);
+  bn_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
+      (const __nv_bfloat16*)residual, drop_p, seed, (__nv_bfloat16*)y, ypitch, yoff);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,
+                                 int xoff, const float* mean_invstd, const float* scale_shift, int act,
+                                 float drop_p, uint64_t seed, int64_t P, int C, double* dsums,
+                                 s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 4096, S2R_ERR_SHAPE, "bn_bwd_reduce: C=%d", C);
+  S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) &&
+                  ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
+              S2R_ERR_SHAPE, "bn_bwd_reduce: bad pitch/offset/alignment");
+  if (P == 0) return S2R_OK;
+  RowReduceCfg cfg = row_reduce_cfg(P, C);
+  size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
+  bn_bwd_reduce_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
+      scale_shift, act, drop_p, seed, P, C, cfg.rows, dsums);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,
+                                int xoff, const float* mean_invstd, const float* scale_shift, int act,
+                                float drop_p, uint64_t seed, const double* dsums, double count,
+                                int64_t P, int C, void* dx, int dxpitch, int dxoff, float* dgamma,
+                                float* dbeta, s2r_stream_t stream) {
+  S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_bwd_apply: C=%d", C);
+  S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) && vec_ok(dx, dxpitch, dxoff) &&
+                  ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
+              S2R_ERR_SHAPE, "bn_bwd_apply: bad pitch/offset/alignment");
+  if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(dsums, dgamma, dbeta, C);
+    S2R_LAUNCH_OK();
+  }
+  if (P == 0 || !dx) return S2R_OK;
+  const long long total = (long long)P * (C / 8);
+  bn_bwd_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
+      scale_shift, act, drop_p, seed, dsums, count, P, C, (__nv_bfloat16*)dx, dxpitch, dxoff);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}

@@ -1,0 +1,165 @@
+// Evaluator confusion matrix on device.
+// Replaces utils/metrics.py:34-43 (Evaluator._generate_matrix / add_batch) and the
+// host argmax at val_adapt.py:131-135 of the reference.  Integer counts, bit-exact.
+//
+// HBM-bound: 12 B/pixel (float gt + int64 pred) or (4*C + 4) B/pixel for the fused
+// argmax variant.  One shared-memory histogram per CTA, warp-aggregated with
+// match.any so spatially coherent label maps do not serialise on one bank, then
+// one 64-bit global atomic per non-empty bin per CTA.
+#include "common.cuh"
+#include "../../include/s2r_b200.h"
+
+namespace {
+
+constexpr int kMaxClass = 64;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void hist_add(unsigned int* hist, int bin) {
+  // bin < 0 means "no contribution"; all 32 lanes must call this together
+  unsigned peers = __match_any_sync(0xffffffffu, bin);
+  int leader = __ffs(peers) - 1;
+  if (bin >= 0 && (int)(threadIdx.x & 31) == leader) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
+template <typename GT>
+__device__ __forceinline__ bool gt_valid(GT g, int nc, int* cls) {
+  // mask = (gt >= 0) & (gt < nc); label uses astype('int') == truncation
+  if (g >= (GT)0 && g < (GT)nc) {
+    *cls = (int)g;
+    return true;
+  }
+  return false;
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kThreads)
+confusion_kernel(const GT* __restrict__ gt, const long long* __restrict__ pred, long long n, int nc,
+                 unsigned long long* __restrict__ counts, unsigned long long* __restrict__ bad) {
+  __shared__ unsigned int hist[kMaxClass * kMaxClass];
+  __shared__ unsigned int nbad;
+  const int bins = nc * nc;
+  for (int i = threadIdx.x; i < bins; i += kThreads) hist[i] = 0;
+  if (threadIdx.x == 0) nbad = 0;
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * kThreads;
+  // block-uniform trip count so that match.any sees all 32 lanes
+  const long long iters = (n + stride - 1) / stride;
+  const long long first = (long long)blockIdx.x * kThreads + threadIdx.x;
+  for (long long it = 0; it < iters; it += 4) {
+    GT g[4];
+    long long p[4];
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      long long i = first + (it + u) * stride;
+      in[u] = (it + u) < iters && i < n;
+      g[u] = in[u] ? gt[i] : (GT)-1;
+      p[u] = in[u] ? pred[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int cls = 0;
+      int bin = -1;
+      if (in[u] && gt_valid<GT>(g[u], nc, &cls)) {
+        if (p[u] >= 0 && p[u] < nc) bin = cls * nc + (int)p[u];
+        else atomicAdd(&nbad, 1u);
+      }
+      hist_add(hist, bin);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kThreads) {
+    unsigned int c = hist[i];
+    if (c) atomicAdd(&counts[i], (unsigned long long)c);
+  }
+  if (threadIdx.x == 0 && nbad && bad) atomicAdd(bad, (unsigned long long)nbad);
+}
+
+// Fused argmax over the class planes of NCHW fp32 logits + confusion histogram.
+// One thread per pixel, class planes walked with stride HW (each plane read is a
+// coalesced 128 B line per warp).  First maximum wins, NaN counts as maximum
+// (numpy.argmax semantics).
+__global__ void __launch_bounds__(kThreads)
+argmax_confusion_kernel(const float* __restrict__ logits, const float* __restrict__ gt, int C,
+                        long long HW, long long npix, int nc, unsigned long long* __restrict__ counts,
+                        long long* __restrict__ pred_out) {
+  __shared__ unsigned int hist[kMaxClass * kMaxClass];
+  const int bins = nc * nc;
+  for (int i = threadIdx.x; i < bins; i += kThreads) hist[i] = 0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long iters = (npix + stride - 1) / stride;
+  const long long first = (long long)blockIdx.x * kThreads + threadIdx.x;
+  for (long long it = 0; it < iters; ++it) {
+    long long i = first + it * stride;
+    int bin = -1;
+    if (i < npix) {
+      long long img = i / HW, px = i - img * HW;
+      const float* base = logits + img * (long long)C * HW + px;
+      float best = __ldg(base);
+      int arg = 0;
+      for (int c = 1; c < C; ++c) {
+        float v = __ldg(base + (long long)c * HW);
+        // strict > keeps the first maximum; a NaN beats any non-NaN
+        if (v > best || (v != v && best == best)) {
+          best = v;
+          arg = c;
+        }
+      }
+      if (pred_out) pred_out[i] = arg;
+      if (gt) {
+        int cls = 0;
+        if (gt_valid<float>(__ldg(gt + i), nc, &cls) && arg < nc) bin = cls * nc + arg;
+      }
+    }
+    if (gt) hist_add(hist, bin);
+  }
+  __syncthreads();
+  if (gt) {
+    for (int i = threadIdx.x; i < bins; i += kThreads) {
+      unsigned int c = hist[i];
+      if (c) atomicAdd(&counts[i], (unsigned long long)c);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int s2r_confusion_matrix(const void* gt, int gt_is_i64, const int64_t* pred, int64_t n,
+                                    int num_class, int64_t* counts, int64_t* bad_pred,
+                                    s2r_stream_t stream) {
+  S2R_REQUIRE(num_class >= 1 && num_class <= kMaxClass, S2R_ERR_UNSUPPORTED,
+              "confusion_matrix: num_class %d outside [1,%d]", num_class, kMaxClass);
+  S2R_REQUIRE(n >= 0, S2R_ERR_SHAPE, "confusion_matrix: negative element count");
+  if (n == 0) return S2R_OK;
+  S2R_REQUIRE(gt && pred && counts, S2R_ERR_SHAPE, "confusion_matrix: null pointer");
+  int grid = s2r_grid(n, kThreads * 16, 4);
+  if (gt_is_i64)
+    confusion_kernel<long long><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        (const long long*)gt, (const long long*)pred, n, num_class, (unsigned long long*)counts,
+        (unsigned long long*)bad_pred);
+  else
+    confusion_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        (const float*)gt, (const long long*)pred, n, num_class, (unsigned long long*)counts,
+        (unsigned long long*)bad_pred);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_argmax_confusion_nchw(const float* logits, const float* gt, int N, int C,
+                                         int64_t HW, int num_class, int64_t* counts,
+                                         int64_t* pred_out, s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 0 && C >= 1 && HW >= 0, S2R_ERR_SHAPE, "argmax_confusion: bad shape");
+  S2R_REQUIRE(!gt || (num_class >= 1 && num_class <= kMaxClass), S2R_ERR_UNSUPPORTED,
+              "argmax_confusion: num_class %d outside [1,%d]", num_class, kMaxClass);
+  S2R_REQUIRE(!gt || counts, S2R_ERR_SHAPE, "argmax_confusion: counts is null");
+  long long npix = (long long)N * HW;
+  if (npix == 0) return S2R_OK;
+  int grid = s2r_grid(npix, kThreads * 4, 8);
+  argmax_confusion_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      logits, gt, C, HW, npix, num_class > 0 ? num_class : 1, (unsigned long long*)counts,
+      (long long*)pred_out);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}

@@ -1,0 +1,424 @@
+// Bilinear resampling with align_corners=True, global average pooling and the
+// NCHW<->NHWC boundary conversions.
+// Replaces F.interpolate(..., mode='bilinear', align_corners=True) at
+// modeling/deeplab.py:31, modeling/decoder.py:39, modeling/assp.py:71 and
+// nn.AdaptiveAvgPool2d((1,1)) at modeling/assp.py:55 of the reference.
+// Source index arithmetic follows PyTorch's upsample_bilinear2d: scale =
+// (in-1)/(out-1) in fp32, src = scale*dst, i0 = int(src), i1 = i0 + (i0 < in-1).
+// Backward kernels are gather-formulated (no atomics, deterministic).
+#include "common.cuh"
+#include "../../include/s2r_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+
+__device__ __forceinline__ Lerp lerp_src(int o, float scale, int in) {
+  Lerp l;
+  const float t = scale * (float)o;
+  int i0 = (int)t;
+  if (i0 > in - 1) i0 = in - 1;
+  l.i0 = i0;
+  l.i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l.w1 = t - (float)i0;
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+
+__host__ __device__ __forceinline__ float ac_scale(int in, int out) {
+  return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+}
+
+// candidate output range that can reference input index i
+__device__ __forceinline__ void cand_range(int i, float scale, int out, int* lo, int* hi) {
+  if (scale <= 0.f) {
+    *lo = 0;
+    *hi = out - 1;
+    return;
+  }
+  int a = (int)floorf((float)(i - 1) / scale) - 1;
+  int b = (int)ceilf((float)(i + 1) / scale) + 1;
+  *lo = a < 0 ? 0 : a;
+  *hi = b > out - 1 ? out - 1 : b;
+}
+
+__device__ __forceinline__ float lerp_weight(const Lerp& l, int i) {
+  return (l.i0 == i ? l.w0 : 0.f) + (l.i1 == i ? l.w1 : 0.f);
+}
+
+// ------------------------------------------------------------ NHWC bf16 -> NHWC bf16
+__global__ void __launch_bounds__(kThreads)
+up_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Hi, int Wi, int C,
+                   __nv_bfloat16* __restrict__ y, int Ho, int Wo, int ypitch, int yoff, float sh,
+                   float sw) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const int g = (int)(t % cg);
+    long long p = t / cg;
+    const int ow = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oh = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    const Lerp ly = lerp_src(oh, sh, Hi), lx = lerp_src(ow, sw, Wi);
+    const __nv_bfloat16* b = x + (long long)n * Hi * Wi * C + g * 8;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    bf16x8_to_float(ldg16(b + ((long long)ly.i0 * Wi + lx.i0) * C), v00);
+    bf16x8_to_float(ldg16(b + ((long long)ly.i0 * Wi + lx.i1) * C), v01);
+    bf16x8_to_float(ldg16(b + ((long long)ly.i1 * Wi + lx.i0) * C), v10);
+    bf16x8_to_float(ldg16(b + ((long long)ly.i1 * Wi + lx.i1) * C), v11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o[i] = ly.w0 * (lx.w0 * v00[i] + lx.w1 * v01[i]) + ly.w1 * (lx.w0 * v10[i] + lx.w1 * v11[i]);
+    *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(o);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+up_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, int N, int Hi, int Wi,
+                   int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, float sh, float sw) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Hi * Wi * cg;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const int g = (int)(t % cg);
+    long long p = t / cg;
+    const int iw = (int)(p % Wi);
+    long long q = p / Wi;
+    const int ih = (int)(q % Hi);
+    const int n = (int)(q / Hi);
+    int hlo, hhi, wlo, whi;
+    cand_range(ih, sh, Ho, &hlo, &hhi);
+    cand_range(iw, sw, Wo, &wlo, &whi);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int oh = hlo; oh <= hhi; ++oh) {
+      const float wy = lerp_weight(lerp_src(oh, sh, Hi), ih);
+      if (wy == 0.f) continue;
+      for (int ow = wlo; ow <= whi; ++ow) {
+        const float wx = lerp_weight(lerp_src(ow, sw, Wi), iw);
+        if (wx == 0.f) continue;
+        float f[8];
+        bf16x8_to_float(ldg16(dy + (((long long)n * Ho + oh) * Wo + ow) * dypitch + dyoff + g * 8), f);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + t * 8) = float_to_bf16x8(acc);
+  }
+}
+
+// ------------------------------------------------------------ NHWC bf16 -> NCHW fp32
+template <int CG>  // ceil(C/8) vectors per pixel
+__global__ void __launch_bounds__(kThreads)
+up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi, int Wi, int C,
+                  float* __restrict__ y, int Ho, int Wo, float sh, float sw) {
+  const long long total = (long long)N * Ho * Wo;
+  const long long plane = (long long)Ho * Wo;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const int ow = (int)(t % Wo);
+    long long q = t / Wo;
+    const int oh = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    const Lerp ly = lerp_src(oh, sh, Hi), lx = lerp_src(ow, sw, Wi);
+    const __nv_bfloat16* b = x + (long long)n * Hi * Wi * xpitch;
+    const __nv_bfloat16* p00 = b + ((long long)ly.i0 * Wi + lx.i0) * xpitch;
+    const __nv_bfloat16* p01 = b + ((long long)ly.i0 * Wi + lx.i1) * xpitch;
+    const __nv_bfloat16* p10 = b + ((long long)ly.i1 * Wi + lx.i0) * xpitch;
+    const __nv_bfloat16* p11 = b + ((long long)ly.i1 * Wi + lx.i1) * xpitch;
+    float* out = y + (long long)n * C * plane + (long long)oh * Wo + ow;
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+      float v00[8], v01[8], v10[8], v11[8];
+      bf16x8_to_float(ldg16(p00 + g * 8), v00);
+      bf16x8_to_float(ldg16(p01 + g * 8), v01);
+      bf16x8_to_float(ldg16(p10 + g * 8), v10);
+      bf16x8_to_float(ldg16(p11 + g * 8), v11);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        if (c < C)
+          out[(long long)c * plane] = ly.w0 * (lx.w0 * v00[i] + lx.w1 * v01[i]) +
+                                      ly.w1 * (lx.w0 * v10[i] + lx.w1 * v11[i]);
+      }
+    }
+  }
+}
+
+// dy NCHW fp32 [N,C,Ho,Wo] -> dx NHWC bf16 [N,Hi,Wi,dxpitch]; thread per (n, c, ih, iw)
+__global__ void __launch_bounds__(kThreads)
+up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int Wo,
+                        __nv_bfloat16* __restrict__ dx, int dxpitch, int Hi, int Wi, float sh, float sw) {
+  const long long total = (long long)N * dxpitch * Hi * Wi;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const int iw = (int)(t % Wi);
+    long long q = t / Wi;
+    const int ih = (int)(q % Hi);
+    q /= Hi;
+    const int c = (int)(q % dxpitch);
+    const int n = (int)(q / dxpitch);
+    float acc = 0.f;
+    if (c < C) {
+      int hlo, hhi, wlo, whi;
+      cand_range(ih, sh, Ho, &hlo, &hhi);
+      cand_range(iw, sw, Wo, &wlo, &whi);
+      const float* src = dy + ((long long)n * C + c) * Ho * Wo;
+      for (int oh = hlo; oh <= hhi; ++oh) {
+        const float wy = lerp_weight(lerp_src(oh, sh, Hi), ih);
+        if (wy == 0.f) continue;
+        for (int ow = wlo; ow <= whi; ++ow) {
+          const float wx = lerp_weight(lerp_src(ow, sw, Wi), iw);
+          if (wx != 0.f) acc = fmaf(wy * wx, __ldg(src + (long long)oh * Wo + ow), acc);
+        }
+      }
+    }
+    dx[(((long long)n * Hi + ih) * Wi + iw) * dxpitch + c] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------------------------ global average pool
+// one CTA per (image, 64-channel slab); y[n][c] = mean_p x[n][p][c]
+__global__ void __launch_bounds__(kThreads)
+avgpool_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pitch, int coff,
+               __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float scale) {
+  __shared__ float sm[kThreads / 8][8][8];
+  const int n = blockIdx.y;
+  const int g = blockIdx.x * 8 + (threadIdx.x & 7);  // channel group of 8
+  const int r = threadIdx.x >> 3;                    // 32 row slots
+  const int cg = C / 8;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (g < cg) {
+    const __nv_bfloat16* b = x + (long long)n * HW * pitch + coff + g * 8;
+    for (int p = r; p < HW; p += kThreads / 8) {
+      float f[8];
+      bf16x8_to_float(ldg16(b + (long long)p * pitch), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[r][threadIdx.x & 7][i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int gg = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float t = 0.f;
+    for (int rr = 0; rr < kThreads / 8; ++rr) t += sm[rr][gg][i];
+    const int c = (blockIdx.x * 8 + gg) * 8 + i;
+    if (c < C) {
+      if (y_bf16) y_bf16[(long long)n * C + c] = __float2bfloat16(t * scale);
+      if (y_f32) y_f32[(long long)n * C + c] = t * scale;
+    }
+  }
+}
+
+// dx[n][p][c] = dy[n][c] * scale   (backward of the mean; also a plain broadcast with scale = 1)
+__global__ void __launch_bounds__(kThreads)
+broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, float scale,
+                 __nv_bfloat16* __restrict__ y, int ypitch, int yoff) {
+  const int cg = C / 8;
+  const long long total = (long long)N * HW * cg;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const int g = (int)(t % cg);
+    const long long p = t / cg;
+    const int n = (int)(p / HW);
+    float f[8];
+    bf16x8_to_float(ldg16(v + (long long)n * C + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= scale;
+    *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(f);
+  }
+}
+
+// ------------------------------------------------------------ layout conversions
+// x NCHW fp32 -> y NHWC bf16 with channels [C, ypitch) zero filled; pixel index fastest
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, long long HW,
+                    __nv_bfloat16* __restrict__ y, int ypitch) {
+  const int cg = ypitch / 8;
+  const long long npix = (long long)N * HW;
+  const long long total = npix * cg;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const long long p = t % npix;
+    const int g = (int)(t / npix);
+    const long long n = p / HW, px = p - n * HW;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      f[i] = c < C ? __ldg(x + (n * C + c) * HW + px) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(y + p * ypitch + g * 8) = float_to_bf16x8(f);
+  }
+}
+
+// x NHWC bf16 (pitch xpitch) -> y NCHW fp32, first C channels
+__global__ void __launch_bounds__(kThreads)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int C, long long HW,
+                    float* __restrict__ y) {
+  const int cg = (C + 7) / 8;
+  const long long npix = (long long)N * HW;
+  const long long total = npix * cg;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (long long)gridDim.x * kThreads) {
+    const long long p = t % npix;
+    const int g = (int)(t / npix);
+    const long long n = p / HW, px = p - n * HW;
+    float f[8];
+    bf16x8_to_float(ldg16(x + p * xpitch + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      if (c < C) y[(n * C + c) * HW + px] = f[i];
+    }
+  }
+}
+
+// dx = dy * (y > 0 ? 1 : slope); y is the POST-activation tensor (sign preserved by leaky relu)
+__global__ void __launch_bounds__(kThreads)
+leaky_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                 __nv_bfloat16* __restrict__ dx, long long nvec, float slope) {
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < nvec;
+       t += (long long)gridDim.x * kThreads) {
+    float g[8], a[8];
+    bf16x8_to_float(ldg16(dy + t * 8), g);
+    bf16x8_to_float(ldg16(y + t * 8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] *= (a[i] > 0.f ? 1.f : slope);
+    *reinterpret_cast<uint4*>(dx + t * 8) = float_to_bf16x8(g);
+  }
+}
+
+inline bool al16(const void* p) { return (uintptr_t)p % 16 == 0; }
+
+}  // namespace
+
+extern "C" int s2r_upsample_bilinear_nhwc(const void* x, int N, int Hi, int Wi, int C, void* y, int Ho,
+                                          int Wo, int ypitch, int yoff, s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, S2R_ERR_SHAPE, "upsample: bad shape");
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && ypitch % 8 == 0 && yoff % 8 == 0 && ypitch >= yoff + C && al16(x) && al16(y),
+              S2R_ERR_SHAPE, "upsample: channels/pitch must be multiples of 8 and buffers 16B aligned");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  up_nhwc_fwd_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
+      ac_scale(Wi, Wo));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_upsample_bilinear_nhwc_bwd(const void* dy, int dypitch, int dyoff, int N, int Hi,
+                                              int Wi, int C, int Ho, int Wo, void* dx,
+                                              s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, S2R_ERR_SHAPE, "upsample_bwd: bad shape");
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && dypitch % 8 == 0 && dyoff % 8 == 0 && dypitch >= dyoff + C && al16(dy) && al16(dx),
+              S2R_ERR_SHAPE, "upsample_bwd: channels/pitch must be multiples of 8 and buffers 16B aligned");
+  const long long total = (long long)N * Hi * Wi * (C / 8);
+  up_nhwc_bwd_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
+      ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int N, int Hi, int Wi,
+                                                  int C, float* y, int Ho, int Wo,
+                                                  s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1, S2R_ERR_SHAPE, "upsample_to_nchw: bad shape");
+  const int cgs = (C + 7) / 8;
+  S2R_REQUIRE(xpitch % 8 == 0 && xpitch >= cgs * 8 && al16(x), S2R_ERR_SHAPE,
+              "upsample_to_nchw: pitch %d must be a multiple of 8 covering C=%d", xpitch, C);
+  S2R_REQUIRE(cgs <= 4, S2R_ERR_UNSUPPORTED, "upsample_to_nchw: C=%d > 32 not supported", C);
+  const long long total = (long long)N * Ho * Wo;
+  const int grid = s2r_grid(total, kThreads, 16);
+  const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (cgs) {
+    case 1: up_to_nchw_kernel<1><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
+    case 2: up_to_nchw_kernel<2><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
+    case 3: up_to_nchw_kernel<3><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
+    default: up_to_nchw_kernel<4><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
+  }
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, int C, int Ho, int Wo,
+                                                      void* dx, int dxpitch, int Hi, int Wi,
+                                                      s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1 && dxpitch >= C, S2R_ERR_SHAPE,
+              "upsample_from_nchw_bwd: bad shape");
+  const long long total = (long long)N * dxpitch * Hi * Wi;
+  up_from_nchw_bwd_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_avgpool_nhwc(const void* x, int N, int HW, int C, int pitch, int coff, float scale,
+                                void* y_bf16, float* y_f32, s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0 && pitch % 8 == 0 && coff % 8 == 0 && al16(x),
+              S2R_ERR_SHAPE, "avgpool: bad shape/alignment");
+  dim3 grid(s2r_div_up(C / 8, 8), N);
+  avgpool_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, HW, C, pitch, coff,
+                                                             (__nv_bfloat16*)y_bf16, y_f32, scale);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_broadcast_nhwc(const void* v, int N, int HW, int C, float scale, void* y, int ypitch,
+                                  int yoff, s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0 && ypitch % 8 == 0 && yoff % 8 == 0 &&
+                  ypitch >= yoff + C && al16(v) && al16(y),
+              S2R_ERR_SHAPE, "broadcast: bad shape/alignment");
+  const long long total = (long long)N * HW * (C / 8);
+  broadcast_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)v, N, HW, C, scale, (__nv_bfloat16*)y, ypitch, yoff);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int64_t HW, void* y, int ypitch,
+                                         s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && C >= 1 && HW >= 1 && ypitch % 8 == 0 && ypitch >= C && al16(y), S2R_ERR_SHAPE,
+              "nchw_to_nhwc: bad shape (pitch must be a multiple of 8 >= C)");
+  const long long total = (long long)N * HW * (ypitch / 8);
+  nchw_to_nhwc_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      x, N, C, HW, (__nv_bfloat16*)y, ypitch);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_nhwc_bf16_to_nchw_f32(const void* x, int xpitch, int N, int C, int64_t HW, float* y,
+                                         s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 1 && C >= 1 && HW >= 1 && xpitch % 8 == 0 && xpitch >= ((C + 7) / 8) * 8 && al16(x),
+              S2R_ERR_SHAPE, "nhwc_to_nchw: bad shape");
+  const long long total = (long long)N * HW * ((C + 7) / 8);
+  nhwc_to_nchw_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, xpitch, N, C, HW, y);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_leaky_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, float slope,
+                                       s2r_stream_t stream) {
+  S2R_REQUIRE(n % 8 == 0 && al16(dy) && al16(y) && al16(dx), S2R_ERR_SHAPE, "leaky_relu_bwd: n must be a multiple of 8");
+  if (n == 0) return S2R_OK;
+  leaky_bwd_kernel<<<s2r_grid(n / 8, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, n / 8, slope);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
