@@ -1,0 +1,241 @@
+/* s2r_b200.h -- C ABI of the B200-native segmentation hot path.
+ *
+ * One shared library (libs2r_b200.so, built from
+ * synthetic-to-real-semantic-segmentation_b200/csrc/ by __graft_entry__.build()) exports every
+ * symbol declared here.  The reference (haofengsiji/synthetic-to-real-semantic-segmentation) is
+ * pure Python on top of PyTorch: it has no FFI of its own, its "operator interface" for this
+ * path is the set of torch calls listed next to each entry point below (file:line relative to
+ * the reference root).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add to route those calls here.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name ends in _host;
+ *   - the callee never allocates, frees or synchronises; it enqueues on `stream`;
+ *   - activations are NHWC bf16: element (n,h,w,c) of a tensor with channel pitch `pitch`
+ *     and channel offset `off` lives at base[((n*H + h)*W + w)*pitch + off + c];
+ *   - return value 0 = success, <0 = error (S2R_ERR_*), message via s2r_last_error().
+ */
+#ifndef S2R_B200_H_
+#define S2R_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* s2r_stream_t; /* a cudaStream_t */
+
+#define S2R_OK 0
+#define S2R_ERR_SHAPE (-1)
+#define S2R_ERR_UNSUPPORTED (-2)
+#define S2R_ERR_CUDA (-3)
+
+/* activation codes */
+#define S2R_ACT_NONE 0
+#define S2R_ACT_RELU 1
+#define S2R_ACT_RELU6 2
+#define S2R_ACT_LEAKY 3
+
+int s2r_version(void);
+const char* s2r_last_error(void);
+/* 1 when the current device is sm_100 (the only architecture the kernels are built for) */
+int s2r_device_ok(void);
+
+/* ------------------------------------------------------------------ dense convolutions
+ * A convolution is a "tap GEMM":
+ *   out[n,oh,ow,co] = epi( sum_t sum_ci src_t[n, oh+dh_t, ow+dw_t, ci] * W[slice_t][co][ci] )
+ * Every tap reads a strided VIEW of an NHWC bf16 tensor (out-of-view reads are zero), which
+ * expresses padding, dilation, stride-2 (one view per input parity) and transposed (data
+ * gradient) convolutions with unit-step pixel boxes.  Replaces nn.Conv2d forward/backward at
+ * modeling/backbone/mobilenet.py:11,44,50,58; modeling/assp.py:10,56,59; modeling/decoder.py:19,22,26,30;
+ * modeling/discriminator.py:11-15; modeling/domian.py:15,19,23.
+ */
+#define S2R_MAX_TAPS 16
+
+typedef struct {
+  const void* base; /* bf16; channel 0 of view pixel (0,0,0) */
+  int64_t sn, sh, sw; /* element strides of the view */
+  int32_t H, W;       /* view extent; reads outside are zero */
+  int32_t dh, dw;     /* source pixel = (oh + dh, ow + dw) */
+  int32_t wslice;     /* fwd: weight slice index; wgrad: unused */
+  int32_t _pad;
+  int64_t wofs;       /* wgrad: element offset of this tap inside the weight-gradient tensor */
+} s2r_tap;
+
+#define S2R_AUX_NONE 0
+#define S2R_AUX_ADD 1        /* out = act(acc + bias) + aux */
+#define S2R_AUX_LEAKY_MASK 2 /* out = (acc + bias) * (aux > 0 ? 1 : slope) */
+
+typedef struct {
+  uint32_t struct_size; /* sizeof(s2r_conv_args), checked */
+  int32_t ntaps;
+  s2r_tap taps[S2R_MAX_TAPS];
+  int32_t N, OH, OW; /* output pixel grid, M = N*OH*OW */
+  int32_t Cin, Cout; /* contraction width per tap (multiple of 8), output channels */
+  const void* w;     /* packed bf16 [nslices][Cout_pad][Kpad] (see s2r_pack_weight) */
+  int32_t Cout_pad, Kpad;
+  void* out; /* bf16 view */
+  int64_t on, oh, ow;
+  const float* bias; /* [Cout] or NULL */
+  int32_t act;
+  float slope;
+  int32_t aux_mode;
+  int32_t _pad;
+  const void* aux; /* bf16 view, same pixel grid as out */
+  int64_t an, ah, aw;
+  double* stats; /* [2][Cout]: += sum and sum of squares of (acc + bias), or NULL */
+} s2r_conv_args;
+
+int s2r_conv_fwd(const s2r_conv_args* a, s2r_stream_t stream);
+/* the shape-agnostic mma.sync implementation, exported as the on-device cross-check */
+int s2r_conv_fwd_mma(const s2r_conv_args* a, s2r_stream_t stream);
+
+typedef struct {
+  uint32_t struct_size;
+  int32_t ntaps;
+  s2r_tap taps[S2R_MAX_TAPS]; /* source views (the conv input) */
+  int32_t N, OH, OW;          /* pixel grid of dy */
+  int32_t Cin, Cout; /* real (unpadded) channel counts of the weight; views hold >= round8() */
+  const void* dy; /* bf16 view [N,OH,OW,>=round8(Cout)] */
+  int64_t dn, dh, dw;
+  float* dweight;       /* fp32, += ; element (co,ci,tap) at co*s_co + ci*s_ci + taps[t].wofs */
+  int64_t s_co, s_ci;
+} s2r_wgrad_args;
+
+int s2r_conv_wgrad(const s2r_wgrad_args* a, s2r_stream_t stream);
+
+/* w: fp32 [Cout][Cin][R][S] (OIHW, nn.Conv2d.weight).  packed: bf16 [R*S][A_pad][B_pad] with
+ * (A,B) = (Cout,Cin) when transpose == 0 (forward) or (Cin,Cout) when transpose == 1 (data
+ * gradient); A_pad/B_pad >= A/B, padding is zero filled. */
+int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int transpose, void* packed,
+                    int A_pad, int B_pad, s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ depthwise 3x3
+ * groups=C nn.Conv2d of InvertedResidual (modeling/backbone/mobilenet.py:40,54), fused with the
+ * BatchNorm+ReLU6 that precedes it (mobilenet.py:51-52 / :12-13) as a load prologue and with
+ * the zero padding of fixed_padding (mobilenet.py:17-23,62).
+ *   in(n,h,w,c) = act(x*scale[c] + shift[c]) inside the tensor,
+ *                 halo_const ? act(shift[c]) : 0 outside (|pad| pixels on every side).
+ * in_scale_shift == NULL means in = x (no prologue).  stats (optional) += per-channel sum and
+ * sum of squares of the raw output. */
+int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
+                      const float* w, void* y, double* stats, int N, int H, int W, int C,
+                      int stride, int dil, int pad, s2r_stream_t stream);
+/* Data gradient w.r.t. the PRE-prologue tensor's BN output, masked by act':
+ *   g = dgrad(dy) * act'(x*scale + shift), written on the domain extended by `ext` pixels on
+ *   every side (ext = pad when halo_const, where x counts as 0; else 0):  g[N][H+2ext][W+2ext][C].
+ *   bwd_sums (optional, [2][C]) += sum g and sum g*xhat, xhat = (x - mean)*invstd. */
+int s2r_dwconv3x3_dgrad(const void* dy, const float* w, const void* x, const float* in_scale_shift,
+                        const float* in_mean_invstd, int in_act, int ext, void* g, double* bwd_sums,
+                        int N, int H, int W, int C, int stride, int dil, int pad,
+                        s2r_stream_t stream);
+int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, int in_act, int halo_const,
+                        const void* dy, float* dw, int N, int H, int W, int C, int stride, int dil,
+                        int pad, s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ batch norm
+ * modeling/sync_batchnorm/batchnorm.py:48-78,113-125 and the F.batch_norm fallback (:50-53). */
+int s2r_channel_sums_bf16(const void* x, int64_t P, int C, int pitch, int coff, double* sums,
+                          s2r_stream_t stream);
+/* clamp_mode 0: invstd = (var+eps)^-1/2 (F.batch_norm); 1: max(var,eps)^-1/2 (batchnorm.py:125) */
+int s2r_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
+                    float eps, int clamp_mode, float momentum, float* running_mean,
+                    float* running_var, float* mean_invstd, float* scale_shift, int C,
+                    s2r_stream_t stream);
+int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* mean_invstd,
+                            float* scale_shift, int C, s2r_stream_t stream);
+/* y = dropout(act(x*scale + shift)) + residual */
+int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
+                     const float* scale_shift, int act, const void* residual, float drop_p,
+                     uint64_t seed, void* y, int ypitch, int yoff, s2r_stream_t stream);
+int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch, int xoff,
+                      const float* mean_invstd, const float* scale_shift, int act, float drop_p,
+                      uint64_t seed, int64_t P, int C, double* dsums, s2r_stream_t stream);
+/* dx = scale*(dy' - mean(dy') - xhat*mean(dy' xhat)); count<=0: frozen statistics.
+ * win_pad > 0: dy is the interior window of a [N][win_H+2pad][win_W+2pad] pixel grid. */
+int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const void* x, int xpitch, int xoff,
+                     const float* mean_invstd, const float* scale_shift, int act, float drop_p,
+                     uint64_t seed, const double* dsums, double count, int64_t P, int C, void* dx,
+                     int dxpitch, int dxoff, float* dgamma /* += */, float* dbeta /* += */, int win_H, int win_W,
+                     int win_pad, s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ resampling / layout
+ * F.interpolate(mode='bilinear', align_corners=True) at modeling/deeplab.py:31,
+ * modeling/decoder.py:39, modeling/assp.py:71; nn.AdaptiveAvgPool2d at modeling/assp.py:55. */
+int s2r_upsample_bilinear_nhwc(const void* x, int N, int Hi, int Wi, int C, void* y, int Ho, int Wo,
+                               int ypitch, int yoff, s2r_stream_t stream);
+int s2r_upsample_bilinear_nhwc_bwd(const void* dy, int dypitch, int dyoff, int N, int Hi, int Wi,
+                                   int C, int Ho, int Wo, void* dx, s2r_stream_t stream);
+int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int N, int Hi, int Wi, int C,
+                                       float* y, int Ho, int Wo, s2r_stream_t stream);
+int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, int C, int Ho, int Wo, void* dx,
+                                           int dxpitch, int Hi, int Wi, s2r_stream_t stream);
+int s2r_avgpool_nhwc(const void* x, int N, int HW, int C, int pitch, int coff, float scale,
+                     void* y_bf16, float* y_f32, s2r_stream_t stream);
+/* y[n,p,c] (+)= v[n,c]*scale */
+int s2r_broadcast_nhwc(const void* v, int N, int HW, int C, float scale, int accumulate, void* y,
+                       int ypitch, int yoff, s2r_stream_t stream);
+int s2r_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int64_t HW, void* y, int ypitch,
+                              s2r_stream_t stream);
+int s2r_nhwc_bf16_to_nchw_f32(const void* x, int xpitch, int N, int C, int64_t HW, float* y,
+                              s2r_stream_t stream);
+int s2r_leaky_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, float slope,
+                            s2r_stream_t stream);
+/* a[i] += b[i] on bf16 vectors (n multiple of 8) */
+int s2r_add_bf16(void* a, const void* b, int64_t n, s2r_stream_t stream);
+/* out[c] += (float)sums[c] */
+int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ losses
+ * F.softmax(x, dim=0) at train_adapt.py:151,166,174; nn.CrossEntropyLoss at utils/loss.py:21-30,
+ * 57-69; torch.nn.BCEWithLogitsLoss at train_adapt.py:75,153,168,176. */
+int s2r_softmax_dim0_fwd(const float* x, float* y, int B, int64_t M, s2r_stream_t stream);
+int s2r_softmax_dim0_bwd(const float* y, const float* dy, float* dx, int B, int64_t M,
+                         s2r_stream_t stream);
+int s2r_cross_entropy_nchw(const float* logits, const float* target, int const_target,
+                           const float* weight, int N, int C, int64_t HW, int ignore_index,
+                           double* sums, float* grad_unscaled, s2r_stream_t stream);
+int s2r_ratio(const double* sums, double denom_override, float* out, s2r_stream_t stream);
+int s2r_scale_by_ratio(float* g, int64_t n, const float* gout, const double* sums,
+                       double denom_override, s2r_stream_t stream);
+int s2r_bce_logits_fwd(const float* x, const float* target, float const_target, int64_t n,
+                       double* sums, s2r_stream_t stream);
+int s2r_bce_logits_bwd(const float* x, const float* target, float const_target, int64_t n,
+                       const float* gout, float* dx, s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ Evaluator
+ * utils/metrics.py:34-43 (_generate_matrix/add_batch) and the host argmax at val_adapt.py:131-135. */
+int s2r_confusion_matrix(const void* gt, int gt_is_i64, const int64_t* pred, int64_t n,
+                         int num_class, int64_t* counts, int64_t* bad_pred, s2r_stream_t stream);
+int s2r_argmax_confusion_nchw(const float* logits, const float* gt, int N, int C, int64_t HW,
+                              int num_class, int64_t* counts, int64_t* pred_out,
+                              s2r_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizers
+ * torch.optim.SGD / Adam steps at train_adapt.py:58-60,180-181 and train.py:63-82,202-204, as
+ * multi-tensor kernels over a device table of (param, grad, state) pointers. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* s0; /* SGD: momentum buffer; Adam: exp_avg */
+  float* s1; /* Adam: exp_avg_sq */
+  int64_t n;
+  float lr_mult; /* per-tensor lr multiplier (1x / 10x groups, deeplab.py:42-72) */
+  float _pad;
+} s2r_param_slot;
+
+/* hyper (device): [0] = lr, [1] = 1 - beta1^t, [2] = 1 - beta2^t (Adam only).
+ * SGD: g' = g*gscale + wd*p; buf = momentum*buf + (1-dampening)*g'; p -= lr*lr_mult*(nesterov ? g' + momentum*buf : buf)
+ * (momentum buffers start at zero, which equals torch's first-step rule for dampening == 0). */
+int s2r_sgd_step(const s2r_param_slot* slots, int nslots, const float* hyper, float momentum,
+                 float dampening, float weight_decay, int nesterov, float gscale,
+                 s2r_stream_t stream);
+int s2r_adam_step(const s2r_param_slot* slots, int nslots, const float* hyper, float beta1,
+                  float beta2, float eps, float weight_decay, float gscale, s2r_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2R_B200_H_ */

@@ -1,0 +1,142 @@
+"""ctypes binding of libs2r_b200.so (the C ABI declared in include/s2r_b200.h).
+
+The product path has no CPU or eager fallback: if the shared library is missing, or a call is
+made without a CUDA device, the error is raised here and propagates.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs2r_b200.so")
+
+S2R_MAX_TAPS = 16
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = 0, 1, 2, 3
+AUX_NONE, AUX_ADD, AUX_LEAKY_MASK = 0, 1, 2
+
+vp = C.c_void_p
+i32 = C.c_int
+i64 = C.c_int64
+u64 = C.c_uint64
+f32 = C.c_float
+f64 = C.c_double
+
+
+class Tap(C.Structure):
+    _fields_ = [("base", vp), ("sn", i64), ("sh", i64), ("sw", i64), ("H", i32), ("W", i32),
+                ("dh", i32), ("dw", i32), ("wslice", i32), ("_pad", i32), ("wofs", i64)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("ntaps", i32), ("taps", Tap * S2R_MAX_TAPS),
+                ("N", i32), ("OH", i32), ("OW", i32), ("Cin", i32), ("Cout", i32),
+                ("w", vp), ("Cout_pad", i32), ("Kpad", i32),
+                ("out", vp), ("on", i64), ("oh", i64), ("ow", i64),
+                ("bias", vp), ("act", i32), ("slope", f32), ("aux_mode", i32), ("_pad", i32),
+                ("aux", vp), ("an", i64), ("ah", i64), ("aw", i64), ("stats", vp)]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("ntaps", i32), ("taps", Tap * S2R_MAX_TAPS),
+                ("N", i32), ("OH", i32), ("OW", i32), ("Cin", i32), ("Cout", i32),
+                ("dy", vp), ("dn", i64), ("dh", i64), ("dw", i64),
+                ("dweight", vp), ("s_co", i64), ("s_ci", i64)]
+
+
+class ParamSlot(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("s0", vp), ("s1", vp), ("n", i64), ("lr_mult", f32),
+                ("_pad", f32)]
+
+
+# name -> argtypes (the trailing stream argument included); every function returns int
+PROTOTYPES = {
+    "s2r_conv_fwd": [C.POINTER(ConvArgs), vp],
+    "s2r_conv_fwd_mma": [C.POINTER(ConvArgs), vp],
+    "s2r_conv_wgrad": [C.POINTER(WgradArgs), vp],
+    "s2r_pack_weight": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
+    "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_channel_sums_bf16": [vp, i64, i32, i32, i32, vp, vp],
+    "s2r_bn_finalize": [vp, f64, vp, vp, f32, i32, f32, vp, vp, vp, vp, i32, vp],
+    "s2r_bn_eval_scale_shift": [vp, vp, vp, vp, f32, vp, vp, i32, vp],
+    "s2r_bn_apply_act": [vp, i64, i32, i32, i32, vp, i32, vp, f32, u64, vp, i32, i32, vp],
+    "s2r_bn_bwd_reduce": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, i64, i32, vp, vp],
+    "s2r_bn_bwd_apply": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, f64, i64, i32, vp,
+                         i32, i32, vp, vp, i32, i32, i32, vp],
+    "s2r_upsample_bilinear_nhwc": [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp],
+    "s2r_upsample_bilinear_nhwc_bwd": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
+    "s2r_upsample_bilinear_nhwc_to_nchw": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
+    "s2r_upsample_bilinear_nchw_bwd_to_nhwc": [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp],
+    "s2r_avgpool_nhwc": [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
+    "s2r_broadcast_nhwc": [vp, i32, i32, i32, f32, i32, vp, i32, i32, vp],
+    "s2r_nchw_f32_to_nhwc_bf16": [vp, i32, i32, i64, vp, i32, vp],
+    "s2r_nhwc_bf16_to_nchw_f32": [vp, i32, i32, i32, i64, vp, vp],
+    "s2r_leaky_relu_bwd_bf16": [vp, vp, vp, i64, f32, vp],
+    "s2r_add_bf16": [vp, vp, i64, vp],
+    "s2r_add_f64_to_f32": [vp, vp, i32, vp],
+    "s2r_softmax_dim0_fwd": [vp, vp, i32, i64, vp],
+    "s2r_softmax_dim0_bwd": [vp, vp, vp, i32, i64, vp],
+    "s2r_cross_entropy_nchw": [vp, vp, i32, vp, i32, i32, i64, i32, vp, vp, vp],
+    "s2r_ratio": [vp, f64, vp, vp],
+    "s2r_scale_by_ratio": [vp, i64, vp, vp, f64, vp],
+    "s2r_bce_logits_fwd": [vp, vp, f32, i64, vp, vp],
+    "s2r_bce_logits_bwd": [vp, vp, f32, i64, vp, vp, vp],
+    "s2r_confusion_matrix": [vp, i32, vp, i64, i32, vp, vp, vp],
+    "s2r_argmax_confusion_nchw": [vp, vp, i32, i32, i64, i32, vp, vp, vp],
+    "s2r_sgd_step": [vp, i32, vp, f32, f32, f32, i32, f32, vp],
+    "s2r_adam_step": [vp, i32, vp, f32, f32, f32, f32, f32, vp],
+}
+PLAIN = {"s2r_version": (i32, []), "s2r_last_error": (C.c_char_p, []), "s2r_device_ok": (i32, [])}
+
+_lib = None
+launches = 0  # number of C-ABI compute calls issued by this process (bench.py reports it)
+
+
+class S2RError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise S2RError(
+                "libs2r_b200.so is missing (%s): run __graft_entry__.build(); there is no fallback path"
+                % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = i32
+        for name, (res, argtypes) in PLAIN.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().s2r_last_error().decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point and convert a non-zero status into an exception."""
+    global launches
+    rc = getattr(lib(), name)(*args)
+    launches += 1
+    if rc != 0:
+        msg = last_error()
+        if rc == -1:
+            raise ValueError("%s: %s" % (name, msg))
+        if rc == -2:
+            raise NotImplementedError("%s: %s" % (name, msg))
+        raise S2RError("%s failed (%d): %s" % (name, rc, msg))
+    return rc
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise S2RError("s2r_b200 needs a CUDA device (sm_100a); there is no CPU path")

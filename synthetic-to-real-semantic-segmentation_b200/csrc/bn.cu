@@ -10,7 +10,6 @@
 // HBM-bound: 16-byte vector of 8 channels per thread, channel-group fastest so a warp
 // touches contiguous memory.
 #include "common.cuh"
-#include "../../include/s2r_b200.h"
 
 namespace {
 
@@ -215,7 +214,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
                     const float* __restrict__ mean_invstd, const float* __restrict__ scale_shift,
                     int act, float drop_p, unsigned long long seed,
                     const double* __restrict__ dsums, double count, long long P, int C,
-                    __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff) {
+                    __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff, int win_H, int win_W,
+                    int win_pad) {
   const int cg = C / 8;
   const long long total = P * cg;
   const float inv_n = count > 0 ? (float)(1.0 / count) : 0.f;
@@ -224,7 +224,15 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
     const long long p = t / cg;
     const int g = (int)(t - p * cg);
     float gdy[8], xh[8], o[8];
-    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
+    long long pd = p;  // pixel index inside dy (interior window of a padded grid when win_pad > 0)
+    if (win_pad > 0) {
+      const int w_ = (int)(p % win_W);
+      const long long q_ = p / win_W;
+      const int h_ = (int)(q_ % win_H);
+      const long long n_ = q_ / win_H;
+      pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * (win_W + 2 * win_pad) + w_ + win_pad;
+    }
+    bn_bwd_load(dy + pd * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
                 mean_invstd, C, g, act, drop_p, seed, t, gdy, xh);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -241,13 +249,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
   }
 }
 
-// dgamma = sum dy' xhat, dbeta = sum dy'
+// dgamma += sum dy' xhat, dbeta += sum dy'
 __global__ void bn_param_grad_kernel(const double* __restrict__ dsums, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dbeta) dbeta[c] = (float)dsums[c];
-  if (dgamma) dgamma[c] = (float)dsums[C + c];
+  if (dbeta) dbeta[c] += (float)dsums[c];
+  if (dgamma) dgamma[c] += (float)dsums[C + c];
 }
 
 inline bool vec_ok(const void* p, int pitch, int off) {
@@ -333,7 +341,7 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
                                 int xoff, const float* mean_invstd, const float* scale_shift, int act,
                                 float drop_p, uint64_t seed, const double* dsums, double count,
                                 int64_t P, int C, void* dx, int dxpitch, int dxoff, float* dgamma,
-                                float* dbeta, s2r_stream_t stream) {
+                                float* dbeta, int win_H, int win_W, int win_pad, s2r_stream_t stream) {
   S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_bwd_apply: C=%d", C);
   S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) && vec_ok(dx, dxpitch, dxoff) &&
                   ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
@@ -343,10 +351,13 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
     S2R_LAUNCH_OK();
   }
   if (P == 0 || !dx) return S2R_OK;
+  S2R_REQUIRE(win_pad == 0 || (win_H >= 1 && win_W >= 1 && P % ((int64_t)win_H * win_W) == 0), S2R_ERR_SHAPE,
+              "bn_bwd_apply: window %dx%d does not tile P", win_H, win_W);
   const long long total = (long long)P * (C / 8);
   bn_bwd_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
-      scale_shift, act, drop_p, seed, dsums, count, P, C, (__nv_bfloat16*)dx, dxpitch, dxoff);
+      scale_shift, act, drop_p, seed, dsums, count, P, C, (__nv_bfloat16*)dx, dxpitch, dxoff, win_H,
+      win_W, win_pad);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

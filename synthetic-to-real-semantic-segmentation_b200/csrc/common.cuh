@@ -9,10 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define S2R_OK 0
-#define S2R_ERR_SHAPE (-1)        // bad shape / alignment
-#define S2R_ERR_UNSUPPORTED (-2)  // configuration not supported by this build
-#define S2R_ERR_CUDA (-3)         // CUDA runtime/driver error (see s2r_last_error)
+#include "../../include/s2r_b200.h"
 
 void s2r_set_error(const char* fmt, ...);
 
@@ -44,8 +41,6 @@ void s2r_set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
-// activation codes shared by conv epilogues and the BN-apply kernels
-enum : int { S2R_ACT_NONE = 0, S2R_ACT_RELU = 1, S2R_ACT_RELU6 = 2, S2R_ACT_LEAKY = 3 };
 
 static inline int s2r_sm_count() {
   static int n = 0;

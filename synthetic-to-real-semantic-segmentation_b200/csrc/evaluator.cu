@@ -7,7 +7,6 @@
 // match.any so spatially coherent label maps do not serialise on one bank, then
 // one 64-bit global atomic per non-empty bin per CTA.
 #include "common.cuh"
-#include "../../include/s2r_b200.h"
 
 namespace {
 

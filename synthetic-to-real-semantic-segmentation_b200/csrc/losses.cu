@@ -3,7 +3,6 @@
 //   * ignore-index / class-weighted cross entropy (utils/loss.py:21-30, 57-69)
 //   * BCE-with-logits against a constant or tensor target (train_adapt.py:75,153,168,176)
 #include "common.cuh"
-#include "../../include/s2r_b200.h"
 
 namespace {
 

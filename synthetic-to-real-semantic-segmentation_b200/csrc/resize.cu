@@ -7,7 +7,6 @@
 // (in-1)/(out-1) in fp32, src = scale*dst, i0 = int(src), i1 = i0 + (i0 < in-1).
 // Backward kernels are gather-formulated (no atomics, deterministic).
 #include "common.cuh"
-#include "../../include/s2r_b200.h"
 
 namespace {
 
@@ -225,7 +224,7 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pitch, in
 
 // dx[n][p][c] = dy[n][c] * scale   (backward of the mean; also a plain broadcast with scale = 1)
 __global__ void __launch_bounds__(kThreads)
-broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, float scale,
+broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, float scale, int accumulate,
                  __nv_bfloat16* __restrict__ y, int ypitch, int yoff) {
   const int cg = C / 8;
   const long long total = (long long)N * HW * cg;
@@ -238,6 +237,12 @@ broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, floa
     bf16x8_to_float(ldg16(v + (long long)n * C + g * 8), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] *= scale;
+    if (accumulate) {
+      float o[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(y + p * ypitch + yoff + g * 8), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += o[i];
+    }
     *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(f);
   }
 }
@@ -379,14 +384,14 @@ extern "C" int s2r_avgpool_nhwc(const void* x, int N, int HW, int C, int pitch, 
   return S2R_OK;
 }
 
-extern "C" int s2r_broadcast_nhwc(const void* v, int N, int HW, int C, float scale, void* y, int ypitch,
-                                  int yoff, s2r_stream_t stream) {
+extern "C" int s2r_broadcast_nhwc(const void* v, int N, int HW, int C, float scale, int accumulate,
+                                  void* y, int ypitch, int yoff, s2r_stream_t stream) {
   S2R_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0 && ypitch % 8 == 0 && yoff % 8 == 0 &&
                   ypitch >= yoff + C && al16(v) && al16(y),
               S2R_ERR_SHAPE, "broadcast: bad shape/alignment");
   const long long total = (long long)N * HW * (C / 8);
   broadcast_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)v, N, HW, C, scale, (__nv_bfloat16*)y, ypitch, yoff);
+      (const __nv_bfloat16*)v, N, HW, C, scale, accumulate, (__nv_bfloat16*)y, ypitch, yoff);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

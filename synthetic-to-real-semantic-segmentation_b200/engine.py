@@ -1,0 +1,460 @@
+"""Host-side execution engine: NHWC bf16 activation views, tap tables for the tap-GEMM
+convolutions, thin wrappers over the C ABI and the composite layers (conv+BN+act,
+InvertedResidual) with hand-written backward passes.
+
+Everything here only moves pointers and sizes; the arithmetic is in csrc/*.cu.  torch supplies
+device memory (caching allocator), the current stream and, for data-parallel runs,
+torch.distributed (NCCL) for the BN-statistics and gradient all-reduces.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class Act:
+    """View of an NHWC bf16 tensor: channels [off, off+C) of storage t[N,H,W,pitch]."""
+    __slots__ = ("t", "N", "H", "W", "C", "pitch", "off")
+
+    def __init__(self, t, C=None, off=0):
+        assert t.dtype == BF16 and t.dim() == 4 and t.is_contiguous()
+        self.t = t
+        self.N, self.H, self.W, self.pitch = t.shape
+        self.off = off
+        self.C = (self.pitch - off) if C is None else C
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.off
+
+    @property
+    def P(self):
+        return self.N * self.H * self.W
+
+    def slice(self, off, C):
+        return Act(self.t, C, self.off + off)
+
+    def vp(self):
+        return C.c_void_p(self.ptr)
+
+
+class Ctx:
+    """Per-call execution context (stream, mode, cross-rank synchronisation of BN)."""
+
+    def __init__(self, device, training, sync_group=None, dropout=True):
+        L.require_cuda()
+        self.device = device
+        self.training = training
+        self.stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        self.group = sync_group
+        self.world = 1
+        if sync_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(sync_group)
+        self.dropout = dropout
+        # host-side seed stream for dropout masks (regenerated, never stored)
+        self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and dropout) else 0
+
+    def next_seed(self):
+        self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        return self._seed
+
+    def new(self, N, H, W, Cc, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return Act(f((N, H, W, Cc), dtype=BF16, device=self.device))
+
+    def f32(self, n, zero=True):
+        return (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.device)
+
+    def f64(self, n):
+        return torch.zeros(n, dtype=torch.float64, device=self.device)
+
+    def allreduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+
+
+# --------------------------------------------------------------------------- weights
+def packed_weight(cx, w, transpose):
+    """bf16 [R*S][A_pad][B_pad] copy of an OIHW fp32 parameter, cached per parameter version."""
+    cache = getattr(w, "_s2r_pack", None)
+    if cache is None:
+        cache = {}
+        w._s2r_pack = cache
+    key = (transpose, w.data_ptr())
+    ent = cache.get(key)
+    if ent is not None and ent[0] == w._version:
+        return ent[1], ent[2], ent[3]
+    Cout, Cin, R, S = w.shape
+    A, B = (Cin, Cout) if transpose else (Cout, Cin)
+    A_pad, B_pad = round_up(A, 16), round_up(B, 64)
+    buf = ent[1] if ent is not None else torch.empty((R * S, A_pad, B_pad), dtype=BF16, device=w.device)
+    L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, R, S, 1 if transpose else 0, _vp(buf), A_pad, B_pad,
+           cx.stream)
+    cache[key] = (w._version, buf, A_pad, B_pad)
+    return buf, A_pad, B_pad
+
+
+def grad_of(p):
+    """fp32 gradient buffer of a parameter, allocated (zero) on first use; kernels accumulate."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+# --------------------------------------------------------------------------- tap tables
+def _fill_tap(tap, base, sn, sh, sw, H, W, dh, dw, wslice, wofs):
+    tap.base = base
+    tap.sn, tap.sh, tap.sw = sn, sh, sw
+    tap.H, tap.W = H, W
+    tap.dh, tap.dw = dh, dw
+    tap.wslice = wslice
+    tap.wofs = wofs
+
+
+def fwd_taps(taps, x, R, S, stride, pad, dil):
+    """Forward taps of an RxS conv on x: one strided view per input parity (stride 1: one view)."""
+    n = 0
+    for kh in range(R):
+        eh = kh * dil - pad
+        ph = eh % stride
+        for kw in range(S):
+            ew = kw * dil - pad
+            pw = ew % stride
+            base = x.ptr + 2 * (ph * x.W + pw) * x.pitch
+            _fill_tap(taps[n], base, x.H * x.W * x.pitch, stride * x.W * x.pitch, stride * x.pitch,
+                      (x.H - ph + stride - 1) // stride, (x.W - pw + stride - 1) // stride,
+                      (eh - ph) // stride, (ew - pw) // stride, kh * S + kw, kh * S + kw)
+            n += 1
+    return n
+
+
+def conv_out_hw(H, W, R, S, stride, pad, dil):
+    return ((H + 2 * pad - dil * (R - 1) - 1) // stride + 1, (W + 2 * pad - dil * (S - 1) - 1) // stride + 1)
+
+
+def conv_fwd(cx, x, w, out, stride=1, pad=0, dil=1, bias=None, act=L.ACT_NONE, slope=0.0, stats=None,
+             aux=None, aux_mode=L.AUX_NONE, force_mma=False):
+    """out = epi(conv(x, w)); x/out are Act views, w an OIHW fp32 parameter."""
+    Cout, Cin, R, S = w.shape
+    assert x.C >= Cin and out.C >= Cout, (x.C, Cin, out.C, Cout)
+    OH, OW = conv_out_hw(x.H, x.W, R, S, stride, pad, dil)
+    assert (out.N, out.H, out.W) == (x.N, OH, OW), ((out.N, out.H, out.W), (x.N, OH, OW))
+    wp, Cout_pad, Kpad = packed_weight(cx, w, False)
+    a = L.ConvArgs()
+    a.struct_size = C.sizeof(L.ConvArgs)
+    a.ntaps = fwd_taps(a.taps, x, R, S, stride, pad, dil)
+    a.N, a.OH, a.OW = x.N, OH, OW
+    a.Cin, a.Cout = round_up(Cin, 8), Cout
+    assert x.pitch - x.off >= a.Cin
+    a.w, a.Cout_pad, a.Kpad = wp.data_ptr(), Cout_pad, Kpad
+    a.out = out.ptr
+    a.on, a.oh, a.ow = out.H * out.W * out.pitch, out.W * out.pitch, out.pitch
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.act, a.slope = act, slope
+    a.aux_mode = aux_mode
+    if aux is not None:
+        a.aux = aux.ptr
+        a.an, a.ah, a.aw = aux.H * aux.W * aux.pitch, aux.W * aux.pitch, aux.pitch
+    a.stats = stats.data_ptr() if stats is not None else None
+    L.call("s2r_conv_fwd_mma" if force_mma else "s2r_conv_fwd", C.byref(a), cx.stream)
+    return out
+
+
+def conv_dgrad(cx, dy, w, dx, stride=1, pad=0, dil=1, aux=None, aux_mode=L.AUX_NONE, slope=0.0,
+               force_mma=False):
+    """dx = conv_transpose(dy, w) written per input-parity class; dx is an Act [N,H,W,>=Cin]."""
+    Cout, Cin, R, S = w.shape
+    assert dy.pitch - dy.off >= round_up(Cout, 8) and dx.C >= Cin
+    wp, Cin_pad, Kpad = packed_weight(cx, w, True)
+    H, W = dx.H, dx.W
+    for ph in range(min(stride, H)):
+        for pw in range(min(stride, W)):
+            a = L.ConvArgs()
+            a.struct_size = C.sizeof(L.ConvArgs)
+            n = 0
+            for kh in range(R):
+                if (ph + pad - kh * dil) % stride:
+                    continue
+                for kw in range(S):
+                    if (pw + pad - kw * dil) % stride:
+                        continue
+                    _fill_tap(a.taps[n], dy.ptr, dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch, dy.H, dy.W,
+                              (ph + pad - kh * dil) // stride, (pw + pad - kw * dil) // stride, kh * S + kw, 0)
+                    n += 1
+            OHc, OWc = (H - ph + stride - 1) // stride, (W - pw + stride - 1) // stride
+            if n == 0:
+                raise NotImplementedError("conv_dgrad: parity class without taps")
+            a.ntaps = n
+            a.N, a.OH, a.OW = dx.N, OHc, OWc
+            a.Cin, a.Cout = round_up(Cout, 8), Cin
+            a.w, a.Cout_pad, a.Kpad = wp.data_ptr(), Cin_pad, Kpad
+            a.out = dx.ptr + 2 * (ph * W + pw) * dx.pitch
+            a.on, a.oh, a.ow = H * W * dx.pitch, stride * W * dx.pitch, stride * dx.pitch
+            a.bias = None
+            a.act, a.slope = L.ACT_NONE, slope
+            a.aux_mode = aux_mode
+            if aux is not None:
+                a.aux = aux.ptr + 2 * (ph * W + pw) * aux.pitch
+                a.an, a.ah, a.aw = H * W * aux.pitch, stride * W * aux.pitch, stride * aux.pitch
+            a.stats = None
+            L.call("s2r_conv_fwd_mma" if force_mma else "s2r_conv_fwd", C.byref(a), cx.stream)
+    return dx
+
+
+def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1):
+    """w.grad += conv weight gradient; bias handled by the caller."""
+    Cout, Cin, R, S = w.shape
+    g = grad_of(w)
+    a = L.WgradArgs()
+    a.struct_size = C.sizeof(L.WgradArgs)
+    a.ntaps = fwd_taps(a.taps, x, R, S, stride, pad, dil)
+    a.N, a.OH, a.OW = dy.N, dy.H, dy.W
+    a.Cin, a.Cout = Cin, Cout
+    a.dy = dy.ptr
+    a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
+    a.dweight = g.data_ptr()
+    a.s_co, a.s_ci = Cin * R * S, R * S
+    L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+
+
+def bias_grad(cx, dy, b):
+    """b.grad += per-channel sum of dy."""
+    Cc = round_up(b.numel(), 8)
+    sums = cx.f64(2 * Cc)
+    L.call("s2r_channel_sums_bf16", dy.vp(), dy.P, Cc, dy.pitch, 0, _vp(sums), cx.stream)
+    L.call("s2r_add_f64_to_f32", _vp(sums), _vp(grad_of(b)), b.numel(), cx.stream)
+
+
+# --------------------------------------------------------------------------- batch norm
+class BNState:
+    """Per-forward BN results: scale/shift and mean/invstd ([2][C] fp32 each) + element count."""
+    __slots__ = ("ss", "mi", "count", "frozen")
+
+    def __init__(self, ss, mi, count, frozen):
+        self.ss, self.mi, self.count, self.frozen = ss, mi, count, frozen
+
+
+def bn_finalize(cx, bn, sums, count_local):
+    """Turn (cross-rank reduced) channel sums into scale/shift; updates the running statistics.
+    Mirrors _SynchronizedBatchNorm._compute_mean_std (batchnorm.py:113-125) when synchronised
+    across ranks and F.batch_norm (batchnorm.py:50-53) otherwise."""
+    Cc = bn.num_features
+    ss = cx.f32(2 * Cc, zero=False)
+    mi = cx.f32(2 * Cc, zero=False)
+    sync = cx.world > 1 and getattr(bn, "_s2r_sync", False)
+    if sync:
+        cx.allreduce(sums)
+    count = float(count_local) * (cx.world if sync else 1)
+    if count <= 1:
+        raise ValueError("BatchNorm computes unbiased standard-deviation, which requires size > 1.")
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    L.call("s2r_bn_finalize", _vp(sums), count, _vp(bn.weight), _vp(bn.bias), float(bn.eps), 1 if sync else 0,
+           float(mom), _vp(bn.running_mean), _vp(bn.running_var), _vp(mi), _vp(ss), Cc, cx.stream)
+    return BNState(ss, mi, count, False)
+
+
+def bn_eval(cx, bn):
+    Cc = bn.num_features
+    ss = cx.f32(2 * Cc, zero=False)
+    mi = cx.f32(2 * Cc, zero=False)
+    L.call("s2r_bn_eval_scale_shift", _vp(bn.weight), _vp(bn.bias), _vp(bn.running_mean), _vp(bn.running_var),
+           float(bn.eps), _vp(mi), _vp(ss), Cc, cx.stream)
+    return BNState(ss, mi, 0.0, True)
+
+
+def bn_state(cx, bn, sums, count_local):
+    if cx.training and bn.training:
+        return bn_finalize(cx, bn, sums, count_local)
+    return bn_eval(cx, bn)
+
+
+def bn_apply(cx, z, st, act, out, residual=None, drop_p=0.0, seed=0):
+    L.call("s2r_bn_apply_act", z.vp(), z.P, z.C, z.pitch, 0, _vp(st.ss), act,
+           residual.vp() if residual is not None else None, float(drop_p), seed, out.vp(), out.pitch, 0,
+           cx.stream)
+    return out
+
+
+def bn_backward(cx, bn, dy, z, st, act, dx, drop_p=0.0, seed=0, presummed=None, win=None):
+    """dz of a training-mode BN (+act, +dropout) given dy; accumulates gamma/beta grads.
+    presummed: fp64 [2][C] sums already produced by the kernel that wrote dy (dw dgrad)."""
+    Cc = z.C
+    if presummed is None:
+        sums = cx.f64(2 * Cc)
+        L.call("s2r_bn_bwd_reduce", dy.vp(), dy.pitch, 0, z.vp(), z.pitch, 0, _vp(st.mi), _vp(st.ss), act,
+               float(drop_p), seed, z.P, Cc, _vp(sums), cx.stream)
+    else:
+        sums = presummed
+    sync = cx.world > 1 and getattr(bn, "_s2r_sync", False) and not st.frozen
+    if sync:
+        cx.allreduce(sums)
+    dgamma = _vp(grad_of(bn.weight)) if bn.weight is not None and bn.weight.requires_grad else None
+    dbeta = _vp(grad_of(bn.bias)) if bn.bias is not None and bn.bias.requires_grad else None
+    wH, wW, wpad = win if win is not None else (0, 0, 0)
+    L.call("s2r_bn_bwd_apply", dy.vp(), dy.pitch, 0, z.vp(), z.pitch, 0, _vp(st.mi), _vp(st.ss), act,
+           float(drop_p), seed, _vp(sums), 0.0 if st.frozen else st.count, z.P, Cc,
+           dx.vp() if dx is not None else None, dx.pitch if dx is not None else 0, 0, dgamma, dbeta, wH, wW, wpad,
+           cx.stream)
+    return dx
+
+
+# --------------------------------------------------------------------------- composite layers
+class ConvBNAct:
+    """conv -> BatchNorm -> activation [-> dropout], the BN output materialised in bf16.
+    Used where the consumer is a TMA-fed GEMM (ASPP, decoder, domain classifier, pointwise)."""
+
+    def __init__(self, conv, bn, act, drop_p=0.0):
+        self.conv, self.bn, self.act, self.drop_p = conv, bn, act, drop_p
+        self.stride, self.pad, self.dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+
+    def forward(self, cx, x, out=None, residual=None, count_pad=0):
+        w = self.conv.weight
+        Cout = w.shape[0]
+        OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
+        z = cx.new(x.N, OH, OW, Cout)
+        train = cx.training and self.bn.training
+        sums = cx.f64(2 * Cout) if train else None
+        conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
+        # count_pad: the reference ran this conv on an input padded by count_pad pixels per side
+        # (mobilenet.py:62-67): the extra border outputs are exact zeros but count in the statistics
+        count = x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad)
+        st = bn_state(cx, self.bn, sums, count)
+        p = self.drop_p if (cx.training and cx.dropout) else 0.0
+        seed = cx.next_seed() if p > 0 else 0
+        y = out if out is not None else cx.new(x.N, OH, OW, Cout)
+        bn_apply(cx, z, st, self.act, y, residual, p, seed)
+        self.saved = (x, z, st, p, seed)
+        return y
+
+    def forward_raw(self, cx, x, count_pad=0):
+        """conv + statistics only; returns (z, BNState) for a consumer with a BN prologue."""
+        w = self.conv.weight
+        Cout = w.shape[0]
+        OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
+        z = cx.new(x.N, OH, OW, Cout)
+        train = cx.training and self.bn.training
+        sums = cx.f64(2 * Cout) if train else None
+        conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
+        st = bn_state(cx, self.bn, sums, x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad))
+        self.saved = (x, z, st, 0.0, 0)
+        return z, st
+
+    def backward(self, cx, dy, need_dx=True, dx=None, dx_accumulate=False):
+        """dy: gradient w.r.t. the layer output (Act view, may be a concat slice)."""
+        x, z, st, p, seed = self.saved
+        dz = cx.new(z.N, z.H, z.W, z.C)
+        bn_backward(cx, self.bn, dy, z, st, self.act, dz, p, seed)
+        return self.backward_raw(cx, dz, need_dx, dx, dx_accumulate)
+
+    def backward_raw(self, cx, dz, need_dx=True, dx=None, dx_accumulate=False):
+        x = self.saved[0]
+        w = self.conv.weight
+        self.saved = None
+        if w.requires_grad:
+            conv_wgrad(cx, x, dz, w, self.stride, self.pad, self.dil)
+        if not need_dx:
+            return None
+        if dx is None:
+            dx = cx.new(x.N, x.H, x.W, round_up(w.shape[1], 8))
+            dx_accumulate = False
+        conv_dgrad(cx, dz, w, dx, self.stride, self.pad, self.dil,
+                   aux=dx if dx_accumulate else None, aux_mode=L.AUX_ADD if dx_accumulate else L.AUX_NONE)
+        return dx
+
+
+def dw_fwd(cx, x, st_in, in_act, halo_const, w, stride, dil, pad, stats):
+    Ho, Wo = conv_out_hw(x.H, x.W, 3, 3, stride, pad, dil)
+    y = cx.new(x.N, Ho, Wo, x.C)
+    L.call("s2r_dwconv3x3_fwd", x.vp(), _vp(st_in.ss) if st_in is not None else None, in_act,
+           1 if halo_const else 0, _vp(w), y.vp(), _vp(stats) if stats is not None else None, x.N, x.H, x.W,
+           x.C, stride, dil, pad, cx.stream)
+    return y
+
+
+class InvertedResidual:
+    """One MobileNetV2 block (modeling/backbone/mobilenet.py:26-68) on the fused kernels:
+    expand GEMM (+stats) -> depthwise 3x3 with BN+ReLU6 prologue and halo constant (+stats)
+    -> BN+ReLU6 apply -> project GEMM (+stats) -> BN apply (+residual)."""
+
+    def __init__(self, mod):
+        seq = mod.conv
+        self.mod = mod
+        self.expand = len(seq) == 8
+        if self.expand:
+            self.pw1 = ConvBNAct(seq[0], seq[1], L.ACT_RELU6)
+            self.dw, self.bn2 = seq[3], seq[4]
+            self.pw2 = ConvBNAct(seq[6], seq[7], L.ACT_NONE)
+        else:
+            self.pw1 = None
+            self.dw, self.bn2 = seq[0], seq[1]
+            self.pw2 = ConvBNAct(seq[3], seq[4], L.ACT_NONE)
+        self.stride = self.dw.stride[0]
+        self.dil = self.dw.dilation[0]
+        self.res = mod.use_res_connect
+
+    def forward(self, cx, x, lazy=None):
+        """x: block input (Act).  lazy = BNState of a producer whose BN+ReLU6 has not been applied
+        to x yet (the stem feeding the expand_ratio==1 block): applied in the dw prologue."""
+        d = self.dil
+        if self.expand:
+            z1, st1 = self.pw1.forward_raw(cx, x, count_pad=d)
+            dw_in, st_in, halo = z1, st1, True
+        else:
+            dw_in, st_in, halo = x, lazy, False
+        train = cx.training and self.bn2.training
+        sums2 = cx.f64(2 * dw_in.C) if train else None
+        z2 = dw_fwd(cx, dw_in, st_in, L.ACT_RELU6, halo, self.dw.weight, self.stride, d, d, sums2)
+        st2 = bn_state(cx, self.bn2, sums2, z2.P)
+        y2 = cx.new(z2.N, z2.H, z2.W, z2.C)
+        bn_apply(cx, z2, st2, L.ACT_RELU6, y2)
+        out = self.pw2.forward(cx, y2, residual=x if self.res else None)
+        self.saved = (x, dw_in, st_in, halo, z2, st2)
+        return out
+
+    def backward(self, cx, dout, need_dx=True):
+        """Returns (dx, bwd_sums_for_lazy_producer).  For the expand_ratio==1 block dx is the
+        act'-masked gradient w.r.t. the producer's BN output and the sums feed its BN backward."""
+        x, dw_in, st_in, halo, z2, st2 = self.saved
+        self.saved = None
+        d = self.dil
+        dy2 = self.pw2.backward(cx, dout)                      # BN3 bwd, wgrad, dgrad -> [N,Ho,Wo,Ch]
+        dz2 = cx.new(z2.N, z2.H, z2.W, z2.C)
+        bn_backward(cx, self.bn2, dy2, z2, st2, L.ACT_RELU6, dz2)
+        if self.dw.weight.requires_grad:
+            L.call("s2r_dwconv3x3_wgrad", dw_in.vp(), _vp(st_in.ss) if st_in is not None else None,
+                   L.ACT_RELU6, 1 if halo else 0, dz2.vp(), _vp(grad_of(self.dw.weight)), dw_in.N, dw_in.H,
+                   dw_in.W, dw_in.C, self.stride, d, d, cx.stream)
+        ext = d if halo else 0
+        g = cx.new(dw_in.N, dw_in.H + 2 * ext, dw_in.W + 2 * ext, dw_in.C)
+        masked = st_in is not None
+        bsums = cx.f64(2 * dw_in.C) if (masked and not st_in.frozen) else None
+        L.call("s2r_dwconv3x3_dgrad", dz2.vp(), _vp(self.dw.weight), dw_in.vp() if masked else None,
+               _vp(st_in.ss) if masked else None, _vp(st_in.mi) if masked else None, L.ACT_RELU6, ext, g.vp(),
+               _vp(bsums) if bsums is not None else None, dw_in.N, dw_in.H, dw_in.W, dw_in.C, self.stride, d, d,
+               cx.stream)
+        if not self.expand:
+            return g, bsums
+        # BN1 backward on the padded domain, interior written as dz1
+        if st_in.frozen:
+            bsums = cx.f64(2 * dw_in.C)
+        dz1 = cx.new(dw_in.N, dw_in.H, dw_in.W, dw_in.C)
+        bn_backward(cx, self.pw1.bn, g, dw_in, st_in, L.ACT_NONE, dz1, presummed=bsums,
+                    win=(dw_in.H, dw_in.W, ext) if ext > 0 else None)
+        if self.res:
+            dx = self.pw1.backward_raw(cx, dz1, True, dx=dout, dx_accumulate=True)
+        else:
+            dx = self.pw1.backward_raw(cx, dz1, need_dx)
+        return dx, None

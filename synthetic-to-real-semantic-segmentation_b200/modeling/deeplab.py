@@ -1,0 +1,90 @@
+"""DeepLabV3+ with the reference's constructor, attributes, parameter-group generators and
+state_dict keys (modeling/deeplab.py:9-72).
+
+forward(input[N,3,H,W] fp32) -> [N,num_classes,H,W] fp32.  Backbone, ASPP and decoder run
+back-to-back on NHWC bf16 activations (no NCHW round trips between them); the final x4 bilinear
+up-sampling (deeplab.py:31) writes the NCHW fp32 logits the callers expect.
+"""
+import torch.nn as nn
+
+from .. import _lib as L
+from ..engine import _vp, round_up
+from ..runtime import RunBase, call_module
+from .sync_batchnorm import SynchronizedBatchNorm2d
+from .assp import build_aspp, ASPPRun
+from .decoder import build_decoder, DecoderRun
+from .backbone import build_backbone
+from .backbone.mobilenet import MobileNetV2Run
+
+import torch
+
+
+class DeepLabRun(RunBase):
+    def __init__(self, mod):
+        self.backbone = MobileNetV2Run(mod.backbone)
+        self.aspp = ASPPRun(mod.aspp)
+        self.decoder = DecoderRun(mod.decoder)
+
+    def forward(self, cx, x):
+        self.in_hw = (x.H, x.W)
+        high, low = self.backbone.forward(cx, x)
+        return self.decoder.forward(cx, self.aspp.forward(cx, high), low)
+
+    def export(self, cx, i, a):
+        # F.interpolate(x, size=input.size()[2:], mode='bilinear', align_corners=True) fused with
+        # the NHWC bf16 -> NCHW fp32 boundary conversion
+        H, W = self.in_hw
+        self.small = (a.N, a.H, a.W, a.C, a.pitch)
+        y = torch.empty((a.N, a.C, H, W), dtype=torch.float32, device=cx.device)
+        L.call("s2r_upsample_bilinear_nhwc_to_nchw", a.vp(), a.pitch, a.N, a.H, a.W, a.C, _vp(y), H, W, cx.stream)
+        return y
+
+    def import_grad(self, cx, i, d):
+        if d is None:
+            return None
+        N, h, w, Cc, pitch = self.small
+        d = d.contiguous()
+        g = cx.new(N, h, w, pitch)
+        g.C = Cc
+        L.call("s2r_upsample_bilinear_nchw_bwd_to_nhwc", _vp(d), N, Cc, d.shape[2], d.shape[3], g.vp(), pitch, h, w,
+               cx.stream)
+        return g
+
+    def backward(self, cx, douts, need=None):
+        dx, dlow = self.decoder.backward(cx, douts)
+        dhigh = self.aspp.backward(cx, dx)
+        self.backbone.backward(cx, (dhigh, dlow))
+        return None
+
+
+class DeepLab(nn.Module):
+    def __init__(self, backbone='resnet', output_stride=16, num_classes=19, sync_bn=True, freeze_bn=False):
+        super().__init__()
+        if backbone == 'drn':
+            output_stride = 8
+        BatchNorm = SynchronizedBatchNorm2d if sync_bn == True else nn.BatchNorm2d  # noqa: E712
+        self.backbone = build_backbone(backbone, output_stride, BatchNorm)
+        self.aspp = build_aspp(backbone, output_stride, BatchNorm)
+        self.decoder = build_decoder(num_classes, backbone, BatchNorm)
+        self.freeze_bn = freeze_bn
+        self._s2r_has_sync_bn = bool(sync_bn)
+
+    def forward(self, input):
+        return call_module(self, lambda: DeepLabRun(self), (input,))
+
+    def _lr_params(self, modules):
+        # deeplab.py:42-72: Conv2d (+ BatchNorm unless freeze_bn) parameters of the given sub-modules
+        for root in modules:
+            for _, m in root.named_modules():
+                wanted = isinstance(m, nn.Conv2d) or \
+                    (not self.freeze_bn and isinstance(m, nn.modules.batchnorm._BatchNorm))
+                if wanted:
+                    for p in m.parameters():
+                        if p.requires_grad:
+                            yield p
+
+    def get_1x_lr_params(self):
+        return self._lr_params([self.backbone])
+
+    def get_10x_lr_params(self):
+        return self._lr_params([self.aspp, self.decoder])

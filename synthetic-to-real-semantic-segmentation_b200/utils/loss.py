@@ -1,0 +1,60 @@
+"""Losses with the reference's class and method names (utils/loss.py:5-69)."""
+import torch
+
+from ..functional import cross_entropy, bce_with_logits
+
+
+class SegmentationLosses(object):
+    def __init__(self, weight=None, batch_average=True, ignore_index=255, cuda=False):
+        self.ignore_index = ignore_index
+        self.weight = weight
+        self.batch_average = batch_average
+        self.cuda = cuda
+
+    def build_loss(self, mode='ce'):
+        """Choices: ['ce' or 'focal']"""
+        if mode == 'ce':
+            return self.CrossEntropyLoss
+        elif mode == 'focal':
+            return self.FocalLoss
+        else:
+            raise NotImplementedError
+
+    def CrossEntropyLoss(self, logit, target):
+        # loss.py:21-30: nn.CrossEntropyLoss(weight, ignore_index, reduction='mean')(logit, target.long())
+        return cross_entropy(logit, target, weight=self.weight, ignore_index=self.ignore_index)
+
+    def FocalLoss(self, logit, target, gamma=2, alpha=0.5):
+        # loss.py:32-46: a scalar transform of the MEAN cross entropy
+        logpt = -cross_entropy(logit, target, weight=self.weight, ignore_index=self.ignore_index)
+        pt = torch.exp(logpt)
+        if alpha is not None:
+            logpt = logpt * alpha
+        return -((1 - pt) ** gamma) * logpt
+
+
+class DomainLosses(object):
+    def __init__(self, batch_average=True, cuda=False):
+        self.batch_average = batch_average
+        self.cuda = cuda
+
+    def build_loss(self):
+        return self.DomainClassiferLoss
+
+    def DomainClassiferLoss(self, src_logit, tgt_logit):
+        # loss.py:57-69: CE(src, 0) + CE(tgt, 1) and the domain accuracy as a python float
+        assert src_logit.size() == tgt_logit.size()
+        n, c, h, w = src_logit.size()
+        stats = []
+        loss = cross_entropy(src_logit, None, const_target=0, ignore_index=-100, stats_out=stats) + \
+            cross_entropy(tgt_logit, None, const_target=1, ignore_index=-100, stats_out=stats)
+        hits = stats[0][2] + stats[1][2]
+        acc = (hits / 2 / n / h / w).float()
+        return loss, acc.item()
+
+
+class BCEWithLogitsLoss(object):
+    """torch.nn.BCEWithLogitsLoss() as instantiated at train_adapt.py:75."""
+
+    def __call__(self, input, target):
+        return bce_with_logits(input, target)

@@ -1,0 +1,101 @@
+"""Evaluator with the reference's interface (utils/metrics.py:4-46); the confusion matrix is
+accumulated on the device by the fused histogram kernels and read back only when a metric is asked
+for.  Counts are exact integers (the reference accumulates them in float64)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..engine import _vp
+
+
+class Evaluator(object):
+    def __init__(self, num_class, device=None):
+        self.num_class = num_class
+        self.device = torch.device(device) if device is not None else None
+        self._counts = None
+        self._bad = None
+
+    def _ensure(self, device):
+        if self._counts is None:
+            L.require_cuda()
+            self.device = device if device is not None else (self.device or torch.device("cuda", torch.cuda.current_device()))
+            self._counts = torch.zeros((self.num_class, self.num_class), dtype=torch.int64, device=self.device)
+            self._bad = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    @property
+    def confusion_matrix(self):
+        if self._counts is None:
+            return np.zeros((self.num_class,) * 2)
+        if int(self._bad.item()) != 0:
+            raise ValueError("prediction outside [0, num_class) for a valid label")
+        return self._counts.cpu().numpy().astype(np.float64)
+
+    @confusion_matrix.setter
+    def confusion_matrix(self, value):
+        self._ensure(None)
+        self._counts.copy_(torch.as_tensor(np.asarray(value)).to(torch.int64))
+
+    def Pixel_Accuracy(self):
+        cm = self.confusion_matrix
+        return np.diag(cm).sum() / cm.sum()
+
+    def Pixel_Accuracy_Class(self):
+        cm = self.confusion_matrix
+        Acc = np.diag(cm) / cm.sum(axis=1)
+        return np.nanmean(Acc)
+
+    def Mean_Intersection_over_Union(self):
+        cm = self.confusion_matrix
+        IoU = np.diag(cm) / (np.sum(cm, axis=1) + np.sum(cm, axis=0) - np.diag(cm))
+        return np.nanmean(IoU), IoU
+
+    def Frequency_Weighted_Intersection_over_Union(self):
+        cm = self.confusion_matrix
+        freq = np.sum(cm, axis=1) / np.sum(cm)
+        iu = np.diag(cm) / (np.sum(cm, axis=1) + np.sum(cm, axis=0) - np.diag(cm))
+        return (freq[freq > 0] * iu[freq > 0]).sum()
+
+    def _as_cuda(self, a, want_int):
+        if isinstance(a, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        else:
+            t = a
+        self._ensure(t.device if t.device.type == "cuda" else None)
+        t = t.to(self.device, non_blocking=True)
+        if want_int:
+            t = t.to(torch.int64)
+        elif t.dtype not in (torch.float32, torch.int64):
+            t = t.to(torch.int64) if not t.dtype.is_floating_point else t.float()
+        return t.contiguous()
+
+    def add_batch(self, gt_image, pre_image):
+        """gt_image: labels (any numeric dtype, numpy or torch); pre_image: integer predictions."""
+        assert gt_image.shape == pre_image.shape
+        gt = self._as_cuda(gt_image, False)
+        pred = self._as_cuda(pre_image, True)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            L.call("s2r_confusion_matrix", _vp(gt), 1 if gt.dtype == torch.int64 else 0, _vp(pred), gt.numel(),
+                   self.num_class, _vp(self._counts), _vp(self._bad), st)
+
+    def add_batch_logits(self, gt_image, logits):
+        """Fused argmax over the class axis of NCHW fp32 logits + histogram (replaces the logits
+        D2H copy and np.argmax at val_adapt.py:131-135).  Returns nothing; counts stay on device."""
+        gt = self._as_cuda(gt_image, False)
+        if gt.dtype != torch.float32:
+            gt = gt.float()
+        logits = logits.contiguous().float()
+        N, Cc = logits.shape[0], logits.shape[1]
+        HW = logits.numel() // (N * Cc)
+        assert gt.numel() == N * HW
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            L.call("s2r_argmax_confusion_nchw", _vp(logits), _vp(gt), N, Cc, HW, self.num_class,
+                   _vp(self._counts), None, st)
+
+    def reset(self):
+        if self._counts is not None:
+            self._counts.zero_()
+            self._bad.zero_()

@@ -1,0 +1,291 @@
+"""Generates tests/golden/*.npz from the REAL reference (/root/reference, build container only)
+and checks oracle/ref_port.py against it.  Run:  python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs on fixed seeds are committed here as
+small fixtures; tests/test_oracle.py re-checks the oracle against them everywhere.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("S2R_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+
+from modeling.backbone import mobilenet as ref_mobilenet  # noqa: E402
+ref_mobilenet.MobileNetV2._load_pretrained_model = lambda self: None  # the checkpoint blob is not in the tree
+from modeling.deeplab import DeepLab as RefDeepLab  # noqa: E402
+from modeling.discriminator import FCDiscriminator as RefD  # noqa: E402
+from modeling.domian import DomainClassifer as RefDC  # noqa: E402
+from modeling.assp import ASPP as RefASPP  # noqa: E402
+from modeling.decoder import Decoder as RefDecoder  # noqa: E402
+from utils.loss import SegmentationLosses as RefSegLoss, DomainLosses as RefDomLoss  # noqa: E402
+from utils.metrics import Evaluator as RefEvaluator  # noqa: E402
+
+from oracle import ref_port as O  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def no_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def clone_sd(model, grad=True):
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    if grad:
+        for k, v in O.leaf_params(sd).items():
+            v.requires_grad_(True)
+    return sd
+
+
+def checksums(model):
+    names, vals = [], []
+    for k, v in model.state_dict().items():
+        if v.dtype.is_floating_point:
+            names.append(k)
+            vals.append([float(v.double().sum()), float(v.double().abs().sum())])
+    return np.array(names), np.array(vals, dtype=np.float64)
+
+
+def head(t, n=4096):
+    """First n elements of a tensor (fixtures stay small; norms of the full tensors are stored too)."""
+    return t.detach().reshape(-1)[:n].numpy().copy()
+
+
+def relerr(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def make_inputs(seed, n, h, w, ncls=19):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    lab = torch.randint(0, ncls + 1, (n, h, w), generator=g).float()
+    lab[lab == ncls] = 255
+    return x, lab
+
+
+def deeplab_case(tag, n, h, w, train):
+    torch.manual_seed(1)
+    ref = no_dropout(RefDeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False))
+    ref.train(train)
+    names, sums = checksums(ref)
+    sd = clone_sd(ref)
+    x, lab = make_inputs(0, n, h, w)
+    crit = RefSegLoss().build_loss('ce')
+    out = ref(x)
+    loss = crit(out, lab)
+    fix = dict(x=x.numpy(), label=lab.numpy(), logits=out.detach().numpy(), loss=np.float64(loss.item()),
+               param_names=names, param_sums=sums)
+    cfg = O.BNCfg(training=train)
+    o_out = O.deeplab_forward(sd, x, cfg, 16, drop=False)
+    o_loss = O.seg_cross_entropy(o_out, lab)
+    print(tag, 'logits rel err oracle vs reference', relerr(o_out.detach(), out.detach()), 'loss', loss.item(), o_loss.item())
+    assert relerr(o_out.detach(), out.detach()) < 1e-5
+    if train:
+        loss.backward()
+        o_loss.backward()
+        picks = ['backbone.features.0.0.weight', 'backbone.features.1.conv.0.weight', 'backbone.features.2.conv.0.weight',
+                 'backbone.features.2.conv.1.weight', 'backbone.features.2.conv.1.bias',
+                 'backbone.features.2.conv.3.weight', 'backbone.features.7.conv.3.weight',
+                 'backbone.features.17.conv.6.weight', 'aspp.aspp1.atrous_conv.weight', 'aspp.aspp3.atrous_conv.weight',
+                 'aspp.global_avg_pool.1.weight', 'aspp.conv1.weight', 'aspp.bn1.weight', 'decoder.conv1.weight',
+                 'decoder.last_conv.0.weight', 'decoder.last_conv.4.weight', 'decoder.last_conv.8.weight',
+                 'decoder.last_conv.8.bias']
+        refp = dict(ref.named_parameters())
+        worst = 0.0
+        norms = {}
+        for k, p in refp.items():
+            e = relerr(sd[k].grad, p.grad)
+            worst = max(worst, e)
+            norms[k] = float(p.grad.double().norm())
+        print(tag, 'worst param-grad rel err oracle vs reference', worst)
+        assert worst < 2e-3, worst
+        for k in picks:
+            fix['grad:' + k] = head(refp[k].grad)
+        fix['grad_norm_names'] = np.array(list(norms.keys()))
+        fix['grad_norms'] = np.array(list(norms.values()), dtype=np.float64)
+        # running statistics after one training forward
+        for k in ['backbone.features.0.1.running_mean', 'backbone.features.0.1.running_var',
+                  'backbone.features.2.conv.1.running_mean', 'backbone.features.2.conv.1.running_var',
+                  'aspp.global_avg_pool.2.running_var', 'decoder.last_conv.5.running_var']:
+            fix['buf:' + k] = ref.state_dict()[k].numpy()
+            assert relerr(sd[k], ref.state_dict()[k]) < 1e-5, k
+    np.savez_compressed(os.path.join(HERE, tag + '.npz'), **fix)
+
+
+def discriminator_case():
+    torch.manual_seed(2)
+    ref = RefD(num_classes=19)
+    names, sums = checksums(ref)
+    sd = clone_sd(ref)
+    g = torch.Generator().manual_seed(3)
+    x = torch.softmax(torch.randn(2, 19, 64, 96, generator=g), dim=0).requires_grad_(True)
+    out = ref(x)
+    loss = torch.nn.BCEWithLogitsLoss()(out, torch.zeros_like(out))
+    loss.backward()
+    xo = x.detach().clone().requires_grad_(True)
+    o_out = O.discriminator_forward(sd, xo)
+    o_loss = torch.nn.functional.binary_cross_entropy_with_logits(o_out, torch.zeros_like(o_out))
+    o_loss.backward()
+    assert relerr(o_out.detach(), out.detach()) < 1e-6
+    assert relerr(xo.grad, x.grad) < 1e-5
+    fix = dict(x=x.detach().numpy(), out=out.detach().numpy(), loss=np.float64(loss.item()), dx=x.grad.numpy(),
+               param_names=names, param_sums=sums)
+    for k, p in ref.named_parameters():
+        assert relerr(sd[k].grad, p.grad) < 1e-4, k
+        if k in ('conv1.weight', 'conv1.bias', 'conv3.weight', 'classifier.weight', 'classifier.bias'):
+            fix['grad:' + k] = head(p.grad)
+            fix['gradnorm:' + k] = np.float64(p.grad.double().norm())
+    np.savez_compressed(os.path.join(HERE, 'discriminator.npz'), **fix)
+    print('discriminator ok')
+
+
+def domain_case():
+    torch.manual_seed(4)
+    ref = no_dropout(RefDC('mobilenet', torch.nn.BatchNorm2d))
+    ref.train()
+    names, sums = checksums(ref)
+    sd = clone_sd(ref)
+    g = torch.Generator().manual_seed(5)
+    xs = torch.randn(2, 256, 9, 12, generator=g)
+    xt = torch.randn(2, 256, 9, 12, generator=g)
+    crit = RefDomLoss().build_loss()
+    cfg = O.BNCfg(True)
+    ps, pt = ref(xs), ref(xt)
+    loss, acc = crit(ps, pt)
+    loss.backward()
+    os_, ot_ = O.domain_classifier_forward(sd, xs, cfg, False), O.domain_classifier_forward(sd, xt, cfg, False)
+    ol, oacc = O.domain_loss(os_, ot_)
+    ol.backward()
+    assert relerr(os_.detach(), ps.detach()) < 1e-5 and abs(oacc - acc) < 1e-7
+    refp = dict(ref.named_parameters())
+    for k, p in refp.items():
+        assert relerr(sd[k].grad, p.grad) < 1e-3, (k, relerr(sd[k].grad, p.grad))
+    fix = dict(xs=xs.numpy(), xt=xt.numpy(), ps=ps.detach().numpy(), pt=pt.detach().numpy(),
+               loss=np.float64(loss.item()), acc=np.float64(acc), param_names=names, param_sums=sums)
+    for k in ('DC_adnn3.weight', 'DC_adnn1.0.weight', 'DC_adnn2.0.weight', 'DC_adnn2.1.weight'):
+        fix['grad:' + k] = head(refp[k].grad)
+        fix['gradnorm:' + k] = np.float64(refp[k].grad.double().norm())
+    np.savez_compressed(os.path.join(HERE, 'domain_classifier.npz'), **fix)
+    # the analytic known answer of utils/loss.py:80-87
+    a, b = torch.ones(1, 1, 7, 7), torch.zeros(1, 1, 7, 7)
+    l, ac = crit(torch.cat([a, b], 1), torch.cat([b, a], 1))
+    assert abs(l.item() - 0.626523) < 1e-5 and ac == 1.0
+    print('domain classifier ok', l.item(), ac)
+
+
+def evaluator_case():
+    rng = np.random.RandomState(7)
+    gt = rng.randint(0, 20, size=(2, 37, 53)).astype(np.float32)
+    gt[gt == 19] = 255
+    pred = rng.randint(0, 19, size=(2, 37, 53)).astype(np.int64)
+    ev = RefEvaluator(19)
+    ev.add_batch(gt, pred)
+    ev.add_batch(gt[:, ::-1].copy(), pred)
+    cm = ev.confusion_matrix
+    miou, iou = ev.Mean_Intersection_over_Union()
+    fix = dict(gt=gt, pred=pred, cm=cm, PA=ev.Pixel_Accuracy(), mPA=ev.Pixel_Accuracy_Class(), mIoU=miou, IoU=iou,
+               fwIoU=ev.Frequency_Weighted_Intersection_over_Union())
+    ocm = O.confusion_matrix(gt, pred, 19) + O.confusion_matrix(gt[:, ::-1].copy(), pred, 19)
+    assert (ocm == cm).all()
+    m = O.evaluator_metrics(ocm)
+    assert m['mIoU'] == miou and m['fwIoU'] == fix['fwIoU']
+    np.savez_compressed(os.path.join(HERE, 'evaluator.npz'), **fix)
+    print('evaluator ok', miou)
+
+
+def adapt_step_case():
+    """Two iterations of train_adapt.py:137-181 on the reference modules (device-agnostic restatement
+    of the script body, which hard-codes .cuda()) vs the oracle's adapt_step."""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    G = no_dropout(RefDeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False))
+    D = RefD(num_classes=19)
+    G.train()
+    D.train()
+    g_sd, d_sd = clone_sd(G), clone_sd(D)
+    lr = 5e-4
+    opt = torch.optim.SGD([{'params': G.get_1x_lr_params(), 'lr': lr}, {'params': G.get_10x_lr_params(), 'lr': lr * 10}],
+                          momentum=0.9, weight_decay=5e-4, nesterov=False)
+    opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    one, ten = O.split_lr_groups(list(O.leaf_params(g_sd).keys()))
+    o_opt = torch.optim.SGD([{'params': [g_sd[k] for k in one], 'lr': lr}, {'params': [g_sd[k] for k in ten], 'lr': lr * 10}],
+                            momentum=0.9, weight_decay=5e-4, nesterov=False)
+    o_opt_d = torch.optim.Adam(list(O.leaf_params(d_sd).values()), lr=1e-4, betas=(0.9, 0.99))
+    crit = RefSegLoss().build_loss('ce')
+    bce = torch.nn.BCEWithLogitsLoss()
+    cfg = O.BNCfg(True)
+    hist = []
+    for it in range(2):
+        src, lab = make_inputs(100 + it, 2, 65, 97)
+        tgt, _ = make_inputs(200 + it, 2, 65, 97)
+        for o in (opt, opt_d, o_opt, o_opt_d):
+            for gi, grp in enumerate(o.param_groups):
+                grp['lr'] = O.poly_lr(lr, it, 10) * (10 if gi > 0 else 1)   # lr_scheduler.py:63-70
+        opt.zero_grad()
+        opt_d.zero_grad()
+        for p in D.parameters():
+            p.requires_grad = False
+        so = G(src)
+        ls = crit(so, lab)
+        ls.backward()
+        to = G(tgt)
+        la = bce(D(F.softmax(to, dim=0)), torch.zeros(2, 1, 2, 3))
+        la.backward()
+        for p in D.parameters():
+            p.requires_grad = True
+        l1 = bce(D(F.softmax(so.detach(), dim=0)), torch.zeros(2, 1, 2, 3))
+        l1.backward()
+        l2 = bce(D(F.softmax(to.detach(), dim=0)), torch.ones(2, 1, 2, 3))
+        l2.backward()
+        opt.step()
+        opt_d.step()
+        ref_losses = (ls.item(), la.item(), l1.item(), l2.item())
+        o_losses = O.adapt_step(g_sd, d_sd, o_opt, o_opt_d, src, lab, tgt, cfg, drop=False)
+        print('adapt it', it, ref_losses, o_losses)
+        assert np.allclose(ref_losses, o_losses, rtol=2e-4, atol=1e-6)
+        hist.append(ref_losses)
+    fix = dict(losses=np.array(hist, dtype=np.float64))
+    for k in ['backbone.features.0.0.weight', 'decoder.last_conv.8.weight', 'aspp.conv1.weight']:
+        w = dict(G.named_parameters())[k].detach()
+        assert relerr(g_sd[k].detach(), w) < 1e-4, k
+        fix['w:' + k] = head(w)
+        fix['wnorm:' + k] = np.float64(w.double().norm())
+    fix['wd:conv1.weight'] = head(D.conv1.weight)
+    fix['wdnorm:conv1.weight'] = np.float64(D.conv1.weight.detach().double().norm())
+    assert relerr(d_sd['conv1.weight'].detach(), D.conv1.weight.detach()) < 1e-4
+    np.savez_compressed(os.path.join(HERE, 'adapt_step.npz'), **fix)
+
+
+def shapes_case():
+    """The output shapes of the reference's __main__ smoke blocks."""
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = ref_mobilenet.MobileNetV2(output_stride=16, BatchNorm=torch.nn.BatchNorm2d)
+        hi, lo = m(torch.rand(1, 3, 512, 512))
+        assert tuple(hi.shape) == (1, 320, 32, 32) and tuple(lo.shape) == (1, 24, 128, 128)
+        a = RefASPP('mobilenet', 16, torch.nn.BatchNorm2d).eval()
+        assert tuple(a(torch.rand(2, 320, 32, 32)).shape) == (2, 256, 32, 32)
+        d = RefDecoder(19, 'mobilenet', torch.nn.BatchNorm2d).eval()
+        assert tuple(d(torch.rand(1, 256, 32, 32), torch.rand(1, 24, 128, 128)).shape) == (1, 19, 128, 128)
+        assert tuple(RefD(19)(torch.rand(1, 19, 512, 512)).shape) == (1, 1, 16, 16)
+    print('shapes ok')
+
+
+if __name__ == '__main__':
+    shapes_case()
+    evaluator_case()
+    discriminator_case()
+    domain_case()
+    deeplab_case('deeplab_train_2x65x97', 2, 65, 97, True)
+    deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
+    adapt_step_case()
+    print('all golden fixtures written to', HERE)

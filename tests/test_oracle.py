@@ -1,0 +1,187 @@
+"""The CPU oracle (oracle/ref_port.py, oracle/confusion_matrix.c) against the fixtures that
+tests/golden/make_golden.py generated from the real reference.  CPU only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from conftest import ROOT, golden, sub
+from oracle import ref_port as O
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def seeded_state(kind):
+    """Reference-initialised weights come from OUR module constructors under the same seed; that
+    they coincide with the reference's is itself checked against the stored checksums."""
+    if kind == 'deeplab':
+        torch.manual_seed(1)
+        m = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    elif kind == 'disc':
+        torch.manual_seed(2)
+        m = sub("modeling.discriminator").FCDiscriminator(num_classes=19)
+    else:
+        torch.manual_seed(4)
+        m = sub("modeling.domian").DomainClassifer('mobilenet', torch.nn.BatchNorm2d)
+    return m
+
+
+def check_sums(m, fix):
+    sd = m.state_dict()
+    names = [str(n) for n in fix['param_names']]
+    assert names == [k for k, v in sd.items() if v.dtype.is_floating_point]
+    for n, (s, a) in zip(names, fix['param_sums']):
+        v = sd[n].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(1.0, abs(a)), n
+        assert abs(float(v.abs().sum()) - a) <= 1e-9 * max(1.0, abs(a)), n
+
+
+def grad_sd(m):
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for v in O.leaf_params(sd).values():
+        v.requires_grad_(True)
+    return sd
+
+
+def test_module_init_matches_reference_checksums():
+    check_sums(seeded_state('deeplab'), golden('deeplab_train_2x65x97'))
+    check_sums(seeded_state('disc'), golden('discriminator'))
+    check_sums(seeded_state('dc'), golden('domain_classifier'))
+
+
+def test_state_dict_layout():
+    m = seeded_state('deeplab')
+    sd = m.state_dict()
+    assert len(sd) == 668          # 668 entries for DeepLab
+    for k in ('backbone.features.0.0.weight', 'backbone.features.1.conv.0.weight', 'aspp.aspp4.atrous_conv.weight',
+              'aspp.global_avg_pool.1.weight', 'decoder.last_conv.8.bias', 'backbone.features.17.conv.7.running_var'):
+        assert k in sd
+    assert sum(p.numel() for p in m.parameters()) == 5815539
+    one = sum(p.numel() for p in m.get_1x_lr_params())
+    ten = sum(p.numel() for p in m.get_10x_lr_params())
+    assert one + ten == 5815539 and one == sum(p.numel() for p in m.backbone.parameters())
+    d = seeded_state('disc')
+    assert sum(p.numel() for p in d.parameters()) == 2781121
+    dc = seeded_state('dc')
+    assert sum(p.numel() for p in dc.parameters()) == 9721858
+
+
+def test_deeplab_train_forward_backward():
+    fix = golden('deeplab_train_2x65x97')
+    sd = grad_sd(seeded_state('deeplab'))
+    x, lab = torch.from_numpy(fix['x']), torch.from_numpy(fix['label'])
+    out = O.deeplab_forward(sd, x, O.BNCfg(True), 16, drop=False)
+    assert rel(out.detach(), fix['logits']) < 1e-5
+    loss = O.seg_cross_entropy(out, lab)
+    assert abs(loss.item() - float(fix['loss'])) < 1e-5
+    loss.backward()
+    for k in fix.files:
+        if k.startswith('grad:'):
+            g = sd[k[5:]].grad.reshape(-1)[:4096]
+            assert rel(g, fix[k]) < 2e-3, k
+        if k.startswith('buf:'):
+            assert rel(sd[k[4:]], fix[k]) < 1e-5, k
+    norms = dict(zip([str(n) for n in fix['grad_norm_names']], fix['grad_norms']))
+    for k, v in O.leaf_params(sd).items():
+        assert abs(float(v.grad.double().norm()) - norms[k]) <= 2e-3 * norms[k] + 1e-9, k
+
+
+def test_deeplab_eval_forward():
+    fix = golden('deeplab_eval_1x97x65')
+    sd = grad_sd(seeded_state('deeplab'))
+    out = O.deeplab_forward(sd, torch.from_numpy(fix['x']), O.BNCfg(False), 16)
+    assert rel(out.detach(), fix['logits']) < 1e-5
+
+
+def test_discriminator():
+    fix = golden('discriminator')
+    sd = grad_sd(seeded_state('disc'))
+    x = torch.from_numpy(fix['x']).requires_grad_(True)
+    out = O.discriminator_forward(sd, x)
+    assert rel(out.detach(), fix['out']) < 1e-6
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, torch.zeros_like(out))
+    assert abs(loss.item() - float(fix['loss'])) < 1e-6
+    loss.backward()
+    assert rel(x.grad, fix['dx']) < 1e-5
+    for k in fix.files:
+        if k.startswith('grad:'):
+            assert rel(sd[k[5:]].grad.reshape(-1)[:4096], fix[k]) < 1e-4, k
+
+
+def test_domain_classifier_and_loss_known_answer():
+    fix = golden('domain_classifier')
+    sd = grad_sd(seeded_state('dc'))
+    cfg = O.BNCfg(True)
+    ps = O.domain_classifier_forward(sd, torch.from_numpy(fix['xs']), cfg, False)
+    pt = O.domain_classifier_forward(sd, torch.from_numpy(fix['xt']), cfg, False)
+    assert rel(ps.detach(), fix['ps']) < 1e-5 and rel(pt.detach(), fix['pt']) < 1e-5
+    loss, acc = O.domain_loss(ps, pt)
+    assert abs(loss.item() - float(fix['loss'])) < 1e-5 and abs(acc - float(fix['acc'])) < 1e-7
+    # utils/loss.py:80-87: loss = 2 ln(1 + e^-1), accuracy 1
+    a, b = torch.ones(1, 1, 7, 7), torch.zeros(1, 1, 7, 7)
+    l, ac = O.domain_loss(torch.cat([a, b], 1), torch.cat([b, a], 1))
+    assert abs(l.item() - 0.626523) < 1e-5 and ac == 1.0
+
+
+def test_evaluator_numpy_and_c():
+    fix = golden('evaluator')
+    gt, pred = fix['gt'], fix['pred']
+    cm = O.confusion_matrix(gt, pred, 19) + O.confusion_matrix(gt[:, ::-1].copy(), pred, 19)
+    assert (cm == fix['cm']).all()
+    m = O.evaluator_metrics(cm)
+    assert m['mIoU'] == float(fix['mIoU']) and m['PA'] == float(fix['PA'])
+    assert m['mPA'] == float(fix['mPA']) and m['fwIoU'] == float(fix['fwIoU'])
+    assert np.array_equal(m['IoU'], fix['IoU'])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "liboracle_cm.so"))
+    lib.oracle_confusion_matrix_f32.restype = ctypes.c_int64
+    counts = np.zeros((19, 19), dtype=np.int64)
+    for g in (gt, gt[:, ::-1].copy()):
+        g = np.ascontiguousarray(g)
+        bad = lib.oracle_confusion_matrix_f32(g.ctypes.data_as(ctypes.c_void_p), pred.ctypes.data_as(ctypes.c_void_p),
+                                              ctypes.c_int64(g.size), 19, counts.ctypes.data_as(ctypes.c_void_p))
+        assert bad == 0
+    assert (counts == fix['cm']).all()
+    # empty and all-ignored inputs
+    assert O.confusion_matrix(np.zeros((0,), np.float32), np.zeros((0,), np.int64), 19).sum() == 0
+    assert O.confusion_matrix(np.full((5,), 255, np.float32), np.zeros((5,), np.int64), 19).sum() == 0
+
+
+def test_adapt_step_two_iterations():
+    fix = golden('adapt_step')
+    import importlib
+    mk = importlib.import_module("tests.golden.make_golden") if False else None  # inputs are re-derived below
+    torch.manual_seed(1)
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    D = sub("modeling.discriminator").FCDiscriminator(num_classes=19)
+    g_sd, d_sd = grad_sd(G), grad_sd(D)
+    lr = 5e-4
+    one, ten = O.split_lr_groups(list(O.leaf_params(g_sd).keys()))
+    opt = torch.optim.SGD([{'params': [g_sd[k] for k in one], 'lr': lr}, {'params': [g_sd[k] for k in ten], 'lr': lr * 10}],
+                          momentum=0.9, weight_decay=5e-4)
+    opt_d = torch.optim.Adam(list(O.leaf_params(d_sd).values()), lr=1e-4, betas=(0.9, 0.99))
+
+    def inputs(seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(2, 3, 65, 97, generator=g)
+        lab = torch.randint(0, 20, (2, 65, 97), generator=g).float()
+        lab[lab == 19] = 255
+        return x, lab
+
+    for it in range(2):
+        src, lab = inputs(100 + it)
+        tgt, _ = inputs(200 + it)
+        for o in (opt, opt_d):
+            for gi, grp in enumerate(o.param_groups):
+                grp['lr'] = O.poly_lr(lr, it, 10) * (10 if gi > 0 else 1)
+        losses = O.adapt_step(g_sd, d_sd, opt, opt_d, src, lab, tgt, O.BNCfg(True), drop=False)
+        assert np.allclose(losses, fix['losses'][it], rtol=2e-4, atol=1e-6), (losses, fix['losses'][it])
+    for k in fix.files:
+        if k.startswith('w:'):
+            assert rel(g_sd[k[2:]].detach().reshape(-1)[:4096], fix[k]) < 1e-4, k
+    assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
