@@ -87,6 +87,11 @@ class Ctx:
 
 
 # --------------------------------------------------------------------------- weights
+# Bumped by the fused optimizers, which update parameters through raw pointers and therefore do
+# not touch torch's per-tensor version counter.
+WEIGHT_EPOCH = [0]
+
+
 def packed_weight(cx, w, transpose):
     """bf16 [R*S][A_pad][B_pad] copy of an OIHW fp32 parameter, cached per parameter version."""
     cache = getattr(w, "_s2r_pack", None)
@@ -95,7 +100,8 @@ def packed_weight(cx, w, transpose):
         w._s2r_pack = cache
     key = (transpose, w.data_ptr())
     ent = cache.get(key)
-    if ent is not None and ent[0] == w._version:
+    stamp = (w._version, WEIGHT_EPOCH[0])
+    if ent is not None and ent[0] == stamp:
         return ent[1], ent[2], ent[3]
     Cout, Cin, R, S = w.shape
     A, B = (Cin, Cout) if transpose else (Cout, Cin)
@@ -103,7 +109,7 @@ def packed_weight(cx, w, transpose):
     buf = ent[1] if ent is not None else torch.empty((R * S, A_pad, B_pad), dtype=BF16, device=w.device)
     L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, R, S, 1 if transpose else 0, _vp(buf), A_pad, B_pad,
            cx.stream)
-    cache[key] = (w._version, buf, A_pad, B_pad)
+    cache[key] = (stamp, buf, A_pad, B_pad)
     return buf, A_pad, B_pad
 
 

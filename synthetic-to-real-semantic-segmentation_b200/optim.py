@@ -1,0 +1,172 @@
+"""Multi-tensor optimizers on the C-ABI kernels (s2r_sgd_step / s2r_adam_step) with the
+torch.optim surface the reference's scripts use: param_groups with a mutable 'lr'
+(utils/lr_scheduler.py:63-70 writes it), step(), zero_grad().
+
+Gradients of all parameters live in ONE flat fp32 buffer (p.grad are views): zero_grad is a single
+memset, the data-parallel gradient all-reduce is a single NCCL call, and the slot table the
+kernels walk is built once.  Learning rate / bias corrections travel through a pinned host buffer
+and a device copy so that a captured CUDA graph replays with the current schedule value.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from .engine import _vp, WEIGHT_EPOCH
+
+
+def _groups(params, defaults):
+    params = list(params)
+    if len(params) == 0:
+        raise ValueError("optimizer got an empty parameter list")
+    if not isinstance(params[0], dict):
+        params = [{'params': params}]
+    groups = []
+    for g in params:
+        g = dict(g)
+        g['params'] = list(g['params'])
+        for k, v in defaults.items():
+            g.setdefault(k, v)
+        groups.append(g)
+    return groups
+
+
+class _FusedBase(object):
+    n_state = 1
+
+    def __init__(self, params, defaults):
+        self.param_groups = _groups(params, defaults)
+        self.defaults = defaults
+        allp = [p for g in self.param_groups for p in g['params']]
+        if len(set(id(p) for p in allp)) != len(allp):
+            raise ValueError("some parameters appear in more than one parameter group")
+        dev = allp[0].device
+        if dev.type != "cuda":
+            raise L.S2RError("fused optimizers need CUDA parameters; there is no CPU path")
+        self.device = dev
+        total = sum(p.numel() for p in allp)
+        # flat gradient buffer; existing gradients are carried over
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.state_bufs = [torch.zeros(total, dtype=torch.float32, device=dev) for _ in range(self.n_state)]
+        off = 0
+        self._views = []
+        for p in allp:
+            n = p.numel()
+            gv = self.flat_grad[off:off + n].view_as(p)
+            if p.grad is not None:
+                gv.copy_(p.grad)
+            p.grad = gv
+            self._views.append((p, off, n))
+            off += n
+        self._tables = None
+        self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in self.param_groups]
+        self._hyper_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in self.param_groups]
+        self.steps = 0
+        self.grad_scale = 1.0
+
+    def _build_tables(self):
+        tables = []
+        lookup = {id(p): (off, n) for p, off, n in self._views}
+        for g in self.param_groups:
+            ps = [p for p in g['params'] if p.requires_grad or p.grad is not None]
+            arr = (L.ParamSlot * max(1, len(ps)))()
+            for i, p in enumerate(ps):
+                off, n = lookup[id(p)]
+                if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                    # the caller replaced .grad (e.g. zero_grad(set_to_none=True) elsewhere): re-attach
+                    gv = self.flat_grad[off:off + n].view_as(p)
+                    if p.grad is not None:
+                        gv.copy_(p.grad)
+                    else:
+                        gv.zero_()
+                    p.grad = gv
+                arr[i].p = p.data_ptr()
+                arr[i].g = p.grad.data_ptr()
+                arr[i].s0 = self.state_bufs[0].data_ptr() + 4 * off
+                arr[i].s1 = self.state_bufs[1].data_ptr() + 4 * off if self.n_state > 1 else None
+                arr[i].n = n
+                arr[i].lr_mult = 1.0
+            raw = bytes(arr)[:C.sizeof(L.ParamSlot) * len(ps)]
+            dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device) if len(ps) else None
+            tables.append((dev, len(ps)))
+        self._tables = tables
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+    def all_reduce_grads(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat_grad, group=group)
+            self.grad_scale = 1.0 / dist.get_world_size(group)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def state_dict(self):
+        return {'steps': self.steps, 'state': [b.clone() for b in self.state_bufs],
+                'param_groups': [{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.steps = sd['steps']
+        for b, s in zip(self.state_bufs, sd['state']):
+            b.copy_(s)
+        for g, s in zip(self.param_groups, sd['param_groups']):
+            g.update(s)
+
+
+class FusedSGD(_FusedBase):
+    """torch.optim.SGD(params, lr, momentum, weight_decay, nesterov) -- train_adapt.py:58-59."""
+    n_state = 1
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
+                                      nesterov=nesterov))
+
+    @torch.no_grad()
+    def step(self):
+        if self._tables is None:
+            self._build_tables()
+        with torch.cuda.device(self.device):
+            for gi, g in enumerate(self.param_groups):
+                tab, n = self._tables[gi]
+                if n == 0:
+                    continue
+                self._hyper_host[gi][0] = float(g['lr'])
+                self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
+                L.call("s2r_sgd_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(g['momentum']),
+                       float(g['dampening']), float(g['weight_decay']), 1 if g['nesterov'] else 0,
+                       float(self.grad_scale), self._stream())
+        self.steps += 1
+        WEIGHT_EPOCH[0] += 1
+
+
+class FusedAdam(_FusedBase):
+    """torch.optim.Adam(params, lr, betas, eps, weight_decay) -- train_adapt.py:60, train.py:77-80."""
+    n_state = 2
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self):
+        if self._tables is None:
+            self._build_tables()
+        self.steps += 1
+        with torch.cuda.device(self.device):
+            for gi, g in enumerate(self.param_groups):
+                tab, n = self._tables[gi]
+                if n == 0:
+                    continue
+                b1, b2 = g['betas']
+                h = self._hyper_host[gi]
+                h[0] = float(g['lr'])
+                h[1] = 1.0 - math.pow(b1, self.steps)
+                h[2] = 1.0 - math.pow(b2, self.steps)
+                self._hyper_dev[gi].copy_(h, non_blocking=True)
+                L.call("s2r_adam_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(b1), float(b2), float(g['eps']),
+                       float(g['weight_decay']), float(self.grad_scale), self._stream())
+        WEIGHT_EPOCH[0] += 1

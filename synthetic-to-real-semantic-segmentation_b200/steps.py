@@ -1,0 +1,160 @@
+"""The three loop bodies of the reference as callables over the drop-in modules:
+  AdaptStep    train_adapt.py:126-181  output-space adaptation (AdaptSegNet): G + FCDiscriminator
+  FeatureStep  train.py:163-216        feature adaptation (FCN in the wild): domain classifier
+  ValStep      val_adapt.py:122-135    eval forward + Evaluator confusion matrix
+Order of forward/backward passes, requires_grad toggling, loss definitions (including the
+batch-axis softmax and the un-weighted adversarial loss) and optimizer steps follow the
+reference; losses stay on the device (no per-step .item()).
+
+Data parallel (one process per GPU): each rank runs the step on its shard of the batch; BN
+statistics are all-reduced inside the engine when the model was built with sync_bn=True, and the
+flat gradient buffers are all-reduced (averaged) before the optimizer steps.  Deviation from the
+single-process DataParallel of the reference, stated in DESIGN.md: the cross-entropy mean and
+F.softmax(dim=0) are taken over the rank-local batch.
+"""
+import torch
+
+from .functional import softmax_dim0, bce_with_logits, cross_entropy
+from .optim import FusedSGD, FusedAdam
+from .utils.loss import SegmentationLosses, DomainLosses
+from .utils.lr_scheduler import LR_Scheduler
+from .utils.metrics import Evaluator
+
+
+class AdaptStep(object):
+    def __init__(self, model, model_D, lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False,
+                 lr_scheduler='poly', epochs=200, iters_per_epoch=1000, class_weight=None, loss_type='ce'):
+        self.model, self.model_D = model, model_D
+        train_params = [{'params': list(model.get_1x_lr_params()), 'lr': lr},
+                        {'params': list(model.get_10x_lr_params()), 'lr': lr * 10}]
+        self.optimizer = FusedSGD(train_params, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov)
+        self.optimizer_D = FusedAdam(model_D.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        self.criterion = SegmentationLosses(weight=class_weight).build_loss(mode=loss_type)
+        self.scheduler = LR_Scheduler(lr_scheduler, lr, epochs, iters_per_epoch)
+        self.source_label, self.target_label = 0, 1
+
+    def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        model, model_D = self.model, self.model_D
+        self.scheduler(self.optimizer, i, epoch)
+        self.optimizer.zero_grad()
+        self.scheduler(self.optimizer_D, i, epoch)
+        self.optimizer_D.zero_grad()
+        # ---- train G; don't accumulate grads in D (train_adapt.py:140-155)
+        for p in model_D.parameters():
+            p.requires_grad = False
+        src_output = model(src_image)
+        loss_seg = self.criterion(src_output, src_label)
+        loss_seg.backward()
+        tgt_output = model(tgt_image)
+        D_out = model_D(softmax_dim0(tgt_output))
+        loss_adv = bce_with_logits(D_out, self.source_label)
+        loss_adv.backward()
+        # ---- train D (train_adapt.py:160-178)
+        for p in model_D.parameters():
+            p.requires_grad = True
+        src_output = src_output.detach()
+        loss_D_src = bce_with_logits(model_D(softmax_dim0(src_output)), self.source_label)
+        loss_D_src.backward()
+        tgt_output = tgt_output.detach()
+        loss_D_tgt = bce_with_logits(model_D(softmax_dim0(tgt_output)), self.target_label)
+        loss_D_tgt.backward()
+        self.optimizer.all_reduce_grads()
+        self.optimizer_D.all_reduce_grads()
+        self.optimizer.step()
+        self.optimizer_D.step()
+        return {'loss_seg': loss_seg.detach(), 'loss_adv': loss_adv.detach(), 'loss_D_src': loss_D_src.detach(),
+                'loss_D_tgt': loss_D_tgt.detach()}
+
+
+class FeatureStep(object):
+    def __init__(self, backbone_model, assp_model, y_model, d_model, lr=5e-4, optimizer='Adam', momentum=0.9,
+                 weight_decay=5e-4, nesterov=False, lr_scheduler='poly', epochs=200, iters_per_epoch=1000):
+        self.f, self.a, self.y, self.d = backbone_model, assp_model, y_model, d_model
+        f_params = list(backbone_model.parameters()) + list(assp_model.parameters())
+        y_params = list(y_model.parameters())
+        d_params = list(d_model.parameters())
+        # train.py:63-82: task (f+y), d, d_inv (f again); c_optimizer exists there but never steps
+        if optimizer == 'SGD':
+            mk = lambda ps: FusedSGD(ps, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov)  # noqa: E731
+        elif optimizer == 'Adam':
+            mk = lambda ps: FusedAdam(ps, lr=lr)  # noqa: E731
+        else:
+            raise NotImplementedError
+        self.task_optimizer = mk(f_params + y_params)
+        self.d_optimizer = mk(d_params)
+        self.d_inv_optimizer = _SharedGradOptimizer(mk, f_params, self.task_optimizer)
+        self.task_loss = SegmentationLosses().build_loss('ce')
+        self.domain_loss = DomainLosses().build_loss()
+        self.scheduler = LR_Scheduler(lr_scheduler, lr, epochs, iters_per_epoch)
+
+    def _forward(self, image):
+        high0, low = self.f(image)
+        high = self.a(high0)
+        out = torch.nn.functional.interpolate(self.y(high, low), image.size()[2:], mode='bilinear', align_corners=True)
+        return out, self.d(high)
+
+    def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        for o in (self.task_optimizer, self.d_optimizer, self.d_inv_optimizer):
+            self.scheduler(o, i, epoch)
+        self.task_optimizer.zero_grad()
+        self.d_optimizer.zero_grad()
+        src_output, src_d_pred = self._forward(src_image)
+        task_loss = self.task_loss(src_output, src_label)
+        _, tgt_d_pred = self._forward(tgt_image)
+        d_loss, d_acc = self.domain_loss(src_d_pred, tgt_d_pred)
+        d_inv_loss, _ = self.domain_loss(tgt_d_pred, src_d_pred)
+        loss = task_loss + d_loss + d_inv_loss
+        loss.backward()
+        self.task_optimizer.all_reduce_grads()
+        self.d_optimizer.all_reduce_grads()
+        self.task_optimizer.step()
+        self.d_optimizer.step()
+        self.d_inv_optimizer.step()
+        return {'task_loss': task_loss.detach(), 'd_loss': d_loss.detach(), 'd_inv_loss': d_inv_loss.detach(),
+                'd_acc': d_acc}
+
+
+class _SharedGradOptimizer(object):
+    """A second optimizer over parameters whose gradients already live in another optimizer's
+    flat buffer (train.py:71-73,204: d_inv_optimizer steps backbone+ASPP again with the same grads)."""
+
+    def __init__(self, mk, params, owner):
+        grads = [p.grad for p in params]
+        self.inner = mk(params)          # re-points p.grad at its own flat buffer
+        self.params, self.owner = params, owner
+        for p, g in zip(params, grads):  # restore the owner's views: both optimizers read the same grads
+            p.grad = g
+        self.param_groups = self.inner.param_groups
+        self.inner._tables = None
+
+    def step(self):
+        if self.inner._tables is None:
+            # build tables against the owner's gradient views
+            inner = self.inner
+            inner.flat_grad = self.owner.flat_grad
+            lookup = {id(p): off for p, off, n in self.owner._views}
+            inner._views = [(p, lookup[id(p)], p.numel()) for p in self.params]
+            # state buffers stay private but are indexed with the owner's offsets: size them alike
+            inner.state_bufs = [torch.zeros_like(self.owner.flat_grad) for _ in range(inner.n_state)]
+            inner._build_tables()
+        self.inner.grad_scale = self.owner.grad_scale
+        self.inner.step()
+
+    def zero_grad(self):
+        pass
+
+
+class ValStep(object):
+    """val_adapt.py:122-135 with argmax + confusion matrix fused on the device."""
+
+    def __init__(self, model, num_class=19):
+        self.model = model
+        self.evaluator = Evaluator(num_class)
+        self.criterion = SegmentationLosses().build_loss('ce')
+
+    @torch.no_grad()
+    def __call__(self, image, target, with_loss=False):
+        output = self.model(image)
+        loss = self.criterion(output, target) if with_loss else None
+        self.evaluator.add_batch_logits(target, output)
+        return loss

@@ -1,0 +1,193 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, ctypes structs match the C layout, the tap tables the host builds for the
+tap-GEMM kernels reproduce F.conv2d and its gradients (emulated in numpy, no GPU), and the
+product path refuses to run without CUDA instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT, sub
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "s2r_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2r_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(built_lib, s), s
+    assert built_lib.s2r_version() >= 100
+    L = sub("_lib")
+    assert set(L.PROTOTYPES) | set(L.PLAIN) == set(syms)
+
+
+def test_struct_layout_matches_c(built_lib, tmp_path):
+    """sizeof() of the ctypes mirrors == sizeof() in C (compiled from the header with gcc)."""
+    L = sub("_lib")
+    c = tmp_path / "sz.c"
+    c.write_text('#include <stdio.h>\n#include "s2r_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(s2r_tap),'
+                 ' sizeof(s2r_conv_args), sizeof(s2r_wgrad_args), sizeof(s2r_param_slot));return 0;}\n')
+    exe = tmp_path / "sz"
+    import subprocess
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(L.Tap), ctypes.sizeof(L.ConvArgs), ctypes.sizeof(L.WgradArgs),
+                     ctypes.sizeof(L.ParamSlot)]
+
+
+def test_struct_size_is_checked(built_lib):
+    L = sub("_lib")
+    a = L.ConvArgs()
+    a.struct_size = 4
+    with pytest.raises(ValueError):
+        L.call("s2r_conv_fwd", ctypes.byref(a), None)
+    assert "struct size" in L.last_error()
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    L = sub("_lib")
+    m = sub("modeling.discriminator").FCDiscriminator(19)
+    with pytest.raises(L.S2RError):
+        m(torch.zeros(1, 19, 32, 32))
+    with pytest.raises(L.S2RError):
+        sub("functional").softmax_dim0(torch.zeros(2, 3))
+    with pytest.raises(L.S2RError):
+        sub("utils.metrics").Evaluator(19).add_batch(np.zeros((2, 2), np.float32), np.zeros((2, 2), np.int64))
+
+
+def test_reference_error_conventions():
+    nn = torch.nn
+    with pytest.raises(NotImplementedError):
+        sub("modeling.assp").ASPP('mobilenet', 32, nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        sub("modeling.decoder").Decoder(19, 'vgg', nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        sub("modeling.domian").DomainClassifer('resnet', nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        sub("utils.loss").SegmentationLosses().build_loss('dice')
+    with pytest.raises(NotImplementedError):
+        sub("modeling.backbone").build_backbone('resnet', 16, nn.BatchNorm2d)
+    with pytest.raises(AssertionError):
+        sub("modeling.backbone.mobilenet").InvertedResidual(8, 8, 3, 1, 6, nn.BatchNorm2d)
+
+
+# ----------------------------------------------------------------------------- tap tables
+class FakeAct:
+    """Stand-in for engine.Act on a numpy buffer: ptr is a byte offset (2 bytes per element)."""
+
+    def __init__(self, arr, base):
+        self.arr = arr
+        self.N, self.H, self.W, self.pitch = arr.shape
+        self.C = self.pitch
+        self.off = 0
+        self.ptr = base
+
+
+def read_view(mem, tap, n, y, x, Cn):
+    if not (0 <= y < tap.H and 0 <= x < tap.W):
+        return np.zeros(Cn, dtype=np.float64)
+    e = (tap.base or 0) // 2 + n * tap.sn + y * tap.sh + x * tap.sw
+    return mem[e:e + Cn]
+
+
+@pytest.mark.parametrize("R,stride,pad,dil,H,W", [(3, 1, 1, 1, 7, 9), (3, 1, 6, 6, 9, 11), (3, 2, 1, 1, 9, 8),
+                                                  (4, 2, 1, 1, 8, 10), (4, 2, 1, 1, 9, 11), (1, 1, 0, 1, 5, 4)])
+def test_tap_tables_reproduce_conv2d_and_gradients(R, stride, pad, dil, H, W):
+    eng = sub("engine")
+    L = sub("_lib")
+    rng = np.random.RandomState(R * 100 + stride * 10 + dil)
+    N, Cin, Cout = 2, 8, 5
+    x = rng.randn(N, H, W, Cin)
+    w = rng.randn(Cout, Cin, R, R)
+    OH, OW = eng.conv_out_hw(H, W, R, R, stride, pad, dil)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wt = torch.from_numpy(w).clone().requires_grad_(True)
+    yt = F.conv2d(xt, wt, None, stride, pad, dil)
+    dy = rng.randn(*yt.shape)
+    yt.backward(torch.from_numpy(dy))
+
+    # forward: out[m][co] = sum_t sum_ci view_t[pix + d_t][ci] * w[co][ci][t]
+    mem = x.reshape(-1).copy()
+    xa = FakeAct(x, 0)
+    taps = (L.Tap * 16)()
+    nt = eng.fwd_taps(taps, xa, R, R, stride, pad, dil)
+    assert nt == R * R
+    out = np.zeros((N, OH, OW, Cout))
+    for t in range(nt):
+        kh, kw = divmod(taps[t].wslice, R)
+        for n in range(N):
+            for oh in range(OH):
+                for ow in range(OW):
+                    v = read_view(mem, taps[t], n, oh + taps[t].dh, ow + taps[t].dw, Cin)
+                    out[n, oh, ow] += w[:, :, kh, kw] @ v
+    assert np.allclose(out, yt.detach().permute(0, 2, 3, 1).numpy(), atol=1e-9)
+
+    # weight gradient from the same taps
+    dyn = dy.transpose(0, 2, 3, 1)
+    dw = np.zeros_like(w)
+    for t in range(nt):
+        kh, kw = divmod(taps[t].wofs, R)
+        for n in range(N):
+            for oh in range(OH):
+                for ow in range(OW):
+                    v = read_view(mem, taps[t], n, oh + taps[t].dh, ow + taps[t].dw, Cin)
+                    dw[:, :, kh, kw] += np.outer(dyn[n, oh, ow], v)
+    assert np.allclose(dw, wt.grad.numpy(), atol=1e-8)
+
+    # data gradient: one tap-GEMM per input parity class, recorded instead of launched
+    calls = []
+    real_call = L.call
+
+    def fake_call(name, *args):
+        a = args[0]._obj
+        calls.append((a.ntaps, [(a.taps[i].dh, a.taps[i].dw, a.taps[i].wslice, a.taps[i].H, a.taps[i].W) for i in
+                                range(a.ntaps)], a.OH, a.OW, a.out, a.on, a.oh, a.ow))
+        return 0
+
+    class FakeCx:
+        stream = None
+
+    dya = FakeAct(np.ascontiguousarray(dyn_pad(dyn)), 1 << 20)
+    dxa = FakeAct(np.zeros((N, H, W, Cin)), 0)
+    wparam = torch.zeros(Cout, Cin, R, R)
+    eng_pack = eng.packed_weight
+    eng.packed_weight = lambda cx, w_, tr: (torch.zeros(1), 16, 64)
+    L.call = fake_call
+    try:
+        eng.conv_dgrad(FakeCx(), dya, wparam, dxa, stride, pad, dil)
+    finally:
+        L.call = real_call
+        eng.packed_weight = eng_pack
+    dx = np.zeros((N, H, W, Cin))
+    dymem = dya.arr
+    for ntaps, tl, OHc, OWc, outp, on, oh_s, ow_s in calls:
+        for n in range(N):
+            for i in range(OHc):
+                for j in range(OWc):
+                    acc = np.zeros(Cin)
+                    for dh, dw_, ws, TH, TW in tl:
+                        y, xx = i + dh, j + dw_
+                        if 0 <= y < TH and 0 <= xx < TW:
+                            kh, kw = divmod(ws, R)
+                            acc += w[:, :, kh, kw].T @ dymem[n, y, xx, :Cout]
+                    e = (outp or 0) // 2 + n * on + i * oh_s + j * ow_s
+                    dx.reshape(-1)[e:e + Cin] += acc
+    assert np.allclose(dx, xt.grad.permute(0, 2, 3, 1).numpy(), atol=1e-8)
+
+
+def dyn_pad(dyn):
+    """pad the channel axis of dy to a multiple of 8 (zeros) as the kernels require"""
+    c = dyn.shape[-1]
+    p = (8 - c % 8) % 8
+    return np.pad(dyn, ((0, 0), (0, 0), (0, 0), (0, p)))

@@ -1,0 +1,449 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against a plain fp32 restatement of
+the same op (torch ops on the same device, or the numpy/C oracle for the integer path).
+Tolerances: bit-exact for the confusion matrix; bf16 storage (2^-9 relative per element) bounds
+the floating-point kernels, stated per test as a relative L2 error."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, sub
+from oracle import ref_port as O
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    assert torch.cuda.is_available()
+    return sub("engine")
+
+
+@pytest.fixture()
+def cx(eng):
+    return eng.Ctx(torch.device("cuda", 0), True)
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc_act(eng, t_nchw, pitch=None):
+    """NCHW fp32 -> Act (bf16, channel pitch padded with zeros)"""
+    N, Cc, H, W = t_nchw.shape
+    pitch = pitch or eng.round_up(Cc, 8)
+    buf = torch.zeros((N, H, W, pitch), dtype=torch.bfloat16, device=t_nchw.device)
+    buf[..., :Cc] = t_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    a = eng.Act(buf)
+    a.C = Cc
+    return a
+
+
+def to_nchw(a, Cc=None):
+    Cc = Cc or a.C
+    return a.t[..., a.off:a.off + Cc].float().permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, R, stride, pad, dil
+    (2, 17, 23, 32, 16, 1, 1, 0, 1),
+    (2, 16, 24, 16, 96, 1, 1, 0, 1),
+    (1, 33, 33, 320, 256, 3, 1, 6, 6),
+    (2, 9, 12, 320, 256, 3, 1, 18, 18),
+    (2, 20, 28, 304, 256, 3, 1, 1, 1),
+    (2, 32, 48, 3, 32, 3, 2, 1, 1),
+    (2, 33, 47, 3, 32, 3, 2, 1, 1),
+    (2, 32, 48, 19, 64, 4, 2, 1, 1),
+    (2, 17, 25, 64, 128, 4, 2, 1, 1),
+    (2, 8, 12, 512, 1, 4, 2, 1, 1),
+    (2, 16, 24, 256, 19, 1, 1, 0, 1),
+    (1, 9, 12, 1024, 2, 3, 1, 1, 1),
+    (3, 1, 1, 320, 256, 1, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(eng, cx, case):
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(hash(case) & 0xffff)
+    x = bf(torch.randn(N, Cin, H, W, device="cuda", generator=g))
+    w = torch.randn(Cout, Cin, R, R, device="cuda", generator=g) * (2.0 / (Cin * R * R)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wq = bf(w)
+    xr = x.clone().requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, b, stride, pad, dil)
+    OH, OW = y_ref.shape[2:]
+    xa = nhwc_act(eng, x)
+    wparam = torch.nn.Parameter(w.clone())
+    out = cx.new(N, OH, OW, eng.round_up(Cout, 8), zero=True)
+    out.C = Cout
+    stats = cx.f64(2 * Cout)
+    eng.conv_fwd(cx, xa, wparam, out, stride, pad, dil, bias=b, stats=stats)
+    torch.cuda.synchronize()
+    y = to_nchw(out)
+    assert rel(y, y_ref.detach()) < 4e-3
+    s_ref = torch.stack([y_ref.detach().double().sum((0, 2, 3)), (y_ref.detach().double() ** 2).sum((0, 2, 3))])
+    assert rel(stats.view(2, Cout), s_ref) < 1e-3
+    # leaky epilogue
+    out2 = cx.new(N, OH, OW, eng.round_up(Cout, 8), zero=True)
+    out2.C = Cout
+    eng.conv_fwd(cx, xa, wparam, out2, stride, pad, dil, bias=b, act=L.ACT_LEAKY, slope=0.2)
+    assert rel(to_nchw(out2), F.leaky_relu(y_ref.detach(), 0.2)) < 4e-3
+    # gradients
+    dy = bf(torch.randn(N, Cout, OH, OW, device="cuda", generator=g))
+    y_ref.backward(dy)
+    dya = nhwc_act(eng, dy)
+    wparam.grad = None
+    eng.conv_wgrad(cx, xa, dya, wparam, stride, pad, dil)
+    torch.cuda.synchronize()
+    assert rel(wparam.grad, wr.grad) < 4e-3
+    if Cin % 8 == 0 or True:
+        dx = cx.new(N, H, W, eng.round_up(Cin, 8), zero=True)
+        dx.C = Cin
+        eng.conv_dgrad(cx, dya, wparam, dx, stride, pad, dil)
+        torch.cuda.synchronize()
+        assert rel(to_nchw(dx), xr.grad) < 4e-3
+        # accumulate into an existing gradient
+        eng.conv_dgrad(cx, dya, wparam, dx, stride, pad, dil, aux=dx, aux_mode=L.AUX_ADD)
+        torch.cuda.synchronize()
+        assert rel(to_nchw(dx), 2 * xr.grad) < 6e-3
+    bparam = torch.nn.Parameter(b.clone())
+    eng.bias_grad(cx, dya, bparam)
+    assert rel(bparam.grad, dy.sum((0, 2, 3))) < 1e-4
+
+
+def test_conv_into_concat_slice_and_leaky_mask(eng, cx):
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = bf(torch.randn(2, 64, 12, 10, device="cuda", generator=g))
+    w = torch.nn.Parameter(torch.randn(48, 64, 1, 1, device="cuda", generator=g) * 0.1)
+    cat = cx.new(2, 12, 10, 304, zero=True)
+    eng.conv_fwd(cx, nhwc_act(eng, x), w, cat.slice(256, 48))
+    ref = F.conv2d(x, bf(w.detach()))
+    assert rel(cat.t[..., 256:304].float().permute(0, 3, 1, 2), ref) < 4e-3
+    assert float(cat.t[..., :256].abs().sum()) == 0.0
+    # leaky mask epilogue of the data gradient
+    y_prev = bf(torch.randn(2, 64, 12, 10, device="cuda", generator=g))
+    dy = bf(torch.randn(2, 48, 12, 10, device="cuda", generator=g))
+    dx = cx.new(2, 12, 10, 64)
+    eng.conv_dgrad(cx, nhwc_act(eng, dy), w, dx, aux=nhwc_act(eng, y_prev), aux_mode=L.AUX_LEAKY_MASK, slope=0.2)
+    ref = F.conv_transpose2d(dy, bf(w.detach())) * torch.where(y_prev > 0, 1.0, 0.2)
+    assert rel(to_nchw(dx), ref) < 4e-3
+
+
+DW_CASES = [(2, 18, 26, 32, 1, 1, False), (2, 17, 25, 96, 2, 1, True), (2, 16, 24, 144, 1, 1, True),
+            (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True)]
+
+
+@pytest.mark.parametrize("case", DW_CASES)
+def test_dwconv_fused_prologue_halo(eng, cx, case):
+    """dw3x3 on pad(relu6(bn(z))) where the pad value is relu6(shift) (halo_const) or 0."""
+    N, H, W, Cc, stride, dil, halo = case
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(Cc + stride)
+    z = bf(torch.randn(N, Cc, H, W, device="cuda", generator=g) * 2)
+    sc = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    sh = torch.randn(Cc, device="cuda", generator=g)
+    mean = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    invstd = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    w = torch.randn(Cc, 1, 3, 3, device="cuda", generator=g) * 0.3
+    pad = dil
+    zr = z.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    if halo:
+        # the reference computes bn+relu6 on the zero-padded tensor: border pre-activation = shift
+        zp = F.pad(zr, (pad,) * 4)
+        a = F.relu6(zp * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    else:
+        a = F.pad(F.relu6(zr * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)), (pad,) * 4)
+    y_ref = F.conv2d(a, wr, None, stride, 0, dil, Cc)
+    st = eng.BNState(torch.cat([sc, sh]).contiguous(), torch.cat([mean, invstd]).contiguous(), 1.0, False)
+    za = nhwc_act(eng, z)
+    stats = cx.f64(2 * Cc)
+    y = eng.dw_fwd(cx, za, st, L.ACT_RELU6, halo, w, stride, dil, pad, stats)
+    torch.cuda.synchronize()
+    assert rel(to_nchw(y), y_ref.detach()) < 4e-3
+    s_ref = torch.stack([y_ref.detach().double().sum((0, 2, 3)), (y_ref.detach().double() ** 2).sum((0, 2, 3))])
+    assert rel(stats.view(2, Cc), s_ref) < 1e-3
+    dy = bf(torch.randn(*y_ref.shape, device="cuda", generator=g))
+    if halo:
+        zp.retain_grad()
+    y_ref.backward(dy)
+    dya = nhwc_act(eng, dy)
+    dw = torch.zeros_like(w)
+    L.call("s2r_dwconv3x3_wgrad", za.vp(), C.c_void_p(st.ss.data_ptr()), L.ACT_RELU6, 1 if halo else 0, dya.vp(),
+           C.c_void_p(dw.data_ptr()), N, H, W, Cc, stride, dil, pad, cx.stream)
+    torch.cuda.synchronize()
+    assert rel(dw, wr.grad) < 4e-3
+    ext = pad if halo else 0
+    gbuf = cx.new(N, H + 2 * ext, W + 2 * ext, Cc)
+    bsums = cx.f64(2 * Cc)
+    L.call("s2r_dwconv3x3_dgrad", dya.vp(), C.c_void_p(w.data_ptr()), za.vp(), C.c_void_p(st.ss.data_ptr()),
+           C.c_void_p(st.mi.data_ptr()), L.ACT_RELU6, ext, gbuf.vp(), C.c_void_p(bsums.data_ptr()), N, H, W, Cc, stride,
+           dil, pad, cx.stream)
+    torch.cuda.synchronize()
+    # g = d loss / d (bn output), i.e. grad wrt pre-activation; grad wrt z(p) = g * scale
+    g_ref = (zp.grad if halo else zr.grad) / sc.view(1, -1, 1, 1)
+    assert rel(to_nchw(gbuf), g_ref) < 5e-3
+    zfull = F.pad(z, (ext,) * 4) if halo else z
+    xhat = (zfull - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    b_ref = torch.stack([g_ref.double().sum((0, 2, 3)), (g_ref.double() * xhat.double()).sum((0, 2, 3))])
+    assert rel(bsums.view(2, Cc), b_ref) < 2e-3
+
+
+@pytest.mark.parametrize("Cc,P,clamp", [(32, 5000, 0), (96, 777, 1), (256, 64, 0), (1024, 200, 1)])
+def test_batchnorm_forward_backward(eng, cx, Cc, P, clamp):
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(Cc)
+    N, H, W = 1, P, 1
+    x = bf(torch.randn(N, Cc, H, W, device="cuda", generator=g) * 1.5 + 0.3)
+    bn = torch.nn.BatchNorm2d(Cc).cuda()
+    bn.weight.data = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    bn.bias.data = torch.randn(Cc, device="cuda", generator=g) * 0.5
+    ref = torch.nn.BatchNorm2d(Cc).cuda()
+    ref.load_state_dict(bn.state_dict())
+    xr = x.clone().requires_grad_(True)
+    res = bf(torch.randn(N, Cc, H, W, device="cuda", generator=g))
+    y_ref = F.relu6(ref(xr)) + res
+    xa = nhwc_act(eng, x)
+    sums = cx.f64(2 * Cc)
+    L.call("s2r_channel_sums_bf16", xa.vp(), xa.P, Cc, xa.pitch, 0, C.c_void_p(sums.data_ptr()), cx.stream)
+    if clamp:
+        # the cross-rank branch (clamp(var, eps)^-1/2, batchnorm.py:125) with the all-reduce stubbed:
+        # two "ranks" of P/2 elements whose sums are already added up
+        bn._s2r_sync = True
+        cx.world = 2
+        cx.allreduce = lambda t: None
+        st = eng.bn_finalize(cx, bn, sums, xa.P / 2)
+    else:
+        st = eng.bn_finalize(cx, bn, sums, xa.P)
+    out = cx.new(N, H, W, Cc)
+    eng.bn_apply(cx, xa, st, L.ACT_RELU6, out, residual=nhwc_act(eng, res))
+    torch.cuda.synchronize()
+    assert rel(to_nchw(out), y_ref.detach()) < 4e-3
+    assert rel(bn.running_mean, ref.running_mean) < 1e-4 and rel(bn.running_var, ref.running_var) < 1e-4
+    dy = bf(torch.randn(N, Cc, H, W, device="cuda", generator=g))
+    y_ref.backward(dy)
+    dx = cx.new(N, H, W, Cc)
+    eng.bn_backward(cx, bn, nhwc_act(eng, dy), xa, st, L.ACT_RELU6, dx)
+    torch.cuda.synchronize()
+    assert rel(to_nchw(dx), xr.grad) < 6e-3
+    assert rel(bn.weight.grad, ref.weight.grad) < 3e-3 and rel(bn.bias.grad, ref.bias.grad) < 3e-3
+    # eval mode uses the running statistics
+    ref.eval()
+    st_e = eng.bn_eval(cx, bn)
+    eng.bn_apply(cx, xa, st_e, L.ACT_NONE, out)
+    assert rel(to_nchw(out), ref(x).detach()) < 4e-3
+
+
+def test_bn_dropout_is_regenerated_in_backward(eng, cx):
+    L = sub("_lib")
+    Cc, P = 64, 4096
+    x = bf(torch.randn(1, Cc, P, 1, device="cuda"))
+    bn = torch.nn.BatchNorm2d(Cc).cuda()
+    xa = nhwc_act(eng, x)
+    st = eng.bn_eval(cx, bn)
+    out = cx.new(1, P, 1, Cc)
+    eng.bn_apply(cx, xa, st, L.ACT_NONE, out, drop_p=0.5, seed=1234)
+    y = to_nchw(out)
+    keep = (y != 0)
+    frac = float(keep.float().mean())
+    assert 0.47 < frac < 0.53
+    assert rel(y[keep], (2 * x / (1 + 1e-5) ** 0.5)[keep]) < 4e-3
+    ones = nhwc_act(eng, torch.ones_like(x))
+    dx = cx.new(1, P, 1, Cc)
+    eng.bn_backward(cx, bn, ones, xa, st, L.ACT_NONE, dx, drop_p=0.5, seed=1234)
+    d = to_nchw(dx)
+    assert bool(((d != 0) == keep).all())
+
+
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 64, 128, 256), (5, 7, 17, 25), (33, 33, 129, 129), (1, 1, 9, 12)])
+def test_bilinear_align_corners(eng, cx, Hi, Wi, Ho, Wo):
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(Hi * Wo)
+    x = bf(torch.randn(2, 24, Hi, Wi, device="cuda", generator=g))
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.interpolate(xr, size=(Ho, Wo), mode='bilinear', align_corners=True)
+    xa = nhwc_act(eng, x)
+    out = cx.new(2, Ho, Wo, 40, zero=True)
+    L.call("s2r_upsample_bilinear_nhwc", xa.vp(), 2, Hi, Wi, 24, out.slice(8, 24).vp(), Ho, Wo, 40, 0, cx.stream)
+    assert rel(out.t[..., 8:32].float().permute(0, 3, 1, 2), y_ref.detach()) < 4e-3
+    dy = bf(torch.randn(2, 24, Ho, Wo, device="cuda", generator=g))
+    y_ref.backward(dy)
+    dx = cx.new(2, Hi, Wi, 24)
+    dya = nhwc_act(eng, dy)
+    L.call("s2r_upsample_bilinear_nhwc_bwd", dya.vp(), 24, 0, 2, Hi, Wi, 24, Ho, Wo, dx.vp(), cx.stream)
+    assert rel(to_nchw(dx), xr.grad) < 4e-3
+    # NHWC bf16 (19 of 24 channels) -> NCHW fp32 and its backward
+    y = torch.empty(2, 19, Ho, Wo, device="cuda")
+    L.call("s2r_upsample_bilinear_nhwc_to_nchw", xa.vp(), 24, 2, Hi, Wi, 19, C.c_void_p(y.data_ptr()), Ho, Wo, cx.stream)
+    assert rel(y, y_ref.detach()[:, :19]) < 1e-5
+    gin = torch.randn(2, 19, Ho, Wo, device="cuda", generator=g)
+    xr2 = x[:, :19].clone().requires_grad_(True)
+    F.interpolate(xr2, size=(Ho, Wo), mode='bilinear', align_corners=True).backward(gin)
+    dx2 = cx.new(2, Hi, Wi, 24)
+    L.call("s2r_upsample_bilinear_nchw_bwd_to_nhwc", C.c_void_p(gin.data_ptr()), 2, 19, Ho, Wo, dx2.vp(), 24, Hi, Wi,
+           cx.stream)
+    assert rel(to_nchw(dx2, 19), xr2.grad) < 4e-3
+    assert float(dx2.t[..., 19:].abs().sum()) == 0.0
+
+
+def test_avgpool_broadcast_layout(eng, cx):
+    L = sub("_lib")
+    x = bf(torch.randn(3, 320, 7, 9, device="cuda"))
+    xa = nhwc_act(eng, x)
+    pooled = cx.new(3, 1, 1, 320)
+    L.call("s2r_avgpool_nhwc", xa.vp(), 3, 63, 320, 320, 0, 1.0 / 63, pooled.vp(), None, cx.stream)
+    assert rel(to_nchw(pooled), x.mean((2, 3), keepdim=True)) < 4e-3
+    dst = cx.new(3, 7, 9, 320, zero=True)
+    L.call("s2r_broadcast_nhwc", pooled.vp(), 3, 63, 320, 2.0, 0, dst.vp(), 320, 0, cx.stream)
+    L.call("s2r_broadcast_nhwc", pooled.vp(), 3, 63, 320, 1.0, 1, dst.vp(), 320, 0, cx.stream)
+    assert rel(to_nchw(dst), 3 * x.mean((2, 3), keepdim=True).expand_as(x)) < 8e-3
+    rt = sub("runtime")
+    y = torch.randn(2, 19, 5, 6, device="cuda")
+    a = rt.to_nhwc(cx, y)
+    assert a.pitch == 24 and float(a.t[..., 19:].abs().sum()) == 0.0
+    assert rel(rt.to_nchw(cx, a), bf(y)) == 0.0
+
+
+def test_softmax_dim0_ce_bce(eng):
+    fn = sub("functional")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(4, 19, 13, 21, device="cuda", generator=g, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    y, yr = fn.softmax_dim0(x), F.softmax(xr, dim=0)
+    assert rel(y.detach(), yr.detach()) < 1e-6
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    yr.backward(gy)
+    assert rel(x.grad, xr.grad) < 1e-5
+    # cross entropy with ignore index, float targets and class weights
+    for wgt in (None, torch.rand(19, device="cuda", generator=g) + 0.5):
+        lab = torch.randint(0, 20, (4, 13, 21), device="cuda", generator=g).float()
+        lab[lab == 19] = 255
+        x1 = torch.randn(4, 19, 13, 21, device="cuda", generator=g, requires_grad=True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        l1 = fn.cross_entropy(x1, lab, weight=wgt) * 1.7
+        l2 = F.cross_entropy(x2, lab.long(), weight=wgt, ignore_index=255) * 1.7
+        assert abs(l1.item() - l2.item()) < 1e-5 * abs(l2.item())
+        l1.backward()
+        l2.backward()
+        assert rel(x1.grad, x2.grad) < 1e-5
+    # odd spatial size (scalar path)
+    lab = torch.randint(0, 19, (2, 5, 7), device="cuda", generator=g).float()
+    x1 = torch.randn(2, 19, 5, 7, device="cuda", generator=g)
+    assert abs(fn.cross_entropy(x1, lab).item() - F.cross_entropy(x1, lab.long()).item()) < 1e-5
+    # BCE with logits vs constant targets
+    for t in (0.0, 1.0):
+        d1 = torch.randn(8, 1, 16, 32, device="cuda", generator=g, requires_grad=True)
+        d2 = d1.detach().clone().requires_grad_(True)
+        b1 = fn.bce_with_logits(d1, t)
+        b2 = F.binary_cross_entropy_with_logits(d2, torch.full_like(d2, t))
+        assert abs(b1.item() - b2.item()) < 1e-6
+        b1.backward()
+        b2.backward()
+        assert rel(d1.grad, d2.grad) < 1e-5
+
+
+def test_domain_loss_known_answer():
+    """utils/loss.py:80-87 of the reference: loss = 2 ln(1+e^-1) = 0.626523, accuracy 1.0."""
+    crit = sub("utils.loss").DomainLosses().build_loss()
+    a, b = torch.ones(1, 1, 7, 7).cuda(), torch.zeros(1, 1, 7, 7).cuda()
+    loss, acc = crit(torch.cat([a, b], 1), torch.cat([b, a], 1))
+    assert abs(loss.item() - 0.626523) < 1e-5 and acc == 1.0
+    with pytest.raises(AssertionError):
+        crit(torch.zeros(1, 2, 3, 3).cuda(), torch.zeros(1, 2, 3, 4).cuda())
+
+
+def test_evaluator_bit_exact():
+    fix = golden('evaluator')
+    Ev = sub("utils.metrics").Evaluator
+    ev = Ev(19)
+    ev.add_batch(fix['gt'], fix['pred'])
+    ev.add_batch(fix['gt'][:, ::-1].copy(), fix['pred'])
+    assert np.array_equal(ev.confusion_matrix, fix['cm'])
+    miou, iou = ev.Mean_Intersection_over_Union()
+    assert miou == float(fix['mIoU']) and np.array_equal(iou, fix['IoU'])
+    assert ev.Pixel_Accuracy() == float(fix['PA']) and ev.Pixel_Accuracy_Class() == float(fix['mPA'])
+    assert ev.Frequency_Weighted_Intersection_over_Union() == float(fix['fwIoU'])
+    ev.reset()
+    assert ev.confusion_matrix.sum() == 0
+    # full-size image (1024x2048), labels as float with 255 = ignore, both entry points
+    rng = np.random.RandomState(3)
+    gt = rng.randint(0, 20, size=(1, 1024, 2048)).astype(np.float32)
+    gt[gt == 19] = 255
+    logits = torch.randn(1, 19, 1024, 2048, generator=torch.Generator().manual_seed(4))
+    pred = np.argmax(logits.numpy(), axis=1)
+    want = O.confusion_matrix(gt, pred, 19)
+    ev.add_batch(gt, pred)
+    assert np.array_equal(ev.confusion_matrix, want)
+    ev.reset()
+    ev.add_batch_logits(torch.from_numpy(gt).cuda(), logits.cuda())
+    assert np.array_equal(ev.confusion_matrix, want)
+    assert int(ev.confusion_matrix.sum()) == int(((gt >= 0) & (gt < 19)).sum())   # checksum property
+    # edge cases: empty, all ignored, ragged size, int64 labels, out-of-range prediction
+    ev.reset()
+    ev.add_batch(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.int64))
+    ev.add_batch(np.full((3, 5), 255, np.float32), np.zeros((3, 5), np.int64))
+    assert ev.confusion_matrix.sum() == 0
+    g2 = rng.randint(0, 19, size=(1, 7, 13)).astype(np.int64)
+    p2 = rng.randint(0, 19, size=(1, 7, 13)).astype(np.int64)
+    ev.add_batch(g2, p2)
+    assert np.array_equal(ev.confusion_matrix, O.confusion_matrix(g2, p2, 19))
+    with pytest.raises(AssertionError):
+        ev.add_batch(np.zeros((2, 2)), np.zeros((2, 3)))
+    ev.add_batch(np.zeros((1, 1), np.float32), np.full((1, 1), 19, np.int64))
+    with pytest.raises(ValueError):
+        ev.confusion_matrix
+
+
+def test_fused_optimizers_match_torch():
+    opt = sub("optim")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    shapes = [(32, 3, 3, 3), (32,), (96, 16, 1, 1), (1000, 77), (5,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    mine = opt.FusedSGD([{'params': ps[:2], 'lr': 0.01}, {'params': ps[2:], 'lr': 0.1}], lr=0.01, momentum=0.9,
+                        weight_decay=5e-4)
+    ref = torch.optim.SGD([{'params': qs[:2], 'lr': 0.01}, {'params': qs[2:], 'lr': 0.1}], lr=0.01, momentum=0.9,
+                          weight_decay=5e-4)
+    for it in range(4):
+        mine.zero_grad()
+        ref.zero_grad()
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, device="cuda", generator=g)
+            p.grad.add_(gr)
+            q.grad = gr.clone()
+        for o in (mine, ref):
+            o.param_groups[0]['lr'] = 0.01 * (1 - it / 10)
+            o.param_groups[1]['lr'] = 0.1 * (1 - it / 10)
+        mine.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        assert rel(p.detach(), q.detach()) < 1e-6
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    mine = opt.FusedAdam(ps, lr=1e-3, betas=(0.9, 0.99))
+    ref = torch.optim.Adam(qs, lr=1e-3, betas=(0.9, 0.99))
+    for it in range(5):
+        mine.zero_grad()
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, device="cuda", generator=g)
+            p.grad.add_(gr)
+            q.grad = gr.clone()
+        mine.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        assert rel(p.detach(), q.detach()) < 1e-5
