@@ -21,6 +21,23 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+# Optional hooks used by tests/tools/layer_trace.py and the bf16-emulation parity tests:
+#   Q      rounds a tensor where the B200 path stores it in bf16 (identity = the fp32 reference);
+#   TRACE  when a list, receives (name, tensor) for the intermediate activations.
+Q = None
+TRACE = None
+
+
+def _q(t):
+    return t if Q is None else Q(t)
+
+
+def _tr(name, t):
+    if TRACE is not None:
+        TRACE.append((name, t.detach()))
+    return t
+
+
 MNV2_TABLE = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
               (6, 320, 1, 1))
 
@@ -80,24 +97,24 @@ def inverted_residual(sd, pre, x, inp, oup, stride, dil, expand, cfg):
     h = fixed_padding(x, dil)
     i = 0
     if expand != 1:
-        h = F.conv2d(h, sd[pre + '.conv.0.weight'])
-        h = F.relu6(batch_norm(sd, pre + '.conv.1', h, cfg))
+        h = _q(F.conv2d(h, _q(sd[pre + '.conv.0.weight'])))
+        h = F.relu6(batch_norm(sd, pre + '.conv.1', h, cfg))       # consumed by the dw prologue: not stored
         i = 3
     hidden = h.shape[1]
-    h = F.conv2d(h, sd['%s.conv.%d.weight' % (pre, i)], None, stride, 0, dil, hidden)
-    h = F.relu6(batch_norm(sd, '%s.conv.%d' % (pre, i + 1), h, cfg))
-    h = F.conv2d(h, sd['%s.conv.%d.weight' % (pre, i + 3)])
+    h = _q(F.conv2d(h, sd['%s.conv.%d.weight' % (pre, i)], None, stride, 0, dil, hidden))
+    h = _q(F.relu6(batch_norm(sd, '%s.conv.%d' % (pre, i + 1), h, cfg)))
+    h = _q(F.conv2d(h, _q(sd['%s.conv.%d.weight' % (pre, i + 3)])))
     h = batch_norm(sd, '%s.conv.%d' % (pre, i + 4), h, cfg)
-    return x + h if (stride == 1 and inp == oup) else h
+    return _q(x + h) if (stride == 1 and inp == oup) else _q(h)
 
 
 def mobilenet_forward(sd, x, cfg, output_stride=16, pre='features'):
     """modeling/backbone/mobilenet.py:119-122 -> (high, low_level_feat)."""
-    h = F.conv2d(x, sd[pre + '.0.0.weight'], None, 2, 1)
+    h = _q(F.conv2d(_q(x), _q(sd[pre + '.0.0.weight']), None, 2, 1))
     h = F.relu6(batch_norm(sd, pre + '.0.1', h, cfg))
     low = None
     for k, (inp, oup, stride, dil, t) in enumerate(mnv2_plan(output_stride), start=1):
-        h = inverted_residual(sd, '%s.%d' % (pre, k), h, inp, oup, stride, dil, t, cfg)
+        h = _tr('block%d' % k, inverted_residual(sd, '%s.%d' % (pre, k), h, inp, oup, stride, dil, t, cfg))
         if k == 3:
             low = h
     return h, low
@@ -109,15 +126,15 @@ def aspp_forward(sd, x, cfg, output_stride=16, pre='', drop=None):
     outs = []
     for k, d in enumerate(dils, start=1):
         w = sd['%saspp%d.atrous_conv.weight' % (pre, k)]
-        h = F.conv2d(x, w, None, 1, 0 if k == 1 else d, d)
-        outs.append(F.relu(batch_norm(sd, '%saspp%d.bn' % (pre, k), h, cfg)))
-    g = F.adaptive_avg_pool2d(x, 1)
-    g = F.conv2d(g, sd[pre + 'global_avg_pool.1.weight'])
-    g = F.relu(batch_norm(sd, pre + 'global_avg_pool.2', g, cfg))
+        h = _q(F.conv2d(x, _q(w), None, 1, 0 if k == 1 else d, d))
+        outs.append(_q(F.relu(batch_norm(sd, '%saspp%d.bn' % (pre, k), h, cfg))))
+    g = _q(F.adaptive_avg_pool2d(x, 1))
+    g = _q(F.conv2d(g, _q(sd[pre + 'global_avg_pool.1.weight'])))
+    g = _q(F.relu(batch_norm(sd, pre + 'global_avg_pool.2', g, cfg)))
     outs.append(F.interpolate(g, size=x.shape[2:], mode='bilinear', align_corners=True))
-    h = F.conv2d(torch.cat(outs, 1), sd[pre + 'conv1.weight'])
+    h = _q(F.conv2d(_tr('aspp_cat', torch.cat(outs, 1)), _q(sd[pre + 'conv1.weight'])))
     h = F.relu(batch_norm(sd, pre + 'bn1', h, cfg))
-    return _dropout(h, 0.5, cfg, drop)
+    return _tr('aspp_out', _q(_dropout(h, 0.5, cfg, drop)))
 
 
 def _dropout(x, p, cfg, drop):
@@ -128,15 +145,15 @@ def _dropout(x, p, cfg, drop):
 
 def decoder_forward(sd, x, low, cfg, pre='', drop=None):
     """modeling/decoder.py:34-43."""
-    l = F.conv2d(low, sd[pre + 'conv1.weight'])
-    l = F.relu(batch_norm(sd, pre + 'bn1', l, cfg))
-    x = F.interpolate(x, size=l.shape[2:], mode='bilinear', align_corners=True)
-    h = torch.cat((x, l), 1)
-    h = F.conv2d(h, sd[pre + 'last_conv.0.weight'], None, 1, 1)
-    h = _dropout(F.relu(batch_norm(sd, pre + 'last_conv.1', h, cfg)), 0.5, cfg, drop)
-    h = F.conv2d(h, sd[pre + 'last_conv.4.weight'], None, 1, 1)
-    h = _dropout(F.relu(batch_norm(sd, pre + 'last_conv.5', h, cfg)), 0.1, cfg, drop)
-    return F.conv2d(h, sd[pre + 'last_conv.8.weight'], sd[pre + 'last_conv.8.bias'])
+    l = _q(F.conv2d(low, _q(sd[pre + 'conv1.weight'])))
+    l = _q(F.relu(batch_norm(sd, pre + 'bn1', l, cfg)))
+    x = _q(F.interpolate(x, size=l.shape[2:], mode='bilinear', align_corners=True))
+    h = _tr('dec_cat', torch.cat((x, l), 1))
+    h = _q(F.conv2d(h, _q(sd[pre + 'last_conv.0.weight']), None, 1, 1))
+    h = _tr('dec_y1', _q(_dropout(F.relu(batch_norm(sd, pre + 'last_conv.1', h, cfg)), 0.5, cfg, drop)))
+    h = _q(F.conv2d(h, _q(sd[pre + 'last_conv.4.weight']), None, 1, 1))
+    h = _tr('dec_y2', _q(_dropout(F.relu(batch_norm(sd, pre + 'last_conv.5', h, cfg)), 0.1, cfg, drop)))
+    return _tr('dec_logits', _q(F.conv2d(h, _q(sd[pre + 'last_conv.8.weight']), sd[pre + 'last_conv.8.bias'])))
 
 
 def deeplab_forward(sd, x, cfg, output_stride=16, drop=None):
@@ -149,18 +166,19 @@ def deeplab_forward(sd, x, cfg, output_stride=16, drop=None):
 
 def discriminator_forward(sd, x):
     """modeling/discriminator.py:22-35."""
+    x = _q(x)
     for name in ('conv1', 'conv2', 'conv3', 'conv4'):
-        x = F.leaky_relu(F.conv2d(x, sd[name + '.weight'], sd[name + '.bias'], 2, 1), 0.2)
-    return F.conv2d(x, sd['classifier.weight'], sd['classifier.bias'], 2, 1)
+        x = _q(F.leaky_relu(F.conv2d(x, _q(sd[name + '.weight']), sd[name + '.bias'], 2, 1), 0.2))
+    return _q(F.conv2d(x, _q(sd['classifier.weight']), sd['classifier.bias'], 2, 1))
 
 
 def domain_classifier_forward(sd, x, cfg, drop=None):
     """modeling/domian.py:27-32."""
-    h = F.conv2d(x, sd['DC_adnn1.0.weight'])
-    h = _dropout(F.relu(batch_norm(sd, 'DC_adnn1.1', h, cfg)), 0.5, cfg, drop)
-    h = F.conv2d(h, sd['DC_adnn2.0.weight'], None, 1, 1)
-    h = _dropout(F.relu(batch_norm(sd, 'DC_adnn2.1', h, cfg)), 0.5, cfg, drop)
-    return F.conv2d(h, sd['DC_adnn3.weight'], sd['DC_adnn3.bias'], 1, 1)
+    h = _q(F.conv2d(_q(x), _q(sd['DC_adnn1.0.weight'])))
+    h = _q(_dropout(F.relu(batch_norm(sd, 'DC_adnn1.1', h, cfg)), 0.5, cfg, drop))
+    h = _q(F.conv2d(h, _q(sd['DC_adnn2.0.weight']), None, 1, 1))
+    h = _q(_dropout(F.relu(batch_norm(sd, 'DC_adnn2.1', h, cfg)), 0.5, cfg, drop))
+    return _q(F.conv2d(h, _q(sd['DC_adnn3.weight']), sd['DC_adnn3.bias'], 1, 1))
 
 
 def seg_cross_entropy(logit, target, weight=None, ignore_index=255):

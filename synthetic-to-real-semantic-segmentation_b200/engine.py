@@ -13,6 +13,7 @@ import torch
 from . import _lib as L
 
 BF16 = torch.bfloat16
+TRACE = None
 
 
 def _vp(t):
@@ -63,6 +64,7 @@ class Ctx:
             import torch.distributed as dist
             self.world = dist.get_world_size(sync_group)
         self.dropout = dropout
+        self.trace = TRACE  # when a list: receives (name, Act) of intermediate activations (tests/tools)
         # host-side seed stream for dropout masks (regenerated, never stored)
         self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and dropout) else 0
 
@@ -79,6 +81,11 @@ class Ctx:
 
     def f64(self, n):
         return torch.zeros(n, dtype=torch.float64, device=self.device)
+
+    def tr(self, name, act):
+        if self.trace is not None:
+            self.trace.append((name, act))
+        return act
 
     def allreduce(self, t):
         if self.world > 1:

@@ -53,7 +53,8 @@ class ASPPRun(RunBase):
         L.call("s2r_broadcast_nhwc", y5.vp(), N, H * W, 256, 1.0, 0, cat.slice(1024, 256).vp(), cat.pitch, 0,
                cx.stream)
         self.shape = (N, H, W, x.C)
-        return self.proj.forward(cx, cat)
+        cx.tr('aspp_cat', cat)
+        return cx.tr('aspp_out', self.proj.forward(cx, cat))
 
     def backward(self, cx, douts, need=None):
         dout = douts[0] if isinstance(douts, tuple) else douts

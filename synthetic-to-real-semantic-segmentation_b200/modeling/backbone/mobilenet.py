@@ -58,10 +58,10 @@ class MobileNetV2Run(RunBase):
 
     def forward(self, cx, x):
         z0, st0 = self.stem.forward_raw(cx, x)
-        h = self.blocks[0].forward(cx, z0, lazy=st0)
+        h = cx.tr('block1', self.blocks[0].forward(cx, z0, lazy=st0))
         low = None
         for i, b in enumerate(self.blocks[1:], start=1):
-            h = b.forward(cx, h)
+            h = cx.tr('block%d' % (i + 1), b.forward(cx, h))
             if i + 1 == self.n_low:
                 low = h
         self.z0_st0 = (z0, st0)

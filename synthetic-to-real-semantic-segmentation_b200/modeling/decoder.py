@@ -25,13 +25,14 @@ class DecoderRun(RunBase):
         cat = cx.new(N, H, W, 256 + 48)
         L.call("s2r_upsample_bilinear_nhwc", x.vp(), x.N, x.H, x.W, x.C, cat.vp(), H, W, cat.pitch, 0, cx.stream)
         self.low.forward(cx, low, out=cat.slice(256, 48))
-        y2 = self.c2.forward(cx, self.c1.forward(cx, cat))
+        cx.tr('dec_cat', cat)
+        y2 = cx.tr('dec_y2', self.c2.forward(cx, cx.tr('dec_y1', self.c1.forward(cx, cat))))
         ncls = self.cls.weight.shape[0]
         out = cx.new(N, H, W, round_up(ncls, 8), zero=True)
         out.C = ncls
         conv_fwd(cx, y2, self.cls.weight, out, bias=self.cls.bias)
         self.saved = (x, y2)
-        return out
+        return cx.tr('dec_logits', out)
 
     def backward(self, cx, douts, need=None):
         dlogits = douts[0] if isinstance(douts, tuple) else douts
