@@ -1,9 +1,540 @@
-// tcgen05 / TMA implicit-GEMM convolution (sm_100a).  Placeholder until the UMMA path lands:
-// reports "not handled" so s2r_conv_fwd falls through to the mma.sync tap-GEMM.
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (forward and data gradient of every dense
+// convolution on the path: pointwise expand/project, ASPP, decoder, discriminator, domain classifier).
+//
+//   out[pix][co] = epi( sum_t sum_ci  view_t[pix + d_t][ci] * W[t][co][ci] )
+//
+// Mapping
+//   * M tile = a BH x BW patch of output pixels (BH*BW = 128 rows = the 128 TMEM lanes); MT such
+//     patches per CTA share every weight tile (MT = 2 halves the weight traffic per FLOP).
+//   * A operand: one TMA box [1][BH][BW][64ch] per tap and 64-channel block, fetched from the tap's
+//     strided NHWC view with the tap offset added to the box origin; out-of-view rows/columns/
+//     channels are zero-filled by TMA, which implements padding, dilation halos, stride-2 parity
+//     views and ragged edges without any address arithmetic on the SMs.  The box lands in shared
+//     memory as 128 rows x 128 B with the 128B swizzle, i.e. the canonical K-major UMMA layout.
+//   * B operand: TMA box [1][BN][64] of the packed bf16 weights [slice][Cout_pad][Kpad].
+//   * D: fp32 accumulators in TMEM (MT*BN columns), tcgen05.mma.cta_group::1.kind::f16, M=128,
+//     N=BN, K=16 per instruction, issued by one elected thread.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue (TMEM -> registers via tcgen05.ld 32x32b, one pixel row per thread).
+//   * Epilogue: bias, per-channel BN statistics (warp butterfly transpose-reduce, then one fp64
+//     atomic per channel per CTA), activation, residual add / LeakyReLU mask, bf16 store.
+//   * mbarrier pipeline: full[s] (TMA -> MMA, expect_tx), empty[s] (tcgen05.commit -> TMA),
+//     acc_full (last commit -> epilogue).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_BK = 64;            // channels per pipeline stage (128 B of bf16: one swizzle row)
+constexpr int TC_A_BYTES = 128 * 128;  // one 128-row A sub-tile
+
+struct TcTap {
+  int map;     // index of the tensor map (view) this tap reads
+  int dh, dw;  // box origin offset
+  int wslice;
+};
+
+struct TcParams {
+  TcTap taps[S2R_MAX_TAPS];
+  int ntaps;
+  int kchunks;
+  int N, OH, OW, Cout;
+  int BW, BH, tiles_w, tiles_h;  // patch geometry
+  int n_subtiles;
+  __nv_bfloat16* out;
+  long long on, oh, ow;
+  const float* bias;
+  int act;
+  float slope;
+  int aux_mode;
+  const __nv_bfloat16* aux;
+  long long an, ah, aw;
+  double* stats;
+};
+
+struct TcMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), version 1, layout type 2
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS));
+}
+
+// warp-wide transpose-reduce: on entry lane L holds v[c] for row L, on exit v[0] of lane L is the sum over
+// the 32 rows of column L (31 shuffles)
+__device__ __forceinline__ float warp_col_sums(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+// ------------------------------------------------------------------------------------ kernel
+template <int BN, int MT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = MT * TC_A_BYTES + B_BYTES;
+  constexpr int TCOLS = tmem_cols(MT * BN);
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_sum[BN], s_sq[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int sub0 = blockIdx.x * MT;
+  const int kiters = p.ntaps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_addr(&bar_full[s]), 1);
+      mbar_init(smem_addr(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_addr(&bar_acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
+    prefetch_tmap(&maps.b);
+  }
+  if (warp == 2) tmem_alloc<TCOLS>(smem_addr(&tmem_base_slot));
+  if (p.stats)
+    for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+      s_sum[i] = 0.f;
+      s_sq[i] = 0.f;
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // decode the MT sub-tiles (BH x BW pixel patches) of this CTA
+  int t_n[MT], t_h[MT], t_w[MT];
+  bool t_ok[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    const int t = sub0 + j;
+    t_ok[j] = t < p.n_subtiles;
+    const int tt = t_ok[j] ? t : 0;
+    t_w[j] = (tt % p.tiles_w) * p.BW;
+    const int q = tt / p.tiles_w;
+    t_h[j] = (q % p.tiles_h) * p.BH;
+    t_n[j] = q / p.tiles_h;
+  }
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(smem_addr(&bar_empty[s]), ph ^ 1);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const TcTap T = p.taps[tap];
+        const uint32_t full = smem_addr(&bar_full[s]);
+        const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
+        mbar_expect_tx(full, STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+          tma_load_4d(sa + j * TC_A_BYTES, &maps.a[T.map], full, kc * TC_BK, t_w[j] + T.dw, t_h[j] + T.dh, t_n[j]);
+        tma_load_3d(sa + MT * TC_A_BYTES, &maps.b, full, kc * TC_BK, n0, T.wslice);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(smem_addr(&bar_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + MT * TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t db = umma_desc_k128(sb + k * 32);
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t da = umma_desc_k128(sa + j * TC_A_BYTES + k * 32);
+            umma_bf16(tmem_base + j * BN, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_addr(&bar_empty[s]));  // frees the stage when these MMAs retire
+      }
+      umma_commit(smem_addr(&bar_acc));
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (4 warps = 128 TMEM lanes)
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    mbar_wait(smem_addr(&bar_acc), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      const int oh_ = t_h[j] + row / p.BW, ow_ = t_w[j] + row % p.BW;
+      const bool rok = t_ok[j] && oh_ < p.OH && ow_ < p.OW;
+      __nv_bfloat16* orow = p.out + t_n[j] * p.on + oh_ * p.oh + ow_ * p.ow;
+      const __nv_bfloat16* arow = p.aux ? p.aux + t_n[j] * p.an + oh_ * p.ah + ow_ * p.aw : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.Cout) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * BN + c0), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = __uint_as_float(r[i]);
+          const int co = n0 + c0 + i;
+          if (p.bias && co < p.Cout) v[i] += __ldg(p.bias + co);
+        }
+        if (p.stats) {
+          float a[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
+          const float cs = warp_col_sums(a, lane);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] * v[i] : 0.f;
+          const float cq = warp_col_sums(a, lane);
+          atomicAdd(&s_sum[c0 + lane], cs);
+          atomicAdd(&s_sq[c0 + lane], cq);
+        }
+        if (rok) {
+          if (p.aux_mode == S2R_AUX_LEAKY_MASK) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) v[i] *= (__bfloat162float(arow[n0 + c0 + i]) > 0.f ? 1.f : p.slope);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act, p.slope);
+            if (p.aux_mode == S2R_AUX_ADD) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + c0 + i < p.Cout) v[i] += __bfloat162float(arow[n0 + c0 + i]);
+            }
+          }
+          __nv_bfloat16* dst = orow + n0 + c0;
+          if (n0 + c0 + 32 <= p.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dst + q * 8) = float_to_bf16x8(v + q * 8);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+      const int co = n0 + i;
+      if (co < p.Cout) {
+        atomicAdd(&p.stats[co], (double)s_sum[i]);
+        atomicAdd(&p.stats[p.Cout + co], (double)s_sq[i]);
+      }
+    }
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &sym, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+struct ViewKey {
+  const void* base;
+  long long sn, sh, sw;
+  int H, W;
+  bool operator==(const ViewKey& o) const {
+    return base == o.base && sn == o.sn && sh == o.sh && sw == o.sw && H == o.H && W == o.W;
+  }
+};
+
+bool encode_view(EncodeTiledFn enc, CUtensorMap* m, const ViewKey& v, int C, int N, int BW, int BH) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  // dimensions of extent 1 still need a non-zero 16-byte multiple stride
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0) strides[i] = 16;
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool encode_weights(EncodeTiledFn enc, CUtensorMap* m, const void* w, int Kpad, int Cout_pad, int nslices, int BN) {
+  cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Cout_pad, (cuuint64_t)nslices};
+  cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Kpad * 2 * (cuuint64_t)Cout_pad};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int MT, int STAGES>
+int launch_tc(const TcMaps& maps, const TcParams& p, int n_tiles_n, cudaStream_t st) {
+  constexpr int smem = STAGES * (MT * TC_A_BYTES + BN * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S2R_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(s2r_div_up(p.n_subtiles, MT), n_tiles_n);
+  conv_tc_kernel<BN, MT, STAGES><<<grid, TC_THREADS, smem, st>>>(maps, p);
+  S2R_LAUNCH_OK();
+  return 1;
+}
+
+int tc_mode() {
+  // S2R_CONV=mma forces the mma.sync path (A/B testing); default: tcgen05 where supported
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("S2R_CONV");
+    mode = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return mode;
+}
+
+}  // namespace
+
+// returns 1 when the problem was launched here, 0 when the caller should use the generic path, <0 on error
 int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
-  (void)a;
-  (void)st;
-  return 0;
+  if (!tc_mode()) return 0;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 0;
+  if (a->ntaps < 1 || a->ntaps > S2R_MAX_TAPS || a->Cin % 8 || a->Cin < 8) return 0;
+  if (a->Kpad % TC_BK || a->Cout_pad % 16 || (uintptr_t)a->w % 16 || a->Kpad < a->Cin) return 0;
+  if (a->Cout < 1 || a->N < 1 || a->OH < 1 || a->OW < 1) return 0;
+
+  // distinct views among the taps (<= 4: one per input parity)
+  ViewKey views[4];
+  int nviews = 0;
+  TcParams p;
+  int max_slice = 0;
+  for (int i = 0; i < a->ntaps; ++i) {
+    const s2r_tap& t = a->taps[i];
+    if (!t.base || (uintptr_t)t.base % 16 || t.sn % 8 || t.sh % 8 || t.sw % 8 || t.H < 1 || t.W < 1) return 0;
+    ViewKey k = {t.base, t.sn, t.sh, t.sw, t.H, t.W};
+    int m = -1;
+    for (int j = 0; j < nviews; ++j)
+      if (views[j] == k) m = j;
+    if (m < 0) {
+      if (nviews == 4) return 0;
+      views[nviews] = k;
+      m = nviews++;
+    }
+    p.taps[i].map = m;
+    p.taps[i].dh = t.dh;
+    p.taps[i].dw = t.dw;
+    p.taps[i].wslice = t.wslice;
+    if (t.wslice > max_slice) max_slice = t.wslice;
+  }
+  // pointwise problem on pixel-contiguous tensors: flatten the pixel grid to one long row so that every
+  // 128-row tile is full
+  int N = a->N, OH = a->OH, OW = a->OW;
+  long long on = a->on, oh = a->oh, ow = a->ow, an = a->an, ah = a->ah, aw = a->aw;
+  if (a->ntaps == 1 && nviews == 1 && a->taps[0].dh == 0 && a->taps[0].dw == 0 && views[0].H == OH && views[0].W == OW) {
+    const ViewKey& v = views[0];
+    const bool in_flat = v.sh == v.sw * OW && v.sn == v.sh * OH;
+    const bool out_flat = oh == ow * OW && on == oh * OH;
+    const bool aux_flat = a->aux_mode == S2R_AUX_NONE || (ah == aw * OW && an == ah * OH);
+    if (in_flat && out_flat && aux_flat && (long long)N * OH * OW < (1ll << 31)) {
+      OW = N * OH * OW;
+      OH = 1;
+      N = 1;
+      views[0].W = OW;
+      views[0].H = 1;
+      views[0].sh = views[0].sw * OW;
+      views[0].sn = views[0].sh;
+      oh = ow * OW;
+      on = oh;
+      ah = aw * OW;
+      an = ah;
+    }
+  }
+  // patch shape: BW*BH = 128, minimise the number of (partially empty) patches
+  int bestBW = 128;
+  long long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long long tiles = (long long)s2r_div_up(OW, bw) * s2r_div_up(OH, bh);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      bestBW = bw;
+    }
+  }
+  p.BW = bestBW;
+  p.BH = 128 / bestBW;
+  p.tiles_w = s2r_div_up(OW, p.BW);
+  p.tiles_h = s2r_div_up(OH, p.BH);
+  const long long nsub = (long long)N * p.tiles_w * p.tiles_h;
+  if (nsub >= (1ll << 30)) return 0;
+  p.n_subtiles = (int)nsub;
+  p.ntaps = a->ntaps;
+  p.kchunks = s2r_div_up(a->Cin, TC_BK);
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = a->Cout;
+  p.out = (__nv_bfloat16*)a->out;
+  p.on = on; p.oh = oh; p.ow = ow;
+  p.bias = a->bias; p.act = a->act; p.slope = a->slope;
+  p.aux_mode = a->aux_mode;
+  p.aux = a->aux_mode == S2R_AUX_NONE ? nullptr : (const __nv_bfloat16*)a->aux;
+  p.an = an; p.ah = ah; p.aw = aw;
+  p.stats = a->stats;
+
+  // tile width in output channels
+  int BN;
+  if (a->Cout > 128) BN = 256;
+  else if (a->Cout > 64) BN = 128;
+  else if (a->Cout > 32) BN = 64;
+  else BN = 32;
+  if (a->Cout_pad < BN && a->Cout_pad % BN) {
+    // the weight box may run past Cout_pad: TMA zero-fills, nothing to do
+  }
+  TcMaps maps;
+  for (int i = 0; i < 4; ++i) {
+    const ViewKey& v = views[i < nviews ? i : 0];
+    if (!encode_view(enc, &maps.a[i], v, a->Cin, N, p.BW, p.BH)) {
+      s2r_set_error("conv_tc: cuTensorMapEncodeTiled failed for view %d", i);
+      return 0;
+    }
+  }
+  if (!encode_weights(enc, &maps.b, a->w, a->Kpad, a->Cout_pad, max_slice + 1, BN)) return 0;
+  const int ntn = s2r_div_up(a->Cout, BN);
+  // two M sub-tiles per CTA when the problem is big enough to still fill the machine
+  const bool big = nsub >= 2ll * s2r_sm_count() * 2;
+  switch (BN) {
+    case 256: return big ? launch_tc<256, 2, 3>(maps, p, ntn, st) : launch_tc<256, 1, 4>(maps, p, ntn, st);
+    case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 4>(maps, p, ntn, st);
+    case 64: return launch_tc<64, 1, 4>(maps, p, ntn, st);
+    default: return launch_tc<32, 1, 4>(maps, p, ntn, st);
+  }
 }
