@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     return ap.parse_args()
 
 
@@ -238,14 +239,25 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), L.launches - l0
 
+    use_graph = not args.no_graph
+    launches_per_step = 0
+    if use_graph:
+        l0 = L.launches
+        step.capture(d_src, d_lab, d_tgt, warmup=1)
+        launches_per_step = (L.launches - l0) // 2          # one warm-up step + the captured step
+        run = step.replay
+    else:
+        run = step
+
     def resident(i):
-        return step(d_src, d_lab, d_tgt, i=i, epoch=0)
+        return run(d_src, d_lab, d_tgt, i=i, epoch=0)
 
     def end_to_end(i):
-        s = h_src.to(dev, non_blocking=True)
-        lb = h_lab.to(dev, non_blocking=True)
-        t = h_tgt.to(dev, non_blocking=True)
-        out = step(s, lb, t, i=i, epoch=0)
+        if use_graph:
+            out = step.replay(h_src, h_lab, h_tgt, i=i, epoch=0)   # pinned host -> static device buffers
+        else:
+            out = step(h_src.to(dev, non_blocking=True), h_lab.to(dev, non_blocking=True),
+                       h_tgt.to(dev, non_blocking=True), i=i, epoch=0)
         return torch.stack([out['loss_seg'], out['loss_adv'], out['loss_D_src'], out['loss_D_tgt']]).cpu()
 
     for k in range(args.warmup):
@@ -269,11 +281,11 @@ def run_b200(args):
         "config": {"workload": "AdaptSegNet output-space adaptation step (train_adapt.py:126-181): DeepLabV3+ MNv2 OS16 "
                                "+ FCDiscriminator, src+tgt %dx%d crops, batch %d/GPU, SGD+Adam, random init" % (H, W, B),
                    "pairs_per_step_per_gpu": B, "parallelism": "dp%d" % world, "sync_bn": world > 1,
-                   "dropout": not args.no_dropout,
+                   "dropout": not args.no_dropout, "cuda_graph": use_graph,
                    "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_src.numel() * 4 * 2 + h_lab.numel() * 4),
                 "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+        "gpu_launches": launches_per_step * args.steps if use_graph else launches,
         "clocks": clk.summary(),
         "roofline": roof,
     }

@@ -146,18 +146,23 @@ int s2r_bn_finalize(const double* sums, double count, const float* gamma, const 
 int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* mean_invstd,
                             float* scale_shift, int C, s2r_stream_t stream);
-/* y = dropout(act(x*scale + shift)) + residual */
+/* y = dropout(act(x*scale + shift)) + residual.  The dropout mask is a pure function of
+ * (seed + *seed_dev, element index); seed_dev (device, may be NULL) lets a captured CUDA graph
+ * draw a fresh mask on every replay. */
 int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
                      const float* scale_shift, int act, const void* residual, float drop_p,
-                     uint64_t seed, void* y, int ypitch, int yoff, s2r_stream_t stream);
+                     uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch, int yoff,
+                     s2r_stream_t stream);
 int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch, int xoff,
                       const float* mean_invstd, const float* scale_shift, int act, float drop_p,
-                      uint64_t seed, int64_t P, int C, double* dsums, s2r_stream_t stream);
+                      uint64_t seed, const uint64_t* seed_dev, int64_t P, int C, double* dsums,
+                      s2r_stream_t stream);
 /* dx = scale*(dy' - mean(dy') - xhat*mean(dy' xhat)); count<=0: frozen statistics.
  * win_pad > 0: dy is the interior window of a [N][win_H+2pad][win_W+2pad] pixel grid. */
 int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const void* x, int xpitch, int xoff,
                      const float* mean_invstd, const float* scale_shift, int act, float drop_p,
-                     uint64_t seed, const double* dsums, double count, int64_t P, int C, void* dx,
+                     uint64_t seed, const uint64_t* seed_dev, const double* dsums, double count, int64_t P,
+                     int C, void* dx,
                      int dxpitch, int dxoff, float* dgamma /* += */, float* dbeta /* += */, int win_H, int win_W,
                      int win_pad, s2r_stream_t stream);
 

@@ -59,9 +59,9 @@ PROTOTYPES = {
     "s2r_channel_sums_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "s2r_bn_finalize": [vp, f64, vp, vp, f32, i32, f32, vp, vp, vp, vp, i32, vp],
     "s2r_bn_eval_scale_shift": [vp, vp, vp, vp, f32, vp, vp, i32, vp],
-    "s2r_bn_apply_act": [vp, i64, i32, i32, i32, vp, i32, vp, f32, u64, vp, i32, i32, vp],
-    "s2r_bn_bwd_reduce": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, i64, i32, vp, vp],
-    "s2r_bn_bwd_apply": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, f64, i64, i32, vp,
+    "s2r_bn_apply_act": [vp, i64, i32, i32, i32, vp, i32, vp, f32, u64, vp, vp, i32, i32, vp],
+    "s2r_bn_bwd_reduce": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, i64, i32, vp, vp],
+    "s2r_bn_bwd_apply": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, vp, f64, i64, i32, vp,
                          i32, i32, vp, vp, i32, i32, i32, vp],
     "s2r_upsample_bilinear_nhwc": [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp],
     "s2r_upsample_bilinear_nhwc_bwd": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],

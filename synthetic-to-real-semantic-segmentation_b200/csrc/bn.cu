@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
                 const float* __restrict__ scale_shift, int act,
                 const __nv_bfloat16* __restrict__ residual, float drop_p, unsigned long long seed,
-                __nv_bfloat16* __restrict__ y, int ypitch, int yoff) {
+                const unsigned long long* __restrict__ seed_dev, __nv_bfloat16* __restrict__ y, int ypitch,
+                int yoff) {
+  if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const long long total = P * cg;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -180,8 +182,9 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
                                      const __nv_bfloat16* __restrict__ x, int xpitch, int xoff,
                                      const float* __restrict__ mean_invstd,
                                      const float* __restrict__ scale_shift, int act, float drop_p,
-                                     unsigned long long seed, long long P, int C, int rows,
-                                     double* __restrict__ dsums) {
+                                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                                     long long P, int C, int rows, double* __restrict__ dsums) {
+  if (seed_dev) seed += *seed_dev;
   extern __shared__ float sm[];
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -213,9 +216,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
                     const __nv_bfloat16* __restrict__ x, int xpitch, int xoff,
                     const float* __restrict__ mean_invstd, const float* __restrict__ scale_shift,
                     int act, float drop_p, unsigned long long seed,
+                    const unsigned long long* __restrict__ seed_dev,
                     const double* __restrict__ dsums, double count, long long P, int C,
                     __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff, int win_H, int win_W,
                     int win_pad) {
+  if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const long long total = P * cg;
   const float inv_n = count > 0 ? (float)(1.0 / count) : 0.f;
@@ -303,8 +308,8 @@ extern "C" int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, co
 
 extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
                                 const float* scale_shift, int act, const void* residual,
-                                float drop_p, uint64_t seed, void* y, int ypitch, int yoff,
-                                s2r_stream_t stream) {
+                                float drop_p, uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch,
+                                int yoff, s2r_stream_t stream) {
   S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8", C);
   S2R_REQUIRE(vec_ok(x, xpitch, xoff) && vec_ok(y, ypitch, yoff) && vec_ok(residual, 8, 0) &&
                   ((uintptr_t)scale_shift % 16 == 0),
@@ -314,15 +319,16 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
   const long long total = (long long)P * (C / 8);
   bn_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
-      (const __nv_bfloat16*)residual, drop_p, seed, (__nv_bfloat16*)y, ypitch, yoff);
+      (const __nv_bfloat16*)residual, drop_p, seed, (const unsigned long long*)seed_dev, (__nv_bfloat16*)y, ypitch,
+      yoff);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
 
 extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,
                                  int xoff, const float* mean_invstd, const float* scale_shift, int act,
-                                 float drop_p, uint64_t seed, int64_t P, int C, double* dsums,
-                                 s2r_stream_t stream) {
+                                 float drop_p, uint64_t seed, const uint64_t* seed_dev, int64_t P, int C,
+                                 double* dsums, s2r_stream_t stream) {
   S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 4096, S2R_ERR_SHAPE, "bn_bwd_reduce: C=%d", C);
   S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) &&
                   ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
@@ -332,15 +338,15 @@ extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const v
   size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
   bn_bwd_reduce_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
-      scale_shift, act, drop_p, seed, P, C, cfg.rows, dsums);
+      scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, P, C, cfg.rows, dsums);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
 
 extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,
                                 int xoff, const float* mean_invstd, const float* scale_shift, int act,
-                                float drop_p, uint64_t seed, const double* dsums, double count,
-                                int64_t P, int C, void* dx, int dxpitch, int dxoff, float* dgamma,
+                                float drop_p, uint64_t seed, const uint64_t* seed_dev, const double* dsums,
+                                double count, int64_t P, int C, void* dx, int dxpitch, int dxoff, float* dgamma,
                                 float* dbeta, int win_H, int win_W, int win_pad, s2r_stream_t stream) {
   S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_bwd_apply: C=%d", C);
   S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) && vec_ok(dx, dxpitch, dxoff) &&
@@ -356,7 +362,8 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
   const long long total = (long long)P * (C / 8);
   bn_bwd_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
-      scale_shift, act, drop_p, seed, dsums, count, P, C, (__nv_bfloat16*)dx, dxpitch, dxoff, win_H,
+      scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, dsums, count, P, C, (__nv_bfloat16*)dx,
+      dxpitch, dxoff, win_H,
       win_W, win_pad);
   S2R_LAUNCH_OK();
   return S2R_OK;

@@ -18,8 +18,9 @@
 //     warps 4..7 = epilogue (TMEM -> registers via tcgen05.ld 32x32b, one pixel row per thread).
 //   * Epilogue: bias, per-channel BN statistics (warp butterfly transpose-reduce, then one fp64
 //     atomic per channel per CTA), activation, residual add / LeakyReLU mask, bf16 store.
-//   * mbarrier pipeline: full[s] (TMA -> MMA, expect_tx), empty[s] (tcgen05.commit -> TMA),
-//     acc_full (last commit -> epilogue).
+//   * Persistent CTAs (one per SM) loop over tiles.  mbarrier pipelines: full[s] (TMA -> MMA, expect_tx),
+//     empty[s] (tcgen05.commit -> TMA), acc_full[a] (last commit of a tile -> epilogue), acc_empty[a]
+//     (epilogue -> MMA): with two TMEM accumulators the epilogue of tile i overlaps the mainloop of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -169,30 +170,42 @@ __device__ __forceinline__ float warp_col_sums(float* v, int lane) {
 constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // ------------------------------------------------------------------------------------ kernel
+constexpr int TC_MAX_COUT = 1024;  // per-CTA statistics staging (channels)
+
+// Persistent: one CTA per SM walks output tiles (tile = m_tile * n_tiles + n_tile, n fastest so that CTAs
+// running side by side share the A boxes in L2).  The TMA producer runs ahead across tile boundaries, the
+// MMA issuer alternates between NACC TMEM accumulators, the epilogue warps drain one accumulator while the
+// next tile is being multiplied.
 template <int BN, int MT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = MT * TC_A_BYTES + B_BYTES;
-  constexpr int TCOLS = tmem_cols(MT * BN);
+  constexpr int ACC_COLS = MT * BN;
+  constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+  constexpr int TCOLS = tmem_cols(NACC * ACC_COLS);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[NACC], bar_acc_empty[NACC];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_sum[BN], s_sq[BN];
+  __shared__ float s_sum[TC_MAX_COUT], s_sq[TC_MAX_COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
-  const int sub0 = blockIdx.x * MT;
   const int kiters = p.ntaps * p.kchunks;
+  const int n_tiles_n = (p.Cout + BN - 1) / BN;
+  const int n_tiles_m = (p.n_subtiles + MT - 1) / MT;
+  const int total_tiles = n_tiles_m * n_tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_addr(&bar_full[s]), 1);
       mbar_init(smem_addr(&bar_empty[s]), 1);
     }
-    mbar_init(smem_addr(&bar_acc), 1);
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(smem_addr(&bar_acc_full[a]), 1);
+      mbar_init(smem_addr(&bar_acc_empty[a]), 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -201,7 +214,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   }
   if (warp == 2) tmem_alloc<TCOLS>(smem_addr(&tmem_base_slot));
   if (p.stats)
-    for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
       s_sum[i] = 0.f;
       s_sq[i] = 0.f;
     }
@@ -210,36 +223,36 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  // decode the MT sub-tiles (BH x BW pixel patches) of this CTA
-  int t_n[MT], t_h[MT], t_w[MT];
-  bool t_ok[MT];
-#pragma unroll
-  for (int j = 0; j < MT; ++j) {
-    const int t = sub0 + j;
-    t_ok[j] = t < p.n_subtiles;
-    const int tt = t_ok[j] ? t : 0;
-    t_w[j] = (tt % p.tiles_w) * p.BW;
-    const int q = tt / p.tiles_w;
-    t_h[j] = (q % p.tiles_h) * p.BH;
-    t_n[j] = q / p.tiles_h;
-  }
-
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(smem_addr(&bar_empty[s]), ph ^ 1);
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const TcTap T = p.taps[tap];
-        const uint32_t full = smem_addr(&bar_full[s]);
-        const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
-        mbar_expect_tx(full, STAGE_BYTES);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles_n, n0 = (tile - mt * n_tiles_n) * BN;
+        int t_n[MT], t_h[MT], t_w[MT];
 #pragma unroll
-        for (int j = 0; j < MT; ++j)
-          tma_load_4d(sa + j * TC_A_BYTES, &maps.a[T.map], full, kc * TC_BK, t_w[j] + T.dw, t_h[j] + T.dh, t_n[j]);
-        tma_load_3d(sa + MT * TC_A_BYTES, &maps.b, full, kc * TC_BK, n0, T.wslice);
+        for (int j = 0; j < MT; ++j) {
+          int t = mt * MT + j;
+          if (t >= p.n_subtiles) t = p.n_subtiles - 1;  // duplicate load, rows masked in the epilogue
+          t_w[j] = (t % p.tiles_w) * p.BW;
+          const int q = t / p.tiles_w;
+          t_h[j] = (q % p.tiles_h) * p.BH;
+          t_n[j] = q / p.tiles_h;
+        }
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_addr(&bar_empty[s]), ph ^ 1);
+          const int tap = k / p.kchunks, kc = k - tap * p.kchunks;
+          const TcTap T = p.taps[tap];
+          const uint32_t full = smem_addr(&bar_full[s]);
+          const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
+          mbar_expect_tx(full, STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_4d(sa + j * TC_A_BYTES, &maps.a[T.map], full, kc * TC_BK, t_w[j] + T.dw, t_h[j] + T.dh, t_n[j]);
+          tma_load_3d(sa + MT * TC_A_BYTES, &maps.b, full, kc * TC_BK, n0, T.wslice);
+        }
       }
     }
   } else if (warp == 1) {
@@ -247,98 +260,121 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(smem_addr(&bar_full[s]), ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int ab = lt % NACC;
+        const uint32_t aph = (lt / NACC) & 1;
+        mbar_wait(smem_addr(&bar_acc_empty[ab]), aph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sb = sa + MT * TC_A_BYTES;
+        const uint32_t acc = tmem_base + ab * ACC_COLS;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_addr(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_addr(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + MT * TC_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t db = umma_desc_k128(sb + k * 32);
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            const uint64_t db = umma_desc_k128(sb + kk * 32);
 #pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            const uint64_t da = umma_desc_k128(sa + j * TC_A_BYTES + k * 32);
-            umma_bf16(tmem_base + j * BN, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int j = 0; j < MT; ++j) {
+              const uint64_t da = umma_desc_k128(sa + j * TC_A_BYTES + kk * 32);
+              umma_bf16(acc + j * BN, da, db, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(smem_addr(&bar_empty[s]));  // frees the stage when these MMAs retire
         }
-        umma_commit(smem_addr(&bar_empty[s]));  // frees the stage when these MMAs retire
+        umma_commit(smem_addr(&bar_acc_full[ab]));
       }
-      umma_commit(smem_addr(&bar_acc));
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (4 warps = 128 TMEM lanes)
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    mbar_wait(smem_addr(&bar_acc), 0);
-    tc_fence_after();
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int mt = tile / n_tiles_n, n0 = (tile - mt * n_tiles_n) * BN;
+      const int ab = lt % NACC;
+      const uint32_t aph = (lt / NACC) & 1;
+      mbar_wait(smem_addr(&bar_acc_full[ab]), aph);
+      tc_fence_after();
 #pragma unroll
-    for (int j = 0; j < MT; ++j) {
-      const int oh_ = t_h[j] + row / p.BW, ow_ = t_w[j] + row % p.BW;
-      const bool rok = t_ok[j] && oh_ < p.OH && ow_ < p.OW;
-      __nv_bfloat16* orow = p.out + t_n[j] * p.on + oh_ * p.oh + ow_ * p.ow;
-      const __nv_bfloat16* arow = p.aux ? p.aux + t_n[j] * p.an + oh_ * p.ah + ow_ * p.aw : nullptr;
+      for (int j = 0; j < MT; ++j) {
+        const int t = mt * MT + j;
+        const bool tok = t < p.n_subtiles;
+        const int tt = tok ? t : 0;
+        const int tw_ = (tt % p.tiles_w) * p.BW;
+        const int q = tt / p.tiles_w;
+        const int th_ = (q % p.tiles_h) * p.BH, tn_ = q / p.tiles_h;
+        const int oh_ = th_ + row / p.BW, ow_ = tw_ + row % p.BW;
+        const bool rok = tok && oh_ < p.OH && ow_ < p.OW;
+        __nv_bfloat16* orow = p.out + tn_ * p.on + oh_ * p.oh + ow_ * p.ow;
+        const __nv_bfloat16* arow = p.aux ? p.aux + tn_ * p.an + oh_ * p.ah + ow_ * p.aw : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.Cout) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * BN + c0), r);
-        tmem_ld_wait();
-        float v[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.Cout) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * ACC_COLS + j * BN + c0), r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = __uint_as_float(r[i]);
-          const int co = n0 + c0 + i;
-          if (p.bias && co < p.Cout) v[i] += __ldg(p.bias + co);
-        }
-        if (p.stats) {
-          float a[32];
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r[i]);
+            const int co = n0 + c0 + i;
+            if (p.bias && co < p.Cout) v[i] += __ldg(p.bias + co);
+          }
+          if (p.stats) {
+            float a[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
-          const float cs = warp_col_sums(a, lane);
+            for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
+            const float cs = warp_col_sums(a, lane);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] * v[i] : 0.f;
-          const float cq = warp_col_sums(a, lane);
-          atomicAdd(&s_sum[c0 + lane], cs);
-          atomicAdd(&s_sq[c0 + lane], cq);
-        }
-        if (rok) {
-          if (p.aux_mode == S2R_AUX_LEAKY_MASK) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + c0 + i < p.Cout) v[i] *= (__bfloat162float(arow[n0 + c0 + i]) > 0.f ? 1.f : p.slope);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act, p.slope);
-            if (p.aux_mode == S2R_AUX_ADD) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n0 + c0 + i < p.Cout) v[i] += __bfloat162float(arow[n0 + c0 + i]);
+            for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] * v[i] : 0.f;
+            const float cq = warp_col_sums(a, lane);
+            if (n0 + c0 + lane < p.Cout) {
+              atomicAdd(&s_sum[n0 + c0 + lane], cs);
+              atomicAdd(&s_sq[n0 + c0 + lane], cq);
             }
           }
-          __nv_bfloat16* dst = orow + n0 + c0;
-          if (n0 + c0 + 32 <= p.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (rok) {
+            if (p.aux_mode == S2R_AUX_LEAKY_MASK) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dst + q * 8) = float_to_bf16x8(v + q * 8);
-          } else {
+              for (int i = 0; i < 32; ++i)
+                if (n0 + c0 + i < p.Cout) v[i] *= (__bfloat162float(arow[n0 + c0 + i]) > 0.f ? 1.f : p.slope);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act, p.slope);
+              if (p.aux_mode == S2R_AUX_ADD) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (n0 + c0 + i < p.Cout) v[i] += __bfloat162float(arow[n0 + c0 + i]);
+              }
+            }
+            __nv_bfloat16* dst = orow + n0 + c0;
+            if (n0 + c0 + 32 <= p.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(dst + qq * 8) = float_to_bf16x8(v + qq * 8);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
+            }
           }
         }
       }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_acc_empty[ab])) : "memory");
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (p.stats) {
-    for (int i = threadIdx.x; i < BN; i += TC_THREADS) {
-      const int co = n0 + i;
-      if (co < p.Cout) {
-        atomicAdd(&p.stats[co], (double)s_sum[i]);
-        atomicAdd(&p.stats[p.Cout + co], (double)s_sq[i]);
-      }
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+      atomicAdd(&p.stats[i], (double)s_sum[i]);
+      atomicAdd(&p.stats[p.Cout + i], (double)s_sq[i]);
     }
   }
   if (warp == 2) {
@@ -408,7 +444,8 @@ int launch_tc(const TcMaps& maps, const TcParams& p, int n_tiles_n, cudaStream_t
     S2R_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(s2r_div_up(p.n_subtiles, MT), n_tiles_n);
+  const long long tiles = (long long)s2r_div_up(p.n_subtiles, MT) * n_tiles_n;
+  const int grid = (int)(tiles < s2r_sm_count() ? tiles : s2r_sm_count());  // persistent: one CTA per SM
   conv_tc_kernel<BN, MT, STAGES><<<grid, TC_THREADS, smem, st>>>(maps, p);
   S2R_LAUNCH_OK();
   return 1;
@@ -434,6 +471,7 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
   if (a->ntaps < 1 || a->ntaps > S2R_MAX_TAPS || a->Cin % 8 || a->Cin < 8) return 0;
   if (a->Kpad % TC_BK || a->Cout_pad % 16 || (uintptr_t)a->w % 16 || a->Kpad < a->Cin) return 0;
   if (a->Cout < 1 || a->N < 1 || a->OH < 1 || a->OW < 1) return 0;
+  if (a->stats && a->Cout > TC_MAX_COUT) return 0;
 
   // distinct views among the taps (<= 4: one per input parity)
   ViewKey views[4];
@@ -529,12 +567,15 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
   }
   if (!encode_weights(enc, &maps.b, a->w, a->Kpad, a->Cout_pad, max_slice + 1, BN)) return 0;
   const int ntn = s2r_div_up(a->Cout, BN);
-  // two M sub-tiles per CTA when the problem is big enough to still fill the machine
-  const bool big = nsub >= 2ll * s2r_sm_count() * 2;
+  // two M sub-tiles per CTA (weights fetched once per 256 pixels) when the contraction is deep enough to be
+  // tensor-bound and the problem still fills the machine; otherwise one sub-tile and two TMEM accumulators so
+  // that the epilogue of a tile overlaps the loads and MMAs of the next
+  const bool deep = (long long)p.ntaps * p.kchunks >= 8;
+  const bool big = deep && nsub * ntn >= 2ll * s2r_sm_count() * 2;
   switch (BN) {
     case 256: return big ? launch_tc<256, 2, 3>(maps, p, ntn, st) : launch_tc<256, 1, 4>(maps, p, ntn, st);
-    case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 4>(maps, p, ntn, st);
-    case 64: return launch_tc<64, 1, 4>(maps, p, ntn, st);
-    default: return launch_tc<32, 1, 4>(maps, p, ntn, st);
+    case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 6>(maps, p, ntn, st);
+    case 64: return launch_tc<64, 1, 8>(maps, p, ntn, st);
+    default: return launch_tc<32, 1, 8>(maps, p, ntn, st);
   }
 }

@@ -14,6 +14,18 @@ from . import _lib as L
 
 BF16 = torch.bfloat16
 TRACE = None
+_SEED_DEV = {}
+
+
+def seed_counter(device):
+    """Per-device int64 counter added to every dropout seed on the device side; steps.py bumps it once
+    per training step with a (graph-capturable) device op so replays of a captured step draw new masks."""
+    key = (device.type, device.index)
+    t = _SEED_DEV.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _SEED_DEV[key] = t
+    return t
 
 
 def _vp(t):
@@ -64,6 +76,7 @@ class Ctx:
             import torch.distributed as dist
             self.world = dist.get_world_size(sync_group)
         self.dropout = dropout
+        self.seed_dev = seed_counter(device)
         self.trace = TRACE  # when a list: receives (name, Act) of intermediate activations (tests/tools)
         # host-side seed stream for dropout masks (regenerated, never stored)
         self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and dropout) else 0
@@ -296,7 +309,8 @@ def bn_state(cx, bn, sums, count_local):
 
 def bn_apply(cx, z, st, act, out, residual=None, drop_p=0.0, seed=0):
     L.call("s2r_bn_apply_act", z.vp(), z.P, z.C, z.pitch, 0, _vp(st.ss), act,
-           residual.vp() if residual is not None else None, float(drop_p), seed, out.vp(), out.pitch, 0,
+           residual.vp() if residual is not None else None, float(drop_p), seed, _vp(cx.seed_dev), out.vp(),
+           out.pitch, 0,
            cx.stream)
     return out
 
@@ -308,7 +322,7 @@ def bn_backward(cx, bn, dy, z, st, act, dx, drop_p=0.0, seed=0, presummed=None, 
     if presummed is None:
         sums = cx.f64(2 * Cc)
         L.call("s2r_bn_bwd_reduce", dy.vp(), dy.pitch, 0, z.vp(), z.pitch, 0, _vp(st.mi), _vp(st.ss), act,
-               float(drop_p), seed, z.P, Cc, _vp(sums), cx.stream)
+               float(drop_p), seed, _vp(cx.seed_dev), z.P, Cc, _vp(sums), cx.stream)
     else:
         sums = presummed
     sync = cx.world > 1 and getattr(bn, "_s2r_sync", False) and not st.frozen
@@ -318,7 +332,7 @@ def bn_backward(cx, bn, dy, z, st, act, dx, drop_p=0.0, seed=0, presummed=None, 
     dbeta = _vp(grad_of(bn.bias)) if bn.bias is not None and bn.bias.requires_grad else None
     wH, wW, wpad = win if win is not None else (0, 0, 0)
     L.call("s2r_bn_bwd_apply", dy.vp(), dy.pitch, 0, z.vp(), z.pitch, 0, _vp(st.mi), _vp(st.ss), act,
-           float(drop_p), seed, _vp(sums), 0.0 if st.frozen else st.count, z.P, Cc,
+           float(drop_p), seed, _vp(cx.seed_dev), _vp(sums), 0.0 if st.frozen else st.count, z.P, Cc,
            dx.vp() if dx is not None else None, dx.pitch if dx is not None else 0, 0, dgamma, dbeta, wH, wW, wpad,
            cx.stream)
     return dx

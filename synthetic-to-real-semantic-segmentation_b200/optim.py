@@ -126,8 +126,18 @@ class FusedSGD(_FusedBase):
         super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
                                       nesterov=nesterov))
 
+    def advance(self):
+        """Host half of a step: publish the current learning rates in the pinned buffers the device
+        copy reads (also at CUDA-graph replay)."""
+        for gi, g in enumerate(self.param_groups):
+            self._hyper_host[gi][0] = float(g['lr'])
+        self.steps += 1
+        WEIGHT_EPOCH[0] += 1
+
     @torch.no_grad()
-    def step(self):
+    def launch(self):
+        """Device half of a step (graph-capturable): pinned->device copy of the hyper-parameters and
+        one multi-tensor kernel per parameter group."""
         if self._tables is None:
             self._build_tables()
         with torch.cuda.device(self.device):
@@ -135,13 +145,14 @@ class FusedSGD(_FusedBase):
                 tab, n = self._tables[gi]
                 if n == 0:
                     continue
-                self._hyper_host[gi][0] = float(g['lr'])
                 self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
                 L.call("s2r_sgd_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(g['momentum']),
                        float(g['dampening']), float(g['weight_decay']), 1 if g['nesterov'] else 0,
                        float(self.grad_scale), self._stream())
-        self.steps += 1
-        WEIGHT_EPOCH[0] += 1
+
+    def step(self):
+        self.advance()
+        self.launch()
 
 
 class FusedAdam(_FusedBase):
@@ -151,22 +162,30 @@ class FusedAdam(_FusedBase):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
 
+    def advance(self):
+        self.steps += 1
+        for gi, g in enumerate(self.param_groups):
+            b1, b2 = g['betas']
+            h = self._hyper_host[gi]
+            h[0] = float(g['lr'])
+            h[1] = 1.0 - math.pow(b1, self.steps)
+            h[2] = 1.0 - math.pow(b2, self.steps)
+        WEIGHT_EPOCH[0] += 1
+
     @torch.no_grad()
-    def step(self):
+    def launch(self):
         if self._tables is None:
             self._build_tables()
-        self.steps += 1
         with torch.cuda.device(self.device):
             for gi, g in enumerate(self.param_groups):
                 tab, n = self._tables[gi]
                 if n == 0:
                     continue
                 b1, b2 = g['betas']
-                h = self._hyper_host[gi]
-                h[0] = float(g['lr'])
-                h[1] = 1.0 - math.pow(b1, self.steps)
-                h[2] = 1.0 - math.pow(b2, self.steps)
-                self._hyper_dev[gi].copy_(h, non_blocking=True)
+                self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
                 L.call("s2r_adam_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(b1), float(b2), float(g['eps']),
                        float(g['weight_decay']), float(self.grad_scale), self._stream())
-        WEIGHT_EPOCH[0] += 1
+
+    def step(self):
+        self.advance()
+        self.launch()

@@ -14,6 +14,7 @@ F.softmax(dim=0) are taken over the rank-local batch.
 """
 import torch
 
+from .engine import seed_counter
 from .functional import softmax_dim0, bce_with_logits, cross_entropy
 from .optim import FusedSGD, FusedAdam
 from .utils.loss import SegmentationLosses, DomainLosses
@@ -34,10 +35,53 @@ class AdaptStep(object):
         self.source_label, self.target_label = 0, 1
 
     def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
-        model, model_D = self.model, self.model_D
+        """One eager step.  With capture() done, use replay() instead."""
         self.scheduler(self.optimizer, i, epoch)
-        self.optimizer.zero_grad()
         self.scheduler(self.optimizer_D, i, epoch)
+        self.optimizer.advance()
+        self.optimizer_D.advance()
+        return self._device_step(src_image, src_label, tgt_image)
+
+    def capture(self, src_image, src_label, tgt_image, warmup=2):
+        """Capture the whole step (both generator passes, three discriminator passes, all backward
+        passes, gradient all-reduce and both optimizer kernels) into one CUDA graph.  Inputs are copied
+        into static buffers before each replay; learning rates and Adam bias corrections reach the
+        device through pinned buffers, dropout masks through the device seed counter."""
+        dev = src_image.device
+        self._static = tuple(torch.empty_like(t) for t in (src_image, src_label, tgt_image))
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            st.copy_(t)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for k in range(warmup):
+                self(*self._static, i=0, epoch=0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.scheduler(self.optimizer, 0, 0)
+        self.scheduler(self.optimizer_D, 0, 0)
+        self.optimizer.advance()
+        self.optimizer_D.advance()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._device_step(*self._static)
+        return self
+
+    def replay(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        self.scheduler(self.optimizer, i, epoch)
+        self.scheduler(self.optimizer_D, i, epoch)
+        self.optimizer.advance()
+        self.optimizer_D.advance()
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def _device_step(self, src_image, src_label, tgt_image):
+        model, model_D = self.model, self.model_D
+        seed_counter(src_image.device).add_(1)
+        self.optimizer.zero_grad()
         self.optimizer_D.zero_grad()
         # ---- train G; don't accumulate grads in D (train_adapt.py:140-155)
         for p in model_D.parameters():
@@ -60,8 +104,8 @@ class AdaptStep(object):
         loss_D_tgt.backward()
         self.optimizer.all_reduce_grads()
         self.optimizer_D.all_reduce_grads()
-        self.optimizer.step()
-        self.optimizer_D.step()
+        self.optimizer.launch()
+        self.optimizer_D.launch()
         return {'loss_seg': loss_seg.detach(), 'loss_adv': loss_adv.detach(), 'loss_D_src': loss_D_src.detach(),
                 'loss_D_tgt': loss_D_tgt.detach()}
 
