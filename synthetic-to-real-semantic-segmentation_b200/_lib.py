@@ -121,10 +121,28 @@ def last_error():
     return lib().s2r_last_error().decode("utf-8", "replace")
 
 
+PROFILE = None  # when a list: (name, signature, start_event, end_event) per call (tests/tools/step_profile.py)
+
+
+def _signature(name, args):
+    a = getattr(args[0], "_obj", None) if args else None
+    if a is not None and hasattr(a, "ntaps"):
+        return "taps=%d N=%d OH=%d OW=%d Cin=%d Cout=%d" % (a.ntaps, a.N, a.OH, a.OW, a.Cin, a.Cout)
+    return " ".join(str(v) for v in args if isinstance(v, int) and not isinstance(v, bool))[:60]
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point and convert a non-zero status into an exception."""
     global launches
-    rc = getattr(lib(), name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        PROFILE.append((name, _signature(name, args), e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     launches += 1
     if rc != 0:
         msg = last_error()

@@ -110,39 +110,57 @@ __global__ void bn_eval_kernel(const float* __restrict__ gamma, const float* __r
   scale_shift[C + c] = b - rm[c] * sc;
 }
 
+// Per-thread channel constants: a thread owns one group of 8 channels for its whole lifetime, so the
+// per-channel parameters are loaded once into registers (no per-element division or parameter loads).
+struct ChanConst {
+  float sc[8], sh[8], mu[8], is[8];
+};
+
+__device__ __forceinline__ void load_f8(const float* __restrict__ p, float* f) {
+  *reinterpret_cast<float4*>(f) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(f + 4) = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+
+__device__ __forceinline__ void chan_init(ChanConst& k, const float* __restrict__ scale_shift,
+                                          const float* __restrict__ mean_invstd, int C, int g) {
+  load_f8(scale_shift + g * 8, k.sc);
+  load_f8(scale_shift + C + g * 8, k.sh);
+  if (mean_invstd) {
+    load_f8(mean_invstd + g * 8, k.mu);
+    load_f8(mean_invstd + C + g * 8, k.is);
+  }
+}
+
 // y = dropout(act(x * scale + shift)) + residual
+// thread = (row slot r, channel group g); rows advance by gridDim.x * rows
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
                 const float* __restrict__ scale_shift, int act,
                 const __nv_bfloat16* __restrict__ residual, float drop_p, unsigned long long seed,
                 const unsigned long long* __restrict__ seed_dev, __nv_bfloat16* __restrict__ y, int ypitch,
-                int yoff) {
+                int yoff, int rows) {
   if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
-  const long long total = P * cg;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long p = t / cg;
-    const int g = (int)(t - p * cg);
-    float f[8], sc[8], sh[8];
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  ChanConst k;
+  chan_init(k, scale_shift, nullptr, C, g);
+  const long long step = (long long)gridDim.x * rows;
+  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += step) {
+    float f[8];
     bf16x8_to_float(ldg16(x + p * xpitch + xoff + g * 8), f);
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8));
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8) + 1);
-    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8));
-    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8) + 1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = apply_act(fmaf(f[i], sc[i], sh[i]), act, 0.f);
+    for (int i = 0; i < 8; ++i) f[i] = apply_act(fmaf(f[i], k.sc[i], k.sh[i]), act, 0.f);
     if (drop_p > 0.f) {
       float m[8];
-      dropout_scale8(seed, (unsigned long long)t, drop_p, m);
+      dropout_scale8(seed, (unsigned long long)(p * cg + g), drop_p, m);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] *= m[i];
     }
     if (residual) {
-      float r[8];
-      bf16x8_to_float(ldg16(residual + p * C + g * 8), r);
+      float rr[8];
+      bf16x8_to_float(ldg16(residual + p * C + g * 8), rr);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
+      for (int i = 0; i < 8; ++i) f[i] += rr[i];
     }
     *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(f);
   }
@@ -150,30 +168,21 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpi
 
 // effective upstream gradient through dropout and the activation:
 // dy' = dY * dropout_mask * act'(x * scale + shift)
-__device__ __forceinline__ void bn_bwd_load(const __nv_bfloat16* dy, const __nv_bfloat16* x,
-                                            const float* scale_shift, const float* mean_invstd, int C,
-                                            int g, int act, float drop_p, unsigned long long seed,
-                                            long long t, float* gdy, float* xhat) {
-  float f[8], sc[8], sh[8], mu[8], is[8];
+__device__ __forceinline__ void bn_bwd_load(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ChanConst& k,
+                                            int act, float drop_p, unsigned long long seed, long long t,
+                                            float* gdy, float* xhat) {
+  float f[8];
   bf16x8_to_float(ldg16(dy), gdy);
   bf16x8_to_float(ldg16(x), f);
-  *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8));
-  *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + g * 8) + 1);
-  *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8));
-  *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(scale_shift + C + g * 8) + 1);
-  *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean_invstd + g * 8));
-  *reinterpret_cast<float4*>(mu + 4) = __ldg(reinterpret_cast<const float4*>(mean_invstd + g * 8) + 1);
-  *reinterpret_cast<float4*>(is) = __ldg(reinterpret_cast<const float4*>(mean_invstd + C + g * 8));
-  *reinterpret_cast<float4*>(is + 4) = __ldg(reinterpret_cast<const float4*>(mean_invstd + C + g * 8) + 1);
   float m[8];
   if (drop_p > 0.f) dropout_scale8(seed, (unsigned long long)t, drop_p, m);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float pre = fmaf(f[i], sc[i], sh[i]);
+    const float pre = fmaf(f[i], k.sc[i], k.sh[i]);
     float gd = gdy[i] * act_grad(pre, act, 0.f);
     if (drop_p > 0.f) gd *= m[i];
     gdy[i] = gd;
-    xhat[i] = (f[i] - mu[i]) * is[i];
+    xhat[i] = (f[i] - k.mu[i]) * k.is[i];
   }
 }
 
@@ -188,13 +197,15 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   extern __shared__ float sm[];
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  ChanConst k;
+  chan_init(k, scale_shift, mean_invstd, C, g);
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
     float gdy[8], xh[8];
-    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
-                mean_invstd, C, g, act, drop_p, seed, p * cg + g, gdy, xh);
+    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, k, act, drop_p, seed,
+                p * cg + g, gdy, xh);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += gdy[i]; q[i] += gdy[i] * xh[i]; }
   }
@@ -203,10 +214,10 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
   __syncthreads();
   for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
-    const int gg = t / 16, k = t % 16;
+    const int gg = t / 16, kk = t % 16;
     double acc = 0;
-    for (int rr = 0; rr < rows; ++rr) acc += (double)sm[((size_t)rr * cg + gg) * 16 + k];
-    atomicAdd(&dsums[(k >> 3) * C + gg * 8 + (k & 7)], acc);
+    for (int rr = 0; rr < rows; ++rr) acc += (double)sm[((size_t)rr * cg + gg) * 16 + kk];
+    atomicAdd(&dsums[(kk >> 3) * C + gg * 8 + (kk & 7)], acc);
   }
 }
 
@@ -219,37 +230,35 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
                     const unsigned long long* __restrict__ seed_dev,
                     const double* __restrict__ dsums, double count, long long P, int C,
                     __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff, int win_H, int win_W,
-                    int win_pad) {
+                    int win_pad, int rows) {
   if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
-  const long long total = P * cg;
-  const float inv_n = count > 0 ? (float)(1.0 / count) : 0.f;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long p = t / cg;
-    const int g = (int)(t - p * cg);
-    float gdy[8], xh[8], o[8];
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  ChanConst k;
+  chan_init(k, scale_shift, mean_invstd, C, g);
+  float m1[8], m2[8];
+  const double inv_n = count > 0 ? 1.0 / count : 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m1[i] = count > 0 ? (float)(dsums[g * 8 + i] * inv_n) : 0.f;
+    m2[i] = count > 0 ? (float)(dsums[C + g * 8 + i] * inv_n) : 0.f;
+  }
+  const long long step = (long long)gridDim.x * rows;
+  const int Wp = win_W + 2 * win_pad;
+  const long long plane = (long long)win_H * win_W;
+  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += step) {
     long long pd = p;  // pixel index inside dy (interior window of a padded grid when win_pad > 0)
     if (win_pad > 0) {
-      const int w_ = (int)(p % win_W);
-      const long long q_ = p / win_W;
-      const int h_ = (int)(q_ % win_H);
-      const long long n_ = q_ / win_H;
-      pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * (win_W + 2 * win_pad) + w_ + win_pad;
+      const long long n_ = p / plane;
+      const int rem = (int)(p - n_ * plane);
+      const int h_ = rem / win_W, w_ = rem - h_ * win_W;
+      pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * Wp + w_ + win_pad;
     }
-    bn_bwd_load(dy + pd * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, scale_shift,
-                mean_invstd, C, g, act, drop_p, seed, t, gdy, xh);
+    float gdy[8], xh[8], o[8];
+    bn_bwd_load(dy + pd * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, k, act, drop_p, seed,
+                p * cg + g, gdy, xh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = g * 8 + i;
-      const float sc = __ldg(scale_shift + c);
-      float m1 = 0.f, m2 = 0.f;
-      if (count > 0) {
-        m1 = (float)dsums[c] * inv_n;
-        m2 = (float)dsums[C + c] * inv_n;
-      }
-      o[i] = sc * (gdy[i] - m1 - xh[i] * m2);
-    }
+    for (int i = 0; i < 8; ++i) o[i] = k.sc[i] * (gdy[i] - m1[i] - xh[i] * m2[i]);
     *reinterpret_cast<uint4*>(dx + p * dxpitch + dxoff + g * 8) = float_to_bf16x8(o);
   }
 }
@@ -261,6 +270,24 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ dsums, float* __
   if (c >= C) return;
   if (dbeta) dbeta[c] += (float)dsums[c];
   if (dgamma) dgamma[c] += (float)dsums[C + c];
+}
+
+// launch geometry of the element-wise kernels: threads = rows x channel groups, enough CTAs for ~16 per SM
+struct ElemCfg {
+  int rows, threads, grid;
+};
+inline ElemCfg elem_cfg(long long P, int C) {
+  ElemCfg c;
+  const int cg = C / 8;
+  c.rows = 256 / cg;
+  if (c.rows < 1) c.rows = 1;
+  c.threads = c.rows * cg;
+  long long blocks = (P + (long long)c.rows * 4 - 1) / ((long long)c.rows * 4);  // >= 4 rows per thread
+  const long long cap = (long long)s2r_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  c.grid = (int)blocks;
+  return c;
 }
 
 inline bool vec_ok(const void* p, int pitch, int off) {
@@ -310,17 +337,17 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
                                 const float* scale_shift, int act, const void* residual,
                                 float drop_p, uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch,
                                 int yoff, s2r_stream_t stream) {
-  S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8", C);
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 2048, S2R_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8 in [8,2048]", C);
   S2R_REQUIRE(vec_ok(x, xpitch, xoff) && vec_ok(y, ypitch, yoff) && vec_ok(residual, 8, 0) &&
                   ((uintptr_t)scale_shift % 16 == 0),
               S2R_ERR_SHAPE, "bn_apply: bad pitch/offset/alignment");
   S2R_REQUIRE(drop_p >= 0.f && drop_p < 1.f, S2R_ERR_SHAPE, "bn_apply: dropout p=%f", drop_p);
   if (P == 0) return S2R_OK;
-  const long long total = (long long)P * (C / 8);
-  bn_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  const ElemCfg cfg = elem_cfg(P, C);
+  bn_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
       (const __nv_bfloat16*)residual, drop_p, seed, (const unsigned long long*)seed_dev, (__nv_bfloat16*)y, ypitch,
-      yoff);
+      yoff, cfg.rows);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -348,7 +375,7 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
                                 float drop_p, uint64_t seed, const uint64_t* seed_dev, const double* dsums,
                                 double count, int64_t P, int C, void* dx, int dxpitch, int dxoff, float* dgamma,
                                 float* dbeta, int win_H, int win_W, int win_pad, s2r_stream_t stream) {
-  S2R_REQUIRE(C >= 8 && C % 8 == 0, S2R_ERR_SHAPE, "bn_bwd_apply: C=%d", C);
+  S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 2048, S2R_ERR_SHAPE, "bn_bwd_apply: C=%d must be a multiple of 8 in [8,2048]", C);
   S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) && vec_ok(dx, dxpitch, dxoff) &&
                   ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
               S2R_ERR_SHAPE, "bn_bwd_apply: bad pitch/offset/alignment");
@@ -359,12 +386,12 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
   if (P == 0 || !dx) return S2R_OK;
   S2R_REQUIRE(win_pad == 0 || (win_H >= 1 && win_W >= 1 && P % ((int64_t)win_H * win_W) == 0), S2R_ERR_SHAPE,
               "bn_bwd_apply: window %dx%d does not tile P", win_H, win_W);
-  const long long total = (long long)P * (C / 8);
-  bn_bwd_apply_kernel<<<s2r_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  const ElemCfg cfg = elem_cfg(P, C);
+  bn_bwd_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
       scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, dsums, count, P, C, (__nv_bfloat16*)dx,
       dxpitch, dxoff, win_H,
-      win_W, win_pad);
+      win_W, win_pad, cfg.rows);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -15,7 +15,8 @@
 //   * D: fp32 accumulators in TMEM (MT*BN columns), tcgen05.mma.cta_group::1.kind::f16, M=128,
 //     N=BN, K=16 per instruction, issued by one elected thread.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//     warps 4..7 = epilogue (TMEM -> registers via tcgen05.ld 32x32b, one pixel row per thread).
+//     warps 4..15 = epilogue (TMEM -> registers via tcgen05.ld 32x32b, one pixel row per thread, three
+//     warps per SM sub-partition so their dependent-instruction latencies interleave).
 //   * Epilogue: bias, per-channel BN statistics (warp butterfly transpose-reduce, then one fp64
 //     atomic per channel per CTA), activation, residual add / LeakyReLU mask, bf16 store.
 //   * Persistent CTAs (one per SM) loop over tiles.  mbarrier pipelines: full[s] (TMA -> MMA, expect_tx),
@@ -29,7 +30,8 @@
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;     // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-15: epilogue
+constexpr int TC_EPI_WARPS = 12;
 constexpr int TC_BK = 64;            // channels per pipeline stage (128 B of bf16: one swizzle row)
 constexpr int TC_A_BYTES = 128 * 128;  // one 128-row A sub-tile
 
@@ -204,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     for (int a = 0; a < NACC; ++a) {
       mbar_init(smem_addr(&bar_acc_full[a]), 1);
-      mbar_init(smem_addr(&bar_acc_empty[a]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_addr(&bar_acc_empty[a]), TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -289,9 +291,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (4 warps = 128 TMEM lanes)
-    const int ew = warp & 3;
+    // ===================================================== epilogue: 12 warps = 3 groups of 4 (128 TMEM lanes
+    // each); the (sub-tile, 32-column chunk) units of a tile are dealt round-robin to the groups so that
+    // every SM sub-partition interleaves three epilogue warps
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;         // 0..2
     const int row = ew * 32 + lane;
+    constexpr int CHUNKS = BN / 32;
+    const int act = p.act;
+    const int aux_mode = p.aux_mode;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int mt = tile / n_tiles_n, n0 = (tile - mt * n_tiles_n) * BN;
@@ -299,8 +307,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const uint32_t aph = (lt / NACC) & 1;
       mbar_wait(smem_addr(&bar_acc_full[ab]), aph);
       tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
+#pragma unroll 1
+      for (int u = grp; u < MT * CHUNKS; u += 3) {
+        const int j = u / CHUNKS, c0 = (u - j * CHUNKS) * 32;
+        if (n0 + c0 >= p.Cout) continue;
         const int t = mt * MT + j;
         const bool tok = t < p.n_subtiles;
         const int tt = tok ? t : 0;
@@ -309,57 +319,82 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int th_ = (q % p.tiles_h) * p.BH, tn_ = q / p.tiles_h;
         const int oh_ = th_ + row / p.BW, ow_ = tw_ + row % p.BW;
         const bool rok = tok && oh_ < p.OH && ow_ < p.OW;
-        __nv_bfloat16* orow = p.out + tn_ * p.on + oh_ * p.oh + ow_ * p.ow;
-        const __nv_bfloat16* arow = p.aux ? p.aux + tn_ * p.an + oh_ * p.ah + ow_ * p.aw : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= p.Cout) break;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * ACC_COLS + j * BN + c0), r);
-          tmem_ld_wait();
-          float v[32];
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * ACC_COLS + j * BN + c0), r);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = __uint_as_float(r[i]);
-            const int co = n0 + c0 + i;
-            if (p.bias && co < p.Cout) v[i] += __ldg(p.bias + co);
-          }
-          if (p.stats) {
-            float a[32];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const bool full = n0 + c0 + 32 <= p.Cout;   // warp-uniform
+        if (p.bias) {
+          if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
-            const float cs = warp_col_sums(a, lane);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] * v[i] : 0.f;
-            const float cq = warp_col_sums(a, lane);
-            if (n0 + c0 + lane < p.Cout) {
-              atomicAdd(&s_sum[n0 + c0 + lane], cs);
-              atomicAdd(&s_sq[n0 + c0 + lane], cq);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + i));
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
-          }
-          if (rok) {
-            if (p.aux_mode == S2R_AUX_LEAKY_MASK) {
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n0 + c0 + i < p.Cout) v[i] *= (__bfloat162float(arow[n0 + c0 + i]) > 0.f ? 1.f : p.slope);
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) v[i] += __ldg(p.bias + n0 + c0 + i);
+          }
+        }
+        if (p.stats) {
+          float a[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq[i] = a[i] * a[i];
+          const float cs = warp_col_sums(a, lane);
+          const float cq = warp_col_sums(sq, lane);
+          if (n0 + c0 + lane < p.Cout) {
+            atomicAdd(&s_sum[n0 + c0 + lane], cs);
+            atomicAdd(&s_sq[n0 + c0 + lane], cq);
+          }
+        }
+        if (rok) {
+          __nv_bfloat16* dst = p.out + tn_ * p.on + oh_ * p.oh + ow_ * p.ow + n0 + c0;
+          const __nv_bfloat16* asrc = p.aux ? p.aux + tn_ * p.an + oh_ * p.ah + ow_ * p.aw + n0 + c0 : nullptr;
+          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                           (asrc == nullptr || (reinterpret_cast<uintptr_t>(asrc) & 15) == 0);
+          if (aux_mode == S2R_AUX_NONE) {
+            if (act == S2R_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (act == S2R_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+            } else if (act == S2R_ACT_RELU6) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
+            }
+          } else if (vec) {
+            float av[32];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) bf16x8_to_float(ldg16(asrc + qq * 8), av + qq * 8);
+            if (aux_mode == S2R_AUX_ADD) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += av[i];
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act, p.slope);
-              if (p.aux_mode == S2R_AUX_ADD) {
+              for (int i = 0; i < 32; ++i) v[i] *= (av[i] > 0.f ? 1.f : p.slope);
+            }
+          } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (n0 + c0 + i < p.Cout) v[i] += __bfloat162float(arow[n0 + c0 + i]);
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) {
+                const float av = __bfloat162float(asrc[i]);
+                v[i] = aux_mode == S2R_AUX_ADD ? v[i] + av : v[i] * (av > 0.f ? 1.f : p.slope);
               }
-            }
-            __nv_bfloat16* dst = orow + n0 + c0;
-            if (n0 + c0 + 32 <= p.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          }
+          if (vec) {
 #pragma unroll
-              for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(dst + qq * 8) = float_to_bf16x8(v + qq * 8);
-            } else {
+            for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(dst + qq * 8) = float_to_bf16x8(v + qq * 8);
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
-            }
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
           }
         }
       }

@@ -69,7 +69,6 @@ class Ctx:
         L.require_cuda()
         self.device = device
         self.training = training
-        self.stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         self.group = sync_group
         self.world = 1
         if sync_group is not None:
@@ -80,6 +79,11 @@ class Ctx:
         self.trace = TRACE  # when a list: receives (name, Act) of intermediate activations (tests/tools)
         # host-side seed stream for dropout masks (regenerated, never stored)
         self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and dropout) else 0
+
+    @property
+    def stream(self):
+        # looked up per call: the current stream changes under torch.cuda.graph / torch.cuda.stream
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def next_seed(self):
         self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
