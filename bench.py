@@ -268,9 +268,17 @@ def run_b200(args):
     pairs = B * world
     value = pairs * args.steps / (ms * 1e-3)
     e2e = pairs * args.steps / (ms_e2e * 1e-3)
-    if rank != 0:
+    def finish():
+        # tear down without destroy_process_group(): with NCCL collectives captured in a live CUDA graph the
+        # communicator teardown can block; the ranks meet at a barrier and leave
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks = load_peaks()
     roof = dominant_kernel_roofline(torch, B, H, W, peaks)
@@ -295,8 +303,7 @@ def run_b200(args):
                                 "sample": "1 step (after 1 warm-up) of the oracle port of train_adapt.py:137-181 at batch %d, "
                                           "%dx%d, fp32, %d torch CPU threads (%.1f s/step)" % (args.cpu_batch, H, W, threads, dt)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -555,8 +555,15 @@ extern "C" int s2r_conv_fwd(const s2r_conv_args* a, s2r_stream_t stream) {
   return s2r_conv_fwd_mma(a, stream);
 }
 
+int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st);
+
 extern "C" int s2r_conv_wgrad(const s2r_wgrad_args* a, s2r_stream_t stream) {
   S2R_REQUIRE(a && a->struct_size == sizeof(s2r_wgrad_args), S2R_ERR_SHAPE, "conv_wgrad: struct size mismatch (%u vs %zu)", a ? a->struct_size : 0u, sizeof(s2r_wgrad_args));
+  S2R_REQUIRE(a->dweight != nullptr, S2R_ERR_SHAPE, "conv_wgrad: null dweight");
+  {
+    const int rc_tc = s2r_conv_wgrad_tc(a, (cudaStream_t)stream);
+    if (rc_tc != 0) return rc_tc < 0 ? rc_tc : S2R_OK;
+  }
   int rc = check_taps(a->taps, a->ntaps, (a->Cin + 7) & ~7, "conv_wgrad");
   if (rc) return rc;
   S2R_REQUIRE(a->N >= 1 && a->OH >= 1 && a->OW >= 1 && a->Cout >= 1, S2R_ERR_SHAPE, "conv_wgrad: bad shape");
