@@ -61,21 +61,34 @@ def test_deeplab_train_forward_backward_vs_reference_fixture(built_lib):
             # early layers: tight; late layers inherit the amplified activation differences
             tol = 2e-2 if ('features.0.' in k or 'features.2.' in k) else 1e-1
             assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-4, k
-    # gradients: element-wise agreement is lost with the logits (see module docstring); their norms are
-    # statistics of the same distribution and must agree
+    # gradients: element-wise agreement is lost with the logits (see module docstring), and so is the overall
+    # gradient scale reaching the backbone (it passes the image-pooling BatchNorm over 2 values and 60 batch
+    # normalisations of 70..6000 samples).  The yardstick is again the reference algorithm with bf16 storage: its
+    # conv-weight gradient norms sit 32 % (median) / 46 % (max) away from the fp32 fixture on this input (one
+    # common factor for the whole backbone: the scale of the gradient leaving ASPP).  Kernels and emulation are two
+    # draws of the same chaotic perturbation, so the kernels must stay within 2x of the emulation's deviation.  Element-wise gradient parity is asserted where it is well
+    # posed: per layer group in tests/test_gpu_blocks.py.
     norms = dict(zip([str(n) for n in fix['grad_norm_names']], fix['grad_norms']))
-    # BN scales that feed ReLU6 -> depthwise conv -> BN have an (almost) exactly zero true gradient (the next
-    # per-channel normalisation removes the scale): compare those against an absolute floor
-    # ... and so do BN shifts in front of another BN and the image-pooling branch whose BN sees two values.
-    # The convolution weights have well-conditioned gradients: compare those.
+    esd = {k: v.clone() for k, v in sd.items()}
+    for v in O.leaf_params(esd).values():
+        v.requires_grad_(True)
+    with emulate_bf16():
+        O.seg_cross_entropy(O.deeplab_forward(esd, torch.from_numpy(fix['x']), O.BNCfg(True), 16, drop=False),
+                            torch.from_numpy(fix['label'])).backward()
     floor = 1e-3 * max(norms.values())
-    dev = {k: abs(float(p.grad.double().norm()) - norms[k]) / (norms[k] + floor) for k, p in params.items()
-           if p.dim() == 4 and 'global_avg_pool' not in k}
-    worst = sorted(dev.items(), key=lambda kv: -kv[1])[:5]
-    print("largest grad-norm deviations", worst)
+    keys = [k for k, p in params.items() if p.dim() == 4 and 'global_avg_pool' not in k]
+    dev = {k: abs(float(params[k].grad.double().norm()) - norms[k]) / (norms[k] + floor) for k in keys}
+    dev_emu = {k: abs(float(esd[k].grad.double().norm()) - norms[k]) / (norms[k] + floor) for k in keys}
+    med = lambda d: sorted(d.values())[len(d) // 2]
+    worst = sorted(dev.items(), key=lambda kv: -kv[1])[:3]
+    print("grad-norm deviation from fp32: kernels median %.3f max %.3f; bf16-emulated reference median %.3f max %.3f"
+          % (med(dev), worst[0][1], med(dev_emu), max(dev_emu.values())), worst)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params.values())
-    assert worst[0][1] <= 0.35, worst
-    assert sorted(dev.values())[len(dev) // 2] <= 0.08
+    assert med(dev) <= max(2.0 * med(dev_emu), 0.1)
+    assert worst[0][1] <= 2.0 * max(dev_emu.values()), worst
+    # the last layers see almost the same activations as the reference: tight
+    for k in ('decoder.last_conv.8.weight', 'decoder.last_conv.4.weight', 'decoder.last_conv.0.weight'):
+        assert dev[k] <= 0.1, (k, dev[k])
 
 
 def test_deeplab_eval_forward_vs_fixture(built_lib):
