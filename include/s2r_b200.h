@@ -133,6 +133,13 @@ int s2r_dwconv3x3_dgrad(const void* dy, const float* w, const void* x, const flo
 int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, int in_act, int halo_const,
                         const void* dy, float* dw, int N, int H, int W, int C, int stride, int dil,
                         int pad, s2r_stream_t stream);
+/* Both gradients in one pass over dy and x (autograd of mobilenet.py:40,54 + :51-52 + :62):
+ *   g, bwd_sums as s2r_dwconv3x3_dgrad with ext = halo_const ? pad : 0;  dw (optional, fp32 [C][3][3]) +=
+ *   weight gradient as s2r_dwconv3x3_wgrad. */
+int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, const float* in_scale_shift,
+                      const float* in_mean_invstd, int in_act, int halo_const, void* g,
+                      double* bwd_sums, float* dw, int N, int H, int W, int C, int stride, int dil,
+                      int pad, s2r_stream_t stream);
 
 /* ------------------------------------------------------------------ batch norm
  * modeling/sync_batchnorm/batchnorm.py:48-78,113-125 and the F.batch_norm fallback (:50-53). */

@@ -19,6 +19,8 @@
 // The [C][3][3] fp32 filter is staged once per CTA in shared memory as [9][C].  Per-channel BN
 // statistics of the output (forward) and BN-backward sums of the input (data gradient) are kept in
 // registers per thread (its channel group is fixed) and leave the CTA as one fp64 atomic per channel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -352,12 +354,27 @@ inline int dw_smem_attr(K kernel, size_t smem) {
 
 }  // namespace
 
+// streaming stride-1 kernels (dwconv_s1.cu)
+int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
+                  int N, int H, int W, int C, cudaStream_t stream);
+int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
+                  void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
+
+static bool s1_eligible(const float* ss, int in_act, int stride, int dil, int pad, int C) {
+  return ss != nullptr && in_act == S2R_ACT_RELU6 && stride == 1 && dil == 1 && pad == 1 && C % 16 == 0 &&
+         getenv("S2R_DW_GENERIC") == nullptr;
+}
+
 extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
                                  const float* w, void* y, double* stats, int N, int H, int W, int C,
                                  int stride, int dil, int pad, s2r_stream_t stream) {
   DwGeom G;
   int rc = dw_check(x, y, N, H, W, C, stride, dil, pad, &G);
   if (rc) return rc;
+  if (s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && ((uintptr_t)in_scale_shift % 16 == 0)) {
+    rc = s2r_dw_s1_fwd(x, in_scale_shift, halo_const, w, y, stats, N, H, W, C, (cudaStream_t)stream);
+    if (rc != S2R_ERR_UNSUPPORTED) return rc;
+  }
   const int cg = C / 8;
   const int tw = pick_tw(cg, G.Wo, 1);
   const size_t smem = ((size_t)9 * C + (size_t)tw * cg * 16) * sizeof(float);
@@ -420,4 +437,28 @@ extern "C" int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, i
       (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, (const __nv_bfloat16*)dy, dw, G, tw);
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+// Fused data + weight gradient (one pass over dy and x where the streaming kernel applies, otherwise the
+// two generic kernels).  halo_const selects the reference's padded-border semantics (ext = pad).
+extern "C" int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, const float* in_scale_shift,
+                                 const float* in_mean_invstd, int in_act, int halo_const, void* g,
+                                 double* bwd_sums, float* dw, int N, int H, int W, int C, int stride, int dil,
+                                 int pad, s2r_stream_t stream) {
+  const int ext = halo_const ? pad : 0;
+  if (s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && x && (bwd_sums == nullptr || in_mean_invstd) &&
+      ((uintptr_t)in_scale_shift % 16 == 0) && (in_mean_invstd == nullptr || (uintptr_t)in_mean_invstd % 16 == 0)) {
+    DwGeom G;
+    int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
+    if (rc) return rc;
+    rc = s2r_dw_s1_bwd(dy, x, in_scale_shift, in_mean_invstd, w, ext, g, bwd_sums, dw, N, H, W, C,
+                       (cudaStream_t)stream);
+    if (rc != S2R_ERR_UNSUPPORTED) return rc;
+  }
+  if (dw) {
+    int rc = s2r_dwconv3x3_wgrad(x, in_scale_shift, in_act, halo_const, dy, dw, N, H, W, C, stride, dil, pad, stream);
+    if (rc) return rc;
+  }
+  return s2r_dwconv3x3_dgrad(dy, w, in_scale_shift ? x : nullptr, in_scale_shift, in_mean_invstd, in_act, ext, g,
+                             bwd_sums, N, H, W, C, stride, dil, pad, stream);
 }

@@ -5,33 +5,41 @@
 //
 // Why a second design: at the HBM roofline (2 B in + 2 B out per element, 23 B/clk/SM) an SM has
 // ~0.17 clk per element, i.e. ~22 issue slots per warp-row of 128 elements -- a 3x3 depthwise conv
-// with its BN prologue and its statistics is almost ALU-bound on B200.  So:
-//   * every input element is loaded from HBM once, converted once and activated once
-//     (relu6(x*sc+sh) = 6*sat(x*sc/6+sh/6): ONE FFMA.SAT, the 6 folded into the filter);
-//   * horizontal neighbours are exchanged through a 2-slot shared-memory ring as packed bf16
-//     (one STS.64 + two LDS.64 per thread and row) instead of being re-loaded and re-activated;
-//   * vertical reuse is a rolling 3x3 register window: a CTA walks DOWN a strip of TW columns x
-//     one channel chunk for `rs` rows (one barrier per row);
+// with its BN prologue and its statistics is almost issue-bound on B200.  So:
+//   * a CTA owns (one chunk of CG*4 channels) x (TW columns) and walks DOWN `rs` rows;
+//   * input rows arrive through a TMA ring (3 rows x (TW+2) columns x chunk per stage, one producer
+//     warp, full/empty mbarriers): no address arithmetic, no load instructions, no __syncthreads in
+//     the row loop, and TMA's zero fill IS the reference's zero padding of the block input
+//     (relu6(0*sc+sh) = relu6(sh) is exactly what the reference's BN+ReLU6 produce on its padded border);
+//   * relu6(x*sc+sh) = 6*sat(x*sc/6+sh/6): ONE FFMA.SAT per element, the 6 folded into the filter;
+//   * vertical reuse is input-stationary: each activated row (left, centre, right vector) is used for the
+//     three output rows it touches, whose accumulators live in registers -- no 3x3 window copy;
 //   * all multiply-adds are packed FFMA2 (fma.rn.f32x2, two channels per instruction);
-//   * global loads are register-prefetched PF rows ahead (27 KB in flight per SM).
-//   * fused backward: g = act'(pre) * sum_k dy(pos+1-k) w[k] and dw[k] += a(pos) dy(pos+1-k) use
-//     the SAME dy window, so dy and x are read once (6 B/element instead of 10 for two kernels).
-// thread = (column j, 4 consecutive channels); lane order is channel-fastest, so a warp touches
-// contiguous CG*8-byte pixel segments.  Column 0 and TW+1 of a CTA are load-only halo columns.
-#include "common.cuh"
+//   * fused backward: g = act'(pre) * sum_k dy(pos+1-k) w[k] and dw[k] += a(pos) dy(pos+1-k) share
+//     every dy operand, so dy and x are read once (6 B/element instead of 10 for two kernels).
+// thread = (column j, 4 consecutive channels); lane order is channel-fastest, so a warp stores
+// contiguous CG*8-byte pixel segments.
+#include "tma_util.cuh"
+
+using namespace s2r_tma;
 
 namespace {
 
-constexpr int PF = 6;          // rows of loads in flight per thread; multiple of 6 (ring parity x window)
-constexpr int NT_MAX = 288;    // threads per CTA
+constexpr int RB = 3;            // rows per TMA stage (= accumulator rotation period)
+constexpr int FWD_CONS = 256;    // forward: consumer threads (+ one producer warp)
+constexpr int FWD_STAGES = 4;
+constexpr int BWD_CONS = 352;    // backward: consumer threads (+ one producer warp)
+constexpr int BWD_STAGES = 4;
 
 struct S1Geom {
   int N, H, W, C;   // tensor
   int CG;           // 4-channel groups per CTA chunk (chunk = CG*4 channels)
-  int TW;           // output columns per CTA
+  int TW;           // columns per CTA
   int rs;           // rows per CTA
   int nseg;         // row segments per image
   int ext;          // backward: gradient domain extension (0 or 1)
+  int stage_bytes;  // bytes of one ring stage (padded to 128)
+  int xoff;         // backward: byte offset of the x tile inside a stage
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -41,6 +49,15 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "=f"(r.x), "=f"(r.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return r;
 }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
@@ -67,129 +84,168 @@ __device__ __forceinline__ uint2 pack4(float2 a, float2 b) {
   u.y = *reinterpret_cast<uint32_t*>(&q);
   return u;
 }
-__device__ __forceinline__ uint2 ldg8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+// a6 = sat(x*sc6 + sh6) for 4 packed bf16
+__device__ __forceinline__ void act4(uint2 raw, float2 scA, float2 scB, float2 shA, float2 shB, float2& aA, float2& aB) {
+  float2 xa, xb;
+  unpack4(raw, xa, xb);
+  aA.x = __saturatef(fmaf(xa.x, scA.x, shA.x));
+  aA.y = __saturatef(fmaf(xa.y, scA.y, shA.y));
+  aB.x = __saturatef(fmaf(xb.x, scB.x, shB.x));
+  aB.y = __saturatef(fmaf(xb.y, scB.y, shB.y));
+}
 
-// sum `nv` per-thread floats over the thread columns of a CTA (threads tid = g + CG*j share g);
-// result for (g, k) is returned to thread t = g*nv + k < CG*nv.  red: [nv][NT_MAX+1] floats.
-template <int NV>
-__device__ __forceinline__ float column_reduce(float* red, const float* v, int CG, int ncol) {
+// sum NV per-thread floats over the thread columns of a CTA (consumer threads tid = g + CG*j share g);
+// thread t = g*NV + k < CG*NV returns the total for (g, k).  red: [NV][NCONS+1] floats.  All threads call.
+template <int NV, int NCONS>
+__device__ __forceinline__ float column_reduce(float* red, const float (&v)[NV], int CG, int ncol, bool consumer) {
+  if (consumer) {
 #pragma unroll
-  for (int k = 0; k < NV; ++k) red[k * (NT_MAX + 1) + threadIdx.x] = v[k];
+    for (int k = 0; k < NV; ++k) red[k * (NCONS + 1) + threadIdx.x] = v[k];
+  }
   __syncthreads();
   float acc = 0.f;
   const int t = threadIdx.x;
   if (t < CG * NV) {
     const int g = t / NV, k = t - g * NV;
-    const float* p = red + k * (NT_MAX + 1) + g;
+    const float* p = red + k * (NCONS + 1) + g;
     for (int j = 0; j < ncol; ++j) acc += p[j * CG];
   }
   return acc;
+}
+
+// per-thread filter: w[c..c+3][9] is 36 contiguous floats (144 B, 16-byte aligned since c % 4 == 0)
+__device__ __forceinline__ void load_filter(const float* __restrict__ w, int c, float scale, float2* wA, float2* wB) {
+  float f[36];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w + c * 9) + i);
+    f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wA[k] = make_float2(scale * f[k], scale * f[9 + k]);
+    wB[k] = make_float2(scale * f[18 + k], scale * f[27 + k]);
+  }
 }
 
 // ------------------------------------------------------------------------------------ forward
 // y[oh][ow] = sum_{ky,kx} a(oh+ky-1, ow+kx-1) w[ky][kx],  a = relu6(x*sc+sh) inside the image and
 // HALO ? relu6(sh) : 0 outside.  stats += per-channel sum / sum of squares of y.
 template <bool HALO>
-__global__ void __launch_bounds__(NT_MAX, 2)
-dw_s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ss, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, S1Geom G) {
-  __shared__ uint2 ring[2][NT_MAX];
-  __shared__ float red[8 * (NT_MAX + 1)];
+__global__ void __launch_bounds__(FWD_CONS + 32, 2)
+dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
+                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+  __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
+  __shared__ float red[8 * (FWD_CONS + 1)];
   const int CG = G.CG, TWL = G.TW + 2;
-  const int g = threadIdx.x % CG, j = threadIdx.x / CG;
-  const int c = (blockIdx.x * CG + g) * 4;
+  const int ncons = G.TW * CG;                       // active consumer threads
+  const int ncw = (ncons + 31) / 32;                 // consumer warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ow0 = blockIdx.y * G.TW;
   const int n = blockIdx.z / G.nseg, seg = blockIdx.z - n * G.nseg;
-  const int oh0 = seg * G.rs, oh1 = min(oh0 + G.rs, G.H);
-  const int iw = ow0 - 1 + j;
-  const bool col_ok = j < TWL && (unsigned)iw < (unsigned)G.W;
-  const bool compute = j >= 1 && j <= G.TW && iw < G.W;
+  const int oh0 = seg * G.rs, rows = min(G.rs, G.H - oh0);
+  const int nst = (rows + 2 + RB - 1) / RB;          // stages this CTA consumes
 
-  float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
-  const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-  t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
-  const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-  float2 wA[9], wB[9];  // 6 * filter, channels (0,1) and (2,3)
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    wA[k] = make_float2(6.f * __ldg(w + (c + 0) * 9 + k), 6.f * __ldg(w + (c + 1) * 9 + k));
-    wB[k] = make_float2(6.f * __ldg(w + (c + 2) * 9 + k), 6.f * __ldg(w + (c + 3) * 9 + k));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FWD_STAGES; ++s) {
+      mbar_init(smem_addr(&bar_full[s]), 1);
+      mbar_init(smem_addr(&bar_empty[s]), ncw);
+    }
+    mbar_fence_init();
   }
+  __syncthreads();
 
-  const size_t rowp = (size_t)G.W * G.C;
-  const __nv_bfloat16* xp = x + ((size_t)n * G.H * G.W + iw) * G.C + c;   // + ih*rowp
-  __nv_bfloat16* yp = y + ((size_t)n * G.H * G.W + iw) * G.C + c;          // output column == input column
-  const int ih_first = oh0 - 1;
-  const int total = oh1 - oh0 + 2;
+  if (warp == ncw) {
+    // ---------------- producer warp
+    if (lane == 0) {
+      prefetch_tmap(&xmap);
+      for (int k = 0; k < nst; ++k) {
+        const int s = k % FWD_STAGES;
+        if (k >= FWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((k / FWD_STAGES) - 1) & 1);
+        const uint32_t full = smem_addr(&bar_full[s]);
+        mbar_expect_tx(full, (uint32_t)(RB * TWL * CG * 8));
+        tma_load_4d(smem_addr(smem + (size_t)s * G.stage_bytes), &xmap, full, blockIdx.x * CG * 4, ow0 - 1,
+                    oh0 - 1 + k * RB, n);
+      }
+    }
+  } else if (warp < ncw) {
+    // ---------------- consumers
+    const bool live = threadIdx.x < ncons;
+    const int tid = live ? threadIdx.x : 0;
+    const int g = tid % CG, j = tid / CG;
+    const int c = (blockIdx.x * CG + g) * 4;
+    const int ow = ow0 + j;
+    const bool active = live && ow < G.W;
 
-  uint2 pf[PF];
-#pragma unroll
-  for (int u = 0; u < PF; ++u) {
-    const int ih = ih_first + u;
-    pf[u] = (col_ok && u < total && (unsigned)ih < (unsigned)G.H) ? ldg8(xp + (size_t)ih * rowp) : make_uint2(0u, 0u);
-  }
-  float2 winA[3][3], winB[3][3];
-  float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) winA[a][b] = winB[a][b] = make_float2(0.f, 0.f);
+    float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+    const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
+    const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
+    load_filter(w, c, 6.f, wA, wB);
 
-  for (int r0 = 0; r0 < total; r0 += PF) {
+    const size_t rowp = (size_t)G.W * G.C;
+    __nv_bfloat16* yp = y + (((size_t)n * G.H + oh0) * G.W + min(ow, G.W - 1)) * G.C + c;
+    const bool lok = ow - 1 >= 0, rok = ow + 1 < G.W;   // !HALO: zero (not relu6(shift)) outside the image
+    float2 accA[3], accB[3];
+    float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int r = r0 + u;
-      if (r < total) {   // uniform over the CTA
-        const int ih = ih_first + r;
-        const uint2 raw = pf[u];
-        {
-          const int ihn = ih + PF;
-          pf[u] = (col_ok && r + PF < total && (unsigned)ihn < (unsigned)G.H) ? ldg8(xp + (size_t)ihn * rowp) : make_uint2(0u, 0u);
-        }
-        float2 xa, xb, aA, aB;
-        unpack4(raw, xa, xb);
-        aA.x = __saturatef(fmaf(xa.x, scA.x, shA.x));
-        aA.y = __saturatef(fmaf(xa.y, scA.y, shA.y));
-        aB.x = __saturatef(fmaf(xb.x, scB.x, shB.x));
-        aB.y = __saturatef(fmaf(xb.y, scB.y, shB.y));
+    for (int i = 0; i < 3; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+
+    for (int k = 0; k < nst; ++k) {
+      const int s = k % FWD_STAGES;
+      mbar_wait(smem_addr(&bar_full[s]), (k / FWD_STAGES) & 1);
+      const uint2* tile = reinterpret_cast<const uint2*>(smem + (size_t)s * G.stage_bytes) + j * CG + g;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int r = k * RB + u;            // input row oh0 - 1 + r
+        const uint2* rowt = tile + u * TWL * CG;
+        float2 lA, lB, cA, cB, rA, rB;
+        act4(rowt[0], scA, scB, shA, shB, lA, lB);
+        act4(rowt[CG], scA, scB, shA, shB, cA, cB);
+        act4(rowt[2 * CG], scA, scB, shA, shB, rA, rB);
         if (!HALO) {
-          if (!(col_ok && (unsigned)ih < (unsigned)G.H)) aA = aB = make_float2(0.f, 0.f);
+          const bool row_ok = (unsigned)(oh0 - 1 + r) < (unsigned)G.H;
+          if (!(row_ok && lok)) lA = lB = make_float2(0.f, 0.f);
+          if (!row_ok) cA = cB = make_float2(0.f, 0.f);
+          if (!(row_ok && rok)) rA = rB = make_float2(0.f, 0.f);
         }
-        ring[u & 1][threadIdx.x] = pack4(aA, aB);
-        __syncthreads();
-        const int sl = u % 3;
-        winA[sl][1] = aA;
-        winB[sl][1] = aB;
-        if (compute) {
-          unpack4(ring[u & 1][threadIdx.x - CG], winA[sl][0], winB[sl][0]);
-          unpack4(ring[u & 1][threadIdx.x + CG], winA[sl][2], winB[sl][2]);
-          if (r >= 2) {
-            float2 accA = make_float2(0.f, 0.f), accB = accA;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int s = (u + 1 + ky) % 3;   // row r-2+ky
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                accA = ffma2(winA[s][kx], wA[ky * 3 + kx], accA);
-                accB = ffma2(winB[s][kx], wB[ky * 3 + kx], accB);
-              }
-            }
-            *reinterpret_cast<uint2*>(yp + (size_t)(ih - 1) * rowp) = pack4(accA, accB);
-            sA = fadd2(sA, accA);
-            sB = fadd2(sB, accB);
-            qA = ffma2(accA, accA, qA);
-            qB = ffma2(accB, accB, qB);
-          }
+        // output row o = r - ky gets ky's filter row; slot of o is o % 3 (u == r % 3)
+        const int s0 = u, s1 = (u + 2) % 3, s2 = (u + 1) % 3;
+        accA[s0] = ffma2(rA, wA[2], ffma2(cA, wA[1], fmul2(lA, wA[0])));
+        accB[s0] = ffma2(rB, wB[2], ffma2(cB, wB[1], fmul2(lB, wB[0])));
+        accA[s1] = ffma2(rA, wA[5], ffma2(cA, wA[4], ffma2(lA, wA[3], accA[s1])));
+        accB[s1] = ffma2(rB, wB[5], ffma2(cB, wB[4], ffma2(lB, wB[3], accB[s1])));
+        accA[s2] = ffma2(rA, wA[8], ffma2(cA, wA[7], ffma2(lA, wA[6], accA[s2])));
+        accB[s2] = ffma2(rB, wB[8], ffma2(cB, wB[7], ffma2(lB, wB[6], accB[s2])));
+        const int o = r - 2;
+        if (o >= 0 && o < rows && active) {
+          *reinterpret_cast<uint2*>(yp + (size_t)o * rowp) = pack4(accA[s2], accB[s2]);
+          sA = fadd2(sA, accA[s2]);
+          sB = fadd2(sB, accB[s2]);
+          qA = ffma2(accA[s2], accA[s2], qA);
+          qB = ffma2(accB[s2], accB[s2], qB);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&bar_empty[s]));
+    }
+    if (stats) {
+      const float v[8] = {sA.x, sA.y, sB.x, sB.y, qA.x, qA.y, qB.x, qB.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[k * (FWD_CONS + 1) + threadIdx.x] = live ? v[k] : 0.f;
     }
   }
   if (stats) {
-    const float v[8] = {sA.x, sA.y, sB.x, sB.y, qA.x, qA.y, qB.x, qB.y};
-    const float tot = column_reduce<8>(red, v, CG, TWL);
+    __syncthreads();
     const int t = threadIdx.x;
     if (t < CG * 8) {
       const int gg = t / 8, k = t % 8;
+      const float* p = red + k * (FWD_CONS + 1) + gg;
+      float tot = 0.f;
+      for (int jj = 0; jj < G.TW; ++jj) tot += p[jj * CG];
       atomicAdd(&stats[(k >> 2) * G.C + (blockIdx.x * CG + gg) * 4 + (k & 3)], (double)tot);
     }
   }
@@ -202,122 +258,151 @@ dw_s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 //   g    = (0 < a6 < 1) ? acc : 0                                   -> stored, bf16
 //   bsums += [sum g, sum g*(x-mean)*invstd]                          (BN backward of the producer)
 //   dw[ky][kx] += 6*a6 * dy(ih+1-ky, iw+1-kx)
-__global__ void __launch_bounds__(NT_MAX, 1)
-dw_s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+// Input-stationary in dy: the dy row of step r feeds the g rows r, r-1, r-2 (filter rows 2, 1, 0) and, with
+// the a6 rows r-2, r-1, r, all nine weight-gradient taps.
+__global__ void __launch_bounds__(BWD_CONS + 32, 1)
+dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
                  const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ gout, double* __restrict__ bsums, float* __restrict__ dw, S1Geom G) {
-  __shared__ uint2 ring[2][NT_MAX];
-  __shared__ float red[12 * (NT_MAX + 1)];
+                 __nv_bfloat16* __restrict__ gout, double* __restrict__ bsums, float* __restrict__ dw, const S1Geom G) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+  __shared__ uint64_t bar_full[BWD_STAGES], bar_empty[BWD_STAGES];
+  __shared__ float red[12 * (BWD_CONS + 1)];
   const int CG = G.CG, TWL = G.TW + 2, ext = G.ext;
   const int He = G.H + 2 * ext, We = G.W + 2 * ext;
-  const int g = threadIdx.x % CG, j = threadIdx.x / CG;
-  const int c = (blockIdx.x * CG + g) * 4;
+  const int ncons = G.TW * CG;
+  const int ncw = (ncons + 31) / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e0 = blockIdx.y * G.TW;
   const int n = blockIdx.z / G.nseg, seg = blockIdx.z - n * G.nseg;
-  const int he0 = seg * G.rs, he1 = min(he0 + G.rs, He);
-  const int we = e0 - 1 + j, iw = we - ext;
-  const bool col_ok = j < TWL && (unsigned)iw < (unsigned)G.W;
-  const bool compute = j >= 1 && j <= G.TW && we < We;
+  const int he0 = seg * G.rs, rows = min(G.rs, He - he0);
+  const int ih_start = he0 - ext;                    // image row of the first g row
+  const int nst = (rows + 2 + RB - 1) / RB;
 
-  float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
-  const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-  t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
-  const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-  float2 nmuA = make_float2(0.f, 0.f), nmuB = nmuA;
-  if (mi) {
-    t4 = __ldg(reinterpret_cast<const float4*>(mi + c));
-    nmuA = make_float2(-t4.x, -t4.y);
-    nmuB = make_float2(-t4.z, -t4.w);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BWD_STAGES; ++s) {
+      mbar_init(smem_addr(&bar_full[s]), 1);
+      mbar_init(smem_addr(&bar_empty[s]), ncw);
+    }
+    mbar_fence_init();
   }
-  float2 wA[9], wB[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    wA[k] = make_float2(__ldg(w + (c + 0) * 9 + k), __ldg(w + (c + 1) * 9 + k));
-    wB[k] = make_float2(__ldg(w + (c + 2) * 9 + k), __ldg(w + (c + 3) * 9 + k));
-  }
+  __syncthreads();
+
   float2 dA[9], dB[9];
+  float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
 #pragma unroll
   for (int k = 0; k < 9; ++k) dA[k] = dB[k] = make_float2(0.f, 0.f);
+  bool live = false;
 
-  const size_t rowp = (size_t)G.W * G.C;
-  const __nv_bfloat16* dyp = dy + ((size_t)n * G.H * G.W + iw) * G.C + c;
-  const __nv_bfloat16* xp = x + ((size_t)n * G.H * G.W + iw) * G.C + c;
-  __nv_bfloat16* gp = gout + ((size_t)n * He * We + we) * G.C + c;
-  const size_t growp = (size_t)We * G.C;
-  const int ih_start = he0 - ext;          // image row of the first output row
-  const int total = he1 - he0 + 2;         // step r loads dy row ih_start-1+r and x row ih_start-2+r
+  if (warp == ncw) {
+    if (lane == 0) {
+      prefetch_tmap(&dymap);
+      prefetch_tmap(&xmap);
+      for (int k = 0; k < nst; ++k) {
+        const int s = k % BWD_STAGES;
+        if (k >= BWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((k / BWD_STAGES) - 1) & 1);
+        const uint32_t full = smem_addr(&bar_full[s]);
+        mbar_expect_tx(full, (uint32_t)(RB * (TWL + G.TW) * CG * 8));
+        unsigned char* st = smem + (size_t)s * G.stage_bytes;
+        // step r uses dy row ih_start-1+r (with one halo column per side) and x row ih_start+r
+        tma_load_4d(smem_addr(st), &dymap, full, blockIdx.x * CG * 4, e0 - ext - 1, ih_start - 1 + k * RB, n);
+        tma_load_4d(smem_addr(st + G.xoff), &xmap, full, blockIdx.x * CG * 4, e0 - ext, ih_start + k * RB, n);
+      }
+    }
+  } else if (warp < ncw) {
+    live = threadIdx.x < ncons;
+    const int tid = live ? threadIdx.x : 0;
+    const int g = tid % CG, j = tid / CG;
+    const int c = (blockIdx.x * CG + g) * 4;
+    const int we = e0 + j;
+    const bool active = live && we < We;
 
-  uint2 pfd[PF], pfx[PF];
-#pragma unroll
-  for (int u = 0; u < PF; ++u) {
-    const int dr = ih_start - 1 + u, xr = ih_start - 2 + u;
-    pfd[u] = (col_ok && u < total && (unsigned)dr < (unsigned)G.H) ? ldg8(dyp + (size_t)dr * rowp) : make_uint2(0u, 0u);
-    pfx[u] = (col_ok && u < total && u >= 2 && (unsigned)xr < (unsigned)G.H) ? ldg8(xp + (size_t)xr * rowp) : make_uint2(0u, 0u);
-  }
-  float2 winA[3][3], winB[3][3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) winA[a][b] = winB[a][b] = make_float2(0.f, 0.f);
-  float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
+    float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+    const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
+    const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    float2 nmuA = make_float2(0.f, 0.f), nmuB = nmuA;
+    if (mi) {
+      t4 = __ldg(reinterpret_cast<const float4*>(mi + c));
+      nmuA = make_float2(-t4.x, -t4.y);
+      nmuB = make_float2(-t4.z, -t4.w);
+    }
+    float2 wA[9], wB[9];
+    load_filter(w, c, 1.f, wA, wB);
 
-  for (int r0 = 0; r0 < total; r0 += PF) {
+    const size_t growp = (size_t)We * G.C;
+    __nv_bfloat16* gp = gout + (((size_t)n * He + he0) * We + min(we, We - 1)) * G.C + c;
+    float2 gA[3], gB[3], aA[3], aB[3];
+    uint2 xr[3];
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int r = r0 + u;
-      if (r < total) {
-        const uint2 rawd = pfd[u], rawx = pfx[u];
-        {
-          const int dr = ih_start - 1 + r + PF, xr = dr - 1;
-          const bool more = col_ok && r + PF < total;
-          pfd[u] = (more && (unsigned)dr < (unsigned)G.H) ? ldg8(dyp + (size_t)dr * rowp) : make_uint2(0u, 0u);
-          pfx[u] = (more && (unsigned)xr < (unsigned)G.H) ? ldg8(xp + (size_t)xr * rowp) : make_uint2(0u, 0u);
-        }
-        ring[u & 1][threadIdx.x] = rawd;
-        __syncthreads();
-        const int sl = u % 3;
-        unpack4(rawd, winA[sl][1], winB[sl][1]);
-        if (compute) {
-          unpack4(ring[u & 1][threadIdx.x - CG], winA[sl][0], winB[sl][0]);   // column iw-1
-          unpack4(ring[u & 1][threadIdx.x + CG], winA[sl][2], winB[sl][2]);   // column iw+1
-          if (r >= 2) {
-            float2 xa, xb, aA, aB;
-            unpack4(rawx, xa, xb);
-            aA.x = __saturatef(fmaf(xa.x, scA.x, shA.x));
-            aA.y = __saturatef(fmaf(xa.y, scA.y, shA.y));
-            aB.x = __saturatef(fmaf(xb.x, scB.x, shB.x));
-            aB.y = __saturatef(fmaf(xb.y, scB.y, shB.y));
-            float2 accA = make_float2(0.f, 0.f), accB = accA;
+    for (int i = 0; i < 3; ++i) {
+      gA[i] = gB[i] = aA[i] = aB[i] = make_float2(0.f, 0.f);
+      xr[i] = make_uint2(0u, 0u);
+    }
+
+    for (int k = 0; k < nst; ++k) {
+      const int s = k % BWD_STAGES;
+      mbar_wait(smem_addr(&bar_full[s]), (k / BWD_STAGES) & 1);
+      const unsigned char* st = smem + (size_t)s * G.stage_bytes;
+      const uint2* dtile = reinterpret_cast<const uint2*>(st) + j * CG + g;
+      const uint2* xtile = reinterpret_cast<const uint2*>(st + G.xoff) + j * CG + g;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int s = (u + 3 - ky) % 3;   // dy row ih+1-ky was loaded at step r-ky
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const float2 vA = winA[s][2 - kx], vB = winB[s][2 - kx];   // dy column iw+1-kx
-                accA = ffma2(vA, wA[ky * 3 + kx], accA);
-                accB = ffma2(vB, wB[ky * 3 + kx], accB);
-                dA[ky * 3 + kx] = ffma2(vA, aA, dA[ky * 3 + kx]);
-                dB[ky * 3 + kx] = ffma2(vB, aB, dB[ky * 3 + kx]);
-              }
-            }
-            accA.x = (aA.x > 0.f && aA.x < 1.f) ? accA.x : 0.f;
-            accA.y = (aA.y > 0.f && aA.y < 1.f) ? accA.y : 0.f;
-            accB.x = (aB.x > 0.f && aB.x < 1.f) ? accB.x : 0.f;
-            accB.y = (aB.y > 0.f && aB.y < 1.f) ? accB.y : 0.f;
-            *reinterpret_cast<uint2*>(gp + (size_t)(he0 + r - 2) * growp) = pack4(accA, accB);
-            sA = fadd2(sA, accA);
-            sB = fadd2(sB, accB);
-            qA = ffma2(accA, fadd2(xa, nmuA), qA);
-            qB = ffma2(accB, fadd2(xb, nmuB), qB);
-          }
+      for (int u = 0; u < RB; ++u) {
+        const int r = k * RB + u;            // dy row ih_start-1+r; g / x row o = r (relative to ih_start)
+        const uint2* drow = dtile + u * TWL * CG;
+        float2 lA, lB, cA, cB, rA, rB;       // dy at columns iw-1, iw, iw+1
+        unpack4(drow[0], lA, lB);
+        unpack4(drow[CG], cA, cB);
+        unpack4(drow[2 * CG], rA, rB);
+        const int s0 = u, s1 = (u + 2) % 3, s2 = (u + 1) % 3;   // slots of g rows r, r-1, r-2
+        // x / a6 of row o = r (zero contribution outside this CTA's rows or columns)
+        xr[s0] = xtile[u * G.TW * CG];
+        act4(xr[s0], scA, scB, shA, shB, aA[s0], aB[s0]);
+        if (!(r < rows && active)) aA[s0] = aB[s0] = make_float2(0.f, 0.f);
+        // data gradient: g row o uses dy row r = o + 2 - ky; dy column iw + 1 - kx  (kx=0: right, 2: left)
+        gA[s0] = ffma2(lA, wA[8], ffma2(cA, wA[7], fmul2(rA, wA[6])));
+        gB[s0] = ffma2(lB, wB[8], ffma2(cB, wB[7], fmul2(rB, wB[6])));
+        gA[s1] = ffma2(lA, wA[5], ffma2(cA, wA[4], ffma2(rA, wA[3], gA[s1])));
+        gB[s1] = ffma2(lB, wB[5], ffma2(cB, wB[4], ffma2(rB, wB[3], gB[s1])));
+        gA[s2] = ffma2(lA, wA[2], ffma2(cA, wA[1], ffma2(rA, wA[0], gA[s2])));
+        gB[s2] = ffma2(lB, wB[2], ffma2(cB, wB[1], ffma2(rB, wB[0], gB[s2])));
+        // weight gradient: tap (ky, kx) pairs a6 of row o = r - 2 + ky with this dy row
+        dA[0] = ffma2(rA, aA[s2], dA[0]); dB[0] = ffma2(rB, aB[s2], dB[0]);
+        dA[1] = ffma2(cA, aA[s2], dA[1]); dB[1] = ffma2(cB, aB[s2], dB[1]);
+        dA[2] = ffma2(lA, aA[s2], dA[2]); dB[2] = ffma2(lB, aB[s2], dB[2]);
+        dA[3] = ffma2(rA, aA[s1], dA[3]); dB[3] = ffma2(rB, aB[s1], dB[3]);
+        dA[4] = ffma2(cA, aA[s1], dA[4]); dB[4] = ffma2(cB, aB[s1], dB[4]);
+        dA[5] = ffma2(lA, aA[s1], dA[5]); dB[5] = ffma2(lB, aB[s1], dB[5]);
+        dA[6] = ffma2(rA, aA[s0], dA[6]); dB[6] = ffma2(rB, aB[s0], dB[6]);
+        dA[7] = ffma2(cA, aA[s0], dA[7]); dB[7] = ffma2(cB, aB[s0], dB[7]);
+        dA[8] = ffma2(lA, aA[s0], dA[8]); dB[8] = ffma2(lB, aB[s0], dB[8]);
+        const int o = r - 2;
+        if (o >= 0 && o < rows && active) {
+          float2 vA = gA[s2], vB = gB[s2];
+          const float2 mA = aA[s2], mB = aB[s2];
+          vA.x = (mA.x > 0.f && mA.x < 1.f) ? vA.x : 0.f;
+          vA.y = (mA.y > 0.f && mA.y < 1.f) ? vA.y : 0.f;
+          vB.x = (mB.x > 0.f && mB.x < 1.f) ? vB.x : 0.f;
+          vB.y = (mB.y > 0.f && mB.y < 1.f) ? vB.y : 0.f;
+          *reinterpret_cast<uint2*>(gp + (size_t)o * growp) = pack4(vA, vB);
+          float2 xa, xb;
+          unpack4(xr[s2], xa, xb);
+          sA = fadd2(sA, vA);
+          sB = fadd2(sB, vB);
+          qA = ffma2(vA, fadd2(xa, nmuA), qA);
+          qB = ffma2(vB, fadd2(xb, nmuB), qB);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&bar_empty[s]));
     }
   }
   const int t = threadIdx.x;
+  const bool consumer = t < BWD_CONS;
   if (bsums) {
-    const float v[8] = {sA.x, sA.y, sB.x, sB.y, qA.x, qA.y, qB.x, qB.y};
-    const float tot = column_reduce<8>(red, v, CG, TWL);
+    const float v[8] = {live ? sA.x : 0.f, live ? sA.y : 0.f, live ? sB.x : 0.f, live ? sB.y : 0.f,
+                        live ? qA.x : 0.f, live ? qA.y : 0.f, live ? qB.x : 0.f, live ? qB.y : 0.f};
+    const float tot = column_reduce<8, BWD_CONS>(red, v, CG, G.TW, consumer);
     if (t < CG * 8) {
       const int gg = t / 8, k = t % 8;
       const int ch = (blockIdx.x * CG + gg) * 4 + (k & 3);
@@ -333,12 +418,12 @@ dw_s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
       float v[12];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        v[k * 4 + 0] = dA[part * 3 + k].x;
-        v[k * 4 + 1] = dA[part * 3 + k].y;
-        v[k * 4 + 2] = dB[part * 3 + k].x;
-        v[k * 4 + 3] = dB[part * 3 + k].y;
+        v[k * 4 + 0] = live ? dA[part * 3 + k].x : 0.f;
+        v[k * 4 + 1] = live ? dA[part * 3 + k].y : 0.f;
+        v[k * 4 + 2] = live ? dB[part * 3 + k].x : 0.f;
+        v[k * 4 + 3] = live ? dB[part * 3 + k].y : 0.f;
       }
-      const float tot = column_reduce<12>(red, v, CG, TWL);
+      const float tot = column_reduce<12, BWD_CONS>(red, v, CG, G.TW, consumer);
       if (t < CG * 12) {
         const int gg = t / 12, k = t % 12;
         const int ch = (blockIdx.x * CG + gg) * 4 + (k & 3);
@@ -349,27 +434,52 @@ dw_s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
   }
 }
 
-// chunking: CG 4-channel groups per CTA, TW output columns, so that (TW+2)*CG <= NT_MAX
-inline bool s1_plan(int N, int H, int W, int C, int ext, S1Geom* G, dim3* grid, int* threads) {
+// chunking: CG 4-channel groups per CTA, TW columns, TW*CG <= ncons_max consumer threads
+inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stages, bool bwd, S1Geom* G, dim3* grid,
+                    int* threads, size_t* smem) {
   int CG;
   if (C % 32 == 0) CG = 8;
   else if (C % 48 == 0) CG = 12;
   else if (C % 16 == 0) CG = 4;
   else return false;
   const int He = H + 2 * ext, We = W + 2 * ext;
-  int TW = NT_MAX / CG - 2;
+  int TW = ncons_max / CG;
   const int tiles = s2r_div_up(We, TW);
   TW = s2r_div_up(We, tiles);              // balance the column tiles
+  if (TW + 2 > 256) return false;           // TMA box limit
   const int chunks = C / (CG * 4);
-  // rows per CTA: as long as possible (vertical halo = 2 rows per segment) while filling the GPU ~4x
-  int rs = 64;
-  while (rs > 8 && (long)chunks * tiles * N * s2r_div_up(He, rs) < 4L * s2r_sm_count()) rs >>= 1;
-  const int nseg = s2r_div_up(He, rs);
+  // rows per CTA: as long as possible (vertical halo = 2 rows per segment) while filling the GPU ~4x;
+  // rs + 2 is a multiple of the stage depth RB so no loaded row is wasted
+  int nseg = s2r_div_up(He, 64);
+  while ((long)chunks * tiles * N * nseg < 4L * s2r_sm_count() && He / (nseg * 2) >= 16) nseg *= 2;
+  int rs = s2r_div_up(He, nseg);
+  rs = (rs + 2 + RB - 1) / RB * RB - 2;
+  nseg = s2r_div_up(He, rs);
   if ((long)N * nseg > 65535 || tiles > 65535) return false;
   G->N = N; G->H = H; G->W = W; G->C = C; G->CG = CG; G->TW = TW; G->rs = rs; G->nseg = nseg; G->ext = ext;
+  const int dy_bytes = RB * (TW + 2) * CG * 8, x_bytes = bwd ? RB * TW * CG * 8 : 0;
+  G->xoff = (dy_bytes + 127) / 128 * 128;
+  G->stage_bytes = (G->xoff + x_bytes + 127) / 128 * 128;
   *grid = dim3(chunks, tiles, N * nseg);
-  *threads = ((TW + 2) * CG + 31) / 32 * 32;
+  *threads = (TW * CG + 31) / 32 * 32 + 32;
+  if (*threads < (CG * 12 + 31) / 32 * 32) *threads = (CG * 12 + 31) / 32 * 32;   // the final reductions use CG*12 threads
+  *smem = (size_t)stages * G->stage_bytes + 128;
   return true;
+}
+
+// static + dynamic shared memory can exceed the 48 KB default even when the dynamic part alone does not:
+// opt in once per kernel to the largest ring any plan produces
+constexpr int S1_SMEM_CAP = 160 * 1024;
+template <typename K>
+inline int s1_smem_attr(K kernel, size_t smem, int which) {
+  static bool flags[3] = {false, false, false};   // per kernel (same-signature kernels share this instantiation)
+  bool& done = flags[which];
+  S2R_REQUIRE(smem <= (size_t)S1_SMEM_CAP, S2R_ERR_UNSUPPORTED, "dwconv3x3: ring of %zu bytes exceeds the cap", smem);
+  if (!done) {
+    S2R_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM_CAP));
+    done = true;
+  }
+  return S2R_OK;
 }
 
 }  // namespace
@@ -380,11 +490,19 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
   S1Geom G;
   dim3 grid;
   int threads;
-  if (!s1_plan(N, H, W, C, 0, &G, &grid, &threads)) return S2R_ERR_UNSUPPORTED;
-  if (halo_const)
-    dw_s1_fwd_kernel<true><<<grid, threads, 0, stream>>>((const __nv_bfloat16*)x, ss, w, (__nv_bfloat16*)y, stats, G);
-  else
-    dw_s1_fwd_kernel<false><<<grid, threads, 0, stream>>>((const __nv_bfloat16*)x, ss, w, (__nv_bfloat16*)y, stats, G);
+  size_t smem;
+  if (!s1_plan(N, H, W, C, 0, FWD_CONS, FWD_STAGES, false, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+  CUtensorMap xmap;
+  if (!encode_nhwc(&xmap, x, N, H, W, C, G.CG * 4, G.TW + 2, RB)) return S2R_ERR_UNSUPPORTED;
+  if (halo_const) {
+    int rc = s1_smem_attr(dw_s1_fwd_kernel<true>, smem, 0);
+    if (rc) return rc;
+    dw_s1_fwd_kernel<true><<<grid, threads, smem, stream>>>(xmap, ss, w, (__nv_bfloat16*)y, stats, G);
+  } else {
+    int rc = s1_smem_attr(dw_s1_fwd_kernel<false>, smem, 1);
+    if (rc) return rc;
+    dw_s1_fwd_kernel<false><<<grid, threads, smem, stream>>>(xmap, ss, w, (__nv_bfloat16*)y, stats, G);
+  }
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -394,9 +512,14 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
   S1Geom G;
   dim3 grid;
   int threads;
-  if (!s1_plan(N, H, W, C, ext, &G, &grid, &threads)) return S2R_ERR_UNSUPPORTED;
-  dw_s1_bwd_kernel<<<grid, threads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, ss, mi, w,
-                                                 (__nv_bfloat16*)g, bsums, dw, G);
+  size_t smem;
+  if (!s1_plan(N, H, W, C, ext, BWD_CONS, BWD_STAGES, true, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+  CUtensorMap dymap, xmap;
+  if (!encode_nhwc(&dymap, dy, N, H, W, C, G.CG * 4, G.TW + 2, RB)) return S2R_ERR_UNSUPPORTED;
+  if (!encode_nhwc(&xmap, x, N, H, W, C, G.CG * 4, G.TW, RB)) return S2R_ERR_UNSUPPORTED;
+  int rc = s1_smem_attr(dw_s1_bwd_kernel, smem, 2);
+  if (rc) return rc;
+  dw_s1_bwd_kernel<<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g, bsums, dw, G);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

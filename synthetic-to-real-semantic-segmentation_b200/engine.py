@@ -464,18 +464,15 @@ class InvertedResidual:
         dy2 = self.pw2.backward(cx, dout)                      # BN3 bwd, wgrad, dgrad -> [N,Ho,Wo,Ch]
         dz2 = cx.new(z2.N, z2.H, z2.W, z2.C)
         bn_backward(cx, self.bn2, dy2, z2, st2, L.ACT_RELU6, dz2)
-        if self.dw.weight.requires_grad:
-            L.call("s2r_dwconv3x3_wgrad", dw_in.vp(), _vp(st_in.ss) if st_in is not None else None,
-                   L.ACT_RELU6, 1 if halo else 0, dz2.vp(), _vp(grad_of(self.dw.weight)), dw_in.N, dw_in.H,
-                   dw_in.W, dw_in.C, self.stride, d, d, cx.stream)
         ext = d if halo else 0
         g = cx.new(dw_in.N, dw_in.H + 2 * ext, dw_in.W + 2 * ext, dw_in.C)
         masked = st_in is not None
         bsums = cx.f64(2 * dw_in.C) if (masked and not st_in.frozen) else None
-        L.call("s2r_dwconv3x3_dgrad", dz2.vp(), _vp(self.dw.weight), dw_in.vp() if masked else None,
-               _vp(st_in.ss) if masked else None, _vp(st_in.mi) if masked else None, L.ACT_RELU6, ext, g.vp(),
-               _vp(bsums) if bsums is not None else None, dw_in.N, dw_in.H, dw_in.W, dw_in.C, self.stride, d, d,
-               cx.stream)
+        L.call("s2r_dwconv3x3_bwd", dz2.vp(), _vp(self.dw.weight), dw_in.vp(), _vp(st_in.ss) if masked else None,
+               _vp(st_in.mi) if masked else None, L.ACT_RELU6, 1 if halo else 0, g.vp(),
+               _vp(bsums) if bsums is not None else None,
+               _vp(grad_of(self.dw.weight)) if self.dw.weight.requires_grad else None, dw_in.N, dw_in.H, dw_in.W,
+               dw_in.C, self.stride, d, d, cx.stream)
         if not self.expand:
             return g, bsums
         # BN1 backward on the padded domain, interior written as dz1

@@ -144,7 +144,10 @@ def test_conv_into_concat_slice_and_leaky_mask(eng, cx):
 
 
 DW_CASES = [(2, 18, 26, 32, 1, 1, False), (2, 17, 25, 96, 2, 1, True), (2, 16, 24, 144, 1, 1, True),
-            (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True)]
+            (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True),
+            # streaming stride-1 kernels: several column tiles / row segments, 32-, 48- and 16-channel chunks
+            (2, 70, 75, 64, 1, 1, True), (1, 40, 37, 144, 1, 1, True), (1, 33, 65, 48, 1, 1, False),
+            (1, 21, 150, 16, 1, 1, True), (2, 8, 31, 576, 1, 1, True), (1, 1, 1, 32, 1, 1, True)]
 
 
 @pytest.mark.parametrize("case", DW_CASES)
@@ -201,6 +204,17 @@ def test_dwconv_fused_prologue_halo(eng, cx, case):
     xhat = (zfull - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
     b_ref = torch.stack([g_ref.double().sum((0, 2, 3)), (g_ref.double() * xhat.double()).sum((0, 2, 3))])
     assert rel(bsums.view(2, Cc), b_ref) < 2e-3
+    # both gradients in one pass (the entry point the engine uses)
+    dw2 = torch.zeros_like(w)
+    gbuf2 = cx.new(N, H + 2 * ext, W + 2 * ext, Cc)
+    bsums2 = cx.f64(2 * Cc)
+    L.call("s2r_dwconv3x3_bwd", dya.vp(), C.c_void_p(w.data_ptr()), za.vp(), C.c_void_p(st.ss.data_ptr()),
+           C.c_void_p(st.mi.data_ptr()), L.ACT_RELU6, 1 if halo else 0, gbuf2.vp(), C.c_void_p(bsums2.data_ptr()),
+           C.c_void_p(dw2.data_ptr()), N, H, W, Cc, stride, dil, pad, cx.stream)
+    torch.cuda.synchronize()
+    assert rel(dw2, wr.grad) < 4e-3
+    assert rel(to_nchw(gbuf2), g_ref) < 5e-3
+    assert rel(bsums2.view(2, Cc), b_ref) < 2e-3
 
 
 @pytest.mark.parametrize("Cc,P,clamp", [(32, 5000, 0), (96, 777, 1), (256, 64, 0), (1024, 200, 1)])
