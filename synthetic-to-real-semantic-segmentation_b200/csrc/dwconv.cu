@@ -356,12 +356,22 @@ inline int dw_smem_attr(K kernel, size_t smem) {
 
 // streaming stride-1 kernels (dwconv_s1.cu)
 int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, cudaStream_t stream);
+                  int N, int H, int W, int C, int dil, cudaStream_t stream);
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
-                  void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
+                  void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream);
+
+int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, double* stats, int N, int H, int W, int C,
+                  cudaStream_t stream);
+int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, void* g,
+                  double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
+
+static bool s2_eligible(const float* ss, int in_act, int halo_const, int stride, int dil, int pad, int C) {
+  return ss != nullptr && in_act == S2R_ACT_RELU6 && halo_const && stride == 2 && dil == 1 && pad == 1 && C % 16 == 0 &&
+         getenv("S2R_DW_GENERIC") == nullptr;
+}
 
 static bool s1_eligible(const float* ss, int in_act, int stride, int dil, int pad, int C) {
-  return ss != nullptr && in_act == S2R_ACT_RELU6 && stride == 1 && dil == 1 && pad == 1 && C % 16 == 0 &&
+  return ss != nullptr && in_act == S2R_ACT_RELU6 && stride == 1 && dil >= 1 && dil <= 4 && pad == dil && C % 16 == 0 &&
          getenv("S2R_DW_GENERIC") == nullptr;
 }
 
@@ -372,7 +382,11 @@ extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int
   int rc = dw_check(x, y, N, H, W, C, stride, dil, pad, &G);
   if (rc) return rc;
   if (s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && ((uintptr_t)in_scale_shift % 16 == 0)) {
-    rc = s2r_dw_s1_fwd(x, in_scale_shift, halo_const, w, y, stats, N, H, W, C, (cudaStream_t)stream);
+    rc = s2r_dw_s1_fwd(x, in_scale_shift, halo_const, w, y, stats, N, H, W, C, dil, (cudaStream_t)stream);
+    if (rc != S2R_ERR_UNSUPPORTED) return rc;
+  }
+  if (s2_eligible(in_scale_shift, in_act, halo_const, stride, dil, pad, C) && ((uintptr_t)in_scale_shift % 16 == 0)) {
+    rc = s2r_dw_s2_fwd(x, in_scale_shift, w, y, stats, N, H, W, C, (cudaStream_t)stream);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
   const int cg = C / 8;
@@ -451,8 +465,16 @@ extern "C" int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, 
     DwGeom G;
     int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
     if (rc) return rc;
-    rc = s2r_dw_s1_bwd(dy, x, in_scale_shift, in_mean_invstd, w, ext, g, bwd_sums, dw, N, H, W, C,
+    rc = s2r_dw_s1_bwd(dy, x, in_scale_shift, in_mean_invstd, w, ext, g, bwd_sums, dw, N, H, W, C, dil,
                        (cudaStream_t)stream);
+    if (rc != S2R_ERR_UNSUPPORTED) return rc;
+  }
+  if (s2_eligible(in_scale_shift, in_act, halo_const, stride, dil, pad, C) && x && (bwd_sums == nullptr || in_mean_invstd) &&
+      ((uintptr_t)in_scale_shift % 16 == 0) && (in_mean_invstd == nullptr || (uintptr_t)in_mean_invstd % 16 == 0)) {
+    DwGeom G;
+    int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
+    if (rc) return rc;
+    rc = s2r_dw_s2_bwd(dy, x, in_scale_shift, in_mean_invstd, w, g, bwd_sums, dw, N, H, W, C, (cudaStream_t)stream);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
   if (dw) {

@@ -19,9 +19,10 @@
 //     every dy operand, so dy and x are read once (6 B/element instead of 10 for two kernels).
 // thread = (column j, 4 consecutive channels); lane order is channel-fastest, so a warp stores
 // contiguous CG*8-byte pixel segments.
-#include "tma_util.cuh"
+#include "dw_common.cuh"
 
 using namespace s2r_tma;
+using namespace s2r_dw;
 
 namespace {
 
@@ -40,93 +41,9 @@ struct S1Geom {
   int ext;          // backward: gradient domain extension (0 or 1)
   int stage_bytes;  // bytes of one ring stage (padded to 128)
   int xoff;         // backward: byte offset of the x tile inside a stage
+  // output (y / g) addressing in elements: the tensor may be a strided view (dilation = parity planes)
+  long long os_pix, os_row, os_img;
 };
-
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 r;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return r;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 r;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 r;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-
-// 4 packed bf16 -> two float2 (channels 0,1 and 2,3)
-__device__ __forceinline__ void unpack4(uint2 u, float2& a, float2& b) {
-  a.x = __uint_as_float(u.x << 16);
-  a.y = __uint_as_float(u.x & 0xffff0000u);
-  b.x = __uint_as_float(u.y << 16);
-  b.y = __uint_as_float(u.y & 0xffff0000u);
-}
-__device__ __forceinline__ uint2 pack4(float2 a, float2 b) {
-  uint2 u;
-  __nv_bfloat162 p = __floats2bfloat162_rn(a.x, a.y), q = __floats2bfloat162_rn(b.x, b.y);
-  u.x = *reinterpret_cast<uint32_t*>(&p);
-  u.y = *reinterpret_cast<uint32_t*>(&q);
-  return u;
-}
-// a6 = sat(x*sc6 + sh6) for 4 packed bf16
-__device__ __forceinline__ void act4(uint2 raw, float2 scA, float2 scB, float2 shA, float2 shB, float2& aA, float2& aB) {
-  float2 xa, xb;
-  unpack4(raw, xa, xb);
-  aA.x = __saturatef(fmaf(xa.x, scA.x, shA.x));
-  aA.y = __saturatef(fmaf(xa.y, scA.y, shA.y));
-  aB.x = __saturatef(fmaf(xb.x, scB.x, shB.x));
-  aB.y = __saturatef(fmaf(xb.y, scB.y, shB.y));
-}
-
-// sum NV per-thread floats over the thread columns of a CTA (consumer threads tid = g + CG*j share g);
-// thread t = g*NV + k < CG*NV returns the total for (g, k).  red: [NV][NCONS+1] floats.  All threads call.
-template <int NV, int NCONS>
-__device__ __forceinline__ float column_reduce(float* red, const float (&v)[NV], int CG, int ncol, bool consumer) {
-  if (consumer) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) red[k * (NCONS + 1) + threadIdx.x] = v[k];
-  }
-  __syncthreads();
-  float acc = 0.f;
-  const int t = threadIdx.x;
-  if (t < CG * NV) {
-    const int g = t / NV, k = t - g * NV;
-    const float* p = red + k * (NCONS + 1) + g;
-    for (int j = 0; j < ncol; ++j) acc += p[j * CG];
-  }
-  return acc;
-}
-
-// per-thread filter: w[c..c+3][9] is 36 contiguous floats (144 B, 16-byte aligned since c % 4 == 0)
-__device__ __forceinline__ void load_filter(const float* __restrict__ w, int c, float scale, float2* wA, float2* wB) {
-  float f[36];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(w + c * 9) + i);
-    f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    wA[k] = make_float2(scale * f[k], scale * f[9 + k]);
-    wB[k] = make_float2(scale * f[18 + k], scale * f[27 + k]);
-  }
-}
 
 // ------------------------------------------------------------------------------------ forward
 // y[oh][ow] = sum_{ky,kx} a(oh+ky-1, ow+kx-1) w[ky][kx],  a = relu6(x*sc+sh) inside the image and
@@ -186,8 +103,8 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
     load_filter(w, c, 6.f, wA, wB);
 
-    const size_t rowp = (size_t)G.W * G.C;
-    __nv_bfloat16* yp = y + (((size_t)n * G.H + oh0) * G.W + min(ow, G.W - 1)) * G.C + c;
+    const size_t rowp = (size_t)G.os_row;
+    __nv_bfloat16* yp = y + (size_t)n * G.os_img + (size_t)oh0 * G.os_row + (size_t)min(ow, G.W - 1) * G.os_pix + c;
     const bool lok = ow - 1 >= 0, rok = ow + 1 < G.W;   // !HALO: zero (not relu6(shift)) outside the image
     float2 accA[3], accB[3];
     float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
@@ -330,8 +247,8 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     float2 wA[9], wB[9];
     load_filter(w, c, 1.f, wA, wB);
 
-    const size_t growp = (size_t)We * G.C;
-    __nv_bfloat16* gp = gout + (((size_t)n * He + he0) * We + min(we, We - 1)) * G.C + c;
+    const size_t growp = (size_t)G.os_row;
+    __nv_bfloat16* gp = gout + (size_t)n * G.os_img + (size_t)he0 * G.os_row + (size_t)min(we, We - 1) * G.os_pix + c;
     float2 gA[3], gB[3], aA[3], aB[3];
     uint2 xr[3];
 #pragma unroll
@@ -485,41 +402,65 @@ inline int s1_smem_attr(K kernel, size_t smem, int which) {
 }  // namespace
 
 // Internal entry points (called from dwconv.cu); return S2R_ERR_UNSUPPORTED when the shape is not covered.
+// Dilation d (padding d) is d*d independent dilation-1 problems on the parity planes of the tensor: plane (p, q)
+// holds the pixels (d*i + p, d*j + q) and is addressed through a TMA map with d-fold strides.
 int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, cudaStream_t stream) {
-  S1Geom G;
-  dim3 grid;
-  int threads;
-  size_t smem;
-  if (!s1_plan(N, H, W, C, 0, FWD_CONS, FWD_STAGES, false, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
-  CUtensorMap xmap;
-  if (!encode_nhwc(&xmap, x, N, H, W, C, G.CG * 4, G.TW + 2, RB)) return S2R_ERR_UNSUPPORTED;
-  if (halo_const) {
-    int rc = s1_smem_attr(dw_s1_fwd_kernel<true>, smem, 0);
-    if (rc) return rc;
-    dw_s1_fwd_kernel<true><<<grid, threads, smem, stream>>>(xmap, ss, w, (__nv_bfloat16*)y, stats, G);
-  } else {
-    int rc = s1_smem_attr(dw_s1_fwd_kernel<false>, smem, 1);
-    if (rc) return rc;
-    dw_s1_fwd_kernel<false><<<grid, threads, smem, stream>>>(xmap, ss, w, (__nv_bfloat16*)y, stats, G);
-  }
-  S2R_LAUNCH_OK();
+                  int N, int H, int W, int C, int dil, cudaStream_t stream) {
+  for (int p = 0; p < dil; ++p)
+    for (int q = 0; q < dil; ++q) {
+      const int Hp = (H - p + dil - 1) / dil, Wp = (W - q + dil - 1) / dil;
+      if (Hp <= 0 || Wp <= 0) continue;
+      S1Geom G;
+      dim3 grid;
+      int threads;
+      size_t smem;
+      if (!s1_plan(N, Hp, Wp, C, 0, FWD_CONS, FWD_STAGES, false, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+      const long long poff = ((long long)p * W + q) * C;
+      G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
+      CUtensorMap xmap;
+      if (!encode_nhwc_view(&xmap, (const __nv_bfloat16*)x + poff, N, Hp, Wp, C, G.os_pix, G.os_row, G.os_img,
+                            G.CG * 4, G.TW + 2, RB))
+        return S2R_ERR_UNSUPPORTED;
+      __nv_bfloat16* yv = (__nv_bfloat16*)y + poff;
+      if (halo_const) {
+        int rc = s1_smem_attr(dw_s1_fwd_kernel<true>, smem, 0);
+        if (rc) return rc;
+        dw_s1_fwd_kernel<true><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G);
+      } else {
+        int rc = s1_smem_attr(dw_s1_fwd_kernel<false>, smem, 1);
+        if (rc) return rc;
+        dw_s1_fwd_kernel<false><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G);
+      }
+      S2R_LAUNCH_OK();
+    }
   return S2R_OK;
 }
 
+// ext = 0 or dil (the reference's padded border); g is [N][H+2ext][W+2ext][C]
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
-                  void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream) {
-  S1Geom G;
-  dim3 grid;
-  int threads;
-  size_t smem;
-  if (!s1_plan(N, H, W, C, ext, BWD_CONS, BWD_STAGES, true, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
-  CUtensorMap dymap, xmap;
-  if (!encode_nhwc(&dymap, dy, N, H, W, C, G.CG * 4, G.TW + 2, RB)) return S2R_ERR_UNSUPPORTED;
-  if (!encode_nhwc(&xmap, x, N, H, W, C, G.CG * 4, G.TW, RB)) return S2R_ERR_UNSUPPORTED;
-  int rc = s1_smem_attr(dw_s1_bwd_kernel, smem, 2);
-  if (rc) return rc;
-  dw_s1_bwd_kernel<<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g, bsums, dw, G);
-  S2R_LAUNCH_OK();
+                  void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream) {
+  const int We = W + 2 * ext, He = H + 2 * ext;
+  for (int p = 0; p < dil; ++p)
+    for (int q = 0; q < dil; ++q) {
+      const int Hp = (H - p + dil - 1) / dil, Wp = (W - q + dil - 1) / dil;
+      if (Hp <= 0 || Wp <= 0) continue;
+      S1Geom G;
+      dim3 grid;
+      int threads;
+      size_t smem;
+      if (!s1_plan(N, Hp, Wp, C, ext ? 1 : 0, BWD_CONS, BWD_STAGES, true, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+      const long long poff = ((long long)p * W + q) * C, goff = ((long long)p * We + q) * C;
+      const long long sw = (long long)dil * C, sh = (long long)dil * W * C, sn = (long long)H * W * C;
+      G.os_pix = (long long)dil * C; G.os_row = (long long)dil * We * C; G.os_img = (long long)He * We * C;
+      CUtensorMap dymap, xmap;
+      if (!encode_nhwc_view(&dymap, (const __nv_bfloat16*)dy + poff, N, Hp, Wp, C, sw, sh, sn, G.CG * 4, G.TW + 2, RB))
+        return S2R_ERR_UNSUPPORTED;
+      if (!encode_nhwc_view(&xmap, (const __nv_bfloat16*)x + poff, N, Hp, Wp, C, sw, sh, sn, G.CG * 4, G.TW, RB))
+        return S2R_ERR_UNSUPPORTED;
+      int rc = s1_smem_attr(dw_s1_bwd_kernel, smem, 2);
+      if (rc) return rc;
+      dw_s1_bwd_kernel<<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G);
+      S2R_LAUNCH_OK();
+    }
   return S2R_OK;
 }

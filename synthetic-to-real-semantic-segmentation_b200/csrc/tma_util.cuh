@@ -62,17 +62,23 @@ static inline EncodeTiledFn get_encode() {
   return fn;
 }
 
-// dense NHWC bf16 tensor [N][H][W][C] -> map with box [1][bh][bw][bc], no swizzle, zero fill outside
-static inline bool encode_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bc, int bw, int bh) {
+// NHWC bf16 view [N][H][W][C] with element strides (sw per pixel, sh per row, sn per image; the channel
+// stride is 1) -> map with box [1][bh][bw][bc], no swizzle, zero fill outside
+static inline bool encode_nhwc_view(CUtensorMap* m, const void* base, int N, int H, int W, int C, long long sw,
+                                    long long sh, long long sn, int bc, int bw, int bh) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline bool encode_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bc, int bw, int bh) {
+  return encode_nhwc_view(m, base, N, H, W, C, C, (long long)W * C, (long long)H * W * C, bc, bw, bh);
 }
 
 }  // namespace s2r_tma

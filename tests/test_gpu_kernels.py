@@ -147,7 +147,12 @@ DW_CASES = [(2, 18, 26, 32, 1, 1, False), (2, 17, 25, 96, 2, 1, True), (2, 16, 2
             (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True),
             # streaming stride-1 kernels: several column tiles / row segments, 32-, 48- and 16-channel chunks
             (2, 70, 75, 64, 1, 1, True), (1, 40, 37, 144, 1, 1, True), (1, 33, 65, 48, 1, 1, False),
-            (1, 21, 150, 16, 1, 1, True), (2, 8, 31, 576, 1, 1, True), (1, 1, 1, 32, 1, 1, True)]
+            (1, 21, 150, 16, 1, 1, True), (2, 8, 31, 576, 1, 1, True), (1, 1, 1, 32, 1, 1, True),
+            # dilation = parity planes of the stride-1 kernels
+            (2, 16, 24, 64, 1, 2, True), (2, 11, 10, 32, 1, 2, False), (1, 13, 17, 48, 1, 3, True),
+            # streaming stride-2 kernels (parity planes of the input), even / odd sizes, several tiles and segments
+            (2, 70, 75, 64, 2, 1, True), (1, 41, 38, 144, 2, 1, True), (1, 34, 130, 16, 2, 1, True),
+            (2, 2, 2, 32, 2, 1, True), (1, 3, 5, 96, 2, 1, True)]
 
 
 @pytest.mark.parametrize("case", DW_CASES)
