@@ -27,13 +27,15 @@ inline RowReduceCfg row_reduce_cfg(long long P, int C) {
   c.rows = 256 / c.cg;
   if (c.rows < 1) c.rows = 1;
   c.threads = c.cg * c.rows;
-  long long blocks = (P + (long long)c.rows * 32 - 1) / ((long long)c.rows * 32);  // >= 32 rows per thread
+  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);  // >= 8 rows per thread
   long long cap = (long long)s2r_sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   c.grid = (int)blocks;
   return c;
 }
+
+constexpr int UNR = 4;   // independent 16-byte loads in flight per thread and tensor (latency hiding at low occupancy)
 
 // sums[0][c] += sum_p x[p][c], sums[1][c] += sum_p x[p][c]^2
 __global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int pitch,
@@ -44,11 +46,21 @@ __global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long lo
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-    float f[8];
-    bf16x8_to_float(ldg16(x + p * pitch + coff + g * 8), f);
+  const long long step = (long long)gridDim.x * rows;
+  for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += UNR * step) {
+    uint4 v[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * step;
+      v[u] = p < P ? ldg16(x + p * pitch + coff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float f[8];
+      bf16x8_to_float(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    }
   }
   float* mine = sm + ((size_t)r * cg + g) * 16;
 #pragma unroll
@@ -145,9 +157,20 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpi
   ChanConst k;
   chan_init(k, scale_shift, nullptr, C, g);
   const long long step = (long long)gridDim.x * rows;
-  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += step) {
+  for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += UNR * step) {
+   uint4 xv[UNR], rv[UNR];
+#pragma unroll
+   for (int u = 0; u < UNR; ++u) {
+     const long long p = p0 + u * step;
+     xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+     if (residual) rv[u] = p < P ? ldg16(residual + p * C + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+   }
+#pragma unroll
+   for (int u = 0; u < UNR; ++u) {
+    const long long p = p0 + u * step;
+    if (p >= P) break;
     float f[8];
-    bf16x8_to_float(ldg16(x + p * xpitch + xoff + g * 8), f);
+    bf16x8_to_float(xv[u], f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = apply_act(fmaf(f[i], k.sc[i], k.sh[i]), act, 0.f);
     if (drop_p > 0.f) {
@@ -158,22 +181,23 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpi
     }
     if (residual) {
       float rr[8];
-      bf16x8_to_float(ldg16(residual + p * C + g * 8), rr);
+      bf16x8_to_float(rv[u], rr);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] += rr[i];
     }
     *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(f);
+   }
   }
 }
 
 // effective upstream gradient through dropout and the activation:
 // dy' = dY * dropout_mask * act'(x * scale + shift)
-__device__ __forceinline__ void bn_bwd_load(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ChanConst& k,
+__device__ __forceinline__ void bn_bwd_load(const uint4& dyv, const uint4& xv, const ChanConst& k,
                                             int act, float drop_p, unsigned long long seed, long long t,
                                             float* gdy, float* xhat) {
   float f[8];
-  bf16x8_to_float(ldg16(dy), gdy);
-  bf16x8_to_float(ldg16(x), f);
+  bf16x8_to_float(dyv, gdy);
+  bf16x8_to_float(xv, f);
   float m[8];
   if (drop_p > 0.f) dropout_scale8(seed, (unsigned long long)t, drop_p, m);
 #pragma unroll
@@ -202,12 +226,23 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-    float gdy[8], xh[8];
-    bn_bwd_load(dy + p * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, k, act, drop_p, seed,
-                p * cg + g, gdy, xh);
+  const long long step = (long long)gridDim.x * rows;
+  for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += UNR * step) {
+    uint4 dv[UNR], xv[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] += gdy[i]; q[i] += gdy[i] * xh[i]; }
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * step;
+      dv[u] = p < P ? ldg16(dy + p * dypitch + dyoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * step;
+      float gdy[8], xh[8];   // a zero dy vector contributes nothing
+      bn_bwd_load(dv[u], xv[u], k, act, drop_p, seed, p * cg + g, gdy, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += gdy[i]; q[i] += gdy[i] * xh[i]; }
+    }
   }
   float* mine = sm + ((size_t)r * cg + g) * 16;
 #pragma unroll
@@ -246,20 +281,31 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
   const long long step = (long long)gridDim.x * rows;
   const int Wp = win_W + 2 * win_pad;
   const long long plane = (long long)win_H * win_W;
-  for (long long p = (long long)blockIdx.x * rows + r; p < P; p += step) {
-    long long pd = p;  // pixel index inside dy (interior window of a padded grid when win_pad > 0)
-    if (win_pad > 0) {
-      const long long n_ = p / plane;
-      const int rem = (int)(p - n_ * plane);
-      const int h_ = rem / win_W, w_ = rem - h_ * win_W;
-      pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * Wp + w_ + win_pad;
-    }
-    float gdy[8], xh[8], o[8];
-    bn_bwd_load(dy + pd * dypitch + dyoff + g * 8, x + p * xpitch + xoff + g * 8, k, act, drop_p, seed,
-                p * cg + g, gdy, xh);
+  for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += UNR * step) {
+    uint4 dv[UNR], xv[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = k.sc[i] * (gdy[i] - m1[i] - xh[i] * m2[i]);
-    *reinterpret_cast<uint4*>(dx + p * dxpitch + dxoff + g * 8) = float_to_bf16x8(o);
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * step;
+      long long pd = p;  // pixel index inside dy (interior window of a padded grid when win_pad > 0)
+      if (win_pad > 0) {
+        const long long n_ = p / plane;
+        const int rem = (int)(p - n_ * plane);
+        const int h_ = rem / win_W, w_ = rem - h_ * win_W;
+        pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * Wp + w_ + win_pad;
+      }
+      dv[u] = p < P ? ldg16(dy + pd * dypitch + dyoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * step;
+      if (p >= P) break;
+      float gdy[8], xh[8], o[8];
+      bn_bwd_load(dv[u], xv[u], k, act, drop_p, seed, p * cg + g, gdy, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = k.sc[i] * (gdy[i] - m1[i] - xh[i] * m2[i]);
+      *reinterpret_cast<uint4*>(dx + p * dxpitch + dxoff + g * 8) = float_to_bf16x8(o);
+    }
   }
 }
 

@@ -17,8 +17,10 @@
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 //     warps 4..15 = epilogue (TMEM -> registers via tcgen05.ld 32x32b, one pixel row per thread, three
 //     warps per SM sub-partition so their dependent-instruction latencies interleave).
-//   * Epilogue: bias, per-channel BN statistics (warp butterfly transpose-reduce, then one fp64
-//     atomic per channel per CTA), activation, residual add / LeakyReLU mask, bf16 store.
+//   * Epilogue: bias, activation, residual add / LeakyReLU mask in registers; the 128 x 32 bf16 unit is staged
+//     in shared memory (64B-swizzled rows) and written with ONE TMA store (full 64-byte segments per pixel,
+//     ragged edges and channel tails clipped by the tensor map); per-channel BN statistics are column sums of
+//     the staged (stored) values, then one fp64 atomic per channel per CTA.
 //   * Persistent CTAs (one per SM) loop over tiles.  mbarrier pipelines: full[s] (TMA -> MMA, expect_tx),
 //     empty[s] (tcgen05.commit -> TMA), acc_full[a] (last commit of a tile -> epilogue), acc_empty[a]
 //     (epilogue -> MMA): with two TMEM accumulators the epilogue of tile i overlaps the mainloop of tile i+1.
@@ -62,7 +64,11 @@ struct TcParams {
 struct TcMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap out;   // output view [N][OH][OW][Cout], box [1][BH][BW][32], 64B swizzle (epilogue TMA stores)
 };
+
+constexpr int TC_STG_BYTES = 128 * 64;                 // one epilogue unit: 128 pixel rows x 32 bf16 channels
+constexpr int TC_STG_TOTAL = 3 * TC_STG_BYTES;         // one staging buffer per epilogue warp group
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +105,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -153,22 +171,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS));
 }
 
-// warp-wide transpose-reduce: on entry lane L holds v[c] for row L, on exit v[0] of lane L is the sum over
-// the 32 rows of column L (31 shuffles)
-__device__ __forceinline__ float warp_col_sums(float* v, int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = up ? v[i + s] : v[i];
-      const float send = up ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // ------------------------------------------------------------------------------------ kernel
@@ -189,6 +191,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_stg = smem + (size_t)STAGES * STAGE_BYTES;   // 1024-aligned: STAGE_BYTES is a multiple of 1024
   __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[NACC], bar_acc_empty[NACC];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_sum[TC_MAX_COUT], s_sq[TC_MAX_COUT];
@@ -213,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
+    prefetch_tmap(&maps.out);
   }
   if (warp == 2) tmem_alloc<TCOLS>(smem_addr(&tmem_base_slot));
   if (p.stats)
@@ -307,8 +311,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const uint32_t aph = (lt / NACC) & 1;
       mbar_wait(smem_addr(&bar_acc_full[ab]), aph);
       tc_fence_after();
+      // units are dealt round-robin to the three groups, rotating with the tile so that narrow tiles
+      // (fewer than three units) still use all epilogue warps
 #pragma unroll 1
-      for (int u = grp; u < MT * CHUNKS; u += 3) {
+      for (int u = (grp + 3 - lt % 3) % 3; u < MT * CHUNKS; u += 3) {
         const int j = u / CHUNKS, c0 = (u - j * CHUNKS) * 32;
         if (n0 + c0 >= p.Cout) continue;
         const int t = mt * MT + j;
@@ -339,37 +345,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               if (n0 + c0 + i < p.Cout) v[i] += __ldg(p.bias + n0 + c0 + i);
           }
         }
-        if (p.stats) {
-          float a[32];
+        // activation / auxiliary operand on the fp32 values of this thread's pixel row
+        if (aux_mode == S2R_AUX_NONE) {
+          if (act == S2R_ACT_RELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = rok ? v[i] : 0.f;
-          float sq[32];
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (act == S2R_ACT_LEAKY) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = a[i] * a[i];
-          const float cs = warp_col_sums(a, lane);
-          const float cq = warp_col_sums(sq, lane);
-          if (n0 + c0 + lane < p.Cout) {
-            atomicAdd(&s_sum[n0 + c0 + lane], cs);
-            atomicAdd(&s_sq[n0 + c0 + lane], cq);
+            for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+          } else if (act == S2R_ACT_RELU6) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
           }
-        }
-        if (rok) {
-          __nv_bfloat16* dst = p.out + tn_ * p.on + oh_ * p.oh + ow_ * p.ow + n0 + c0;
-          const __nv_bfloat16* asrc = p.aux ? p.aux + tn_ * p.an + oh_ * p.ah + ow_ * p.aw + n0 + c0 : nullptr;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                           (asrc == nullptr || (reinterpret_cast<uintptr_t>(asrc) & 15) == 0);
-          if (aux_mode == S2R_AUX_NONE) {
-            if (act == S2R_ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            } else if (act == S2R_ACT_LEAKY) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
-            } else if (act == S2R_ACT_RELU6) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
-            }
-          } else if (vec) {
+        } else if (rok) {
+          const __nv_bfloat16* asrc = p.aux + tn_ * p.an + oh_ * p.ah + ow_ * p.aw + n0 + c0;
+          if (full && (reinterpret_cast<uintptr_t>(asrc) & 15) == 0) {
             float av[32];
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) bf16x8_to_float(ldg16(asrc + qq * 8), av + qq * 8);
@@ -388,14 +378,47 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 v[i] = aux_mode == S2R_AUX_ADD ? v[i] + av : v[i] * (av > 0.f ? 1.f : p.slope);
               }
           }
-          if (vec) {
+        }
+        if (!rok) {   // rows outside the output (ragged patches, duplicated sub-tile): no statistics, store clipped
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(dst + qq * 8) = float_to_bf16x8(v + qq * 8);
-          } else {
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        uint4 pk[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + c0 + i < p.Cout) dst[i] = __float2bfloat16(v[i]);
+        for (int qq = 0; qq < 4; ++qq) pk[qq] = float_to_bf16x8(v + qq * 8);
+        // stage the 128 x 32 unit in shared memory (64-byte rows, 16-byte chunks XOR-swizzled with (row >> 1) & 3:
+        // the layout of CU_TENSOR_MAP_SWIZZLE_64B, conflict-free for these stores) and write it out with one TMA
+        // store: full 64-byte segments per pixel instead of 32 scattered 16-byte stores per instruction
+        uint8_t* stg = smem_stg + grp * TC_STG_BYTES;
+        if (row == 0) bulk_wait_read0();          // the previous store of this group has finished reading the buffer
+        named_bar_sync(1 + grp, 128);
+        {
+          uint8_t* rp = stg + row * 64;
+          const int sw = (row >> 1) & 3;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(rp + ((qq ^ sw) << 4)) = pk[qq];
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + grp, 128);
+        if (row == 0 && tok) {
+          tma_store_4d(&maps.out, smem_addr(stg), n0 + c0, tw_, th_, tn_);
+          bulk_commit();
+        }
+        if (p.stats) {
+          // per-channel sum / sum of squares of the STORED (bf16) values: thread = (channel pair, 16-row segment)
+          const int pr = row & 15, seg = row >> 4;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r2 = seg * 16 + rr;
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + r2 * 64 + ((((pr >> 2) ^ ((r2 >> 1) & 3))) << 4) + (pr & 3) * 4);
+            const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+            s0 += f0; s1 += f1;
+            q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
           }
+          const int ch = n0 + c0 + 2 * pr;
+          if (ch < p.Cout) { atomicAdd(&s_sum[ch], s0); atomicAdd(&s_sq[ch], q0); }
+          if (ch + 1 < p.Cout) { atomicAdd(&s_sum[ch + 1], s1); atomicAdd(&s_sq[ch + 1], q1); }
         }
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back
@@ -403,6 +426,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_acc_empty[ab])) : "memory");
     }
+    if (row == 0) bulk_wait0();   // this group's TMA stores are complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -473,7 +497,7 @@ bool encode_weights(EncodeTiledFn enc, CUtensorMap* m, const void* w, int Kpad, 
 
 template <int BN, int MT, int STAGES>
 int launch_tc(const TcMaps& maps, const TcParams& p, int n_tiles_n, cudaStream_t st) {
-  constexpr int smem = STAGES * (MT * TC_A_BYTES + BN * 128) + 1024;
+  constexpr int smem = STAGES * (MT * TC_A_BYTES + BN * 128) + TC_STG_TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     S2R_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -601,6 +625,21 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
     }
   }
   if (!encode_weights(enc, &maps.b, a->w, a->Kpad, a->Cout_pad, max_slice + 1, BN)) return 0;
+  {
+    // output view for the epilogue's TMA stores; needs 16-byte aligned base and strides
+    if ((uintptr_t)a->out % 16 || on % 8 || oh % 8 || ow % 8) return 0;
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ow * 2, (cuuint64_t)oh * 2, (cuuint64_t)on * 2};
+    for (int i = 0; i < 3; ++i)
+      if (strides[i] == 0) strides[i] = 16;
+    cuuint32_t box[4] = {32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1u};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      s2r_set_error("conv_tc: cuTensorMapEncodeTiled failed for the output view");
+      return 0;
+    }
+  }
   const int ntn = s2r_div_up(a->Cout, BN);
   // two M sub-tiles per CTA (weights fetched once per 256 pixels) when the contraction is deep enough to be
   // tensor-bound and the problem still fills the machine; otherwise one sub-tile and two TMEM accumulators so

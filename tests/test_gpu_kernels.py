@@ -94,8 +94,11 @@ def test_conv_fwd_dgrad_wgrad(eng, cx, case):
     torch.cuda.synchronize()
     y = to_nchw(out)
     assert rel(y, y_ref.detach()) < 4e-3
-    s_ref = torch.stack([y_ref.detach().double().sum((0, 2, 3)), (y_ref.detach().double() ** 2).sum((0, 2, 3))])
-    assert rel(stats.view(2, Cout), s_ref) < 1e-3
+    # the statistics are those of the STORED (bf16) outputs -- what the following BatchNorm normalises
+    s_ref = torch.stack([y.double().sum((0, 2, 3)), (y.double() ** 2).sum((0, 2, 3))])
+    assert rel(stats.view(2, Cout), s_ref) < 1e-4
+    s_ref32 = torch.stack([y_ref.detach().double().sum((0, 2, 3)), (y_ref.detach().double() ** 2).sum((0, 2, 3))])
+    assert rel(stats.view(2, Cout), s_ref32) < 5e-3
     # leaky epilogue
     out2 = cx.new(N, OH, OW, eng.round_up(Cout, 8), zero=True)
     out2.C = Cout
