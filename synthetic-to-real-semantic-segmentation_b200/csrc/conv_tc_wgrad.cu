@@ -221,19 +221,32 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgT
 #pragma unroll 1
       for (int u = grp; u < MT * CHUNKS; u += 3) {
         const int j = u / CHUNKS, c0 = (u - j * CHUNKS) * 32;
-        const int co = co0 + j * 128 + ew * 32 + lane;
         if (ci0 + c0 >= p.Cin) continue;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * BN + c0), r);
         tmem_ld_wait();
-        if (co < p.Cout) {
-          float* dst = p.dwt + co * p.s_co + T.wofs;
+        // transpose through shared memory (the pipeline ring is idle once bar_acc has fired) so that one atomic
+        // instruction covers 32 CONSECUTIVE input channels of one output channel -- a single 128-byte line for
+        // 1x1 filters -- instead of 32 different output-channel rows
+        float* stg = reinterpret_cast<float*>(smem) + (warp - 4) * 1024;   // this warp's 32 rows x 32 floats
+        {
+          uint4* rp = reinterpret_cast<uint4*>(stg + lane * 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int ci = ci0 + c0 + i;
-            if (ci < p.Cin) atomicAdd(dst + ci * p.s_ci, __uint_as_float(r[i]));
+          for (int qq = 0; qq < 8; ++qq) rp[qq ^ (lane & 7)] = make_uint4(r[4 * qq], r[4 * qq + 1], r[4 * qq + 2], r[4 * qq + 3]);
+        }
+        __syncwarp();
+        const int ci = ci0 + c0 + lane;
+        if (ci < p.Cin) {
+          float* dst = p.dwt + (long long)ci * p.s_ci + T.wofs;
+          const int co_base = co0 + j * 128 + ew * 32;
+          const int nrow = min(32, p.Cout - co_base);
+#pragma unroll 4
+          for (int rr = 0; rr < nrow; ++rr) {
+            const float v = stg[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+            atomicAdd(dst + (long long)(co_base + rr) * p.s_co, v);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
     }
@@ -387,8 +400,22 @@ int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st) {
   p.co_tiles = s2r_div_up(a->Cout, MT * 128);
   const long long tiles = (long long)p.ntaps * p.ci_tiles * p.co_tiles;
   // split the pixel range so that about two CTAs per SM exist, each with at least 8 chunks
-  int splits = s2r_div_up(2l * s2r_sm_count(), tiles);
-  const int max_splits = s2r_div_up(nchunks, 8);
+  // Pixel splits trade parallelism against the atomic traffic of the partial tiles (measured, tests/tools/wg_sweep.sh):
+  // 1x1 filters (coalesced atomics, one tile per CTA column): one CTA per SM; multi-tap filters re-read the same
+  // pixels once per tap out of L2 and like two CTAs per SM, unless the pixel range is short and the strided
+  // (uncoalesced) atomics of their large tiles dominate.
+  static double knob_ctas = -1;
+  static int min_chunks = 8;
+  if (knob_ctas < 0) {   // overrides for tuning
+    const char* e = getenv("S2R_WG_CTAS_PER_SM");
+    knob_ctas = e ? atof(e) : 0.0;
+    const char* m = getenv("S2R_WG_MIN_CHUNKS");
+    if (m) min_chunks = atoi(m);
+  }
+  double ctas_per_sm = p.ntaps == 1 ? 1.0 : ((long long)nchunks * WG_BKP >= 100000 ? 2.0 : 0.5);
+  if (knob_ctas > 0) ctas_per_sm = knob_ctas;
+  int splits = s2r_div_up((long)(ctas_per_sm * s2r_sm_count()), tiles);
+  const int max_splits = s2r_div_up(nchunks, min_chunks);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.chunks_per_split = s2r_div_up(nchunks, splits);
