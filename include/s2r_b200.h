@@ -135,9 +135,10 @@ int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, int in_act, 
                         int pad, s2r_stream_t stream);
 /* Both gradients in one pass over dy and x (autograd of mobilenet.py:40,54 + :51-52 + :62):
  *   g, bwd_sums as s2r_dwconv3x3_dgrad with ext = halo_const ? pad : 0;  dw (optional, fp32 [C][3][3]) +=
- *   weight gradient as s2r_dwconv3x3_wgrad. */
+ *   weight gradient as s2r_dwconv3x3_wgrad.  g_interior != 0: g is [N][H][W][C] (the border positions of the
+ *   extended domain enter bwd_sums but are not stored -- all the producer's BN backward needs). */
 int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, const float* in_scale_shift,
-                      const float* in_mean_invstd, int in_act, int halo_const, void* g,
+                      const float* in_mean_invstd, int in_act, int halo_const, int g_interior, void* g,
                       double* bwd_sums, float* dw, int N, int H, int W, int C, int stride, int dil,
                       int pad, s2r_stream_t stream);
 

@@ -180,7 +180,7 @@ dw_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sca
 __global__ void __launch_bounds__(256)
 dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
                 const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale_shift,
-                const float* __restrict__ mean_invstd, int in_act, int ext, __nv_bfloat16* __restrict__ gout,
+                const float* __restrict__ mean_invstd, int in_act, int ext, int interior, __nv_bfloat16* __restrict__ gout,
                 double* __restrict__ bsums, DwGeom G, int tw) {
   extern __shared__ __align__(16) float sm[];
   float* sw = sm;
@@ -203,7 +203,8 @@ dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ 
   }
   const __nv_bfloat16* dimg = dy + (size_t)n * G.Ho * G.Wo * G.C + g * 8;
   const __nv_bfloat16* ximg = x ? x + (size_t)n * G.H * G.W * G.C + g * 8 : nullptr;
-  __nv_bfloat16* out = gout + (size_t)n * He * We * G.C + g * 8;
+  // interior layout: g is [N][H][W][C] and the border positions only feed the sums
+  __nv_bfloat16* out = gout + (interior ? (size_t)n * G.H * G.W * G.C : (size_t)n * He * We * G.C) + g * 8;
   const float* wg = sw + g * 8;
   float s[8], q[8];
 #pragma unroll
@@ -256,7 +257,10 @@ dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ 
           q[i] += acc[i] * (xv[i] - mu[i]) * is[i];
         }
       }
-      *reinterpret_cast<uint4*>(out + ((he0 + r) * We + we) * G.C) = float_to_bf16x8(acc);
+      if (!interior)
+        *reinterpret_cast<uint4*>(out + ((he0 + r) * We + we) * G.C) = float_to_bf16x8(acc);
+      else if ((unsigned)ih < (unsigned)G.H && (unsigned)iw < (unsigned)G.W)
+        *reinterpret_cast<uint4*>(out + (ih * G.W + iw) * G.C) = float_to_bf16x8(acc);
     }
   }
   if (bsums) block_channel_reduce(red, s, q, cg, g, col, tw, G.C, bsums);
@@ -358,12 +362,12 @@ inline int dw_smem_attr(K kernel, size_t smem) {
 int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
                   int N, int H, int W, int C, int dil, cudaStream_t stream);
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
-                  void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream);
+                  int interior, void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream);
 
 int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, double* stats, int N, int H, int W, int C,
                   cudaStream_t stream);
-int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, void* g,
-                  double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
+int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int interior,
+                  void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
 
 static bool s2_eligible(const float* ss, int in_act, int halo_const, int stride, int dil, int pad, int C) {
   return ss != nullptr && in_act == S2R_ACT_RELU6 && halo_const && stride == 2 && dil == 1 && pad == 1 && C % 16 == 0 &&
@@ -409,10 +413,10 @@ extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int
   return S2R_OK;
 }
 
-extern "C" int s2r_dwconv3x3_dgrad(const void* dy, const float* w, const void* x,
-                                   const float* in_scale_shift, const float* in_mean_invstd,
-                                   int in_act, int ext, void* g, double* bwd_sums, int N, int H, int W,
-                                   int C, int stride, int dil, int pad, s2r_stream_t stream) {
+static int dw_dgrad_generic(const void* dy, const float* w, const void* x,
+                            const float* in_scale_shift, const float* in_mean_invstd,
+                            int in_act, int ext, int interior, void* g, double* bwd_sums, int N, int H, int W,
+                            int C, int stride, int dil, int pad, s2r_stream_t stream) {
   DwGeom G;
   int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
   if (rc) return rc;
@@ -427,10 +431,18 @@ extern "C" int s2r_dwconv3x3_dgrad(const void* dy, const float* w, const void* x
   if (rc) return rc;
   dim3 grid(s2r_div_up(We, tw), s2r_div_up(He, ROWS), N);
   dw_dgrad_kernel<<<grid, tw * cg, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, w, (const __nv_bfloat16*)x, in_scale_shift, in_mean_invstd, in_act, ext,
+      (const __nv_bfloat16*)dy, w, (const __nv_bfloat16*)x, in_scale_shift, in_mean_invstd, in_act, ext, interior,
       (__nv_bfloat16*)g, bwd_sums, G, tw);
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+extern "C" int s2r_dwconv3x3_dgrad(const void* dy, const float* w, const void* x,
+                                   const float* in_scale_shift, const float* in_mean_invstd,
+                                   int in_act, int ext, void* g, double* bwd_sums, int N, int H, int W,
+                                   int C, int stride, int dil, int pad, s2r_stream_t stream) {
+  return dw_dgrad_generic(dy, w, x, in_scale_shift, in_mean_invstd, in_act, ext, 0, g, bwd_sums, N, H, W, C, stride, dil,
+                          pad, stream);
 }
 
 extern "C" int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, int in_act,
@@ -456,16 +468,17 @@ extern "C" int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, i
 // Fused data + weight gradient (one pass over dy and x where the streaming kernel applies, otherwise the
 // two generic kernels).  halo_const selects the reference's padded-border semantics (ext = pad).
 extern "C" int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, const float* in_scale_shift,
-                                 const float* in_mean_invstd, int in_act, int halo_const, void* g,
+                                 const float* in_mean_invstd, int in_act, int halo_const, int g_interior, void* g,
                                  double* bwd_sums, float* dw, int N, int H, int W, int C, int stride, int dil,
                                  int pad, s2r_stream_t stream) {
   const int ext = halo_const ? pad : 0;
+  if (ext == 0) g_interior = 0;   // same layout
   if (s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && x && (bwd_sums == nullptr || in_mean_invstd) &&
       ((uintptr_t)in_scale_shift % 16 == 0) && (in_mean_invstd == nullptr || (uintptr_t)in_mean_invstd % 16 == 0)) {
     DwGeom G;
     int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
     if (rc) return rc;
-    rc = s2r_dw_s1_bwd(dy, x, in_scale_shift, in_mean_invstd, w, ext, g, bwd_sums, dw, N, H, W, C, dil,
+    rc = s2r_dw_s1_bwd(dy, x, in_scale_shift, in_mean_invstd, w, ext, g_interior, g, bwd_sums, dw, N, H, W, C, dil,
                        (cudaStream_t)stream);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
@@ -474,13 +487,13 @@ extern "C" int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, 
     DwGeom G;
     int rc = dw_check(dy, g, N, H, W, C, stride, dil, pad, &G);
     if (rc) return rc;
-    rc = s2r_dw_s2_bwd(dy, x, in_scale_shift, in_mean_invstd, w, g, bwd_sums, dw, N, H, W, C, (cudaStream_t)stream);
+    rc = s2r_dw_s2_bwd(dy, x, in_scale_shift, in_mean_invstd, w, g_interior, g, bwd_sums, dw, N, H, W, C, (cudaStream_t)stream);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
   if (dw) {
     int rc = s2r_dwconv3x3_wgrad(x, in_scale_shift, in_act, halo_const, dy, dw, N, H, W, C, stride, dil, pad, stream);
     if (rc) return rc;
   }
-  return s2r_dwconv3x3_dgrad(dy, w, in_scale_shift ? x : nullptr, in_scale_shift, in_mean_invstd, in_act, ext, g,
+  return dw_dgrad_generic(dy, w, in_scale_shift ? x : nullptr, in_scale_shift, in_mean_invstd, in_act, ext, g_interior, g,
                              bwd_sums, N, H, W, C, stride, dil, pad, stream);
 }

@@ -43,6 +43,7 @@ struct S1Geom {
   int xoff;         // backward: byte offset of the x tile inside a stage
   // output (y / g) addressing in elements: the tensor may be a strided view (dilation = parity planes)
   long long os_pix, os_row, os_img;
+  int interior;     // backward: g has the unextended layout, border positions are not stored
 };
 
 // ------------------------------------------------------------------------------------ forward
@@ -248,7 +249,11 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     load_filter(w, c, 1.f, wA, wB);
 
     const size_t growp = (size_t)G.os_row;
-    __nv_bfloat16* gp = gout + (size_t)n * G.os_img + (size_t)he0 * G.os_row + (size_t)min(we, We - 1) * G.os_pix + c;
+    // interior layout: position (he, we) of the extended domain lives at (he - ext, we - ext) and exists only inside
+    const int gsh = G.interior ? ext : 0;
+    __nv_bfloat16* gp = gout + (long long)n * G.os_img + (long long)(he0 - gsh) * G.os_row +
+                        (long long)(min(we, We - 1) - gsh) * G.os_pix + c;
+    const bool col_in = !G.interior || (unsigned)(we - ext) < (unsigned)G.W;
     float2 gA[3], gB[3], aA[3], aB[3];
     uint2 xr[3];
 #pragma unroll
@@ -301,7 +306,8 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
           vA.y = (mA.y > 0.f && mA.y < 1.f) ? vA.y : 0.f;
           vB.x = (mB.x > 0.f && mB.x < 1.f) ? vB.x : 0.f;
           vB.y = (mB.y > 0.f && mB.y < 1.f) ? vB.y : 0.f;
-          *reinterpret_cast<uint2*>(gp + (size_t)o * growp) = pack4(vA, vB);
+          if (col_in && (!G.interior || (unsigned)(ih_start + o) < (unsigned)G.H))
+            *reinterpret_cast<uint2*>(gp + (long long)o * (long long)growp) = pack4(vA, vB);
           float2 xa, xb;
           unpack4(xr[s2], xa, xb);
           sA = fadd2(sA, vA);
@@ -438,8 +444,9 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
 
 // ext = 0 or dil (the reference's padded border); g is [N][H+2ext][W+2ext][C]
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
-                  void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream) {
-  const int We = W + 2 * ext, He = H + 2 * ext;
+                  int interior, void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream) {
+  if (!ext) interior = 0;
+  const int We = interior ? W : W + 2 * ext, He = interior ? H : H + 2 * ext;   // g layout
   for (int p = 0; p < dil; ++p)
     for (int q = 0; q < dil; ++q) {
       const int Hp = (H - p + dil - 1) / dil, Wp = (W - q + dil - 1) / dil;
@@ -452,6 +459,7 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
       const long long poff = ((long long)p * W + q) * C, goff = ((long long)p * We + q) * C;
       const long long sw = (long long)dil * C, sh = (long long)dil * W * C, sn = (long long)H * W * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * We * C; G.os_img = (long long)He * We * C;
+      G.interior = interior;
       CUtensorMap dymap, xmap;
       if (!encode_nhwc_view(&dymap, (const __nv_bfloat16*)dy + poff, N, Hp, Wp, C, sw, sh, sn, G.CG * 4, G.TW + 2, RB))
         return S2R_ERR_UNSUPPORTED;

@@ -27,6 +27,7 @@ struct S2Geom {
   int CG, TW, rs, nseg;
   int stage_bytes;
   int off[5];           // byte offsets of the tiles inside a stage
+  int interior;         // backward: g is [N][H][W][C], border positions are not stored
 };
 
 struct S2Maps {
@@ -160,14 +161,14 @@ dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
 //   g_oe(2i+1, 2j  ) = dy(i,j) w21 + dy(i+1,j) w01
 //   g_oo(2i+1, 2j+1) = dy(i,j) w22 + dy(i,j+1) w20 + dy(i+1,j) w02 + dy(i+1,j+1) w00
 // each masked by act'(pre) of its own position, and the nine weight-gradient taps pair the same operands.
-__device__ __forceinline__ void s2_emit(float2 vA, float2 vB, float2 aA, float2 aB, uint2 xraw, bool ok, __nv_bfloat16* dst,
+__device__ __forceinline__ void s2_emit(float2 vA, float2 vB, float2 aA, float2 aB, uint2 xraw, bool ok, bool st, __nv_bfloat16* dst,
                                         float2 nmuA, float2 nmuB, float2& sA, float2& sB, float2& qA, float2& qB) {
   if (ok) {
     vA.x = (aA.x > 0.f && aA.x < 1.f) ? vA.x : 0.f;
     vA.y = (aA.y > 0.f && aA.y < 1.f) ? vA.y : 0.f;
     vB.x = (aB.x > 0.f && aB.x < 1.f) ? vB.x : 0.f;
     vB.y = (aB.y > 0.f && aB.y < 1.f) ? vB.y : 0.f;
-    *reinterpret_cast<uint2*>(dst) = pack4(vA, vB);
+    if (st) *reinterpret_cast<uint2*>(dst) = pack4(vA, vB);
     float2 xa, xb;
     unpack4(xraw, xa, xb);
     sA = fadd2(sA, vA);
@@ -186,7 +187,8 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
   __shared__ uint64_t bar_full[B_STAGES], bar_empty[B_STAGES];
   __shared__ float red[12 * (B_CONS + 1)];
   const int CG = G.CG, TW = G.TW;
-  const int He = G.H + 2, We = G.W + 2;
+  const int gsh = G.interior ? 0 : 1;               // g element of (ih, iw) sits at (ih + gsh, iw + gsh)
+  const int He = G.H + 2 * gsh, We = G.W + 2 * gsh;
   const int ncons = TW * CG;
   const int ncw = (ncons + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,9 +237,11 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
     const int g = tid % CG, j = tid / CG;
     const int c = (blockIdx.x * CG + g) * 4;
     const int jj = j0 + j;                                  // dy column
-    // column validity of the two input columns 2jj, 2jj+1 inside [-1, W]
+    // column validity of the two input columns 2jj, 2jj+1 inside [-1, W]; cs_*: the position is stored
     const bool ce_ok = live && 2 * jj >= -1 && 2 * jj <= G.W;
     const bool co_ok = live && 2 * jj + 1 >= -1 && 2 * jj + 1 <= G.W;
+    const bool cse = !G.interior || (unsigned)(2 * jj) < (unsigned)G.W;
+    const bool cso = !G.interior || (unsigned)(2 * jj + 1) < (unsigned)G.W;
 
     float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
     const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
@@ -254,7 +258,7 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
 
     const long long growp = (long long)We * G.C;
     // g element of (ih, iw) is at ((n*He + ih + 1)*We + iw + 1)*C; this thread's even column is iw = 2jj
-    __nv_bfloat16* gp = gout + ((long long)n * He * We + (long long)(2 * jj + 1)) * G.C + c;
+    __nv_bfloat16* gp = gout + ((long long)n * He * We + (long long)(2 * jj + gsh)) * G.C + c;
     float2 p0A = make_float2(0.f, 0.f), p0B = p0A, p1A = p0A, p1B = p0A;   // dy(i, jj), dy(i, jj+1)
 
     for (int k = 0; k < nst; ++k) {
@@ -276,7 +280,9 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         const bool row_step = live && r >= 1 && r <= rows;
         const bool re_ok = row_step && 2 * i >= -1 && 2 * i <= G.H;
         const bool ro_ok = row_step && 2 * i + 1 >= -1 && 2 * i + 1 <= G.H;
-        __nv_bfloat16* grow = gp + (long long)(2 * i + 1) * growp;   // row ih = 2i
+        __nv_bfloat16* grow = gp + (long long)(2 * i + gsh) * growp;   // row ih = 2i
+        const bool rse = !G.interior || (unsigned)(2 * i) < (unsigned)G.H;
+        const bool rso = !G.interior || (unsigned)(2 * i + 1) < (unsigned)G.H;
         uint2 xr;
         float2 aA, aB, vA, vB;
         // ---- ee: (2i, 2jj)
@@ -285,7 +291,7 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         if (!row_step) aA = aB = make_float2(0.f, 0.f);
         vA = fmul2(p0A, wA[4]); vB = fmul2(p0B, wB[4]);
         dA[4] = ffma2(p0A, aA, dA[4]); dB[4] = ffma2(p0B, aB, dB[4]);
-        s2_emit(vA, vB, aA, aB, xr, re_ok && ce_ok, grow, nmuA, nmuB, sA, sB, qA, qB);
+        s2_emit(vA, vB, aA, aB, xr, re_ok && ce_ok, rse && cse, grow, nmuA, nmuB, sA, sB, qA, qB);
         // ---- eo: (2i, 2jj+1)
         xr = teo[u * TW * CG];
         act4(xr, scA, scB, shA, shB, aA, aB);
@@ -293,7 +299,7 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         vA = ffma2(p1A, wA[3], fmul2(p0A, wA[5])); vB = ffma2(p1B, wB[3], fmul2(p0B, wB[5]));
         dA[5] = ffma2(p0A, aA, dA[5]); dB[5] = ffma2(p0B, aB, dB[5]);
         dA[3] = ffma2(p1A, aA, dA[3]); dB[3] = ffma2(p1B, aB, dB[3]);
-        s2_emit(vA, vB, aA, aB, xr, re_ok && co_ok, grow + G.C, nmuA, nmuB, sA, sB, qA, qB);
+        s2_emit(vA, vB, aA, aB, xr, re_ok && co_ok, rse && cso, grow + G.C, nmuA, nmuB, sA, sB, qA, qB);
         // ---- oe: (2i+1, 2jj)
         xr = toe[u * TW * CG];
         act4(xr, scA, scB, shA, shB, aA, aB);
@@ -301,7 +307,7 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         vA = ffma2(n0A, wA[1], fmul2(p0A, wA[7])); vB = ffma2(n0B, wB[1], fmul2(p0B, wB[7]));
         dA[7] = ffma2(p0A, aA, dA[7]); dB[7] = ffma2(p0B, aB, dB[7]);
         dA[1] = ffma2(n0A, aA, dA[1]); dB[1] = ffma2(n0B, aB, dB[1]);
-        s2_emit(vA, vB, aA, aB, xr, ro_ok && ce_ok, grow + growp, nmuA, nmuB, sA, sB, qA, qB);
+        s2_emit(vA, vB, aA, aB, xr, ro_ok && ce_ok, rso && cse, grow + growp, nmuA, nmuB, sA, sB, qA, qB);
         // ---- oo: (2i+1, 2jj+1)
         xr = too[u * TW * CG];
         act4(xr, scA, scB, shA, shB, aA, aB);
@@ -312,7 +318,7 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         dA[6] = ffma2(p1A, aA, dA[6]); dB[6] = ffma2(p1B, aB, dB[6]);
         dA[2] = ffma2(n0A, aA, dA[2]); dB[2] = ffma2(n0B, aB, dB[2]);
         dA[0] = ffma2(n1A, aA, dA[0]); dB[0] = ffma2(n1B, aB, dB[0]);
-        s2_emit(vA, vB, aA, aB, xr, ro_ok && co_ok, grow + growp + G.C, nmuA, nmuB, sA, sB, qA, qB);
+        s2_emit(vA, vB, aA, aB, xr, ro_ok && co_ok, rso && cso, grow + growp + G.C, nmuA, nmuB, sA, sB, qA, qB);
         p0A = n0A; p0B = n0B; p1A = n1A; p1B = n1B;
       }
       __syncwarp();
@@ -427,9 +433,10 @@ int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, doubl
   return S2R_OK;
 }
 
-int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, void* g,
-                  double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream) {
+int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int interior,
+                  void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream) {
   S2Geom G;
+  G.interior = interior;
   G.N = N; G.H = H; G.W = W; G.C = C;
   G.Ho = (H - 1) / 2 + 1; G.Wo = (W - 1) / 2 + 1;
   G.CG = pick_cg(C);

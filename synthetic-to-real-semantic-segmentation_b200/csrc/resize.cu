@@ -185,6 +185,78 @@ up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int 
   }
 }
 
+// Separable, row-staged variant of the kernel above for the final x4 up-sampling (deeplab.py:31), whose
+// gradient is the largest activation of the step (N x 19 x 512 x 1024 fp32): a CTA owns (image, channel,
+// UR coarse rows, 256 coarse columns), streams the fine rows that touch them through shared memory (coalesced
+// float4 loads, each fine element read once per CTA) and every thread reduces its column neighbourhood with
+// weights held in registers.  Same arithmetic as up_from_nchw_bwd_kernel up to summation order.
+constexpr int UR = 8;      // coarse rows per CTA
+constexpr int UK = 14;     // max fine columns in the candidate range of one coarse column (2/scale + 4)
+
+__global__ void __launch_bounds__(kThreads)
+up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
+                             int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+  extern __shared__ __align__(16) float rowbuf[];   // [seg_max]
+  const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
+  const int c = blockIdx.y, n = blockIdx.z;
+  const int ih0 = ihb * UR;
+  const int iw = cb * kThreads + threadIdx.x;
+  const bool col_ok = iw < Wi;
+  __nv_bfloat16* out = dx + (((long long)n * Hi + ih0) * Wi + (col_ok ? iw : 0)) * dxpitch + c;
+  if (c >= C) {   // padding channels of the NHWC buffer stay zero
+    if (col_ok)
+      for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(0.f);
+    return;
+  }
+  // fine column segment needed by this CTA's coarse columns
+  int seg_lo, seg_hi, t0, t1;
+  cand_range(cb * kThreads, sw, Wo, &seg_lo, &t0);
+  cand_range(min(cb * kThreads + kThreads - 1, Wi - 1), sw, Wo, &t1, &seg_hi);
+  seg_lo &= ~3;                                     // float4-aligned start
+  const int seg_len = seg_hi - seg_lo + 1;
+  // this thread's column weights
+  int wlo = 0, whi = -1;
+  float wx[UK];
+#pragma unroll
+  for (int k = 0; k < UK; ++k) wx[k] = 0.f;
+  if (col_ok) {
+    cand_range(iw, sw, Wo, &wlo, &whi);
+#pragma unroll
+    for (int k = 0; k < UK; ++k)
+      if (wlo + k <= whi) wx[k] = lerp_weight(lerp_src(wlo + k, sw, Wi), iw);
+  }
+  const int koff = wlo - seg_lo;
+  int hlo, hhi, u0, u1;
+  cand_range(ih0, sh, Ho, &hlo, &u0);
+  cand_range(min(ih0 + UR - 1, Hi - 1), sh, Ho, &u1, &hhi);
+  float acc[UR];
+#pragma unroll
+  for (int r = 0; r < UR; ++r) acc[r] = 0.f;
+  const float* plane = dy + ((long long)n * C + c) * Ho * Wo;
+  const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  for (int oh = hlo; oh <= hhi; ++oh) {
+    const float* src = plane + (long long)oh * Wo + seg_lo;
+    if (vec) {
+      for (int i = threadIdx.x * 4; i < seg_len; i += kThreads * 4) {
+        // seg_lo and Wo are multiples of 4, so a float4 never straddles the row end
+        *reinterpret_cast<float4*>(rowbuf + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+      }
+    } else {
+      for (int i = threadIdx.x; i < seg_len; i += kThreads) rowbuf[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < UK; ++k) v = fmaf(wx[k], (koff + k < seg_len && koff + k >= 0) ? rowbuf[koff + k] : 0.f, v);
+    const Lerp ly = lerp_src(oh, sh, Hi);
+#pragma unroll
+    for (int r = 0; r < UR; ++r) acc[r] = fmaf(lerp_weight(ly, ih0 + r), v, acc[r]);
+    __syncthreads();
+  }
+  if (col_ok)
+    for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(acc[r]);
+}
+
 // ------------------------------------------------------------ global average pool
 // one CTA per (image, 64-channel slab); y[n][c] = mean_p x[n][p][c]
 __global__ void __launch_bounds__(kThreads)
@@ -366,9 +438,20 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
                                                       s2r_stream_t stream) {
   S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1 && dxpitch >= C, S2R_ERR_SHAPE,
               "upsample_from_nchw_bwd: bad shape");
+  const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  // row-staged kernel when at most UK fine columns touch a coarse column (up-sampling factors up to ~4.5)
+  if (sw > 0.f && sh > 0.f && 2.f / sw + 4.f <= (float)UK && N <= 65535 && dxpitch <= 65535) {
+    const int col_chunks = s2r_div_up(Wi, kThreads);
+    const int seg_max = (int)((kThreads + 2) / sw) + 16;
+    dim3 grid(s2r_div_up(Hi, UR) * col_chunks, dxpitch, N);
+    up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)seg_max * sizeof(float), (cudaStream_t)stream>>>(
+        dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
+    S2R_LAUNCH_OK();
+    return S2R_OK;
+  }
   const long long total = (long long)N * dxpitch * Hi * Wi;
   up_from_nchw_bwd_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

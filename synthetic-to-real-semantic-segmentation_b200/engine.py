@@ -464,12 +464,12 @@ class InvertedResidual:
         dy2 = self.pw2.backward(cx, dout)                      # BN3 bwd, wgrad, dgrad -> [N,Ho,Wo,Ch]
         dz2 = cx.new(z2.N, z2.H, z2.W, z2.C)
         bn_backward(cx, self.bn2, dy2, z2, st2, L.ACT_RELU6, dz2)
-        ext = d if halo else 0
-        g = cx.new(dw_in.N, dw_in.H + 2 * ext, dw_in.W + 2 * ext, dw_in.C)
+        # g in the unextended layout: the reference's padded border only enters the BN-backward sums
+        g = cx.new(dw_in.N, dw_in.H, dw_in.W, dw_in.C)
         masked = st_in is not None
         bsums = cx.f64(2 * dw_in.C) if (masked and not st_in.frozen) else None
         L.call("s2r_dwconv3x3_bwd", dz2.vp(), _vp(self.dw.weight), dw_in.vp(), _vp(st_in.ss) if masked else None,
-               _vp(st_in.mi) if masked else None, L.ACT_RELU6, 1 if halo else 0, g.vp(),
+               _vp(st_in.mi) if masked else None, L.ACT_RELU6, 1 if halo else 0, 1, g.vp(),
                _vp(bsums) if bsums is not None else None,
                _vp(grad_of(self.dw.weight)) if self.dw.weight.requires_grad else None, dw_in.N, dw_in.H, dw_in.W,
                dw_in.C, self.stride, d, d, cx.stream)
@@ -479,8 +479,7 @@ class InvertedResidual:
         if st_in.frozen:
             bsums = cx.f64(2 * dw_in.C)
         dz1 = cx.new(dw_in.N, dw_in.H, dw_in.W, dw_in.C)
-        bn_backward(cx, self.pw1.bn, g, dw_in, st_in, L.ACT_NONE, dz1, presummed=bsums,
-                    win=(dw_in.H, dw_in.W, ext) if ext > 0 else None)
+        bn_backward(cx, self.pw1.bn, g, dw_in, st_in, L.ACT_NONE, dz1, presummed=bsums)
         if self.res:
             dx = self.pw1.backward_raw(cx, dz1, True, dx=dout, dx_accumulate=True)
         else:

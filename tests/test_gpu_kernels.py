@@ -217,12 +217,24 @@ def test_dwconv_fused_prologue_halo(eng, cx, case):
     gbuf2 = cx.new(N, H + 2 * ext, W + 2 * ext, Cc)
     bsums2 = cx.f64(2 * Cc)
     L.call("s2r_dwconv3x3_bwd", dya.vp(), C.c_void_p(w.data_ptr()), za.vp(), C.c_void_p(st.ss.data_ptr()),
-           C.c_void_p(st.mi.data_ptr()), L.ACT_RELU6, 1 if halo else 0, gbuf2.vp(), C.c_void_p(bsums2.data_ptr()),
+           C.c_void_p(st.mi.data_ptr()), L.ACT_RELU6, 1 if halo else 0, 0, gbuf2.vp(), C.c_void_p(bsums2.data_ptr()),
            C.c_void_p(dw2.data_ptr()), N, H, W, Cc, stride, dil, pad, cx.stream)
     torch.cuda.synchronize()
     assert rel(dw2, wr.grad) < 4e-3
     assert rel(to_nchw(gbuf2), g_ref) < 5e-3
     assert rel(bsums2.view(2, Cc), b_ref) < 2e-3
+    # ... with g in the unextended layout (border positions only in the sums)
+    gbuf3 = cx.new(N, H, W, Cc)
+    bsums3 = cx.f64(2 * Cc)
+    dw3 = torch.zeros_like(w)
+    L.call("s2r_dwconv3x3_bwd", dya.vp(), C.c_void_p(w.data_ptr()), za.vp(), C.c_void_p(st.ss.data_ptr()),
+           C.c_void_p(st.mi.data_ptr()), L.ACT_RELU6, 1 if halo else 0, 1, gbuf3.vp(), C.c_void_p(bsums3.data_ptr()),
+           C.c_void_p(dw3.data_ptr()), N, H, W, Cc, stride, dil, pad, cx.stream)
+    torch.cuda.synchronize()
+    g_int = g_ref[:, :, ext:ext + H, ext:ext + W] if ext else g_ref
+    assert rel(to_nchw(gbuf3), g_int) < 5e-3
+    assert rel(bsums3.view(2, Cc), b_ref) < 2e-3
+    assert rel(dw3, wr.grad) < 4e-3
 
 
 @pytest.mark.parametrize("Cc,P,clamp", [(32, 5000, 0), (96, 777, 1), (256, 64, 0), (1024, 200, 1)])
@@ -291,7 +303,8 @@ def test_bn_dropout_is_regenerated_in_backward(eng, cx):
     assert bool(((d != 0) == keep).all())
 
 
-@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 64, 128, 256), (5, 7, 17, 25), (33, 33, 129, 129), (1, 1, 9, 12)])
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 64, 128, 256), (5, 7, 17, 25), (33, 33, 129, 129), (1, 1, 9, 12),
+                                         (20, 300, 77, 1197), (24, 260, 94, 1040)])
 def test_bilinear_align_corners(eng, cx, Hi, Wi, Ho, Wo):
     L = sub("_lib")
     g = torch.Generator(device="cuda").manual_seed(Hi * Wo)
