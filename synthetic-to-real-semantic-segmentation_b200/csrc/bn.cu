@@ -9,7 +9,9 @@
 // finalize (mean / inv-std / running stats / scale+shift) -> apply.  All kernels are
 // HBM-bound: 16-byte vector of 8 channels per thread, channel-group fastest so a warp
 // touches contiguous memory.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "dw_common.cuh"
 
 namespace {
 
@@ -37,6 +39,18 @@ inline RowReduceCfg row_reduce_cfg(long long P, int C) {
 
 constexpr int UNR = 4;   // independent 16-byte loads in flight per thread and tensor (latency hiding at low occupancy)
 
+// Keeps the batch of loads issued above this point from being sunk to their uses (ptxas otherwise re-serialises
+// load -> use -> load to save registers, which costs the memory-level parallelism the unrolling is for).
+#define S2R_ISSUE_LOADS_FIRST() asm volatile("" ::: "memory")
+
+// 16-byte read-only load that stays where it is written: LLVM sinks a plain __ldg into the (conditional) block
+// that consumes it, which turns a batch of independent loads back into load -> use -> load.
+__device__ __forceinline__ uint4 ldg16_pinned(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // sums[0][c] += sum_p x[p][c], sums[1][c] += sum_p x[p][c]^2
 __global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int pitch,
                                     int coff, int rows, double* __restrict__ sums) {
@@ -47,21 +61,24 @@ __global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long lo
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   const long long step = (long long)gridDim.x * rows;
-  for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += UNR * step) {
-    uint4 v[UNR];
+  long long p0 = (long long)blockIdx.x * rows + r;
+  const __nv_bfloat16* xp = x + p0 * pitch + coff + g * 8;
+  const long long sx = step * pitch;
+  auto one = [&](const uint4& vv) {
+    float f[8];
+    bf16x8_to_float(vv, f);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const long long p = p0 + u * step;
-      v[u] = p < P ? ldg16(x + p * pitch + coff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+  };
+  constexpr int UNS = 2 * UNR;   // single input stream: twice the batch
+  for (; p0 + (UNS - 1) * step < P; p0 += UNS * step, xp += UNS * sx) {
+    uint4 v[UNS];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      float f[8];
-      bf16x8_to_float(v[u], f);
+    for (int u = 0; u < UNS; ++u) v[u] = ldg16(xp + u * sx);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
-    }
+    for (int u = 0; u < UNS; ++u) one(v[u]);
   }
+  for (; p0 < P; p0 += step, xp += sx) one(ldg16(xp));
   float* mine = sm + ((size_t)r * cg + g) * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
@@ -161,10 +178,11 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpi
    uint4 xv[UNR], rv[UNR];
 #pragma unroll
    for (int u = 0; u < UNR; ++u) {
-     const long long p = p0 + u * step;
-     xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-     if (residual) rv[u] = p < P ? ldg16(residual + p * C + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+     const long long p = min(p0 + u * step, P - 1);   // clamped: unconditional loads are issued back to back
+     xv[u] = ldg16_pinned(x + p * xpitch + xoff + g * 8);
+     if (residual) rv[u] = ldg16_pinned(residual + p * C + g * 8);
    }
+   S2R_ISSUE_LOADS_FIRST();
 #pragma unroll
    for (int u = 0; u < UNR; ++u) {
     const long long p = p0 + u * step;
@@ -231,14 +249,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
     uint4 dv[UNR], xv[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const long long p = p0 + u * step;
-      dv[u] = p < P ? ldg16(dy + p * dypitch + dyoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-      xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      const long long p = min(p0 + u * step, P - 1);   // clamped: unconditional loads are issued back to back
+      dv[u] = ldg16_pinned(dy + p * dypitch + dyoff + g * 8);
+      xv[u] = ldg16_pinned(x + p * xpitch + xoff + g * 8);
     }
+    S2R_ISSUE_LOADS_FIRST();
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const long long p = p0 + u * step;
-      float gdy[8], xh[8];   // a zero dy vector contributes nothing
+      if (p >= P) break;
+      float gdy[8], xh[8];
       bn_bwd_load(dv[u], xv[u], k, act, drop_p, seed, p * cg + g, gdy, xh);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += gdy[i]; q[i] += gdy[i] * xh[i]; }
@@ -285,7 +305,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
     uint4 dv[UNR], xv[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const long long p = p0 + u * step;
+      const long long p = min(p0 + u * step, P - 1);   // clamped: unconditional loads are issued back to back
       long long pd = p;  // pixel index inside dy (interior window of a padded grid when win_pad > 0)
       if (win_pad > 0) {
         const long long n_ = p / plane;
@@ -293,9 +313,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
         const int h_ = rem / win_W, w_ = rem - h_ * win_W;
         pd = (n_ * (win_H + 2 * win_pad) + h_ + win_pad) * Wp + w_ + win_pad;
       }
-      dv[u] = p < P ? ldg16(dy + pd * dypitch + dyoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-      xv[u] = p < P ? ldg16(x + p * xpitch + xoff + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      dv[u] = ldg16_pinned(dy + pd * dypitch + dyoff + g * 8);
+      xv[u] = ldg16_pinned(x + p * xpitch + xoff + g * 8);
     }
+    S2R_ISSUE_LOADS_FIRST();
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const long long p = p0 + u * step;
@@ -305,6 +326,218 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = k.sc[i] * (gdy[i] - m1[i] - xh[i] * m2[i]);
       *reinterpret_cast<uint4*>(dx + p * dxpitch + dxoff + g * 8) = float_to_bf16x8(o);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Lean variants of the three streaming kernels above for the common case (no dropout, no gradient window).
+// The generic kernels spend ~125-210 instructions per 16-byte vector (64-bit index arithmetic per load, generic
+// activation code) and are ISSUE-bound at half the HBM roofline (ncu: profiles/r1_bn_ncu.txt).  Here:
+//   * pointer-increment addressing, one fast path for full batches of UNR rows;
+//   * packed FFMA2 arithmetic with the per-channel affine maps folded on entry:
+//       apply:      y  = act(x*sc + sh) (+ residual)        relu6(v) = 6*sat(v/6): one FFMA.SAT
+//       bwd reduce: s += gd, q += gd*x  with gd = dy*act'(pre); the caller's (sum gd, sum gd*xhat) follow as
+//                   q_hat = invstd*(q - mean*s)
+//       bwd apply:  dx = A*gd + B*x + D,  A = sc, B = -sc*m2*invstd, D = sc*(m2*invstd*mean - m1)
+template <int ACT>
+__device__ __forceinline__ float2 act_mask2(float2 pre6, float2 v) {
+  // pre6: pre-activation (ACT_RELU) or sat(pre/6) (ACT_RELU6); returns v where act' = 1, else 0
+  if (ACT == S2R_ACT_RELU) {
+    v.x = pre6.x > 0.f ? v.x : 0.f;
+    v.y = pre6.y > 0.f ? v.y : 0.f;
+  } else if (ACT == S2R_ACT_RELU6) {
+    v.x = (pre6.x > 0.f && pre6.x < 1.f) ? v.x : 0.f;
+    v.y = (pre6.y > 0.f && pre6.y < 1.f) ? v.y : 0.f;
+  }
+  return v;
+}
+
+struct Lean8 {   // 8 channels as four float2 pairs
+  float2 v[4];
+};
+__device__ __forceinline__ Lean8 lean_unpack(const uint4& u) {
+  Lean8 r;
+  r.v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+  r.v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  r.v[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+  r.v[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ uint4 lean_pack(const Lean8& r) {
+  uint4 u;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(r.v[0].x, r.v[0].y); u.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r.v[1].x, r.v[1].y); u.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r.v[2].x, r.v[2].y); u.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r.v[3].x, r.v[3].y); u.w = *reinterpret_cast<uint32_t*>(&t);
+  return u;
+}
+__device__ __forceinline__ void load_pairs(const float* __restrict__ p, float scale, float2* o) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = make_float2(a.x * scale, a.y * scale);
+  o[1] = make_float2(a.z * scale, a.w * scale);
+  o[2] = make_float2(b.x * scale, b.y * scale);
+  o[3] = make_float2(b.z * scale, b.w * scale);
+}
+
+template <int ACT, bool RES>
+__global__ void __launch_bounds__(256)
+bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
+                     const float* __restrict__ scale_shift, const __nv_bfloat16* __restrict__ residual,
+                     __nv_bfloat16* __restrict__ y, int ypitch, int yoff, int rows) {
+  const int cg = C / 8;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
+  float2 sc[4], sh[4];
+  load_pairs(scale_shift + g * 8, k, sc);
+  load_pairs(scale_shift + C + g * 8, k, sh);
+  const long long step = (long long)gridDim.x * rows;
+  long long p0 = (long long)blockIdx.x * rows + r;
+  const __nv_bfloat16* xp = x + p0 * xpitch + xoff + g * 8;
+  const __nv_bfloat16* rp = RES ? residual + p0 * C + g * 8 : nullptr;
+  __nv_bfloat16* yp = y + p0 * ypitch + yoff + g * 8;
+  const long long sx = step * xpitch, sr = step * C, sy = step * ypitch;
+  auto one = [&](const uint4& xvv, const uint4& rvv, __nv_bfloat16* dst) {
+    Lean8 v = lean_unpack(xvv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (ACT == S2R_ACT_RELU6) {
+        v.v[i].x = 6.f * __saturatef(fmaf(v.v[i].x, sc[i].x, sh[i].x));
+        v.v[i].y = 6.f * __saturatef(fmaf(v.v[i].y, sc[i].y, sh[i].y));
+      } else {
+        v.v[i] = s2r_dw::ffma2(v.v[i], sc[i], sh[i]);
+        if (ACT == S2R_ACT_RELU) {
+          v.v[i].x = fmaxf(v.v[i].x, 0.f);
+          v.v[i].y = fmaxf(v.v[i].y, 0.f);
+        }
+      }
+    }
+    if (RES) {
+      const Lean8 rr = lean_unpack(rvv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v.v[i] = s2r_dw::fadd2(v.v[i], rr.v[i]);
+    }
+    *reinterpret_cast<uint4*>(dst) = lean_pack(v);
+  };
+  // full batches: straight-line code (no per-row branches), so all UNR loads issue before the first use
+  for (; p0 + (UNR - 1) * step < P; p0 += UNR * step, xp += UNR * sx, yp += UNR * sy, rp += RES ? UNR * sr : 0) {
+    uint4 xv[UNR], rv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      xv[u] = ldg16(xp + u * sx);
+      rv[u] = RES ? ldg16(rp + u * sr) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) one(xv[u], rv[u], yp + u * sy);
+  }
+  for (; p0 < P; p0 += step, xp += sx, yp += sy, rp += RES ? sr : 0)
+    one(ldg16(xp), RES ? ldg16(rp) : make_uint4(0u, 0u, 0u, 0u), yp);
+}
+
+// APPLY = false: dsums += [sum gd, sum gd*xhat];  APPLY = true: dx = scale*(gd - m1 - xhat*m2)
+template <int ACT, bool APPLY>
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, const __nv_bfloat16* __restrict__ x,
+                   int xpitch, int xoff, const float* __restrict__ mean_invstd, const float* __restrict__ scale_shift,
+                   double* __restrict__ dsums, double count, long long P, int C, __nv_bfloat16* __restrict__ dx,
+                   int dxpitch, int dxoff, int rows) {
+  extern __shared__ float sm[];
+  const int cg = C / 8;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
+  float2 sc[4], sh[4];   // activation mask: pre (or pre/6)
+  if (ACT != S2R_ACT_NONE) {
+    load_pairs(scale_shift + g * 8, k, sc);
+    load_pairs(scale_shift + C + g * 8, k, sh);
+  }
+  float2 A[4], B[4], D[4];   // APPLY: dx = A*gd + B*x + D
+  float2 s[4], q[4];         // reduce
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = q[i] = make_float2(0.f, 0.f);
+  if (APPLY) {
+    float scl[8], mu[8], is[8];
+    load_f8(scale_shift + g * 8, scl);
+    load_f8(mean_invstd + g * 8, mu);
+    load_f8(mean_invstd + C + g * 8, is);
+    const double inv_n = count > 0 ? 1.0 / count : 0.0;
+    float a[8], b[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float m1 = count > 0 ? (float)(dsums[g * 8 + i] * inv_n) : 0.f;
+      const float m2 = count > 0 ? (float)(dsums[C + g * 8 + i] * inv_n) : 0.f;
+      a[i] = scl[i];
+      b[i] = -scl[i] * m2 * is[i];
+      d[i] = scl[i] * (m2 * is[i] * mu[i] - m1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      A[i] = make_float2(a[2 * i], a[2 * i + 1]);
+      B[i] = make_float2(b[2 * i], b[2 * i + 1]);
+      D[i] = make_float2(d[2 * i], d[2 * i + 1]);
+    }
+  }
+  const long long step = (long long)gridDim.x * rows;
+  long long p0 = (long long)blockIdx.x * rows + r;
+  const __nv_bfloat16* dp = dy + p0 * dypitch + dyoff + g * 8;
+  const __nv_bfloat16* xp = x + p0 * xpitch + xoff + g * 8;
+  __nv_bfloat16* op = APPLY ? dx + p0 * dxpitch + dxoff + g * 8 : nullptr;
+  const long long sd = step * dypitch, sx = step * xpitch, so = step * dxpitch;
+  auto one = [&](const uint4& dvv, const uint4& xvv, __nv_bfloat16* dst) {
+    Lean8 gd = lean_unpack(dvv);
+    const Lean8 xx = lean_unpack(xvv);
+    Lean8 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (ACT == S2R_ACT_RELU6) {
+        float2 a6;
+        a6.x = __saturatef(fmaf(xx.v[i].x, sc[i].x, sh[i].x));
+        a6.y = __saturatef(fmaf(xx.v[i].y, sc[i].y, sh[i].y));
+        gd.v[i] = act_mask2<ACT>(a6, gd.v[i]);
+      } else if (ACT == S2R_ACT_RELU) {
+        gd.v[i] = act_mask2<ACT>(s2r_dw::ffma2(xx.v[i], sc[i], sh[i]), gd.v[i]);
+      }
+      if (APPLY) {
+        o.v[i] = s2r_dw::ffma2(A[i], gd.v[i], s2r_dw::ffma2(B[i], xx.v[i], D[i]));
+      } else {
+        s[i] = s2r_dw::fadd2(s[i], gd.v[i]);
+        q[i] = s2r_dw::ffma2(gd.v[i], xx.v[i], q[i]);
+      }
+    }
+    if (APPLY) *reinterpret_cast<uint4*>(dst) = lean_pack(o);
+  };
+  // full batches: straight-line code (no per-row branches), so all 2*UNR loads issue before the first use
+  for (; p0 + (UNR - 1) * step < P; p0 += UNR * step, dp += UNR * sd, xp += UNR * sx, op += APPLY ? UNR * so : 0) {
+    uint4 dv[UNR], xv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      dv[u] = ldg16(dp + u * sd);
+      xv[u] = ldg16(xp + u * sx);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) one(dv[u], xv[u], APPLY ? op + u * so : nullptr);
+  }
+  for (; p0 < P; p0 += step, dp += sd, xp += sx, op += APPLY ? so : 0) one(ldg16(dp), ldg16(xp), op);
+  if (!APPLY) {
+    // xhat form: sum gd*xhat = invstd * (sum gd*x - mean * sum gd), per thread before the block reduction
+    float mu[8], is[8];
+    load_f8(mean_invstd + g * 8, mu);
+    load_f8(mean_invstd + C + g * 8, is);
+    float* mine = sm + ((size_t)r * cg + g) * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mine[2 * i] = s[i].x;
+      mine[2 * i + 1] = s[i].y;
+      mine[8 + 2 * i] = is[2 * i] * (q[i].x - mu[2 * i] * s[i].x);
+      mine[8 + 2 * i + 1] = is[2 * i + 1] * (q[i].y - mu[2 * i + 1] * s[i].y);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cg * 16; t += blockDim.x) {
+      const int gg = t / 16, kk = t % 16;
+      double acc = 0;
+      for (int rr = 0; rr < rows; ++rr) acc += (double)sm[((size_t)rr * cg + gg) * 16 + kk];
+      atomicAdd(&dsums[(kk >> 3) * C + gg * 8 + (kk & 7)], acc);
     }
   }
 }
@@ -390,6 +623,22 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
   S2R_REQUIRE(drop_p >= 0.f && drop_p < 1.f, S2R_ERR_SHAPE, "bn_apply: dropout p=%f", drop_p);
   if (P == 0) return S2R_OK;
   const ElemCfg cfg = elem_cfg(P, C);
+  if (drop_p == 0.f && getenv("S2R_BN_GENERIC") == nullptr) {
+    const __nv_bfloat16 *xb = (const __nv_bfloat16*)x, *rb = (const __nv_bfloat16*)residual;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    cudaStream_t st = (cudaStream_t)stream;
+#define S2R_APPLY(ACT_)                                                                                                \
+  do {                                                                                                                 \
+    if (residual)                                                                                                      \
+      bn_apply_lean_kernel<ACT_, true><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows); \
+    else                                                                                                               \
+      bn_apply_lean_kernel<ACT_, false><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows); \
+  } while (0)
+    if (act == S2R_ACT_NONE) { S2R_APPLY(S2R_ACT_NONE); S2R_LAUNCH_OK(); return S2R_OK; }
+    if (act == S2R_ACT_RELU) { S2R_APPLY(S2R_ACT_RELU); S2R_LAUNCH_OK(); return S2R_OK; }
+    if (act == S2R_ACT_RELU6) { S2R_APPLY(S2R_ACT_RELU6); S2R_LAUNCH_OK(); return S2R_OK; }
+#undef S2R_APPLY
+  }
   bn_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
       (const __nv_bfloat16*)residual, drop_p, seed, (const unsigned long long*)seed_dev, (__nv_bfloat16*)y, ypitch,
@@ -409,6 +658,18 @@ extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const v
   if (P == 0) return S2R_OK;
   RowReduceCfg cfg = row_reduce_cfg(P, C);
   size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
+  if (drop_p == 0.f && getenv("S2R_BN_GENERIC") == nullptr && (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) {
+    const __nv_bfloat16 *db = (const __nv_bfloat16*)dy, *xb = (const __nv_bfloat16*)x;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (act == S2R_ACT_NONE)
+      bn_bwd_lean_kernel<S2R_ACT_NONE, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
+    else if (act == S2R_ACT_RELU)
+      bn_bwd_lean_kernel<S2R_ACT_RELU, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
+    else
+      bn_bwd_lean_kernel<S2R_ACT_RELU6, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
+    S2R_LAUNCH_OK();
+    return S2R_OK;
+  }
   bn_bwd_reduce_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
       scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, P, C, cfg.rows, dsums);
@@ -433,6 +694,20 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
   S2R_REQUIRE(win_pad == 0 || (win_H >= 1 && win_W >= 1 && P % ((int64_t)win_H * win_W) == 0), S2R_ERR_SHAPE,
               "bn_bwd_apply: window %dx%d does not tile P", win_H, win_W);
   const ElemCfg cfg = elem_cfg(P, C);
+  if (drop_p == 0.f && win_pad == 0 && getenv("S2R_BN_GENERIC") == nullptr &&
+      (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) {
+    const __nv_bfloat16 *db = (const __nv_bfloat16*)dy, *xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* ob = (__nv_bfloat16*)dx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (act == S2R_ACT_NONE)
+      bn_bwd_lean_kernel<S2R_ACT_NONE, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
+    else if (act == S2R_ACT_RELU)
+      bn_bwd_lean_kernel<S2R_ACT_RELU, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
+    else
+      bn_bwd_lean_kernel<S2R_ACT_RELU6, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
+    S2R_LAUNCH_OK();
+    return S2R_OK;
+  }
   bn_bwd_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
       scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, dsums, count, P, C, (__nv_bfloat16*)dx,

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 OUT=../libs2r_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr --extended-lambda"
 mkdir -p build
 pids=()
 for f in *.cu; do

@@ -191,12 +191,13 @@ up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int 
 // float4 loads, each fine element read once per CTA) and every thread reduces its column neighbourhood with
 // weights held in registers.  Same arithmetic as up_from_nchw_bwd_kernel up to summation order.
 constexpr int UR = 8;      // coarse rows per CTA
+constexpr int URB = 4;     // fine rows staged per barrier pair
 constexpr int UK = 14;     // max fine columns in the candidate range of one coarse column (2/scale + 4)
 
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
                              int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
-  extern __shared__ __align__(16) float rowbuf[];   // [seg_max]
+  extern __shared__ __align__(16) float rowbuf[];   // [URB][seg_max]
   const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
   const int c = blockIdx.y, n = blockIdx.z;
   const int ih0 = ihb * UR;
@@ -234,23 +235,43 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
   for (int r = 0; r < UR; ++r) acc[r] = 0.f;
   const float* plane = dy + ((long long)n * C + c) * Ho * Wo;
   const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
-  for (int oh = hlo; oh <= hhi; ++oh) {
-    const float* src = plane + (long long)oh * Wo + seg_lo;
-    if (vec) {
-      for (int i = threadIdx.x * 4; i < seg_len; i += kThreads * 4) {
+  for (int oh0 = hlo; oh0 <= hhi; oh0 += URB) {
+    // stage URB fine rows per barrier pair: URB independent loads in flight per thread
+#pragma unroll
+    for (int b = 0; b < URB; ++b) {
+      const int oh = oh0 + b;
+      if (oh > hhi) break;
+      const float* src = plane + (long long)oh * Wo + seg_lo;
+      float* dstrow = rowbuf + b * seg_max;
+      // element j is stored at j + (j >> 5): the readers below walk the row with a stride of ~1/scale (4) words
+      // per lane, which would be a 4-way bank conflict on a dense row and is conflict-free on the skewed one
+      if (vec) {
         // seg_lo and Wo are multiples of 4, so a float4 never straddles the row end
-        *reinterpret_cast<float4*>(rowbuf + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+        for (int i = threadIdx.x * 4; i < seg_len; i += kThreads * 4) {
+          const float4 v4 = __ldg(reinterpret_cast<const float4*>(src + i));
+          float* d = dstrow + i + (i >> 5);
+          d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
+        }
+      } else {
+        for (int i = threadIdx.x; i < seg_len; i += kThreads) dstrow[i + (i >> 5)] = __ldg(src + i);
       }
-    } else {
-      for (int i = threadIdx.x; i < seg_len; i += kThreads) rowbuf[i] = __ldg(src + i);
     }
     __syncthreads();
-    float v = 0.f;
 #pragma unroll
-    for (int k = 0; k < UK; ++k) v = fmaf(wx[k], (koff + k < seg_len && koff + k >= 0) ? rowbuf[koff + k] : 0.f, v);
-    const Lerp ly = lerp_src(oh, sh, Hi);
+    for (int b = 0; b < URB; ++b) {
+      const int oh = oh0 + b;
+      if (oh > hhi) break;
+      const float* row = rowbuf + b * seg_max;
+      float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < UR; ++r) acc[r] = fmaf(lerp_weight(ly, ih0 + r), v, acc[r]);
+      for (int k = 0; k < UK; ++k) {
+        const int j = koff + k;
+        v = fmaf(wx[k], (j < seg_len && j >= 0) ? row[j + (j >> 5)] : 0.f, v);
+      }
+      const Lerp ly = lerp_src(oh, sh, Hi);
+#pragma unroll
+      for (int r = 0; r < UR; ++r) acc[r] = fmaf(lerp_weight(ly, ih0 + r), v, acc[r]);
+    }
     __syncthreads();
   }
   if (col_ok)
@@ -442,9 +463,10 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
   // row-staged kernel when at most UK fine columns touch a coarse column (up-sampling factors up to ~4.5)
   if (sw > 0.f && sh > 0.f && 2.f / sw + 4.f <= (float)UK && N <= 65535 && dxpitch <= 65535) {
     const int col_chunks = s2r_div_up(Wi, kThreads);
-    const int seg_max = (int)((kThreads + 2) / sw) + 16;
+    int seg_max = (int)((kThreads + 2) / sw) + 16;
+    seg_max = (seg_max + (seg_max >> 5) + 4) & ~3;   // skewed row length
     dim3 grid(s2r_div_up(Hi, UR) * col_chunks, dxpitch, N);
-    up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)seg_max * sizeof(float), (cudaStream_t)stream>>>(
+    up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)URB * seg_max * sizeof(float), (cudaStream_t)stream>>>(
         dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
     S2R_LAUNCH_OK();
     return S2R_OK;
