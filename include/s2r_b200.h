@@ -142,6 +142,13 @@ int s2r_dwconv3x3_bwd(const void* dy, const float* w, const void* x, const float
                       double* bwd_sums, float* dw, int N, int H, int W, int C, int stride, int dil,
                       int pad, s2r_stream_t stream);
 
+/* Patch matrix of an RxS / stride / pad convolution taken straight from an NCHW fp32 tensor:
+ *   P[n][oh][ow][k] = x[n][c][oh*s+ky-pad][ow*s+kx-pad], k = (c*R+ky)*S+kx, zero for k in [C*R*S, Kp).
+ * Turns the few-channel convolutions (mobilenet.py:9-14 stem, discriminator.py:11 conv1) into pointwise GEMMs
+ * whose filter / filter gradient are the OIHW tensors viewed as [Cout][C*R*S]. */
+int s2r_im2col_nchw_f32(const float* x, int N, int C, int H, int W, int R, int S, int stride, int pad,
+                        void* P, int Kp, s2r_stream_t stream);
+
 /* ------------------------------------------------------------------ batch norm
  * modeling/sync_batchnorm/batchnorm.py:48-78,113-125 and the F.batch_norm fallback (:50-53). */
 int s2r_channel_sums_bf16(const void* x, int64_t P, int C, int pitch, int coff, double* sums,

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_im2col_nchw_f32": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_channel_sums_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "s2r_bn_finalize": [vp, f64, vp, vp, f32, i32, f32, vp, vp, vp, vp, i32, vp],
     "s2r_bn_eval_scale_shift": [vp, vp, vp, vp, f32, vp, vp, i32, vp],

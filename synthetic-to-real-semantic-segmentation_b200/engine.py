@@ -144,6 +144,41 @@ def grad_of(p):
     return p.grad
 
 
+class RawNCHW:
+    """A module input kept as the caller's NCHW fp32 tensor (runs with `raw_inputs = True`): the few-channel
+    first convolutions read it through the patch kernel instead of a NHWC copy."""
+    __slots__ = ("t", "N", "C", "H", "W")
+
+    def __init__(self, t):
+        if t.dim() != 4:
+            raise ValueError('expected 4D input (got {}D input)'.format(t.dim()))
+        t = t.contiguous()
+        if t.dtype != torch.float32:
+            t = t.float()
+        self.t = t
+        self.N, self.C, self.H, self.W = t.shape
+
+
+def im2col(cx, raw, R, S, stride, pad):
+    """Patch matrix [N,OH,OW,round_up(C*R*S,8)] (bf16) of an RxS conv on a RawNCHW input."""
+    OH, OW = conv_out_hw(raw.H, raw.W, R, S, stride, pad, 1)
+    K = raw.C * R * S
+    P = cx.new(raw.N, OH, OW, round_up(K, 8))
+    L.call("s2r_im2col_nchw_f32", _vp(raw.t), raw.N, raw.C, raw.H, raw.W, R, S, stride, pad, P.vp(), P.pitch,
+           cx.stream)
+    P.C = K
+    return P
+
+
+def patch_weight(w):
+    """The OIHW filter viewed as the 1x1 filter [Cout, C*R*S, 1, 1] of the patch GEMM (same storage)."""
+    v = getattr(w, "_s2r_w2", None)
+    if v is None or v.data_ptr() != w.data_ptr():
+        v = w.detach().view(w.shape[0], -1, 1, 1)
+        w._s2r_w2 = v
+    return v
+
+
 # --------------------------------------------------------------------------- tap tables
 def _fill_tap(tap, base, sn, sh, sw, H, W, dh, dw, wslice, wofs):
     tap.base = base
@@ -244,10 +279,11 @@ def conv_dgrad(cx, dy, w, dx, stride=1, pad=0, dil=1, aux=None, aux_mode=L.AUX_N
     return dx
 
 
-def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1):
-    """w.grad += conv weight gradient; bias handled by the caller."""
+def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
+    """w.grad += conv weight gradient; bias handled by the caller.  grad_param: the parameter whose .grad
+    receives the result when w is a reshaped view of it (patch GEMM)."""
     Cout, Cin, R, S = w.shape
-    g = grad_of(w)
+    g = grad_of(w if grad_param is None else grad_param)
     a = L.WgradArgs()
     a.struct_size = C.sizeof(L.WgradArgs)
     a.ntaps = fwd_taps(a.taps, x, R, S, stride, pad, dil)
@@ -371,13 +407,23 @@ class ConvBNAct:
         return y
 
     def forward_raw(self, cx, x, count_pad=0):
-        """conv + statistics only; returns (z, BNState) for a consumer with a BN prologue."""
+        """conv + statistics only; returns (z, BNState) for a consumer with a BN prologue.
+        x may be a RawNCHW image: the conv then runs as a pointwise GEMM over its patch matrix."""
         w = self.conv.weight
         Cout = w.shape[0]
         OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
         z = cx.new(x.N, OH, OW, Cout)
         train = cx.training and self.bn.training
         sums = cx.f64(2 * Cout) if train else None
+        if isinstance(x, RawNCHW):
+            assert self.dil == 1
+            x = im2col(cx, x, w.shape[2], w.shape[3], self.stride, self.pad)
+            conv_fwd(cx, x, patch_weight(w), z, stats=sums)
+            st = bn_state(cx, self.bn, sums, x.N * OH * OW)
+            self.saved = (x, z, st, 0.0, 0)
+            self.patch = True
+            return z, st
+        self.patch = False
         conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
         st = bn_state(cx, self.bn, sums, x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad))
         self.saved = (x, z, st, 0.0, 0)
@@ -394,6 +440,11 @@ class ConvBNAct:
         x = self.saved[0]
         w = self.conv.weight
         self.saved = None
+        if getattr(self, "patch", False):
+            assert not need_dx, "the patch GEMM is used for network inputs only"
+            if w.requires_grad:
+                conv_wgrad(cx, x, dz, patch_weight(w), grad_param=w)
+            return None
         if w.requires_grad:
             conv_wgrad(cx, x, dz, w, self.stride, self.pad, self.dil)
         if not need_dx:

@@ -49,6 +49,7 @@ class InvertedResidual(nn.Module):
 
 class MobileNetV2Run(RunBase):
     """One forward/backward of the backbone on Act views."""
+    raw_inputs = True   # the stem reads the NCHW fp32 image through the patch kernel
 
     def __init__(self, mod):
         feats = mod.features

@@ -20,6 +20,8 @@ import torch
 
 
 class DeepLabRun(RunBase):
+    raw_inputs = True   # see MobileNetV2Run
+
     def __init__(self, mod):
         self.backbone = MobileNetV2Run(mod.backbone)
         self.aspp = ASPPRun(mod.aspp)

@@ -6,17 +6,20 @@ mask into the next layer's data-gradient epilogue.
 import torch.nn as nn
 
 from .. import _lib as L
-from ..engine import conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up
+from ..engine import conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up, im2col, patch_weight, Act
 from ..runtime import RunBase, call_module
 
 
 class FCDiscriminatorRun(RunBase):
+    raw_inputs = True   # conv1 reads the NCHW fp32 input through the patch kernel (19 channels, 16 taps)
+
     def __init__(self, mod):
         self.convs = [mod.conv1, mod.conv2, mod.conv3, mod.conv4, mod.classifier]
         self.slope = mod.leaky_relu.negative_slope
 
     def forward(self, cx, x):
-        acts = [x]
+        self.in_shape = (x.N, x.H, x.W, x.C)
+        acts = [im2col(cx, x, 4, 4, 2, 1)]   # conv1 as a pointwise GEMM over 4x4 patches
         h = x
         for i, c in enumerate(self.convs):
             last = i == len(self.convs) - 1
@@ -24,8 +27,11 @@ class FCDiscriminatorRun(RunBase):
             OH, OW = conv_out_hw(h.H, h.W, 4, 4, 2, 1, 1)
             y = cx.new(h.N, OH, OW, round_up(Cout, 8), zero=Cout % 8 != 0)
             y.C = Cout
-            conv_fwd(cx, h, c.weight, y, stride=2, pad=1, bias=c.bias,
-                     act=L.ACT_NONE if last else L.ACT_LEAKY, slope=self.slope)
+            if i == 0:
+                conv_fwd(cx, acts[0], patch_weight(c.weight), y, bias=c.bias, act=L.ACT_LEAKY, slope=self.slope)
+            else:
+                conv_fwd(cx, h, c.weight, y, stride=2, pad=1, bias=c.bias,
+                         act=L.ACT_NONE if last else L.ACT_LEAKY, slope=self.slope)
             acts.append(y)
             h = y
         self.acts = acts
@@ -40,13 +46,21 @@ class FCDiscriminatorRun(RunBase):
             c = self.convs[i]
             xin = acts[i]
             if c.weight.requires_grad:
-                conv_wgrad(cx, xin, d, c.weight, stride=2, pad=1)
+                if i == 0:
+                    conv_wgrad(cx, xin, d, patch_weight(c.weight), grad_param=c.weight)
+                else:
+                    conv_wgrad(cx, xin, d, c.weight, stride=2, pad=1)
             if c.bias is not None and c.bias.requires_grad:
                 bias_grad(cx, d, c.bias)
             if i == 0 and not need_dx:
                 return None
-            dx = cx.new(xin.N, xin.H, xin.W, xin.pitch)
-            dx.C = xin.C
+            if i == 0:
+                N, H, W, Cc = self.in_shape   # gradient w.r.t. the input pixels: the ordinary 4x4 data gradient
+                dx = cx.new(N, H, W, round_up(Cc, 8))
+                dx.C = Cc
+            else:
+                dx = cx.new(xin.N, xin.H, xin.W, xin.pitch)
+                dx.C = xin.C
             # dz_{i-1} = dgrad * leaky'(y_{i-1}); the first layer's input has no activation
             conv_dgrad(cx, d, c.weight, dx, stride=2, pad=1, aux=xin if i > 0 else None,
                        aux_mode=L.AUX_LEAKY_MASK if i > 0 else L.AUX_NONE, slope=self.slope)

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .engine import Act, Ctx, BF16, round_up, _vp
+from .engine import Act, Ctx, BF16, RawNCHW, round_up, _vp
 
 
 def sync_group_for(module):
@@ -58,7 +58,8 @@ class ModuleFn(torch.autograd.Function):
             cx = Ctx(dev, module.training, sync_group_for(module) if module.training else None,
                      dropout=not getattr(module, "_s2r_no_dropout", False))
             run = make_run()
-            acts = [to_nhwc(cx, x) for x in inputs]
+            raw = getattr(run, "raw_inputs", False)
+            acts = [RawNCHW(x) if raw else to_nhwc(cx, x) for x in inputs]
             outs = run.forward(cx, *acts)
             if not isinstance(outs, tuple):
                 outs = (outs,)
