@@ -335,6 +335,33 @@ def test_bilinear_align_corners(eng, cx, Hi, Wi, Ho, Wo):
     assert float(dx2.t[..., 19:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("case", [(2, 3, 33, 40, 3, 3, 2, 1), (2, 19, 32, 64, 4, 4, 2, 1), (1, 19, 17, 23, 4, 4, 2, 1),
+                                  (1, 3, 10, 300, 3, 3, 2, 1), (1, 5, 9, 132, 3, 3, 1, 1)])
+def test_im2col_patch_gemm(eng, cx, case):
+    """Patch matrix from NCHW fp32 (k = (c*R+ky)*S+kx, the OIHW order) and the conv / weight gradient through it."""
+    N, Cc, H, W, R, S, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, Cc, H, W, device="cuda", generator=g)
+    P = eng.im2col(cx, eng.RawNCHW(x), R, S, stride, pad)
+    OH, OW = eng.conv_out_hw(H, W, R, S, stride, pad, 1)
+    ref = F.unfold(bf(x), (R, S), padding=pad, stride=stride).view(N, Cc * R * S, OH, OW).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert P.t.shape == (N, OH, OW, eng.round_up(Cc * R * S, 8))
+    assert torch.equal(P.t[..., :Cc * R * S].float(), ref)
+    assert float(P.t[..., Cc * R * S:].abs().sum()) == 0.0
+    w = torch.nn.Parameter(torch.randn(16, Cc, R, S, device="cuda", generator=g) * 0.2)
+    out = cx.new(N, OH, OW, 16)
+    eng.conv_fwd(cx, P, eng.patch_weight(w), out)
+    y_ref = F.conv2d(bf(x), bf(w.detach()), None, stride, pad)
+    assert rel(to_nchw(out), y_ref) < 4e-3
+    dy = bf(torch.randn(N, 16, OH, OW, device="cuda", generator=g))
+    eng.conv_wgrad(cx, P, nhwc_act(eng, dy), eng.patch_weight(w), grad_param=w)
+    torch.cuda.synchronize()
+    wr = bf(w.detach()).requires_grad_(True)
+    F.conv2d(bf(x), wr, None, stride, pad).backward(dy)
+    assert rel(w.grad, wr.grad) < 4e-3
+
+
 def test_avgpool_broadcast_layout(eng, cx):
     L = sub("_lib")
     x = bf(torch.randn(3, 320, 7, 9, device="cuda"))
