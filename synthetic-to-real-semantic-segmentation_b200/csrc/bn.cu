@@ -382,11 +382,13 @@ __device__ __forceinline__ void load_pairs(const float* __restrict__ p, float sc
   o[3] = make_float2(b.z * scale, b.w * scale);
 }
 
-template <int ACT, bool RES>
+template <int ACT, bool RES, bool DROP>
 __global__ void __launch_bounds__(256)
 bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
                      const float* __restrict__ scale_shift, const __nv_bfloat16* __restrict__ residual,
-                     __nv_bfloat16* __restrict__ y, int ypitch, int yoff, int rows) {
+                     __nv_bfloat16* __restrict__ y, int ypitch, int yoff, int rows, float drop_p,
+                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  if (DROP && seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
   const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
@@ -399,8 +401,10 @@ bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, in
   const __nv_bfloat16* rp = RES ? residual + p0 * C + g * 8 : nullptr;
   __nv_bfloat16* yp = y + p0 * ypitch + yoff + g * 8;
   const long long sx = step * xpitch, sr = step * C, sy = step * ypitch;
-  auto one = [&](const uint4& xvv, const uint4& rvv, __nv_bfloat16* dst) {
+  auto one = [&](const uint4& xvv, const uint4& rvv, __nv_bfloat16* dst, long long prow) {
     Lean8 v = lean_unpack(xvv);
+    float m[8];
+    if (DROP) dropout_scale8(seed, (unsigned long long)(prow * cg + g), drop_p, m);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (ACT == S2R_ACT_RELU6) {
@@ -412,6 +416,10 @@ bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, in
           v.v[i].x = fmaxf(v.v[i].x, 0.f);
           v.v[i].y = fmaxf(v.v[i].y, 0.f);
         }
+      }
+      if (DROP) {
+        v.v[i].x *= m[2 * i];
+        v.v[i].y *= m[2 * i + 1];
       }
     }
     if (RES) {
@@ -430,22 +438,31 @@ bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, in
       rv[u] = RES ? ldg16(rp + u * sr) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) one(xv[u], rv[u], yp + u * sy);
+    for (int u = 0; u < UNR; ++u) one(xv[u], rv[u], yp + u * sy, p0 + u * step);
   }
   for (; p0 < P; p0 += step, xp += sx, yp += sy, rp += RES ? sr : 0)
-    one(ldg16(xp), RES ? ldg16(rp) : make_uint4(0u, 0u, 0u, 0u), yp);
+    one(ldg16(xp), RES ? ldg16(rp) : make_uint4(0u, 0u, 0u, 0u), yp, p0);
 }
 
 // APPLY = false: dsums += [sum gd, sum gd*xhat];  APPLY = true: dx = scale*(gd - m1 - xhat*m2)
-template <int ACT, bool APPLY>
+template <int ACT, bool APPLY, bool DROP>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, const __nv_bfloat16* __restrict__ x,
                    int xpitch, int xoff, const float* __restrict__ mean_invstd, const float* __restrict__ scale_shift,
                    double* __restrict__ dsums, double count, long long P, int C, __nv_bfloat16* __restrict__ dx,
-                   int dxpitch, int dxoff, int rows) {
+                   int dxpitch, int dxoff, int rows, float* __restrict__ dgamma, float* __restrict__ dbeta, float drop_p,
+                   unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ float sm[];
+  if (DROP && seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (APPLY && blockIdx.x == 0 && r == 0) {   // parameter gradients from the (final) sums: dgamma += sum gd*xhat
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (dbeta) dbeta[g * 8 + i] += (float)dsums[g * 8 + i];
+      if (dgamma) dgamma[g * 8 + i] += (float)dsums[C + g * 8 + i];
+    }
+  }
   const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
   float2 sc[4], sh[4];   // activation mask: pre (or pre/6)
   if (ACT != S2R_ACT_NONE) {
@@ -484,12 +501,18 @@ bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
   const __nv_bfloat16* xp = x + p0 * xpitch + xoff + g * 8;
   __nv_bfloat16* op = APPLY ? dx + p0 * dxpitch + dxoff + g * 8 : nullptr;
   const long long sd = step * dypitch, sx = step * xpitch, so = step * dxpitch;
-  auto one = [&](const uint4& dvv, const uint4& xvv, __nv_bfloat16* dst) {
+  auto one = [&](const uint4& dvv, const uint4& xvv, __nv_bfloat16* dst, long long prow) {
     Lean8 gd = lean_unpack(dvv);
     const Lean8 xx = lean_unpack(xvv);
     Lean8 o;
+    float m[8];
+    if (DROP) dropout_scale8(seed, (unsigned long long)(prow * cg + g), drop_p, m);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      if (DROP) {
+        gd.v[i].x *= m[2 * i];
+        gd.v[i].y *= m[2 * i + 1];
+      }
       if (ACT == S2R_ACT_RELU6) {
         float2 a6;
         a6.x = __saturatef(fmaf(xx.v[i].x, sc[i].x, sh[i].x));
@@ -516,9 +539,9 @@ bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
       xv[u] = ldg16(xp + u * sx);
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) one(dv[u], xv[u], APPLY ? op + u * so : nullptr);
+    for (int u = 0; u < UNR; ++u) one(dv[u], xv[u], APPLY ? op + u * so : nullptr, p0 + u * step);
   }
-  for (; p0 < P; p0 += step, dp += sd, xp += sx, op += APPLY ? so : 0) one(ldg16(dp), ldg16(xp), op);
+  for (; p0 < P; p0 += step, dp += sd, xp += sx, op += APPLY ? so : 0) one(ldg16(dp), ldg16(xp), op, p0);
   if (!APPLY) {
     // xhat form: sum gd*xhat = invstd * (sum gd*x - mean * sum gd), per thread before the block reduction
     float mu[8], is[8];
@@ -623,21 +646,25 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
   S2R_REQUIRE(drop_p >= 0.f && drop_p < 1.f, S2R_ERR_SHAPE, "bn_apply: dropout p=%f", drop_p);
   if (P == 0) return S2R_OK;
   const ElemCfg cfg = elem_cfg(P, C);
-  if (drop_p == 0.f && getenv("S2R_BN_GENERIC") == nullptr) {
+  if (getenv("S2R_BN_GENERIC") == nullptr && (drop_p == 0.f || (act == S2R_ACT_RELU && !residual))) {
     const __nv_bfloat16 *xb = (const __nv_bfloat16*)x, *rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     cudaStream_t st = (cudaStream_t)stream;
-#define S2R_APPLY(ACT_)                                                                                                \
-  do {                                                                                                                 \
-    if (residual)                                                                                                      \
-      bn_apply_lean_kernel<ACT_, true><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows); \
-    else                                                                                                               \
-      bn_apply_lean_kernel<ACT_, false><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows); \
-  } while (0)
-    if (act == S2R_ACT_NONE) { S2R_APPLY(S2R_ACT_NONE); S2R_LAUNCH_OK(); return S2R_OK; }
-    if (act == S2R_ACT_RELU) { S2R_APPLY(S2R_ACT_RELU); S2R_LAUNCH_OK(); return S2R_OK; }
-    if (act == S2R_ACT_RELU6) { S2R_APPLY(S2R_ACT_RELU6); S2R_LAUNCH_OK(); return S2R_OK; }
+    const unsigned long long* sd = (const unsigned long long*)seed_dev;
+#define S2R_APPLY(ACT_, RES_, DROP_)                                                                                     \
+  bn_apply_lean_kernel<ACT_, RES_, DROP_><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, \
+                                                                            ypitch, yoff, cfg.rows, drop_p, seed, sd)
+    bool done = true;
+    if (drop_p > 0.f) S2R_APPLY(S2R_ACT_RELU, false, true);
+    else if (act == S2R_ACT_NONE) { if (residual) S2R_APPLY(S2R_ACT_NONE, true, false); else S2R_APPLY(S2R_ACT_NONE, false, false); }
+    else if (act == S2R_ACT_RELU) { if (residual) S2R_APPLY(S2R_ACT_RELU, true, false); else S2R_APPLY(S2R_ACT_RELU, false, false); }
+    else if (act == S2R_ACT_RELU6) { if (residual) S2R_APPLY(S2R_ACT_RELU6, true, false); else S2R_APPLY(S2R_ACT_RELU6, false, false); }
+    else done = false;
 #undef S2R_APPLY
+    if (done) {
+      S2R_LAUNCH_OK();
+      return S2R_OK;
+    }
   }
   bn_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
@@ -658,15 +685,19 @@ extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const v
   if (P == 0) return S2R_OK;
   RowReduceCfg cfg = row_reduce_cfg(P, C);
   size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
-  if (drop_p == 0.f && getenv("S2R_BN_GENERIC") == nullptr && (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) {
+  if (getenv("S2R_BN_GENERIC") == nullptr &&
+      ((drop_p == 0.f && (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) || (drop_p > 0.f && act == S2R_ACT_RELU))) {
     const __nv_bfloat16 *db = (const __nv_bfloat16*)dy, *xb = (const __nv_bfloat16*)x;
     cudaStream_t st = (cudaStream_t)stream;
-    if (act == S2R_ACT_NONE)
-      bn_bwd_lean_kernel<S2R_ACT_NONE, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
-    else if (act == S2R_ACT_RELU)
-      bn_bwd_lean_kernel<S2R_ACT_RELU, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
-    else
-      bn_bwd_lean_kernel<S2R_ACT_RELU6, false><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows);
+    const unsigned long long* sd = (const unsigned long long*)seed_dev;
+#define S2R_RED(ACT_, DROP_)                                                                                          \
+  bn_bwd_lean_kernel<ACT_, false, DROP_><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff,     \
+      mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows, nullptr, nullptr, drop_p, seed, sd)
+    if (drop_p > 0.f) S2R_RED(S2R_ACT_RELU, true);
+    else if (act == S2R_ACT_NONE) S2R_RED(S2R_ACT_NONE, false);
+    else if (act == S2R_ACT_RELU) S2R_RED(S2R_ACT_RELU, false);
+    else S2R_RED(S2R_ACT_RELU6, false);
+#undef S2R_RED
     S2R_LAUNCH_OK();
     return S2R_OK;
   }
@@ -686,6 +717,28 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
   S2R_REQUIRE(vec_ok(dy, dypitch, dyoff) && vec_ok(x, xpitch, xoff) && vec_ok(dx, dxpitch, dxoff) &&
                   ((uintptr_t)scale_shift % 16 == 0) && ((uintptr_t)mean_invstd % 16 == 0),
               S2R_ERR_SHAPE, "bn_bwd_apply: bad pitch/offset/alignment");
+  const bool lean = dx && P > 0 && win_pad == 0 && getenv("S2R_BN_GENERIC") == nullptr &&
+                    ((drop_p == 0.f && (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) ||
+                     (drop_p > 0.f && act == S2R_ACT_RELU));
+  if (lean) {
+    const ElemCfg cfg = elem_cfg(P, C);
+    const __nv_bfloat16 *db = (const __nv_bfloat16*)dy, *xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* ob = (__nv_bfloat16*)dx;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long* sd = (const unsigned long long*)seed_dev;
+    // the parameter gradients (dgamma, dbeta) are added by block 0 of the same launch
+#define S2R_APP(ACT_, DROP_)                                                                                          \
+  bn_bwd_lean_kernel<ACT_, true, DROP_><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff,         \
+      mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows, dgamma, dbeta,  \
+      drop_p, seed, sd)
+    if (drop_p > 0.f) S2R_APP(S2R_ACT_RELU, true);
+    else if (act == S2R_ACT_NONE) S2R_APP(S2R_ACT_NONE, false);
+    else if (act == S2R_ACT_RELU) S2R_APP(S2R_ACT_RELU, false);
+    else S2R_APP(S2R_ACT_RELU6, false);
+#undef S2R_APP
+    S2R_LAUNCH_OK();
+    return S2R_OK;
+  }
   if (dgamma || dbeta) {
     bn_param_grad_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(dsums, dgamma, dbeta, C);
     S2R_LAUNCH_OK();
@@ -694,20 +747,6 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
   S2R_REQUIRE(win_pad == 0 || (win_H >= 1 && win_W >= 1 && P % ((int64_t)win_H * win_W) == 0), S2R_ERR_SHAPE,
               "bn_bwd_apply: window %dx%d does not tile P", win_H, win_W);
   const ElemCfg cfg = elem_cfg(P, C);
-  if (drop_p == 0.f && win_pad == 0 && getenv("S2R_BN_GENERIC") == nullptr &&
-      (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6)) {
-    const __nv_bfloat16 *db = (const __nv_bfloat16*)dy, *xb = (const __nv_bfloat16*)x;
-    __nv_bfloat16* ob = (__nv_bfloat16*)dx;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (act == S2R_ACT_NONE)
-      bn_bwd_lean_kernel<S2R_ACT_NONE, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
-    else if (act == S2R_ACT_RELU)
-      bn_bwd_lean_kernel<S2R_ACT_RELU, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
-    else
-      bn_bwd_lean_kernel<S2R_ACT_RELU6, true><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows);
-    S2R_LAUNCH_OK();
-    return S2R_OK;
-  }
   bn_bwd_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
       scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, dsums, count, P, C, (__nv_bfloat16*)dx,
