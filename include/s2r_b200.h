@@ -255,6 +255,20 @@ int s2r_sgd_step(const s2r_param_slot* slots, int nslots, const float* hyper, fl
 int s2r_adam_step(const s2r_param_slot* slots, int nslots, const float* hyper, float beta1,
                   float beta2, float eps, float weight_decay, float gscale, s2r_stream_t stream);
 
+/* ------------------------------------------------------------------ NVLink peer-memory exchange
+ * Replaces the master/slave reduce + broadcast of modeling/sync_batchnorm/comm.py:18-129 and
+ * batchnorm.py:90-111: a one-kernel, one-shot all-reduce of the small fp64 statistics vectors over CUDA IPC
+ * mapped peer memory.  s2r_comm_create writes this rank's 64-byte CUDA IPC handle; the host exchanges the
+ * handles (any transport) and passes all of them, indexed by rank, to s2r_comm_open.  Every rank must then issue
+ * the same sequence of s2r_allreduce_small_f64 calls.  The sequence counter lives on the device, so the calls may
+ * be captured in CUDA graphs. */
+int s2r_comm_create(int rank, int world, int slot_doubles, void* handle_out);
+int s2r_comm_open(const void* handles);
+int s2r_comm_ready(void);   /* world size once opened, else 0 */
+int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream);
+int s2r_comm_error(void);   /* non-zero: a bounded wait expired (synchronises the device) */
+int s2r_comm_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,10 +85,14 @@ PROTOTYPES = {
     "s2r_bce_logits_bwd": [vp, vp, f32, i64, vp, vp, vp],
     "s2r_confusion_matrix": [vp, i32, vp, i64, i32, vp, vp, vp],
     "s2r_argmax_confusion_nchw": [vp, vp, i32, i32, i64, i32, vp, vp, vp],
+    "s2r_comm_create": [i32, i32, i32, vp],
+    "s2r_comm_open": [vp],
+    "s2r_allreduce_small_f64": [vp, i32, vp],
     "s2r_sgd_step": [vp, i32, vp, f32, f32, f32, i32, f32, vp],
     "s2r_adam_step": [vp, i32, vp, f32, f32, f32, f32, f32, vp],
 }
-PLAIN = {"s2r_version": (i32, []), "s2r_last_error": (C.c_char_p, []), "s2r_device_ok": (i32, [])}
+PLAIN = {"s2r_version": (i32, []), "s2r_last_error": (C.c_char_p, []), "s2r_device_ok": (i32, []),
+         "s2r_comm_ready": (i32, []), "s2r_comm_error": (i32, []), "s2r_comm_destroy": (i32, [])}
 
 _lib = None
 launches = 0  # number of C-ABI compute calls issued by this process (bench.py reports it)

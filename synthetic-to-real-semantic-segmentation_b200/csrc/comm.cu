@@ -1,0 +1,190 @@
+// One-shot all-reduce of small fp64 vectors over NVLink peer memory, for the synchronised-BatchNorm
+// statistics exchange: the per-channel (sum, sum of squares) of the forward pass and (sum dy, sum dy*xhat)
+// of the backward pass (modeling/sync_batchnorm/batchnorm.py:55-78,90-111 of the reference: reduce to the
+// master + broadcast through Python queues; here: every rank is its own master).
+//
+// A step has ~240 such exchanges (60 BatchNorm layers x 2 passes x forward/backward), each a few kilobytes and
+// each on the critical path, so what matters is latency, not bandwidth.  One kernel, one CTA:
+//   1. every rank stores its vector into slot [seq % DEPTH][rank] of every peer's inbox (plain stores to the
+//      peer's mapped memory: NVLink writes through NVSwitch) in the LL wire format described below -- payload and
+//      sequence number in the same 8-byte word, so there is no fence and no separate flag;
+//   2. it polls the words of its own inbox until they carry seq and sums the contributions in rank order
+//      (bitwise identical on every rank) into the caller's buffer.
+// seq lives in device memory and is advanced by the kernel itself, so captured CUDA graphs replay correctly.
+// A slot is reused only DEPTH exchanges later; a rank can be at most one exchange ahead of any peer (it cannot
+// finish exchange k before every peer has contributed to k), so DEPTH = 4 is ample.  Waits are bounded: after
+// ~20 s without progress the kernel records an error code and returns instead of hanging the GPU.
+//
+// Set-up: each process allocates its inbox with cudaMalloc, exports a CUDA IPC handle, and opens the handles
+// of its peers (exchanged by the host through torch.distributed -- plumbing, not the data path).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int CM_DEPTH = 4;
+constexpr int CM_MAX_WORLD = 16;
+constexpr int CM_THREADS = 512;
+
+struct CommDev {
+  double* inbox[CM_MAX_WORLD];                 // base of every rank's inbox region (peer-mapped)
+  unsigned long long* flags[CM_MAX_WORLD];     // base of every rank's flag array [DEPTH][world]
+  unsigned long long* seq;                     // local: exchange counter
+  int* err;                                    // local: sticky error flag
+  int rank, world, slot;                       // slot: doubles per (depth, rank) entry
+};
+
+struct CommHost {
+  bool ready = false;
+  int rank = 0, world = 1, slot = 0;
+  void* local = nullptr;                       // cudaMalloc'ed region: inbox | flags | seq | err
+  void* peers[CM_MAX_WORLD] = {nullptr};
+  size_t inbox_bytes = 0, flags_bytes = 0;
+  CommDev dev;
+};
+
+CommHost g_comm;
+
+// Low-latency ("LL") wire format: every 8-byte word carries 32 payload bits and the 32-bit sequence number of
+// the exchange, so data and flag arrive in ONE atomic store -- no fence, no separate flag write, no second
+// NVLink round trip.  A double travels as two such words.  The reader polls each word until its sequence field
+// matches; a slot still holding the words of exchange seq - DEPTH can never match.
+__device__ __forceinline__ void st_word(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(CM_THREADS)
+allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c) {
+  const unsigned long long seq = *c.seq + 1;      // every thread reads it; thread 0 advances it at the end
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
+  const int d = (int)(seq % CM_DEPTH);
+  const size_t slot_words = (size_t)c.slot * 2;
+  // 1. contribute to every peer's inbox
+  for (int i = threadIdx.x; i < n; i += CM_THREADS) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    for (int r = 0; r < c.world; ++r) {
+      if (r == c.rank) continue;
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.inbox[r]) + ((size_t)d * c.world + c.rank) * slot_words;
+      st_word(dst + 2 * i, w0);
+      st_word(dst + 2 * i + 1, w1);
+    }
+  }
+  // 2. + 3. poll every rank's words and sum in rank order (own value taken from buf)
+  const unsigned long long* in = reinterpret_cast<const unsigned long long*>(c.inbox[c.rank]) + (size_t)d * c.world * slot_words;
+  bool timed_out = false;
+  for (int i = threadIdx.x; i < n; i += CM_THREADS) {
+    double acc = 0.0;
+    const double mine = buf[i];
+    for (int r = 0; r < c.world; ++r) {
+      if (r == c.rank) {
+        acc += mine;
+        continue;
+      }
+      const unsigned long long* src = in + (size_t)r * slot_words + 2 * i;
+      unsigned long long w0 = ld_word(src), w1 = ld_word(src + 1);
+      if (((w0 ^ tag) >> 32) != 0 || ((w1 ^ tag) >> 32) != 0) {
+        const long long t0 = clock64();
+        while (true) {
+          w0 = ld_word(src);
+          w1 = ld_word(src + 1);
+          if (((w0 ^ tag) >> 32) == 0 && ((w1 ^ tag) >> 32) == 0) break;
+          if (timed_out || clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone; do not hang the GPU
+            timed_out = true;
+            break;
+          }
+        }
+      }
+      acc += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+    buf[i] = acc;
+  }
+  if (timed_out) atomicExch(c.err, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) *c.seq = seq;
+}
+
+}  // namespace
+
+/* Allocates this rank's inbox (slot_doubles per contribution) and writes its 64-byte CUDA IPC handle. */
+extern "C" int s2r_comm_create(int rank, int world, int slot_doubles, void* handle_out) {
+  S2R_REQUIRE(!g_comm.ready && g_comm.local == nullptr, S2R_ERR_SHAPE, "comm: already created");
+  S2R_REQUIRE(world >= 1 && world <= CM_MAX_WORLD && rank >= 0 && rank < world && slot_doubles >= 2 && handle_out,
+              S2R_ERR_SHAPE, "comm: bad rank/world/slot");
+  CommHost& h = g_comm;
+  h.rank = rank; h.world = world; h.slot = (slot_doubles + 1) & ~1;
+  h.inbox_bytes = (size_t)CM_DEPTH * world * h.slot * 2 * sizeof(unsigned long long);   // LL words: 2 per double
+  h.flags_bytes = (size_t)CM_DEPTH * world * sizeof(unsigned long long);
+  const size_t total = h.inbox_bytes + h.flags_bytes + 256;
+  S2R_CUDA_OK(cudaMalloc(&h.local, total));
+  S2R_CUDA_OK(cudaMemset(h.local, 0, total));
+  S2R_CUDA_OK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ih;
+  S2R_CUDA_OK(cudaIpcGetMemHandle(&ih, h.local));
+  static_assert(sizeof(ih) == 64, "CUDA IPC handle size");
+  memcpy(handle_out, &ih, sizeof(ih));
+  return S2R_OK;
+}
+
+/* handles: world x 64 bytes, indexed by rank (this rank's own entry is ignored). */
+extern "C" int s2r_comm_open(const void* handles) {
+  CommHost& h = g_comm;
+  S2R_REQUIRE(h.local != nullptr && !h.ready && handles, S2R_ERR_SHAPE, "comm: create first");
+  for (int r = 0; r < h.world; ++r) {
+    if (r == h.rank) {
+      h.peers[r] = h.local;
+    } else {
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, (const char*)handles + (size_t)r * 64, 64);
+      S2R_CUDA_OK(cudaIpcOpenMemHandle(&h.peers[r], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  for (int r = 0; r < h.world; ++r) {
+    h.dev.inbox[r] = (double*)h.peers[r];
+    h.dev.flags[r] = (unsigned long long*)((char*)h.peers[r] + h.inbox_bytes);
+  }
+  h.dev.seq = (unsigned long long*)((char*)h.local + h.inbox_bytes + h.flags_bytes);
+  h.dev.err = (int*)((char*)h.local + h.inbox_bytes + h.flags_bytes + 64);
+  h.dev.rank = h.rank; h.dev.world = h.world; h.dev.slot = h.slot;
+  h.ready = true;
+  return S2R_OK;
+}
+
+extern "C" int s2r_comm_ready() { return g_comm.ready ? g_comm.world : 0; }
+
+/* In-place sum over all ranks of buf[0..n) (fp64).  Every rank must issue the same sequence of calls. */
+extern "C" int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream) {
+  const CommHost& h = g_comm;
+  S2R_REQUIRE(h.ready, S2R_ERR_SHAPE, "comm: not initialised");
+  S2R_REQUIRE(buf && n >= 1 && n <= h.slot, S2R_ERR_SHAPE, "allreduce_small: n=%d exceeds the slot of %d doubles", n, h.slot);
+  if (h.world == 1) return S2R_OK;
+  allreduce_small_kernel<<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+/* Non-zero after a bounded wait expired (a peer died); reading it synchronises the device. */
+extern "C" int s2r_comm_error() {
+  const CommHost& h = g_comm;
+  if (!h.ready) return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, h.dev.err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return e;
+}
+
+extern "C" int s2r_comm_destroy() {
+  CommHost& h = g_comm;
+  if (h.local == nullptr) return S2R_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < h.world; ++r)
+    if (r != h.rank && h.peers[r]) cudaIpcCloseMemHandle(h.peers[r]);
+  cudaFree(h.local);
+  h = CommHost();
+  return S2R_OK;
+}

@@ -66,6 +66,32 @@ class Act:
 POISON = bool(os.environ.get("S2R_POISON"))   # fill uninitialised activation buffers with NaN (tests/debug)
 
 
+PEER = {"world": 0, "slot": 0}
+
+
+def init_peer_exchange(group=None, slot=4096):
+    """Set up the NVLink peer-memory exchange for the BN statistics (csrc/comm.cu): allocate this rank's inbox,
+    swap CUDA IPC handles through torch.distributed (plumbing) and open the peers.  Idempotent; S2R_COMM=nccl
+    keeps every exchange on NCCL."""
+    import torch.distributed as dist
+    if os.environ.get("S2R_COMM", "") == "nccl" or not (dist.is_available() and dist.is_initialized()):
+        return False
+    world = dist.get_world_size(group)
+    if world <= 1 or PEER["world"] == world:
+        return PEER["world"] == world
+    rank = dist.get_rank(group)
+    handle = C.create_string_buffer(64)
+    L.call("s2r_comm_create", rank, world, slot, C.cast(handle, C.c_void_p))
+    handles = [None] * world
+    dist.all_gather_object(handles, handle.raw, group=group)
+    blob = C.create_string_buffer(b"".join(handles), 64 * world)
+    L.call("s2r_comm_open", C.cast(blob, C.c_void_p))
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    PEER["world"], PEER["slot"] = world, slot
+    return True
+
+
 class Ctx:
     """Per-call execution context (stream, mode, cross-rank synchronisation of BN)."""
 
@@ -78,6 +104,8 @@ class Ctx:
         if sync_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(sync_group)
+            if self.world > 1 and PEER["world"] != self.world and not torch.cuda.is_current_stream_capturing():
+                init_peer_exchange(sync_group)   # collective: every rank builds its first synchronised Ctx together
         self.dropout = dropout
         self.seed_dev = seed_counter(device)
         self.trace = TRACE  # when a list: receives (name, Act) of intermediate activations (tests/tools)
@@ -124,7 +152,12 @@ class Ctx:
         return act
 
     def allreduce(self, t):
+        """Sum of a small statistics vector over the ranks: the NVLink peer-memory kernel when the exchange has
+        been set up (init_peer_exchange), NCCL otherwise."""
         if self.world > 1:
+            if PEER["world"] == self.world and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= PEER["slot"]:
+                L.call("s2r_allreduce_small_f64", _vp(t), t.numel(), self.stream)
+                return
             import torch.distributed as dist
             dist.all_reduce(t, group=self.group)
 
