@@ -173,8 +173,45 @@ def dominant_kernel_roofline(torch, batch, h, w, peaks):
     flops = 2.0 * batch * H4 * W4 * 256 * 304 * 9
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = flops / t / 1e12
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 8, 512x1024 from the committed
+    # ncu --set full capture (profiles/r1m_conv_tc_decoder_ncu.txt: 135.7 MB + 115.8 MB; algorithmic 293 MB)
+    traffic = 251.5e6 if (batch, h, w) == (8, 512, 1024) else None
     return {"kernel": "tap-GEMM conv fwd 3x3 304->256 (decoder.last_conv.0)", "bound": "tensor", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+            "peak_source": peaks.get("_source", "fallback"), "launch_ms": t * 1e3}
+
+
+def depthwise_roofline(torch, batch, h, w, peaks):
+    """The largest depthwise launch of the step (features.2: 96 channels, 256x512 -> 128x256, stride 2, BN+ReLU6
+    prologue, statistics), timed alone with CUDA events and the L2 flushed: algorithmic bytes = input + output."""
+    import ctypes as C
+    eng = sub("engine")
+    L = sub("_lib")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cx = eng.Ctx(dev, True)
+    H2, W2, Cc = h // 2, w // 2, 96
+    x = eng.Act((torch.randn(batch, H2, W2, Cc, device=dev) * 2).to(torch.bfloat16))
+    ss = torch.cat([torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev)]).contiguous()
+    st = eng.BNState(ss, ss.clone(), 1.0, False)
+    wgt = torch.randn(Cc, 1, 3, 3, device=dev) * 0.3
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(6):
+        stats = cx.f64(2 * Cc)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = eng.dw_fwd(cx, x, st, L.ACT_RELU6, True, wgt, 2, 1, 1, stats)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    t = sum(times) / len(times)
+    byts = 2.0 * (x.t.numel() + y.t.numel())
+    peak = peaks.get("hbm_gbs", 6650.0)
+    ach = byts / t / 1e9
+    return {"kernel": "depthwise 3x3 stride 2 + BN/ReLU6 prologue + statistics, 96 ch 256x512 (features.2)", "bound": "hbm",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "peak_source": peaks.get("_source", "fallback"), "launch_ms": t * 1e3}
 
 
@@ -290,12 +327,15 @@ def run_b200(args):
                                "+ FCDiscriminator, src+tgt %dx%d crops, batch %d/GPU, SGD+Adam, random init" % (H, W, B),
                    "pairs_per_step_per_gpu": B, "parallelism": "dp%d" % world, "sync_bn": world > 1,
                    "dropout": not args.no_dropout, "cuda_graph": use_graph,
+                   "bn_exchange": ("nvlink peer memory (csrc/comm.cu)" if sub("engine").PEER["world"] == world else "nccl")
+                   if world > 1 else "none",
                    "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_src.numel() * 4 * 2 + h_lab.numel() * 4),
                 "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps if use_graph else launches,
         "clocks": clk.summary(),
         "roofline": roof,
+        "roofline_depthwise": depthwise_roofline(torch, B, H, W, peaks),
     }
     if not args.no_cpu_baseline and world == 1:
         val, dt, threads = cpu_adapt_steps(args.cpu_batch, H, W, 1, 1)
