@@ -78,6 +78,39 @@ class AdaptStep(object):
         self._graph.replay()
         return self._static_out
 
+    # ---- input pipelining for the captured step: the next step's host tensors are copied into device staging
+    # buffers on a copy stream while the current graph replay runs; the replay then starts with a device-to-device
+    # copy into the graph's static inputs (what a prefetching data loader does around train_adapt.py:126-129).
+    def stage(self, src_image, src_label, tgt_image):
+        """Start the asynchronous host->device copy of one step's inputs (pinned host tensors)."""
+        dev = self._static[0].device
+        if getattr(self, "_stage_bufs", None) is None:
+            self._stage_bufs = tuple(torch.empty_like(t) for t in self._static)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = None
+        # the staging buffers may still be read by the previous replay's device-to-device copy (but the copy
+        # must NOT wait for the replay itself, which is what it is meant to overlap)
+        if getattr(self, "_d2d_done", None) is not None:
+            self._copy_stream.wait_event(self._d2d_done)
+        with torch.cuda.stream(self._copy_stream):
+            for b, t in zip(self._stage_bufs, (src_image, src_label, tgt_image)):
+                b.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = ev
+
+    def replay_staged(self, i=0, epoch=0):
+        """Replay the captured step on the inputs of the last stage() call."""
+        assert getattr(self, "_staged", None) is not None, "stage() first"
+        cur = torch.cuda.current_stream(self._static[0].device)
+        cur.wait_event(self._staged)
+        self._staged = None
+        for st, b in zip(self._static, self._stage_bufs):
+            st.copy_(b, non_blocking=True)
+        self._d2d_done = torch.cuda.Event()
+        self._d2d_done.record(cur)
+        return self.replay(*self._static, i=i, epoch=epoch)
+
     def _device_step(self, src_image, src_label, tgt_image):
         model, model_D = self.model, self.model_D
         seed_counter(src_image.device).add_(1)
