@@ -48,6 +48,14 @@ __device__ __forceinline__ uint2 pack4(float2 a, float2 b) {
   u.y = *reinterpret_cast<uint32_t*>(&q);
   return u;
 }
+// 8-byte global store under a predicate, without control flow (a C++ `if (p) *dst = v` inside the row loop makes
+// the compiler branch around the store and costs 30 % of the stride-2 backward kernel)
+__device__ __forceinline__ void st8_if(void* dst, uint2 v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.u32 [%0], {%1, %2};\n\t}"
+               ::"l"(dst), "r"(v.x), "r"(v.y), "r"((unsigned)p)
+               : "memory");
+}
+
 // a6 = sat(x*sc6 + sh6) for 4 packed bf16
 __device__ __forceinline__ void act4(uint2 raw, float2 scA, float2 scB, float2 shA, float2 shB, float2& aA, float2& aB) {
   float2 xa, xb;

@@ -38,6 +38,8 @@ struct S1Geom {
   int TW;           // columns per CTA
   int rs;           // rows per CTA
   int nseg;         // row segments per image
+  int tiles;        // column tiles
+  int nunits;       // N * nseg * tiles work units; a CTA (blockIdx.y) takes units blockIdx.y, +gridDim.y, ...
   int ext;          // backward: gradient domain extension (0 or 1)
   int stage_bytes;  // bytes of one ring stage (padded to 128)
   int xoff;         // backward: byte offset of the x tile inside a stage
@@ -46,10 +48,19 @@ struct S1Geom {
   int interior;     // backward: g has the unextended layout, border positions are not stored
 };
 
+// 8-byte shared-memory load at a 32-bit shared address plus a compile-time byte offset: the three neighbours of
+// a row are one address register and three immediates (CG is a template parameter)
+template <int OFF>
+__device__ __forceinline__ uint2 lds8(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------ forward
 // y[oh][ow] = sum_{ky,kx} a(oh+ky-1, ow+kx-1) w[ky][kx],  a = relu6(x*sc+sh) inside the image and
 // HALO ? relu6(sh) : 0 outside.  stats += per-channel sum / sum of squares of y.
-template <bool HALO>
+template <bool HALO, int CG>
 __global__ void __launch_bounds__(FWD_CONS + 32, 2)
 dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
                  __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G) {
@@ -57,14 +68,19 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
   __shared__ float red[8 * (FWD_CONS + 1)];
-  const int CG = G.CG, TWL = G.TW + 2;
+  const int TWL = G.TW + 2;
   const int ncons = G.TW * CG;                       // active consumer threads
   const int ncw = (ncons + 31) / 32;                 // consumer warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ow0 = blockIdx.y * G.TW;
-  const int n = blockIdx.z / G.nseg, seg = blockIdx.z - n * G.nseg;
-  const int oh0 = seg * G.rs, rows = min(G.rs, G.H - oh0);
-  const int nst = (rows + 2 + RB - 1) / RB;          // stages this CTA consumes
+  // Persistent over work units (image, row segment, column tile) of one channel chunk: the filter, the channel
+  // constants and the statistics accumulators stay in registers, the TMA ring keeps running across units, and the
+  // prologue / block reduction are paid once per CTA instead of once per tile.
+#define S1_UNIT(unit_)                                                   \
+  const int tile_ = (unit_) % G.tiles, rest_ = (unit_) / G.tiles;        \
+  const int seg_ = rest_ % G.nseg, n = rest_ / G.nseg;                   \
+  const int ow0 = tile_ * G.TW, oh0 = seg_ * G.rs;                       \
+  const int rows = min(G.rs, G.H - oh0);                                 \
+  const int nst = (rows + 2 + RB - 1) / RB;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < FWD_STAGES; ++s) {
@@ -79,13 +95,17 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     // ---------------- producer warp
     if (lane == 0) {
       prefetch_tmap(&xmap);
-      for (int k = 0; k < nst; ++k) {
-        const int s = k % FWD_STAGES;
-        if (k >= FWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((k / FWD_STAGES) - 1) & 1);
-        const uint32_t full = smem_addr(&bar_full[s]);
-        mbar_expect_tx(full, (uint32_t)(RB * TWL * CG * 8));
-        tma_load_4d(smem_addr(smem + (size_t)s * G.stage_bytes), &xmap, full, blockIdx.x * CG * 4, ow0 - 1,
-                    oh0 - 1 + k * RB, n);
+      int it = 0;
+      for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+        S1_UNIT(unit)
+        for (int k = 0; k < nst; ++k, ++it) {
+          const int s = it % FWD_STAGES;
+          if (it >= FWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((it / FWD_STAGES) - 1) & 1);
+          const uint32_t full = smem_addr(&bar_full[s]);
+          mbar_expect_tx(full, (uint32_t)(RB * TWL * CG * 8));
+          tma_load_4d(smem_addr(smem + (size_t)s * G.stage_bytes), &xmap, full, blockIdx.x * CG * 4, ow0 - 1,
+                      oh0 - 1 + k * RB, n);
+        }
       }
     }
   } else if (warp < ncw) {
@@ -94,8 +114,6 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     const int tid = live ? threadIdx.x : 0;
     const int g = tid % CG, j = tid / CG;
     const int c = (blockIdx.x * CG + g) * 4;
-    const int ow = ow0 + j;
-    const bool active = live && ow < G.W;
 
     float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
     const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
@@ -104,26 +122,34 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
     load_filter(w, c, 6.f, wA, wB);
 
-    const size_t rowp = (size_t)G.os_row;
-    __nv_bfloat16* yp = y + (size_t)n * G.os_img + (size_t)oh0 * G.os_row + (size_t)min(ow, G.W - 1) * G.os_pix + c;
+    const long long rowp = G.os_row;
+    const uint32_t tile0 = smem_addr(smem) + (uint32_t)(j * CG + g) * 8u;   // this thread's left neighbour in row 0 of stage 0
+    const uint32_t rowstride = (uint32_t)(TWL * CG) * 8u;
+    float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
+    int it = 0;
+    for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+    S1_UNIT(unit)
+    const int ow = ow0 + j;
+    const bool active = live && ow < G.W;
+    // running output pointer: row o = r - 2 of step r
+    __nv_bfloat16* yrow = y + (long long)n * G.os_img + (long long)(oh0 - 2) * G.os_row + (long long)min(ow, G.W - 1) * G.os_pix + c;
     const bool lok = ow - 1 >= 0, rok = ow + 1 < G.W;   // !HALO: zero (not relu6(shift)) outside the image
     float2 accA[3], accB[3];
-    float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
 #pragma unroll
     for (int i = 0; i < 3; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
 
-    for (int k = 0; k < nst; ++k) {
-      const int s = k % FWD_STAGES;
-      mbar_wait(smem_addr(&bar_full[s]), (k / FWD_STAGES) & 1);
-      const uint2* tile = reinterpret_cast<const uint2*>(smem + (size_t)s * G.stage_bytes) + j * CG + g;
+    for (int k = 0; k < nst; ++k, ++it) {
+      const int s = it % FWD_STAGES;
+      mbar_wait(smem_addr(&bar_full[s]), (it / FWD_STAGES) & 1);
+      const uint32_t tile = tile0 + (uint32_t)s * (uint32_t)G.stage_bytes;
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const int r = k * RB + u;            // input row oh0 - 1 + r
-        const uint2* rowt = tile + u * TWL * CG;
+        const uint32_t rowt = tile + (uint32_t)u * rowstride;
         float2 lA, lB, cA, cB, rA, rB;
-        act4(rowt[0], scA, scB, shA, shB, lA, lB);
-        act4(rowt[CG], scA, scB, shA, shB, cA, cB);
-        act4(rowt[2 * CG], scA, scB, shA, shB, rA, rB);
+        act4(lds8<0>(rowt), scA, scB, shA, shB, lA, lB);
+        act4(lds8<CG * 8>(rowt), scA, scB, shA, shB, cA, cB);
+        act4(lds8<CG * 16>(rowt), scA, scB, shA, shB, rA, rB);
         if (!HALO) {
           const bool row_ok = (unsigned)(oh0 - 1 + r) < (unsigned)G.H;
           if (!(row_ok && lok)) lA = lB = make_float2(0.f, 0.f);
@@ -138,18 +164,19 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
         accB[s1] = ffma2(rB, wB[5], ffma2(cB, wB[4], ffma2(lB, wB[3], accB[s1])));
         accA[s2] = ffma2(rA, wA[8], ffma2(cA, wA[7], ffma2(lA, wA[6], accA[s2])));
         accB[s2] = ffma2(rB, wB[8], ffma2(cB, wB[7], ffma2(lB, wB[6], accB[s2])));
-        const int o = r - 2;
-        if (o >= 0 && o < rows && active) {
-          *reinterpret_cast<uint2*>(yp + (size_t)o * rowp) = pack4(accA[s2], accB[s2]);
+        if ((unsigned)(r - 2) < (unsigned)rows && active) {
+          *reinterpret_cast<uint2*>(yrow) = pack4(accA[s2], accB[s2]);
           sA = fadd2(sA, accA[s2]);
           sB = fadd2(sB, accB[s2]);
           qA = ffma2(accA[s2], accA[s2], qA);
           qB = ffma2(accB[s2], accB[s2], qB);
         }
+        yrow += rowp;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&bar_empty[s]));
     }
+    }   // units
     if (stats) {
       const float v[8] = {sA.x, sA.y, sB.x, sB.y, qA.x, qA.y, qB.x, qB.y};
 #pragma unroll
@@ -178,6 +205,7 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
 //   dw[ky][kx] += 6*a6 * dy(ih+1-ky, iw+1-kx)
 // Input-stationary in dy: the dy row of step r feeds the g rows r, r-1, r-2 (filter rows 2, 1, 0) and, with
 // the a6 rows r-2, r-1, r, all nine weight-gradient taps.
+template <int CG>
 __global__ void __launch_bounds__(BWD_CONS + 32, 1)
 dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
                  const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ w,
@@ -186,15 +214,17 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[BWD_STAGES], bar_empty[BWD_STAGES];
   __shared__ float red[12 * (BWD_CONS + 1)];
-  const int CG = G.CG, TWL = G.TW + 2, ext = G.ext;
+  const int TWL = G.TW + 2, ext = G.ext;
   const int He = G.H + 2 * ext, We = G.W + 2 * ext;
   const int ncons = G.TW * CG;
   const int ncw = (ncons + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e0 = blockIdx.y * G.TW;
-  const int n = blockIdx.z / G.nseg, seg = blockIdx.z - n * G.nseg;
-  const int he0 = seg * G.rs, rows = min(G.rs, He - he0);
-  const int ih_start = he0 - ext;                    // image row of the first g row
+#define S1_BUNIT(unit_)                                                  \
+  const int tile_ = (unit_) % G.tiles, rest_ = (unit_) / G.tiles;        \
+  const int seg_ = rest_ % G.nseg, n = rest_ / G.nseg;                   \
+  const int e0 = tile_ * G.TW, he0 = seg_ * G.rs;                        \
+  const int rows = min(G.rs, He - he0);                                  \
+  const int ih_start = he0 - ext; /* image row of the first g row */     \
   const int nst = (rows + 2 + RB - 1) / RB;
 
   if (threadIdx.x == 0) {
@@ -216,15 +246,19 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     if (lane == 0) {
       prefetch_tmap(&dymap);
       prefetch_tmap(&xmap);
-      for (int k = 0; k < nst; ++k) {
-        const int s = k % BWD_STAGES;
-        if (k >= BWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((k / BWD_STAGES) - 1) & 1);
-        const uint32_t full = smem_addr(&bar_full[s]);
-        mbar_expect_tx(full, (uint32_t)(RB * (TWL + G.TW) * CG * 8));
-        unsigned char* st = smem + (size_t)s * G.stage_bytes;
-        // step r uses dy row ih_start-1+r (with one halo column per side) and x row ih_start+r
-        tma_load_4d(smem_addr(st), &dymap, full, blockIdx.x * CG * 4, e0 - ext - 1, ih_start - 1 + k * RB, n);
-        tma_load_4d(smem_addr(st + G.xoff), &xmap, full, blockIdx.x * CG * 4, e0 - ext, ih_start + k * RB, n);
+      int it = 0;
+      for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+        S1_BUNIT(unit)
+        for (int k = 0; k < nst; ++k, ++it) {
+          const int s = it % BWD_STAGES;
+          if (it >= BWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((it / BWD_STAGES) - 1) & 1);
+          const uint32_t full = smem_addr(&bar_full[s]);
+          mbar_expect_tx(full, (uint32_t)(RB * (TWL + G.TW) * CG * 8));
+          unsigned char* st = smem + (size_t)s * G.stage_bytes;
+          // step r uses dy row ih_start-1+r (with one halo column per side) and x row ih_start+r
+          tma_load_4d(smem_addr(st), &dymap, full, blockIdx.x * CG * 4, e0 - ext - 1, ih_start - 1 + k * RB, n);
+          tma_load_4d(smem_addr(st + G.xoff), &xmap, full, blockIdx.x * CG * 4, e0 - ext, ih_start + k * RB, n);
+        }
       }
     }
   } else if (warp < ncw) {
@@ -232,8 +266,6 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     const int tid = live ? threadIdx.x : 0;
     const int g = tid % CG, j = tid / CG;
     const int c = (blockIdx.x * CG + g) * 4;
-    const int we = e0 + j;
-    const bool active = live && we < We;
 
     float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
     const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
@@ -248,11 +280,20 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     float2 wA[9], wB[9];
     load_filter(w, c, 1.f, wA, wB);
 
-    const size_t growp = (size_t)G.os_row;
+    const long long growp = G.os_row;
     // interior layout: position (he, we) of the extended domain lives at (he - ext, we - ext) and exists only inside
     const int gsh = G.interior ? ext : 0;
-    __nv_bfloat16* gp = gout + (long long)n * G.os_img + (long long)(he0 - gsh) * G.os_row +
-                        (long long)(min(we, We - 1) - gsh) * G.os_pix + c;
+    const uint32_t dtile0 = smem_addr(smem) + (uint32_t)(j * CG + g) * 8u;
+    const uint32_t xtile0 = dtile0 + (uint32_t)G.xoff;
+    const uint32_t drowstride = (uint32_t)(TWL * CG) * 8u, xrowstride = (uint32_t)(G.TW * CG) * 8u;
+    int it = 0;
+    for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+    S1_BUNIT(unit)
+    const int we = e0 + j;
+    const bool active = live && we < We;
+    // running output pointer: row o = r - 2 of step r
+    __nv_bfloat16* grow = gout + (long long)n * G.os_img + (long long)(he0 - gsh - 2) * G.os_row +
+                          (long long)(min(we, We - 1) - gsh) * G.os_pix + c;
     const bool col_in = !G.interior || (unsigned)(we - ext) < (unsigned)G.W;
     float2 gA[3], gB[3], aA[3], aB[3];
     uint2 xr[3];
@@ -262,23 +303,21 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
       xr[i] = make_uint2(0u, 0u);
     }
 
-    for (int k = 0; k < nst; ++k) {
-      const int s = k % BWD_STAGES;
-      mbar_wait(smem_addr(&bar_full[s]), (k / BWD_STAGES) & 1);
-      const unsigned char* st = smem + (size_t)s * G.stage_bytes;
-      const uint2* dtile = reinterpret_cast<const uint2*>(st) + j * CG + g;
-      const uint2* xtile = reinterpret_cast<const uint2*>(st + G.xoff) + j * CG + g;
+    for (int k = 0; k < nst; ++k, ++it) {
+      const int s = it % BWD_STAGES;
+      mbar_wait(smem_addr(&bar_full[s]), (it / BWD_STAGES) & 1);
+      const uint32_t soff = (uint32_t)s * (uint32_t)G.stage_bytes;
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const int r = k * RB + u;            // dy row ih_start-1+r; g / x row o = r (relative to ih_start)
-        const uint2* drow = dtile + u * TWL * CG;
+        const uint32_t drow = dtile0 + soff + (uint32_t)u * drowstride;
         float2 lA, lB, cA, cB, rA, rB;       // dy at columns iw-1, iw, iw+1
-        unpack4(drow[0], lA, lB);
-        unpack4(drow[CG], cA, cB);
-        unpack4(drow[2 * CG], rA, rB);
+        unpack4(lds8<0>(drow), lA, lB);
+        unpack4(lds8<CG * 8>(drow), cA, cB);
+        unpack4(lds8<CG * 16>(drow), rA, rB);
         const int s0 = u, s1 = (u + 2) % 3, s2 = (u + 1) % 3;   // slots of g rows r, r-1, r-2
         // x / a6 of row o = r (zero contribution outside this CTA's rows or columns)
-        xr[s0] = xtile[u * G.TW * CG];
+        xr[s0] = lds8<0>(xtile0 + soff + (uint32_t)u * xrowstride);
         act4(xr[s0], scA, scB, shA, shB, aA[s0], aB[s0]);
         if (!(r < rows && active)) aA[s0] = aB[s0] = make_float2(0.f, 0.f);
         // data gradient: g row o uses dy row r = o + 2 - ky; dy column iw + 1 - kx  (kx=0: right, 2: left)
@@ -299,15 +338,14 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
         dA[7] = ffma2(cA, aA[s0], dA[7]); dB[7] = ffma2(cB, aB[s0], dB[7]);
         dA[8] = ffma2(lA, aA[s0], dA[8]); dB[8] = ffma2(lB, aB[s0], dB[8]);
         const int o = r - 2;
-        if (o >= 0 && o < rows && active) {
+        if ((unsigned)o < (unsigned)rows && active) {
           float2 vA = gA[s2], vB = gB[s2];
           const float2 mA = aA[s2], mB = aB[s2];
           vA.x = (mA.x > 0.f && mA.x < 1.f) ? vA.x : 0.f;
           vA.y = (mA.y > 0.f && mA.y < 1.f) ? vA.y : 0.f;
           vB.x = (mB.x > 0.f && mB.x < 1.f) ? vB.x : 0.f;
           vB.y = (mB.y > 0.f && mB.y < 1.f) ? vB.y : 0.f;
-          if (col_in && (!G.interior || (unsigned)(ih_start + o) < (unsigned)G.H))
-            *reinterpret_cast<uint2*>(gp + (long long)o * (long long)growp) = pack4(vA, vB);
+          st8_if(grow, pack4(vA, vB), col_in && (!G.interior || (unsigned)(ih_start + o) < (unsigned)G.H));
           float2 xa, xb;
           unpack4(xr[s2], xa, xb);
           sA = fadd2(sA, vA);
@@ -315,10 +353,12 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
           qA = ffma2(vA, fadd2(xa, nmuA), qA);
           qB = ffma2(vB, fadd2(xb, nmuB), qB);
         }
+        grow += growp;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&bar_empty[s]));
     }
+    }   // units
   }
   const int t = threadIdx.x;
   const bool consumer = t < BWD_CONS;
@@ -358,7 +398,7 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
 }
 
 // chunking: CG 4-channel groups per CTA, TW columns, TW*CG <= ncons_max consumer threads
-inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stages, bool bwd, S1Geom* G, dim3* grid,
+inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stages, bool bwd, int ctas_per_sm, S1Geom* G, dim3* grid,
                     int* threads, size_t* smem) {
   int CG;
   if (C % 32 == 0) CG = 8;
@@ -371,19 +411,26 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
   TW = s2r_div_up(We, tiles);              // balance the column tiles
   if (TW + 2 > 256) return false;           // TMA box limit
   const int chunks = C / (CG * 4);
-  // rows per CTA: as long as possible (vertical halo = 2 rows per segment) while filling the GPU ~4x;
-  // rs + 2 is a multiple of the stage depth RB so no loaded row is wasted
+  // persistent CTAs: `per_chunk` of them per channel chunk (ctas_per_sm resident CTAs on every SM in total), each
+  // taking work units (image, row segment, column tile) round-robin.  Rows per unit: as long as possible (vertical
+  // halo = 2 rows per segment) but at least ~6 units per CTA for balance; rs + 2 is a multiple of the stage depth
+  // RB so no loaded row is wasted.
+  int per_chunk = (ctas_per_sm * s2r_sm_count()) / chunks;
+  if (per_chunk < 1) per_chunk = 1;
   int nseg = s2r_div_up(He, 64);
-  while ((long)chunks * tiles * N * nseg < 4L * s2r_sm_count() && He / (nseg * 2) >= 16) nseg *= 2;
+  while ((long)tiles * N * nseg < 6L * per_chunk && He / (nseg * 2) >= 13) nseg *= 2;
   int rs = s2r_div_up(He, nseg);
   rs = (rs + 2 + RB - 1) / RB * RB - 2;
   nseg = s2r_div_up(He, rs);
-  if ((long)N * nseg > 65535 || tiles > 65535) return false;
+  const long nunits = (long)tiles * N * nseg;
+  if (nunits > 0x7fffffffL) return false;
+  if (per_chunk > nunits) per_chunk = (int)nunits;
+  G->tiles = tiles; G->nunits = (int)nunits;
   G->N = N; G->H = H; G->W = W; G->C = C; G->CG = CG; G->TW = TW; G->rs = rs; G->nseg = nseg; G->ext = ext;
   const int dy_bytes = RB * (TW + 2) * CG * 8, x_bytes = bwd ? RB * TW * CG * 8 : 0;
   G->xoff = (dy_bytes + 127) / 128 * 128;
   G->stage_bytes = (G->xoff + x_bytes + 127) / 128 * 128;
-  *grid = dim3(chunks, tiles, N * nseg);
+  *grid = dim3(chunks, per_chunk, 1);
   *threads = (TW * CG + 31) / 32 * 32 + 32;
   if (*threads < (CG * 12 + 31) / 32 * 32) *threads = (CG * 12 + 31) / 32 * 32;   // the final reductions use CG*12 threads
   *smem = (size_t)stages * G->stage_bytes + 128;
@@ -395,7 +442,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
 constexpr int S1_SMEM_CAP = 160 * 1024;
 template <typename K>
 inline int s1_smem_attr(K kernel, size_t smem, int which) {
-  static bool flags[3] = {false, false, false};   // per kernel (same-signature kernels share this instantiation)
+  static bool flags[9] = {false, false, false, false, false, false, false, false, false};   // per kernel instance
   bool& done = flags[which];
   S2R_REQUIRE(smem <= (size_t)S1_SMEM_CAP, S2R_ERR_UNSUPPORTED, "dwconv3x3: ring of %zu bytes exceeds the cap", smem);
   if (!done) {
@@ -420,7 +467,7 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
       dim3 grid;
       int threads;
       size_t smem;
-      if (!s1_plan(N, Hp, Wp, C, 0, FWD_CONS, FWD_STAGES, false, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+      if (!s1_plan(N, Hp, Wp, C, 0, FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
       const long long poff = ((long long)p * W + q) * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
       CUtensorMap xmap;
@@ -428,15 +475,22 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
                             G.CG * 4, G.TW + 2, RB))
         return S2R_ERR_UNSUPPORTED;
       __nv_bfloat16* yv = (__nv_bfloat16*)y + poff;
+#define S2R_DW_FWD(HALO_, CG_, SLOT_)                                                       \
+  do {                                                                                      \
+    int rc = s1_smem_attr(dw_s1_fwd_kernel<HALO_, CG_>, smem, SLOT_);                       \
+    if (rc) return rc;                                                                      \
+    dw_s1_fwd_kernel<HALO_, CG_><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G); \
+  } while (0)
       if (halo_const) {
-        int rc = s1_smem_attr(dw_s1_fwd_kernel<true>, smem, 0);
-        if (rc) return rc;
-        dw_s1_fwd_kernel<true><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G);
+        if (G.CG == 8) S2R_DW_FWD(true, 8, 0);
+        else if (G.CG == 12) S2R_DW_FWD(true, 12, 1);
+        else S2R_DW_FWD(true, 4, 2);
       } else {
-        int rc = s1_smem_attr(dw_s1_fwd_kernel<false>, smem, 1);
-        if (rc) return rc;
-        dw_s1_fwd_kernel<false><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G);
+        if (G.CG == 8) S2R_DW_FWD(false, 8, 3);
+        else if (G.CG == 12) S2R_DW_FWD(false, 12, 4);
+        else S2R_DW_FWD(false, 4, 5);
       }
+#undef S2R_DW_FWD
       S2R_LAUNCH_OK();
     }
   return S2R_OK;
@@ -455,7 +509,7 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
       dim3 grid;
       int threads;
       size_t smem;
-      if (!s1_plan(N, Hp, Wp, C, ext ? 1 : 0, BWD_CONS, BWD_STAGES, true, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+      if (!s1_plan(N, Hp, Wp, C, ext ? 1 : 0, BWD_CONS, BWD_STAGES, true, 1, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
       const long long poff = ((long long)p * W + q) * C, goff = ((long long)p * We + q) * C;
       const long long sw = (long long)dil * C, sh = (long long)dil * W * C, sn = (long long)H * W * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * We * C; G.os_img = (long long)He * We * C;
@@ -465,9 +519,16 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
         return S2R_ERR_UNSUPPORTED;
       if (!encode_nhwc_view(&xmap, (const __nv_bfloat16*)x + poff, N, Hp, Wp, C, sw, sh, sn, G.CG * 4, G.TW, RB))
         return S2R_ERR_UNSUPPORTED;
-      int rc = s1_smem_attr(dw_s1_bwd_kernel, smem, 2);
-      if (rc) return rc;
-      dw_s1_bwd_kernel<<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G);
+#define S2R_DW_BWD(CG_, SLOT_)                                                                                       \
+  do {                                                                                                               \
+    int rc = s1_smem_attr(dw_s1_bwd_kernel<CG_>, smem, SLOT_);                                                       \
+    if (rc) return rc;                                                                                               \
+    dw_s1_bwd_kernel<CG_><<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G); \
+  } while (0)
+      if (G.CG == 8) S2R_DW_BWD(8, 6);
+      else if (G.CG == 12) S2R_DW_BWD(12, 7);
+      else S2R_DW_BWD(4, 8);
+#undef S2R_DW_BWD
       S2R_LAUNCH_OK();
     }
   return S2R_OK;

@@ -168,7 +168,7 @@ __device__ __forceinline__ void s2_emit(float2 vA, float2 vB, float2 aA, float2 
     vA.y = (aA.y > 0.f && aA.y < 1.f) ? vA.y : 0.f;
     vB.x = (aB.x > 0.f && aB.x < 1.f) ? vB.x : 0.f;
     vB.y = (aB.y > 0.f && aB.y < 1.f) ? vB.y : 0.f;
-    if (st) *reinterpret_cast<uint2*>(dst) = pack4(vA, vB);
+    st8_if(dst, pack4(vA, vB), st);
     float2 xa, xb;
     unpack4(xraw, xa, xb);
     sA = fadd2(sA, vA);

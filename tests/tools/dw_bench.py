@@ -48,7 +48,8 @@ for name, H, W, Cc, s, d, halo, cnt in SHAPES:
     stats = cx.f64(2 * Cc)
     ext = d if halo else 0
     dy = eng.Act(torch.randn(N, Ho, Wo, Cc, device=dev).to(torch.bfloat16))
-    g = cx.new(N, H + 2 * ext, W + 2 * ext, Cc)
+    GEXT = bool(os.environ.get('S2R_BENCH_GEXT'))   # 1: extended gradient layout (border stored)
+    g = cx.new(N, H + 2 * ext, W + 2 * ext, Cc) if GEXT else cx.new(N, H, W, Cc)   # default: unextended, as the engine requests it
     bs = cx.f64(2 * Cc); dw = torch.zeros_like(w)
     for mode in ("new", "generic"):
         if mode == "generic":
@@ -58,9 +59,9 @@ for name, H, W, Cc, s, d, halo, cnt in SHAPES:
             os.environ.pop("S2R_DW_GENERIC", None)
         tf = timed(lambda: eng.dw_fwd(cx, x, st, L.ACT_RELU6, halo, w, s, d, d, stats))
         tb = timed(lambda: L.call("s2r_dwconv3x3_bwd", dy.vp(), vp(w), x.vp(), vp(ss), vp(mi), L.ACT_RELU6, 1 if halo else 0,
-                                  g.vp(), vp(bs), vp(dw), N, H, W, Cc, s, d, d, cx.stream))
+                                  0 if GEXT else 1, g.vp(), vp(bs), vp(dw), N, H, W, Cc, s, d, d, cx.stream))
         bf_ = (N * H * W * Cc + N * Ho * Wo * Cc) * 2
-        bb = (N * Ho * Wo * Cc + N * H * W * Cc + N * (H + 2 * ext) * (W + 2 * ext) * Cc) * 2
+        bb = (N * Ho * Wo * Cc + 2 * N * H * W * Cc) * 2
         print("%-22s %-8s %9.1f %8.0f %6.3f" % (name, "fwd/" + mode[:3], tf, bf_ / tf / 1e3, bf_ / tf / 1e3 / PEAK))
         print("%-22s %-8s %9.1f %8.0f %6.3f" % (name, "bwd/" + mode[:3], tb, bb / tb / 1e3, bb / tb / 1e3 / PEAK))
         if mode == "new":
