@@ -25,7 +25,7 @@ namespace {
 
 constexpr int CM_DEPTH = 4;
 constexpr int CM_MAX_WORLD = 16;
-constexpr int CM_THREADS = 512;
+constexpr int CM_THREADS = 1024;
 
 struct CommDev {
   double* inbox[CM_MAX_WORLD];                 // base of every rank's inbox region (peer-mapped)
@@ -59,6 +59,9 @@ __device__ __forceinline__ unsigned long long ld_word(const unsigned long long* 
   return v;
 }
 
+// WORLD > 0: the rank count is a compile-time constant, so the polls of all peers are issued together (their L2
+// latencies overlap) instead of one peer after the other; WORLD == 0: generic loop.
+template <int WORLD>
 __global__ void __launch_bounds__(CM_THREADS)
 allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c) {
   const unsigned long long seq = *c.seq + 1;      // every thread reads it; thread 0 advances it at the end
@@ -79,7 +82,34 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c) {
   // 2. + 3. poll every rank's words and sum in rank order (own value taken from buf)
   const unsigned long long* in = reinterpret_cast<const unsigned long long*>(c.inbox[c.rank]) + (size_t)d * c.world * slot_words;
   bool timed_out = false;
-  for (int i = threadIdx.x; i < n; i += CM_THREADS) {
+  for (int i = threadIdx.x; WORLD > 0 && i < n; i += CM_THREADS) {
+    const double mine = buf[i];
+    unsigned long long w0[WORLD > 0 ? WORLD : 1], w1[WORLD > 0 ? WORLD : 1];
+    const long long t0 = clock64();
+    bool all_ok;
+    do {
+      all_ok = true;
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) {
+        const unsigned long long* src = in + (size_t)r * slot_words + 2 * i;
+        w0[r] = ld_word(src);
+        w1[r] = ld_word(src + 1);
+      }
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r)
+        if (r != c.rank && ((((w0[r] ^ tag) | (w1[r] ^ tag)) >> 32) != 0)) all_ok = false;
+      if (!all_ok && clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone; do not hang the GPU
+        timed_out = true;
+        break;
+      }
+    } while (!all_ok);
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r)
+      acc += (r == c.rank) ? mine : __longlong_as_double((long long)((w0[r] & 0xffffffffull) | (w1[r] << 32)));
+    buf[i] = acc;
+  }
+  for (int i = threadIdx.x; WORLD == 0 && i < n; i += CM_THREADS) {
     double acc = 0.0;
     const double mine = buf[i];
     for (int r = 0; r < c.world; ++r) {
@@ -164,7 +194,10 @@ extern "C" int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream) 
   S2R_REQUIRE(h.ready, S2R_ERR_SHAPE, "comm: not initialised");
   S2R_REQUIRE(buf && n >= 1 && n <= h.slot, S2R_ERR_SHAPE, "allreduce_small: n=%d exceeds the slot of %d doubles", n, h.slot);
   if (h.world == 1) return S2R_OK;
-  allreduce_small_kernel<<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  if (h.world == 2) allreduce_small_kernel<2><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  else if (h.world == 4) allreduce_small_kernel<4><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  else if (h.world == 8) allreduce_small_kernel<8><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  else allreduce_small_kernel<0><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
