@@ -103,6 +103,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_invstd, float* __restrict__ scale_shift,
                                    int C) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -388,6 +390,8 @@ bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, in
                      const float* __restrict__ scale_shift, const __nv_bfloat16* __restrict__ residual,
                      __nv_bfloat16* __restrict__ y, int ypitch, int yoff, int rows, float drop_p,
                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  pdl_wait();
+  pdl_trigger();
   if (DROP && seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -453,6 +457,8 @@ bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
                    int dxpitch, int dxoff, int rows, float* __restrict__ dgamma, float* __restrict__ dbeta, float drop_p,
                    unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ float sm[];
+  pdl_wait();
+  pdl_trigger();
   if (DROP && seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -618,9 +624,8 @@ extern "C" int s2r_bn_finalize(const double* sums, double count, const float* ga
   S2R_REQUIRE(C >= 1, S2R_ERR_SHAPE, "bn_finalize: C=%d", C);
   // batchnorm.py:116 -- the statistics need more than one value per channel
   S2R_REQUIRE(count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
-  bn_finalize_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      sums, count, gamma, beta, eps, clamp_mode, momentum, running_mean, running_var, mean_invstd,
-      scale_shift, C);
+  S2R_CUDA_OK(s2r_launch(bn_finalize_kernel, dim3(s2r_div_up(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, count,
+                         gamma, beta, eps, clamp_mode, momentum, running_mean, running_var, mean_invstd, scale_shift, C));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -652,8 +657,9 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long* sd = (const unsigned long long*)seed_dev;
 #define S2R_APPLY(ACT_, RES_, DROP_)                                                                                     \
-  bn_apply_lean_kernel<ACT_, RES_, DROP_><<<cfg.grid, cfg.threads, 0, st>>>(xb, P, C, xpitch, xoff, scale_shift, rb, yb, \
-                                                                            ypitch, yoff, cfg.rows, drop_p, seed, sd)
+  S2R_CUDA_OK(s2r_launch(bn_apply_lean_kernel<ACT_, RES_, DROP_>, dim3(cfg.grid), dim3(cfg.threads), 0, st, xb,          \
+                         (long long)P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows, drop_p,               \
+                         (unsigned long long)seed, sd))
     bool done = true;
     if (drop_p > 0.f) S2R_APPLY(S2R_ACT_RELU, false, true);
     else if (act == S2R_ACT_NONE) { if (residual) S2R_APPLY(S2R_ACT_NONE, true, false); else S2R_APPLY(S2R_ACT_NONE, false, false); }
@@ -691,8 +697,9 @@ extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const v
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long* sd = (const unsigned long long*)seed_dev;
 #define S2R_RED(ACT_, DROP_)                                                                                          \
-  bn_bwd_lean_kernel<ACT_, false, DROP_><<<cfg.grid, cfg.threads, smem, st>>>(db, dypitch, dyoff, xb, xpitch, xoff,     \
-      mean_invstd, scale_shift, dsums, 0.0, P, C, nullptr, 0, 0, cfg.rows, nullptr, nullptr, drop_p, seed, sd)
+  S2R_CUDA_OK(s2r_launch(bn_bwd_lean_kernel<ACT_, false, DROP_>, dim3(cfg.grid), dim3(cfg.threads), smem, st, db,      \
+      dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, dsums, 0.0, (long long)P, C, (__nv_bfloat16*)nullptr,  \
+      0, 0, cfg.rows, (float*)nullptr, (float*)nullptr, drop_p, (unsigned long long)seed, sd))
     if (drop_p > 0.f) S2R_RED(S2R_ACT_RELU, true);
     else if (act == S2R_ACT_NONE) S2R_RED(S2R_ACT_NONE, false);
     else if (act == S2R_ACT_RELU) S2R_RED(S2R_ACT_RELU, false);
@@ -728,9 +735,9 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
     const unsigned long long* sd = (const unsigned long long*)seed_dev;
     // the parameter gradients (dgamma, dbeta) are added by block 0 of the same launch
 #define S2R_APP(ACT_, DROP_)                                                                                          \
-  bn_bwd_lean_kernel<ACT_, true, DROP_><<<cfg.grid, cfg.threads, 0, st>>>(db, dypitch, dyoff, xb, xpitch, xoff,         \
-      mean_invstd, scale_shift, const_cast<double*>(dsums), count, P, C, ob, dxpitch, dxoff, cfg.rows, dgamma, dbeta,  \
-      drop_p, seed, sd)
+  S2R_CUDA_OK(s2r_launch(bn_bwd_lean_kernel<ACT_, true, DROP_>, dim3(cfg.grid), dim3(cfg.threads), (size_t)0, st, db,  \
+      dypitch, dyoff, xb, xpitch, xoff, mean_invstd, scale_shift, const_cast<double*>(dsums), count, (long long)P, C,   \
+      ob, dxpitch, dxoff, cfg.rows, dgamma, dbeta, drop_p, (unsigned long long)seed, sd))
     if (drop_p > 0.f) S2R_APP(S2R_ACT_RELU, true);
     else if (act == S2R_ACT_NONE) S2R_APP(S2R_ACT_NONE, false);
     else if (act == S2R_ACT_RELU) S2R_APP(S2R_ACT_RELU, false);

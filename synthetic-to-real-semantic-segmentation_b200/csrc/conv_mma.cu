@@ -433,6 +433,8 @@ tap_wgrad_kernel(const __grid_constant__ WgParams p) {
 // ------------------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int RS, int transpose,
                                    __nv_bfloat16* __restrict__ out, int A_pad, int B_pad) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)RS * A_pad * B_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -591,8 +593,7 @@ extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, 
   const int A = transpose ? Cin : Cout, B = transpose ? Cout : Cin;
   S2R_REQUIRE(A_pad >= A && B_pad >= B, S2R_ERR_SHAPE, "pack_weight: padded dims (%d,%d) smaller than (%d,%d)", A_pad, B_pad, A, B);
   const long long total = (long long)R * S * A_pad * B_pad;
-  pack_weight_kernel<<<s2r_grid(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      w, Cout, Cin, R * S, transpose, (__nv_bfloat16*)packed, A_pad, B_pad);
-  S2R_LAUNCH_OK();
+  S2R_CUDA_OK(s2r_launch(pack_weight_kernel, dim3(s2r_grid(total, 256, 8)), dim3(256), (size_t)0, (cudaStream_t)stream, w,
+                         Cout, Cin, R * S, transpose, (__nv_bfloat16*)packed, A_pad, B_pad));
   return S2R_OK;
 }

@@ -228,6 +228,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory only from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -505,7 +507,7 @@ int launch_tc(const TcMaps& maps, const TcParams& p, int n_tiles_n, cudaStream_t
   }
   const long long tiles = (long long)s2r_div_up(p.n_subtiles, MT) * n_tiles_n;
   const int grid = (int)(tiles < s2r_sm_count() ? tiles : s2r_sm_count());  // persistent: one CTA per SM
-  conv_tc_kernel<BN, MT, STAGES><<<grid, TC_THREADS, smem, st>>>(maps, p);
+  S2R_CUDA_OK(s2r_launch(conv_tc_kernel<BN, MT, STAGES>, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, maps, p));
   S2R_LAUNCH_OK();
   return 1;
 }

@@ -166,6 +166,8 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgT
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (kiters > 0) {
     if (warp == 0) {
@@ -308,7 +310,7 @@ int launch_wg(const WgMaps& maps, const WgTcParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(p.ntaps * p.ci_tiles * p.co_tiles, p.splits);
-  wgrad_tc_kernel<BN, MT, STAGES><<<grid, WG_THREADS, smem, st>>>(maps, p);
+  S2R_CUDA_OK(s2r_launch(wgrad_tc_kernel<BN, MT, STAGES>, grid, dim3(WG_THREADS), (size_t)smem, st, maps, p));
   S2R_LAUNCH_OK();
   return 1;
 }

@@ -90,6 +90,8 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == ncw) {
     // ---------------- producer warp
@@ -235,6 +237,8 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
 
   float2 dA[9], dB[9];
   float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
@@ -470,6 +474,7 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
       if (!s1_plan(N, Hp, Wp, C, 0, FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
       const long long poff = ((long long)p * W + q) * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
+      G.interior = 0;
       CUtensorMap xmap;
       if (!encode_nhwc_view(&xmap, (const __nv_bfloat16*)x + poff, N, Hp, Wp, C, G.os_pix, G.os_row, G.os_img,
                             G.CG * 4, G.TW + 2, RB))
@@ -479,7 +484,7 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
   do {                                                                                      \
     int rc = s1_smem_attr(dw_s1_fwd_kernel<HALO_, CG_>, smem, SLOT_);                       \
     if (rc) return rc;                                                                      \
-    dw_s1_fwd_kernel<HALO_, CG_><<<grid, threads, smem, stream>>>(xmap, ss, w, yv, stats, G); \
+    S2R_CUDA_OK(s2r_launch(dw_s1_fwd_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G)); \
   } while (0)
       if (halo_const) {
         if (G.CG == 8) S2R_DW_FWD(true, 8, 0);
@@ -523,7 +528,7 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
   do {                                                                                                               \
     int rc = s1_smem_attr(dw_s1_bwd_kernel<CG_>, smem, SLOT_);                                                       \
     if (rc) return rc;                                                                                               \
-    dw_s1_bwd_kernel<CG_><<<grid, threads, smem, stream>>>(dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G); \
+    S2R_CUDA_OK(s2r_launch(dw_s1_bwd_kernel<CG_>, grid, dim3(threads), smem, stream, dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G)); \
   } while (0)
       if (G.CG == 8) S2R_DW_BWD(8, 6);
       else if (G.CG == 12) S2R_DW_BWD(12, 7);

@@ -59,6 +59,8 @@ dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == ncw) {
     if (lane == 0) {
@@ -206,6 +208,8 @@ dw_s2_bwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
 
   float2 dA[9], dB[9];
   float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
@@ -428,7 +432,7 @@ int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, doubl
   }
   int threads = (TW * G.CG + 31) / 32 * 32 + 32;
   if (threads < (G.CG * 12 + 31) / 32 * 32) threads = (G.CG * 12 + 31) / 32 * 32;
-  dw_s2_fwd_kernel<<<dim3(chunks, tiles, N * G.nseg), threads, smem, stream>>>(M, ss, w, (__nv_bfloat16*)y, stats, G);
+  S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w, (__nv_bfloat16*)y, stats, G));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -467,7 +471,7 @@ int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* m
   }
   int threads = (TW * G.CG + 31) / 32 * 32 + 32;
   if (threads < (G.CG * 12 + 31) / 32 * 32) threads = (G.CG * 12 + 31) / 32 * 32;
-  dw_s2_bwd_kernel<<<dim3(chunks, tiles, N * G.nseg), threads, smem, stream>>>(M, ss, mi, w, (__nv_bfloat16*)g, bsums, dw, G);
+  S2R_CUDA_OK(s2r_launch(dw_s2_bwd_kernel, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, mi, w, (__nv_bfloat16*)g, bsums, dw, G));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
