@@ -215,6 +215,36 @@ def depthwise_roofline(torch, batch, h, w, peaks):
             "peak_source": peaks.get("_source", "fallback"), "launch_ms": t * 1e3}
 
 
+def val_throughput(torch, G):
+    """BASELINE config 5 (val_adapt.py:122-135): eval forward at 1x3x1024x2048 + fused argmax / confusion matrix,
+    captured in a CUDA graph, inputs resident, 30 images after 3 warm-up replays."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    was_training = G.training
+    G.eval()
+    vstep = sub("steps").ValStep(G, 19)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(1, 3, 1024, 2048, generator=g).to(dev)
+    tl = torch.randint(0, 19, (1, 1024, 2048), generator=g).float()
+    tl[torch.rand(1, 1024, 2048, generator=g) < 0.05] = 255
+    tl = tl.to(dev)
+    vstep.capture(img, tl)
+    for _ in range(3):
+        vstep.replay(img, tl)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(30):
+        vstep.replay(img, tl)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 30
+    miou, _ = vstep.evaluator.Mean_Intersection_over_Union()
+    G.train(was_training)
+    return {"value": 1e3 / ms, "unit": "img/s", "ms_per_image": ms,
+            "config": "val_adapt.py:122-135 at 1x3x1024x2048, eval forward + fused argmax/confusion matrix, CUDA graph",
+            "miou_random_init": float(miou)}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -344,6 +374,8 @@ def run_b200(args):
         "roofline": roof,
         "roofline_depthwise": depthwise_roofline(torch, B, H, W, peaks),
     }
+    if world == 1:
+        line["val"] = val_throughput(torch, G)
     if not args.no_cpu_baseline and world == 1:
         val, dt, threads = cpu_adapt_steps(args.cpu_batch, H, W, 1, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

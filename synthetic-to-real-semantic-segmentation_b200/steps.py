@@ -235,3 +235,31 @@ class ValStep(object):
         loss = self.criterion(output, target) if with_loss else None
         self.evaluator.add_batch_logits(target, output)
         return loss
+
+    @torch.no_grad()
+    def capture(self, image, target):
+        """Capture forward + fused argmax/confusion matrix into one CUDA graph (a batch-1 eval forward is ~200
+        short launches: issued from Python they starve the GPU).  replay() copies the inputs into the static
+        buffers; the confusion matrix keeps accumulating on the device."""
+        dev = image.device
+        self._static = (torch.empty_like(image), torch.empty_like(target))
+        for st, t in zip(self._static, (image, target)):
+            st.copy_(t)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self(*self._static)          # warm-up: weight packing, lazy buffers
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self(*self._static)
+        self.evaluator.reset()           # drop the warm-up counts
+        return self
+
+    @torch.no_grad()
+    def replay(self, image, target):
+        for st, t in zip(self._static, (image, target)):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self._graph.replay()
