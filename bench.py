@@ -111,22 +111,56 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons during the timed region, every 100 ms.  Sampled in-process through NVML
+    (pynvml): forking `nvidia-smi` from a thread stalls the benchmark's own Python thread (and its CUDA calls) for
+    milliseconds, which the end-to-end loop -- one host synchronisation per step -- would pay for directly.
+    `nvidia-smi` remains the fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML enumerates all of them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"   # noqa: E731
+        return [str(sm), str(mx), act(nv.nvmlClocksThrottleReasonHwSlowdown), act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                act(nv.nvmlClocksThrottleReasonSwThermalSlowdown), act(nv.nvmlClocksThrottleReasonSwPowerCap)]
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode()
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nv is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                                   "--format=csv,noheader,nounits"], timeout=5).decode()
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nv is not None else 0.2)
+
+    def sample_once(self):
+        try:
+            if self.nv is not None:
+                self.rows.append(self._sample_nvml())
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
@@ -143,7 +177,8 @@ class ClockSampler(object):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nv is not None else "nvidia-smi",
+                "sampled": "every 100 ms during the resident timed region; one sample before and after the e2e region"}
 
 
 # ----------------------------------------------------------------------------- roofline of the dominant kernel
@@ -334,9 +369,15 @@ def run_b200(args):
 
     for k in range(args.warmup):
         resident(k)
+    # Clocks are polled (every 100 ms) during the device-resident region only: every NVML / nvidia-smi query takes
+    # the driver lock for tens of milliseconds, which the end-to-end loop -- a host synchronisation and fresh CUDA
+    # calls every step -- pays for directly (measured: 24 ms -> 41-47 ms per step when polled).  The end-to-end
+    # region, which follows immediately, is bracketed by one sample before and one after instead.
     with ClockSampler(local) as clk:
         ms, launches = timed(resident, args.steps, args.warmup)
-        ms_e2e, _ = timed(end_to_end, args.steps, args.warmup + args.steps)
+    clk.sample_once()
+    ms_e2e, _ = timed(end_to_end, args.steps, args.warmup + args.steps)
+    clk.sample_once()
     pairs = B * world
     value = pairs * args.steps / (ms * 1e-3)
     e2e = pairs * args.steps / (ms_e2e * 1e-3)
