@@ -187,12 +187,24 @@ up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int 
 
 // Separable, row-staged variant of the kernel above for the final x4 up-sampling (deeplab.py:31), whose
 // gradient is the largest activation of the step (N x 19 x 512 x 1024 fp32): a CTA owns (image, channel,
-// UR coarse rows, 256 coarse columns), streams the fine rows that touch them through shared memory (coalesced
-// float4 loads, each fine element read once per CTA) and every thread reduces its column neighbourhood with
-// weights held in registers.  Same arithmetic as up_from_nchw_bwd_kernel up to summation order.
+// UR coarse rows, 256 coarse columns).  The fine rows are walked one coarse INTERVAL at a time (the ~1/scale
+// rows whose source coordinate lies in [ih, ih+1)): they are staged in shared memory with coalesced float4 loads
+// (each fine element read once per CTA), every thread reduces its column neighbourhood with weights held in
+// registers (exactly the <= UKX fine columns with a non-zero weight), and the two row weights of an interval are
+// applied to two accumulators with static indices.  Same arithmetic as up_from_nchw_bwd_kernel up to summation order.
 constexpr int UR = 8;      // coarse rows per CTA
-constexpr int URB = 4;     // fine rows staged per barrier pair
-constexpr int UK = 14;     // max fine columns in the candidate range of one coarse column (2/scale + 4)
+constexpr int UKX = 10;    // max fine columns with a non-zero weight for one coarse column (floor(2/scale) + 1)
+constexpr int URB = 6;     // fine rows staged per barrier pair (an interval has ceil(1/scale) <= URB rows)
+
+// smallest fine row oh >= 0 whose (clamped) source row index is >= i
+__device__ __forceinline__ int first_fine_row(int i, float sh, int Hi, int Ho) {
+  if (i <= 0) return 0;
+  int o = (int)ceilf((float)i / sh);
+  if (o > Ho) o = Ho;
+  while (o > 0 && lerp_src(o - 1, sh, Hi).i0 >= i) --o;
+  while (o < Ho && lerp_src(o, sh, Hi).i0 < i) ++o;
+  return o;
+}
 
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
@@ -215,64 +227,71 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
   cand_range(min(cb * kThreads + kThreads - 1, Wi - 1), sw, Wo, &t1, &seg_hi);
   seg_lo &= ~3;                                     // float4-aligned start
   const int seg_len = seg_hi - seg_lo + 1;
-  // this thread's column weights
-  int wlo = 0, whi = -1;
-  float wx[UK];
+  // this thread's column weights: the first fine column with a non-zero weight and the UKX columns from there
+  int wlo = 0;
+  float wx[UKX];
 #pragma unroll
-  for (int k = 0; k < UK; ++k) wx[k] = 0.f;
+  for (int k = 0; k < UKX; ++k) wx[k] = 0.f;
   if (col_ok) {
+    int whi;
     cand_range(iw, sw, Wo, &wlo, &whi);
+    while (wlo < whi && lerp_weight(lerp_src(wlo, sw, Wi), iw) == 0.f) ++wlo;
 #pragma unroll
-    for (int k = 0; k < UK; ++k)
+    for (int k = 0; k < UKX; ++k)
       if (wlo + k <= whi) wx[k] = lerp_weight(lerp_src(wlo + k, sw, Wi), iw);
   }
   const int koff = wlo - seg_lo;
-  int hlo, hhi, u0, u1;
-  cand_range(ih0, sh, Ho, &hlo, &u0);
-  cand_range(min(ih0 + UR - 1, Hi - 1), sh, Ho, &u1, &hhi);
   float acc[UR];
 #pragma unroll
   for (int r = 0; r < UR; ++r) acc[r] = 0.f;
   const float* plane = dy + ((long long)n * C + c) * Ho * Wo;
   const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
-  for (int oh0 = hlo; oh0 <= hhi; oh0 += URB) {
-    // stage URB fine rows per barrier pair: URB independent loads in flight per thread
 #pragma unroll
-    for (int b = 0; b < URB; ++b) {
-      const int oh = oh0 + b;
-      if (oh > hhi) break;
-      const float* src = plane + (long long)oh * Wo + seg_lo;
-      float* dstrow = rowbuf + b * seg_max;
-      // element j is stored at j + (j >> 5): the readers below walk the row with a stride of ~1/scale (4) words
-      // per lane, which would be a 4-way bank conflict on a dense row and is conflict-free on the skewed one
-      if (vec) {
-        // seg_lo and Wo are multiples of 4, so a float4 never straddles the row end
-        for (int i = threadIdx.x * 4; i < seg_len; i += kThreads * 4) {
-          const float4 v4 = __ldg(reinterpret_cast<const float4*>(src + i));
-          float* d = dstrow + i + (i >> 5);
-          d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
+  for (int k = 0; k <= UR; ++k) {
+    const int ih = ih0 - 1 + k;                      // interval [ih, ih+1): weight w0 to row ih, w1 to row ih+1
+    if (ih < 0 || ih > Hi - 1) continue;             // uniform over the CTA
+    const int a = first_fine_row(ih, sh, Hi, Ho);
+    const int b = ih == Hi - 1 ? Ho : first_fine_row(ih + 1, sh, Hi, Ho);
+    float lo = 0.f, hi = 0.f;
+    for (int o0 = a; o0 < b; o0 += URB) {
+      const int nr = min(URB, b - o0);
+      for (int rr = 0; rr < nr; ++rr) {
+        const float* src = plane + (long long)(o0 + rr) * Wo + seg_lo;
+        float* dstrow = rowbuf + rr * seg_max;
+        // element j is stored at j + (j >> 5): the readers walk the row with a stride of ~1/scale (4) words per
+        // lane, which would be a 4-way bank conflict on a dense row and is conflict-free on the skewed one
+        if (vec) {
+          // seg_lo and Wo are multiples of 4, so a float4 never straddles the row end
+          for (int i = threadIdx.x * 4; i < seg_len; i += kThreads * 4) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(src + i));
+            float* d = dstrow + i + (i >> 5);
+            d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
+          }
+        } else {
+          for (int i = threadIdx.x; i < seg_len; i += kThreads) dstrow[i + (i >> 5)] = __ldg(src + i);
         }
-      } else {
-        for (int i = threadIdx.x; i < seg_len; i += kThreads) dstrow[i + (i >> 5)] = __ldg(src + i);
       }
-    }
-    __syncthreads();
+      __syncthreads();
+      for (int rr = 0; rr < nr; ++rr) {
+        const float* row = rowbuf + rr * seg_max;
+        float v = 0.f;
 #pragma unroll
-    for (int b = 0; b < URB; ++b) {
-      const int oh = oh0 + b;
-      if (oh > hhi) break;
-      const float* row = rowbuf + b * seg_max;
-      float v = 0.f;
-#pragma unroll
-      for (int k = 0; k < UK; ++k) {
-        const int j = koff + k;
-        v = fmaf(wx[k], (j < seg_len && j >= 0) ? row[j + (j >> 5)] : 0.f, v);
+        for (int kk = 0; kk < UKX; ++kk) {
+          const int j = koff + kk;
+          v = fmaf(wx[kk], (j < seg_len && j >= 0) ? row[j + (j >> 5)] : 0.f, v);
+        }
+        const Lerp ly = lerp_src(o0 + rr, sh, Hi);  // ly.i0 == ih
+        lo = fmaf(ly.w0, v, lo);
+        hi = fmaf(ly.w1, v, hi);
       }
-      const Lerp ly = lerp_src(oh, sh, Hi);
-#pragma unroll
-      for (int r = 0; r < UR; ++r) acc[r] = fmaf(lerp_weight(ly, ih0 + r), v, acc[r]);
+      __syncthreads();
     }
-    __syncthreads();
+    if (k >= 1) acc[k - 1] += lo;
+    if (ih + 1 <= Hi - 1) {
+      if (k <= UR - 1) acc[k] += hi;
+    } else if (k >= 1) {
+      acc[k - 1] += hi;                              // i1 is clamped to the last row
+    }
   }
   if (col_ok)
     for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(acc[r]);
@@ -460,8 +479,9 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
   S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1 && dxpitch >= C, S2R_ERR_SHAPE,
               "upsample_from_nchw_bwd: bad shape");
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
-  // row-staged kernel when at most UK fine columns touch a coarse column (up-sampling factors up to ~4.5)
-  if (sw > 0.f && sh > 0.f && 2.f / sw + 4.f <= (float)UK && N <= 65535 && dxpitch <= 65535) {
+  // row-staged kernel when at most UKX fine columns weigh on a coarse column and an interval has at most URB rows
+  // (up-sampling factors up to ~4.4 in both directions)
+  if (sw > 0.f && sh > 0.f && 2.f / sw + 1.f <= (float)UKX && 1.f / sh + 1.f <= (float)URB && N <= 65535 && dxpitch <= 65535) {
     const int col_chunks = s2r_div_up(Wi, kThreads);
     int seg_max = (int)((kThreads + 2) / sw) + 16;
     seg_max = (seg_max + (seg_max >> 5) + 4) & ~3;   // skewed row length
