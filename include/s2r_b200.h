@@ -110,6 +110,16 @@ int s2r_conv_wgrad(const s2r_wgrad_args* a, s2r_stream_t stream);
  * gradient); A_pad/B_pad >= A/B, padding is zero filled. */
 int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int transpose, void* packed,
                     int A_pad, int B_pad, s2r_stream_t stream);
+/* The same for many filters in one launch.  A job packs the elements [begin, end) of one packed filter
+ * (flattened [R*S][A_pad][B_pad] index); the table lives in device memory. */
+typedef struct s2r_pack_job {
+  const float* w;
+  void* packed;
+  int32_t Cout, Cin, RS, transpose, A_pad, B_pad;
+  int64_t begin, end;
+} s2r_pack_job;
+int s2r_pack_weights_multi(const s2r_pack_job* jobs, int njobs, s2r_stream_t stream);
+
 
 /* ------------------------------------------------------------------ depthwise 3x3
  * groups=C nn.Conv2d of InvertedResidual (modeling/backbone/mobilenet.py:40,54), fused with the

@@ -42,6 +42,11 @@ class WgradArgs(C.Structure):
                 ("dweight", vp), ("s_co", i64), ("s_ci", i64)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", vp), ("packed", vp), ("Cout", i32), ("Cin", i32), ("RS", i32), ("transpose", i32),
+                ("A_pad", i32), ("B_pad", i32), ("begin", i64), ("end", i64)]
+
+
 class ParamSlot(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("s0", vp), ("s1", vp), ("n", i64), ("lr_mult", f32),
                 ("_pad", f32)]
@@ -53,6 +58,7 @@ PROTOTYPES = {
     "s2r_conv_fwd_mma": [C.POINTER(ConvArgs), vp],
     "s2r_conv_wgrad": [C.POINTER(WgradArgs), vp],
     "s2r_pack_weight": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
+    "s2r_pack_weights_multi": [vp, i32, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

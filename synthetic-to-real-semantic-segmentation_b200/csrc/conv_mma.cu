@@ -449,6 +449,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
+// One launch for many filters: blockIdx.y walks a device table of jobs (each a range of at most a few thousand
+// output elements of one packed filter), so re-packing all ~190 filter copies after an optimizer step is one
+// launch instead of ~100 (each of which was mostly launch latency).
+__global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs) {
+  const s2r_pack_job j = jobs[blockIdx.y];
+  const float* __restrict__ w = j.w;
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.packed);
+  for (long long i = j.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.end;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % j.B_pad);
+    const long long q = i / j.B_pad;
+    const int a = (int)(q % j.A_pad);
+    const int t = (int)(q / j.A_pad);
+    const int co = j.transpose ? b : a, ci = j.transpose ? a : b;
+    float v = 0.f;
+    if (co < j.Cout && ci < j.Cin) v = __ldg(w + ((long long)co * j.Cin + ci) * j.RS + t);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 void copy_taps(TapDev* dst, const s2r_tap* src, int n) {
   for (int i = 0; i < n; ++i) {
     dst[i].base = (const __nv_bfloat16*)src[i].base;
@@ -595,5 +615,14 @@ extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, 
   const long long total = (long long)R * S * A_pad * B_pad;
   S2R_CUDA_OK(s2r_launch(pack_weight_kernel, dim3(s2r_grid(total, 256, 8)), dim3(256), (size_t)0, (cudaStream_t)stream, w,
                          Cout, Cin, R * S, transpose, (__nv_bfloat16*)packed, A_pad, B_pad));
+  return S2R_OK;
+}
+
+extern "C" int s2r_pack_weights_multi(const s2r_pack_job* jobs, int njobs, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535, S2R_ERR_SHAPE, "pack_weights_multi: %d jobs", njobs);
+  if (njobs == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "pack_weights_multi: null table");
+  pack_weights_multi_kernel<<<dim3(4, njobs), 256, 0, (cudaStream_t)stream>>>(jobs);
+  S2R_LAUNCH_OK();
   return S2R_OK;
 }

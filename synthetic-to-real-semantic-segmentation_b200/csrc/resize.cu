@@ -51,6 +51,9 @@ __device__ __forceinline__ float lerp_weight(const Lerp& l, int i) {
 }
 
 // ------------------------------------------------------------ NHWC bf16 -> NHWC bf16
+// IT: index type of the flattened element counter.  unsigned (32-bit) whenever the tensor allows it: the three
+// div/mod pairs per element are ~10 instructions in 32 bits and ~100 in 64 bits, more than the interpolation itself.
+template <typename IT>
 __global__ void __launch_bounds__(kThreads)
 up_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Hi, int Wi, int C,
                    __nv_bfloat16* __restrict__ y, int Ho, int Wo, int ypitch, int yoff, float sh,
@@ -59,12 +62,13 @@ up_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Hi, int Wi, i
   const long long total = (long long)N * Ho * Wo * cg;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
        t += (long long)gridDim.x * kThreads) {
-    const int g = (int)(t % cg);
-    long long p = t / cg;
-    const int ow = (int)(p % Wo);
-    long long q = p / Wo;
-    const int oh = (int)(q % Ho);
-    const int n = (int)(q / Ho);
+    const IT tt = (IT)t;
+    const int g = (int)(tt % (IT)cg);
+    const IT p = tt / (IT)cg;
+    const int ow = (int)(p % (IT)Wo);
+    const IT q = p / (IT)Wo;
+    const int oh = (int)(q % (IT)Ho);
+    const int n = (int)(q / (IT)Ho);
     const Lerp ly = lerp_src(oh, sh, Hi), lx = lerp_src(ow, sw, Wi);
     const __nv_bfloat16* b = x + (long long)n * Hi * Wi * C + g * 8;
     float v00[8], v01[8], v10[8], v11[8], o[8];
@@ -75,10 +79,11 @@ up_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Hi, int Wi, i
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       o[i] = ly.w0 * (lx.w0 * v00[i] + lx.w1 * v01[i]) + ly.w1 * (lx.w0 * v10[i] + lx.w1 * v11[i]);
-    *reinterpret_cast<uint4*>(y + p * ypitch + yoff + g * 8) = float_to_bf16x8(o);
+    *reinterpret_cast<uint4*>(y + (long long)p * ypitch + yoff + g * 8) = float_to_bf16x8(o);
   }
 }
 
+template <typename IT>
 __global__ void __launch_bounds__(kThreads)
 up_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, int N, int Hi, int Wi,
                    int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, float sh, float sw) {
@@ -86,12 +91,13 @@ up_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
   const long long total = (long long)N * Hi * Wi * cg;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
        t += (long long)gridDim.x * kThreads) {
-    const int g = (int)(t % cg);
-    long long p = t / cg;
-    const int iw = (int)(p % Wi);
-    long long q = p / Wi;
-    const int ih = (int)(q % Hi);
-    const int n = (int)(q / Hi);
+    const IT tt = (IT)t;
+    const int g = (int)(tt % (IT)cg);
+    const IT p = tt / (IT)cg;
+    const int iw = (int)(p % (IT)Wi);
+    const IT q = p / (IT)Wi;
+    const int ih = (int)(q % (IT)Hi);
+    const int n = (int)(q / (IT)Hi);
     int hlo, hhi, wlo, whi;
     cand_range(ih, sh, Ho, &hlo, &hhi);
     cand_range(iw, sw, Wo, &wlo, &whi);
@@ -116,7 +122,7 @@ up_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
 }
 
 // ------------------------------------------------------------ NHWC bf16 -> NCHW fp32
-template <int CG>  // ceil(C/8) vectors per pixel
+template <int CG, typename IT>  // ceil(C/8) vectors per pixel
 __global__ void __launch_bounds__(kThreads)
 up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi, int Wi, int C,
                   float* __restrict__ y, int Ho, int Wo, float sh, float sw) {
@@ -124,10 +130,11 @@ up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi
   const long long plane = (long long)Ho * Wo;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
        t += (long long)gridDim.x * kThreads) {
-    const int ow = (int)(t % Wo);
-    long long q = t / Wo;
-    const int oh = (int)(q % Ho);
-    const int n = (int)(q / Ho);
+    const IT tt = (IT)t;
+    const int ow = (int)(tt % (IT)Wo);
+    const IT q = tt / (IT)Wo;
+    const int oh = (int)(q % (IT)Ho);
+    const int n = (int)(q / (IT)Ho);
     const Lerp ly = lerp_src(oh, sh, Hi), lx = lerp_src(ow, sw, Wi);
     const __nv_bfloat16* b = x + (long long)n * Hi * Wi * xpitch;
     const __nv_bfloat16* p00 = b + ((long long)ly.i0 * Wi + lx.i0) * xpitch;
@@ -429,9 +436,14 @@ extern "C" int s2r_upsample_bilinear_nhwc(const void* x, int N, int Hi, int Wi, 
   S2R_REQUIRE(C >= 8 && C % 8 == 0 && ypitch % 8 == 0 && yoff % 8 == 0 && ypitch >= yoff + C && al16(x) && al16(y),
               S2R_ERR_SHAPE, "upsample: channels/pitch must be multiples of 8 and buffers 16B aligned");
   const long long total = (long long)N * Ho * Wo * (C / 8);
-  up_nhwc_fwd_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
-      ac_scale(Wi, Wo));
+  if (total < (1ll << 32))
+    up_nhwc_fwd_kernel<unsigned><<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
+        ac_scale(Wi, Wo));
+  else
+    up_nhwc_fwd_kernel<long long><<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
+        ac_scale(Wi, Wo));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -443,9 +455,14 @@ extern "C" int s2r_upsample_bilinear_nhwc_bwd(const void* dy, int dypitch, int d
   S2R_REQUIRE(C >= 8 && C % 8 == 0 && dypitch % 8 == 0 && dyoff % 8 == 0 && dypitch >= dyoff + C && al16(dy) && al16(dx),
               S2R_ERR_SHAPE, "upsample_bwd: channels/pitch must be multiples of 8 and buffers 16B aligned");
   const long long total = (long long)N * Hi * Wi * (C / 8);
-  up_nhwc_bwd_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
-      ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  if (total < (1ll << 32))
+    up_nhwc_bwd_kernel<unsigned><<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
+        ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  else
+    up_nhwc_bwd_kernel<long long><<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
+        ac_scale(Hi, Ho), ac_scale(Wi, Wo));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -463,12 +480,15 @@ extern "C" int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
   const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
   cudaStream_t st = (cudaStream_t)stream;
+#define S2R_UP(CG_, IT_) up_to_nchw_kernel<CG_, IT_><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw)
+  const bool small = total < (1ll << 32);
   switch (cgs) {
-    case 1: up_to_nchw_kernel<1><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
-    case 2: up_to_nchw_kernel<2><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
-    case 3: up_to_nchw_kernel<3><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
-    default: up_to_nchw_kernel<4><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw); break;
+    case 1: if (small) S2R_UP(1, unsigned); else S2R_UP(1, long long); break;
+    case 2: if (small) S2R_UP(2, unsigned); else S2R_UP(2, long long); break;
+    case 3: if (small) S2R_UP(3, unsigned); else S2R_UP(3, long long); break;
+    default: if (small) S2R_UP(4, unsigned); else S2R_UP(4, long long); break;
   }
+#undef S2R_UP
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -8,6 +8,7 @@ torch.distributed (NCCL) for the BN-statistics and gradient all-reduces.
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -168,6 +169,17 @@ class Ctx:
 WEIGHT_EPOCH = [0]
 
 
+def _pack_dims(w, transpose):
+    Cout, Cin, R, S = w.shape
+    A, B = (Cin, Cout) if transpose else (Cout, Cin)
+    return Cout, Cin, R * S, round_up(A, 16), round_up(B, 64)
+
+
+# every (filter, orientation) that has been packed: prepack_weights() refreshes all stale ones in one launch
+_PACK_REGISTRY = {}
+_PACK_JOB_ELEMS = 4096
+
+
 def packed_weight(cx, w, transpose):
     """bf16 [R*S][A_pad][B_pad] copy of an OIHW fp32 parameter, cached per parameter version."""
     cache = getattr(w, "_s2r_pack", None)
@@ -179,14 +191,64 @@ def packed_weight(cx, w, transpose):
     stamp = (w._version, WEIGHT_EPOCH[0])
     if ent is not None and ent[0] == stamp:
         return ent[1], ent[2], ent[3]
-    Cout, Cin, R, S = w.shape
-    A, B = (Cin, Cout) if transpose else (Cout, Cin)
-    A_pad, B_pad = round_up(A, 16), round_up(B, 64)
-    buf = ent[1] if ent is not None else torch.empty((R * S, A_pad, B_pad), dtype=BF16, device=w.device)
-    L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, R, S, 1 if transpose else 0, _vp(buf), A_pad, B_pad,
-           cx.stream)
+    Cout, Cin, RS, A_pad, B_pad = _pack_dims(w, transpose)
+    buf = ent[1] if ent is not None else torch.empty((RS, A_pad, B_pad), dtype=BF16, device=w.device)
+    L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, w.shape[2], w.shape[3], 1 if transpose else 0, _vp(buf),
+           A_pad, B_pad, cx.stream)
     cache[key] = (stamp, buf, A_pad, B_pad)
+    _PACK_REGISTRY[(id(w), transpose)] = (weakref.ref(w), transpose)
     return buf, A_pad, B_pad
+
+
+def prepack_weights(stream, build_only=False):
+    """Re-pack, in ONE launch, every filter copy whose parameter changed since it was packed (call after the
+    optimizer kernels / at the start of a step).  Later packed_weight() calls then hit the cache.
+    build_only: only upload the job table (a host->device copy, which must happen outside CUDA-graph capture)."""
+    stale = []
+    for k, (ref, transpose) in list(_PACK_REGISTRY.items()):
+        w = ref()
+        if w is None:
+            del _PACK_REGISTRY[k]
+            continue
+        ent = w._s2r_pack.get((transpose, w.data_ptr()))
+        stamp = (w._version, WEIGHT_EPOCH[0])
+        if ent is None or ent[0] == stamp:
+            continue
+        stale.append((w, transpose, ent, stamp))
+    if not stale:
+        return 0
+    sig = tuple((w.data_ptr(), t, ent[1].data_ptr()) for w, t, ent, _ in stale)
+    tab = _PACK_TABLES.get(sig)
+    if tab is None:
+        jobs = []
+        for w, transpose, ent, _ in stale:
+            Cout, Cin, RS, A_pad, B_pad = _pack_dims(w, transpose)
+            total = RS * A_pad * B_pad
+            for b in range(0, total, _PACK_JOB_ELEMS):
+                jobs.append((w.data_ptr(), ent[1].data_ptr(), Cout, Cin, RS, 1 if transpose else 0, A_pad, B_pad, b,
+                             min(total, b + _PACK_JOB_ELEMS)))
+        chunks = []
+        for s0 in range(0, len(jobs), 65535):
+            part = jobs[s0:s0 + 65535]
+            arr = (L.PackJob * len(part))()
+            for i, j in enumerate(part):
+                (arr[i].w, arr[i].packed, arr[i].Cout, arr[i].Cin, arr[i].RS, arr[i].transpose, arr[i].A_pad, arr[i].B_pad,
+                 arr[i].begin, arr[i].end) = j
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(stale[0][0].device)
+            chunks.append((dev, len(part)))
+        tab = chunks
+        _PACK_TABLES.clear()          # one live signature is enough (the set of filters of a training job is fixed)
+        _PACK_TABLES[sig] = tab
+    if build_only:
+        return len(stale)
+    for dev, n in tab:
+        L.call("s2r_pack_weights_multi", _vp(dev), n, stream)
+    for w, transpose, ent, stamp in stale:
+        w._s2r_pack[(transpose, w.data_ptr())] = (stamp, ent[1], ent[2], ent[3])
+    return len(stale)
+
+
+_PACK_TABLES = {}
 
 
 def grad_of(p):

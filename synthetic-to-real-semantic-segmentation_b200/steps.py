@@ -14,7 +14,7 @@ F.softmax(dim=0) are taken over the rank-local batch.
 """
 import torch
 
-from .engine import seed_counter
+from .engine import seed_counter, prepack_weights
 from .functional import softmax_dim0, bce_with_logits, cross_entropy
 from .optim import FusedSGD, FusedAdam
 from .utils.loss import SegmentationLosses, DomainLosses
@@ -62,6 +62,7 @@ class AdaptStep(object):
         self.scheduler(self.optimizer_D, 0, 0)
         self.optimizer.advance()
         self.optimizer_D.advance()
+        prepack_weights(None, build_only=True)   # the job table is uploaded here, its launch is captured below
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_out = self._device_step(*self._static)
@@ -116,6 +117,8 @@ class AdaptStep(object):
         seed_counter(src_image.device).add_(1)
         self.optimizer.zero_grad()
         self.optimizer_D.zero_grad()
+        # all bf16 filter copies invalidated by the previous optimizer step, in one launch
+        prepack_weights(torch.cuda.current_stream(src_image.device).cuda_stream)
         # ---- train G; don't accumulate grads in D (train_adapt.py:140-155)
         for p in model_D.parameters():
             p.requires_grad = False
