@@ -431,21 +431,42 @@ tap_wgrad_kernel(const __grid_constant__ WgParams p) {
 }
 
 // ------------------------------------------------------------------------------ weight packing
-__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int RS, int transpose,
+// Source element of packed[t][a][b] in the OIHW fp32 filter, or -1 for zero padding.
+//   mode 0: forward, (a, b) = (co, ci), t = filter tap           mode 1: data gradient, (a, b) = (ci, co)
+// Row-tap forms of a 4x4 stride-2 pad-1 filter over a zero-padded NHWC buffer with Cp = round8(Cin) channels per pixel
+// (FCDiscriminator conv1; see engine.rowtap_*):
+//   mode 2: forward, slice t = kh, a = co, b = kw*Cp + c   (the four kw taps of a filter row are one contiguous run
+//           of 4*Cp channels in memory)
+//   mode 3/4: data gradient of the padded rows of parity ph = mode - 3, slice t = 2*ta + tb (dy offset (-ta, -tb)),
+//           a = pw*Cp + c (two adjacent padded pixels), b = co, filter element (kh, kw) = (ph + 2*ta, pw + 2*tb)
+__device__ __forceinline__ long long pack_src(int mode, int Cout, int Cin, int RS, int t, int a, int b) {
+  if (mode <= 1) {
+    const int co = mode ? b : a, ci = mode ? a : b;
+    return (co < Cout && ci < Cin) ? ((long long)co * Cin + ci) * RS + t : -1;
+  }
+  const int Cp = (Cin + 7) & ~7;
+  if (mode == 2) {
+    const int kw = b / Cp, c = b - kw * Cp;
+    return (a < Cout && kw < 4 && c < Cin) ? ((long long)a * Cin + c) * 16 + t * 4 + kw : -1;
+  }
+  const int ph = mode - 3, pw = a / Cp, c = a - pw * Cp;
+  const int kh = ph + 2 * (t >> 1), kw = pw + 2 * (t & 1);
+  return (b < Cout && pw < 2 && c < Cin) ? ((long long)b * Cin + c) * 16 + kh * 4 + kw : -1;
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int RS, int nslices, int mode,
                                    __nv_bfloat16* __restrict__ out, int A_pad, int B_pad) {
   pdl_wait();
   pdl_trigger();
-  const long long total = (long long)RS * A_pad * B_pad;
+  const long long total = (long long)nslices * A_pad * B_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i % B_pad);
     const long long q = i / B_pad;
     const int a = (int)(q % A_pad);
     const int t = (int)(q / A_pad);
-    const int co = transpose ? b : a, ci = transpose ? a : b;
-    float v = 0.f;
-    if (co < Cout && ci < Cin) v = __ldg(w + ((long long)co * Cin + ci) * RS + t);
-    out[i] = __float2bfloat16(v);
+    const long long src = pack_src(mode, Cout, Cin, RS, t, a, b);
+    out[i] = __float2bfloat16(src >= 0 ? __ldg(w + src) : 0.f);
   }
 }
 
@@ -462,10 +483,18 @@ __global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs)
     const long long q = i / j.B_pad;
     const int a = (int)(q % j.A_pad);
     const int t = (int)(q / j.A_pad);
-    const int co = j.transpose ? b : a, ci = j.transpose ? a : b;
-    float v = 0.f;
-    if (co < j.Cout && ci < j.Cin) v = __ldg(w + ((long long)co * j.Cin + ci) * j.RS + t);
-    out[i] = __float2bfloat16(v);
+    const long long src = pack_src(j.transpose, j.Cout, j.Cin, j.RS, t, a, b);
+    out[i] = __float2bfloat16(src >= 0 ? __ldg(w + src) : 0.f);
+  }
+}
+
+// w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]: the row-tap weight gradient (mode 2 layout, fp32) back to OIHW
+__global__ void rowtap_wgrad_scatter_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin, int Cp) {
+  const int total = Cout * Cin * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kw = i & 3, kh = (i >> 2) & 3, q = i >> 4;
+    const int c = q % Cin, co = q / Cin;
+    dw[i] += G[((long long)co * 4 + kh) * (4 * Cp) + kw * Cp + c];
   }
 }
 
@@ -607,14 +636,27 @@ extern "C" int s2r_conv_wgrad(const s2r_wgrad_args* a, s2r_stream_t stream) {
   return launch_wgrad<64>(p, st);
 }
 
-extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int transpose,
+extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode,
                                void* packed, int A_pad, int B_pad, s2r_stream_t stream) {
-  S2R_REQUIRE(w && packed && Cout >= 1 && Cin >= 1 && R >= 1 && S >= 1, S2R_ERR_SHAPE, "pack_weight: bad arguments");
-  const int A = transpose ? Cin : Cout, B = transpose ? Cout : Cin;
+  S2R_REQUIRE(w && packed && Cout >= 1 && Cin >= 1 && R >= 1 && S >= 1 && mode >= 0 && mode <= 4, S2R_ERR_SHAPE,
+              "pack_weight: bad arguments");
+  S2R_REQUIRE(mode <= 1 || (R == 4 && S == 4), S2R_ERR_UNSUPPORTED, "pack_weight: row-tap modes take 4x4 filters");
+  const int Cp = (Cin + 7) & ~7;
+  const int A = mode == 0 ? Cout : mode == 1 ? Cin : mode == 2 ? Cout : 2 * Cp;
+  const int B = mode == 0 ? Cin : mode == 1 ? Cout : mode == 2 ? 4 * Cp : Cout;
+  const int nslices = mode <= 1 ? R * S : 4;
   S2R_REQUIRE(A_pad >= A && B_pad >= B, S2R_ERR_SHAPE, "pack_weight: padded dims (%d,%d) smaller than (%d,%d)", A_pad, B_pad, A, B);
-  const long long total = (long long)R * S * A_pad * B_pad;
+  const long long total = (long long)nslices * A_pad * B_pad;
   S2R_CUDA_OK(s2r_launch(pack_weight_kernel, dim3(s2r_grid(total, 256, 8)), dim3(256), (size_t)0, (cudaStream_t)stream, w,
-                         Cout, Cin, R * S, transpose, (__nv_bfloat16*)packed, A_pad, B_pad));
+                         Cout, Cin, R * S, nslices, mode, (__nv_bfloat16*)packed, A_pad, B_pad));
+  return S2R_OK;
+}
+
+extern "C" int s2r_rowtap_wgrad_scatter(const float* G, float* dw, int Cout, int Cin, s2r_stream_t stream) {
+  S2R_REQUIRE(G && dw && Cout >= 1 && Cin >= 1, S2R_ERR_SHAPE, "rowtap_wgrad_scatter: bad arguments");
+  const int total = Cout * Cin * 16;
+  rowtap_wgrad_scatter_kernel<<<s2r_grid(total, 256, 1), 256, 0, (cudaStream_t)stream>>>(G, dw, Cout, Cin, (Cin + 7) & ~7);
+  S2R_LAUNCH_OK();
   return S2R_OK;
 }
 

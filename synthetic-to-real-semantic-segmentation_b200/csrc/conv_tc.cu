@@ -306,30 +306,58 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     constexpr int CHUNKS = BN / 32;
     const int act = p.act;
     const int aux_mode = p.aux_mode;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int mt = tile / n_tiles_n, n0 = (tile - mt * n_tiles_n) * BN;
+    const int row_h = row / p.BW, row_w = row - row_h * p.BW;   // this thread's pixel inside a patch
+    const bool one_n = n_tiles_n == 1;                            // Cout <= BN: tile index = pixel tile
+    const bool one_row = p.tiles_h == 1 && p.N == 1;              // flattened pointwise problem: one long pixel row
+    int lt = 0, rot = grp;                                        // rot = (grp + 3 - lt % 3) % 3, kept incrementally
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt, rot = rot == 0 ? 2 : rot - 1) {
+      const int mt = one_n ? tile : tile / n_tiles_n, n0 = one_n ? 0 : (tile - mt * n_tiles_n) * BN;
       const int ab = lt % NACC;
       const uint32_t aph = (lt / NACC) & 1;
+      // patch coordinates of the tile's sub-tiles: once per tile, not per unit, and without integer divisions in the
+      // common cases (they were a quarter of the epilogue's dependent-instruction chain on the pointwise convolutions)
+      int s_tw[MT], s_th[MT], s_tn[MT], s_oh[MT], s_ow[MT];
+      bool s_tok[MT], s_rok[MT];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int t = mt * MT + j;
+        s_tok[j] = t < p.n_subtiles;
+        const int tt = s_tok[j] ? t : 0;
+        const int q = one_row ? 0 : tt / p.tiles_w;
+        s_tw[j] = (tt - q * p.tiles_w) * p.BW;
+        s_tn[j] = one_row ? 0 : q / p.tiles_h;
+        s_th[j] = (q - s_tn[j] * p.tiles_h) * p.BH;
+        s_oh[j] = s_th[j] + row_h;
+        s_ow[j] = s_tw[j] + row_w;
+        s_rok[j] = s_tok[j] && s_oh[j] < p.OH && s_ow[j] < p.OW;
+      }
       mbar_wait(smem_addr(&bar_acc_full[ab]), aph);
       tc_fence_after();
+      bool released = false;
       // units are dealt round-robin to the three groups, rotating with the tile so that narrow tiles
       // (fewer than three units) still use all epilogue warps
 #pragma unroll 1
-      for (int u = (grp + 3 - lt % 3) % 3; u < MT * CHUNKS; u += 3) {
-        const int j = u / CHUNKS, c0 = (u - j * CHUNKS) * 32;
+      for (int u = rot; u < MT * CHUNKS; u += 3) {
+        const int j = (MT == 1) ? 0 : u / CHUNKS, c0 = (u - j * CHUNKS) * 32;
         if (n0 + c0 >= p.Cout) continue;
-        const int t = mt * MT + j;
-        const bool tok = t < p.n_subtiles;
-        const int tt = tok ? t : 0;
-        const int tw_ = (tt % p.tiles_w) * p.BW;
-        const int q = tt / p.tiles_w;
-        const int th_ = (q % p.tiles_h) * p.BH, tn_ = q / p.tiles_h;
-        const int oh_ = th_ + row / p.BW, ow_ = tw_ + row % p.BW;
-        const bool rok = tok && oh_ < p.OH && ow_ < p.OW;
+        static_assert(MT <= 2, "sub-tile select below");
+#define TC_SEL(a) ((MT == 1 || j == 0) ? a[0] : a[MT - 1])   // register select, no local-memory indexing
+        const bool tok = TC_SEL(s_tok);
+        const int tw_ = TC_SEL(s_tw), th_ = TC_SEL(s_th), tn_ = TC_SEL(s_tn);
+        const int oh_ = TC_SEL(s_oh), ow_ = TC_SEL(s_ow);
+        const bool rok = TC_SEL(s_rok);
+#undef TC_SEL
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * ACC_COLS + j * BN + c0), r);
         tmem_ld_wait();
+        if (u + 3 >= MT * CHUNKS) {
+          // last TMEM read of this warp in this tile: hand the accumulator back before the staging / store /
+          // statistics part, so that the MMAs of the tile after next do not wait for it
+          released = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_acc_empty[ab])) : "memory");
+        }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -407,26 +435,41 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           bulk_commit();
         }
         if (p.stats) {
-          // per-channel sum / sum of squares of the STORED (bf16) values: thread = (channel pair, 16-row segment)
-          const int pr = row & 15, seg = row >> 4;
+          // per-channel sum / sum of squares of the STORED (bf16) values.  thread = (channel pair, row class): warp ew
+          // owns the channel pairs 4*ew..4*ew+3, lane = (row class r mod 8, pair), so the 8 partial sums of a channel
+          // meet inside ONE warp (3 shuffle steps) and a single lane per channel touches the CTA accumulators.
+          // Shared-memory float atomics are CAS loops (ATOMS.CAST.SPIN): with one partial per (channel, 16-row
+          // segment) they ran 8-way contended and dominated the epilogue's latency chain.  Rows 8*rr + cls of one
+          // load instruction sit in 32 distinct banks (64-byte rows, chunk XOR (row >> 1) & 3).
+          const int pr = ew * 4 + (lane & 3), cls = lane >> 2;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
-            const int r2 = seg * 16 + rr;
+            const int r2 = rr * 8 + cls;
             const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + r2 * 64 + ((((pr >> 2) ^ ((r2 >> 1) & 3))) << 4) + (pr & 3) * 4);
             const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
             s0 += f0; s1 += f1;
             q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
           }
-          const int ch = n0 + c0 + 2 * pr;
-          if (ch < p.Cout) { atomicAdd(&s_sum[ch], s0); atomicAdd(&s_sq[ch], q0); }
-          if (ch + 1 < p.Cout) { atomicAdd(&s_sum[ch + 1], s1); atomicAdd(&s_sq[ch + 1], q1); }
+#pragma unroll
+          for (int sh = 4; sh < 32; sh <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, sh);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, sh);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, sh);
+          }
+          // all 8 lanes of a channel pair now hold the 4 totals: lanes cls = 0..3 add one of them each (one CAS loop
+          // per thread instead of four in sequence)
+          const int ch = n0 + c0 + 2 * pr + (cls >> 1);
+          const float tv = cls == 0 ? s0 : cls == 1 ? q0 : cls == 2 ? s1 : q1;
+          if (cls < 4 && ch < p.Cout) atomicAdd(((cls & 1) ? s_sq : s_sum) + ch, tv);
         }
       }
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_acc_empty[ab])) : "memory");
+      if (!released) {   // no unit, or the last one was skipped: all TMEM reads of this accumulator are complete
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_acc_empty[ab])) : "memory");
+      }
     }
     if (row == 0) bulk_wait0();   // this group's TMA stores are complete before the CTA exits
   }
@@ -611,7 +654,8 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
 
   // tile width in output channels
   int BN;
-  if (a->Cout > 128) BN = 256;
+  if (a->Cout > 256 && a->Cout <= 320) BN = 160;   // 257..320 channels: two 160-wide tiles instead of 256 + a sliver
+  else if (a->Cout > 128) BN = 256;
   else if (a->Cout > 64) BN = 128;
   else if (a->Cout > 32) BN = 64;
   else BN = 32;
@@ -650,6 +694,7 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
   const bool big = deep && nsub * ntn >= 2ll * s2r_sm_count() * 2;
   switch (BN) {
     case 256: return big ? launch_tc<256, 2, 3>(maps, p, ntn, st) : launch_tc<256, 1, 4>(maps, p, ntn, st);
+    case 160: return big ? launch_tc<160, 2, 3>(maps, p, ntn, st) : launch_tc<160, 1, 5>(maps, p, ntn, st);
     case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 6>(maps, p, ntn, st);
     case 64: return launch_tc<64, 1, 8>(maps, p, ntn, st);
     default: return launch_tc<32, 1, 8>(maps, p, ntn, st);

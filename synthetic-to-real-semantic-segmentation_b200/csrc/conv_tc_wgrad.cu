@@ -393,7 +393,8 @@ int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st) {
 
   const int cin8 = (a->Cin + 7) & ~7, cout8 = (a->Cout + 7) & ~7;
   int BN;
-  if (a->Cin > 128) BN = 256;
+  if (a->Cin > 256 && a->Cin <= 320) BN = 160;   // 257..320 input channels: two 160-wide tiles, not 256 + a sliver
+  else if (a->Cin > 128) BN = 256;
   else if (a->Cin > 64) BN = 128;
   else if (a->Cin > 32) BN = 64;
   else BN = 32;
@@ -431,6 +432,7 @@ int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st) {
   if (MT == 2) {
     switch (BN) {
       case 256: return launch_wg<256, 2, 3>(maps, p, st);
+      case 160: return launch_wg<160, 2, 3>(maps, p, st);
       case 128: return launch_wg<128, 2, 4>(maps, p, st);
       case 64: return launch_wg<64, 2, 4>(maps, p, st);
       default: return launch_wg<32, 2, 4>(maps, p, st);
@@ -438,6 +440,7 @@ int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st) {
   }
   switch (BN) {
     case 256: return launch_wg<256, 1, 4>(maps, p, st);
+    case 160: return launch_wg<160, 1, 4>(maps, p, st);
     case 128: return launch_wg<128, 1, 6>(maps, p, st);
     case 64: return launch_wg<64, 1, 8>(maps, p, st);
     default: return launch_wg<32, 1, 8>(maps, p, st);
