@@ -105,17 +105,25 @@ typedef struct {
 
 int s2r_conv_wgrad(const s2r_wgrad_args* a, s2r_stream_t stream);
 
-/* w: fp32 [Cout][Cin][R][S] (OIHW, nn.Conv2d.weight).  packed: bf16 [R*S][A_pad][B_pad] with
- * (A,B) = (Cout,Cin) when transpose == 0 (forward) or (Cin,Cout) when transpose == 1 (data
- * gradient); A_pad/B_pad >= A/B, padding is zero filled. */
-int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int transpose, void* packed,
+/* w: fp32 [Cout][Cin][R][S] (OIHW, nn.Conv2d.weight).  packed: bf16 [slices][A_pad][B_pad], zero padded.
+ *   mode 0 (forward):       slices = R*S, (A,B) = (Cout,Cin)
+ *   mode 1 (data gradient): slices = R*S, (A,B) = (Cin,Cout)
+ * Row-tap forms of a 4x4 stride-2 pad-1 filter (modeling/discriminator.py:11) over a zero-padded NHWC buffer with
+ * Cp = round8(Cin) channels per pixel, where the four kw taps of a filter row are 4*Cp contiguous channels:
+ *   mode 2 (forward):       slices = 4 (kh), (A,B) = (Cout, 4*Cp), b = kw*Cp + c
+ *   mode 3/4 (data gradient of the padded rows of parity mode-3): slices = 4 (dy offset (-ta,-tb), slice 2*ta+tb),
+ *                           (A,B) = (2*Cp, Cout), a = pw*Cp + c, filter element (kh,kw) = (ph+2*ta, pw+2*tb) */
+int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, void* packed,
                     int A_pad, int B_pad, s2r_stream_t stream);
+/* w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]: a weight gradient accumulated in the mode-2 layout (fp32
+ * [Cout][4][4*Cp]) added into the OIHW gradient of the 4x4 filter. */
+int s2r_rowtap_wgrad_scatter(const float* G, float* dw, int Cout, int Cin, s2r_stream_t stream);
 /* The same for many filters in one launch.  A job packs the elements [begin, end) of one packed filter
  * (flattened [R*S][A_pad][B_pad] index); the table lives in device memory. */
 typedef struct s2r_pack_job {
   const float* w;
   void* packed;
-  int32_t Cout, Cin, RS, transpose, A_pad, B_pad;
+  int32_t Cout, Cin, RS, transpose /* = mode of s2r_pack_weight */, A_pad, B_pad;
   int64_t begin, end;
 } s2r_pack_job;
 int s2r_pack_weights_multi(const s2r_pack_job* jobs, int njobs, s2r_stream_t stream);
@@ -224,6 +232,15 @@ int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t strea
 int s2r_softmax_dim0_fwd(const float* x, float* y, int B, int64_t M, s2r_stream_t stream);
 int s2r_softmax_dim0_bwd(const float* y, const float* dy, float* dx, int B, int64_t M,
                          s2r_stream_t stream);
+/* The composite `model_D(F.softmax(x, dim=0))` input stage (train_adapt.py:151,166,174 feeding
+ * modeling/discriminator.py:23): x fp32 [B][C][H][W] -> yp bf16 [B][H+2][W+2][Cp], the (optional) batch-axis softmax
+ * written into the interior of a zero-padded NHWC buffer (border and pad channels are written as zeros).  softmax != 0
+ * needs B <= 8 (S2R_ERR_UNSUPPORTED otherwise).  _bwd: dx fp32 [B][C][H][W] from the gradient gp w.r.t. yp (same padded
+ * layout, interior read) with the softmax recomputed from x; softmax == 0: layout conversion only (x may be NULL). */
+int s2r_softmax0_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, int softmax, void* yp, int Cp,
+                                  s2r_stream_t stream);
+int s2r_softmax0_nhwc_pad_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, int softmax,
+                              float* dx, s2r_stream_t stream);
 int s2r_cross_entropy_nchw(const float* logits, const float* target, int const_target,
                            const float* weight, int N, int C, int64_t HW, int ignore_index,
                            double* sums, float* grad_unscaled, s2r_stream_t stream);

@@ -59,6 +59,9 @@ PROTOTYPES = {
     "s2r_conv_wgrad": [C.POINTER(WgradArgs), vp],
     "s2r_pack_weight": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
     "s2r_pack_weights_multi": [vp, i32, vp],
+    "s2r_rowtap_wgrad_scatter": [vp, vp, i32, i32, vp],
+    "s2r_softmax0_nchw_to_nhwc_pad": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
+    "s2r_softmax0_nhwc_pad_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -228,6 +228,134 @@ bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ target, fl
   }
 }
 
+
+// ---------------------------------------------------------------- softmax(dim=0) -> zero-padded NHWC bf16
+// The discriminator consumes F.softmax(logits, dim=0) (train_adapt.py:151,166,174) through a 4x4 stride-2 pad-1
+// convolution.  Instead of an fp32 NCHW softmax tensor followed by a patch matrix (16x the input in bf16), the batch
+// softmax is written ONCE as bf16 into a zero-padded NHWC buffer [B][H+2][W+2][Cp]: in that buffer the four kw taps of
+// a filter row are one contiguous run of 4*Cp channels, so conv1 becomes a 4-tap GEMM over an overlapping strided view
+// (engine.rowtap_*).  A CTA handles a strip of 128 pixels of one image row for up to 8 batch entries: coalesced fp32
+// reads along w, transpose through shared memory, coalesced 16-byte stores of whole pixels.
+constexpr int SP_TW = 128;
+constexpr int SP_THREADS = 256;
+constexpr int SP_MAXB = 8;
+
+template <bool SOFTMAX>
+__global__ void __launch_bounds__(SP_THREADS)
+softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, int W, __nv_bfloat16* __restrict__ y, int Cp) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(sp_smem);   // [bc][SP_TW][Cp]
+  const int w0 = blockIdx.x * SP_TW, h = blockIdx.y, b0 = blockIdx.z * SP_MAXB;
+  const int bc = min(SP_MAXB, B - b0), npx = min(SP_TW, W - w0);
+  const long long plane = (long long)H * W;
+  const int Wp = W + 2, Hp = H + 2;
+  // pad channels (and everything else) start at zero
+  for (int i = threadIdx.x; i < bc * SP_TW * Cp / 8; i += SP_THREADS) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int cpairs = (C + 1) >> 1;
+  for (int it = threadIdx.x; it < cpairs * SP_TW; it += SP_THREADS) {
+    const int w = it & (SP_TW - 1), cp = it / SP_TW;
+    if (w >= npx) continue;
+    const int c0 = 2 * cp;
+    const bool has1 = c0 + 1 < C;
+    float t0[SP_MAXB], t1[SP_MAXB];
+    const float* src = x + ((long long)b0 * C + c0) * plane + (long long)h * W + w0 + w;
+#pragma unroll
+    for (int b = 0; b < SP_MAXB; ++b) {
+      t0[b] = b < bc ? __ldg(src + (long long)b * C * plane) : -INFINITY;
+      t1[b] = (b < bc && has1) ? __ldg(src + (long long)b * C * plane + plane) : -INFINITY;
+    }
+    if (SOFTMAX) {
+      float m0 = -INFINITY, m1 = -INFINITY, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) { m0 = fmaxf(m0, t0[b]); m1 = fmaxf(m1, t1[b]); }
+      if (!has1) m1 = 0.f;
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) {
+        t0[b] = b < bc ? __expf(t0[b] - m0) : 0.f;
+        t1[b] = (b < bc && has1) ? __expf(t1[b] - m1) : 0.f;
+        s0 += t0[b]; s1 += t1[b];
+      }
+      s0 = 1.f / s0; s1 = has1 ? 1.f / s1 : 0.f;
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) { t0[b] *= s0; t1[b] *= s1; }
+    }
+#pragma unroll
+    for (int b = 0; b < SP_MAXB; ++b)
+      if (b < bc) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(t0[b], has1 ? t1[b] : 0.f);
+        *reinterpret_cast<__nv_bfloat162*>(tile + ((long long)b * SP_TW + w) * Cp + c0) = v;
+      }
+  }
+  __syncthreads();
+  const int vpp = Cp / 8;   // 16-byte vectors per pixel
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  for (int b = 0; b < bc; ++b) {
+    __nv_bfloat16* img = y + (long long)(b0 + b) * Hp * Wp * Cp;
+    uint4* dst = reinterpret_cast<uint4*>(img + ((long long)(h + 1) * Wp + w0 + 1) * Cp);
+    const uint4* srcv = reinterpret_cast<const uint4*>(tile + (long long)b * SP_TW * Cp);
+    for (int v = threadIdx.x; v < npx * vpp; v += SP_THREADS) dst[v] = srcv[v];
+    // zero border: left / right pixel of this row, and the rows above / below the image for this strip (+ corners)
+    if (w0 == 0 && threadIdx.x < vpp) reinterpret_cast<uint4*>(img + (long long)(h + 1) * Wp * Cp)[threadIdx.x] = z4;
+    if (w0 + npx == W && threadIdx.x < vpp)
+      reinterpret_cast<uint4*>(img + ((long long)(h + 1) * Wp + W + 1) * Cp)[threadIdx.x] = z4;
+    if (h == 0 || h == H - 1) {
+      const int lo = w0 == 0 ? 0 : w0 + 1, hi = w0 + npx == W ? W + 2 : w0 + npx + 1;   // padded columns [lo, hi)
+      for (int r = 0; r < 2; ++r) {
+        if ((r == 0 && h != 0) || (r == 1 && h != H - 1)) continue;
+        uint4* row = reinterpret_cast<uint4*>(img + ((long long)(r == 0 ? 0 : H + 1) * Wp + lo) * Cp);
+        for (int v = threadIdx.x; v < (hi - lo) * vpp; v += SP_THREADS) row[v] = z4;
+      }
+    }
+  }
+}
+
+// dx[b][c][h][w] = y_b * (g_b - sum_b' g_b' y_b') with y = softmax over b of x (recomputed) and g read from the
+// interior of the padded NHWC bf16 gradient; SOFTMAX = false: plain layout conversion dx = g.
+template <bool SOFTMAX>
+__global__ void __launch_bounds__(SP_THREADS)
+softmax0_nhwc_pad_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ gp, int B, int C, int H,
+                             int W, int Cp, float* __restrict__ dx) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(sp_smem);
+  const int w0 = blockIdx.x * SP_TW, h = blockIdx.y, b0 = blockIdx.z * SP_MAXB;
+  const int bc = min(SP_MAXB, B - b0), npx = min(SP_TW, W - w0);
+  const long long plane = (long long)H * W;
+  const int Wp = W + 2, Hp = H + 2, vpp = Cp / 8;
+  for (int b = 0; b < bc; ++b) {
+    const uint4* src = reinterpret_cast<const uint4*>(gp + (((long long)(b0 + b) * Hp + h + 1) * Wp + w0 + 1) * Cp);
+    uint4* dstv = reinterpret_cast<uint4*>(tile + (long long)b * SP_TW * Cp);
+    for (int v = threadIdx.x; v < npx * vpp; v += SP_THREADS) dstv[v] = __ldg(src + v);
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < C * SP_TW; it += SP_THREADS) {
+    const int w = it & (SP_TW - 1), c = it / SP_TW;
+    if (w >= npx) continue;
+    const long long off = ((long long)b0 * C + c) * plane + (long long)h * W + w0 + w;
+    float g[SP_MAXB], t[SP_MAXB];
+#pragma unroll
+    for (int b = 0; b < SP_MAXB; ++b) {
+      g[b] = b < bc ? __bfloat162float(tile[((long long)b * SP_TW + w) * Cp + c]) : 0.f;
+      t[b] = (SOFTMAX && b < bc) ? __ldg(x + off + (long long)b * C * plane) : -INFINITY;
+    }
+    if (SOFTMAX) {
+      float m = -INFINITY, s = 0.f, dot = 0.f;
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) m = fmaxf(m, t[b]);
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) { t[b] = b < bc ? __expf(t[b] - m) : 0.f; s += t[b]; }
+      s = 1.f / s;
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) { t[b] *= s; dot = fmaf(t[b], g[b], dot); }
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b) g[b] = t[b] * (g[b] - dot);
+    }
+#pragma unroll
+    for (int b = 0; b < SP_MAXB; ++b)
+      if (b < bc) dx[off + (long long)b * C * plane] = g[b];
+  }
+}
+
 }  // namespace
 
 extern "C" int s2r_softmax_dim0_fwd(const float* x, float* y, int B, int64_t M, s2r_stream_t stream) {
@@ -305,4 +433,53 @@ extern "C" int s2r_bce_logits_bwd(const float* x, const float* target, float con
   bce_bwd_kernel<<<s2r_grid(n, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(x, target, const_target, n, gout, dx);
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+template <bool SOFTMAX>
+static int launch_sp_fwd(const float* x, int B, int C, int H, int W, void* yp, int Cp, cudaStream_t st) {
+  const int smem = min(B, SP_MAXB) * SP_TW * Cp * 2;
+  static bool attr = false;
+  if (!attr) {
+    S2R_CUDA_OK(cudaFuncSetAttribute(softmax0_to_nhwc_pad_kernel<SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_MAXB * SP_TW * 64 * 2));
+    attr = true;
+  }
+  dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
+  softmax0_to_nhwc_pad_kernel<SOFTMAX><<<grid, SP_THREADS, smem, st>>>(x, B, C, H, W, (__nv_bfloat16*)yp, Cp);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+template <bool SOFTMAX>
+static int launch_sp_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, float* dx, cudaStream_t st) {
+  const int smem = min(B, SP_MAXB) * SP_TW * Cp * 2;
+  static bool attr = false;
+  if (!attr) {
+    S2R_CUDA_OK(cudaFuncSetAttribute(softmax0_nhwc_pad_bwd_kernel<SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_MAXB * SP_TW * 64 * 2));
+    attr = true;
+  }
+  dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
+  softmax0_nhwc_pad_bwd_kernel<SOFTMAX><<<grid, SP_THREADS, smem, st>>>(x, (const __nv_bfloat16*)gp, B, C, H, W, Cp, dx);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_softmax0_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, int softmax, void* yp, int Cp,
+                                             s2r_stream_t stream) {
+  S2R_REQUIRE(x && yp && B >= 1 && C >= 1 && H >= 1 && W >= 1 && H <= 65535, S2R_ERR_SHAPE, "softmax0_to_nhwc_pad: bad shape");
+  S2R_REQUIRE(Cp % 8 == 0 && Cp >= C && Cp <= 64 && (uintptr_t)yp % 16 == 0, S2R_ERR_SHAPE,
+              "softmax0_to_nhwc_pad: channel pitch %d (need a multiple of 8 in [C, 64]) / alignment", Cp);
+  S2R_REQUIRE(!softmax || B <= SP_MAXB, S2R_ERR_UNSUPPORTED, "softmax0_to_nhwc_pad: batch %d > %d", B, SP_MAXB);
+  return softmax ? launch_sp_fwd<true>(x, B, C, H, W, yp, Cp, (cudaStream_t)stream)
+                 : launch_sp_fwd<false>(x, B, C, H, W, yp, Cp, (cudaStream_t)stream);
+}
+
+extern "C" int s2r_softmax0_nhwc_pad_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, int softmax,
+                                         float* dx, s2r_stream_t stream) {
+  S2R_REQUIRE(gp && dx && (x || !softmax) && B >= 1 && C >= 1 && H >= 1 && W >= 1 && H <= 65535, S2R_ERR_SHAPE,
+              "softmax0_nhwc_pad_bwd: bad shape");
+  S2R_REQUIRE(Cp % 8 == 0 && Cp >= C && Cp <= 64 && (uintptr_t)gp % 16 == 0, S2R_ERR_SHAPE,
+              "softmax0_nhwc_pad_bwd: channel pitch %d (need a multiple of 8 in [C, 64]) / alignment", Cp);
+  S2R_REQUIRE(!softmax || B <= SP_MAXB, S2R_ERR_UNSUPPORTED, "softmax0_nhwc_pad_bwd: batch %d > %d", B, SP_MAXB);
+  return softmax ? launch_sp_bwd<true>(x, gp, B, C, H, W, Cp, dx, (cudaStream_t)stream)
+                 : launch_sp_bwd<false>(x, gp, B, C, H, W, Cp, dx, (cudaStream_t)stream);
 }

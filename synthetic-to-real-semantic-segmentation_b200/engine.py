@@ -169,10 +169,18 @@ class Ctx:
 WEIGHT_EPOCH = [0]
 
 
-def _pack_dims(w, transpose):
+def _pack_dims(w, mode):
+    """(Cout, Cin, R*S, slices, A_pad, B_pad) of the packed copy of an OIHW filter; modes as s2r_pack_weight."""
     Cout, Cin, R, S = w.shape
-    A, B = (Cin, Cout) if transpose else (Cout, Cin)
-    return Cout, Cin, R * S, round_up(A, 16), round_up(B, 64)
+    mode = int(mode)
+    Cp = round_up(Cin, 8)
+    if mode <= 1:
+        A, B, ns = ((Cin, Cout) if mode else (Cout, Cin)) + (R * S,)
+    elif mode == 2:
+        A, B, ns = Cout, 4 * Cp, 4
+    else:
+        A, B, ns = 2 * Cp, Cout, 4
+    return Cout, Cin, R * S, ns, round_up(A, 16), round_up(B, 64)
 
 
 # every (filter, orientation) that has been packed: prepack_weights() refreshes all stale ones in one launch
@@ -180,23 +188,25 @@ _PACK_REGISTRY = {}
 _PACK_JOB_ELEMS = 4096
 
 
-def packed_weight(cx, w, transpose):
-    """bf16 [R*S][A_pad][B_pad] copy of an OIHW fp32 parameter, cached per parameter version."""
+def packed_weight(cx, w, mode):
+    """bf16 [slices][A_pad][B_pad] copy of an OIHW fp32 parameter, cached per parameter version.
+    mode: False/0 forward, True/1 data gradient, 2..4 the row-tap forms of a 4x4 stride-2 filter (s2r_pack_weight)."""
+    mode = int(mode)
     cache = getattr(w, "_s2r_pack", None)
     if cache is None:
         cache = {}
         w._s2r_pack = cache
-    key = (transpose, w.data_ptr())
+    key = (mode, w.data_ptr())
     ent = cache.get(key)
     stamp = (w._version, WEIGHT_EPOCH[0])
     if ent is not None and ent[0] == stamp:
         return ent[1], ent[2], ent[3]
-    Cout, Cin, RS, A_pad, B_pad = _pack_dims(w, transpose)
-    buf = ent[1] if ent is not None else torch.empty((RS, A_pad, B_pad), dtype=BF16, device=w.device)
-    L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, w.shape[2], w.shape[3], 1 if transpose else 0, _vp(buf),
+    Cout, Cin, RS, ns, A_pad, B_pad = _pack_dims(w, mode)
+    buf = ent[1] if ent is not None else torch.empty((ns, A_pad, B_pad), dtype=BF16, device=w.device)
+    L.call("s2r_pack_weight", _vp(w.detach()), Cout, Cin, w.shape[2], w.shape[3], mode, _vp(buf),
            A_pad, B_pad, cx.stream)
     cache[key] = (stamp, buf, A_pad, B_pad)
-    _PACK_REGISTRY[(id(w), transpose)] = (weakref.ref(w), transpose)
+    _PACK_REGISTRY[(id(w), mode)] = (weakref.ref(w), mode)
     return buf, A_pad, B_pad
 
 
@@ -222,10 +232,10 @@ def prepack_weights(stream, build_only=False):
     if tab is None:
         jobs = []
         for w, transpose, ent, _ in stale:
-            Cout, Cin, RS, A_pad, B_pad = _pack_dims(w, transpose)
-            total = RS * A_pad * B_pad
+            Cout, Cin, RS, ns, A_pad, B_pad = _pack_dims(w, transpose)
+            total = ns * A_pad * B_pad
             for b in range(0, total, _PACK_JOB_ELEMS):
-                jobs.append((w.data_ptr(), ent[1].data_ptr(), Cout, Cin, RS, 1 if transpose else 0, A_pad, B_pad, b,
+                jobs.append((w.data_ptr(), ent[1].data_ptr(), Cout, Cin, RS, int(transpose), A_pad, B_pad, b,
                              min(total, b + _PACK_JOB_ELEMS)))
         chunks = []
         for s0 in range(0, len(jobs), 65535):
@@ -408,6 +418,107 @@ def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
     a.dweight = g.data_ptr()
     a.s_co, a.s_ci = Cin * R * S, R * S
     L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+
+
+# --------------------------------------------------------------------------- row-tap 4x4 stride-2 convolution
+class PadAct:
+    """Zero-padded NHWC bf16 image [N][H+2][W+2][Cp] of a logical [N,H,W,C] tensor (Cp = round8(C)).  In this buffer the
+    four kw taps of a row of a 4x4 stride-2 pad-1 filter (modeling/discriminator.py:11) are ONE contiguous run of 4*Cp
+    channels starting at padded pixel (2*oh + kh, 2*ow), so the convolution is a 4-tap GEMM over an overlapping strided
+    view -- no patch matrix (16x the input) and no 16 taps of 24 channels padded to 64."""
+    __slots__ = ("t", "N", "H", "W", "C", "Cp")
+
+    def __init__(self, t, H, W, Cc):
+        self.t, self.N, self.H, self.W, self.C = t, t.shape[0], H, W, Cc
+        self.Cp = t.shape[3]
+        assert tuple(t.shape) == (self.N, H + 2, W + 2, self.Cp) and t.dtype == BF16 and t.is_contiguous()
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+def rowtap_ok(Cc, H, W):
+    return Cc <= 64 and H % 2 == 0 and W % 2 == 0 and H >= 2 and W >= 2
+
+
+def _rowtap_views(taps, xp):
+    Hp, Wp, Cp = xp.H + 2, xp.W + 2, xp.Cp
+    OH, OW = xp.H // 2, xp.W // 2
+    for kh in range(4):
+        _fill_tap(taps[kh], xp.ptr + 2 * kh * Wp * Cp, Hp * Wp * Cp, 2 * Wp * Cp, 2 * Cp, OH, OW, 0, 0, kh, kh * 4 * Cp)
+    return OH, OW
+
+
+def rowtap_fwd(cx, xp, w, out, bias=None, act=L.ACT_NONE, slope=0.0):
+    """out = act(conv4x4_s2_p1(x, w) + bias) with x given as a PadAct."""
+    Cout, Cin, R, S = w.shape
+    assert (R, S) == (4, 4) and Cin == xp.C
+    wp, A_pad, B_pad = packed_weight(cx, w, 2)
+    a = L.ConvArgs()
+    a.struct_size = C.sizeof(L.ConvArgs)
+    a.ntaps = 4
+    OH, OW = _rowtap_views(a.taps, xp)
+    assert (out.N, out.H, out.W) == (xp.N, OH, OW) and out.C >= Cout
+    a.N, a.OH, a.OW = xp.N, OH, OW
+    a.Cin, a.Cout = 4 * xp.Cp, Cout
+    a.w, a.Cout_pad, a.Kpad = wp.data_ptr(), A_pad, B_pad
+    a.out = out.ptr
+    a.on, a.oh, a.ow = out.H * out.W * out.pitch, out.W * out.pitch, out.pitch
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.act, a.slope = act, slope
+    a.aux_mode = L.AUX_NONE
+    a.stats = None
+    L.call("s2r_conv_fwd", C.byref(a), cx.stream)
+    return out
+
+
+def rowtap_wgrad(cx, xp, dy, w):
+    """w.grad += weight gradient of the same convolution (accumulated in the row-tap layout, then scattered to OIHW)."""
+    Cout, Cin, R, S = w.shape
+    Cp = xp.Cp
+    G = cx.f32(Cout * 16 * Cp)
+    a = L.WgradArgs()
+    a.struct_size = C.sizeof(L.WgradArgs)
+    a.ntaps = 4
+    _rowtap_views(a.taps, xp)
+    a.N, a.OH, a.OW = dy.N, dy.H, dy.W
+    a.Cin, a.Cout = 4 * Cp, Cout
+    a.dy = dy.ptr
+    a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
+    a.dweight = G.data_ptr()
+    a.s_co, a.s_ci = 16 * Cp, 1
+    L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+    L.call("s2r_rowtap_wgrad_scatter", _vp(G), _vp(grad_of(w)), Cout, Cin, cx.stream)
+
+
+def rowtap_dgrad(cx, dy, w, H, W):
+    """Gradient w.r.t. the padded input as a PadAct (border rows / columns hold the irrelevant gradient of the zero
+    padding): one launch per padded-row parity, each output "pixel" = two adjacent padded pixels (2*Cp channels)."""
+    Cout, Cin, R, S = w.shape
+    Cp = round_up(Cin, 8)
+    Hp, Wp = H + 2, W + 2
+    dxp = PadAct(torch.empty((dy.N, Hp, Wp, Cp), dtype=BF16, device=cx.device), H, W, Cin)
+    for ph in range(2):
+        wp, A_pad, B_pad = packed_weight(cx, w, 3 + ph)
+        a = L.ConvArgs()
+        a.struct_size = C.sizeof(L.ConvArgs)
+        a.ntaps = 4
+        for t in range(4):
+            _fill_tap(a.taps[t], dy.ptr, dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch, dy.H, dy.W,
+                      -(t >> 1), -(t & 1), t, 0)
+        a.N, a.OH, a.OW = dy.N, Hp // 2, Wp // 2
+        a.Cin, a.Cout = round_up(Cout, 8), 2 * Cp
+        assert dy.pitch - dy.off >= a.Cin
+        a.w, a.Cout_pad, a.Kpad = wp.data_ptr(), A_pad, B_pad
+        a.out = dxp.ptr + 2 * ph * Wp * Cp
+        a.on, a.oh, a.ow = Hp * Wp * Cp, 2 * Wp * Cp, 2 * Cp
+        a.bias = None
+        a.act, a.slope = L.ACT_NONE, 0.0
+        a.aux_mode = L.AUX_NONE
+        a.stats = None
+        L.call("s2r_conv_fwd", C.byref(a), cx.stream)
+    return dxp
 
 
 def bias_grad(cx, dy, b):

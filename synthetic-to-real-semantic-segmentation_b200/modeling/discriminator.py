@@ -3,23 +3,44 @@ five biased 4x4 stride-2 convolutions, LeakyReLU(0.2) between them, as tap-GEMMs
 input-parity views with bias + LeakyReLU fused in the epilogue; the backward fuses the LeakyReLU
 mask into the next layer's data-gradient epilogue.
 """
+import ctypes as C
+
 import torch.nn as nn
 
+import torch
+
 from .. import _lib as L
-from ..engine import conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up, im2col, patch_weight, Act
+from ..engine import (conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up, im2col, patch_weight, Act,
+                      PadAct, rowtap_ok, rowtap_fwd, rowtap_wgrad, rowtap_dgrad, BF16, _vp)
 from ..runtime import RunBase, call_module
 
 
 class FCDiscriminatorRun(RunBase):
-    raw_inputs = True   # conv1 reads the NCHW fp32 input through the patch kernel (19 channels, 16 taps)
+    """conv1 reads its NCHW fp32 argument directly (raw_inputs): the argument -- optionally through the batch-axis
+    softmax of train_adapt.py:151,166,174 (softmax0=True, the fused form of `model_D(F.softmax(x, dim=0))`) -- is
+    written once as bf16 into a zero-padded NHWC buffer and conv1 runs as a 4-tap row GEMM on it (engine.PadAct).
+    Inputs the row-tap form does not cover (odd sizes, > 64 channels) take the patch-matrix path."""
+    raw_inputs = True
 
-    def __init__(self, mod):
+    def __init__(self, mod, softmax0=False):
         self.convs = [mod.conv1, mod.conv2, mod.conv3, mod.conv4, mod.classifier]
         self.slope = mod.leaky_relu.negative_slope
+        self.softmax0 = softmax0
 
     def forward(self, cx, x):
         self.in_shape = (x.N, x.H, x.W, x.C)
-        acts = [im2col(cx, x, 4, 4, 2, 1)]   # conv1 as a pointwise GEMM over 4x4 patches
+        self.rowtap = rowtap_ok(x.C, x.H, x.W) and not (self.softmax0 and x.N > 8)
+        if self.rowtap:
+            Cp = round_up(x.C, 8)
+            xp = PadAct(torch.empty((x.N, x.H + 2, x.W + 2, Cp), dtype=BF16, device=cx.device), x.H, x.W, x.C)
+            L.call("s2r_softmax0_nchw_to_nhwc_pad", _vp(x.t), x.N, x.C, x.H, x.W, 1 if self.softmax0 else 0,
+                   C.c_void_p(xp.ptr), Cp, cx.stream)
+            self.logits = x.t if self.softmax0 else None
+            acts = [xp]
+        else:
+            if self.softmax0:
+                raise NotImplementedError("fused softmax input needs even sizes, <= 64 channels and batch <= 8")
+            acts = [im2col(cx, x, 4, 4, 2, 1)]   # conv1 as a pointwise GEMM over 4x4 patches
         h = x
         for i, c in enumerate(self.convs):
             last = i == len(self.convs) - 1
@@ -27,7 +48,9 @@ class FCDiscriminatorRun(RunBase):
             OH, OW = conv_out_hw(h.H, h.W, 4, 4, 2, 1, 1)
             y = cx.new(h.N, OH, OW, round_up(Cout, 8), zero=Cout % 8 != 0)
             y.C = Cout
-            if i == 0:
+            if i == 0 and self.rowtap:
+                rowtap_fwd(cx, acts[0], c.weight, y, bias=c.bias, act=L.ACT_LEAKY, slope=self.slope)
+            elif i == 0:
                 conv_fwd(cx, acts[0], patch_weight(c.weight), y, bias=c.bias, act=L.ACT_LEAKY, slope=self.slope)
             else:
                 conv_fwd(cx, h, c.weight, y, stride=2, pad=1, bias=c.bias,
@@ -46,7 +69,9 @@ class FCDiscriminatorRun(RunBase):
             c = self.convs[i]
             xin = acts[i]
             if c.weight.requires_grad:
-                if i == 0:
+                if i == 0 and self.rowtap:
+                    rowtap_wgrad(cx, xin, d, c.weight)
+                elif i == 0:
                     conv_wgrad(cx, xin, d, patch_weight(c.weight), grad_param=c.weight)
                 else:
                     conv_wgrad(cx, xin, d, c.weight, stride=2, pad=1)
@@ -54,6 +79,15 @@ class FCDiscriminatorRun(RunBase):
                 bias_grad(cx, d, c.bias)
             if i == 0 and not need_dx:
                 return None
+            if i == 0 and self.rowtap:
+                # gradient w.r.t. the padded bf16 input, then (softmax backward +) NHWC -> NCHW fp32 in one pass
+                N, H, W, Cc = self.in_shape
+                dxp = rowtap_dgrad(cx, d, c.weight, H, W)
+                dx = torch.empty((N, Cc, H, W), dtype=torch.float32, device=cx.device)
+                L.call("s2r_softmax0_nhwc_pad_bwd", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
+                       1 if self.softmax0 else 0, _vp(dx), cx.stream)
+                self.logits = None
+                return dx
             if i == 0:
                 N, H, W, Cc = self.in_shape   # gradient w.r.t. the input pixels: the ordinary 4x4 data gradient
                 dx = cx.new(N, H, W, round_up(Cc, 8))
@@ -80,3 +114,8 @@ class FCDiscriminator(nn.Module):
 
     def forward(self, x):
         return call_module(self, lambda: FCDiscriminatorRun(self), (x,))
+
+    def forward_softmax0(self, logits):
+        """`self(F.softmax(logits, dim=0))` -- the call train_adapt.py:151,166,174 makes -- with the batch-axis
+        softmax (and its backward) fused into the input stage: the fp32 softmax tensor is never materialised."""
+        return call_module(self, lambda: FCDiscriminatorRun(self, softmax0=True), (logits,))

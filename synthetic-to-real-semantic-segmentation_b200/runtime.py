@@ -86,6 +86,8 @@ class ModuleFn(torch.autograd.Function):
             for i, d in enumerate(dins):
                 if d is None or not need[i]:
                     res.append(None)
+                elif isinstance(d, torch.Tensor):   # the run already produced the NCHW fp32 gradient
+                    res.append(d)
                 else:
                     res.append(to_nchw(cx, d, ctx.in_shapes[i][1]))
         ctx.run = None

@@ -22,6 +22,16 @@ from .utils.lr_scheduler import LR_Scheduler
 from .utils.metrics import Evaluator
 
 
+def _disc_on_softmax0(model_D, logits):
+    """model_D(F.softmax(logits, dim=0)) (train_adapt.py:151,166,174); the discriminator's fused input stage
+    when it covers the shape, the two separate calls otherwise."""
+    fused = getattr(model_D, "forward_softmax0", None)
+    if (fused is not None and logits.dim() == 4 and logits.shape[0] <= 8 and logits.shape[1] <= 64
+            and logits.shape[2] % 2 == 0 and logits.shape[3] % 2 == 0):
+        return fused(logits)
+    return model_D(softmax_dim0(logits))
+
+
 class AdaptStep(object):
     def __init__(self, model, model_D, lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False,
                  lr_scheduler='poly', epochs=200, iters_per_epoch=1000, class_weight=None, loss_type='ce'):
@@ -126,17 +136,17 @@ class AdaptStep(object):
         loss_seg = self.criterion(src_output, src_label)
         loss_seg.backward()
         tgt_output = model(tgt_image)
-        D_out = model_D(softmax_dim0(tgt_output))
+        D_out = _disc_on_softmax0(model_D, tgt_output)
         loss_adv = bce_with_logits(D_out, self.source_label)
         loss_adv.backward()
         # ---- train D (train_adapt.py:160-178)
         for p in model_D.parameters():
             p.requires_grad = True
         src_output = src_output.detach()
-        loss_D_src = bce_with_logits(model_D(softmax_dim0(src_output)), self.source_label)
+        loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
         loss_D_src.backward()
         tgt_output = tgt_output.detach()
-        loss_D_tgt = bce_with_logits(model_D(softmax_dim0(tgt_output)), self.target_label)
+        loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
         loss_D_tgt.backward()
         self.optimizer.all_reduce_grads()
         self.optimizer_D.all_reduce_grads()

@@ -262,3 +262,40 @@ def test_discriminator_and_domain_classifier_isolated(built_lib):
     assert e_o <= 1e-2 and e_p <= 1e-2
     assert max(errs.values()) <= 6e-2, {k: v for k, v in errs.items() if v > 6e-2}
     assert max(errs32.values()) <= 1.5e-1, {k: v for k, v in errs32.items() if v > 1.5e-1}
+
+
+def test_discriminator_fused_softmax_input(built_lib):
+    """FCDiscriminator.forward_softmax0(logits) == model_D(F.softmax(logits, dim=0)) (train_adapt.py:151,166,174):
+    output, gradient w.r.t. the logits (through the batch softmax) and parameter gradients against the fp32 oracle and
+    against the unfused module call."""
+    torch.manual_seed(18)
+    D = sub("modeling.discriminator").FCDiscriminator(19)
+    sD = leaf_sd(D)
+    sync_weights(D, sD)
+    D.cuda().train()
+    g = torch.Generator().manual_seed(19)
+    logits = torch.randn(4, 19, 64, 96, generator=g) * 2
+    go = bf(torch.randn(4, 1, 2, 3, generator=g))
+    xo = logits.clone().requires_grad_(True)
+    o_ref = O.discriminator_forward(sD, torch.softmax(xo, 0))
+    o_ref.backward(go)
+    xc = logits.cuda().requires_grad_(True)
+    o = D.forward_softmax0(xc)
+    o.backward(go.cuda())
+    fused = {k: q.grad.clone() for k, q in D.named_parameters()}
+    for q in D.parameters():
+        q.grad = None
+    xu = logits.cuda().requires_grad_(True)
+    ou = D(sub("functional").softmax_dim0(xu))
+    ou.backward(go.cuda())
+    torch.cuda.synchronize()
+    e_o, e_dx = rel(o.detach(), o_ref.detach()), rel(xc.grad, xo.grad)
+    errs = {k: rel(fused[k], sD[k].grad) for k in fused}
+    print("fused D fwd %.4f dlogits %.4f" % (e_o, e_dx), {k: round(v, 4) for k, v in errs.items()})
+    assert e_o <= 1e-2
+    assert e_dx <= 1e-1 and max(errs.values()) <= 1e-1, (e_dx, errs)
+    # fused and unfused paths differ only by where the softmax output is rounded to bf16
+    assert rel(o.detach(), ou.detach()) <= 5e-3
+    assert rel(xc.grad, xu.grad) <= 5e-2
+    for k, q in D.named_parameters():
+        assert rel(fused[k], q.grad) <= 5e-2, k

@@ -30,7 +30,7 @@ def cx(eng):
 
 
 def rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
@@ -509,3 +509,77 @@ def test_fused_optimizers_match_torch():
         ref.step()
     for p, q in zip(ps, qs):
         assert rel(p.detach(), q.detach()) < 1e-5
+
+
+def test_softmax0_to_padded_nhwc_and_back(eng):
+    """s2r_softmax0_nchw_to_nhwc_pad / _bwd: interior = (batch softmax of) the input in bf16, border pixels and pad
+    channels exactly zero; ragged strip widths, batch < 8 and > 8 (conversion only), backward against autograd."""
+    import ctypes as C
+    L = sub("_lib")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    for (B, Cc, H, W, sm) in ((8, 19, 6, 260, 1), (3, 19, 4, 130, 1), (1, 5, 2, 2, 1), (11, 19, 3, 40, 0), (2, 64, 2, 128, 0)):
+        Cp = (Cc + 7) // 8 * 8
+        x = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+        yp = torch.full((B, H + 2, W + 2, Cp), float('nan'), device="cuda", dtype=torch.bfloat16)
+        L.call("s2r_softmax0_nchw_to_nhwc_pad", C.c_void_p(x.data_ptr()), B, Cc, H, W, sm, C.c_void_p(yp.data_ptr()), Cp, st)
+        ref = (F.softmax(x, 0) if sm else x).permute(0, 2, 3, 1)
+        got = yp.float()
+        assert rel(got[:, 1:-1, 1:-1, :Cc], ref) < 3e-3          # bf16 rounding only
+        assert float(got[:, 1:-1, 1:-1, Cc:].abs().sum()) == 0.0 if Cp > Cc else True
+        border = got.clone()
+        border[:, 1:-1, 1:-1, :] = 0
+        assert not torch.isnan(got).any() and float(border.abs().sum()) == 0.0
+        # backward: gradient given in the padded layout (border holds garbage that must be ignored)
+        gp = torch.randn(B, H + 2, W + 2, Cp, device="cuda", generator=g).to(torch.bfloat16)
+        dx = torch.empty_like(x)
+        L.call("s2r_softmax0_nhwc_pad_bwd", C.c_void_p(x.data_ptr()) if sm else None, C.c_void_p(gp.data_ptr()), B, Cc, H, W, Cp,
+               sm, C.c_void_p(dx.data_ptr()), st)
+        gi = gp[:, 1:-1, 1:-1, :Cc].float().permute(0, 3, 1, 2)
+        if sm:
+            xr = x.clone().requires_grad_(True)
+            F.softmax(xr, 0).backward(gi)
+            assert rel(dx, xr.grad) < 1e-5
+        else:
+            assert rel(dx, gi) == 0.0
+    # the batch softmax needs the whole batch in one CTA
+    x = torch.randn(9, 3, 2, 2, device="cuda")
+    yp = torch.empty(9, 4, 4, 8, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(NotImplementedError):
+        L.call("s2r_softmax0_nchw_to_nhwc_pad", C.c_void_p(x.data_ptr()), 9, 3, 2, 2, 1, C.c_void_p(yp.data_ptr()), 8, st)
+
+
+def test_rowtap_conv4x4_s2(eng):
+    """Row-tap form of the 4x4 stride-2 pad-1 convolution on a zero-padded NHWC buffer (engine.rowtap_*): forward,
+    weight gradient and data gradient against F.conv2d and autograd on bf16-representable operands."""
+    import ctypes as C
+    L = sub("_lib")
+    cx = eng.Ctx(torch.device("cuda", 0), True)
+    g = torch.Generator().manual_seed(22)
+    for (N, Cin, Cout, H, W) in ((2, 19, 64, 16, 24), (1, 19, 64, 34, 258), (3, 8, 40, 6, 10)):
+        Cp = (Cin + 7) // 8 * 8
+        x = bf(torch.randn(N, Cin, H, W, generator=g))
+        w = torch.nn.Parameter(bf(torch.randn(Cout, Cin, 4, 4, generator=g) * 0.1).cuda())
+        b = torch.randn(Cout, generator=g)
+        go = bf(torch.randn(N, Cout, H // 2, W // 2, generator=g))
+        xr = x.clone().requires_grad_(True)
+        wr = w.detach().cpu().clone().requires_grad_(True)
+        yr = F.leaky_relu(F.conv2d(xr, wr, b, stride=2, padding=1), 0.2)
+        pre_grad = go * torch.where(yr > 0, 1.0, 0.2)      # gradient w.r.t. the conv output
+        F.conv2d(xr, wr, None, stride=2, padding=1).backward(pre_grad)
+        xp = eng.PadAct(torch.empty(N, H + 2, W + 2, Cp, device="cuda", dtype=torch.bfloat16), H, W, Cin)
+        L.call("s2r_softmax0_nchw_to_nhwc_pad", C.c_void_p(x.cuda().data_ptr()), N, Cin, H, W, 0, C.c_void_p(xp.ptr), Cp, cx.stream)
+        out = cx.new(N, H // 2, W // 2, eng.round_up(Cout, 8))
+        out.C = Cout
+        eng.rowtap_fwd(cx, xp, w, out, bias=b.cuda(), act=L.ACT_LEAKY, slope=0.2)
+        assert rel(out.t[..., :Cout].float().permute(0, 3, 1, 2), yr.detach()) < 4e-3
+        dy = eng.Act(pre_grad.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda())
+        dyf = dy.t.float().permute(0, 3, 1, 2).cpu()       # what the kernels see (bf16)
+        xr2 = x.clone().requires_grad_(True)
+        wr2 = w.detach().cpu().clone().requires_grad_(True)
+        F.conv2d(xr2, wr2, None, stride=2, padding=1).backward(dyf)
+        w.grad = None
+        eng.rowtap_wgrad(cx, xp, dy, w)
+        assert rel(w.grad, wr2.grad) < 2e-3
+        dxp = eng.rowtap_dgrad(cx, dy, w, H, W)
+        assert rel(dxp.t[:, 1:-1, 1:-1, :Cin].float().permute(0, 3, 1, 2), xr2.grad) < 4e-3
