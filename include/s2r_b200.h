@@ -118,6 +118,9 @@ int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, v
 /* w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]: a weight gradient accumulated in the mode-2 layout (fp32
  * [Cout][4][4*Cp]) added into the OIHW gradient of the 4x4 filter. */
 int s2r_rowtap_wgrad_scatter(const float* G, float* dw, int Cout, int Cin, s2r_stream_t stream);
+/* w.grad[co][ci][t] += G[t][co][ci] (row pitch Cp >= Cin): a multi-tap weight gradient accumulated tap-major by
+ * s2r_conv_wgrad (s_ci = 1: coalesced atomics) added into the OIHW gradient. */
+int s2r_wgrad_scatter_taps(const float* G, float* dw, int Cout, int Cin, int RS, int Cp, s2r_stream_t stream);
 /* The same for many filters in one launch.  A job packs the elements [begin, end) of one packed filter
  * (flattened [R*S][A_pad][B_pad] index); the table lives in device memory. */
 typedef struct s2r_pack_job {

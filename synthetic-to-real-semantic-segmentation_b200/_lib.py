@@ -60,6 +60,7 @@ PROTOTYPES = {
     "s2r_pack_weight": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
     "s2r_pack_weights_multi": [vp, i32, vp],
     "s2r_rowtap_wgrad_scatter": [vp, vp, i32, i32, vp],
+    "s2r_wgrad_scatter_taps": [vp, vp, i32, i32, i32, i32, vp],
     "s2r_softmax0_nchw_to_nhwc_pad": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_softmax0_nhwc_pad_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -488,6 +488,20 @@ __global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs)
   }
 }
 
+// w.grad[co][ci][t] += G[t][co][ci] (row pitch Cp): multi-tap weight gradients are accumulated tap-major, so that the
+// atomics of the gradient kernels cover 32 consecutive input channels (one 128-byte line) per instruction -- in the
+// OIHW tensor itself those 32 elements are R*S floats apart -- and are moved into the OIHW gradient here
+__global__ void wgrad_scatter_taps_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin, int RS,
+                                          int Cp) {
+  const long long total = (long long)Cout * Cin * RS;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % RS);
+    const long long q = i / RS;
+    const int ci = (int)(q % Cin), co = (int)(q / Cin);
+    dw[i] += G[((long long)t * Cout + co) * Cp + ci];
+  }
+}
+
 // w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]: the row-tap weight gradient (mode 2 layout, fp32) back to OIHW
 __global__ void rowtap_wgrad_scatter_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin, int Cp) {
   const int total = Cout * Cin * 16;
@@ -649,6 +663,14 @@ extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, 
   const long long total = (long long)nslices * A_pad * B_pad;
   S2R_CUDA_OK(s2r_launch(pack_weight_kernel, dim3(s2r_grid(total, 256, 8)), dim3(256), (size_t)0, (cudaStream_t)stream, w,
                          Cout, Cin, R * S, nslices, mode, (__nv_bfloat16*)packed, A_pad, B_pad));
+  return S2R_OK;
+}
+
+extern "C" int s2r_wgrad_scatter_taps(const float* G, float* dw, int Cout, int Cin, int RS, int Cp, s2r_stream_t stream) {
+  S2R_REQUIRE(G && dw && Cout >= 1 && Cin >= 1 && RS >= 1 && Cp >= Cin, S2R_ERR_SHAPE, "wgrad_scatter_taps: bad arguments");
+  const long long total = (long long)Cout * Cin * RS;
+  wgrad_scatter_taps_kernel<<<s2r_grid(total, 256, 4), 256, 0, (cudaStream_t)stream>>>(G, dw, Cout, Cin, RS, Cp);
+  S2R_LAUNCH_OK();
   return S2R_OK;
 }
 

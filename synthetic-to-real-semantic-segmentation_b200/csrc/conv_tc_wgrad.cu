@@ -415,7 +415,7 @@ int s2r_conv_wgrad_tc(const s2r_wgrad_args* a, cudaStream_t st) {
     const char* m = getenv("S2R_WG_MIN_CHUNKS");
     if (m) min_chunks = atoi(m);
   }
-  double ctas_per_sm = p.ntaps == 1 ? 1.0 : ((long long)nchunks * WG_BKP >= 100000 ? 2.0 : 0.5);
+  double ctas_per_sm = p.ntaps == 1 ? 1.0 : ((long long)nchunks * WG_BKP >= 50000 ? 4.0 : 0.5);   // re-swept with tap-major (coalesced) atomics
   if (knob_ctas > 0) ctas_per_sm = knob_ctas;
   int splits = s2r_div_up((long)(ctas_per_sm * s2r_sm_count()), tiles);
   const int max_splits = s2r_div_up(nchunks, min_chunks);

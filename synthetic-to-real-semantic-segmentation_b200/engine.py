@@ -403,6 +403,9 @@ def conv_dgrad(cx, dy, w, dx, stride=1, pad=0, dil=1, aux=None, aux_mode=L.AUX_N
     return dx
 
 
+WGRAD_TAP_MAJOR = os.environ.get("S2R_WGRAD_TAP_MAJOR", "1") != "0"
+
+
 def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
     """w.grad += conv weight gradient; bias handled by the caller.  grad_param: the parameter whose .grad
     receives the result when w is a reshaped view of it (patch GEMM)."""
@@ -415,6 +418,18 @@ def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
     a.Cin, a.Cout = Cin, Cout
     a.dy = dy.ptr
     a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
+    if R * S > 1 and WGRAD_TAP_MAJOR:
+        # tap-major fp32 scratch [R*S][Cout][Cp]: the kernel's atomics hit 32 consecutive input channels (one 128-byte
+        # line) per instruction instead of 32 elements R*S floats apart; one small pass adds it into the OIHW gradient
+        Cp = round_up(Cin, 32)
+        G = cx.f32(R * S * Cout * Cp)
+        for t in range(a.ntaps):
+            a.taps[t].wofs = a.taps[t].wofs * Cout * Cp
+        a.dweight = G.data_ptr()
+        a.s_co, a.s_ci = Cp, 1
+        L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+        L.call("s2r_wgrad_scatter_taps", _vp(G), _vp(g), Cout, Cin, R * S, Cp, cx.stream)
+        return
     a.dweight = g.data_ptr()
     a.s_co, a.s_ci = Cin * R * S, R * S
     L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
