@@ -174,7 +174,8 @@ class FeatureStep(object):
         self.d_optimizer = mk(d_params)
         self.d_inv_optimizer = _SharedGradOptimizer(mk, f_params, self.task_optimizer)
         self.task_loss = SegmentationLosses().build_loss('ce')
-        self.domain_loss = DomainLosses().build_loss()
+        self._domain_losses = DomainLosses()
+        self.domain_loss = self._domain_losses.build_loss()
         self.scheduler = LR_Scheduler(lr_scheduler, lr, epochs, iters_per_epoch)
 
     def _forward(self, image):
@@ -183,11 +184,58 @@ class FeatureStep(object):
         out = torch.nn.functional.interpolate(self.y(high, low), image.size()[2:], mode='bilinear', align_corners=True)
         return out, self.d(high)
 
+    def _optimizers(self):
+        return (self.task_optimizer, self.d_optimizer, self.d_inv_optimizer)
+
     def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
-        for o in (self.task_optimizer, self.d_optimizer, self.d_inv_optimizer):
+        for o in self._optimizers():
             self.scheduler(o, i, epoch)
+        return self._device_step(src_image, src_label, tgt_image)
+
+    def _advance(self, i, epoch):
+        """Host half of a captured step: learning rates / Adam bias corrections into the pinned buffers."""
+        for o in self._optimizers():
+            self.scheduler(o, i, epoch)
+        self.task_optimizer.advance()
+        self.d_optimizer.advance()
+        self.d_inv_optimizer.advance()
+
+    def capture(self, src_image, src_label, tgt_image, warmup=2):
+        """Capture the whole feature-adaptation step (two forwards through backbone + ASPP + decoder + domain
+        classifier, one backward, gradient all-reduce, the three optimizer kernels) into one CUDA graph -- the
+        counterpart of AdaptStep.capture.  The domain accuracy stays on the device (no .item() inside the step)."""
+        dev = src_image.device
+        self._static = tuple(torch.empty_like(t) for t in (src_image, src_label, tgt_image))
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            st.copy_(t)
+        self._domain_losses.device_acc = True
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for k in range(warmup):
+                self(*self._static, i=0, epoch=0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._advance(0, 0)
+        prepack_weights(None, build_only=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._device_step(*self._static, launch_only=True)
+        return self
+
+    def replay(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        self._advance(i, epoch)
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def _device_step(self, src_image, src_label, tgt_image, launch_only=False):
+        seed_counter(src_image.device).add_(1)
         self.task_optimizer.zero_grad()
         self.d_optimizer.zero_grad()
+        prepack_weights(torch.cuda.current_stream(src_image.device).cuda_stream)
         src_output, src_d_pred = self._forward(src_image)
         task_loss = self.task_loss(src_output, src_label)
         _, tgt_d_pred = self._forward(tgt_image)
@@ -197,9 +245,11 @@ class FeatureStep(object):
         loss.backward()
         self.task_optimizer.all_reduce_grads()
         self.d_optimizer.all_reduce_grads()
-        self.task_optimizer.step()
-        self.d_optimizer.step()
-        self.d_inv_optimizer.step()
+        for o in self._optimizers():
+            if launch_only:
+                o.launch()     # the host half (advance) ran before the capture / runs before every replay
+            else:
+                o.step()
         return {'task_loss': task_loss.detach(), 'd_loss': d_loss.detach(), 'd_inv_loss': d_inv_loss.detach(),
                 'd_acc': d_acc}
 
@@ -229,6 +279,23 @@ class _SharedGradOptimizer(object):
             inner._build_tables()
         self.inner.grad_scale = self.owner.grad_scale
         self.inner.step()
+
+    def _prepare(self):
+        if self.inner._tables is None:
+            inner = self.inner
+            inner.flat_grad = self.owner.flat_grad
+            lookup = {id(p): off for p, off, n in self.owner._views}
+            inner._views = [(p, lookup[id(p)], p.numel()) for p in self.params]
+            inner.state_bufs = [torch.zeros_like(self.owner.flat_grad) for _ in range(inner.n_state)]
+            inner._build_tables()
+        self.inner.grad_scale = self.owner.grad_scale
+
+    def advance(self):
+        self.inner.advance()
+
+    def launch(self):
+        self._prepare()
+        self.inner.launch()
 
     def zero_grad(self):
         pass

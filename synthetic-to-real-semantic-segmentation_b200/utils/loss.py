@@ -37,6 +37,7 @@ class DomainLosses(object):
     def __init__(self, batch_average=True, cuda=False):
         self.batch_average = batch_average
         self.cuda = cuda
+        self.device_acc = False   # True: the accuracy stays a device scalar (the reference returns .item(), loss.py:67)
 
     def build_loss(self):
         return self.DomainClassiferLoss
@@ -50,6 +51,8 @@ class DomainLosses(object):
             cross_entropy(tgt_logit, None, const_target=1, ignore_index=-100, stats_out=stats)
         hits = stats[0][2] + stats[1][2]
         acc = (hits / 2 / n / h / w).float()
+        if self.device_acc:      # CUDA-graph capture (steps.FeatureStep.capture): no host synchronisation
+            return loss, acc
         return loss, acc.item()
 
 

@@ -274,6 +274,46 @@ def test_feature_step_runs_and_matches_oracle_losses(built_lib):
         assert abs(got[0] - want[0]) <= (1e-2 if it == 0 else 2e-2) * want[0]
 
 
+def test_feature_step_cuda_graph_replay_matches_eager(built_lib):
+    """FeatureStep.capture/replay (whole train.py:163-216 step as one CUDA graph) against the eager step started
+    from the same weights on the same inputs: first-iteration losses agree to atomics-order noise."""
+    nn = torch.nn
+
+    def build():
+        torch.manual_seed(7)
+        bb = sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d)
+        aspp = sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d)
+        dec = sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d)
+        dc = sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d)
+        for mod in (bb, aspp, dec, dc):
+            mod._s2r_no_dropout = True
+            mod.cuda().train()
+        return sub("steps").FeatureStep(bb, aspp, dec, dc, lr=5e-4, optimizer='Adam', epochs=1, iters_per_epoch=10)
+
+    g = torch.Generator().manual_seed(12)
+    src = torch.randn(2, 3, 64, 96, generator=g).cuda()
+    tgt = torch.randn(2, 3, 64, 96, generator=g).cuda()
+    lab = torch.randint(0, 19, (2, 64, 96), generator=g).float().cuda()
+    keys = ('task_loss', 'd_loss', 'd_inv_loss', 'd_acc')
+    eager = build()
+    want = []
+    for it in range(3):
+        out = eager(src, lab, tgt, i=it, epoch=0)
+        want.append([float(out[k]) for k in keys])
+    graph = build()
+    graph.capture(src, lab, tgt, warmup=1)          # runs iteration 0 eagerly, then captures
+    got = []
+    for it in (1, 2):
+        out = graph.replay(src, lab, tgt, i=it, epoch=0)
+        got.append([float(out[k]) for k in keys])
+    print("feature graph", got, "eager", want[1:])
+    # iteration 1 starts from weights that went through one identical Adam step (same gradients up to the order of
+    # the atomics); later iterations drift chaotically, so only a loose band is asserted there
+    assert np.allclose(got[0][:3], want[1][:3], rtol=5e-2, atol=5e-3), (got[0], want[1])
+    assert np.allclose(got[1][:3], want[2][:3], rtol=5e-1, atol=5e-2), (got[1], want[2])
+    assert all(np.isfinite(v) for row in got for v in row)
+
+
 def test_val_step_confusion_matrix_matches_oracle_on_same_predictions(built_lib):
     m = make_deeplab().cuda().eval()
     val = sub("steps").ValStep(m, 19)

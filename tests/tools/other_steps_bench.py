@@ -31,6 +31,9 @@ fstep = sub("steps").FeatureStep(bb, aspp, dec, dc, lr=5e-4, epochs=1, iters_per
 src, lab, tgt = (t.to(dev) for t in bench.synth(1000, 8, 512, 1024))
 ms = timed(lambda i: fstep(src, lab, tgt, i=i), 5)
 print("feature step (train.py:163-216), B=8 512x1024: %.1f ms/step = %.1f img-pairs/s (eager)" % (ms, 8 / ms * 1e3))
+fstep.capture(src, lab, tgt, warmup=1)
+ms = timed(lambda i: fstep.replay(src, lab, tgt, i=i), 10)
+print("feature step, CUDA graph: %.1f ms/step = %.1f img-pairs/s" % (ms, 8 / ms * 1e3))
 
 G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False).to(dev).eval()
 vstep = sub("steps").ValStep(G, 19)
