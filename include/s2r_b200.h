@@ -229,6 +229,27 @@ int s2r_add_bf16(void* a, const void* b, int64_t n, s2r_stream_t stream);
 /* out[c] += (float)sums[c] */
 int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t stream);
 
+/* ------------------------------------------------------------------ device input stage (uint8 -> network input)
+ * The reference's per-sample CPU pipeline as byte kernels on images resident in HBM, bit-exact:
+ * dataloders/custom_transforms.py:59-71 (RandomHorizontalFlip), :108-147 (RandomScaleCrop: PIL resize, pad, crop),
+ * :17-56 (Normalize, ToTensor); dataloders/datasets/gtav2cityscapes.py:76-83 (encode_segmap).
+ * s2r_resize_bilinear_u8: one pass of PIL's BILINEAR resize (libImaging/Resample.c) over in u8 [N][H][W][C] along
+ *   axis 1 (columns -> out [N][H][out_size][C], flip != 0 mirrors the source columns first) or axis 0 (rows -> out
+ *   [N][out_size][W][C]); bounds int32 [out_size][2] = (first source index, count), kk int32 [out_size][ksize] =
+ *   22-bit fixed-point coefficients (device memory, computed as precompute_coeffs / normalize_coeffs_8bpc do).
+ * s2r_resize_nearest_u8: PIL's NEAREST resize of u8 [N][H][W] with source index tables (-1 = outside -> 0).
+ * s2r_input_stage_u8: crop window (x1, y1) of the flipped image padded on the right/bottom (image 0, label
+ *   fill_label) -> out_img fp32 [N][3][H][W] = ((u8/255 - mean)/std with numpy's float32/float64 casting) and out_label
+ *   fp32 [N][H][W] = lut[label] (lut u8 [256] in device memory, NULL = identity).  img or label may be NULL.
+ *   mean/std are HOST pointers to 3 doubles. */
+int s2r_resize_bilinear_u8(const uint8_t* in, int N, int H, int W, int C, int axis, int out_size, const int32_t* bounds,
+                           const int32_t* kk, int ksize, int flip, uint8_t* out, s2r_stream_t stream);
+int s2r_resize_nearest_u8(const uint8_t* in, int N, int H, int W, const int32_t* xtab, const int32_t* ytab, int OH,
+                          int OW, int flip, uint8_t* out, s2r_stream_t stream);
+int s2r_input_stage_u8(const uint8_t* img, const uint8_t* label, int N, int Hs, int Ws, int flip, int x1, int y1,
+                       const double* mean, const double* std_, const uint8_t* lut, int fill_label, float* out_img,
+                       float* out_label, int H, int W, s2r_stream_t stream);
+
 /* ------------------------------------------------------------------ losses
  * F.softmax(x, dim=0) at train_adapt.py:151,166,174; nn.CrossEntropyLoss at utils/loss.py:21-30,
  * 57-69; torch.nn.BCEWithLogitsLoss at train_adapt.py:75,153,168,176. */

@@ -1,0 +1,179 @@
+// Device input stage: the reference's per-sample CPU pipeline
+//   dataloders/datasets/gtav2cityscapes.py:76-83   encode_segmap (labelId -> trainId table)
+//   dataloders/custom_transforms.py:59-71          RandomHorizontalFlip
+//   dataloders/custom_transforms.py:108-147        RandomScaleCrop (PIL resize, pad right/bottom, crop window)
+//   dataloders/custom_transforms.py:17-56          Normalize + ToTensor
+// as byte kernels on uint8 HWC images already resident in HBM.  Everything is bit-exact against the reference:
+//   * PIL's BILINEAR resize is a two-pass fixed-point convolution (libImaging/Resample.c: int32 accumulation of
+//     uint8 * 22-bit coefficients starting at 1 << 21, arithmetic shift, clip, uint8 intermediate between the passes);
+//     the coefficient / bounds tables are computed by the host mirror exactly as precompute_coeffs does and passed in;
+//   * PIL's NEAREST resize copies in[ytab[y]][xtab[x]] with tables from incremental double additions (Geometry.c);
+//   * Normalize runs /255 in float32 and (-mean), (/std) in float64 rounded to float32 (numpy's casting of the tuple
+//     operands): a 3 x 256 table built per CTA with exactly those operations.
+// All kernels are HBM-bound byte movers: coalesced reads along the pixel row, coalesced fp32 plane writes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int PRECISION_BITS = 32 - 8 - 2;
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= PRECISION_BITS;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// out[n][y][xx][c] = clip8(2^21 + sum_x in[n][y][src(xmin + x)][c] * k[xx][x]); src mirrors the column when flip != 0
+// (the reference flips the PIL image before it is resized)
+__global__ void __launch_bounds__(kThreads)
+resize_h_kernel(const uint8_t* __restrict__ in, int N, int H, int W, int C, int OW, const int* __restrict__ bounds,
+                const int* __restrict__ kk, int ksize, int flip, uint8_t* __restrict__ out) {
+  const long long total = (long long)N * H * OW * C;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int c = (int)(i % C);
+    long long q = i / C;
+    const int xx = (int)(q % OW);
+    q /= OW;   // q = n * H + y
+    const int xmin = __ldg(bounds + 2 * xx), cnt = __ldg(bounds + 2 * xx + 1);
+    const uint8_t* row = in + q * (long long)W * C + c;
+    const int* k = kk + (long long)xx * ksize;
+    int acc = 1 << (PRECISION_BITS - 1);
+    for (int x = 0; x < cnt; ++x) {
+      const int sx = flip ? (W - 1 - (xmin + x)) : (xmin + x);
+      acc += (int)row[(long long)sx * C] * __ldg(k + x);
+    }
+    out[i] = clip8(acc);
+  }
+}
+
+// out[n][yy][x][c] = clip8(2^21 + sum_y in[n][ymin + y][x][c] * k[yy][y]); rows are contiguous: thread = byte of a row
+__global__ void __launch_bounds__(kThreads)
+resize_v_kernel(const uint8_t* __restrict__ in, int N, int H, int WC, int OH, const int* __restrict__ bounds,
+                const int* __restrict__ kk, int ksize, uint8_t* __restrict__ out) {
+  const long long total = (long long)N * OH * WC;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % WC);
+    long long q = i / WC;
+    const int yy = (int)(q % OH);
+    const int n = (int)(q / OH);
+    const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
+    const uint8_t* col = in + ((long long)n * H + ymin) * WC + x;
+    const int* k = kk + (long long)yy * ksize;
+    int acc = 1 << (PRECISION_BITS - 1);
+    for (int y = 0; y < cnt; ++y) acc += (int)col[(long long)y * WC] * __ldg(k + y);
+    out[i] = clip8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+resize_nearest_kernel(const uint8_t* __restrict__ in, int N, int H, int W, const int* __restrict__ xtab,
+                      const int* __restrict__ ytab, int OH, int OW, int flip, uint8_t* __restrict__ out) {
+  const long long total = (long long)N * OH * OW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % OW);
+    long long q = i / OW;
+    const int y = (int)(q % OH);
+    const int n = (int)(q / OH);
+    const int sx = __ldg(xtab + x), sy = __ldg(ytab + y);
+    uint8_t v = 0;   // ImagingScaleAffine clears the row first (fill = 1)
+    if (sx >= 0 && sy >= 0) v = in[((long long)n * H + sy) * W + (flip ? W - 1 - sx : sx)];
+    out[i] = v;
+  }
+}
+
+struct NormParams {
+  double mean[3], std[3];
+};
+
+// Crop window (x1, y1) of the (flipped, zero / fill padded) image -> normalised fp32 CHW planes and fp32 labels.
+// grid = (ceil(W / kThreads), H, N)
+__global__ void __launch_bounds__(kThreads)
+input_stage_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ label, int Hs, int Ws, int flip, int x1,
+                   int y1, NormParams np, const uint8_t* __restrict__ lut, int fill_label, float* __restrict__ out_img,
+                   float* __restrict__ out_label, int H, int W) {
+  __shared__ float tab[3][256];
+  __shared__ float ltab[256];
+  for (int i = threadIdx.x; i < 768; i += kThreads) {
+    const int c = i >> 8, u = i & 255;
+    const float v = __fdiv_rn((float)u, 255.0f);           // float32 array /= 255.0
+    const float a = (float)((double)v - np.mean[c]);        // float64 loop, result stored as float32
+    tab[c][u] = (float)((double)a / np.std[c]);
+  }
+  for (int i = threadIdx.x; i < 256; i += kThreads) ltab[i] = (float)(lut ? lut[i] : (uint8_t)i);
+  __syncthreads();
+  const int x = blockIdx.x * kThreads + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= W) return;
+  const int sy = y1 + y, sx0 = x1 + x;
+  const bool inside = sy < Hs && sx0 < Ws;                  // pad is on the right / bottom only (ImageOps.expand border)
+  const int sx = flip ? Ws - 1 - sx0 : sx0;
+  const long long plane = (long long)H * W;
+  const long long o = (long long)y * W + x;
+  if (img) {
+    uint8_t r = 0, g = 0, b = 0;                            // fill = 0 for the image, before normalisation
+    if (inside) {
+      const uint8_t* p = img + (((long long)n * Hs + sy) * Ws + sx) * 3;
+      r = p[0]; g = p[1]; b = p[2];
+    }
+    float* oi = out_img + (long long)n * 3 * plane + o;
+    oi[0] = tab[0][r];
+    oi[plane] = tab[1][g];
+    oi[2 * plane] = tab[2][b];
+  }
+  if (label) {
+    float v = (float)fill_label;
+    if (inside) v = ltab[label[((long long)n * Hs + sy) * Ws + sx]];
+    out_label[(long long)n * plane + o] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int s2r_resize_bilinear_u8(const uint8_t* in, int N, int H, int W, int C, int axis, int out_size,
+                                      const int32_t* bounds, const int32_t* kk, int ksize, int flip, uint8_t* out,
+                                      s2r_stream_t stream) {
+  S2R_REQUIRE(in && out && bounds && kk && N >= 1 && H >= 1 && W >= 1 && C >= 1 && out_size >= 1 && ksize >= 1,
+              S2R_ERR_SHAPE, "resize_bilinear_u8: bad arguments");
+  S2R_REQUIRE(axis == 0 || axis == 1, S2R_ERR_SHAPE, "resize_bilinear_u8: axis must be 0 (rows) or 1 (columns)");
+  S2R_REQUIRE(axis == 1 || !flip, S2R_ERR_UNSUPPORTED, "resize_bilinear_u8: the mirror is applied by the column pass");
+  if (axis == 1) {
+    const long long total = (long long)N * H * out_size * C;
+    resize_h_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(in, N, H, W, C, out_size, bounds, kk,
+                                                                                        ksize, flip, out);
+  } else {
+    const long long total = (long long)N * out_size * W * C;
+    resize_v_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(in, N, H, W * C, out_size, bounds, kk,
+                                                                                        ksize, out);
+  }
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_resize_nearest_u8(const uint8_t* in, int N, int H, int W, const int32_t* xtab, const int32_t* ytab,
+                                     int OH, int OW, int flip, uint8_t* out, s2r_stream_t stream) {
+  S2R_REQUIRE(in && out && xtab && ytab && N >= 1 && H >= 1 && W >= 1 && OH >= 1 && OW >= 1, S2R_ERR_SHAPE,
+              "resize_nearest_u8: bad arguments");
+  const long long total = (long long)N * OH * OW;
+  resize_nearest_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(in, N, H, W, xtab, ytab, OH, OW,
+                                                                                            flip, out);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_input_stage_u8(const uint8_t* img, const uint8_t* label, int N, int Hs, int Ws, int flip, int x1,
+                                  int y1, const double* mean, const double* std_, const uint8_t* lut, int fill_label,
+                                  float* out_img, float* out_label, int H, int W, s2r_stream_t stream) {
+  S2R_REQUIRE((img || label) && N >= 1 && Hs >= 1 && Ws >= 1 && H >= 1 && W >= 1 && x1 >= 0 && y1 >= 0, S2R_ERR_SHAPE,
+              "input_stage_u8: bad arguments");
+  S2R_REQUIRE((!img || (out_img && mean && std_)) && (!label || out_label), S2R_ERR_SHAPE, "input_stage_u8: null output");
+  S2R_REQUIRE(H <= 65535 && N <= 65535, S2R_ERR_SHAPE, "input_stage_u8: grid too large");
+  NormParams np;
+  for (int c = 0; c < 3; ++c) {
+    np.mean[c] = mean ? mean[c] : 0.0;
+    np.std[c] = std_ ? std_[c] : 1.0;
+  }
+  dim3 grid(s2r_div_up(W, kThreads), H, N);
+  input_stage_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img, label, Hs, Ws, flip, x1, y1, np, lut, fill_label,
+                                                                  out_img, out_label, H, W);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}

@@ -1,0 +1,233 @@
+"""The reference's sample pipeline on the device.
+
+`DeviceTrainTransform` is `TrainSet.transform_tr` (dataloders/datasets/gtav2cityscapes.py:66-74) -- RandomHorizontalFlip,
+RandomScaleCrop, Normalize, ToTensor from dataloders/custom_transforms.py -- plus `encode_segmap` (:76-83), applied to
+uint8 images / labelId maps that are already in HBM; `DeviceValTransform` is `ValSet.transform_val` (:139-146:
+FixedResize, Normalize, ToTensor).  The host computes what the reference computes on the host -- the random draws, in
+the reference's order, and Pillow's resampling tables -- and the bytes are moved by csrc/input_stage.cu.  Outputs are
+bit-identical to the reference's tensors (tests/golden/input_stage.npz).  RandomGaussianBlur (custom_transforms.py:
+91-105) is not reproduced: its draws are consumed, so the random stream stays aligned, and a sample on which it would
+fire is reported in `last_draws` (blur=True).
+
+No CPU path: tensors must be CUDA tensors and the C-ABI library must be present.
+"""
+import ctypes as C
+import math
+import random
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+MEAN = (0.485, 0.456, 0.406)
+STD = (0.229, 0.224, 0.225)
+VOID_CLASSES = [0, 1, 2, 3, 4, 5, 6, 9, 10, 14, 15, 16, 18, 29, 30, 34, -1]
+VALID_CLASSES = [7, 8, 11, 12, 13, 17, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 31, 32, 33]
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def segmap_lut(ignore_index=255):
+    """encode_segmap (gtav2cityscapes.py:76-83) as a byte table: the sequential relabelling applied to 0..255."""
+    m = np.arange(256, dtype=np.uint8)
+    for v in VOID_CLASSES:
+        if 0 <= v <= 255:
+            m[m == v] = ignore_index
+    for i, v in enumerate(VALID_CLASSES):
+        m[m == v] = i
+    return m
+
+
+def _bilinear_tables(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) for the bilinear filter, vectorised
+    over the output positions with the per-position operations kept in Pillow's order (double precision)."""
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    xx = np.arange(out_size, dtype=np.float64)
+    center = 0 + (xx + 0.5) * scale
+    ss = 1.0 / filterscale
+    xmin = np.maximum(np.trunc(center - support + 0.5).astype(np.int64), 0)
+    xmax = np.minimum(np.trunc(center + support + 0.5).astype(np.int64), in_size) - xmin
+    k = np.zeros((out_size, ksize), np.float64)
+    ww = np.zeros(out_size, np.float64)
+    for x in range(ksize):
+        arg = np.abs((x + xmin - center + 0.5) * ss)
+        w = np.where(arg < 1.0, 1.0 - arg, 0.0)
+        w = np.where(x < xmax, w, 0.0)
+        k[:, x] = w
+        ww = ww + w
+    nz = ww != 0.0
+    k[nz] = k[nz] / ww[nz][:, None]
+    kk = np.where(k < 0, np.trunc(-0.5 + k * (1 << _PRECISION_BITS)), np.trunc(0.5 + k * (1 << _PRECISION_BITS))).astype(np.int32)
+    bounds = np.stack([xmin, xmax], 1).astype(np.int32)
+    return bounds, kk, ksize
+
+
+def _nearest_table(in_size, out_size):
+    """Source index per output position of Pillow's ImagingScaleAffine: repeated double additions, truncation."""
+    a = float(in_size) / out_size
+    xo = a * 0.5
+    tab = np.empty(out_size, np.int32)
+    for x in range(out_size):
+        xin = -1 if xo < 0.0 else int(xo)
+        tab[x] = xin if 0 <= xin < in_size else -1
+        xo += a
+    return tab
+
+
+def _scale_size(w, h, short_size):
+    if h > w:
+        ow = short_size
+        oh = int(1.0 * h * ow / w)
+    else:
+        oh = short_size
+        ow = int(1.0 * w * oh / h)
+    return ow, oh
+
+
+class _Stage(object):
+    def __init__(self, mean, std):
+        self.mean = (C.c_double * 3)(*mean)
+        self.std = (C.c_double * 3)(*std)
+        self._tables = {}
+        self._lut = {}
+
+    @staticmethod
+    def _check(t, shape_len, what):
+        if t.device.type != "cuda":
+            raise L.S2RError("%s must be a CUDA tensor (got %s); there is no CPU path" % (what, t.device))
+        if t.dtype != torch.uint8 or t.dim() != shape_len or not t.is_contiguous():
+            raise ValueError("%s: expected a contiguous uint8 tensor with %d dimensions" % (what, shape_len))
+
+    def _dev(self, key, build, device):
+        ent = self._tables.get((key, device))
+        if ent is None:
+            ent = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(device) if isinstance(a, np.ndarray) else a for a in build())
+            if len(self._tables) > 64:
+                self._tables.clear()
+            self._tables[(key, device)] = ent
+        return ent
+
+    def lut(self, device):
+        t = self._lut.get(device)
+        if t is None:
+            t = torch.from_numpy(segmap_lut()).to(device)
+            self._lut[device] = t
+        return t
+
+    def resize_image(self, img, ow, oh, flip, st):
+        """PIL resize((ow, oh), BILINEAR) of the (mirrored) u8 [n,H,W,3] image; returns (tensor, flip still pending)."""
+        n, H, W, _ = img.shape
+        if W != ow:
+            b, kk, ks = self._dev(("bl", W, ow), lambda: _bilinear_tables(W, ow), img.device)
+            out = torch.empty((n, H, ow, 3), dtype=torch.uint8, device=img.device)
+            L.call("s2r_resize_bilinear_u8", img.data_ptr(), n, H, W, 3, 1, ow, b.data_ptr(), kk.data_ptr(), ks, int(flip),
+                   out.data_ptr(), st)
+            img, flip, W = out, False, ow
+        if H != oh:
+            b, kk, ks = self._dev(("bl", H, oh), lambda: _bilinear_tables(H, oh), img.device)
+            out = torch.empty((n, oh, W, 3), dtype=torch.uint8, device=img.device)
+            L.call("s2r_resize_bilinear_u8", img.data_ptr(), n, H, W, 3, 0, oh, b.data_ptr(), kk.data_ptr(), ks, 0,
+                   out.data_ptr(), st)
+            img = out
+        return img, flip
+
+    def resize_label(self, lab, ow, oh, flip, st):
+        n, H, W = lab.shape
+        if (W, H) == (ow, oh):
+            return lab, flip
+        (xt,) = self._dev(("nn", W, ow), lambda: (_nearest_table(W, ow),), lab.device)
+        (yt,) = self._dev(("nn", H, oh), lambda: (_nearest_table(H, oh),), lab.device)
+        out = torch.empty((n, oh, ow), dtype=torch.uint8, device=lab.device)
+        L.call("s2r_resize_nearest_u8", lab.data_ptr(), n, H, W, xt.data_ptr(), yt.data_ptr(), oh, ow, int(flip),
+               out.data_ptr(), st)
+        return out, False
+
+    def finish(self, img, lab, flip_img, flip_lab, x1, y1, out_img, out_lab, H, W, st, use_lut=True, fill=255):
+        n = img.shape[0] if img is not None else lab.shape[0]
+        if img is not None:
+            L.call("s2r_input_stage_u8", img.data_ptr(), None, n, img.shape[1], img.shape[2], int(flip_img), x1, y1,
+                   C.cast(self.mean, C.c_void_p), C.cast(self.std, C.c_void_p), None, 255, out_img.data_ptr(), None, H, W, st)
+        if lab is not None:
+            L.call("s2r_input_stage_u8", None, lab.data_ptr(), n, lab.shape[1], lab.shape[2], int(flip_lab), x1, y1, None, None,
+                   self.lut(lab.device).data_ptr() if use_lut else None, int(fill), None, out_lab.data_ptr(), H, W, st)
+
+
+class DeviceTrainTransform(object):
+    """transform_tr of the reference's TrainSet on a batch of equally sized uint8 device tensors:
+    src/tgt images [N,H,W,3] (RGB, HWC as PIL decodes them) and labelId maps [N,H,W] ->
+    {'src_image': f32 [N,3,crop,crop], 'tgt_image': ..., 'src_label': f32 [N,crop,crop]}.
+    Per sample the draws are made with python's `random` in the reference's order (flip, short edge, x1, y1, blur)
+    unless `draws` = [(flip, short_size, x1, y1), ...] is given."""
+
+    def __init__(self, base_size, crop_size, mean=MEAN, std=STD, fill=255):
+        self.base_size, self.crop_size, self.fill = base_size, crop_size, fill
+        self.stage = _Stage(mean, std)
+        self.last_draws = []
+
+    def draw(self, w, h):
+        flip = random.random() < 0.5                                           # custom_transforms.py:64
+        short = random.randint(int(self.base_size * 0.5), int(self.base_size * 2.0))   # :119
+        ow, oh = _scale_size(w, h, short)
+        pw = max(ow, self.crop_size) if short < self.crop_size else ow         # :130-135
+        ph = max(oh, self.crop_size) if short < self.crop_size else oh
+        x1 = random.randint(0, pw - self.crop_size)                            # :138-139
+        y1 = random.randint(0, ph - self.crop_size)
+        blur = random.random() < 0.5                                           # :96 (radius draws follow when it fires)
+        if blur:
+            random.random()
+            random.random()
+        return flip, short, x1, y1, blur
+
+    def __call__(self, src_image, tgt_image, src_label, draws=None):
+        st_ = self.stage
+        st_._check(src_image, 4, "src_image"); st_._check(tgt_image, 4, "tgt_image"); st_._check(src_label, 3, "src_label")
+        N, H, W, _ = src_image.shape
+        assert tgt_image.shape == src_image.shape and tuple(src_label.shape) == (N, H, W)
+        dev, cs = src_image.device, self.crop_size
+        out = {'src_image': torch.empty((N, 3, cs, cs), dtype=torch.float32, device=dev),
+               'tgt_image': torch.empty((N, 3, cs, cs), dtype=torch.float32, device=dev),
+               'src_label': torch.empty((N, cs, cs), dtype=torch.float32, device=dev)}
+        self.last_draws = []
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for n in range(N):
+                d = draws[n] if draws is not None else self.draw(W, H)
+                flip, short, x1, y1 = d[:4]
+                self.last_draws.append(tuple(d))
+                ow, oh = _scale_size(W, H, short)
+                if x1 + cs > max(ow, cs) or y1 + cs > max(oh, cs):
+                    raise ValueError("crop window (%d,%d)+%d outside the %dx%d scaled image" % (x1, y1, cs, ow, oh))
+                for key, t in (('src_image', src_image), ('tgt_image', tgt_image)):
+                    im, fl = st_.resize_image(t[n:n + 1], ow, oh, flip, st)
+                    st_.finish(im, None, fl, False, x1, y1, out[key][n:n + 1], None, cs, cs, st)
+                lb, fl = st_.resize_label(src_label[n:n + 1], ow, oh, flip, st)
+                st_.finish(None, lb, False, fl, x1, y1, None, out['src_label'][n:n + 1], cs, cs, st, fill=self.fill)
+        return out
+
+
+class DeviceValTransform(object):
+    """transform_val of the reference's ValSet (FixedResize((size, size)), Normalize, ToTensor) + encode_segmap on a
+    batch: images u8 [N,H,W,3], labelId maps u8 [N,H,W] -> {'image': f32 [N,3,size,size], 'label': f32 [N,size,size]}."""
+
+    def __init__(self, crop_size, mean=MEAN, std=STD):
+        self.size = crop_size
+        self.stage = _Stage(mean, std)
+
+    def __call__(self, image, label):
+        st_ = self.stage
+        st_._check(image, 4, "image"); st_._check(label, 3, "label")
+        N, H, W, _ = image.shape
+        assert tuple(label.shape) == (N, H, W)                               # custom_transforms_eval.py:159
+        dev, s = image.device, self.size
+        out = {'image': torch.empty((N, 3, s, s), dtype=torch.float32, device=dev),
+               'label': torch.empty((N, s, s), dtype=torch.float32, device=dev)}
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            im, _ = st_.resize_image(image, s, s, False, st)
+            # the reference relabels BEFORE the nearest resize; a per-pixel table commutes with a nearest-neighbour copy
+            lb, _ = st_.resize_label(label, s, s, False, st)
+            st_.finish(im, lb, False, False, 0, 0, out['image'], out['label'], s, s, st)
+        return out

@@ -583,3 +583,49 @@ def test_rowtap_conv4x4_s2(eng):
         assert rel(w.grad, wr2.grad) < 2e-3
         dxp = eng.rowtap_dgrad(cx, dy, w, H, W)
         assert rel(dxp.t[:, 1:-1, 1:-1, :Cin].float().permute(0, 3, 1, 2), xr2.grad) < 4e-3
+
+
+def test_device_input_stage_bit_exact_against_reference_fixture(eng):
+    """dataloders.device_transforms (flip, PIL-exact bilinear / nearest resize, pad, crop, Normalize, ToTensor,
+    encode_segmap) against the tensors the reference's TrainSet / ValSet produced for the same files and draws
+    (tests/golden/input_stage.npz): bit-exact."""
+    import numpy as np
+    from conftest import golden
+    dt = sub("dataloders.device_transforms")
+    fix = golden("input_stage")
+    for k in fix["cases"]:
+        flip, short, crop, x1, y1 = (int(v) for v in fix[k + "_draw"])
+        tr = dt.DeviceTrainTransform(base_size=1, crop_size=crop)
+        src = torch.from_numpy(fix[k + "_src"]).cuda()[None].contiguous()
+        tgt = torch.from_numpy(fix[k + "_tgt"]).cuda()[None].contiguous()
+        lab = torch.from_numpy(fix[k + "_lab"]).cuda()[None].contiguous()
+        out = tr(src, tgt, lab, draws=[(bool(flip), short, x1, y1)])
+        assert np.array_equal(out['src_image'][0].cpu().numpy(), fix[k + "_out_src"]), k
+        assert np.array_equal(out['tgt_image'][0].cpu().numpy(), fix[k + "_out_tgt"]), k
+        assert np.array_equal(out['src_label'][0].cpu().numpy(), fix[k + "_out_lab"]), k
+    s = int(fix["val_size"][0])
+    va = dt.DeviceValTransform(s)
+    img = torch.from_numpy(np.stack([fix["val_img"]] * 2)).cuda()
+    lab = torch.from_numpy(np.stack([fix["val_lab"]] * 2)).cuda()
+    out = va(img, lab)
+    for n in range(2):
+        assert np.array_equal(out['image'][n].cpu().numpy(), fix["val_out_img"])
+        assert np.array_equal(out['label'][n].cpu().numpy(), fix["val_out_lab"])
+    # the random stream: draws are made in the reference's order and reported
+    import random
+    random.seed(3)
+    tr = dt.DeviceTrainTransform(base_size=40, crop_size=32)
+    x = torch.randint(0, 256, (2, 40, 64, 3), dtype=torch.uint8, device="cuda")
+    lb = torch.randint(0, 34, (2, 40, 64), dtype=torch.uint8, device="cuda")
+    o = tr(x, x, lb)
+    assert o['src_image'].shape == (2, 3, 32, 32) and len(tr.last_draws) == 2 and torch.isfinite(o['src_image']).all()
+    # size-independent property at full resolution: labels map through the table, valid trainIds or 255 only
+    big = torch.randint(0, 256, (1, 1024, 2048), dtype=torch.uint8, device="cuda")
+    img = torch.randint(0, 256, (1, 1024, 2048, 3), dtype=torch.uint8, device="cuda")
+    tr = dt.DeviceTrainTransform(base_size=1024, crop_size=512)
+    o = tr(img, img, big, draws=[(True, 1024, 700, 300)])     # no resize: pure flip + crop + table
+    lut = torch.from_numpy(dt.segmap_lut()).cuda()
+    want = lut[big[0].flip(1)[300:812, 700:1212].long()].float()
+    assert torch.equal(o['src_label'][0], want)
+    with pytest.raises(sub("_lib").S2RError):
+        tr(img.cpu(), img.cpu(), big.cpu())

@@ -185,3 +185,27 @@ def test_adapt_step_two_iterations():
         if k.startswith('w:'):
             assert rel(g_sd[k[2:]].detach().reshape(-1)[:4096], fix[k]) < 1e-4, k
     assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
+
+
+def test_input_stage_oracle_and_host_tables_against_reference_fixture():
+    """oracle/input_stage.py (and the host-side resampling tables of the device input stage) against the outputs of
+    the reference's own TrainSet/ValSet pipeline stored by tests/golden/make_golden_input.py."""
+    from oracle import input_stage as OI
+    fix = golden("input_stage")
+    assert np.array_equal(OI.segmap_lut(), fix["lut"])
+    for k in fix["cases"]:
+        flip, short, crop, x1, y1 = (int(v) for v in fix[k + "_draw"])
+        img, lab = OI.train_sample(fix[k + "_src"], fix[k + "_lab"], flip, short, crop, x1, y1)
+        tgt, _ = OI.train_sample(fix[k + "_tgt"], fix[k + "_lab"], flip, short, crop, x1, y1)
+        assert np.array_equal(img, fix[k + "_out_src"]) and np.array_equal(tgt, fix[k + "_out_tgt"]), k
+        assert np.array_equal(lab, fix[k + "_out_lab"]), k
+    s = int(fix["val_size"][0])
+    assert np.array_equal(OI.normalize_to_tensor(OI.resize_bilinear(fix["val_img"], s, s)), fix["val_out_img"])
+    assert np.array_equal(OI.resize_nearest(OI.encode_segmap(fix["val_lab"]), s, s).astype(np.float32), fix["val_out_lab"])
+    dt = sub("dataloders.device_transforms")
+    assert np.array_equal(dt.segmap_lut(), fix["lut"])
+    for (i, o) in [(40, 64), (64, 40), (37, 111), (513, 257), (100, 7), (7, 100), (1024, 730)]:
+        b, kk, ks = dt._bilinear_tables(i, o)
+        b2, kk2 = OI.precompute_coeffs(i, o)
+        assert ks == kk2.shape[1] and np.array_equal(b, b2) and np.array_equal(kk, kk2), (i, o)
+        assert np.array_equal(dt._nearest_table(i, o), OI.nearest_table(i, o)), (i, o)
