@@ -229,6 +229,14 @@ int s2r_add_bf16(void* a, const void* b, int64_t n, s2r_stream_t stream);
 /* out[c] += (float)sums[c] */
 int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t stream);
 
+/* Prediction export: test_adapt.py:118-157 (imgsaver: trainId -> labelId image and palette image, NEAREST resize to the
+ * output size) fused with the host argmax at test_adapt.py:170-171.  logits fp32 [N][C][H][W]; xtab/ytab int32 source
+ * index per output column/row (PIL NEAREST tables, -1 = outside); id_table u8 [ntab], rgb_table u8 [ntab][3] (device);
+ * ids u8 [N][OH][OW] and/or rgb u8 [N][OH][OW][3]. */
+int s2r_export_prediction_nchw(const float* logits, int N, int C, int H, int W, const int32_t* xtab, const int32_t* ytab,
+                               int OH, int OW, const uint8_t* id_table, const uint8_t* rgb_table, int ntab, uint8_t* ids,
+                               uint8_t* rgb, s2r_stream_t stream);
+
 /* ------------------------------------------------------------------ device input stage (uint8 -> network input)
  * The reference's per-sample CPU pipeline as byte kernels on images resident in HBM, bit-exact:
  * dataloders/custom_transforms.py:59-71 (RandomHorizontalFlip), :108-147 (RandomScaleCrop: PIL resize, pad, crop),

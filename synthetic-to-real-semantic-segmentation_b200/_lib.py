@@ -61,6 +61,7 @@ PROTOTYPES = {
     "s2r_pack_weights_multi": [vp, i32, vp],
     "s2r_rowtap_wgrad_scatter": [vp, vp, i32, i32, vp],
     "s2r_resize_bilinear_u8": [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
+    "s2r_export_prediction_nchw": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
     "s2r_resize_nearest_u8": [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp],
     "s2r_input_stage_u8": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "s2r_wgrad_scatter_taps": [vp, vp, i32, i32, i32, i32, vp],

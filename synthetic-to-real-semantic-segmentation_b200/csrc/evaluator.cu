@@ -123,6 +123,43 @@ argmax_confusion_kernel(const float* __restrict__ logits, const float* __restric
   }
 }
 
+
+// Prediction export (test_adapt.py:118-157 / val_adapt.py:179-218 imgsaver + the host argmax at test_adapt.py:170-171):
+// argmax over the class planes at the source pixel PIL's NEAREST resize picks for every output position, then the two
+// byte tables (trainId -> labelId, trainId -> RGB).  ids u8 [N][OH][OW], rgb u8 [N][OH][OW][3]; ties -> lowest class
+// (np.argmax); values without a table entry stay 0 like the reference's zero-initialised images.
+__global__ void __launch_bounds__(kThreads)
+export_prediction_kernel(const float* __restrict__ logits, int N, int C, int H, int W, const int* __restrict__ xtab,
+                         const int* __restrict__ ytab, int OH, int OW, const unsigned char* __restrict__ id_table,
+                         const unsigned char* __restrict__ rgb_table, int ntab, unsigned char* __restrict__ ids,
+                         unsigned char* __restrict__ rgb) {
+  const long long total = (long long)N * OH * OW;
+  const long long plane = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % OW);
+    long long q = i / OW;
+    const int y = (int)(q % OH);
+    const int n = (int)(q / OH);
+    const int sx = __ldg(xtab + x), sy = __ldg(ytab + y);
+    unsigned char id = 0, r = 0, g = 0, b = 0;
+    if (sx >= 0 && sy >= 0) {
+      const float* p = logits + (long long)n * C * plane + (long long)sy * W + sx;
+      float best = __ldg(p);
+      int arg = 0;
+      for (int c = 1; c < C; ++c) {
+        const float v = __ldg(p + c * plane);
+        if (v > best) { best = v; arg = c; }   // strict: the first maximum wins, as in np.argmax
+      }
+      if (arg < ntab) {
+        id = id_table[arg];
+        r = rgb_table[3 * arg]; g = rgb_table[3 * arg + 1]; b = rgb_table[3 * arg + 2];
+      }
+    }
+    if (ids) ids[i] = id;
+    if (rgb) { rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b; }
+  }
+}
+
 }  // namespace
 
 extern "C" int s2r_confusion_matrix(const void* gt, int gt_is_i64, const int64_t* pred, int64_t n,
@@ -159,6 +196,19 @@ extern "C" int s2r_argmax_confusion_nchw(const float* logits, const float* gt, i
   argmax_confusion_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
       logits, gt, C, HW, npix, num_class > 0 ? num_class : 1, (unsigned long long*)counts,
       (long long*)pred_out);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_export_prediction_nchw(const float* logits, int N, int C, int H, int W, const int32_t* xtab,
+                                          const int32_t* ytab, int OH, int OW, const uint8_t* id_table,
+                                          const uint8_t* rgb_table, int ntab, uint8_t* ids, uint8_t* rgb,
+                                          s2r_stream_t stream) {
+  S2R_REQUIRE(logits && xtab && ytab && id_table && rgb_table && (ids || rgb), S2R_ERR_SHAPE, "export_prediction: null pointer");
+  S2R_REQUIRE(N >= 1 && C >= 1 && H >= 1 && W >= 1 && OH >= 1 && OW >= 1 && ntab >= 0, S2R_ERR_SHAPE, "export_prediction: bad shape");
+  const long long total = (long long)N * OH * OW;
+  export_prediction_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      logits, N, C, H, W, xtab, ytab, OH, OW, id_table, rgb_table, ntab, ids, rgb);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -629,3 +629,47 @@ def test_device_input_stage_bit_exact_against_reference_fixture(eng):
     assert torch.equal(o['src_label'][0], want)
     with pytest.raises(sub("_lib").S2RError):
         tr(img.cpu(), img.cpu(), big.cpu())
+
+
+def test_prediction_export_and_validation_report(eng):
+    """utils.report: fused argmax + labelId / palette tables + PIL NEAREST resize against the numpy restatement of
+    test_adapt.py:118-157 (bit-exact, ties included) and against Pillow's own resize; report text of val_adapt.py:159-166."""
+    import numpy as np
+    from oracle import report as OR
+    rep = sub("utils.report")
+    g = torch.Generator().manual_seed(31)
+    logits = torch.randn(2, 19, 64, 96, generator=g)
+    logits[:, 3] = logits[:, 7]                       # ties: the lower class index must win
+    logits[0, :, :8] = 0.0                            # all-equal pixels -> class 0
+    ex = rep.PredictionExporter(out_size=(150, 80))
+    ids, rgb = ex(logits.cuda())
+    for n in range(2):
+        want_ids, want_rgb = OR.imgsaver_arrays(logits[n].numpy(), 150, 80)
+        assert np.array_equal(ids[n].cpu().numpy(), want_ids) and np.array_equal(rgb[n].cpu().numpy(), want_rgb)
+    try:
+        from PIL import Image
+        im1 = np.uint8(np.argmax(logits[1].numpy(), 0))
+        lab = np.zeros_like(im1)
+        for c in range(19):
+            lab[im1 == c] = OR.VALID_CLASSES[c]
+        assert np.array_equal(np.array(Image.fromarray(lab, mode='L').resize((150, 80), Image.NEAREST)), ids[1].cpu().numpy())
+    except ImportError:
+        pass
+    # full-size case through the default (1280, 640) output: every value is a valid labelId / palette colour
+    big = torch.randn(1, 19, 512, 512, generator=g).cuda()
+    ids, rgb = rep.PredictionExporter()(big)
+    assert ids.shape == (1, 640, 1280) and set(ids.unique().tolist()) <= set(OR.VALID_CLASSES)
+    pal = {tuple(p) for p in OR.PALETTE}
+    assert {tuple(v) for v in rgb.reshape(-1, 3).unique(dim=0).tolist()} <= pal
+    # report text
+    ev = sub("utils.metrics").Evaluator(19)
+    gt = torch.randint(0, 19, (2, 33, 47), generator=g).float()
+    pr = torch.randint(0, 19, (2, 33, 47), generator=g)
+    ev.add_batch(gt.cuda(), pr.cuda())
+    text = rep.validation_report(ev, 3, 2, 1.23456)
+    lines = text.split('\n')
+    mIoU, IoU = ev.Mean_Intersection_over_Union()
+    assert lines[0] == 'Validation:' and lines[1] == '[Epoch: 3, numImages:     2]' and lines[3] == 'Loss: 1.235'
+    assert lines[2] == "Acc:{}, Acc_class:{}, mIoU:{}, fwIoU: {}".format(ev.Pixel_Accuracy(), ev.Pixel_Accuracy_Class(), mIoU,
+                                                                        ev.Frequency_Weighted_Intersection_over_Union())
+    assert lines[6] == '\troad: \t\t' + str(IoU[0]) and lines[7] == '\tsidewalk: \t' + str(IoU[1]) and len(lines) == 6 + 19 + 1

@@ -1,0 +1,61 @@
+"""Device input stage (dataloders.device_transforms) on GTA5 -> Cityscapes shaped uint8 batches: time per batch of 8
+source/target pairs (1052x1914 RGB + labelIds -> 3x512x512 crops, random scale in [0.5, 2] x base 512) with CUDA
+events, next to the same pipeline on the host through Pillow + numpy (what the reference's DataLoader workers run,
+custom_transforms.py:59-147,17-56) on one core.  GPU box:  python tests/tools/input_stage_bench.py"""
+import os, sys, time, random
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import sub
+dt = sub("dataloders.device_transforms")
+dev = torch.device("cuda", 0)
+N, H, W, BASE, CROP = 8, 1052, 1914, 512, 512
+g = torch.Generator().manual_seed(0)
+src = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, generator=g)
+tgt = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, generator=g)
+lab = torch.randint(0, 35, (N, H, W), dtype=torch.uint8, generator=g)
+d_src, d_tgt, d_lab = src.to(dev), tgt.to(dev), lab.to(dev)
+tr = dt.DeviceTrainTransform(BASE, CROP)
+random.seed(0)
+draws = [tr.draw(W, H)[:4] for _ in range(N)]
+for _ in range(2):
+    out = tr(d_src, d_tgt, d_lab, draws=draws)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    out = tr(d_src, d_tgt, d_lab, draws=draws)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+in_bytes = N * H * W * 7
+print("device input stage: %.2f ms per batch of %d pairs (%.0f pairs/s), %.1f GB/s of source bytes; draws %s"
+      % (ms, N, N / ms * 1e3, in_bytes / ms / 1e6, draws[:2]))
+
+# the same arithmetic on the host through Pillow (one core), sample 0..N-1
+from PIL import Image, ImageOps
+mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+lut = dt.segmap_lut()
+t0 = time.time()
+ok = True
+for n in range(N):
+    flip, short, x1, y1 = draws[n]
+    ims = [Image.fromarray(src[n].numpy()), Image.fromarray(tgt[n].numpy()), Image.fromarray(lut[lab[n].numpy()])]
+    if flip:
+        ims = [im.transpose(Image.FLIP_LEFT_RIGHT) for im in ims]
+    ow, oh = dt._scale_size(W, H, short)
+    ims = [ims[0].resize((ow, oh), Image.BILINEAR), ims[1].resize((ow, oh), Image.BILINEAR), ims[2].resize((ow, oh), Image.NEAREST)]
+    if short < CROP:
+        padh, padw = (CROP - oh if oh < CROP else 0), (CROP - ow if ow < CROP else 0)
+        ims = [ImageOps.expand(ims[0], border=(0, 0, padw, padh), fill=0), ImageOps.expand(ims[1], border=(0, 0, padw, padh), fill=0),
+               ImageOps.expand(ims[2], border=(0, 0, padw, padh), fill=255)]
+    ims = [im.crop((x1, y1, x1 + CROP, y1 + CROP)) for im in ims]
+    res = []
+    for im in ims[:2]:
+        a = np.array(im).astype(np.float32); a /= 255.0; a -= mean; a /= std
+        res.append(a.transpose((2, 0, 1)))
+    m = np.array(ims[2]).astype(np.float32)
+    ok &= np.array_equal(res[0], out['src_image'][n].cpu().numpy()) and np.array_equal(res[1], out['tgt_image'][n].cpu().numpy())
+    ok &= np.array_equal(m, out['src_label'][n].cpu().numpy())
+cpu_ms = (time.time() - t0) * 1e3
+print("Pillow + numpy on 1 host core: %.1f ms per batch (includes the comparison); device output bit-identical: %s" % (cpu_ms, ok))
