@@ -113,16 +113,62 @@ class _FusedBase(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # state names in torch.optim's state_dict (torch.optim.SGD: 'momentum_buffer'; Adam: 'exp_avg', 'exp_avg_sq')
+    state_names = ('momentum_buffer',)
+
     def state_dict(self):
-        return {'steps': self.steps, 'state': [b.clone() for b in self.state_bufs],
-                'param_groups': [{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups]}
+        """torch.optim-format state dict -- what train_adapt.py:206 / train.py:248-251 store under 'optimizer' --
+        so checkpoints move between the reference's optimizers and these: {'state': {index: {name: tensor, ...}},
+        'param_groups': [{..hyper-parameters.., 'params': [indices]}]} with parameters numbered in group order."""
+        state, groups, idx = {}, [], 0
+        lookup = {id(p): (off, n) for p, off, n in self._views}
+        for g in self.param_groups:
+            ids = []
+            for p in g['params']:
+                off, n = lookup[id(p)]
+                if self.steps > 0:
+                    ent = {name: self.state_bufs[k][off:off + n].view_as(p).clone() for k, name in enumerate(self.state_names)}
+                    if 'exp_avg' in ent:
+                        ent['step'] = torch.tensor(float(self.steps))
+                    state[idx] = ent
+                ids.append(idx)
+                idx += 1
+            pg = {k: v for k, v in g.items() if k != 'params'}
+            pg['params'] = ids
+            groups.append(pg)
+        return {'state': state, 'param_groups': groups}
 
     def load_state_dict(self, sd):
-        self.steps = sd['steps']
-        for b, s in zip(self.state_bufs, sd['state']):
-            b.copy_(s)
-        for g, s in zip(self.param_groups, sd['param_groups']):
-            g.update(s)
+        """Accepts torch.optim-format dicts (reference checkpoints) and the flat format of earlier versions."""
+        if isinstance(sd.get('state'), (list, tuple)):      # {'steps', 'state': [flat buffers], 'param_groups'}
+            self.steps = sd['steps']
+            for b, s_ in zip(self.state_bufs, sd['state']):
+                b.copy_(s_)
+            for g, s_ in zip(self.param_groups, sd['param_groups']):
+                g.update({k: v for k, v in s_.items() if k != 'params'})
+            return
+        if len(sd['param_groups']) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        lookup = {id(p): (off, n) for p, off, n in self._views}
+        idx, steps = 0, 0
+        for g, sg in zip(self.param_groups, sd['param_groups']):
+            if len(sg['params']) != len(g['params']):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            g.update({k: v for k, v in sg.items() if k != 'params'})
+            for p, key in zip(g['params'], sg['params']):
+                ent = sd['state'].get(key)
+                off, n = lookup[id(p)]
+                for k, name in enumerate(self.state_names):
+                    if ent is not None and ent.get(name) is not None:
+                        self.state_bufs[k][off:off + n].copy_(ent[name].reshape(-1))
+                    else:
+                        self.state_bufs[k][off:off + n].zero_()
+                if ent is not None:
+                    steps = max(steps, int(float(ent['step'])) if 'step' in ent else 1)
+                idx += 1
+        # SGD: the first step initialises the momentum buffer with the gradient (torch.optim.SGD); a loaded buffer
+        # means that step is behind us.  Adam: the bias corrections continue from the stored step count.
+        self.steps = steps
 
 
 class FusedSGD(_FusedBase):
@@ -167,6 +213,7 @@ class FusedSGD(_FusedBase):
 class FusedAdam(_FusedBase):
     """torch.optim.Adam(params, lr, betas, eps, weight_decay) -- train_adapt.py:60, train.py:77-80."""
     n_state = 2
+    state_names = ('exp_avg', 'exp_avg_sq')
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))

@@ -293,6 +293,14 @@ class _SharedGradOptimizer(object):
     def advance(self):
         self.inner.advance()
 
+    def state_dict(self):
+        self._prepare()
+        return self.inner.state_dict()
+
+    def load_state_dict(self, sd):
+        self._prepare()
+        self.inner.load_state_dict(sd)
+
     def launch(self):
         self._prepare()
         self.inner.launch()

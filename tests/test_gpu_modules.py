@@ -347,3 +347,78 @@ def test_batchnorm_needs_more_than_one_value(built_lib):
     aspp = sub("modeling.assp").ASPP('mobilenet', 16, torch.nn.BatchNorm2d).cuda().train()
     with pytest.raises(ValueError):
         aspp(torch.randn(1, 320, 8, 8).cuda())
+
+
+def test_checkpoints_in_the_reference_layouts(built_lib, tmp_path):
+    """utils.checkpoint: a file in train_adapt.py's layout written with torch.optim.SGD state (what the reference
+    stores) drives the fused optimizer, and the fused optimizer's own state loads into torch.optim -- after one more
+    identical step both hold the same weights and momentum; train.py's four-model layout round-trips."""
+    ck = sub("utils.checkpoint")
+    optim = sub("optim")
+    torch.manual_seed(3)
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False).cuda().train()
+    groups = lambda m: [{'params': list(m.get_1x_lr_params()), 'lr': 5e-4}, {'params': list(m.get_10x_lr_params()), 'lr': 5e-3}]  # noqa: E731
+    # a "reference" run: torch.optim.SGD on a clone of the parameters, two steps with synthetic gradients
+    import copy
+    R = copy.deepcopy(G)
+    ropt = torch.optim.SGD(groups(R), lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    grads = [[torch.randn(p.shape, device="cuda", generator=gen) * 1e-2 for g in ropt.param_groups for p in g['params']] for _ in range(3)]
+
+    def set_grads(opt, gs):
+        for p, g in zip([p for grp in opt.param_groups for p in grp['params']], gs):
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+
+    for it in range(2):
+        set_grads(ropt, grads[it])
+        ropt.step()
+    path = str(tmp_path / "checkpoint.pth.tar")
+    torch.save({'epoch': 7, 'state_dict': {'module.' + k: v for k, v in R.state_dict().items()}, 'optimizer': ropt.state_dict(),
+                'best_pred': 0.25}, path)
+    fopt = optim.FusedSGD(groups(G), lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False)
+    epoch, best = ck.load_adapt(path, G, fopt)
+    assert (epoch, best) == (7, 0.25)
+    for k, v in R.state_dict().items():
+        assert torch.equal(G.state_dict()[k], v), k
+    # third step on both sides
+    set_grads(ropt, grads[2]); ropt.step()
+    set_grads(fopt, grads[2]); fopt.step()
+    torch.cuda.synchronize()
+    for (k, a), b in zip(G.named_parameters(), R.parameters()):
+        assert rel(a.detach(), b.detach()) <= 1e-6, k
+    # and back: the fused optimizer's state in torch.optim's format
+    st = ck.adapt_state(G, fopt, 7, 0.3)
+    assert set(st) == {'epoch', 'state_dict', 'optimizer', 'best_pred'} and st['epoch'] == 8
+    ropt2 = torch.optim.SGD(groups(R), lr=5e-4, momentum=0.9, weight_decay=5e-4)
+    ropt2.load_state_dict(st['optimizer'])
+    for i, p in enumerate([p for grp in ropt.param_groups for p in grp['params']]):
+        assert rel(ropt2.state[p]['momentum_buffer'], ropt.state[p]['momentum_buffer']) <= 1e-6, i
+    assert list(st['state_dict'].keys()) == list(R.state_dict().keys())
+    # train.py's layout with Adam state
+    nn = torch.nn
+    bb = sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d).cuda().train()
+    aspp = sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d).cuda().train()
+    dec = sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d).cuda().train()
+    dc = sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d).cuda().train()
+    fs = sub("steps").FeatureStep(bb, aspp, dec, dc, lr=5e-4, optimizer='Adam', epochs=1, iters_per_epoch=10)
+    g = torch.Generator().manual_seed(5)
+    src, tgt = torch.randn(2, 3, 64, 96, generator=g).cuda(), torch.randn(2, 3, 64, 96, generator=g).cuda()
+    lab = torch.randint(0, 19, (2, 64, 96), generator=g).float().cuda()
+    fs(src, lab, tgt, i=0, epoch=0)
+    state = ck.feature_state(bb, aspp, dec, dc, fs.task_optimizer, fs.d_optimizer, fs.d_inv_optimizer, 0, 0.1)
+    assert {'backbone_model_state_dict', 'assp_model_state_dict', 'y_model_state_dict', 'd_model_state_dict', 'task_optimizer',
+            'd_optimizer', 'd_inv_optimizer', 'c_optimizer', 'best_pred', 'epoch'} == set(state)
+    torch.save(state, str(tmp_path / "f.pth.tar"))
+    tadam = torch.optim.Adam(list(dc.parameters()), lr=5e-4)
+    tadam.load_state_dict(state['d_optimizer'])                      # torch accepts the fused Adam's state
+    assert float(tadam.state[next(iter(dc.parameters()))]['step']) == 1.0
+    w0 = dc.DC_adnn1[0].weight.detach().clone()
+    fs(src, lab, tgt, i=1, epoch=0)
+    assert not torch.equal(dc.DC_adnn1[0].weight.detach(), w0)
+    e, b = ck.load_feature(str(tmp_path / "f.pth.tar"), bb, aspp, dec, dc, fs.task_optimizer, fs.d_optimizer, fs.d_inv_optimizer)
+    assert (e, b) == (1, 0.1) and torch.equal(dc.DC_adnn1[0].weight.detach(), w0) and fs.d_optimizer.steps == 1
+    with pytest.raises(RuntimeError):
+        ck.load_adapt(str(tmp_path / "missing.pth.tar"), G)
