@@ -209,8 +209,9 @@ def dominant_kernel_roofline(torch, batch, h, w, peaks):
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = flops / t / 1e12
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 8, 512x1024 from the committed
-    # ncu --set full capture (profiles/r1m_conv_tc_decoder_ncu.txt: 135.7 MB + 115.8 MB; algorithmic 293 MB)
-    traffic = 251.5e6 if (batch, h, w) == (8, 512, 1024) else None
+    # ncu --set full capture (profiles/r2a_conv_tc_decoder_ncu.txt: 161.1 MB read + 95.2 MB written -- part of the
+    # 134 MB output is still in the 126 MB L2 when the kernel ends; algorithmic 159 + 134 = 293 MB)
+    traffic = 256.3e6 if (batch, h, w) == (8, 512, 1024) else None
     return {"kernel": "tap-GEMM conv fwd 3x3 304->256 (decoder.last_conv.0)", "bound": "tensor", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": peaks.get("_source", "fallback"), "launch_ms": t * 1e3}

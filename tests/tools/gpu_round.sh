@@ -16,6 +16,6 @@ if [ -z "$2" ]; then
   echo "launch list rc=$?"
   CMD2="python tests/tools/conv_bench.py dec"
   S2R_BENCH_EAGER=1 $CMD2 > gpurun_out/plain2_$TAG.log 2>&1 &&
-  S2R_BENCH_EAGER=1 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 3 -c 2 -o gpurun_out/prof_conv_tc_$TAG $CMD2 > gpurun_out/ncu2_$TAG.log 2>&1
+  S2R_BENCH_EAGER=1 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 2 -o gpurun_out/prof_conv_tc_$TAG $CMD2 > gpurun_out/ncu2_$TAG.log 2>&1
   echo "full capture rc=$?"
 fi
