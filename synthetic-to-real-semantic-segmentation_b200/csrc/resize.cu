@@ -304,6 +304,99 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
     for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(acc[r]);
 }
 
+// Vertical-first variant of the row-staged kernel (used when the rows can be read as float4): the kernel above reduces
+// every FINE row horizontally (10 bounds-checked shared-memory taps per fine row and coarse column: 179 M warp
+// instructions for the final x4 gradient, issue-bound at 1.3 TB/s).  Here a thread first reduces its four fine columns
+// VERTICALLY in registers while the rows stream in (one LDG.128 + 8 FMA per fine row, all loads of an interval in
+// flight together), the UR vertically reduced rows go to shared memory once, and the horizontal 10-tap reduction runs
+// once per COARSE row.  Same sums, different order.
+__global__ void __launch_bounds__(kThreads, 3)   // <= 85 registers: without the bound ptxas hoists all 54 row loads (255 registers, spills)
+up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
+                            int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+  extern __shared__ __align__(16) float rowbuf[];   // [UR][seg_max], skewed like above
+  const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
+  const int c = blockIdx.y, n = blockIdx.z;
+  const int ih0 = ihb * UR;
+  const int iw = cb * kThreads + threadIdx.x;
+  const bool col_ok = iw < Wi;
+  __nv_bfloat16* out = dx + (((long long)n * Hi + ih0) * Wi + (col_ok ? iw : 0)) * dxpitch + c;
+  if (c >= C) {   // padding channels of the NHWC buffer stay zero
+    if (col_ok)
+      for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(0.f);
+    return;
+  }
+  int seg_lo, seg_hi, t0, t1;
+  cand_range(cb * kThreads, sw, Wo, &seg_lo, &t0);
+  cand_range(min(cb * kThreads + kThreads - 1, Wi - 1), sw, Wo, &t1, &seg_hi);
+  seg_lo &= ~3;
+  const int seg_len = seg_hi - seg_lo + 1;
+  const int ngroups = (seg_len + 3) >> 2;
+  // interval k = 0 .. UR belongs to coarse row ih = ih0 - 1 + k: its fine rows [fa(ih), fa(ih + 1)) weigh w0 on row ih and
+  // w1 on row ih + 1, so output row k - 1 = hi(interval k - 1) + lo(interval k) and is complete -- and written to shared
+  // memory -- as soon as interval k has been reduced: three float4 accumulators instead of UR of them
+  const float* plane = dy + ((long long)n * C + c) * Ho * Wo + seg_lo;
+  for (int g0 = 0; g0 < ngroups; g0 += kThreads) {
+    const int g = g0 + threadIdx.x;
+    const bool gv = g < ngroups;
+    float ph[4] = {0.f, 0.f, 0.f, 0.f};
+    int ra = ih0 - 1 <= 0 ? 0 : first_fine_row(ih0 - 1, sh, Hi, Ho);
+#pragma unroll 1
+    for (int k = 0; k <= UR; ++k) {
+      const int ih = ih0 - 1 + k;
+      const int rb = ih + 1 <= 0 ? 0 : (ih + 1 > Hi - 1 ? Ho : first_fine_row(ih + 1, sh, Hi, Ho));
+      float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r0 = ra; r0 < rb; r0 += URB) {
+        float4 vv[URB];
+#pragma unroll
+        for (int rr = 0; rr < URB; ++rr) {
+          vv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gv && r0 + rr < rb) vv[rr] = __ldg(reinterpret_cast<const float4*>(plane + (long long)(r0 + rr) * Wo) + g);
+        }
+#pragma unroll
+        for (int rr = 0; rr < URB; ++rr) {
+          const float4 v = vv[rr];
+          const Lerp ly = lerp_src(r0 + rr, sh, Hi);
+          lo[0] = fmaf(ly.w0, v.x, lo[0]); lo[1] = fmaf(ly.w0, v.y, lo[1]); lo[2] = fmaf(ly.w0, v.z, lo[2]); lo[3] = fmaf(ly.w0, v.w, lo[3]);
+          hi[0] = fmaf(ly.w1, v.x, hi[0]); hi[1] = fmaf(ly.w1, v.y, hi[1]); hi[2] = fmaf(ly.w1, v.z, hi[2]); hi[3] = fmaf(ly.w1, v.w, hi[3]);
+        }
+      }
+      const bool clamped = ih + 1 > Hi - 1;          // i1 is clamped to the last row: w1 stays on row ih
+      if (k >= 1 && gv) {
+        float* d = rowbuf + (k - 1) * seg_max + 4 * g + ((4 * g) >> 5);   // the four columns share one skew offset
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = ph[e] + lo[e] + (clamped ? hi[e] : 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ph[e] = clamped ? 0.f : hi[e];
+      ra = rb;
+    }
+  }
+  __syncthreads();
+  if (!col_ok) return;
+  int wlo, whi;
+  cand_range(iw, sw, Wo, &wlo, &whi);
+  while (wlo < whi && lerp_weight(lerp_src(wlo, sw, Wi), iw) == 0.f) ++wlo;
+  float wx[UKX];
+  int jj[UKX];
+#pragma unroll
+  for (int k = 0; k < UKX; ++k) {
+    int j = wlo + k - seg_lo;
+    const bool ok = wlo + k <= whi && j >= 0 && j < seg_len;
+    wx[k] = ok ? lerp_weight(lerp_src(wlo + k, sw, Wi), iw) : 0.f;
+    if (!ok) j = 0;
+    jj[k] = j + (j >> 5);
+  }
+#pragma unroll
+  for (int r = 0; r < UR; ++r) {
+    if (ih0 + r >= Hi) break;
+    const float* row = rowbuf + r * seg_max;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < UKX; ++k) v = fmaf(wx[k], row[jj[k]], v);
+    out[(long long)r * Wi * dxpitch] = __float2bfloat16(v);
+  }
+}
+
 // ------------------------------------------------------------ global average pool
 // one CTA per (image, 64-channel slab); y[n][c] = mean_p x[n][p][c]
 __global__ void __launch_bounds__(kThreads)
@@ -506,8 +599,18 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
     int seg_max = (int)((kThreads + 2) / sw) + 16;
     seg_max = (seg_max + (seg_max >> 5) + 4) & ~3;   // skewed row length
     dim3 grid(s2r_div_up(Hi, UR) * col_chunks, dxpitch, N);
-    up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)URB * seg_max * sizeof(float), (cudaStream_t)stream>>>(
-        dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
+    static int use_sep = -1;
+    if (use_sep < 0) {
+      const char* e = getenv("S2R_UPBWD");        // S2R_UPBWD=rows keeps the horizontal-first kernel (A/B testing)
+      use_sep = (e && e[0] == 'r') ? 0 : 1;
+    }
+    const size_t sep_smem = (size_t)UR * seg_max * sizeof(float);
+    if (use_sep && Wo % 4 == 0 && ((uintptr_t)dy & 15) == 0 && sep_smem <= 48 * 1024)
+      up_from_nchw_bwd_sep_kernel<<<grid, kThreads, sep_smem, (cudaStream_t)stream>>>(
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
+    else
+      up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)URB * seg_max * sizeof(float), (cudaStream_t)stream>>>(
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
     S2R_LAUNCH_OK();
     return S2R_OK;
   }

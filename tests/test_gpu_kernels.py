@@ -304,7 +304,7 @@ def test_bn_dropout_is_regenerated_in_backward(eng, cx):
 
 
 @pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 64, 128, 256), (5, 7, 17, 25), (33, 33, 129, 129), (1, 1, 9, 12),
-                                         (20, 300, 77, 1197), (24, 260, 94, 1040)])
+                                         (20, 300, 77, 1197), (24, 260, 94, 1040), (128, 256, 512, 1024)])
 def test_bilinear_align_corners(eng, cx, Hi, Wi, Ho, Wo):
     L = sub("_lib")
     g = torch.Generator(device="cuda").manual_seed(Hi * Wo)
