@@ -54,6 +54,8 @@ __device__ __forceinline__ uint4 ldg16_pinned(const void* p) {
 // sums[0][c] += sum_p x[p][c], sums[1][c] += sum_p x[p][c]^2
 __global__ void channel_sums_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int pitch,
                                     int coff, int rows, double* __restrict__ sums) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ float sm[];  // [rows][cg][16]
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -130,6 +132,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 __global__ void bn_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                float* __restrict__ mean_invstd, float* __restrict__ scale_shift, int C) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(rv[c] + eps);
@@ -170,6 +174,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpi
                 const __nv_bfloat16* __restrict__ residual, float drop_p, unsigned long long seed,
                 const unsigned long long* __restrict__ seed_dev, __nv_bfloat16* __restrict__ y, int ypitch,
                 int yoff, int rows) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -237,6 +243,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
                                      const float* __restrict__ scale_shift, int act, float drop_p,
                                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                                      long long P, int C, int rows, double* __restrict__ dsums) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   if (seed_dev) seed += *seed_dev;
   extern __shared__ float sm[];
   const int cg = C / 8;
@@ -288,6 +296,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff
                     const double* __restrict__ dsums, double count, long long P, int C,
                     __nv_bfloat16* __restrict__ dx, int dxpitch, int dxoff, int win_H, int win_W,
                     int win_pad, int rows) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   if (seed_dev) seed += *seed_dev;
   const int cg = C / 8;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -574,6 +584,8 @@ bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
 // dgamma += sum dy' xhat, dbeta += sum dy'
 __global__ void bn_param_grad_kernel(const double* __restrict__ dsums, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int C) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dbeta) dbeta[c] += (float)dsums[c];
@@ -611,8 +623,8 @@ extern "C" int s2r_channel_sums_bf16(const void* x, int64_t P, int C, int pitch,
   if (P == 0) return S2R_OK;
   RowReduceCfg cfg = row_reduce_cfg(P, C);
   size_t smem = (size_t)cfg.rows * cfg.cg * 16 * sizeof(float);
-  channel_sums_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, P, C, pitch, coff, cfg.rows, sums);
+  S2R_CUDA_OK(s2r_launch(channel_sums_kernel, dim3(cfg.grid), dim3(cfg.threads), (size_t)(smem), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, P, C, pitch, coff, cfg.rows, sums));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -634,8 +646,8 @@ extern "C" int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, co
                                        const float* running_var, float eps, float* mean_invstd,
                                        float* scale_shift, int C, s2r_stream_t stream) {
   S2R_REQUIRE(C >= 1, S2R_ERR_SHAPE, "bn_eval: C=%d", C);
-  bn_eval_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      gamma, beta, running_mean, running_var, eps, mean_invstd, scale_shift, C);
+  S2R_CUDA_OK(s2r_launch(bn_eval_kernel, dim3(s2r_div_up(C, 128)), dim3(128), (size_t)0, (cudaStream_t)stream, 
+      gamma, beta, running_mean, running_var, eps, mean_invstd, scale_shift, C));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -672,10 +684,10 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
       return S2R_OK;
     }
   }
-  bn_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
+  S2R_CUDA_OK(s2r_launch(bn_apply_kernel, dim3(cfg.grid), dim3(cfg.threads), (size_t)0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, P, C, xpitch, xoff, scale_shift, act,
       (const __nv_bfloat16*)residual, drop_p, seed, (const unsigned long long*)seed_dev, (__nv_bfloat16*)y, ypitch,
-      yoff, cfg.rows);
+      yoff, cfg.rows));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -708,9 +720,9 @@ extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const v
     S2R_LAUNCH_OK();
     return S2R_OK;
   }
-  bn_bwd_reduce_kernel<<<cfg.grid, cfg.threads, smem, (cudaStream_t)stream>>>(
+  S2R_CUDA_OK(s2r_launch(bn_bwd_reduce_kernel, dim3(cfg.grid), dim3(cfg.threads), (size_t)(smem), (cudaStream_t)stream, 
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
-      scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, P, C, cfg.rows, dsums);
+      scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, P, C, cfg.rows, dsums));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -747,18 +759,18 @@ extern "C" int s2r_bn_bwd_apply(const void* dy, int dypitch, int dyoff, const vo
     return S2R_OK;
   }
   if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<s2r_div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(dsums, dgamma, dbeta, C);
+    S2R_CUDA_OK(s2r_launch(bn_param_grad_kernel, dim3(s2r_div_up(C, 128)), dim3(128), (size_t)0, (cudaStream_t)stream, dsums, dgamma, dbeta, C));
     S2R_LAUNCH_OK();
   }
   if (P == 0 || !dx) return S2R_OK;
   S2R_REQUIRE(win_pad == 0 || (win_H >= 1 && win_W >= 1 && P % ((int64_t)win_H * win_W) == 0), S2R_ERR_SHAPE,
               "bn_bwd_apply: window %dx%d does not tile P", win_H, win_W);
   const ElemCfg cfg = elem_cfg(P, C);
-  bn_bwd_apply_kernel<<<cfg.grid, cfg.threads, 0, (cudaStream_t)stream>>>(
+  S2R_CUDA_OK(s2r_launch(bn_bwd_apply_kernel, dim3(cfg.grid), dim3(cfg.threads), (size_t)0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)dy, dypitch, dyoff, (const __nv_bfloat16*)x, xpitch, xoff, mean_invstd,
       scale_shift, act, drop_p, seed, (const unsigned long long*)seed_dev, dsums, count, P, C, (__nv_bfloat16*)dx,
       dxpitch, dxoff, win_H,
-      win_W, win_pad, cfg.rows);
+      win_W, win_pad, cfg.rows));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -68,14 +68,15 @@ static inline int s2r_grid(long work, int per_block, int waves = 8) {
 // Programmatic dependent launch: kernels launched through s2r_launch may start (and run their prologue: barrier /
 // TMEM / shared-memory set-up, tensor-map prefetch) while the previous kernel in the stream is still draining.
 // They call pdl_wait() before touching any global memory -- it returns once every earlier kernel has completed and
-// its writes are visible -- and pdl_trigger() right after, which lets the NEXT kernel do the same.  The ~1000
-// Measured on the captured step (B=8, 512x1024): 23.57 ms with, 23.82 ms without -- but the end-to-end loop
-// (input staging on a copy stream next to the replay) got 2.4 ms slower, so it is OFF by default; S2R_PDL=1 enables it.
+// its writes are visible -- and pdl_trigger() right after, which lets the NEXT kernel do the same.  Every kernel of the
+// training step goes through s2r_launch (the peer-exchange kernel of comm.cu, which spins on remote flags, does not).
+// Measured on the captured step (B=8, 512x1024): 19.84-19.98 ms with, 20.03 ms without when only the GEMM / depthwise
+// kernels took part; on by default, S2R_PDL=0 disables it.
 static inline bool s2r_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("S2R_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
 }

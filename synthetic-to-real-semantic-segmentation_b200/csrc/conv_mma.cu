@@ -97,6 +97,8 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint
 template <int BN>
 __global__ void __launch_bounds__(THREADS)
 tap_fwd_kernel(const __grid_constant__ FwdParams p) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int WN = BN / 32, WM = 8 / WN, WTM = BM / WM, MI = WTM / 16, NI = 4;
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -303,6 +305,8 @@ constexpr int WBK = 32;  // pixels per pipeline stage
 template <int BN>
 __global__ void __launch_bounds__(THREADS)
 tap_wgrad_kernel(const __grid_constant__ WgParams p) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int WN = BN / 32, WM = 8 / WN, WTM = BM / WM, MI = WTM / 16, NI = 4;
   constexpr int A_ROW = BM * 2, B_ROW = BN * 2;  // bytes per pixel row
   constexpr int A_BYTES = WBK * A_ROW, B_BYTES = WBK * B_ROW, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -474,6 +478,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 // output elements of one packed filter), so re-packing all ~190 filter copies after an optimizer step is one
 // launch instead of ~100 (each of which was mostly launch latency).
 __global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const s2r_pack_job j = jobs[blockIdx.y];
   const float* __restrict__ w = j.w;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.packed);
@@ -493,6 +499,8 @@ __global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs)
 // OIHW tensor itself those 32 elements are R*S floats apart -- and are moved into the OIHW gradient here
 __global__ void wgrad_scatter_taps_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin, int RS,
                                           int Cp) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long total = (long long)Cout * Cin * RS;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % RS);
@@ -504,6 +512,8 @@ __global__ void wgrad_scatter_taps_kernel(const float* __restrict__ G, float* __
 
 // w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]: the row-tap weight gradient (mode 2 layout, fp32) back to OIHW
 __global__ void rowtap_wgrad_scatter_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin, int Cp) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int total = Cout * Cin * 16;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kw = i & 3, kh = (i >> 2) & 3, q = i >> 4;
@@ -537,7 +547,7 @@ int launch_fwd(const FwdParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(s2r_div_up(p.M, BM), s2r_div_up(p.Cout, BN));
-  tap_fwd_kernel<BN><<<grid, THREADS, smem, st>>>(p);
+  S2R_CUDA_OK(s2r_launch(tap_fwd_kernel<BN>, dim3(grid), dim3(THREADS), (size_t)(smem), st, p));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -562,7 +572,7 @@ int launch_wgrad(WgParams& p, cudaStream_t st) {
   splits = s2r_div_up(p.P, pps);
   p.pix_per_split = pps;
   dim3 grid(s2r_div_up(p.Cout, BM), p.ci_tiles * p.ntaps, splits);
-  tap_wgrad_kernel<BN><<<grid, THREADS, smem, st>>>(p);
+  S2R_CUDA_OK(s2r_launch(tap_wgrad_kernel<BN>, dim3(grid), dim3(THREADS), (size_t)(smem), st, p));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -669,7 +679,7 @@ extern "C" int s2r_pack_weight(const float* w, int Cout, int Cin, int R, int S, 
 extern "C" int s2r_wgrad_scatter_taps(const float* G, float* dw, int Cout, int Cin, int RS, int Cp, s2r_stream_t stream) {
   S2R_REQUIRE(G && dw && Cout >= 1 && Cin >= 1 && RS >= 1 && Cp >= Cin, S2R_ERR_SHAPE, "wgrad_scatter_taps: bad arguments");
   const long long total = (long long)Cout * Cin * RS;
-  wgrad_scatter_taps_kernel<<<s2r_grid(total, 256, 4), 256, 0, (cudaStream_t)stream>>>(G, dw, Cout, Cin, RS, Cp);
+  S2R_CUDA_OK(s2r_launch(wgrad_scatter_taps_kernel, dim3(s2r_grid(total, 256, 4)), dim3(256), (size_t)0, (cudaStream_t)stream, G, dw, Cout, Cin, RS, Cp));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -677,7 +687,7 @@ extern "C" int s2r_wgrad_scatter_taps(const float* G, float* dw, int Cout, int C
 extern "C" int s2r_rowtap_wgrad_scatter(const float* G, float* dw, int Cout, int Cin, s2r_stream_t stream) {
   S2R_REQUIRE(G && dw && Cout >= 1 && Cin >= 1, S2R_ERR_SHAPE, "rowtap_wgrad_scatter: bad arguments");
   const int total = Cout * Cin * 16;
-  rowtap_wgrad_scatter_kernel<<<s2r_grid(total, 256, 1), 256, 0, (cudaStream_t)stream>>>(G, dw, Cout, Cin, (Cin + 7) & ~7);
+  S2R_CUDA_OK(s2r_launch(rowtap_wgrad_scatter_kernel, dim3(s2r_grid(total, 256, 1)), dim3(256), (size_t)0, (cudaStream_t)stream, G, dw, Cout, Cin, (Cin + 7) & ~7));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -686,7 +696,7 @@ extern "C" int s2r_pack_weights_multi(const s2r_pack_job* jobs, int njobs, s2r_s
   S2R_REQUIRE(njobs >= 0 && njobs <= 65535, S2R_ERR_SHAPE, "pack_weights_multi: %d jobs", njobs);
   if (njobs == 0) return S2R_OK;
   S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "pack_weights_multi: null table");
-  pack_weights_multi_kernel<<<dim3(4, njobs), 256, 0, (cudaStream_t)stream>>>(jobs);
+  S2R_CUDA_OK(s2r_launch(pack_weights_multi_kernel, dim3(dim3(4, njobs)), dim3(256), (size_t)0, (cudaStream_t)stream, jobs));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

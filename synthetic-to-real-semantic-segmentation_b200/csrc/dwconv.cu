@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(256)
 dw_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale_shift, int in_act,
               int halo_const, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
               double* __restrict__ stats, DwGeom G, int tw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* sw = sm;               // [9][C]
   float* red = sm + 9 * G.C;    // [tw][cg][16]
@@ -182,6 +184,8 @@ dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ 
                 const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale_shift,
                 const float* __restrict__ mean_invstd, int in_act, int ext, int interior, __nv_bfloat16* __restrict__ gout,
                 double* __restrict__ bsums, DwGeom G, int tw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* sw = sm;
   float* red = sm + 9 * G.C;
@@ -274,6 +278,8 @@ constexpr int WROWS = 64;
 __global__ void __launch_bounds__(384)
 dw_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale_shift, int in_act,
                 int halo_const, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, DwGeom G, int tw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];  // [tw][3*cg][24]
   const int cg = G.C / 8;
   const int g = threadIdx.x % cg;
@@ -401,13 +407,13 @@ extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int
   if (slide) {
     rc = dw_smem_attr(dw_fwd_kernel<true>, smem);
     if (rc) return rc;
-    dw_fwd_kernel<true><<<grid, tw * cg, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw);
+    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<true>, dim3(grid), dim3(tw * cg), (size_t)(smem), (cudaStream_t)stream, 
+        (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw));
   } else {
     rc = dw_smem_attr(dw_fwd_kernel<false>, smem);
     if (rc) return rc;
-    dw_fwd_kernel<false><<<grid, tw * cg, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw);
+    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<false>, dim3(grid), dim3(tw * cg), (size_t)(smem), (cudaStream_t)stream, 
+        (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw));
   }
   S2R_LAUNCH_OK();
   return S2R_OK;
@@ -430,9 +436,9 @@ static int dw_dgrad_generic(const void* dy, const float* w, const void* x,
   rc = dw_smem_attr(dw_dgrad_kernel, smem);
   if (rc) return rc;
   dim3 grid(s2r_div_up(We, tw), s2r_div_up(He, ROWS), N);
-  dw_dgrad_kernel<<<grid, tw * cg, smem, (cudaStream_t)stream>>>(
+  S2R_CUDA_OK(s2r_launch(dw_dgrad_kernel, dim3(grid), dim3(tw * cg), (size_t)(smem), (cudaStream_t)stream, 
       (const __nv_bfloat16*)dy, w, (const __nv_bfloat16*)x, in_scale_shift, in_mean_invstd, in_act, ext, interior,
-      (__nv_bfloat16*)g, bwd_sums, G, tw);
+      (__nv_bfloat16*)g, bwd_sums, G, tw));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -459,8 +465,8 @@ extern "C" int s2r_dwconv3x3_wgrad(const void* x, const float* in_scale_shift, i
   rc = dw_smem_attr(dw_wgrad_kernel, smem);
   if (rc) return rc;
   dim3 grid(s2r_div_up(G.Wo, tw), s2r_div_up(G.Ho, WROWS), N);
-  dw_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, (const __nv_bfloat16*)dy, dw, G, tw);
+  S2R_CUDA_OK(s2r_launch(dw_wgrad_kernel, dim3(grid), dim3(threads), (size_t)(smem), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, (const __nv_bfloat16*)dy, dw, G, tw));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

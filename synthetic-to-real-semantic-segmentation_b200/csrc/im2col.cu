@@ -22,6 +22,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(IC_THREADS)
 im2col_nchw_kernel(const float* __restrict__ x, int C, int H, int W, int R, int S, int stride, int pad,
                    __nv_bfloat16* __restrict__ P, int OH, int OW, int Kp, int Wt) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float win[];   // [C*R][Wt]
   const int ow0 = blockIdx.x * IC_TP, oh = blockIdx.y, n = blockIdx.z;
   int ix0 = ow0 * stride - pad;
@@ -113,11 +115,11 @@ extern "C" int s2r_im2col_nchw_f32(const float* x, int N, int C, int H, int W, i
   }
   dim3 grid(s2r_div_up(OW, IC_TP), OH, N);
   if (vec)
-    im2col_nchw_kernel<true><<<grid, IC_THREADS, smem, (cudaStream_t)stream>>>(x, C, H, W, R, S, stride, pad,
-                                                                            (__nv_bfloat16*)P, OH, OW, Kp, Wt);
+    S2R_CUDA_OK(s2r_launch(im2col_nchw_kernel<true>, dim3(grid), dim3(IC_THREADS), (size_t)(smem), (cudaStream_t)stream, x, C, H, W, R, S, stride, pad,
+                                                                            (__nv_bfloat16*)P, OH, OW, Kp, Wt));
   else
-    im2col_nchw_kernel<false><<<grid, IC_THREADS, smem, (cudaStream_t)stream>>>(x, C, H, W, R, S, stride, pad,
-                                                                             (__nv_bfloat16*)P, OH, OW, Kp, Wt);
+    S2R_CUDA_OK(s2r_launch(im2col_nchw_kernel<false>, dim3(grid), dim3(IC_THREADS), (size_t)(smem), (cudaStream_t)stream, x, C, H, W, R, S, stride, pad,
+                                                                             (__nv_bfloat16*)P, OH, OW, Kp, Wt));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

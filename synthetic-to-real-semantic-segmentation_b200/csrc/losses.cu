@@ -13,6 +13,8 @@ constexpr int kThreads = 256;
 template <int V>
 __global__ void __launch_bounds__(kThreads)
 softmax0_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, long long M) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long nvec = M / V;
   for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < nvec;
        j += (long long)gridDim.x * kThreads) {
@@ -52,6 +54,8 @@ template <int V>
 __global__ void __launch_bounds__(kThreads)
 softmax0_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                     float* __restrict__ dx, int B, long long M) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long nvec = M / V;
   for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < nvec;
        j += (long long)gridDim.x * kThreads) {
@@ -97,6 +101,8 @@ __global__ void __launch_bounds__(kThreads)
 ce_kernel(const float* __restrict__ logits, const float* __restrict__ target, int const_target,
           const float* __restrict__ weight, int C, long long HW, long long npix, int ignore_index,
           double* __restrict__ sums, float* __restrict__ grad) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   float loss_acc = 0.f, w_acc = 0.f, hit_acc = 0.f;
   const long long nvec = npix / V;  // HW % V == 0 guaranteed by the launcher
   for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < nvec;
@@ -169,6 +175,8 @@ ce_kernel(const float* __restrict__ logits, const float* __restrict__ target, in
 }
 
 __global__ void ratio_kernel(const double* __restrict__ sums, float* __restrict__ out, double denom_override) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   // out[0] = sums[0] / (denom_override > 0 ? denom_override : sums[1])
   double d = denom_override > 0 ? denom_override : sums[1];
   out[0] = (float)(sums[0] / d);
@@ -178,6 +186,8 @@ __global__ void ratio_kernel(const double* __restrict__ sums, float* __restrict_
 __global__ void __launch_bounds__(kThreads)
 scale_by_ratio_kernel(float* __restrict__ g, long long n, const float* __restrict__ gout,
                       const double* __restrict__ sums, double denom_override) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const double d = denom_override > 0 ? denom_override : sums[1];
   const float sc = (float)((double)gout[0] / d);
   const long long n4 = n / 4;
@@ -198,6 +208,8 @@ scale_by_ratio_kernel(float* __restrict__ g, long long n, const float* __restric
 __global__ void __launch_bounds__(kThreads)
 bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target, float const_target,
                long long n, double* __restrict__ sums) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
        i += (long long)gridDim.x * kThreads) {
@@ -219,6 +231,8 @@ bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target, fl
 __global__ void __launch_bounds__(kThreads)
 bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ target, float const_target,
                long long n, const float* __restrict__ gout, float* __restrict__ dx) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const float sc = gout[0] / (float)n;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
        i += (long long)gridDim.x * kThreads) {
@@ -243,6 +257,8 @@ constexpr int SP_MAXB = 8;
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(SP_THREADS)
 softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, int W, __nv_bfloat16* __restrict__ y, int Cp) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t sp_smem[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(sp_smem);   // [bc][SP_TW][Cp]
   const int w0 = blockIdx.x * SP_TW, h = blockIdx.y, b0 = blockIdx.z * SP_MAXB;
@@ -316,6 +332,8 @@ template <bool SOFTMAX>
 __global__ void __launch_bounds__(SP_THREADS)
 softmax0_nhwc_pad_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ gp, int B, int C, int H,
                              int W, int Cp, float* __restrict__ dx) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t sp_smem[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(sp_smem);
   const int w0 = blockIdx.x * SP_TW, h = blockIdx.y, b0 = blockIdx.z * SP_MAXB;
@@ -363,9 +381,9 @@ extern "C" int s2r_softmax_dim0_fwd(const float* x, float* y, int B, int64_t M, 
   if (M == 0) return S2R_OK;
   const bool vec = (M % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0);
   if (vec)
-    softmax0_fwd_kernel<4><<<s2r_grid(M / 4, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(x, y, B, M);
+    S2R_CUDA_OK(s2r_launch(softmax0_fwd_kernel<4>, dim3(s2r_grid(M / 4, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, x, y, B, M));
   else
-    softmax0_fwd_kernel<1><<<s2r_grid(M, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(x, y, B, M);
+    S2R_CUDA_OK(s2r_launch(softmax0_fwd_kernel<1>, dim3(s2r_grid(M, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, x, y, B, M));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -376,9 +394,9 @@ extern "C" int s2r_softmax_dim0_bwd(const float* y, const float* dy, float* dx, 
   if (M == 0) return S2R_OK;
   const bool vec = (M % 4 == 0) && (((uintptr_t)y | (uintptr_t)dy | (uintptr_t)dx) % 16 == 0);
   if (vec)
-    softmax0_bwd_kernel<4><<<s2r_grid(M / 4, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(y, dy, dx, B, M);
+    S2R_CUDA_OK(s2r_launch(softmax0_bwd_kernel<4>, dim3(s2r_grid(M / 4, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, y, dy, dx, B, M));
   else
-    softmax0_bwd_kernel<1><<<s2r_grid(M, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(y, dy, dx, B, M);
+    S2R_CUDA_OK(s2r_launch(softmax0_bwd_kernel<1>, dim3(s2r_grid(M, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, y, dy, dx, B, M));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -394,17 +412,17 @@ extern "C" int s2r_cross_entropy_nchw(const float* logits, const float* target, 
   const bool vec = (HW % 4 == 0) &&
                    (((uintptr_t)logits | (uintptr_t)grad_unscaled) % 16 == 0);
   if (vec)
-    ce_kernel<4><<<s2r_grid(npix / 4, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
-        logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled);
+    S2R_CUDA_OK(s2r_launch(ce_kernel<4>, dim3(s2r_grid(npix / 4, kThreads, 8)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+        logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled));
   else
-    ce_kernel<1><<<s2r_grid(npix, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
-        logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled);
+    S2R_CUDA_OK(s2r_launch(ce_kernel<1>, dim3(s2r_grid(npix, kThreads, 8)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+        logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
 
 extern "C" int s2r_ratio(const double* sums, double denom_override, float* out, s2r_stream_t stream) {
-  ratio_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, out, denom_override);
+  S2R_CUDA_OK(s2r_launch(ratio_kernel, dim3(1), dim3(1), (size_t)0, (cudaStream_t)stream, sums, out, denom_override));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -413,8 +431,8 @@ extern "C" int s2r_scale_by_ratio(float* g, int64_t n, const float* gout, const 
                                   double denom_override, s2r_stream_t stream) {
   if (n == 0) return S2R_OK;
   S2R_REQUIRE(((uintptr_t)g) % 16 == 0, S2R_ERR_SHAPE, "scale_by_ratio: unaligned buffer");
-  scale_by_ratio_kernel<<<s2r_grid(n / 4 + 1, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      g, n, gout, sums, denom_override);
+  S2R_CUDA_OK(s2r_launch(scale_by_ratio_kernel, dim3(s2r_grid(n / 4 + 1, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      g, n, gout, sums, denom_override));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -422,7 +440,7 @@ extern "C" int s2r_scale_by_ratio(float* g, int64_t n, const float* gout, const 
 extern "C" int s2r_bce_logits_fwd(const float* x, const float* target, float const_target, int64_t n,
                                   double* sums, s2r_stream_t stream) {
   S2R_REQUIRE(n >= 1, S2R_ERR_SHAPE, "bce_logits: empty input");
-  bce_fwd_kernel<<<s2r_grid(n, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(x, target, const_target, n, sums);
+  S2R_CUDA_OK(s2r_launch(bce_fwd_kernel, dim3(s2r_grid(n, kThreads, 2)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, x, target, const_target, n, sums));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -430,7 +448,7 @@ extern "C" int s2r_bce_logits_fwd(const float* x, const float* target, float con
 extern "C" int s2r_bce_logits_bwd(const float* x, const float* target, float const_target, int64_t n,
                                   const float* gout, float* dx, s2r_stream_t stream) {
   S2R_REQUIRE(n >= 1, S2R_ERR_SHAPE, "bce_logits_bwd: empty input");
-  bce_bwd_kernel<<<s2r_grid(n, kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(x, target, const_target, n, gout, dx);
+  S2R_CUDA_OK(s2r_launch(bce_bwd_kernel, dim3(s2r_grid(n, kThreads, 2)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, x, target, const_target, n, gout, dx));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -444,7 +462,7 @@ static int launch_sp_fwd(const float* x, int B, int C, int H, int W, void* yp, i
     attr = true;
   }
   dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
-  softmax0_to_nhwc_pad_kernel<SOFTMAX><<<grid, SP_THREADS, smem, st>>>(x, B, C, H, W, (__nv_bfloat16*)yp, Cp);
+  S2R_CUDA_OK(s2r_launch(softmax0_to_nhwc_pad_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, B, C, H, W, (__nv_bfloat16*)yp, Cp));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -458,7 +476,7 @@ static int launch_sp_bwd(const float* x, const void* gp, int B, int C, int H, in
     attr = true;
   }
   dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
-  softmax0_nhwc_pad_bwd_kernel<SOFTMAX><<<grid, SP_THREADS, smem, st>>>(x, (const __nv_bfloat16*)gp, B, C, H, W, Cp, dx);
+  S2R_CUDA_OK(s2r_launch(softmax0_nhwc_pad_bwd_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, (const __nv_bfloat16*)gp, B, C, H, W, Cp, dx));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -15,6 +15,8 @@ constexpr int kBlocksPerSlot = 16;
 __global__ void __launch_bounds__(kThreads)
 sgd_kernel(const s2r_param_slot* __restrict__ slots, const float* __restrict__ hyper, float momentum,
            float dampening, float wd, int nesterov, float gscale) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const s2r_param_slot s = slots[blockIdx.y];
   if (s.g == nullptr) return;
   const float lr = hyper[0] * s.lr_mult;
@@ -35,6 +37,8 @@ sgd_kernel(const s2r_param_slot* __restrict__ slots, const float* __restrict__ h
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(const s2r_param_slot* __restrict__ slots, const float* __restrict__ hyper, float beta1,
             float beta2, float eps, float wd, float gscale) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const s2r_param_slot s = slots[blockIdx.y];
   if (s.g == nullptr) return;
   const float lr = hyper[0] * s.lr_mult;
@@ -62,8 +66,8 @@ extern "C" int s2r_sgd_step(const s2r_param_slot* slots, int nslots, const float
   if (nslots == 0) return S2R_OK;
   S2R_REQUIRE(slots && hyper, S2R_ERR_SHAPE, "sgd_step: null table");
   dim3 grid(kBlocksPerSlot, nslots);
-  sgd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(slots, hyper, momentum, dampening, weight_decay,
-                                                         nesterov, gscale);
+  S2R_CUDA_OK(s2r_launch(sgd_kernel, dim3(grid), dim3(kThreads), (size_t)0, (cudaStream_t)stream, slots, hyper, momentum, dampening, weight_decay,
+                                                         nesterov, gscale));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -75,8 +79,8 @@ extern "C" int s2r_adam_step(const s2r_param_slot* slots, int nslots, const floa
   if (nslots == 0) return S2R_OK;
   S2R_REQUIRE(slots && hyper, S2R_ERR_SHAPE, "adam_step: null table");
   dim3 grid(kBlocksPerSlot, nslots);
-  adam_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(slots, hyper, beta1, beta2, eps, weight_decay,
-                                                          gscale);
+  S2R_CUDA_OK(s2r_launch(adam_kernel, dim3(grid), dim3(kThreads), (size_t)0, (cudaStream_t)stream, slots, hyper, beta1, beta2, eps, weight_decay,
+                                                          gscale));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

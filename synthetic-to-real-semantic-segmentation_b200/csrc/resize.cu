@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(kThreads)
 up_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Hi, int Wi, int C,
                    __nv_bfloat16* __restrict__ y, int Ho, int Wo, int ypitch, int yoff, float sh,
                    float sw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int cg = C / 8;
   const long long total = (long long)N * Ho * Wo * cg;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
@@ -87,6 +89,8 @@ template <typename IT>
 __global__ void __launch_bounds__(kThreads)
 up_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, int N, int Hi, int Wi,
                    int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, float sh, float sw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int cg = C / 8;
   const long long total = (long long)N * Hi * Wi * cg;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
@@ -126,6 +130,8 @@ template <int CG, typename IT>  // ceil(C/8) vectors per pixel
 __global__ void __launch_bounds__(kThreads)
 up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi, int Wi, int C,
                   float* __restrict__ y, int Ho, int Wo, float sh, float sw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long total = (long long)N * Ho * Wo;
   const long long plane = (long long)Ho * Wo;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
@@ -164,6 +170,8 @@ up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int Wo,
                         __nv_bfloat16* __restrict__ dx, int dxpitch, int Hi, int Wi, float sh, float sw) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long total = (long long)N * dxpitch * Hi * Wi;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
        t += (long long)gridDim.x * kThreads) {
@@ -216,6 +224,8 @@ __device__ __forceinline__ int first_fine_row(int i, float sh, int Hi, int Ho) {
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
                              int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float rowbuf[];   // [URB][seg_max]
   const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
   const int c = blockIdx.y, n = blockIdx.z;
@@ -313,6 +323,8 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
 __global__ void __launch_bounds__(kThreads, 3)   // <= 85 registers: without the bound ptxas hoists all 54 row loads (255 registers, spills)
 up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
                             int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) float rowbuf[];   // [UR][seg_max], skewed like above
   const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
   const int c = blockIdx.y, n = blockIdx.z;
@@ -402,6 +414,8 @@ up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo,
 __global__ void __launch_bounds__(kThreads)
 avgpool_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pitch, int coff,
                __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float scale) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   __shared__ float sm[kThreads / 8][8][8];
   const int n = blockIdx.y;
   const int g = blockIdx.x * 8 + (threadIdx.x & 7);  // channel group of 8
@@ -438,6 +452,8 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pitch, in
 __global__ void __launch_bounds__(kThreads)
 broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, float scale, int accumulate,
                  __nv_bfloat16* __restrict__ y, int ypitch, int yoff) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int cg = C / 8;
   const long long total = (long long)N * HW * cg;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total;
@@ -464,6 +480,8 @@ broadcast_kernel(const __nv_bfloat16* __restrict__ v, int N, int HW, int C, floa
 __global__ void __launch_bounds__(kThreads)
 nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, long long HW,
                     __nv_bfloat16* __restrict__ y, int ypitch) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int cg = ypitch / 8;
   const long long npix = (long long)N * HW;
   const long long total = npix * cg;
@@ -486,6 +504,8 @@ nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, long long HW,
 __global__ void __launch_bounds__(kThreads)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int C, long long HW,
                     float* __restrict__ y) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int cg = (C + 7) / 8;
   const long long npix = (long long)N * HW;
   const long long total = npix * cg;
@@ -508,6 +528,8 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int 
 __global__ void __launch_bounds__(kThreads)
 leaky_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                  __nv_bfloat16* __restrict__ dx, long long nvec, float slope) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < nvec;
        t += (long long)gridDim.x * kThreads) {
     float g[8], a[8];
@@ -530,13 +552,13 @@ extern "C" int s2r_upsample_bilinear_nhwc(const void* x, int N, int Hi, int Wi, 
               S2R_ERR_SHAPE, "upsample: channels/pitch must be multiples of 8 and buffers 16B aligned");
   const long long total = (long long)N * Ho * Wo * (C / 8);
   if (total < (1ll << 32))
-    up_nhwc_fwd_kernel<unsigned><<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+    S2R_CUDA_OK(s2r_launch(up_nhwc_fwd_kernel<unsigned>, dim3(s2r_grid(total, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
-        ac_scale(Wi, Wo));
+        ac_scale(Wi, Wo)));
   else
-    up_nhwc_fwd_kernel<long long><<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
+    S2R_CUDA_OK(s2r_launch(up_nhwc_fwd_kernel<long long>, dim3(s2r_grid(total, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, N, Hi, Wi, C, (__nv_bfloat16*)y, Ho, Wo, ypitch, yoff, ac_scale(Hi, Ho),
-        ac_scale(Wi, Wo));
+        ac_scale(Wi, Wo)));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -549,13 +571,13 @@ extern "C" int s2r_upsample_bilinear_nhwc_bwd(const void* dy, int dypitch, int d
               S2R_ERR_SHAPE, "upsample_bwd: channels/pitch must be multiples of 8 and buffers 16B aligned");
   const long long total = (long long)N * Hi * Wi * (C / 8);
   if (total < (1ll << 32))
-    up_nhwc_bwd_kernel<unsigned><<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+    S2R_CUDA_OK(s2r_launch(up_nhwc_bwd_kernel<unsigned>, dim3(s2r_grid(total, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
-        ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+        ac_scale(Hi, Ho), ac_scale(Wi, Wo)));
   else
-    up_nhwc_bwd_kernel<long long><<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+    S2R_CUDA_OK(s2r_launch(up_nhwc_bwd_kernel<long long>, dim3(s2r_grid(total, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
-        ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+        ac_scale(Hi, Ho), ac_scale(Wi, Wo)));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -573,7 +595,7 @@ extern "C" int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
   const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
   cudaStream_t st = (cudaStream_t)stream;
-#define S2R_UP(CG_, IT_) up_to_nchw_kernel<CG_, IT_><<<grid, kThreads, 0, st>>>(xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw)
+#define S2R_UP(CG_, IT_) S2R_CUDA_OK(s2r_launch(up_to_nchw_kernel<CG_, IT_>, dim3(grid), dim3(kThreads), (size_t)0, st, xb, xpitch, N, Hi, Wi, C, y, Ho, Wo, sh, sw))
   const bool small = total < (1ll << 32);
   switch (cgs) {
     case 1: if (small) S2R_UP(1, unsigned); else S2R_UP(1, long long); break;
@@ -606,17 +628,17 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
     }
     const size_t sep_smem = (size_t)UR * seg_max * sizeof(float);
     if (use_sep && Wo % 4 == 0 && ((uintptr_t)dy & 15) == 0 && sep_smem <= 48 * 1024)
-      up_from_nchw_bwd_sep_kernel<<<grid, kThreads, sep_smem, (cudaStream_t)stream>>>(
-          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
+      S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_sep_kernel, dim3(grid), dim3(kThreads), (size_t)(sep_smem), (cudaStream_t)stream, 
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max));
     else
-      up_from_nchw_bwd_rows_kernel<<<grid, kThreads, (size_t)URB * seg_max * sizeof(float), (cudaStream_t)stream>>>(
-          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max);
+      S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_rows_kernel, dim3(grid), dim3(kThreads), (size_t)((size_t)URB * seg_max * sizeof(float)), (cudaStream_t)stream, 
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max));
     S2R_LAUNCH_OK();
     return S2R_OK;
   }
   const long long total = (long long)N * dxpitch * Hi * Wi;
-  up_from_nchw_bwd_kernel<<<s2r_grid(total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw);
+  S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_kernel, dim3(s2r_grid(total, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -626,8 +648,8 @@ extern "C" int s2r_avgpool_nhwc(const void* x, int N, int HW, int C, int pitch, 
   S2R_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0 && pitch % 8 == 0 && coff % 8 == 0 && al16(x),
               S2R_ERR_SHAPE, "avgpool: bad shape/alignment");
   dim3 grid(s2r_div_up(C / 8, 8), N);
-  avgpool_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, HW, C, pitch, coff,
-                                                             (__nv_bfloat16*)y_bf16, y_f32, scale);
+  S2R_CUDA_OK(s2r_launch(avgpool_kernel, dim3(grid), dim3(kThreads), (size_t)0, (cudaStream_t)stream, (const __nv_bfloat16*)x, HW, C, pitch, coff,
+                                                             (__nv_bfloat16*)y_bf16, y_f32, scale));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -638,8 +660,8 @@ extern "C" int s2r_broadcast_nhwc(const void* v, int N, int HW, int C, float sca
                   ypitch >= yoff + C && al16(v) && al16(y),
               S2R_ERR_SHAPE, "broadcast: bad shape/alignment");
   const long long total = (long long)N * HW * (C / 8);
-  broadcast_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)v, N, HW, C, scale, accumulate, (__nv_bfloat16*)y, ypitch, yoff);
+  S2R_CUDA_OK(s2r_launch(broadcast_kernel, dim3(s2r_grid(total, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)v, N, HW, C, scale, accumulate, (__nv_bfloat16*)y, ypitch, yoff));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -649,8 +671,8 @@ extern "C" int s2r_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int64_t H
   S2R_REQUIRE(N >= 1 && C >= 1 && HW >= 1 && ypitch % 8 == 0 && ypitch >= C && al16(y), S2R_ERR_SHAPE,
               "nchw_to_nhwc: bad shape (pitch must be a multiple of 8 >= C)");
   const long long total = (long long)N * HW * (ypitch / 8);
-  nchw_to_nhwc_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      x, N, C, HW, (__nv_bfloat16*)y, ypitch);
+  S2R_CUDA_OK(s2r_launch(nchw_to_nhwc_kernel, dim3(s2r_grid(total, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      x, N, C, HW, (__nv_bfloat16*)y, ypitch));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -660,8 +682,8 @@ extern "C" int s2r_nhwc_bf16_to_nchw_f32(const void* x, int xpitch, int N, int C
   S2R_REQUIRE(N >= 1 && C >= 1 && HW >= 1 && xpitch % 8 == 0 && xpitch >= ((C + 7) / 8) * 8 && al16(x),
               S2R_ERR_SHAPE, "nhwc_to_nchw: bad shape");
   const long long total = (long long)N * HW * ((C + 7) / 8);
-  nhwc_to_nchw_kernel<<<s2r_grid(total, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, xpitch, N, C, HW, y);
+  S2R_CUDA_OK(s2r_launch(nhwc_to_nchw_kernel, dim3(s2r_grid(total, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, xpitch, N, C, HW, y));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -670,8 +692,8 @@ extern "C" int s2r_leaky_relu_bwd_bf16(const void* dy, const void* y, void* dx, 
                                        s2r_stream_t stream) {
   S2R_REQUIRE(n % 8 == 0 && al16(dy) && al16(y) && al16(dx), S2R_ERR_SHAPE, "leaky_relu_bwd: n must be a multiple of 8");
   if (n == 0) return S2R_OK;
-  leaky_bwd_kernel<<<s2r_grid(n / 8, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, n / 8, slope);
+  S2R_CUDA_OK(s2r_launch(leaky_bwd_kernel, dim3(s2r_grid(n / 8, kThreads * 2, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, n / 8, slope));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
