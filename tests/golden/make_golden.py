@@ -280,7 +280,32 @@ def shapes_case():
     print('shapes ok')
 
 
+def config1_case():
+    """BASELINE.json configs[0] / SURVEY.md section 8(d) config 1: DeepLab('mobilenet', 16, 19).train() under
+    torch.manual_seed(1), batch 2x3x513x513 from Generator(0), forward + CE + backward on the CPU (dropout off so the
+    run is reproducible).  Only summaries are stored (the logits alone would be 40 MB)."""
+    torch.manual_seed(1)
+    ref = no_dropout(RefDeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)).train()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 513, 513, generator=g)
+    lab = torch.randint(0, 20, (2, 513, 513), generator=g).float()
+    lab[lab == 19] = 255
+    out = ref(x)
+    loss = RefSegLoss().build_loss('ce')(out, lab)
+    loss.backward()
+    names = [k for k, p in ref.named_parameters()]
+    fix = dict(loss=np.float64(loss.item()), logits_head=head(out, 8192),
+               class_mean=out.detach().double().mean((0, 2, 3)).numpy(), class_std=out.detach().double().std((0, 2, 3)).numpy(),
+               grad_norm_names=np.array(names),
+               grad_norms=np.array([float(p.grad.double().norm()) for k, p in ref.named_parameters()], dtype=np.float64))
+    print('config1 loss', loss.item(), 'logits std', float(out.std()))
+    np.savez_compressed(os.path.join(HERE, 'config1_2x513x513.npz'), **fix)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'config1':
+        config1_case()
+        sys.exit(0)
     shapes_case()
     evaluator_case()
     discriminator_case()
@@ -288,4 +313,5 @@ if __name__ == '__main__':
     deeplab_case('deeplab_train_2x65x97', 2, 65, 97, True)
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
+    config1_case()
     print('all golden fixtures written to', HERE)

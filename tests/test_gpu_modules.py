@@ -94,6 +94,39 @@ def test_deeplab_train_forward_backward_vs_reference_fixture(built_lib):
     assert dev['decoder.last_conv.8.weight'] <= 0.15, dev['decoder.last_conv.8.weight']
 
 
+def test_config1_2x513x513_forward_ce_backward(built_lib):
+    """BASELINE.json configs[0] (the reference's CPU-runnable case): DeepLab('mobilenet', 16, 19).train(), batch
+    2x3x513x513 (odd sizes: ragged tiles, 33x33 ASPP maps, 129x129 decoder maps), forward + CE + backward against the
+    summaries of the reference run in tests/golden/config1_2x513x513.npz.  Train-mode logits of the random-initialised
+    network are chaotic end to end (module docstring), so the loss, the per-class statistics of the logits and the
+    classifier gradient are what is pinned."""
+    fix = golden('config1_2x513x513')
+    m = make_deeplab().cuda().train()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 513, 513, generator=g)
+    lab = torch.randint(0, 20, (2, 513, 513), generator=g).float()
+    lab[lab == 19] = 255
+    out = m(x.cuda())
+    assert out.shape == (2, 19, 513, 513) and out.dtype == torch.float32
+    loss = sub("utils.loss").SegmentationLosses().build_loss('ce')(out, lab.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    print("config 1 loss", loss.item(), float(fix['loss']))
+    assert abs(loss.item() - float(fix['loss'])) <= 1e-2 * float(fix['loss'])
+    std = out.detach().double().std((0, 2, 3)).cpu().numpy()
+    assert np.allclose(std, fix['class_std'], rtol=0.35), (std, fix['class_std'])
+    norms = dict(zip([str(n) for n in fix['grad_norm_names']], fix['grad_norms']))
+    params = dict(m.named_parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params.values())
+    for k in ('decoder.last_conv.8.weight', 'decoder.last_conv.8.bias'):
+        got = float(params[k].grad.double().norm())
+        assert abs(got - norms[k]) <= 0.15 * norms[k], (k, got, norms[k])
+    keys = [k for k, p in params.items() if p.dim() == 4 and 'global_avg_pool' not in k]
+    dev = sorted(abs(float(params[k].grad.double().norm()) - norms[k]) / (norms[k] + 1e-3 * max(norms.values())) for k in keys)
+    print("config 1 grad-norm deviation: median %.3f max %.3f" % (dev[len(dev) // 2], dev[-1]))
+    assert dev[len(dev) // 2] <= 3.0 and dev[-1] <= 6.0
+
+
 def test_deeplab_eval_forward_vs_fixture(built_lib):
     fix = golden('deeplab_eval_1x97x65')
     m = make_deeplab().cuda().eval()
