@@ -696,7 +696,7 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
     case 256: return big ? launch_tc<256, 2, 3>(maps, p, ntn, st) : launch_tc<256, 1, 4>(maps, p, ntn, st);
     case 160: return big ? launch_tc<160, 2, 3>(maps, p, ntn, st) : launch_tc<160, 1, 5>(maps, p, ntn, st);
     case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 6>(maps, p, ntn, st);
-    case 64: return launch_tc<64, 1, 8>(maps, p, ntn, st);
+    case 64: return big ? launch_tc<64, 2, 4>(maps, p, ntn, st) : launch_tc<64, 1, 8>(maps, p, ntn, st);
     default: return launch_tc<32, 1, 8>(maps, p, ntn, st);
   }
 }
