@@ -93,13 +93,57 @@ def init_peer_exchange(group=None, slot=4096):
     return True
 
 
+_SIDE_STREAMS = {}
+WGRAD_STREAM = os.environ.get("S2R_WGRAD_STREAM", "1") != "0"
+
+
+class _Fork(object):
+    """Runs the enclosed launches on the context's side stream, after everything issued on the main stream so far."""
+
+    def __init__(self, cx, keep):
+        self.cx, self.keep = cx, keep
+
+    def __enter__(self):
+        cx = self.cx
+        main = torch.cuda.current_stream(cx.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        cx.side.wait_event(ev)
+        cx._forked = True
+        cx._keep.extend(self.keep)       # operands stay allocated until join(): the main stream must not reuse them
+        self._ctx = torch.cuda.stream(cx.side)
+        self._ctx.__enter__()
+
+    def __exit__(self, *a):
+        self._ctx.__exit__(*a)
+
+
+class _NoFork(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class Ctx:
     """Per-call execution context (stream, mode, cross-rank synchronisation of BN)."""
 
-    def __init__(self, device, training, sync_group=None, dropout=True):
+    def __init__(self, device, training, sync_group=None, dropout=True, async_wgrad=False):
         L.require_cuda()
         self.device = device
         self.training = training
+        # weight gradients are leaves of the backward pass (nothing downstream reads them before the optimizer): with
+        # async_wgrad they are issued on a side stream and overlap the data-gradient chain, whose many small kernels
+        # leave most SMs idle; join() orders them before whatever follows the module's backward
+        self.side = None
+        self._keep = []
+        self._forked = False
+        if async_wgrad and WGRAD_STREAM:
+            key = (device.type, device.index)
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.side = _SIDE_STREAMS[key]
         self.group = sync_group
         self.world = 1
         if sync_group is not None:
@@ -117,6 +161,16 @@ class Ctx:
     def stream(self):
         # looked up per call: the current stream changes under torch.cuda.graph / torch.cuda.stream
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def fork(self, *keep):
+        """`with cx.fork(tensors...):` -- launches inside go to the side stream (no-op without async_wgrad)."""
+        return _Fork(self, keep) if self.side is not None else _NoFork()
+
+    def join(self):
+        if self.side is not None and self._forked:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            self._forked = False
+        self._keep = []
 
     def next_seed(self):
         self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
@@ -418,21 +472,23 @@ def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
     a.Cin, a.Cout = Cin, Cout
     a.dy = dy.ptr
     a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
-    if R * S > 1 and WGRAD_TAP_MAJOR:
-        # tap-major fp32 scratch [R*S][Cout][Cp]: the kernel's atomics hit 32 consecutive input channels (one 128-byte
-        # line) per instruction instead of 32 elements R*S floats apart; one small pass adds it into the OIHW gradient
-        Cp = round_up(Cin, 32)
-        G = cx.f32(R * S * Cout * Cp)
-        for t in range(a.ntaps):
-            a.taps[t].wofs = a.taps[t].wofs * Cout * Cp
-        a.dweight = G.data_ptr()
-        a.s_co, a.s_ci = Cp, 1
+    with cx.fork(x.t, dy.t):
+        if R * S > 1 and WGRAD_TAP_MAJOR:
+            # tap-major fp32 scratch [R*S][Cout][Cp]: the kernel's atomics hit 32 consecutive input channels (one
+            # 128-byte line) per instruction instead of 32 elements R*S floats apart; one small pass adds it into the
+            # OIHW gradient
+            Cp = round_up(Cin, 32)
+            G = cx.f32(R * S * Cout * Cp)
+            for t in range(a.ntaps):
+                a.taps[t].wofs = a.taps[t].wofs * Cout * Cp
+            a.dweight = G.data_ptr()
+            a.s_co, a.s_ci = Cp, 1
+            L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+            L.call("s2r_wgrad_scatter_taps", _vp(G), _vp(g), Cout, Cin, R * S, Cp, cx.stream)
+            return
+        a.dweight = g.data_ptr()
+        a.s_co, a.s_ci = Cin * R * S, R * S
         L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
-        L.call("s2r_wgrad_scatter_taps", _vp(G), _vp(g), Cout, Cin, R * S, Cp, cx.stream)
-        return
-    a.dweight = g.data_ptr()
-    a.s_co, a.s_ci = Cin * R * S, R * S
-    L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
 
 
 # --------------------------------------------------------------------------- row-tap 4x4 stride-2 convolution
@@ -492,7 +548,7 @@ def rowtap_wgrad(cx, xp, dy, w):
     """w.grad += weight gradient of the same convolution (accumulated in the row-tap layout, then scattered to OIHW)."""
     Cout, Cin, R, S = w.shape
     Cp = xp.Cp
-    G = cx.f32(Cout * 16 * Cp)
+    g = grad_of(w)
     a = L.WgradArgs()
     a.struct_size = C.sizeof(L.WgradArgs)
     a.ntaps = 4
@@ -501,10 +557,12 @@ def rowtap_wgrad(cx, xp, dy, w):
     a.Cin, a.Cout = 4 * Cp, Cout
     a.dy = dy.ptr
     a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
-    a.dweight = G.data_ptr()
-    a.s_co, a.s_ci = 16 * Cp, 1
-    L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
-    L.call("s2r_rowtap_wgrad_scatter", _vp(G), _vp(grad_of(w)), Cout, Cin, cx.stream)
+    with cx.fork(xp.t, dy.t):
+        G = cx.f32(Cout * 16 * Cp)
+        a.dweight = G.data_ptr()
+        a.s_co, a.s_ci = 16 * Cp, 1
+        L.call("s2r_conv_wgrad", C.byref(a), cx.stream)
+        L.call("s2r_rowtap_wgrad_scatter", _vp(G), _vp(g), Cout, Cin, cx.stream)
 
 
 def rowtap_dgrad(cx, dy, w, H, W):

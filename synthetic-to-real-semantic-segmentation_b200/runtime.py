@@ -76,7 +76,7 @@ class ModuleFn(torch.autograd.Function):
     def backward(ctx, *douts):
         run, module, dev = ctx.run, ctx.module, ctx.dev
         with torch.cuda.device(dev):
-            cx = Ctx(dev, True, sync_group_for(module), dropout=False)
+            cx = Ctx(dev, True, sync_group_for(module), dropout=False, async_wgrad=True)
             dacts = tuple(run.import_grad(cx, i, d) for i, d in enumerate(douts))
             need = ctx.needs_input_grad[3:3 + ctx.n_in]
             dins = run.backward(cx, dacts, need)
@@ -90,6 +90,7 @@ class ModuleFn(torch.autograd.Function):
                     res.append(d)
                 else:
                     res.append(to_nchw(cx, d, ctx.in_shapes[i][1]))
+            cx.join()        # side-stream weight gradients are ordered before whatever follows this backward
         ctx.run = None
         return (None, None, None) + tuple(res) + (None,) * (len(ctx.needs_input_grad) - 3 - ctx.n_in)
 
