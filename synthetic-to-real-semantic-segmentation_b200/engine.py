@@ -140,7 +140,8 @@ class Ctx:
         self._keep = []
         self._forked = False
         if async_wgrad and WGRAD_STREAM:
-            key = (device.type, device.index)
+            # one side stream per ambient stream (two backward passes may run on two streams, steps.AdaptStep)
+            key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
             if key not in _SIDE_STREAMS:
                 _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
             self.side = _SIDE_STREAMS[key]

@@ -12,6 +12,8 @@ flat gradient buffers are all-reduced (averaged) before the optimizer steps.  De
 single-process DataParallel of the reference, stated in DESIGN.md: the cross-entropy mean and
 F.softmax(dim=0) are taken over the rank-local batch.
 """
+import os
+
 import torch
 
 from .engine import seed_counter, prepack_weights
@@ -129,31 +131,90 @@ class AdaptStep(object):
         self.optimizer_D.zero_grad()
         # all bf16 filter copies invalidated by the previous optimizer step, in one launch
         prepack_weights(torch.cuda.current_stream(src_image.device).cuda_stream)
-        # ---- train G; don't accumulate grads in D (train_adapt.py:140-155)
-        for p in model_D.parameters():
-            p.requires_grad = False
-        src_output = model(src_image)
-        loss_seg = self.criterion(src_output, src_label)
-        loss_seg.backward()
-        tgt_output = model(tgt_image)
-        D_out = _disc_on_softmax0(model_D, tgt_output)
-        loss_adv = bce_with_logits(D_out, self.source_label)
-        loss_adv.backward()
-        # ---- train D (train_adapt.py:160-178)
-        for p in model_D.parameters():
-            p.requires_grad = True
-        src_output = src_output.detach()
-        loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
-        loss_D_src.backward()
-        tgt_output = tgt_output.detach()
-        loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
-        loss_D_tgt.backward()
+        if self._two_streams(src_image.device):
+            loss_seg, loss_adv, loss_D_src, loss_D_tgt = self._passes_two_streams(src_image, src_label, tgt_image)
+        else:
+            # ---- train G; don't accumulate grads in D (train_adapt.py:140-155)
+            for p in model_D.parameters():
+                p.requires_grad = False
+            src_output = model(src_image)
+            loss_seg = self.criterion(src_output, src_label)
+            loss_seg.backward()
+            tgt_output = model(tgt_image)
+            D_out = _disc_on_softmax0(model_D, tgt_output)
+            loss_adv = bce_with_logits(D_out, self.source_label)
+            loss_adv.backward()
+            # ---- train D (train_adapt.py:160-178)
+            for p in model_D.parameters():
+                p.requires_grad = True
+            src_output = src_output.detach()
+            loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
+            loss_D_src.backward()
+            tgt_output = tgt_output.detach()
+            loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
+            loss_D_tgt.backward()
         self.optimizer.all_reduce_grads()
         self.optimizer_D.all_reduce_grads()
         self.optimizer.launch()
         self.optimizer_D.launch()
         return {'loss_seg': loss_seg.detach(), 'loss_adv': loss_adv.detach(), 'loss_D_src': loss_D_src.detach(),
                 'loss_D_tgt': loss_D_tgt.detach()}
+
+
+def _adapt_two_streams(self, dev):
+    """The two-stream schedule needs every pass to be free of cross-rank exchanges (the BN peer exchange is a sequence
+    of collective steps that must be issued in the same order on every rank): single process, or no synchronised BN."""
+    if os.environ.get("S2R_OVERLAP", "1") == "0":
+        return False
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and getattr(self.model, "_s2r_has_sync_bn", False):
+        return False
+    return True
+
+
+def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
+    """train_adapt.py:140-178 with the same arithmetic on two streams.  The passes of the step form two chains that only
+    meet in the gradient buffers:  A = G(src) forward -> CE -> G backward -> D training passes (src, tgt);
+    B = G(tgt) forward -> D (frozen) -> BCE -> backward through D and G.  B's forward runs beside A's backward, B's
+    backward (which accumulates into the same generator gradients) starts when A's backward has finished and runs
+    beside the discriminator's training passes.  Each chain is a sequence of ~400 kernels most of which fill a fraction
+    of the GPU, so the chains interleave well.  Autograd runs every backward node on the stream of its forward."""
+    model, model_D = self.model, self.model_D
+    dev = src_image.device
+    A = torch.cuda.current_stream(dev)
+    if getattr(self, "_stream_B", None) is None:
+        self._stream_B = torch.cuda.Stream(device=dev)
+    B = self._stream_B
+    src_output = model(src_image)
+    loss_seg = self.criterion(src_output, src_label)
+    B.wait_stream(A)                       # BN running statistics: G(src) forward before G(tgt) forward
+    for p in model_D.parameters():
+        p.requires_grad = False            # train G: no gradients in D (train_adapt.py:140-141)
+    with torch.cuda.stream(B):
+        tgt_output = model(tgt_image)
+        D_out = _disc_on_softmax0(model_D, tgt_output)
+        loss_adv = bce_with_logits(D_out, self.source_label)
+        fwd_B = torch.cuda.Event()
+        fwd_B.record(B)
+    loss_seg.backward()                    # on A, beside B's forward
+    B.wait_stream(A)                       # both backward passes accumulate into the generator's gradients
+    with torch.cuda.stream(B):
+        loss_adv.backward()
+    for p in model_D.parameters():
+        p.requires_grad = True             # train D (train_adapt.py:158-159)
+    src_output = src_output.detach()
+    loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
+    loss_D_src.backward()
+    A.wait_event(fwd_B)
+    tgt_output = tgt_output.detach()
+    loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
+    loss_D_tgt.backward()
+    A.wait_stream(B)
+    return loss_seg, loss_adv, loss_D_src, loss_D_tgt
+
+
+AdaptStep._two_streams = _adapt_two_streams
+AdaptStep._passes_two_streams = _adapt_passes_two_streams
 
 
 class FeatureStep(object):
