@@ -386,29 +386,60 @@ class ValStep(object):
         return loss
 
     @torch.no_grad()
-    def capture(self, image, target):
+    def capture(self, image, target, lanes=1):
         """Capture forward + fused argmax/confusion matrix into one CUDA graph (a batch-1 eval forward is ~200
         short launches: issued from Python they starve the GPU).  replay() copies the inputs into the static
-        buffers; the confusion matrix keeps accumulating on the device."""
+        buffers; the confusion matrix keeps accumulating on the device.
+        lanes > 1: that many copies of the graph, each with its own static buffers and stream; successive images go
+        to the lanes round-robin and overlap on the GPU (a batch-1 forward is a chain of kernels that fill a fraction
+        of the SMs; the counts are integer atomics, so the result does not depend on the interleaving).  Call
+        finish() before reading the evaluator."""
         dev = image.device
-        self._static = (torch.empty_like(image), torch.empty_like(target))
-        for st, t in zip(self._static, (image, target)):
-            st.copy_(t)
+        cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
+        side.wait_stream(cur)
         with torch.cuda.stream(side):
-            self(*self._static)          # warm-up: weight packing, lazy buffers
-        torch.cuda.current_stream(dev).wait_stream(side)
+            self(image, target)          # warm-up: weight packing, lazy buffers
+        cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self(*self._static)
+        self._lanes, self._next = [], 0
+        for lane in range(max(1, lanes)):
+            static = (torch.empty_like(image), torch.empty_like(target))
+            for st, t in zip(static, (image, target)):
+                st.copy_(t)
+            stream = torch.cuda.Stream(device=dev) if lanes > 1 else None
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            if stream is None:
+                with torch.cuda.graph(graph):
+                    self(*static)
+            else:
+                with torch.cuda.graph(graph, stream=stream):
+                    self(*static)
+            self._lanes.append((static, graph, stream))
+        self._static, self._graph = self._lanes[0][0], self._lanes[0][1]
         self.evaluator.reset()           # drop the warm-up counts
         return self
 
     @torch.no_grad()
     def replay(self, image, target):
-        for st, t in zip(self._static, (image, target)):
-            if st.data_ptr() != t.data_ptr():
-                st.copy_(t, non_blocking=True)
-        self._graph.replay()
+        static, graph, stream = self._lanes[self._next]
+        self._next = (self._next + 1) % len(self._lanes)
+        if stream is None:
+            for st, t in zip(static, (image, target)):
+                if st.data_ptr() != t.data_ptr():
+                    st.copy_(t, non_blocking=True)
+            graph.replay()
+            return
+        stream.wait_stream(torch.cuda.current_stream(image.device))     # the caller's tensors are ready
+        with torch.cuda.stream(stream):
+            for st, t in zip(static, (image, target)):
+                if st.data_ptr() != t.data_ptr():
+                    st.copy_(t, non_blocking=True)
+            graph.replay()
+
+    def finish(self):
+        """Order every lane before the current stream (call before reading the evaluator)."""
+        for static, graph, stream in getattr(self, "_lanes", []):
+            if stream is not None:
+                torch.cuda.current_stream(static[0].device).wait_stream(stream)

@@ -364,6 +364,30 @@ def test_val_step_confusion_matrix_matches_oracle_on_same_predictions(built_lib)
     assert val.evaluator.Mean_Intersection_over_Union()[0] == m_['mIoU']
 
 
+def test_val_step_graph_lanes_accumulate_identical_counts(built_lib):
+    """ValStep.capture(lanes=2): successive images replayed on two graph lanes give exactly the counts of the eager
+    loop (integer atomics; order-independent)."""
+    torch.manual_seed(2)
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False).cuda().eval()
+    g = torch.Generator().manual_seed(6)
+    imgs = [torch.randn(1, 3, 64, 96, generator=g).cuda() for _ in range(5)]
+    labs = []
+    for _ in range(5):
+        t = torch.randint(0, 19, (1, 64, 96), generator=g).float()
+        t[torch.rand(1, 64, 96, generator=g) < 0.1] = 255
+        labs.append(t.cuda())
+    eager = sub("steps").ValStep(G, 19)
+    for im, lb in zip(imgs, labs):
+        eager(im, lb)
+    want = eager.evaluator.confusion_matrix
+    lanes = sub("steps").ValStep(G, 19).capture(imgs[0], labs[0], lanes=2)
+    for im, lb in zip(imgs, labs):
+        lanes.replay(im, lb)
+    lanes.finish()
+    got = lanes.evaluator.confusion_matrix
+    assert np.array_equal(got, want) and got.sum() == sum(int((lb != 255).sum()) for lb in labs)
+
+
 def test_dropout_train_mode_statistics(built_lib):
     """With dropout enabled the step still runs; about half of the ASPP output is zero (p=0.5)."""
     torch.manual_seed(1)
