@@ -49,7 +49,7 @@ add_bf16_kernel(__nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__
 
 __global__ void add_f64_to_f32_kernel(const double* __restrict__ s, float* __restrict__ o, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] += (float)s[i];
+  if (i < n) atomicAdd(o + i, (float)s[i]);   // atomic: gradient buffers may be accumulated from two streams
 }
 
 }  // namespace

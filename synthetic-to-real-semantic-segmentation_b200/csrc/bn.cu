@@ -475,8 +475,9 @@ bn_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff,
   if (APPLY && blockIdx.x == 0 && r == 0) {   // parameter gradients from the (final) sums: dgamma += sum gd*xhat
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (dbeta) dbeta[g * 8 + i] += (float)dsums[g * 8 + i];
-      if (dgamma) dgamma[g * 8 + i] += (float)dsums[C + g * 8 + i];
+      // atomic: two backward passes (source / target) may add into the same parameter gradient from two streams
+      if (dbeta) atomicAdd(dbeta + g * 8 + i, (float)dsums[g * 8 + i]);
+      if (dgamma) atomicAdd(dgamma + g * 8 + i, (float)dsums[C + g * 8 + i]);
     }
   }
   const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
@@ -588,8 +589,8 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ dsums, float* __
   pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dbeta) dbeta[c] += (float)dsums[c];
-  if (dgamma) dgamma[c] += (float)dsums[C + c];
+  if (dbeta) atomicAdd(dbeta + c, (float)dsums[c]);
+  if (dgamma) atomicAdd(dgamma + c, (float)dsums[C + c]);
 }
 
 // launch geometry of the element-wise kernels: threads = rows x channel groups, enough CTAs for ~16 per SM

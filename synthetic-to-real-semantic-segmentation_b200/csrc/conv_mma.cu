@@ -506,7 +506,7 @@ __global__ void wgrad_scatter_taps_kernel(const float* __restrict__ G, float* __
     const int t = (int)(i % RS);
     const long long q = i / RS;
     const int ci = (int)(q % Cin), co = (int)(q / Cin);
-    dw[i] += G[((long long)t * Cout + co) * Cp + ci];
+    atomicAdd(dw + i, G[((long long)t * Cout + co) * Cp + ci]);   // atomic: see s2r_add_f64_to_f32
   }
 }
 
@@ -518,7 +518,7 @@ __global__ void rowtap_wgrad_scatter_kernel(const float* __restrict__ G, float* 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kw = i & 3, kh = (i >> 2) & 3, q = i >> 4;
     const int c = q % Cin, co = q / Cin;
-    dw[i] += G[((long long)co * 4 + kh) * (4 * Cp) + kw * Cp + c];
+    atomicAdd(dw + i, G[((long long)co * 4 + kh) * (4 * Cp) + kw * Cp + c]);
   }
 }
 
