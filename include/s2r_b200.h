@@ -325,6 +325,9 @@ int s2r_comm_create(int rank, int world, int slot_doubles, void* handle_out);
 int s2r_comm_open(const void* handles);
 int s2r_comm_ready(void);   /* world size once opened, else 0 */
 int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream);
+/* The same on exchange channel 0 or 1: every rank issues the same sequence of calls PER CHANNEL, and calls on
+ * different channels may be in flight together (the two streams of the training step). */
+int s2r_allreduce_small_f64_ch(double* buf, int n, int channel, s2r_stream_t stream);
 int s2r_comm_error(void);   /* non-zero: a bounded wait expired (synchronises the device) */
 int s2r_comm_destroy(void);
 

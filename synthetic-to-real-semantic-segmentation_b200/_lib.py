@@ -102,6 +102,7 @@ PROTOTYPES = {
     "s2r_comm_create": [i32, i32, i32, vp],
     "s2r_comm_open": [vp],
     "s2r_allreduce_small_f64": [vp, i32, vp],
+    "s2r_allreduce_small_f64_ch": [vp, i32, i32, vp],
     "s2r_sgd_step": [vp, i32, vp, f32, f32, f32, i32, f32, vp],
     "s2r_adam_step": [vp, i32, vp, f32, f32, f32, f32, f32, vp],
 }

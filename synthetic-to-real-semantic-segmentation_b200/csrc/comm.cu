@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int CM_DEPTH = 4;
+constexpr int CM_CHANNELS = 2;   // independent exchange sequences (one per stream of the two-stream training step)
 constexpr int CM_MAX_WORLD = 16;
 constexpr int CM_THREADS = 1024;
 
@@ -63,24 +64,28 @@ __device__ __forceinline__ unsigned long long ld_word(const unsigned long long* 
 // latencies overlap) instead of one peer after the other; WORLD == 0: generic loop.
 template <int WORLD>
 __global__ void __launch_bounds__(CM_THREADS)
-allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c) {
-  const unsigned long long seq = *c.seq + 1;      // every thread reads it; thread 0 advances it at the end
+allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
+  // channel ch has its own sequence counter and its own region of every inbox: two streams can run their exchange
+  // sequences concurrently as long as every rank issues the same sequence PER CHANNEL
+  unsigned long long* seqp = c.seq + ch;
+  const unsigned long long seq = *seqp + 1;       // every thread reads it; thread 0 advances it at the end
   const unsigned long long tag = (seq & 0xffffffffull) << 32;
   const int d = (int)(seq % CM_DEPTH);
   const size_t slot_words = (size_t)c.slot * 2;
+  const size_t ch_words = (size_t)ch * CM_DEPTH * c.world * slot_words;
   // 1. contribute to every peer's inbox
   for (int i = threadIdx.x; i < n; i += CM_THREADS) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
     const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
     for (int r = 0; r < c.world; ++r) {
       if (r == c.rank) continue;
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.inbox[r]) + ((size_t)d * c.world + c.rank) * slot_words;
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.inbox[r]) + ch_words + ((size_t)d * c.world + c.rank) * slot_words;
       st_word(dst + 2 * i, w0);
       st_word(dst + 2 * i + 1, w1);
     }
   }
   // 2. + 3. poll every rank's words and sum in rank order (own value taken from buf)
-  const unsigned long long* in = reinterpret_cast<const unsigned long long*>(c.inbox[c.rank]) + (size_t)d * c.world * slot_words;
+  const unsigned long long* in = reinterpret_cast<const unsigned long long*>(c.inbox[c.rank]) + ch_words + (size_t)d * c.world * slot_words;
   bool timed_out = false;
   for (int i = threadIdx.x; WORLD > 0 && i < n; i += CM_THREADS) {
     const double mine = buf[i];
@@ -137,7 +142,7 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c) {
   }
   if (timed_out) atomicExch(c.err, 1);
   __syncthreads();
-  if (threadIdx.x == 0) *c.seq = seq;
+  if (threadIdx.x == 0) *seqp = seq;
 }
 
 }  // namespace
@@ -149,7 +154,7 @@ extern "C" int s2r_comm_create(int rank, int world, int slot_doubles, void* hand
               S2R_ERR_SHAPE, "comm: bad rank/world/slot");
   CommHost& h = g_comm;
   h.rank = rank; h.world = world; h.slot = (slot_doubles + 1) & ~1;
-  h.inbox_bytes = (size_t)CM_DEPTH * world * h.slot * 2 * sizeof(unsigned long long);   // LL words: 2 per double
+  h.inbox_bytes = (size_t)CM_CHANNELS * CM_DEPTH * world * h.slot * 2 * sizeof(unsigned long long);   // LL words: 2 per double
   h.flags_bytes = (size_t)CM_DEPTH * world * sizeof(unsigned long long);
   const size_t total = h.inbox_bytes + h.flags_bytes + 256;
   S2R_CUDA_OK(cudaMalloc(&h.local, total));
@@ -188,18 +193,24 @@ extern "C" int s2r_comm_open(const void* handles) {
 
 extern "C" int s2r_comm_ready() { return g_comm.ready ? g_comm.world : 0; }
 
-/* In-place sum over all ranks of buf[0..n) (fp64).  Every rank must issue the same sequence of calls. */
-extern "C" int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream) {
+/* In-place sum over all ranks of buf[0..n) (fp64) on exchange channel `channel` (0 or 1).  Every rank must issue the
+ * same sequence of calls per channel; calls on different channels may be in flight together (two streams). */
+extern "C" int s2r_allreduce_small_f64_ch(double* buf, int n, int channel, s2r_stream_t stream) {
   const CommHost& h = g_comm;
   S2R_REQUIRE(h.ready, S2R_ERR_SHAPE, "comm: not initialised");
   S2R_REQUIRE(buf && n >= 1 && n <= h.slot, S2R_ERR_SHAPE, "allreduce_small: n=%d exceeds the slot of %d doubles", n, h.slot);
+  S2R_REQUIRE(channel >= 0 && channel < CM_CHANNELS, S2R_ERR_SHAPE, "allreduce_small: channel %d", channel);
   if (h.world == 1) return S2R_OK;
-  if (h.world == 2) allreduce_small_kernel<2><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
-  else if (h.world == 4) allreduce_small_kernel<4><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
-  else if (h.world == 8) allreduce_small_kernel<8><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
-  else allreduce_small_kernel<0><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev);
+  if (h.world == 2) allreduce_small_kernel<2><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
+  else if (h.world == 4) allreduce_small_kernel<4><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
+  else if (h.world == 8) allreduce_small_kernel<8><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
+  else allreduce_small_kernel<0><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+extern "C" int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream) {
+  return s2r_allreduce_small_f64_ch(buf, n, 0, stream);
 }
 
 /* Non-zero after a bounded wait expired (a peer died); reading it synchronises the device. */

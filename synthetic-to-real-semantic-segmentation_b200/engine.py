@@ -68,6 +68,9 @@ POISON = bool(os.environ.get("S2R_POISON"))   # fill uninitialised activation bu
 
 
 PEER = {"world": 0, "slot": 0}
+# exchange channel of the BN-statistics all-reduce: every rank issues the same sequence of exchanges per channel, so
+# the two streams of steps.AdaptStep use one channel each (set by the step around the passes it issues on stream B)
+COMM_CHANNEL = [0]
 
 
 def init_peer_exchange(group=None, slot=4096):
@@ -212,7 +215,7 @@ class Ctx:
         been set up (init_peer_exchange), NCCL otherwise."""
         if self.world > 1:
             if PEER["world"] == self.world and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= PEER["slot"]:
-                L.call("s2r_allreduce_small_f64", _vp(t), t.numel(), self.stream)
+                L.call("s2r_allreduce_small_f64_ch", _vp(t), t.numel(), COMM_CHANNEL[0], self.stream)
                 return
             import torch.distributed as dist
             dist.all_reduce(t, group=self.group)

@@ -16,7 +16,7 @@ import os
 
 import torch
 
-from .engine import seed_counter, prepack_weights
+from .engine import seed_counter, prepack_weights, PEER, COMM_CHANNEL
 from .functional import softmax_dim0, bce_with_logits, cross_entropy
 from .optim import FusedSGD, FusedAdam
 from .utils.loss import SegmentationLosses, DomainLosses
@@ -162,13 +162,15 @@ class AdaptStep(object):
 
 
 def _adapt_two_streams(self, dev):
-    """The two-stream schedule needs every pass to be free of cross-rank exchanges (the BN peer exchange is a sequence
-    of collective steps that must be issued in the same order on every rank): single process, or no synchronised BN."""
+    """Two streams need two independent sequences of BN-statistics exchanges: single process, no synchronised BN, or the
+    peer-memory exchange with its two channels."""
     if os.environ.get("S2R_OVERLAP", "1") == "0":
         return False
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and getattr(self.model, "_s2r_has_sync_bn", False):
-        return False
+        # with the NVLink peer exchange each stream has its own exchange channel (csrc/comm.cu); NCCL collectives of one
+        # communicator cannot be issued from two streams at once
+        return PEER["world"] == dist.get_world_size()
     return True
 
 
@@ -190,18 +192,22 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
     B.wait_stream(A)                       # BN running statistics: G(src) forward before G(tgt) forward
     for p in model_D.parameters():
         p.requires_grad = False            # train G: no gradients in D (train_adapt.py:140-141)
+    COMM_CHANNEL[0] = 1                    # stream B's BN exchanges form their own sequence
     with torch.cuda.stream(B):
         tgt_output = model(tgt_image)
         D_out = _disc_on_softmax0(model_D, tgt_output)
         loss_adv = bce_with_logits(D_out, self.source_label)
         fwd_B = torch.cuda.Event()
         fwd_B.record(B)
+    COMM_CHANNEL[0] = 0
     loss_seg.backward()                    # on A, beside B's forward
     # the two generator backward passes run one after the other: overlapping them as well (all gradient accumulation
     # is atomic, so it would be legal) measured no gain -- 17.8 ms either way, the GPU is full by then
     B.wait_stream(A)
+    COMM_CHANNEL[0] = 1
     with torch.cuda.stream(B):
         loss_adv.backward()
+    COMM_CHANNEL[0] = 0
     for p in model_D.parameters():
         p.requires_grad = True             # train D (train_adapt.py:158-159)
     src_output = src_output.detach()

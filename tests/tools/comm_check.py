@@ -48,6 +48,25 @@ e0.record()
 for _ in range(50): dist.all_reduce(buf2)
 e1.record(); torch.cuda.synchronize()
 t_nccl = e0.elapsed_time(e1) / 50 * 1e3
+# two channels on two streams at once: every rank issues the same sequence PER CHANNEL, but interleaves the channels
+# differently (rank-dependent delays), as the two streams of steps.AdaptStep do
+sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+a = torch.full((1920,), 1.0, device=dev, dtype=torch.float64)
+b = torch.full((640,), 2.0, device=dev, dtype=torch.float64)
+spin = torch.empty(1 << 22, device=dev)
+torch.cuda.synchronize(); dist.barrier()
+for it in range(40):
+    with torch.cuda.stream(sA):
+        if (it + rank) % 3 == 0: spin.normal_()          # skew the streams against each other
+        L.call("s2r_allreduce_small_f64_ch", C.c_void_p(a.data_ptr()), 1920, 0, C.c_void_p(sA.cuda_stream))
+        a.mul_(1.0 / world)
+    with torch.cuda.stream(sB):
+        if (it + 2 * rank) % 4 == 0: spin.normal_()
+        L.call("s2r_allreduce_small_f64_ch", C.c_void_p(b.data_ptr()), 640, 1, C.c_void_p(sB.cuda_stream))
+        b.mul_(1.0 / world)
+torch.cuda.synchronize()
+if abs(float(a[7]) - 1.0) > 1e-9 or abs(float(b[5]) - 2.0) > 1e-9 or abs(float(a.sum()) - 1920.0) > 1e-6:
+    ok = False; print("rank %d two-channel result %g %g" % (rank, float(a[7]), float(b[5])), flush=True)
 err = L.lib().s2r_comm_error()
 flag = torch.tensor([1 if (ok and err == 0) else 0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
