@@ -209,7 +209,7 @@ def dominant_kernel_roofline(torch, batch, h, w, peaks):
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = flops / t / 1e12
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 8, 512x1024 from the committed
-    # ncu --set full capture (profiles/r2a_conv_tc_decoder_ncu.txt: 161.1 MB read + 95.2 MB written -- part of the
+    # ncu --set full capture (profiles/r1s_conv_tc_decoder_ncu.txt: 161.1 MB read + 95.2 MB written -- part of the
     # 134 MB output is still in the 126 MB L2 when the kernel ends; algorithmic 159 + 134 = 293 MB)
     traffic = 256.3e6 if (batch, h, w) == (8, 512, 1024) else None
     return {"kernel": "tap-GEMM conv fwd 3x3 304->256 (decoder.last_conv.0)", "bound": "tensor", "achieved": ach,
