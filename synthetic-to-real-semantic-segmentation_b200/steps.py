@@ -193,21 +193,25 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
     for p in model_D.parameters():
         p.requires_grad = False            # train G: no gradients in D (train_adapt.py:140-141)
     COMM_CHANNEL[0] = 1                    # stream B's BN exchanges form their own sequence
-    with torch.cuda.stream(B):
-        tgt_output = model(tgt_image)
-        D_out = _disc_on_softmax0(model_D, tgt_output)
-        loss_adv = bce_with_logits(D_out, self.source_label)
-        fwd_B = torch.cuda.Event()
-        fwd_B.record(B)
-    COMM_CHANNEL[0] = 0
+    try:
+        with torch.cuda.stream(B):
+            tgt_output = model(tgt_image)
+            D_out = _disc_on_softmax0(model_D, tgt_output)
+            loss_adv = bce_with_logits(D_out, self.source_label)
+            fwd_B = torch.cuda.Event()
+            fwd_B.record(B)
+    finally:
+        COMM_CHANNEL[0] = 0
     loss_seg.backward()                    # on A, beside B's forward
     # the two generator backward passes run one after the other: overlapping them as well (all gradient accumulation
     # is atomic, so it would be legal) measured no gain -- 17.8 ms either way, the GPU is full by then
     B.wait_stream(A)
     COMM_CHANNEL[0] = 1
-    with torch.cuda.stream(B):
-        loss_adv.backward()
-    COMM_CHANNEL[0] = 0
+    try:
+        with torch.cuda.stream(B):
+            loss_adv.backward()
+    finally:
+        COMM_CHANNEL[0] = 0
     for p in model_D.parameters():
         p.requires_grad = True             # train D (train_adapt.py:158-159)
     src_output = src_output.detach()

@@ -1,6 +1,10 @@
 """Per-call device time of one eager adaptation step (CUDA events around every C-ABI call), aggregated
-by (entry point, shape signature).  GPU box:  python tests/tools/step_profile.py [topN]"""
+by (entry point, shape signature); the step is run on ONE stream (S2R_OVERLAP=0, S2R_WGRAD_STREAM=0) so that the
+per-call times do not overlap.  GPU box:  python tests/tools/step_profile.py [topN]"""
 import collections, os, sys
+# per-call times are only meaningful when the calls do not overlap: one stream, no side-stream weight gradients
+os.environ["S2R_OVERLAP"] = "0"
+os.environ["S2R_WGRAD_STREAM"] = "0"
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
