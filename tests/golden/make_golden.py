@@ -280,6 +280,48 @@ def shapes_case():
     print('shapes ok')
 
 
+def policy_case():
+    """utils/lr_scheduler.py (poly / cos / step, warm-up, 1 and 2+ parameter groups -- the second call also overwrites
+    the discriminator's Adam lr, train_adapt.py:131-133) and SegmentationLosses.FocalLoss (utils/loss.py:32-46) of the
+    reference, on fixed inputs."""
+    import contextlib
+    import io
+    from utils.lr_scheduler import LR_Scheduler as RefSched
+
+    class Opt(object):
+        def __init__(self, n):
+            self.param_groups = [{'lr': -1.0} for _ in range(n)]
+
+    rows = []
+    cfgs = [('poly', 5e-4, 4, 25, 0, 0), ('cos', 1e-3, 3, 10, 0, 0), ('step', 7e-3, 6, 5, 2, 0), ('poly', 2.5e-4, 5, 8, 0, 2)]
+    for ci, (mode, lr, epochs, ipe, lr_step, warm) in enumerate(cfgs):
+        with contextlib.redirect_stdout(io.StringIO()):
+            sch = RefSched(mode, lr, epochs, ipe, lr_step=lr_step, warmup_epochs=warm)
+            for ngroups in (1, 2, 3):
+                for epoch in range(epochs):
+                    for i in range(0, ipe, 3):
+                        o = Opt(ngroups)
+                        sch(o, i, epoch, 0.0)
+                        rows.append([ci, ngroups, epoch, i] + [g['lr'] for g in o.param_groups] + [0.0] * (3 - ngroups))
+    fix = dict(sched_cfgs=np.array([[0 if m == 'poly' else 1 if m == 'cos' else 2, lr, e, ipe, st, w] for m, lr, e, ipe, st, w in cfgs],
+                                   dtype=np.float64), sched_rows=np.array(rows, dtype=np.float64))
+    g = torch.Generator().manual_seed(41)
+    logit = torch.randn(2, 19, 9, 11, generator=g, requires_grad=True)
+    lab = torch.randint(0, 20, (2, 9, 11), generator=g).float()
+    lab[lab == 19] = 255
+    for tag, wgt in (('', None), ('_w', torch.rand(19, generator=g) + 0.5)):
+        logit.grad = None
+        loss = RefSegLoss(weight=wgt).build_loss('focal')(logit, lab)
+        loss.backward()
+        fix['focal_loss' + tag] = np.float64(loss.item())
+        fix['focal_grad' + tag] = logit.grad.numpy().copy()
+        if wgt is not None:
+            fix['focal_weight'] = wgt.numpy()
+    fix['focal_logit'], fix['focal_label'] = logit.detach().numpy(), lab.numpy()
+    np.savez_compressed(os.path.join(HERE, 'policy.npz'), **fix)
+    print('policy fixtures:', len(rows), 'schedule points; focal', fix['focal_loss'], fix['focal_loss_w'])
+
+
 def config1_case():
     """BASELINE.json configs[0] / SURVEY.md section 8(d) config 1: DeepLab('mobilenet', 16, 19).train() under
     torch.manual_seed(1), batch 2x3x513x513 from Generator(0), forward + CE + backward on the CPU (dropout off so the
@@ -306,6 +348,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'config1':
         config1_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'policy':
+        policy_case()
+        sys.exit(0)
     shapes_case()
     evaluator_case()
     discriminator_case()
@@ -314,4 +359,5 @@ if __name__ == '__main__':
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
     config1_case()
+    policy_case()
     print('all golden fixtures written to', HERE)

@@ -673,3 +673,20 @@ def test_prediction_export_and_validation_report(eng):
     assert lines[2] == "Acc:{}, Acc_class:{}, mIoU:{}, fwIoU: {}".format(ev.Pixel_Accuracy(), ev.Pixel_Accuracy_Class(), mIoU,
                                                                         ev.Frequency_Weighted_Intersection_over_Union())
     assert lines[6] == '\troad: \t\t' + str(IoU[0]) and lines[7] == '\tsidewalk: \t' + str(IoU[1]) and len(lines) == 6 + 19 + 1
+
+
+def test_focal_loss_against_reference_fixture(eng):
+    """SegmentationLosses.build_loss('focal') (utils/loss.py:32-46: a scalar transform of the mean cross entropy) --
+    value and gradient against the reference's own output (tests/golden/policy.npz), with and without class weights."""
+    from conftest import golden
+    fix = golden("policy")
+    loss_mod = sub("utils.loss")
+    lab = torch.from_numpy(fix["focal_label"]).cuda()
+    for tag, wgt in (("", None), ("_w", torch.from_numpy(fix["focal_weight"]))):
+        x = torch.from_numpy(fix["focal_logit"]).cuda().requires_grad_(True)
+        loss = loss_mod.SegmentationLosses(weight=wgt).build_loss('focal')(x, lab)
+        loss.backward()
+        assert abs(loss.item() - float(fix["focal_loss" + tag])) <= 1e-5 * abs(float(fix["focal_loss" + tag]))
+        assert rel(x.grad, torch.from_numpy(fix["focal_grad" + tag])) < 1e-5
+    with pytest.raises(NotImplementedError):
+        loss_mod.SegmentationLosses().build_loss('dice')

@@ -209,3 +209,27 @@ def test_input_stage_oracle_and_host_tables_against_reference_fixture():
         b2, kk2 = OI.precompute_coeffs(i, o)
         assert ks == kk2.shape[1] and np.array_equal(b, b2) and np.array_equal(kk, kk2), (i, o)
         assert np.array_equal(dt._nearest_table(i, o), OI.nearest_table(i, o)), (i, o)
+
+
+def test_lr_policy_against_reference_fixture():
+    """utils.lr_scheduler.LR_Scheduler (poly / cos / step, warm-up, lr to group 0 and 10*lr to the others --
+    utils/lr_scheduler.py:43-70, incl. the overwrite of the discriminator's lr at train_adapt.py:133) against the
+    values the reference class produced (tests/golden/policy.npz); unknown modes raise like the reference."""
+    fix = golden("policy")
+    LR = sub("utils.lr_scheduler").LR_Scheduler
+
+    class Opt(object):
+        def __init__(self, n):
+            self.param_groups = [{'lr': -1.0} for _ in range(n)]
+
+    scheds = []
+    for m, lr, e, ipe, st, w in fix["sched_cfgs"]:
+        scheds.append(LR(['poly', 'cos', 'step'][int(m)], float(lr), int(e), int(ipe), lr_step=int(st), warmup_epochs=int(w)))
+    for row in fix["sched_rows"]:
+        ci, ng, epoch, i = (int(v) for v in row[:4])
+        o = Opt(ng)
+        scheds[ci](o, i, epoch, 0.0)
+        assert [g['lr'] for g in o.param_groups] == list(row[4:4 + ng]), (ci, ng, epoch, i)
+    import pytest
+    with pytest.raises((NotImplementedError, TypeError)):
+        LR('linear', 1e-3, 2, 5)(Opt(1), 0, 0)
