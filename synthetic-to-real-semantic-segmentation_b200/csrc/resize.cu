@@ -409,6 +409,84 @@ up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo,
   }
 }
 
+// NHWC bf16 gradient of the align-corners up-sampling, column-stationary: the gather kernel up_nhwc_bwd_kernel walks
+// the ~12 x 12 candidate fine pixels of every coarse pixel and recomputes both interpolation weights for each of them
+// (83 M warp instructions for the ASPP -> decoder x4 gradient: issue-bound at 1.4 TB/s).  Here a thread owns (coarse
+// column, 8-channel group) and walks the fine rows of UCR coarse rows once: per fine row it reduces its <= UKX fine
+// columns with weights held in registers (16-byte loads, 512 contiguous bytes per pixel across the warp), applies the
+// two row weights to rolling accumulators (row k - 1 = hi(interval k - 1) + lo(interval k)) and writes every coarse
+// row as soon as it is complete.  No shared memory, no atomics, deterministic.
+constexpr int UCR = 4;     // coarse rows per CTA of the column-stationary kernel (more CTAs; 1.25x vertical halo reads)
+__global__ void __launch_bounds__(kThreads, 2)
+up_nhwc_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy, int dypitch, int dyoff, int Hi, int Wi, int C, int Ho, int Wo,
+                        __nv_bfloat16* __restrict__ dx, float sh, float sw, int col_chunks) {
+  pdl_wait();      // programmatic dependent launch: see common.cuh
+  pdl_trigger();
+  const int cg = C >> 3, cols = kThreads / cg;
+  const int g = threadIdx.x % cg, col = threadIdx.x / cg;
+  const int ihb = blockIdx.x / col_chunks, cb = blockIdx.x - ihb * col_chunks;
+  const int n = blockIdx.y, ih0 = ihb * UCR;
+  const int iw = cb * cols + col;
+  if (col >= cols || iw >= Wi) return;
+  int wlo, whi;
+  cand_range(iw, sw, Wo, &wlo, &whi);
+  while (wlo < whi && lerp_weight(lerp_src(wlo, sw, Wi), iw) == 0.f) ++wlo;
+  float wx[UKX];
+#pragma unroll
+  for (int k = 0; k < UKX; ++k) wx[k] = wlo + k <= whi ? lerp_weight(lerp_src(wlo + k, sw, Wi), iw) : 0.f;
+  const __nv_bfloat16* base = dy + (long long)n * Ho * Wo * dypitch + dyoff + g * 8 + (long long)wlo * dypitch;
+  __nv_bfloat16* out = dx + (((long long)n * Hi + ih0) * Wi + iw) * C + g * 8;
+  float ph[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ph[i] = 0.f;
+  int ra = ih0 - 1 <= 0 ? 0 : first_fine_row(ih0 - 1, sh, Hi, Ho);
+#pragma unroll 1
+  for (int k = 0; k <= UCR; ++k) {
+    const int ih = ih0 - 1 + k;
+    const int rb = ih + 1 <= 0 ? 0 : (ih + 1 > Hi - 1 ? Ho : first_fine_row(ih + 1, sh, Hi, Ho));
+    float lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lo[i] = 0.f; hi[i] = 0.f; }
+#pragma unroll 2
+    for (int r = ra; r < rb; ++r) {
+      const __nv_bfloat16* rowp = base + (long long)r * Wo * dypitch;
+      uint4 v[UKX];
+#pragma unroll
+      for (int kk = 0; kk < UKX; ++kk) {
+        v[kk] = make_uint4(0, 0, 0, 0);
+        if (wx[kk] != 0.f) v[kk] = ldg16(rowp + (long long)kk * dypitch);
+      }
+      float h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < UKX; ++kk) {
+        if (wx[kk] == 0.f) continue;                 // uniform over the warp (one coarse column per warp when C >= 256)
+        float f[8];
+        bf16x8_to_float(v[kk], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = fmaf(wx[kk], f[i], h[i]);
+      }
+      const Lerp ly = lerp_src(r, sh, Hi);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        lo[i] = fmaf(ly.w0, h[i], lo[i]);
+        hi[i] = fmaf(ly.w1, h[i], hi[i]);
+      }
+    }
+    const bool clamped = ih + 1 > Hi - 1;            // i1 is clamped to the last row: w1 stays on row ih
+    if (k >= 1 && ih0 + k - 1 < Hi) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = ph[i] + lo[i] + (clamped ? hi[i] : 0.f);
+      *reinterpret_cast<uint4*>(out + (long long)(k - 1) * Wi * C) = float_to_bf16x8(o);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ph[i] = clamped ? 0.f : hi[i];
+    ra = rb;
+  }
+}
+
 // ------------------------------------------------------------ global average pool
 // one CTA per (image, 64-channel slab); y[n][c] = mean_p x[n][p][c]
 __global__ void __launch_bounds__(kThreads)
@@ -570,6 +648,24 @@ extern "C" int s2r_upsample_bilinear_nhwc_bwd(const void* dy, int dypitch, int d
   S2R_REQUIRE(C >= 8 && C % 8 == 0 && dypitch % 8 == 0 && dyoff % 8 == 0 && dypitch >= dyoff + C && al16(dy) && al16(dx),
               S2R_ERR_SHAPE, "upsample_bwd: channels/pitch must be multiples of 8 and buffers 16B aligned");
   const long long total = (long long)N * Hi * Wi * (C / 8);
+  {
+    // column-stationary kernel for up-sampling factors up to ~4.4 (at most UKX fine columns per coarse column)
+    const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+    const int cg = C / 8;
+    static int use_cols = -1;
+    if (use_cols < 0) {
+      const char* e = getenv("S2R_UPBWD_NHWC");     // S2R_UPBWD_NHWC=gather keeps the gather kernel (A/B testing)
+      use_cols = (e && e[0] == 'g') ? 0 : 1;
+    }
+    if (use_cols && sw > 0.f && sh > 0.f && 2.f / sw + 1.f <= (float)UKX && cg <= kThreads && N <= 65535) {
+      const int cols = kThreads / cg, col_chunks = s2r_div_up(Wi, cols);
+      dim3 grid(s2r_div_up(Hi, UCR) * col_chunks, N);
+      S2R_CUDA_OK(s2r_launch(up_nhwc_bwd_cols_kernel, grid, dim3(kThreads), (size_t)0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)dy, dypitch, dyoff, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx, sh, sw, col_chunks));
+      S2R_LAUNCH_OK();
+      return S2R_OK;
+    }
+  }
   if (total < (1ll << 32))
     S2R_CUDA_OK(s2r_launch(up_nhwc_bwd_kernel<unsigned>, dim3(s2r_grid(total, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)dy, dypitch, dyoff, N, Hi, Wi, C, Ho, Wo, (__nv_bfloat16*)dx,
