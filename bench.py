@@ -415,6 +415,9 @@ def run_b200(args):
                                "+ FCDiscriminator, src+tgt %dx%d crops, batch %d/GPU, SGD+Adam, random init" % (H, W, B),
                    "pairs_per_step_per_gpu": B, "parallelism": "dp%d" % world, "sync_bn": world > 1,
                    "dropout": not args.no_dropout, "cuda_graph": use_graph,
+                   "streams": "two pass chains (G(src) fwd/bwd + D training | G(tgt) fwd + adversarial bwd) and one "
+                              "weight-gradient side stream per chain, all inside the one graph"
+                              if os.environ.get("S2R_OVERLAP", "1") != "0" else "one",
                    "bn_exchange": ("nvlink peer memory (csrc/comm.cu)" if sub("engine").PEER["world"] == world else "nccl")
                    if world > 1 else "none",
                    "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush",
