@@ -387,14 +387,21 @@ class ValStep(object):
 
     def __init__(self, model, num_class=19):
         self.model = model
-        self.evaluator = Evaluator(num_class)
+        self._evaluator = Evaluator(num_class)
         self.criterion = SegmentationLosses().build_loss('ce')
+
+    @property
+    def evaluator(self):
+        """The Evaluator, with every graph lane ordered before the current stream (so that reading a metric sees all
+        replayed images)."""
+        self.finish()
+        return self._evaluator
 
     @torch.no_grad()
     def __call__(self, image, target, with_loss=False):
         output = self.model(image)
         loss = self.criterion(output, target) if with_loss else None
-        self.evaluator.add_batch_logits(target, output)
+        self._evaluator.add_batch_logits(target, output)
         return loss
 
     @torch.no_grad()
@@ -430,7 +437,7 @@ class ValStep(object):
                     self(*static)
             self._lanes.append((static, graph, stream))
         self._static, self._graph = self._lanes[0][0], self._lanes[0][1]
-        self.evaluator.reset()           # drop the warm-up counts
+        self._evaluator.reset()           # drop the warm-up counts
         return self
 
     @torch.no_grad()
