@@ -247,7 +247,11 @@ def depthwise_roofline(torch, batch, h, w, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     ach = byts / t / 1e9
     return {"kernel": "depthwise 3x3 stride 2 + BN/ReLU6 prologue + statistics, 96 ch 256x512 (features.2)", "bound": "hbm",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
+            # (profiles/r1z_dw_s2_fwd_ncu.txt: 202.7 MB read + 35.8 MB written; algorithmic 201.3 + 50.3 MB -- part of
+            # the output is still in L2 when the kernel ends)
+            "traffic": 238.5e6 if (batch, h, w) == (8, 512, 1024) else None,
             "peak_source": peaks.get("_source", "fallback"), "launch_ms": t * 1e3}
 
 
