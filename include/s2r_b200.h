@@ -213,6 +213,10 @@ int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int N, int Hi,
                                        float* y, int Ho, int Wo, s2r_stream_t stream);
 int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, int C, int Ho, int Wo, void* dx,
                                            int dxpitch, int Hi, int Wi, s2r_stream_t stream);
+/* The same, multiplied by the device scalar *scale (NULL = 1): a mean-reduced loss hands over its unscaled gradient
+ * and the 1/sum-of-weights factor separately (utils/loss.py:21-30 followed by deeplab.py:31's backward). */
+int s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled(const float* dy, int N, int C, int Ho, int Wo, void* dx, int dxpitch,
+                                                  int Hi, int Wi, const float* scale, s2r_stream_t stream);
 int s2r_avgpool_nhwc(const void* x, int N, int HW, int C, int pitch, int coff, float scale,
                      void* y_bf16, float* y_f32, s2r_stream_t stream);
 /* y[n,p,c] (+)= v[n,c]*scale */

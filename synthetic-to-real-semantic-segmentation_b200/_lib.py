@@ -83,6 +83,7 @@ PROTOTYPES = {
     "s2r_upsample_bilinear_nhwc_bwd": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
     "s2r_upsample_bilinear_nhwc_to_nchw": [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp],
     "s2r_upsample_bilinear_nchw_bwd_to_nhwc": [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp],
+    "s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled": [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp],
     "s2r_avgpool_nhwc": [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
     "s2r_broadcast_nhwc": [vp, i32, i32, i32, f32, i32, vp, i32, i32, vp],
     "s2r_nchw_f32_to_nhwc_bf16": [vp, i32, i32, i64, vp, i32, vp],

@@ -169,7 +169,8 @@ up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi
 // dy NCHW fp32 [N,C,Ho,Wo] -> dx NHWC bf16 [N,Hi,Wi,dxpitch]; thread per (n, c, ih, iw)
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int Wo,
-                        __nv_bfloat16* __restrict__ dx, int dxpitch, int Hi, int Wi, float sh, float sw) {
+                        __nv_bfloat16* __restrict__ dx, int dxpitch, int Hi, int Wi, float sh, float sw,
+                        const float* __restrict__ gscale) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
   const long long total = (long long)N * dxpitch * Hi * Wi;
@@ -196,7 +197,7 @@ up_from_nchw_bwd_kernel(const float* __restrict__ dy, int N, int C, int Ho, int 
         }
       }
     }
-    dx[(((long long)n * Hi + ih) * Wi + iw) * dxpitch + c] = __float2bfloat16(acc);
+    dx[(((long long)n * Hi + ih) * Wi + iw) * dxpitch + c] = __float2bfloat16(gscale ? acc * __ldg(gscale) : acc);
   }
 }
 
@@ -223,7 +224,8 @@ __device__ __forceinline__ int first_fine_row(int i, float sh, int Hi, int Ho) {
 
 __global__ void __launch_bounds__(kThreads)
 up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
-                             int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+                             int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max,
+                             const float* __restrict__ gscale) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
   extern __shared__ __align__(16) float rowbuf[];   // [URB][seg_max]
@@ -310,8 +312,9 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
       acc[k - 1] += hi;                              // i1 is clamped to the last row
     }
   }
+  const float gs = gscale ? __ldg(gscale) : 1.f;
   if (col_ok)
-    for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(acc[r]);
+    for (int r = 0; r < UR && ih0 + r < Hi; ++r) out[(long long)r * Wi * dxpitch] = __float2bfloat16(acc[r] * gs);
 }
 
 // Vertical-first variant of the row-staged kernel (used when the rows can be read as float4): the kernel above reduces
@@ -322,7 +325,8 @@ up_from_nchw_bwd_rows_kernel(const float* __restrict__ dy, int C, int Ho, int Wo
 // once per COARSE row.  Same sums, different order.
 __global__ void __launch_bounds__(kThreads, 3)   // <= 85 registers: without the bound ptxas hoists all 54 row loads (255 registers, spills)
 up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx,
-                            int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max) {
+                            int dxpitch, int Hi, int Wi, float sh, float sw, int col_chunks, int seg_max,
+                            const float* __restrict__ gscale) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
   extern __shared__ __align__(16) float rowbuf[];   // [UR][seg_max], skewed like above
@@ -385,6 +389,7 @@ up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo,
   }
   __syncthreads();
   if (!col_ok) return;
+  const float gs = gscale ? __ldg(gscale) : 1.f;   // deferred scale of the loss (mean cross entropy): see functional.py
   int wlo, whi;
   cand_range(iw, sw, Wo, &wlo, &whi);
   while (wlo < whi && lerp_weight(lerp_src(wlo, sw, Wi), iw) == 0.f) ++wlo;
@@ -405,7 +410,7 @@ up_from_nchw_bwd_sep_kernel(const float* __restrict__ dy, int C, int Ho, int Wo,
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < UKX; ++k) v = fmaf(wx[k], row[jj[k]], v);
-    out[(long long)r * Wi * dxpitch] = __float2bfloat16(v);
+    out[(long long)r * Wi * dxpitch] = __float2bfloat16(v * gs);
   }
 }
 
@@ -704,9 +709,21 @@ extern "C" int s2r_upsample_bilinear_nhwc_to_nchw(const void* x, int xpitch, int
   return S2R_OK;
 }
 
+extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled(const float* dy, int N, int C, int Ho, int Wo, void* dx,
+                                                             int dxpitch, int Hi, int Wi, const float* scale,
+                                                             s2r_stream_t stream);
+
 extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, int C, int Ho, int Wo,
                                                       void* dx, int dxpitch, int Hi, int Wi,
                                                       s2r_stream_t stream) {
+  return s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled(dy, N, C, Ho, Wo, dx, dxpitch, Hi, Wi, nullptr, stream);
+}
+
+/* scale: device scalar the result is multiplied by (NULL = 1): lets a loss hand over its UNSCALED gradient and the
+ * 1 / sum-of-weights factor separately instead of making one more pass over the largest tensor of the step. */
+extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled(const float* dy, int N, int C, int Ho, int Wo, void* dx,
+                                                             int dxpitch, int Hi, int Wi, const float* scale,
+                                                             s2r_stream_t stream) {
   S2R_REQUIRE(N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1 && dxpitch >= C, S2R_ERR_SHAPE,
               "upsample_from_nchw_bwd: bad shape");
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
@@ -725,16 +742,16 @@ extern "C" int s2r_upsample_bilinear_nchw_bwd_to_nhwc(const float* dy, int N, in
     const size_t sep_smem = (size_t)UR * seg_max * sizeof(float);
     if (use_sep && Wo % 4 == 0 && ((uintptr_t)dy & 15) == 0 && sep_smem <= 48 * 1024)
       S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_sep_kernel, dim3(grid), dim3(kThreads), (size_t)(sep_smem), (cudaStream_t)stream, 
-          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max));
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max, scale));
     else
       S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_rows_kernel, dim3(grid), dim3(kThreads), (size_t)((size_t)URB * seg_max * sizeof(float)), (cudaStream_t)stream, 
-          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max));
+          dy, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, col_chunks, seg_max, scale));
     S2R_LAUNCH_OK();
     return S2R_OK;
   }
   const long long total = (long long)N * dxpitch * Hi * Wi;
   S2R_CUDA_OK(s2r_launch(up_from_nchw_bwd_kernel, dim3(s2r_grid(total, kThreads, 16)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
-      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw));
+      dy, N, C, Ho, Wo, (__nv_bfloat16*)dx, dxpitch, Hi, Wi, sh, sw, scale));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

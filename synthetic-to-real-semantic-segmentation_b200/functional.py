@@ -47,6 +47,20 @@ def softmax_dim0(x):
     return _SoftmaxDim0.apply(x)
 
 
+# Deferred scaling of the cross-entropy gradient.  The kernel writes the UNSCALED gradient in its forward pass; the mean
+# reduction's factor gout / sum(weights) is normally applied by one more pass over the tensor (the largest of the step:
+# N x 19 x H x W fp32).  Inside the captured training steps, where the only consumer of that gradient is the DeepLab
+# node's up-sampling backward, the factor is handed over as a device scalar instead: the backward registers it under the
+# gradient's address and DeepLabRun.import_grad folds it into its kernel (s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled).
+# Off by default: any other consumer (user code, hooks) sees the fully scaled gradient.
+DEFER_CE_SCALE = [False]
+PENDING_SCALE = {}
+
+
+def pop_pending_scale(t):
+    return PENDING_SCALE.pop(t.data_ptr(), None) if PENDING_SCALE else None
+
+
 class _CrossEntropy(torch.autograd.Function):
     """mean_{valid}(w_t * (lse - x_t)) with ignore_index (nn.CrossEntropyLoss, reduction='mean')."""
 
@@ -82,6 +96,10 @@ class _CrossEntropy(torch.autograd.Function):
         grad, sums = ctx.grad, ctx.sums
         ctx.grad = None
         gout = gout.contiguous().float()
+        if DEFER_CE_SCALE[0]:
+            PENDING_SCALE.clear()          # at most one pending gradient: a stale entry must never meet a recycled address
+            PENDING_SCALE[grad.data_ptr()] = (gout.double() / sums[1]).float().reshape(1)
+            return grad, None, None, None, None, None
         with torch.cuda.device(grad.device):
             L.call("s2r_scale_by_ratio", _vp(grad), grad.numel(), _vp(gout), _vp(sums), 0.0, _stream(grad))
         return grad, None, None, None, None, None

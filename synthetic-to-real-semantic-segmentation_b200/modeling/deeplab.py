@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from ..engine import _vp, round_up
+from ..functional import pop_pending_scale
 from ..runtime import RunBase, call_module
 from .sync_batchnorm import SynchronizedBatchNorm2d
 from .assp import build_aspp, ASPPRun
@@ -45,11 +46,12 @@ class DeepLabRun(RunBase):
         if d is None:
             return None
         N, h, w, Cc, pitch = self.small
+        scale = pop_pending_scale(d)       # a loss that left its mean-reduction factor to this kernel (functional.py)
         d = d.contiguous()
         g = cx.new(N, h, w, pitch)
         g.C = Cc
-        L.call("s2r_upsample_bilinear_nchw_bwd_to_nhwc", _vp(d), N, Cc, d.shape[2], d.shape[3], g.vp(), pitch, h, w,
-               cx.stream)
+        L.call("s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled", _vp(d), N, Cc, d.shape[2], d.shape[3], g.vp(), pitch, h, w,
+               _vp(scale), cx.stream)
         return g
 
     def backward(self, cx, douts, need=None):

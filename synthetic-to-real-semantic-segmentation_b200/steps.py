@@ -17,11 +17,29 @@ import os
 import torch
 
 from .engine import seed_counter, prepack_weights, PEER, COMM_CHANNEL
+from . import functional as _fn
 from .functional import softmax_dim0, bce_with_logits, cross_entropy
 from .optim import FusedSGD, FusedAdam
 from .utils.loss import SegmentationLosses, DomainLosses
 from .utils.lr_scheduler import LR_Scheduler
 from .utils.metrics import Evaluator
+
+
+def _backward_ce_deferred(loss, model):
+    """loss.backward() for a loss whose cross-entropy gradient goes straight into `model`'s (DeepLab) backward: the mean
+    reduction's factor is folded into the up-sampling backward kernel instead of one more pass over the N x 19 x H x W
+    gradient (functional.DEFER_CE_SCALE).  Any other model takes the ordinary path."""
+    if type(model).__name__ != 'DeepLab':
+        loss.backward()
+        return
+    _fn.DEFER_CE_SCALE[0] = True
+    try:
+        loss.backward()
+    finally:
+        _fn.DEFER_CE_SCALE[0] = False
+    if _fn.PENDING_SCALE:
+        _fn.PENDING_SCALE.clear()
+        raise RuntimeError("deferred cross-entropy scale was not consumed by the model's backward")
 
 
 def _disc_on_softmax0(model_D, logits):
@@ -139,7 +157,7 @@ class AdaptStep(object):
                 p.requires_grad = False
             src_output = model(src_image)
             loss_seg = self.criterion(src_output, src_label)
-            loss_seg.backward()
+            _backward_ce_deferred(loss_seg, model)
             tgt_output = model(tgt_image)
             D_out = _disc_on_softmax0(model_D, tgt_output)
             loss_adv = bce_with_logits(D_out, self.source_label)
@@ -202,7 +220,7 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
             fwd_B.record(B)
     finally:
         COMM_CHANNEL[0] = 0
-    loss_seg.backward()                    # on A, beside B's forward
+    _backward_ce_deferred(loss_seg, model)  # on A, beside B's forward
     # the two generator backward passes run one after the other: overlapping them as well (all gradient accumulation
     # is atomic, so it would be legal) measured no gain -- 17.8 ms either way, the GPU is full by then
     B.wait_stream(A)

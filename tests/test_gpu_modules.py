@@ -127,6 +127,41 @@ def test_config1_2x513x513_forward_ce_backward(built_lib):
     assert dev[len(dev) // 2] <= 3.0 and dev[-1] <= 6.0
 
 
+def test_deferred_cross_entropy_scale_matches_scaled_gradient(built_lib):
+    """steps._backward_ce_deferred: the mean-reduction factor of the cross entropy folded into DeepLab's up-sampling
+    backward kernel gives the gradients of the ordinary path (which scales the N x 19 x H x W gradient in a pass of its
+    own) up to bf16 rounding of the first activation gradient; a non-DeepLab consumer takes the ordinary path."""
+    steps = sub("steps")
+    fn = sub("functional")
+    m = make_deeplab().cuda().train()
+    crit = sub("utils.loss").SegmentationLosses().build_loss('ce')
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 64, 96, generator=g).cuda()
+    lab = torch.randint(0, 20, (2, 64, 96), generator=g).float()
+    lab[lab == 19] = 255
+    lab = lab.cuda()
+    grads = []
+    for deferred in (False, True):
+        for p in m.parameters():
+            p.grad = None
+        torch.manual_seed(0)
+        loss = crit(m(x), lab) * 1.7
+        if deferred:
+            steps._backward_ce_deferred(loss, m)
+        else:
+            loss.backward()
+        torch.cuda.synchronize()
+        grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters()})
+    assert not fn.PENDING_SCALE and fn.DEFER_CE_SCALE[0] is False
+    for k in ('decoder.last_conv.8.weight', 'decoder.last_conv.8.bias', 'decoder.last_conv.4.weight', 'aspp.conv1.weight'):
+        assert rel(grads[1][k], grads[0][k]) <= 2e-2, (k, rel(grads[1][k], grads[0][k]))
+    # BatchNorm running statistics moved between the two forwards, so only the layers next to the loss are compared
+    # tightly; everything else must at least have the same scale (a dropped factor would be ~1e4 off)
+    for k in grads[0]:
+        a, b = float(grads[1][k].double().norm()), float(grads[0][k].double().norm())
+        assert 0.2 * b <= a <= 5.0 * b + 1e-12, (k, a, b)
+
+
 def test_deeplab_eval_forward_vs_fixture(built_lib):
     fix = golden('deeplab_eval_1x97x65')
     m = make_deeplab().cuda().eval()
