@@ -265,14 +265,19 @@ softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, in
   const int bc = min(SP_MAXB, B - b0), npx = min(SP_TW, W - w0);
   const long long plane = (long long)H * W;
   const int Wp = W + 2, Hp = H + 2;
-  // pad channels (and everything else) start at zero
-  for (int i = threadIdx.x; i < bc * SP_TW * Cp / 8; i += SP_THREADS) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  const int cpairs = (C + 1) >> 1;
-  for (int it = threadIdx.x; it < cpairs * SP_TW; it += SP_THREADS) {
+  // every channel pair of the padded pixel is written by the loop below (pairs past C as zeros), so the tile needs no
+  // clearing pass
+  const int cpairs = (C + 1) >> 1, ppairs = Cp >> 1;
+  for (int it = threadIdx.x; it < ppairs * SP_TW; it += SP_THREADS) {
     const int w = it & (SP_TW - 1), cp = it / SP_TW;
     if (w >= npx) continue;
     const int c0 = 2 * cp;
+    if (cp >= cpairs) {                     // pad channels
+#pragma unroll
+      for (int b = 0; b < SP_MAXB; ++b)
+        if (b < bc) *reinterpret_cast<uint32_t*>(tile + ((long long)b * SP_TW + w) * Cp + c0) = 0u;
+      continue;
+    }
     const bool has1 = c0 + 1 < C;
     float t0[SP_MAXB], t1[SP_MAXB];
     const float* src = x + ((long long)b0 * C + c0) * plane + (long long)h * W + w0 + w;
