@@ -191,3 +191,115 @@ def dyn_pad(dyn):
     c = dyn.shape[-1]
     p = (8 - c % 8) % 8
     return np.pad(dyn, ((0, 0), (0, 0), (0, 0), (0, p)))
+
+
+def _pack_numpy(w, mode):
+    """numpy restatement of s2r_pack_weight's index maps for the row-tap modes (csrc/conv_mma.cu pack_src):
+    mode 2: [kh][co][kw*Cp + c]; mode 3/4 (ph = mode - 3): [2*ta + tb][pw*Cp + c][co] with (kh, kw) = (ph+2ta, pw+2tb)."""
+    Cout, Cin = w.shape[:2]
+    Cp = (Cin + 7) // 8 * 8
+    if mode == 2:
+        out = np.zeros((4, Cout, 4 * Cp))
+        for kh in range(4):
+            for kw in range(4):
+                out[kh, :, kw * Cp:kw * Cp + Cin] = w[:, :, kh, kw]
+        return out
+    ph = mode - 3
+    out = np.zeros((4, 2 * Cp, Cout))
+    for ta in range(2):
+        for tb in range(2):
+            for pw in range(2):
+                out[2 * ta + tb, pw * Cp:pw * Cp + Cin, :] = w[:, :, ph + 2 * ta, pw + 2 * tb].T
+    return out
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout", [(8, 12, 19, 6), (6, 6, 8, 5)])
+def test_rowtap_views_and_pack_maps_reproduce_conv4x4_s2(H, W, Cin, Cout):
+    """Host logic of the discriminator's row-tap convolution (engine.PadAct / rowtap_*): the four overlapping strided
+    views over the zero-padded NHWC buffer, with the packed-filter index maps, reproduce F.conv2d(k=4, s=2, p=1), its
+    weight gradient and its data gradient (numpy, no GPU)."""
+    eng = sub("engine")
+    L = sub("_lib")
+    rng = np.random.RandomState(H * W + Cin)
+    N = 2
+    Cp = (Cin + 7) // 8 * 8
+    x = rng.randn(N, Cin, H, W)
+    w = rng.randn(Cout, Cin, 4, 4)
+    xt = torch.from_numpy(x).clone().requires_grad_(True)
+    wt = torch.from_numpy(w).clone().requires_grad_(True)
+    yt = F.conv2d(xt, wt, None, 2, 1)
+    dy = rng.randn(*yt.shape)
+    yt.backward(torch.from_numpy(dy))
+    OH, OW = H // 2, W // 2
+    xp = np.zeros((N, H + 2, W + 2, Cp))
+    xp[:, 1:-1, 1:-1, :Cin] = x.transpose(0, 2, 3, 1)
+    mem = xp.reshape(-1)
+
+    class FakePad:
+        ptr = 0
+
+    fp = FakePad()
+    fp.N, fp.H, fp.W, fp.C, fp.Cp = N, H, W, Cin, Cp
+    taps = (L.Tap * 16)()
+    assert eng._rowtap_views(taps, fp) == (OH, OW)
+    # forward and weight gradient through the four views (K = 4*Cp contiguous channels per tap)
+    wp = _pack_numpy(w, 2)
+    out = np.zeros((N, OH, OW, Cout))
+    G = np.zeros((Cout, 4, 4 * Cp))
+    dyn = dy.transpose(0, 2, 3, 1)
+    for t in range(4):
+        assert taps[t].wslice == t and taps[t].wofs == t * 4 * Cp
+        for n in range(N):
+            for oh in range(OH):
+                for ow in range(OW):
+                    v = read_view(mem, taps[t], n, oh, ow, 4 * Cp)
+                    out[n, oh, ow] += wp[t] @ v
+                    G[:, t, :] += np.outer(dyn[n, oh, ow], v)
+    assert np.allclose(out, yt.detach().permute(0, 2, 3, 1).numpy(), atol=1e-9)
+    dw = np.zeros_like(w)                      # s2r_rowtap_wgrad_scatter: w.grad[co][c][kh][kw] += G[co][kh][kw*Cp + c]
+    for kh in range(4):
+        for kw in range(4):
+            dw[:, :, kh, kw] = G[:, kh, kw * Cp:kw * Cp + Cin]
+    assert np.allclose(dw, wt.grad.numpy(), atol=1e-8)
+    # data gradient: one launch per padded-row parity, output "pixel" = two adjacent padded pixels
+    calls = []
+    real_call, real_pack = L.call, eng.packed_weight
+
+    def fake_call(name, *args):
+        a = args[0]._obj
+        calls.append(([(a.taps[i].dh, a.taps[i].dw, a.taps[i].wslice) for i in range(a.ntaps)], a.OH, a.OW, a.out, a.on, a.oh,
+                      a.ow, a.Cout))
+        return 0
+
+    class FakeCx:
+        stream = None
+        device = torch.device("cpu")
+
+    modes = []
+    eng.packed_weight = lambda cx, w_, mode: (modes.append(mode) or torch.zeros(1), 48, 64)
+    L.call = fake_call
+    real_empty = torch.empty
+    try:
+        torch.empty = lambda *a, **k: real_empty(*a, **{kk: vv for kk, vv in k.items() if kk != 'device'})
+        dya = FakeAct(np.ascontiguousarray(dyn_pad(dyn)), 1 << 20)
+        dxp = eng.rowtap_dgrad(FakeCx(), dya, torch.zeros(Cout, Cin, 4, 4), H, W)
+    finally:
+        torch.empty = real_empty
+        L.call, eng.packed_weight = real_call, real_pack
+    assert modes == [3, 4] and len(calls) == 2
+    base = dxp.ptr
+    dxmem = np.zeros((N, H + 2, W + 2, Cp))
+    for ph, (tl, OHc, OWc, outp, on, oh_s, ow_s, nout) in enumerate(calls):
+        wd = _pack_numpy(w, 3 + ph)
+        assert nout == 2 * Cp and (OHc, OWc) == ((H + 2) // 2, (W + 2) // 2)
+        for n in range(N):
+            for i in range(OHc):
+                for j in range(OWc):
+                    acc = np.zeros(2 * Cp)
+                    for dh, dw_, ws in tl:
+                        y, xx = i + dh, j + dw_
+                        if 0 <= y < OH and 0 <= xx < OW:
+                            acc += wd[ws] @ dyn[n, y, xx]
+                    e = (outp - base) // 2 + n * on + i * oh_s + j * ow_s
+                    dxmem.reshape(-1)[e:e + 2 * Cp] += acc
+    assert np.allclose(dxmem[:, 1:-1, 1:-1, :Cin], xt.grad.permute(0, 2, 3, 1).numpy(), atol=1e-8)
