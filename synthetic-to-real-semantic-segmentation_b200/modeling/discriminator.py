@@ -10,7 +10,7 @@ import torch.nn as nn
 import torch
 
 from .. import _lib as L
-from ..engine import (conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up, im2col, patch_weight, Act,
+from ..engine import (conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, round_up, im2col, patch_weight,
                       PadAct, rowtap_ok, rowtap_fwd, rowtap_wgrad, rowtap_dgrad, BF16, _vp)
 from ..runtime import RunBase, call_module
 
