@@ -233,3 +233,24 @@ def test_lr_policy_against_reference_fixture():
     import pytest
     with pytest.raises((NotImplementedError, TypeError)):
         LR('linear', 1e-3, 2, 5)(Opt(1), 0, 0)
+
+
+def test_prediction_export_oracle_against_pillow():
+    """oracle/report.py (test_adapt.py:118-157 after np.argmax) against the same statements executed with Pillow itself:
+    labelId image and palette image, NEAREST-resized."""
+    PIL = __import__("pytest").importorskip("PIL")
+    from PIL import Image
+    from oracle import report as OR
+    rng = np.random.RandomState(5)
+    logits = rng.randn(19, 40, 56).astype(np.float32)
+    logits[4] = logits[9]                               # ties -> lowest index (np.argmax)
+    ids, rgb = OR.imgsaver_arrays(logits, 150, 70)
+    im1 = np.uint8(np.argmax(logits[None], axis=1).transpose(1, 2, 0)).squeeze()
+    im1_np = np.uint8(np.zeros(im1.shape))
+    im2_np = np.uint8(np.zeros(im1.shape + (3,)))
+    for c in range(19):
+        im1_np[im1 == c] = OR.VALID_CLASSES[c]
+        im2_np[im1 == c] = OR.PALETTE[c]
+    want_ids = np.array(Image.fromarray(im1_np, mode='L').resize((150, 70), Image.NEAREST))
+    want_rgb = np.array(Image.fromarray(im2_np).resize((150, 70), Image.NEAREST))
+    assert np.array_equal(ids, want_ids) and np.array_equal(rgb, want_rgb)
