@@ -233,6 +233,35 @@ int s2r_add_bf16(void* a, const void* b, int64_t n, s2r_stream_t stream);
 /* out[c] += (float)sums[c] */
 int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t stream);
 
+/* Batched forms of the three entry points above: one launch per pass for a batch whose samples have different scaled
+ * sizes (every sample draws its own scale).  The job tables live in device memory; a job is one image or label map.
+ * max_elems: the largest output element count among the jobs (sizes the grid). */
+typedef struct s2r_resize_job {
+  const uint8_t* in;
+  uint8_t* out;
+  const int32_t* bounds;
+  const int32_t* kk;
+  int32_t H, W, C, out_size, ksize, flip, axis, _pad;
+} s2r_resize_job;
+typedef struct s2r_nearest_job {
+  const uint8_t* in;
+  uint8_t* out;
+  const int32_t* xtab;
+  const int32_t* ytab;
+  int32_t H, W, OH, OW, flip, _pad;
+} s2r_nearest_job;
+typedef struct s2r_stage_job {
+  const uint8_t* img;   /* u8 [Hs][Ws][3] or NULL */
+  const uint8_t* label; /* u8 [Hs][Ws] or NULL */
+  float* out_img;       /* f32 [3][H][W] */
+  float* out_label;     /* f32 [H][W] */
+  int32_t Hs, Ws, flip, x1, y1, _pad;
+} s2r_stage_job;
+int s2r_resize_bilinear_u8_multi(const s2r_resize_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream);
+int s2r_resize_nearest_u8_multi(const s2r_nearest_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream);
+int s2r_input_stage_u8_multi(const s2r_stage_job* jobs, int njobs, const double* mean, const double* std_,
+                             const uint8_t* lut, int fill_label, int H, int W, s2r_stream_t stream);
+
 /* Prediction export: test_adapt.py:118-157 (imgsaver: trainId -> labelId image and palette image, NEAREST resize to the
  * output size) fused with the host argmax at test_adapt.py:170-171.  logits fp32 [N][C][H][W]; xtab/ytab int32 source
  * index per output column/row (PIL NEAREST tables, -1 = outside); id_table u8 [ntab], rgb_table u8 [ntab][3] (device);

@@ -47,6 +47,21 @@ class PackJob(C.Structure):
                 ("A_pad", i32), ("B_pad", i32), ("begin", i64), ("end", i64)]
 
 
+class ResizeJob(C.Structure):
+    _fields_ = [("inp", vp), ("out", vp), ("bounds", vp), ("kk", vp), ("H", i32), ("W", i32), ("C", i32), ("out_size", i32),
+                ("ksize", i32), ("flip", i32), ("axis", i32), ("_pad", i32)]
+
+
+class NearestJob(C.Structure):
+    _fields_ = [("inp", vp), ("out", vp), ("xtab", vp), ("ytab", vp), ("H", i32), ("W", i32), ("OH", i32), ("OW", i32),
+                ("flip", i32), ("_pad", i32)]
+
+
+class StageJob(C.Structure):
+    _fields_ = [("img", vp), ("label", vp), ("out_img", vp), ("out_label", vp), ("Hs", i32), ("Ws", i32), ("flip", i32),
+                ("x1", i32), ("y1", i32), ("_pad", i32)]
+
+
 class ParamSlot(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("s0", vp), ("s1", vp), ("n", i64), ("lr_mult", f32),
                 ("_pad", f32)]
@@ -62,6 +77,9 @@ PROTOTYPES = {
     "s2r_rowtap_wgrad_scatter": [vp, vp, i32, i32, vp],
     "s2r_resize_bilinear_u8": [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
     "s2r_export_prediction_nchw": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
+    "s2r_resize_bilinear_u8_multi": [vp, i32, i64, vp],
+    "s2r_resize_nearest_u8_multi": [vp, i32, i64, vp],
+    "s2r_input_stage_u8_multi": [vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "s2r_resize_nearest_u8": [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp],
     "s2r_input_stage_u8": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "s2r_wgrad_scatter_taps": [vp, vp, i32, i32, i32, i32, vp],

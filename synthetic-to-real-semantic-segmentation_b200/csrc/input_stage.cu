@@ -126,6 +126,99 @@ input_stage_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ 
   }
 }
 
+
+// ---- batched variants: one launch per pass for a whole batch whose samples have different scaled sizes.  blockIdx.y
+// walks a device table of per-sample jobs (the arithmetic per element is that of the single-sample kernels above).
+__global__ void __launch_bounds__(kThreads)
+resize_multi_kernel(const s2r_resize_job* __restrict__ jobs) {
+  const s2r_resize_job j = jobs[blockIdx.y];
+  const int C = j.C;
+  if (j.axis == 1) {
+    const long long total = (long long)j.H * j.out_size * C;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+      const int c = (int)(i % C);
+      long long q = i / C;
+      const int xx = (int)(q % j.out_size);
+      q /= j.out_size;   // row
+      const int xmin = __ldg(j.bounds + 2 * xx), cnt = __ldg(j.bounds + 2 * xx + 1);
+      const uint8_t* row = j.in + q * (long long)j.W * C + c;
+      const int* k = j.kk + (long long)xx * j.ksize;
+      int acc = 1 << (PRECISION_BITS - 1);
+      for (int x = 0; x < cnt; ++x) {
+        const int sx = j.flip ? (j.W - 1 - (xmin + x)) : (xmin + x);
+        acc += (int)row[(long long)sx * C] * __ldg(k + x);
+      }
+      j.out[i] = clip8(acc);
+    }
+  } else {
+    const int WC = j.W * C;
+    const long long total = (long long)j.out_size * WC;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+      const int x = (int)(i % WC);
+      const int yy = (int)(i / WC);
+      const int ymin = __ldg(j.bounds + 2 * yy), cnt = __ldg(j.bounds + 2 * yy + 1);
+      const uint8_t* col = j.in + (long long)ymin * WC + x;
+      const int* k = j.kk + (long long)yy * j.ksize;
+      int acc = 1 << (PRECISION_BITS - 1);
+      for (int y = 0; y < cnt; ++y) acc += (int)col[(long long)y * WC] * __ldg(k + y);
+      j.out[i] = clip8(acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+nearest_multi_kernel(const s2r_nearest_job* __restrict__ jobs) {
+  const s2r_nearest_job j = jobs[blockIdx.y];
+  const long long total = (long long)j.OH * j.OW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int x = (int)(i % j.OW), y = (int)(i / j.OW);
+    const int sx = __ldg(j.xtab + x), sy = __ldg(j.ytab + y);
+    uint8_t v = 0;
+    if (sx >= 0 && sy >= 0) v = j.in[(long long)sy * j.W + (j.flip ? j.W - 1 - sx : sx)];
+    j.out[i] = v;
+  }
+}
+
+// grid = (ceil(W / kThreads), H, njobs)
+__global__ void __launch_bounds__(kThreads)
+input_stage_multi_kernel(const s2r_stage_job* __restrict__ jobs, NormParams np, const uint8_t* __restrict__ lut,
+                         int fill_label, int H, int W) {
+  __shared__ float tab[3][256];
+  __shared__ float ltab[256];
+  const s2r_stage_job j = jobs[blockIdx.z];
+  for (int i = threadIdx.x; i < 768; i += kThreads) {
+    const int c = i >> 8, u = i & 255;
+    const float v = __fdiv_rn((float)u, 255.0f);
+    const float a = (float)((double)v - np.mean[c]);
+    tab[c][u] = (float)((double)a / np.std[c]);
+  }
+  for (int i = threadIdx.x; i < 256; i += kThreads) ltab[i] = (float)(lut ? lut[i] : (uint8_t)i);
+  __syncthreads();
+  const int x = blockIdx.x * kThreads + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int sy = j.y1 + y, sx0 = j.x1 + x;
+  const bool inside = sy < j.Hs && sx0 < j.Ws;
+  const int sx = j.flip ? j.Ws - 1 - sx0 : sx0;
+  const long long plane = (long long)H * W;
+  const long long o = (long long)y * W + x;
+  if (j.img) {
+    uint8_t r = 0, g = 0, b = 0;
+    if (inside) {
+      const uint8_t* p = j.img + ((long long)sy * j.Ws + sx) * 3;
+      r = p[0]; g = p[1]; b = p[2];
+    }
+    float* oi = j.out_img + o;
+    oi[0] = tab[0][r];
+    oi[plane] = tab[1][g];
+    oi[2 * plane] = tab[2][b];
+  }
+  if (j.label) {
+    float v = (float)fill_label;
+    if (inside) v = ltab[j.label[(long long)sy * j.Ws + sx]];
+    j.out_label[o] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" int s2r_resize_bilinear_u8(const uint8_t* in, int N, int H, int W, int C, int axis, int out_size,
@@ -174,6 +267,44 @@ extern "C" int s2r_input_stage_u8(const uint8_t* img, const uint8_t* label, int 
   dim3 grid(s2r_div_up(W, kThreads), H, N);
   input_stage_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img, label, Hs, Ws, flip, x1, y1, np, lut, fill_label,
                                                                   out_img, out_label, H, W);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_resize_bilinear_u8_multi(const s2r_resize_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535 && max_elems >= 0, S2R_ERR_SHAPE, "resize_bilinear_u8_multi: bad job count");
+  if (njobs == 0 || max_elems == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "resize_bilinear_u8_multi: null table");
+  int gx = s2r_div_up(max_elems, kThreads * 4);
+  if (gx > 4096) gx = 4096;
+  resize_multi_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_resize_nearest_u8_multi(const s2r_nearest_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535 && max_elems >= 0, S2R_ERR_SHAPE, "resize_nearest_u8_multi: bad job count");
+  if (njobs == 0 || max_elems == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "resize_nearest_u8_multi: null table");
+  int gx = s2r_div_up(max_elems, kThreads * 4);
+  if (gx > 4096) gx = 4096;
+  nearest_multi_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_input_stage_u8_multi(const s2r_stage_job* jobs, int njobs, const double* mean, const double* std_,
+                                        const uint8_t* lut, int fill_label, int H, int W, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535 && H >= 1 && W >= 1 && H <= 65535, S2R_ERR_SHAPE, "input_stage_u8_multi: bad shape");
+  if (njobs == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "input_stage_u8_multi: null table");
+  NormParams np;
+  for (int c = 0; c < 3; ++c) {
+    np.mean[c] = mean ? mean[c] : 0.0;
+    np.std[c] = std_ ? std_[c] : 1.0;
+  }
+  input_stage_multi_kernel<<<dim3(s2r_div_up(W, kThreads), H, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, np, lut,
+                                                                                                       fill_label, H, W);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

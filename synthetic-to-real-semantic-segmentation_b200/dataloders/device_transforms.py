@@ -181,7 +181,7 @@ class DeviceTrainTransform(object):
             random.random()
         return flip, short, x1, y1, blur
 
-    def __call__(self, src_image, tgt_image, src_label, draws=None):
+    def __call__(self, src_image, tgt_image, src_label, draws=None, batched=True):
         st_ = self.stage
         st_._check(src_image, 4, "src_image"); st_._check(tgt_image, 4, "tgt_image"); st_._check(src_label, 3, "src_label")
         N, H, W, _ = src_image.shape
@@ -191,21 +191,113 @@ class DeviceTrainTransform(object):
                'tgt_image': torch.empty((N, 3, cs, cs), dtype=torch.float32, device=dev),
                'src_label': torch.empty((N, cs, cs), dtype=torch.float32, device=dev)}
         self.last_draws = []
+        plan = []
+        for n in range(N):
+            d = draws[n] if draws is not None else self.draw(W, H)
+            flip, short, x1, y1 = d[:4]
+            self.last_draws.append(tuple(d))
+            ow, oh = _scale_size(W, H, short)
+            if x1 + cs > max(ow, cs) or y1 + cs > max(oh, cs):
+                raise ValueError("crop window (%d,%d)+%d outside the %dx%d scaled image" % (x1, y1, cs, ow, oh))
+            plan.append((bool(flip), ow, oh, int(x1), int(y1)))
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if batched:
+                self._run_batched(src_image, tgt_image, src_label, plan, out, st)
+                return out
             for n in range(N):
-                d = draws[n] if draws is not None else self.draw(W, H)
-                flip, short, x1, y1 = d[:4]
-                self.last_draws.append(tuple(d))
-                ow, oh = _scale_size(W, H, short)
-                if x1 + cs > max(ow, cs) or y1 + cs > max(oh, cs):
-                    raise ValueError("crop window (%d,%d)+%d outside the %dx%d scaled image" % (x1, y1, cs, ow, oh))
+                flip, ow, oh, x1, y1 = plan[n]
                 for key, t in (('src_image', src_image), ('tgt_image', tgt_image)):
                     im, fl = st_.resize_image(t[n:n + 1], ow, oh, flip, st)
                     st_.finish(im, None, fl, False, x1, y1, out[key][n:n + 1], None, cs, cs, st)
                 lb, fl = st_.resize_label(src_label[n:n + 1], ow, oh, flip, st)
                 st_.finish(None, lb, False, fl, x1, y1, None, out['src_label'][n:n + 1], cs, cs, st, fill=self.fill)
         return out
+
+
+    def _run_batched(self, src_image, tgt_image, src_label, plan, out, st):
+        """Five launches for the whole batch (column pass, row pass, nearest, crop/normalise of images and labels) through
+        device tables of per-sample jobs -- the per-sample path above costs ~9 launches per sample and is launch-bound."""
+        st_ = self.stage
+        N, H, W, _ = src_image.shape
+        dev, cs = src_image.device, self.crop_size
+
+        def upload(jobs):
+            arr = (type(jobs[0]) * len(jobs))(*jobs)
+            return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+
+        def pool(sizes):
+            offs, tot = [], 0
+            for sz in sizes:
+                offs.append(tot)
+                tot += (sz + 15) & ~15
+            return torch.empty(max(tot, 16), dtype=torch.uint8, device=dev), offs
+
+        keep = []
+        images = [(key, t[n].data_ptr(), n) for n in range(N) for key, t in (('src_image', src_image), ('tgt_image', tgt_image))]
+        cur = {}   # (key, n) -> [ptr, Hc, Wc, flip pending]
+        for key, ptr, n in images:
+            cur[(key, n)] = [ptr, H, W, plan[n][0]]
+        # column pass
+        todo = [(key, n) for key, _, n in images if plan[n][1] != W]
+        if todo:
+            buf, offs = pool([H * plan[n][1] * 3 for _, n in todo])
+            keep.append(buf)
+            jobs, mx = [], 0
+            for (key, n), off in zip(todo, offs):
+                ow = plan[n][1]
+                b, kk, ks = st_._dev(("bl", W, ow), lambda W=W, ow=ow: _bilinear_tables(W, ow), dev)
+                c = cur[(key, n)]
+                jobs.append(L.ResizeJob(c[0], buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), H, W, 3, ow, ks, int(c[3]), 1, 0))
+                cur[(key, n)] = [buf.data_ptr() + off, H, ow, False]
+                mx = max(mx, H * ow * 3)
+            tab = upload(jobs); keep.append(tab)
+            L.call("s2r_resize_bilinear_u8_multi", tab.data_ptr(), len(jobs), mx, st)
+        # row pass
+        todo = [(key, n) for key, _, n in images if plan[n][2] != H]
+        if todo:
+            buf, offs = pool([plan[n][2] * cur[(key, n)][2] * 3 for key, n in todo])
+            keep.append(buf)
+            jobs, mx = [], 0
+            for (key, n), off in zip(todo, offs):
+                oh = plan[n][2]
+                b, kk, ks = st_._dev(("bl", H, oh), lambda H=H, oh=oh: _bilinear_tables(H, oh), dev)
+                c = cur[(key, n)]
+                jobs.append(L.ResizeJob(c[0], buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), H, c[2], 3, oh, ks, 0, 0, 0))
+                cur[(key, n)] = [buf.data_ptr() + off, oh, c[2], c[3]]
+                mx = max(mx, oh * c[2] * 3)
+            tab = upload(jobs); keep.append(tab)
+            L.call("s2r_resize_bilinear_u8_multi", tab.data_ptr(), len(jobs), mx, st)
+        # labels: nearest
+        lab = {n: [src_label[n].data_ptr(), H, W, plan[n][0]] for n in range(N)}
+        todo = [n for n in range(N) if (plan[n][1], plan[n][2]) != (W, H)]
+        if todo:
+            buf, offs = pool([plan[n][1] * plan[n][2] for n in todo])
+            keep.append(buf)
+            jobs, mx = [], 0
+            for n, off in zip(todo, offs):
+                ow, oh = plan[n][1], plan[n][2]
+                (xt,) = st_._dev(("nn", W, ow), lambda W=W, ow=ow: (_nearest_table(W, ow),), dev)
+                (yt,) = st_._dev(("nn", H, oh), lambda H=H, oh=oh: (_nearest_table(H, oh),), dev)
+                jobs.append(L.NearestJob(lab[n][0], buf.data_ptr() + off, xt.data_ptr(), yt.data_ptr(), H, W, oh, ow,
+                                         int(lab[n][3]), 0))
+                lab[n] = [buf.data_ptr() + off, oh, ow, False]
+                mx = max(mx, oh * ow)
+            tab = upload(jobs); keep.append(tab)
+            L.call("s2r_resize_nearest_u8_multi", tab.data_ptr(), len(jobs), mx, st)
+        # crop window + Normalize/ToTensor (images) and the labelId table (labels): one launch
+        jobs = []
+        for key, _, n in images:
+            c = cur[(key, n)]
+            jobs.append(L.StageJob(c[0], None, out[key][n].data_ptr(), None, c[1], c[2], int(c[3]), plan[n][3], plan[n][4], 0))
+        for n in range(N):
+            c = lab[n]
+            jobs.append(L.StageJob(None, c[0], None, out['src_label'][n].data_ptr(), c[1], c[2], int(c[3]), plan[n][3],
+                                   plan[n][4], 0))
+        tab = upload(jobs); keep.append(tab)
+        L.call("s2r_input_stage_u8_multi", tab.data_ptr(), len(jobs), C.cast(st_.mean, C.c_void_p), C.cast(st_.std, C.c_void_p),
+               st_.lut(dev).data_ptr(), int(self.fill), cs, cs, st)
+        return keep
 
 
 class DeviceValTransform(object):

@@ -603,6 +603,23 @@ def test_device_input_stage_bit_exact_against_reference_fixture(eng):
         assert np.array_equal(out['src_image'][0].cpu().numpy(), fix[k + "_out_src"]), k
         assert np.array_equal(out['tgt_image'][0].cpu().numpy(), fix[k + "_out_tgt"]), k
         assert np.array_equal(out['src_label'][0].cpu().numpy(), fix[k + "_out_lab"]), k
+    # the same cases two samples at a time (different flip / scale / window per sample), through the batched launches
+    # and through the per-sample launches
+    names = [str(k) for k in fix["cases"]]
+    for a, b in zip(names[0::2], names[1::2]):
+        da, db = [int(v) for v in fix[a + "_draw"]], [int(v) for v in fix[b + "_draw"]]
+        assert da[2] == db[2] and fix[a + "_src"].shape == fix[b + "_src"].shape
+        tr = dt.DeviceTrainTransform(base_size=1, crop_size=da[2])
+        src = torch.from_numpy(np.stack([fix[a + "_src"], fix[b + "_src"]])).cuda()
+        tgt = torch.from_numpy(np.stack([fix[a + "_tgt"], fix[b + "_tgt"]])).cuda()
+        lab = torch.from_numpy(np.stack([fix[a + "_lab"], fix[b + "_lab"]])).cuda()
+        draws = [(bool(da[0]), da[1], da[3], da[4]), (bool(db[0]), db[1], db[3], db[4])]
+        for batched in (True, False):
+            out = tr(src, tgt, lab, draws=draws, batched=batched)
+            for n, k in enumerate((a, b)):
+                assert np.array_equal(out['src_image'][n].cpu().numpy(), fix[k + "_out_src"]), (k, batched)
+                assert np.array_equal(out['tgt_image'][n].cpu().numpy(), fix[k + "_out_tgt"]), (k, batched)
+                assert np.array_equal(out['src_label'][n].cpu().numpy(), fix[k + "_out_lab"]), (k, batched)
     s = int(fix["val_size"][0])
     va = dt.DeviceValTransform(s)
     img = torch.from_numpy(np.stack([fix["val_img"]] * 2)).cuda()

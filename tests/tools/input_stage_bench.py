@@ -29,8 +29,17 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 in_bytes = N * H * W * 7
-print("device input stage: %.2f ms per batch of %d pairs (%.0f pairs/s), %.1f GB/s of source bytes; draws %s"
+print("device input stage (batched launches): %.2f ms per batch of %d pairs (%.0f pairs/s), %.1f GB/s of source bytes; draws %s"
       % (ms, N, N / ms * 1e3, in_bytes / ms / 1e6, draws[:2]))
+for _ in range(2):
+    tr(d_src, d_tgt, d_lab, draws=draws, batched=False)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(5):
+    out1 = tr(d_src, d_tgt, d_lab, draws=draws, batched=False)
+e1.record(); torch.cuda.synchronize()
+print("device input stage (per-sample launches): %.2f ms per batch; identical to the batched result: %s"
+      % (e0.elapsed_time(e1) / 5, all(torch.equal(out[k], out1[k]) for k in out)))
 
 # the same arithmetic on the host through Pillow (one core), sample 0..N-1
 from PIL import Image, ImageOps
