@@ -234,21 +234,26 @@ int s2r_add_bf16(void* a, const void* b, int64_t n, s2r_stream_t stream);
 int s2r_add_f64_to_f32(const double* sums, float* out, int n, s2r_stream_t stream);
 
 /* Batched forms of the three entry points above: one launch per pass for a batch whose samples have different scaled
- * sizes (every sample draws its own scale).  The job tables live in device memory; a job is one image or label map.
+ * sizes (every sample draws its own scale).  The job tables live in device memory; a job is one image or label map, and
+ * the resampling jobs produce only the window of the scaled image that the crop keeps.
  * max_elems: the largest output element count among the jobs (sizes the grid). */
 typedef struct s2r_resize_job {
-  const uint8_t* in;
-  uint8_t* out;
-  const int32_t* bounds;
+  const uint8_t* in;     /* axis 1: first needed source row; axis 0: byte 0 (first window column) of source row `base` */
+  uint8_t* out;          /* axis 1: [lines][on][C]; axis 0: [on][lines] */
+  const int32_t* bounds; /* tables of the WHOLE axis (s2r_resize_bilinear_u8) */
   const int32_t* kk;
-  int32_t H, W, C, out_size, ksize, flip, axis, _pad;
+  int32_t W, C, ksize, flip, axis; /* W, flip: axis 1 only (source width, mirror) */
+  int32_t o0, on;        /* window [o0, o0 + on) of the resampled axis */
+  int32_t lines;         /* axis 1: source rows; axis 0: bytes per output row */
+  int32_t in_pitch;      /* bytes between input rows */
+  int32_t base;          /* axis 0: source row index `in` points at */
 } s2r_resize_job;
 typedef struct s2r_nearest_job {
   const uint8_t* in;
-  uint8_t* out;
+  uint8_t* out;          /* [OH][OW]: window [y0, y0 + OH) x [x0, x0 + OW) of the resized map */
   const int32_t* xtab;
   const int32_t* ytab;
-  int32_t H, W, OH, OW, flip, _pad;
+  int32_t W, OH, OW, x0, y0, flip;
 } s2r_nearest_job;
 typedef struct s2r_stage_job {
   const uint8_t* img;   /* u8 [Hs][Ws][3] or NULL */

@@ -48,13 +48,13 @@ class PackJob(C.Structure):
 
 
 class ResizeJob(C.Structure):
-    _fields_ = [("inp", vp), ("out", vp), ("bounds", vp), ("kk", vp), ("H", i32), ("W", i32), ("C", i32), ("out_size", i32),
-                ("ksize", i32), ("flip", i32), ("axis", i32), ("_pad", i32)]
+    _fields_ = [("inp", vp), ("out", vp), ("bounds", vp), ("kk", vp), ("W", i32), ("C", i32), ("ksize", i32), ("flip", i32),
+                ("axis", i32), ("o0", i32), ("on", i32), ("lines", i32), ("in_pitch", i32), ("base", i32)]
 
 
 class NearestJob(C.Structure):
-    _fields_ = [("inp", vp), ("out", vp), ("xtab", vp), ("ytab", vp), ("H", i32), ("W", i32), ("OH", i32), ("OW", i32),
-                ("flip", i32), ("_pad", i32)]
+    _fields_ = [("inp", vp), ("out", vp), ("xtab", vp), ("ytab", vp), ("W", i32), ("OH", i32), ("OW", i32), ("x0", i32),
+                ("y0", i32), ("flip", i32)]
 
 
 class StageJob(C.Structure):

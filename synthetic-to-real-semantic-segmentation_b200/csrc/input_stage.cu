@@ -131,17 +131,20 @@ input_stage_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ 
 // walks a device table of per-sample jobs (the arithmetic per element is that of the single-sample kernels above).
 __global__ void __launch_bounds__(kThreads)
 resize_multi_kernel(const s2r_resize_job* __restrict__ jobs) {
+  // A job produces the WINDOW [o0, o0 + on) of the resampled axis for `lines` lines of the other axis (only the crop
+  // window of the scaled image is ever used); in points at line 0 / source index `base` of the job's input.
   const s2r_resize_job j = jobs[blockIdx.y];
   const int C = j.C;
   if (j.axis == 1) {
-    const long long total = (long long)j.H * j.out_size * C;
+    // columns: in = first needed source row, rows of W*C bytes; out [lines][on][C]
+    const long long total = (long long)j.lines * j.on * C;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
       const int c = (int)(i % C);
       long long q = i / C;
-      const int xx = (int)(q % j.out_size);
-      q /= j.out_size;   // row
+      const int xx = j.o0 + (int)(q % j.on);
+      q /= j.on;   // line (source row relative to in)
       const int xmin = __ldg(j.bounds + 2 * xx), cnt = __ldg(j.bounds + 2 * xx + 1);
-      const uint8_t* row = j.in + q * (long long)j.W * C + c;
+      const uint8_t* row = j.in + q * (long long)j.in_pitch + c;
       const int* k = j.kk + (long long)xx * j.ksize;
       int acc = 1 << (PRECISION_BITS - 1);
       for (int x = 0; x < cnt; ++x) {
@@ -151,16 +154,16 @@ resize_multi_kernel(const s2r_resize_job* __restrict__ jobs) {
       j.out[i] = clip8(acc);
     }
   } else {
-    const int WC = j.W * C;
-    const long long total = (long long)j.out_size * WC;
+    // rows: in = byte 0 of source row `base`, lines = bytes per output row (window columns * C); out [on][lines]
+    const long long total = (long long)j.on * j.lines;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-      const int x = (int)(i % WC);
-      const int yy = (int)(i / WC);
+      const int x = (int)(i % j.lines);
+      const int yy = j.o0 + (int)(i / j.lines);
       const int ymin = __ldg(j.bounds + 2 * yy), cnt = __ldg(j.bounds + 2 * yy + 1);
-      const uint8_t* col = j.in + (long long)ymin * WC + x;
+      const uint8_t* col = j.in + (long long)(ymin - j.base) * j.in_pitch + x;
       const int* k = j.kk + (long long)yy * j.ksize;
       int acc = 1 << (PRECISION_BITS - 1);
-      for (int y = 0; y < cnt; ++y) acc += (int)col[(long long)y * WC] * __ldg(k + y);
+      for (int y = 0; y < cnt; ++y) acc += (int)col[(long long)y * j.in_pitch] * __ldg(k + y);
       j.out[i] = clip8(acc);
     }
   }
@@ -168,11 +171,12 @@ resize_multi_kernel(const s2r_resize_job* __restrict__ jobs) {
 
 __global__ void __launch_bounds__(kThreads)
 nearest_multi_kernel(const s2r_nearest_job* __restrict__ jobs) {
+  // window [y0, y0 + OH) x [x0, x0 + OW) of the resized label map
   const s2r_nearest_job j = jobs[blockIdx.y];
   const long long total = (long long)j.OH * j.OW;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int x = (int)(i % j.OW), y = (int)(i / j.OW);
-    const int sx = __ldg(j.xtab + x), sy = __ldg(j.ytab + y);
+    const int sx = __ldg(j.xtab + j.x0 + x), sy = __ldg(j.ytab + j.y0 + y);
     uint8_t v = 0;
     if (sx >= 0 && sy >= 0) v = j.in[(long long)sy * j.W + (j.flip ? j.W - 1 - sx : sx)];
     j.out[i] = v;

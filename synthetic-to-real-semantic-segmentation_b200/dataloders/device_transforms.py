@@ -216,8 +216,10 @@ class DeviceTrainTransform(object):
 
 
     def _run_batched(self, src_image, tgt_image, src_label, plan, out, st):
-        """Five launches for the whole batch (column pass, row pass, nearest, crop/normalise of images and labels) through
-        device tables of per-sample jobs -- the per-sample path above costs ~9 launches per sample and is launch-bound."""
+        """At most four launches for the whole batch (column pass, row pass, nearest, crop/normalise) through device
+        tables of per-sample jobs, and only the WINDOW of every scaled image that its crop keeps is resampled: the
+        column pass produces the window's columns for the source rows the row pass will read, the row pass the
+        window's rows.  Same arithmetic per byte as the per-sample path (bit-identical)."""
         st_ = self.stage
         N, H, W, _ = src_image.shape
         dev, cs = src_image.device, self.crop_size
@@ -233,67 +235,108 @@ class DeviceTrainTransform(object):
                 tot += (sz + 15) & ~15
             return torch.empty(max(tot, 16), dtype=torch.uint8, device=dev), offs
 
+        def tables(a, b):
+            """(device bounds, device coefficients, ksize, host bounds) of the bilinear resampling a -> b"""
+            key = ("blh", a, b)
+            ent = st_._tables.get((key, dev))
+            if ent is None:
+                bnd, kk, ks = _bilinear_tables(a, b)
+                ent = (torch.from_numpy(bnd).to(dev), torch.from_numpy(kk).to(dev), ks, bnd)
+                if len(st_._tables) > 64:
+                    st_._tables.clear()
+                st_._tables[(key, dev)] = ent
+            return ent
+
         keep = []
+        win = []      # per sample: window (cx0, cx1, cy0, cy1) in scaled coordinates and the source rows [r0, r1) it needs
+        for flip, ow, oh, x1, y1 in plan:
+            cx0, cx1, cy0, cy1 = x1, min(x1 + cs, ow), y1, min(y1 + cs, oh)
+            if oh != H:
+                bv = tables(H, oh)[3]
+                r0, r1 = int(bv[cy0][0]), int(bv[cy1 - 1][0] + bv[cy1 - 1][1])
+            else:
+                r0, r1 = cy0, cy1
+            win.append((cx0, cx1, cy0, cy1, r0, r1))
         images = [(key, t[n].data_ptr(), n) for n in range(N) for key, t in (('src_image', src_image), ('tgt_image', tgt_image))]
-        cur = {}   # (key, n) -> [ptr, Hc, Wc, flip pending]
+        # per image: [pointer to (row r0, first window column), row pitch in bytes, mirror still pending, windowed?]
+        cur = {}
         for key, ptr, n in images:
-            cur[(key, n)] = [ptr, H, W, plan[n][0]]
+            flip, ow, oh, x1, y1 = plan[n]
+            cx0, cx1, cy0, cy1, r0, r1 = win[n]
+            coloff = (W - cx1) if flip else cx0          # without a column pass the window is cut from the source columns
+            cur[(key, n)] = [ptr + (r0 * W + coloff) * 3, W * 3, flip, False]
         # column pass
-        todo = [(key, n) for key, _, n in images if plan[n][1] != W]
+        todo = [(key, ptr, n) for key, ptr, n in images if plan[n][1] != W]
         if todo:
-            buf, offs = pool([H * plan[n][1] * 3 for _, n in todo])
+            buf, offs = pool([(win[n][5] - win[n][4]) * (win[n][1] - win[n][0]) * 3 for _, _, n in todo])
             keep.append(buf)
             jobs, mx = [], 0
-            for (key, n), off in zip(todo, offs):
-                ow = plan[n][1]
-                b, kk, ks = st_._dev(("bl", W, ow), lambda W=W, ow=ow: _bilinear_tables(W, ow), dev)
-                c = cur[(key, n)]
-                jobs.append(L.ResizeJob(c[0], buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), H, W, 3, ow, ks, int(c[3]), 1, 0))
-                cur[(key, n)] = [buf.data_ptr() + off, H, ow, False]
-                mx = max(mx, H * ow * 3)
+            for (key, ptr, n), off in zip(todo, offs):
+                flip, ow = plan[n][0], plan[n][1]
+                cx0, cx1, cy0, cy1, r0, r1 = win[n]
+                b, kk, ks, _ = tables(W, ow)
+                ww, lines = cx1 - cx0, r1 - r0
+                jobs.append(L.ResizeJob(ptr + r0 * W * 3, buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), W, 3, ks, int(flip), 1,
+                                        cx0, ww, lines, W * 3, 0))
+                cur[(key, n)] = [buf.data_ptr() + off, ww * 3, False, True]
+                mx = max(mx, lines * ww * 3)
             tab = upload(jobs); keep.append(tab)
             L.call("s2r_resize_bilinear_u8_multi", tab.data_ptr(), len(jobs), mx, st)
         # row pass
         todo = [(key, n) for key, _, n in images if plan[n][2] != H]
         if todo:
-            buf, offs = pool([plan[n][2] * cur[(key, n)][2] * 3 for key, n in todo])
+            buf, offs = pool([(win[n][3] - win[n][2]) * (win[n][1] - win[n][0]) * 3 for _, n in todo])
             keep.append(buf)
             jobs, mx = [], 0
             for (key, n), off in zip(todo, offs):
                 oh = plan[n][2]
-                b, kk, ks = st_._dev(("bl", H, oh), lambda H=H, oh=oh: _bilinear_tables(H, oh), dev)
+                cx0, cx1, cy0, cy1, r0, r1 = win[n]
+                b, kk, ks, _ = tables(H, oh)
                 c = cur[(key, n)]
-                jobs.append(L.ResizeJob(c[0], buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), H, c[2], 3, oh, ks, 0, 0, 0))
-                cur[(key, n)] = [buf.data_ptr() + off, oh, c[2], c[3]]
-                mx = max(mx, oh * c[2] * 3)
+                ww, wh = cx1 - cx0, cy1 - cy0
+                jobs.append(L.ResizeJob(c[0], buf.data_ptr() + off, b.data_ptr(), kk.data_ptr(), 0, 3, ks, 0, 0,
+                                        cy0, wh, ww * 3, c[1], r0))
+                cur[(key, n)] = [buf.data_ptr() + off, ww * 3, c[2], True]
+                mx = max(mx, wh * ww * 3)
             tab = upload(jobs); keep.append(tab)
             L.call("s2r_resize_bilinear_u8_multi", tab.data_ptr(), len(jobs), mx, st)
-        # labels: nearest
-        lab = {n: [src_label[n].data_ptr(), H, W, plan[n][0]] for n in range(N)}
+        # labels: nearest, window only
+        lab = {}
         todo = [n for n in range(N) if (plan[n][1], plan[n][2]) != (W, H)]
         if todo:
-            buf, offs = pool([plan[n][1] * plan[n][2] for n in todo])
+            buf, offs = pool([(win[n][3] - win[n][2]) * (win[n][1] - win[n][0]) for n in todo])
             keep.append(buf)
             jobs, mx = [], 0
             for n, off in zip(todo, offs):
-                ow, oh = plan[n][1], plan[n][2]
+                flip, ow, oh = plan[n][0], plan[n][1], plan[n][2]
+                cx0, cx1, cy0, cy1, r0, r1 = win[n]
                 (xt,) = st_._dev(("nn", W, ow), lambda W=W, ow=ow: (_nearest_table(W, ow),), dev)
                 (yt,) = st_._dev(("nn", H, oh), lambda H=H, oh=oh: (_nearest_table(H, oh),), dev)
-                jobs.append(L.NearestJob(lab[n][0], buf.data_ptr() + off, xt.data_ptr(), yt.data_ptr(), H, W, oh, ow,
-                                         int(lab[n][3]), 0))
-                lab[n] = [buf.data_ptr() + off, oh, ow, False]
-                mx = max(mx, oh * ow)
+                jobs.append(L.NearestJob(src_label[n].data_ptr(), buf.data_ptr() + off, xt.data_ptr(), yt.data_ptr(), W,
+                                         cy1 - cy0, cx1 - cx0, cx0, cy0, int(flip)))
+                lab[n] = buf.data_ptr() + off
+                mx = max(mx, (cy1 - cy0) * (cx1 - cx0))
             tab = upload(jobs); keep.append(tab)
             L.call("s2r_resize_nearest_u8_multi", tab.data_ptr(), len(jobs), mx, st)
-        # crop window + Normalize/ToTensor (images) and the labelId table (labels): one launch
+        # crop window + Normalize/ToTensor (images) and the labelId table (labels): one launch.  A resampled image is
+        # already cut to its window (origin 0, 0); an image that was not resampled at all is read in place.
         jobs = []
-        for key, _, n in images:
+        for key, ptr, n in images:
+            flip, ow, oh, x1, y1 = plan[n]
+            cx0, cx1, cy0, cy1, r0, r1 = win[n]
             c = cur[(key, n)]
-            jobs.append(L.StageJob(c[0], None, out[key][n].data_ptr(), None, c[1], c[2], int(c[3]), plan[n][3], plan[n][4], 0))
+            if c[3]:
+                jobs.append(L.StageJob(c[0], None, out[key][n].data_ptr(), None, cy1 - cy0, cx1 - cx0, int(c[2]), 0, 0, 0))
+            else:
+                jobs.append(L.StageJob(ptr, None, out[key][n].data_ptr(), None, H, W, int(flip), x1, y1, 0))
         for n in range(N):
-            c = lab[n]
-            jobs.append(L.StageJob(None, c[0], None, out['src_label'][n].data_ptr(), c[1], c[2], int(c[3]), plan[n][3],
-                                   plan[n][4], 0))
+            flip, ow, oh, x1, y1 = plan[n]
+            cx0, cx1, cy0, cy1, r0, r1 = win[n]
+            if n in lab:
+                jobs.append(L.StageJob(None, lab[n], None, out['src_label'][n].data_ptr(), cy1 - cy0, cx1 - cx0, 0, 0, 0, 0))
+            else:
+                jobs.append(L.StageJob(None, src_label[n].data_ptr(), None, out['src_label'][n].data_ptr(), H, W, int(flip),
+                                       x1, y1, 0))
         tab = upload(jobs); keep.append(tab)
         L.call("s2r_input_stage_u8_multi", tab.data_ptr(), len(jobs), C.cast(st_.mean, C.c_void_p), C.cast(st_.std, C.c_void_p),
                st_.lut(dev).data_ptr(), int(self.fill), cs, cs, st)

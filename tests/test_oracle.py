@@ -254,3 +254,13 @@ def test_prediction_export_oracle_against_pillow():
     want_ids = np.array(Image.fromarray(im1_np, mode='L').resize((150, 70), Image.NEAREST))
     want_rgb = np.array(Image.fromarray(im2_np).resize((150, 70), Image.NEAREST))
     assert np.array_equal(ids, want_ids) and np.array_equal(rgb, want_rgb)
+
+
+def test_batched_input_stage_host_planning_with_emulated_kernels():
+    """The REAL host planning of the batched device input stage (window of the scaled image per sample, job tables for
+    the column / row / nearest / crop launches) driven through a pure-Python emulation of the kernels reproduces the
+    reference's tensors (tests/tools/emul_input_stage.py; no GPU)."""
+    import sys as _sys
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tests", "tools", "emul_input_stage.py")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), r.stdout[-2000:] + r.stderr[-2000:]
