@@ -262,6 +262,21 @@ typedef struct s2r_stage_job {
   float* out_label;     /* f32 [H][W] */
   int32_t Hs, Ws, flip, x1, y1, _pad;
 } s2r_stage_job;
+/* RandomGaussianBlur (dataloders/custom_transforms.py:92-105): PIL's ImageFilter.GaussianBlur(radius) applied to the
+ * H x W crop.  A job cuts its crop from img exactly as s2r_stage_job does (mirror, window origin (x1, y1), zero padding
+ * on the right / bottom) and writes the blurred crop as u8 [H][W][3] (then fed to s2r_input_stage_u8_multi as an
+ * H x W image).  PIL runs three box-blur passes per axis (libImaging/BoxBlur.c); ww / fw are that file's 24-bit weights
+ * of the centre pixel and of its two neighbours, computed by the caller in single precision as ImagingHorizontalBoxBlur
+ * does.  Only box radii with integer part 0 (GaussianBlur radius < 1.41; the reference draws [0, 1)) are supported:
+ * the caller rejects larger ones.  Two launches (row passes into tmp, column passes into out). */
+typedef struct s2r_blur_job {
+  const uint8_t* img;   /* u8 [Hs][Ws][3] */
+  uint8_t* tmp;         /* u8 [H][W][3] scratch */
+  uint8_t* out;         /* u8 [H][W][3] */
+  int32_t Hs, Ws, flip, x1, y1;
+  uint32_t ww, fw, _pad;
+} s2r_blur_job;
+int s2r_gaussian_blur3_u8_multi(const s2r_blur_job* jobs, int njobs, int H, int W, s2r_stream_t stream);
 int s2r_resize_bilinear_u8_multi(const s2r_resize_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream);
 int s2r_resize_nearest_u8_multi(const s2r_nearest_job* jobs, int njobs, int64_t max_elems, s2r_stream_t stream);
 int s2r_input_stage_u8_multi(const s2r_stage_job* jobs, int njobs, const double* mean, const double* std_,

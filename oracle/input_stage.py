@@ -5,6 +5,7 @@
   dataloders/custom_transforms.py:59-71           RandomHorizontalFlip
   dataloders/custom_transforms.py:108-147         RandomScaleCrop  (resize, pad right/bottom, crop window)
   dataloders/custom_transforms.py:150-176         FixScaleCrop
+  dataloders/custom_transforms.py:92-105          RandomGaussianBlur (PIL ImageFilter.GaussianBlur)
   dataloders/custom_transforms.py:17-33           Normalize
   dataloders/custom_transforms.py:36-56           ToTensor (HWC -> CHW float32)
 
@@ -12,7 +13,9 @@ The reference does the geometry on PIL images; the resampling arithmetic therefo
 vendored; pinned here against Pillow 12.2.0 as installed in the build container, algorithm unchanged since 4.x):
 `Image.resize(BILINEAR)` is the two-pass fixed-point convolution of libImaging/Resample.c (22-bit coefficients, uint8
 intermediate), `Image.resize(NEAREST)` the incremental-coordinate copy of libImaging/Geometry.c (ImagingScaleAffine).
-Both are restated below and pinned by tests/golden/make_golden_input.py, which runs the REAL reference classes on PIL
+`Image.filter(GaussianBlur(radius))` is three passes of the fractional-radius box blur of libImaging/BoxBlur.c per axis
+(24-bit fixed-point weights derived in single precision, uint8 intermediate after every pass, edge pixels replicated).
+All are restated below and pinned by tests/golden/make_golden_input.py, which runs the REAL reference classes on PIL
 images and stores their outputs (tests/golden/input_stage.npz).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.
@@ -149,6 +152,89 @@ def resize_nearest(mask_u8, ow, oh):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ Pillow Gaussian blur
+_F = np.float32
+
+
+def gaussian_blur_radius(radius, passes=3):
+    """libImaging/BoxBlur.c _gaussian_blur_radius: the (fractional) box radius whose `passes`-fold convolution has the
+    variance of a Gaussian of standard deviation `radius`.  C semantics kept: the arguments and locals are floats,
+    sqrt/floor are evaluated in double on double literals."""
+    r = _F(radius)
+    sigma2 = _F(_F(r * r) / _F(passes))
+    big_l = _F(math.sqrt(12.0 * float(sigma2) + 1.0))
+    l = _F(math.floor((float(big_l) - 1.0) / 2.0))
+    a = _F(_F(_F(2) * l + _F(1)) * _F(_F(l * _F(l + _F(1))) - _F(_F(3) * sigma2)))
+    a = _F(a / _F(_F(6) * _F(sigma2 - _F(_F(l + _F(1)) * _F(l + _F(1))))))
+    return _F(l + a)
+
+
+def box_blur_weights(float_radius):
+    """ImagingHorizontalBoxBlur's fixed-point weights: (radius, ww, fw) = integer radius, the weight of the 2*radius+1
+    inner pixels and of the two fractional outer pixels, in units of 2^-24 (the division runs in single precision)."""
+    fr = _F(float_radius)
+    radius = int(fr)
+    ww = int(_F(16777216.0) / _F(_F(fr * _F(2)) + _F(1)))
+    fw = (((1 << 24) - (radius * 2 + 1) * ww) & 0xffffffff) // 2
+    return radius, ww, fw
+
+
+def box_blur_axis1(a, float_radius):
+    """One ImagingHorizontalBoxBlur (ImagingLineBoxBlur32 per line) along axis 1 of a uint8 [H][W][C] array: running
+    sum `acc` over the inner window in uint32, out = (acc*ww + (left + right)*fw + 2^23) >> 24, indices beyond the
+    line replaced by its first / last pixel."""
+    radius, ww, fw = box_blur_weights(float_radius)
+    w = a.shape[1]
+    lastx = w - 1
+    edge_a, edge_b = min(radius + 1, w), max(w - radius - 1, 0)
+    src = a.astype(np.int64)
+    out = np.empty_like(a)
+    m32 = 0xffffffff
+    acc = src[:, 0] * (radius + 1)
+    for x in range(edge_a - 1):
+        acc = acc + src[:, x]
+    acc = (acc + src[:, lastx] * (radius - edge_a + 1)) & m32
+
+    def step(acc, sub, add, left, right, x):
+        acc = (acc + src[:, add] - src[:, sub]) & m32
+        bulk = (acc * ww + (src[:, left] + src[:, right]) * fw) & m32
+        out[:, x] = (((bulk + (1 << 23)) & m32) >> 24).astype(np.uint8)
+        return acc
+
+    if edge_a <= edge_b:
+        for x in range(0, edge_a):
+            acc = step(acc, 0, x + radius, 0, x + radius + 1, x)
+        for x in range(edge_a, edge_b):
+            acc = step(acc, x - radius - 1, x + radius, x - radius - 1, x + radius + 1, x)
+        for x in range(edge_b, lastx + 1):
+            acc = step(acc, x - radius - 1, lastx, x - radius - 1, lastx, x)
+    else:
+        for x in range(0, edge_b):
+            acc = step(acc, 0, x + radius, 0, x + radius + 1, x)
+        for x in range(edge_b, edge_a):
+            acc = step(acc, 0, lastx, 0, lastx, x)
+        for x in range(edge_a, lastx + 1):
+            acc = step(acc, x - radius - 1, lastx, x - radius - 1, lastx, x)
+    return out
+
+
+def gaussian_blur(img_u8, radius, passes=3):
+    """PIL.Image.filter(ImageFilter.GaussianBlur(radius)) on an HWC uint8 array (ImageFilter.py GaussianBlur.filter ->
+    ImagingGaussianBlur -> ImagingBoxBlur: `passes` box blurs along x, transpose, `passes` along y, transpose)."""
+    a = np.asarray(img_u8, dtype=np.uint8)
+    if radius == 0:
+        return a.copy()
+    fr = gaussian_blur_radius(radius, passes)
+    if fr != 0:
+        for _ in range(passes):
+            a = box_blur_axis1(a, fr)
+        t = np.ascontiguousarray(a.transpose(1, 0, 2))
+        for _ in range(passes):
+            t = box_blur_axis1(t, fr)
+        a = np.ascontiguousarray(t.transpose(1, 0, 2))
+    return a
+
+
 # ------------------------------------------------------------------------------------------------ geometry
 def scale_size(w, h, short_size):
     """custom_transforms.py:117-123 (RandomScaleCrop) -- also FixScaleCrop's :157-162 with short_size = crop_size and
@@ -179,9 +265,12 @@ def flip_scale_pad_crop(img_u8, mask_u8, flip, short_size, crop_size, x1, y1, fi
     return img[y1:y1 + crop_size, x1:x1 + crop_size], mask[y1:y1 + crop_size, x1:x1 + crop_size]
 
 
-def train_sample(img_u8, label_ids_u8, flip, short_size, crop_size, x1, y1):
+def train_sample(img_u8, label_ids_u8, flip, short_size, crop_size, x1, y1, blur_radius=None):
     """TrainSet.__getitem__ + transform_tr (gtav2cityscapes.py:49-74) for one image/label pair with the random draws
-    given and without RandomGaussianBlur: (float32 CHW image, float32 HW label)."""
+    given: (float32 CHW image, float32 HW label).  blur_radius = the radius RandomGaussianBlur drew for this image
+    (custom_transforms.py:96-100) or None when it did not fire; the label is never blurred."""
     mask = encode_segmap(label_ids_u8)
     img, mask = flip_scale_pad_crop(img_u8, mask, flip, short_size, crop_size, x1, y1, fill=255)
+    if blur_radius is not None:
+        img = gaussian_blur(img, blur_radius)
     return normalize_to_tensor(img), np.array(mask).astype(np.float32)

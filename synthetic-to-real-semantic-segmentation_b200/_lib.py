@@ -62,6 +62,11 @@ class StageJob(C.Structure):
                 ("x1", i32), ("y1", i32), ("_pad", i32)]
 
 
+class BlurJob(C.Structure):
+    _fields_ = [("img", vp), ("tmp", vp), ("out", vp), ("Hs", i32), ("Ws", i32), ("flip", i32), ("x1", i32), ("y1", i32),
+                ("ww", C.c_uint32), ("fw", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class ParamSlot(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("s0", vp), ("s1", vp), ("n", i64), ("lr_mult", f32),
                 ("_pad", f32)]
@@ -79,6 +84,7 @@ PROTOTYPES = {
     "s2r_export_prediction_nchw": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
     "s2r_resize_bilinear_u8_multi": [vp, i32, i64, vp],
     "s2r_resize_nearest_u8_multi": [vp, i32, i64, vp],
+    "s2r_gaussian_blur3_u8_multi": [vp, i32, i32, i32, vp],
     "s2r_input_stage_u8_multi": [vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "s2r_resize_nearest_u8": [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp],
     "s2r_input_stage_u8": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp],

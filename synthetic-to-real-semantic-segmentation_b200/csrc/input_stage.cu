@@ -2,12 +2,17 @@
 //   dataloders/datasets/gtav2cityscapes.py:76-83   encode_segmap (labelId -> trainId table)
 //   dataloders/custom_transforms.py:59-71          RandomHorizontalFlip
 //   dataloders/custom_transforms.py:108-147        RandomScaleCrop (PIL resize, pad right/bottom, crop window)
+//   dataloders/custom_transforms.py:92-105         RandomGaussianBlur (PIL GaussianBlur on the crop)
 //   dataloders/custom_transforms.py:17-56          Normalize + ToTensor
 // as byte kernels on uint8 HWC images already resident in HBM.  Everything is bit-exact against the reference:
 //   * PIL's BILINEAR resize is a two-pass fixed-point convolution (libImaging/Resample.c: int32 accumulation of
 //     uint8 * 22-bit coefficients starting at 1 << 21, arithmetic shift, clip, uint8 intermediate between the passes);
 //     the coefficient / bounds tables are computed by the host mirror exactly as precompute_coeffs does and passed in;
 //   * PIL's NEAREST resize copies in[ytab[y]][xtab[x]] with tables from incremental double additions (Geometry.c);
+//   * PIL's GaussianBlur(radius) is three box-blur passes per axis (libImaging/BoxBlur.c) with a fractional box radius;
+//     for the reference's radii (< 1) the integer part of that radius is 0, i.e. every pass is the 3-tap fixed-point
+//     filter (c*ww + (l + r)*fw + 2^23) >> 24 in uint32 with the line ends replicated and a uint8 result per pass;
+//     ww / fw (24-bit weights, derived in single precision) come from the host mirror;
 //   * Normalize runs /255 in float32 and (-mean), (/std) in float64 rounded to float32 (numpy's casting of the tuple
 //     operands): a 3 x 256 table built per CTA with exactly those operations.
 // All kernels are HBM-bound byte movers: coalesced reads along the pixel row, coalesced fp32 plane writes.
@@ -223,7 +228,70 @@ input_stage_multi_kernel(const s2r_stage_job* __restrict__ jobs, NormParams np, 
   }
 }
 
+// ---- RandomGaussianBlur: the crop (cut from the scaled image exactly as input_stage_multi_kernel cuts it: mirror,
+// zero padding on the right / bottom) goes through three 3-tap passes along x (blur_rows_kernel -> tmp) and three
+// along y (blur_cols_kernel -> out).  P_0 = the line, P_{k+1}(j) = tap(P_k(max(j-1, 0)), P_k(j), P_k(min(j+1, last)));
+// a thread evaluates P_3 at its position by recursion (27 L1-resident byte loads; the whole stage moves < 1 MB per
+// image), so there is no intermediate buffer between the passes of one axis.
+__device__ __forceinline__ uint32_t blur_tap(uint32_t l, uint32_t c, uint32_t r, uint32_t ww, uint32_t fw) {
+  return (c * ww + (l + r) * fw + (1u << 23)) >> 24;
+}
+
+template <class Line>
+__device__ __forceinline__ uint8_t blur_three_passes(Line p0, int x, int last, uint32_t ww, uint32_t fw) {
+  auto lo = [](int j) { return j < 0 ? 0 : j; };
+  auto hi = [last](int j) { return j > last ? last : j; };
+  auto p1 = [&](int j) { return blur_tap(p0(lo(j - 1)), p0(j), p0(hi(j + 1)), ww, fw); };
+  auto p2 = [&](int j) { return blur_tap(p1(lo(j - 1)), p1(j), p1(hi(j + 1)), ww, fw); };
+  return (uint8_t)blur_tap(p2(lo(x - 1)), p2(x), p2(hi(x + 1)), ww, fw);
+}
+
+// grid = (blocks over H*W*3 bytes of the crop, njobs)
+__global__ void __launch_bounds__(kThreads)
+blur_rows_kernel(const s2r_blur_job* __restrict__ jobs, int H, int W) {
+  const s2r_blur_job j = jobs[blockIdx.y];
+  const int total = H * W * 3;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const int c = i % 3, x = (i / 3) % W, y = i / (3 * W);
+    const int sy = j.y1 + y;
+    const uint8_t* row = j.img + (long long)sy * j.Ws * 3 + c;
+    const bool row_inside = sy < j.Hs;
+    auto px = [&](int xx) -> uint32_t {
+      const int sx0 = j.x1 + xx;
+      if (!row_inside || sx0 >= j.Ws) return 0u;             // ImageOps.expand(border, fill = 0) before the crop
+      return row[(j.flip ? j.Ws - 1 - sx0 : sx0) * 3];
+    };
+    j.tmp[i] = blur_three_passes(px, x, W - 1, j.ww, j.fw);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+blur_cols_kernel(const s2r_blur_job* __restrict__ jobs, int H, int W) {
+  const s2r_blur_job j = jobs[blockIdx.y];
+  const int pitch = W * 3, total = H * pitch;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const int xb = i % pitch, y = i / pitch;
+    const uint8_t* col = j.tmp + xb;
+    auto px = [&](int yy) -> uint32_t { return col[yy * pitch]; };
+    j.out[i] = blur_three_passes(px, y, H - 1, j.ww, j.fw);
+  }
+}
+
 }  // namespace
+
+extern "C" int s2r_gaussian_blur3_u8_multi(const s2r_blur_job* jobs, int njobs, int H, int W, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535 && H >= 1 && W >= 1 && (long long)H * W * 3 < (1ll << 30), S2R_ERR_SHAPE,
+              "gaussian_blur3_u8_multi: bad shape");
+  if (njobs == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "gaussian_blur3_u8_multi: null table");
+  int gx = s2r_div_up((long long)H * W * 3, kThreads);
+  if (gx > 4096) gx = 4096;
+  blur_rows_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
+  S2R_LAUNCH_OK();
+  blur_cols_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
 
 extern "C" int s2r_resize_bilinear_u8(const uint8_t* in, int N, int H, int W, int C, int axis, int out_size,
                                       const int32_t* bounds, const int32_t* kk, int ksize, int flip, uint8_t* out,

@@ -1,13 +1,12 @@
 """The reference's sample pipeline on the device.
 
 `DeviceTrainTransform` is `TrainSet.transform_tr` (dataloders/datasets/gtav2cityscapes.py:66-74) -- RandomHorizontalFlip,
-RandomScaleCrop, Normalize, ToTensor from dataloders/custom_transforms.py -- plus `encode_segmap` (:76-83), applied to
-uint8 images / labelId maps that are already in HBM; `DeviceValTransform` is `ValSet.transform_val` (:139-146:
-FixedResize, Normalize, ToTensor).  The host computes what the reference computes on the host -- the random draws, in
-the reference's order, and Pillow's resampling tables -- and the bytes are moved by csrc/input_stage.cu.  Outputs are
-bit-identical to the reference's tensors (tests/golden/input_stage.npz).  RandomGaussianBlur (custom_transforms.py:
-91-105) is not reproduced: its draws are consumed, so the random stream stays aligned, and a sample on which it would
-fire is reported in `last_draws` (blur=True).
+RandomScaleCrop, RandomGaussianBlur, Normalize, ToTensor from dataloders/custom_transforms.py -- plus `encode_segmap`
+(:76-83), applied to uint8 images / labelId maps that are already in HBM; `DeviceValTransform` is
+`ValSet.transform_val` (:139-146: FixedResize, Normalize, ToTensor).  The host computes what the reference computes on
+the host -- the random draws, in the reference's order, Pillow's resampling tables and the fixed-point weights of its
+box blur -- and the bytes are moved by csrc/input_stage.cu.  Outputs are bit-identical to the reference's tensors
+(tests/golden/input_stage.npz).
 
 No CPU path: tensors must be CUDA tensors and the C-ABI library must be present.
 """
@@ -77,6 +76,33 @@ def _nearest_table(in_size, out_size):
     return tab
 
 
+def _gaussian_blur_weights(radius, passes=3):
+    """The 24-bit weights (ww: centre pixel, fw: each neighbour) of one box-blur pass of PIL's
+    ImageFilter.GaussianBlur(radius): libImaging/BoxBlur.c `_gaussian_blur_radius` (box radius whose `passes`-fold
+    convolution has the Gaussian's variance; float locals, sqrt/floor in double) and ImagingHorizontalBoxBlur
+    (`ww = (UINT32)(1 << 24) / (floatRadius * 2 + 1)` in single precision).  The kernels implement the case where the
+    integer part of the box radius is 0, i.e. radius < sqrt(2); the reference draws radius from [0, 1)
+    (custom_transforms.py:97-100)."""
+    f = np.float32
+    if radius == 0:                                    # ImageFilter.GaussianBlur.filter: plain copy
+        return 1 << 24, 0
+    r = f(radius)
+    sigma2 = f(f(r * r) / f(passes))
+    big_l = f(math.sqrt(12.0 * float(sigma2) + 1.0))
+    l = f(math.floor((float(big_l) - 1.0) / 2.0))
+    if l != 0:
+        raise NotImplementedError("GaussianBlur radius %r: box radius >= 1 (only radius < sqrt(2) is implemented; "
+                                  "the reference draws [0, 1))" % (radius,))
+    a = f(f(f(2) * l + f(1)) * f(f(l * f(l + f(1))) - f(f(3) * sigma2)))
+    a = f(a / f(f(6) * f(sigma2 - f(f(l + f(1)) * f(l + f(1))))))
+    fr = f(l + a)
+    if fr == 0:                                        # ImagingBoxBlur skips an axis whose radius is 0
+        return 1 << 24, 0
+    ww = int(f(16777216.0) / f(f(fr * f(2)) + f(1)))
+    fw = (((1 << 24) - ww) & 0xffffffff) // 2
+    return ww, fw
+
+
 def _scale_size(w, h, short_size):
     if h > w:
         ow = short_size
@@ -85,6 +111,12 @@ def _scale_size(w, h, short_size):
         oh = short_size
         ow = int(1.0 * w * oh / h)
     return ow, oh
+
+
+def _upload(jobs, dev):
+    """A ctypes job table -> device memory."""
+    arr = (type(jobs[0]) * len(jobs))(*jobs)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
 
 
 class _Stage(object):
@@ -159,11 +191,13 @@ class DeviceTrainTransform(object):
     """transform_tr of the reference's TrainSet on a batch of equally sized uint8 device tensors:
     src/tgt images [N,H,W,3] (RGB, HWC as PIL decodes them) and labelId maps [N,H,W] ->
     {'src_image': f32 [N,3,crop,crop], 'tgt_image': ..., 'src_label': f32 [N,crop,crop]}.
-    Per sample the draws are made with python's `random` in the reference's order (flip, short edge, x1, y1, blur)
-    unless `draws` = [(flip, short_size, x1, y1), ...] is given."""
+    Per sample the draws are made with python's `random` in the reference's order (flip, short edge, x1, y1, blur and,
+    when it fires, the source and the target image's blur radius) unless `draws` = [(flip, short_size, x1, y1[, blur,
+    src_radius, tgt_radius]), ...] is given.  `last_draws` holds the draws of the last call.  gaussian_blur=False drops
+    the blur (its draws are still consumed, so the random stream stays aligned with the reference's)."""
 
-    def __init__(self, base_size, crop_size, mean=MEAN, std=STD, fill=255):
-        self.base_size, self.crop_size, self.fill = base_size, crop_size, fill
+    def __init__(self, base_size, crop_size, mean=MEAN, std=STD, fill=255, gaussian_blur=True):
+        self.base_size, self.crop_size, self.fill, self.gaussian_blur = base_size, crop_size, fill, gaussian_blur
         self.stage = _Stage(mean, std)
         self.last_draws = []
 
@@ -175,11 +209,10 @@ class DeviceTrainTransform(object):
         ph = max(oh, self.crop_size) if short < self.crop_size else oh
         x1 = random.randint(0, pw - self.crop_size)                            # :138-139
         y1 = random.randint(0, ph - self.crop_size)
-        blur = random.random() < 0.5                                           # :96 (radius draws follow when it fires)
-        if blur:
-            random.random()
-            random.random()
-        return flip, short, x1, y1, blur
+        blur = random.random() < 0.5                                           # :96
+        r_src = random.random() if blur else None                              # :97-98 source image radius
+        r_tgt = random.random() if blur else None                              # :99-100 target image radius
+        return flip, short, x1, y1, blur, r_src, r_tgt
 
     def __call__(self, src_image, tgt_image, src_label, draws=None, batched=True):
         st_ = self.stage
@@ -191,7 +224,7 @@ class DeviceTrainTransform(object):
                'tgt_image': torch.empty((N, 3, cs, cs), dtype=torch.float32, device=dev),
                'src_label': torch.empty((N, cs, cs), dtype=torch.float32, device=dev)}
         self.last_draws = []
-        plan = []
+        plan, blur = [], []      # blur[n]: None or the (ww, fw) box-blur weights of sample n's source and target image
         for n in range(N):
             d = draws[n] if draws is not None else self.draw(W, H)
             flip, short, x1, y1 = d[:4]
@@ -200,33 +233,53 @@ class DeviceTrainTransform(object):
             if x1 + cs > max(ow, cs) or y1 + cs > max(oh, cs):
                 raise ValueError("crop window (%d,%d)+%d outside the %dx%d scaled image" % (x1, y1, cs, ow, oh))
             plan.append((bool(flip), ow, oh, int(x1), int(y1)))
+            fires = self.gaussian_blur and len(d) >= 7 and bool(d[4])
+            blur.append({'src_image': _gaussian_blur_weights(d[5]), 'tgt_image': _gaussian_blur_weights(d[6])} if fires else None)
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             if batched:
-                self._run_batched(src_image, tgt_image, src_label, plan, out, st)
+                self._run_batched(src_image, tgt_image, src_label, plan, out, st, blur)
                 return out
             for n in range(N):
                 flip, ow, oh, x1, y1 = plan[n]
                 for key, t in (('src_image', src_image), ('tgt_image', tgt_image)):
                     im, fl = st_.resize_image(t[n:n + 1], ow, oh, flip, st)
-                    st_.finish(im, None, fl, False, x1, y1, out[key][n:n + 1], None, cs, cs, st)
+                    if blur[n] is not None:
+                        im, _keep = self._blur([(im.data_ptr(), im.shape[1], im.shape[2], fl, x1, y1) + blur[n][key]], dev, st)
+                        im, fl, x1_, y1_ = im.view(1, cs, cs, 3), False, 0, 0
+                    else:
+                        x1_, y1_ = x1, y1
+                    st_.finish(im, None, fl, False, x1_, y1_, out[key][n:n + 1], None, cs, cs, st)
                 lb, fl = st_.resize_label(src_label[n:n + 1], ow, oh, flip, st)
                 st_.finish(None, lb, False, fl, x1, y1, None, out['src_label'][n:n + 1], cs, cs, st, fill=self.fill)
         return out
 
 
-    def _run_batched(self, src_image, tgt_image, src_label, plan, out, st):
+    def _blur(self, entries, dev, st):
+        """RandomGaussianBlur on crops: entries = [(image pointer, Hs, Ws, mirror, x1, y1, ww, fw), ...] in the terms of
+        a StageJob; returns (u8 [n][crop][crop][3] blurred crops, tensors to keep alive).  Two launches."""
+        cs = self.crop_size
+        n = len(entries)
+        buf = torch.empty((2, n, cs, cs, 3), dtype=torch.uint8, device=dev)
+        jobs = [L.BlurJob(p, buf[0, k].data_ptr(), buf[1, k].data_ptr(), int(hs), int(ws), int(fl), int(x1), int(y1),
+                          int(ww), int(fw), 0) for k, (p, hs, ws, fl, x1, y1, ww, fw) in enumerate(entries)]
+        tab = _upload(jobs, dev)
+        L.call("s2r_gaussian_blur3_u8_multi", tab.data_ptr(), n, cs, cs, st)
+        return buf[1], [buf, tab]
+
+    def _run_batched(self, src_image, tgt_image, src_label, plan, out, st, blur=None):
         """At most four launches for the whole batch (column pass, row pass, nearest, crop/normalise) through device
-        tables of per-sample jobs, and only the WINDOW of every scaled image that its crop keeps is resampled: the
-        column pass produces the window's columns for the source rows the row pass will read, the row pass the
-        window's rows.  Same arithmetic per byte as the per-sample path (bit-identical)."""
+        tables of per-sample jobs -- six when RandomGaussianBlur fires on a sample of the batch -- and only the WINDOW
+        of every scaled image that its crop keeps is resampled: the column pass produces the window's columns for the
+        source rows the row pass will read, the row pass the window's rows.  Same arithmetic per byte as the
+        per-sample path (bit-identical)."""
         st_ = self.stage
         N, H, W, _ = src_image.shape
         dev, cs = src_image.device, self.crop_size
+        blur = blur if blur is not None else [None] * N
 
         def upload(jobs):
-            arr = (type(jobs[0]) * len(jobs))(*jobs)
-            return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            return _upload(jobs, dev)
 
         def pool(sizes):
             offs, tot = [], 0
@@ -320,15 +373,24 @@ class DeviceTrainTransform(object):
             L.call("s2r_resize_nearest_u8_multi", tab.data_ptr(), len(jobs), mx, st)
         # crop window + Normalize/ToTensor (images) and the labelId table (labels): one launch.  A resampled image is
         # already cut to its window (origin 0, 0); an image that was not resampled at all is read in place.
-        jobs = []
+        # (a crop on which RandomGaussianBlur fires is first cut and blurred as uint8, then normalised like an image of
+        # the crop's size)
+        geom = {}
         for key, ptr, n in images:
             flip, ow, oh, x1, y1 = plan[n]
             cx0, cx1, cy0, cy1, r0, r1 = win[n]
             c = cur[(key, n)]
-            if c[3]:
-                jobs.append(L.StageJob(c[0], None, out[key][n].data_ptr(), None, cy1 - cy0, cx1 - cx0, int(c[2]), 0, 0, 0))
-            else:
-                jobs.append(L.StageJob(ptr, None, out[key][n].data_ptr(), None, H, W, int(flip), x1, y1, 0))
+            geom[(key, n)] = (c[0], cy1 - cy0, cx1 - cx0, int(c[2]), 0, 0) if c[3] else (ptr, H, W, int(flip), x1, y1)
+        fired = [(key, n) for key, _, n in images if blur[n] is not None]
+        if fired:
+            crops, kept = self._blur([geom[kn] + blur[kn[1]][kn[0]] for kn in fired], dev, st)
+            keep.extend(kept)
+            for k, kn in enumerate(fired):
+                geom[kn] = (crops[k].data_ptr(), cs, cs, 0, 0, 0)
+        jobs = []
+        for key, ptr, n in images:
+            p, hs, ws, fl, gx1, gy1 = geom[(key, n)]
+            jobs.append(L.StageJob(p, None, out[key][n].data_ptr(), None, hs, ws, fl, gx1, gy1, 0))
         for n in range(N):
             flip, ow, oh, x1, y1 = plan[n]
             cx0, cx1, cy0, cy1, r0, r1 = win[n]

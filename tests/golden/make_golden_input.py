@@ -1,8 +1,9 @@
 """Generates tests/golden/input_stage.npz from the REAL reference input pipeline (build container only):
 `dataloders.datasets.gtav2cityscapes.TrainSet.__getitem__` / `ValSet.__getitem__` run UNMODIFIED on small synthetic
-PNG files (PIL resize / flip / pad / crop, Normalize, ToTensor), with `random` seeded so that the draws are known and
-RandomGaussianBlur (not part of the device input stage) does not fire.  Also checks oracle/input_stage.py against
-every case and against Pillow itself over a sweep of sizes.  Run:  python tests/golden/make_golden_input.py
+PNG files (PIL resize / flip / pad / crop, GaussianBlur, Normalize, ToTensor), with `random` seeded so that the draws
+are known: per image configuration two cases on which RandomGaussianBlur does not fire (train*) and two on which it
+does (trainb*).  Also checks oracle/input_stage.py against every case and against Pillow itself over a sweep of sizes
+and blur radii.  Run:  python tests/golden/make_golden_input.py
 """
 import os
 import random
@@ -35,7 +36,8 @@ def draws(seed, n_tgt, w, h, base_size, crop_size):
     x1 = random.randint(0, pw - crop_size)
     y1 = random.randint(0, ph - crop_size)
     blur = random.random() < 0.5
-    return tgt_index, flip, short, x1, y1, blur
+    radii = (random.random(), random.random()) if blur else None      # custom_transforms.py:97-100: src, then tgt
+    return tgt_index, flip, short, x1, y1, blur, radii
 
 
 def main():
@@ -44,7 +46,7 @@ def main():
     with tempfile.TemporaryDirectory() as d:
         for sub in ("src", "lab", "tgt", "vimg", "vlab"):
             os.makedirs(os.path.join(d, sub))
-        cases = []
+        cases, blur_cases = [], []
         # (H, W, base_size, crop_size): up-scaling, down-scaling with padding, portrait (h > w)
         for ci, (H, W, base, crop) in enumerate([(40, 64, 40, 32), (48, 36, 20, 32), (33, 57, 36, 24), (64, 96, 24, 40)]):
             for f in os.listdir(os.path.join(d, "src")):
@@ -62,7 +64,7 @@ def main():
             ds = ref_ds.TrainSet(args)
             found = 0
             for seed in range(1000):
-                _, flip, short, x1, y1, blur = draws(seed, 1, W, H, base, crop)
+                _, flip, short, x1, y1, blur, _ = draws(seed, 1, W, H, base, crop)
                 if blur:
                     continue
                 want_flip = found % 2 == 0
@@ -86,6 +88,31 @@ def main():
                 if found == 2:
                     break
             assert found == 2
+            # the same images on draws where RandomGaussianBlur fires (own radius for the source and the target image)
+            found = 0
+            for seed in range(1000, 2000):
+                _, flip, short, x1, y1, blur, radii = draws(seed, 1, W, H, base, crop)
+                if not blur or flip != (found % 2 == 1):
+                    continue
+                random.seed(seed)
+                sample = ds[0]                      # the reference, unmodified
+                got_img, got_lab = OI.train_sample(src, lab, flip, short, crop, x1, y1, blur_radius=radii[0])
+                got_tgt, _ = OI.train_sample(tgt, lab, flip, short, crop, x1, y1, blur_radius=radii[1])
+                assert np.array_equal(sample['src_image'].numpy(), got_img), ("blurred src image", ci, seed)
+                assert np.array_equal(sample['tgt_image'].numpy(), got_tgt), ("blurred tgt image", ci, seed)
+                assert np.array_equal(sample['src_label'].numpy(), got_lab), ("label", ci, seed)
+                k = "trainb%d_%d" % (ci, found)
+                out[k + "_src"], out[k + "_tgt"], out[k + "_lab"] = src, tgt, lab
+                out[k + "_draw"] = np.array([int(flip), short, crop, x1, y1], np.int32)
+                out[k + "_radii"] = np.array(radii, np.float64)
+                out[k + "_out_src"] = sample['src_image'].numpy()
+                out[k + "_out_tgt"] = sample['tgt_image'].numpy()
+                out[k + "_out_lab"] = sample['src_label'].numpy()
+                blur_cases.append(k)
+                found += 1
+                if found == 2:
+                    break
+            assert found == 2
         # validation pipeline: FixedResize((size, size)) + Normalize + ToTensor (ValSet.transform_val)
         img = rng.randint(0, 256, (50, 70, 3)).astype(np.uint8)
         lab = rng.randint(0, 36, (50, 70)).astype(np.uint8)
@@ -99,6 +126,7 @@ def main():
         out["val_img"], out["val_lab"], out["val_size"] = img, lab, np.array([36], np.int32)
         out["val_out_img"], out["val_out_lab"] = vs['image'].numpy(), vs['label'].numpy()
         out["cases"] = np.array(cases)
+        out["blur_cases"] = np.array(blur_cases)
     # the label table against the reference's own relabelling of every byte value
     holder = types.SimpleNamespace(void_classes=OI.VOID_CLASSES, valid_classes=OI.VALID_CLASSES, ignore_index=255,
                                    class_map=dict(zip(OI.VALID_CLASSES, range(19))))
@@ -115,7 +143,16 @@ def main():
                 assert np.array_equal(np.array(Image.fromarray(a).resize((ow, oh), Image.BILINEAR)), OI.resize_bilinear(a, ow, oh)), (h, w, ow, oh)
                 assert np.array_equal(np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST)), OI.resize_nearest(m, ow, oh)), (h, w, ow, oh)
                 n += 1
-    print("oracle == Pillow on %d resize shapes; %d pipeline cases written" % (n, len(cases) + 1))
+    # Pillow's GaussianBlur over radii of the reference's range [0, 1) and beyond, on small and degenerate sizes
+    from PIL import ImageFilter
+    nb = 0
+    for trial in range(600):
+        h, w = int(rng.randint(1, 40)), int(rng.randint(1, 40))
+        a = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        r = float(rng.rand()) * (1.0, 6.0, 40.0)[trial % 3]
+        assert np.array_equal(np.array(Image.fromarray(a).filter(ImageFilter.GaussianBlur(radius=r))), OI.gaussian_blur(a, r)), (h, w, r)
+        nb += 1
+    print("oracle == Pillow on %d resize shapes and %d blurs; %d pipeline cases written" % (n, nb, len(cases) + len(blur_cases) + 1))
     np.savez_compressed(os.path.join(HERE, "input_stage.npz"), **out)
 
 

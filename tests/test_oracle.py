@@ -5,6 +5,7 @@ import os
 import subprocess
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import ROOT, golden, sub
@@ -211,6 +212,44 @@ def test_input_stage_oracle_and_host_tables_against_reference_fixture():
         assert np.array_equal(dt._nearest_table(i, o), OI.nearest_table(i, o)), (i, o)
 
 
+def test_gaussian_blur_oracle_against_reference_fixture_and_pillow():
+    """RandomGaussianBlur (custom_transforms.py:92-105): the numpy restatement of Pillow's GaussianBlur (three
+    fractional-radius box blurs per axis, libImaging/BoxBlur.c) against the tensors the reference's unmodified TrainSet
+    produced on draws where the blur fires, against Pillow itself, and the host mirror's fixed-point weights against the
+    oracle's over the reference's range of radii."""
+    from oracle import input_stage as OI
+    fix = golden("input_stage")
+    assert len(fix["blur_cases"]) == 8
+    for k in fix["blur_cases"]:
+        flip, short, crop, x1, y1 = (int(v) for v in fix[k + "_draw"])
+        r_src, r_tgt = (float(v) for v in fix[k + "_radii"])
+        img, lab = OI.train_sample(fix[k + "_src"], fix[k + "_lab"], flip, short, crop, x1, y1, blur_radius=r_src)
+        tgt, _ = OI.train_sample(fix[k + "_tgt"], fix[k + "_lab"], flip, short, crop, x1, y1, blur_radius=r_tgt)
+        assert np.array_equal(img, fix[k + "_out_src"]) and np.array_equal(tgt, fix[k + "_out_tgt"]), k
+        assert np.array_equal(lab, fix[k + "_out_lab"]), k
+        plain, _ = OI.train_sample(fix[k + "_src"], fix[k + "_lab"], flip, short, crop, x1, y1)
+        assert not np.array_equal(plain, img), k                       # the blur does something on these cases
+    from PIL import Image, ImageFilter
+    rng = np.random.RandomState(7)
+    for trial in range(120):                # degenerate sizes and radii far beyond the reference's included
+        h, w = int(rng.randint(1, 36)), int(rng.randint(1, 36))
+        a = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        r = float(rng.rand()) * (1.0, 1.0, 5.0, 30.0)[trial % 4]
+        want = np.array(Image.fromarray(a).filter(ImageFilter.GaussianBlur(radius=r)))
+        assert np.array_equal(OI.gaussian_blur(a, r), want), (h, w, r)
+    dt = sub("dataloders.device_transforms")
+    for r in list(rng.rand(5000)) + [0.0, 1e-30, 1e-10, 0.999999, 1.0, 1.41]:
+        ww, fw = dt._gaussian_blur_weights(float(r))
+        fr = OI.gaussian_blur_radius(r) if r != 0 else 0
+        if fr == 0:
+            assert (ww, fw) == (1 << 24, 0), r      # identity: Pillow copies / skips the passes
+        else:
+            assert (0, ww, fw) == OI.box_blur_weights(fr), r
+        assert ww + 2 * fw <= 1 << 24 and 255 * (ww + 2 * fw) + (1 << 23) < 1 << 32     # the kernel's uint32 arithmetic
+    with pytest.raises(NotImplementedError):
+        dt._gaussian_blur_weights(1.5)
+
+
 def test_lr_policy_against_reference_fixture():
     """utils.lr_scheduler.LR_Scheduler (poly / cos / step, warm-up, lr to group 0 and 10*lr to the others --
     utils/lr_scheduler.py:43-70, incl. the overwrite of the discriminator's lr at train_adapt.py:133) against the
@@ -258,8 +297,8 @@ def test_prediction_export_oracle_against_pillow():
 
 def test_batched_input_stage_host_planning_with_emulated_kernels():
     """The REAL host planning of the batched device input stage (window of the scaled image per sample, job tables for
-    the column / row / nearest / crop launches) driven through a pure-Python emulation of the kernels reproduces the
-    reference's tensors (tests/tools/emul_input_stage.py; no GPU)."""
+    the column / row / nearest / blur / crop launches) driven through a pure-Python emulation of the kernels reproduces
+    the reference's tensors, RandomGaussianBlur cases included (tests/tools/emul_input_stage.py; no GPU)."""
     import sys as _sys
     r = subprocess.run([_sys.executable, os.path.join(ROOT, "tests", "tools", "emul_input_stage.py")], capture_output=True,
                        text=True, timeout=300)

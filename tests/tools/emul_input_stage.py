@@ -60,6 +60,30 @@ def emu(name,*a):
                         v=float(fill)
                         if inside: v=float(lutv[arr(j.label+sy*j.Ws+sx,1)[0]])
                         np.ctypeslib.as_array(C.cast(j.out_label,C.POINTER(C.c_float)),shape=(H*W,))[y*W+x]=v
+    elif name=="s2r_gaussian_blur3_u8_multi":
+        # blur_rows_kernel then blur_cols_kernel of csrc/input_stage.cu, statement by statement
+        tab,n,H,W,st=a
+        def tap(l,c,r,ww,fw): return ((c*ww+(l+r)*fw+(1<<23))&0xffffffff)>>24
+        def three(p0,x,last,ww,fw):
+            lo=lambda j: 0 if j<0 else j
+            hi=lambda j: last if j>last else j
+            p1=lambda j: tap(p0(lo(j-1)),p0(j),p0(hi(j+1)),ww,fw)
+            p2=lambda j: tap(p1(lo(j-1)),p1(j),p1(hi(j+1)),ww,fw)
+            return tap(p2(lo(x-1)),p2(x),p2(hi(x+1)),ww,fw)
+        for j in (L.BlurJob*n).from_address(tab):
+            tmp=arr(j.tmp,H*W*3); out=arr(j.out,H*W*3)
+            for i in range(H*W*3):
+                c,x,y=i%3,(i//3)%W,i//(3*W)
+                sy=j.y1+y
+                def px(xx):
+                    sx0=j.x1+xx
+                    if not (sy<j.Hs) or sx0>=j.Ws: return 0
+                    return int(arr(j.img+sy*j.Ws*3+c+((j.Ws-1-sx0) if j.flip else sx0)*3,1)[0])
+                tmp[i]=three(px,x,W-1,j.ww,j.fw)
+            pitch=W*3
+            for i in range(H*pitch):
+                xb,y=i%pitch,i//pitch
+                out[i]=three(lambda yy: int(tmp[xb+yy*pitch]),y,H-1,j.ww,j.fw)
     return 0
 L.call=emu
 dt.L.call=emu
@@ -76,6 +100,23 @@ for a,b in zip(names[0::2],names[1::2]):
     for d in (da,db):
         ow,oh=dt._scale_size(W,H,d[1]); plan.append((bool(d[0]),ow,oh,d[3],d[4]))
     keep=tr._run_batched(src,tgt,lab,plan,out,None)
+    for n,k in enumerate((a,b)):
+        e=[np.array_equal(out['src_image'][n].numpy(),fix[k+'_out_src']),np.array_equal(out['tgt_image'][n].numpy(),fix[k+'_out_tgt']),np.array_equal(out['src_label'][n].numpy(),fix[k+'_out_lab'])]
+        print(k,plan[n],e); ok&=all(e)
+# RandomGaussianBlur cases (the blur fires on both samples of a pair, own radius per image) and a mixed batch
+names=[str(k) for k in fix['blur_cases']]
+for a,b in zip(names[0::2],names[1::2]):
+    da,db=[int(v) for v in fix[a+'_draw']],[int(v) for v in fix[b+'_draw']]
+    tr=dt.DeviceTrainTransform(1,da[2])
+    src=torch.from_numpy(np.stack([fix[a+'_src'],fix[b+'_src']])); tgt=torch.from_numpy(np.stack([fix[a+'_tgt'],fix[b+'_tgt']])); lab=torch.from_numpy(np.stack([fix[a+'_lab'],fix[b+'_lab']]))
+    N,H,W,_=src.shape; cs=da[2]
+    out={'src_image':torch.zeros(N,3,cs,cs),'tgt_image':torch.zeros(N,3,cs,cs),'src_label':torch.zeros(N,cs,cs)}
+    plan,blur=[],[]
+    for d,k in ((da,a),(db,b)):
+        ow,oh=dt._scale_size(W,H,d[1]); plan.append((bool(d[0]),ow,oh,d[3],d[4]))
+        r=fix[k+'_radii']
+        blur.append({'src_image':dt._gaussian_blur_weights(float(r[0])),'tgt_image':dt._gaussian_blur_weights(float(r[1]))})
+    keep=tr._run_batched(src,tgt,lab,plan,out,None,blur)
     for n,k in enumerate((a,b)):
         e=[np.array_equal(out['src_image'][n].numpy(),fix[k+'_out_src']),np.array_equal(out['tgt_image'][n].numpy(),fix[k+'_out_tgt']),np.array_equal(out['src_label'][n].numpy(),fix[k+'_out_lab'])]
         print(k,plan[n],e); ok&=all(e)
