@@ -66,11 +66,8 @@ def cpu_adapt_steps(batch, h, w, steps, warmup):
     from oracle import ref_port as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    torch.manual_seed(1)
-    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
-    D = sub("modeling.discriminator").FCDiscriminator(num_classes=19)
-    g_sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
-    d_sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    # nothing of this repo's package on this path: weights, forward, backward and optimizers are the oracle's + torch's
+    g_sd, d_sd = O.init_deeplab(seed=1), O.init_discriminator(seed=2)
     for sd in (g_sd, d_sd):
         for v in O.leaf_params(sd).values():
             v.requires_grad_(True)

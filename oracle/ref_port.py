@@ -248,6 +248,75 @@ def leaf_params(sd):
             and not k.startswith(('low_level_features.', 'high_level_features.'))}
 
 
+def _conv_w(sd, name, cout, cin, k, gen, bias=False, default_init=False):
+    """Weights of one nn.Conv2d: kaiming_normal_ where the reference's _init_weight / _initialize_weights loops touch
+    the layer (mobilenet.py:134-145, assp.py:22-32,80-91, decoder.py:45-54), nn.Conv2d's own default
+    (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias) otherwise (discriminator.py has no init loop; biases are
+    never re-initialised)."""
+    fan_in = cin * k * k
+    bound = 1.0 / math.sqrt(fan_in)
+    if default_init:
+        sd[name + '.weight'] = (torch.rand(cout, cin, k, k, generator=gen) * 2 - 1) * bound
+    else:
+        sd[name + '.weight'] = torch.randn(cout, cin, k, k, generator=gen) * math.sqrt(2.0 / fan_in)
+    if bias:
+        sd[name + '.bias'] = (torch.rand(cout, generator=gen) * 2 - 1) * bound
+
+
+def _bn(sd, name, c):
+    sd[name + '.weight'], sd[name + '.bias'] = torch.ones(c), torch.zeros(c)
+    sd[name + '.running_mean'], sd[name + '.running_var'] = torch.zeros(c), torch.ones(c)
+    sd[name + '.num_batches_tracked'] = torch.zeros((), dtype=torch.long)
+
+
+def init_deeplab(seed=1, output_stride=16, num_classes=19):
+    """A randomly initialised state dict of DeepLab(backbone='mobilenet') with the reference's key names, shapes and
+    initial distributions (deeplab.py:9-25 -> mobilenet.py:71-117, assp.py:34-63, decoder.py:7-32) built from plain
+    tensors -- so that the CPU baseline needs nothing but this module and torch.  Same distributions as the
+    reference's constructors, not the same random stream (tests that need identical weights on both sides copy them
+    from one model)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    f = 'backbone.features.'
+    _conv_w(sd, f + '0.0', 32, 3, 3, gen)
+    _bn(sd, f + '0.1', 32)
+    for k, (inp, oup, stride, dil, t) in enumerate(mnv2_plan(output_stride), start=1):
+        hidden, i = inp * t, 0
+        if t != 1:
+            _conv_w(sd, '%s%d.conv.0' % (f, k), hidden, inp, 1, gen)
+            _bn(sd, '%s%d.conv.1' % (f, k), hidden)
+            i = 3
+        sd['%s%d.conv.%d.weight' % (f, k, i)] = torch.randn(hidden, 1, 3, 3, generator=gen) * math.sqrt(2.0 / 9)
+        _bn(sd, '%s%d.conv.%d' % (f, k, i + 1), hidden)
+        _conv_w(sd, '%s%d.conv.%d' % (f, k, i + 3), oup, hidden, 1, gen)
+        _bn(sd, '%s%d.conv.%d' % (f, k, i + 4), oup)
+    for k in (1, 2, 3, 4):
+        _conv_w(sd, 'aspp.aspp%d.atrous_conv' % k, 256, 320, 1 if k == 1 else 3, gen)
+        _bn(sd, 'aspp.aspp%d.bn' % k, 256)
+    _conv_w(sd, 'aspp.global_avg_pool.1', 256, 320, 1, gen)
+    _bn(sd, 'aspp.global_avg_pool.2', 256)
+    _conv_w(sd, 'aspp.conv1', 256, 1280, 1, gen)
+    _bn(sd, 'aspp.bn1', 256)
+    _conv_w(sd, 'decoder.conv1', 48, 24, 1, gen)
+    _bn(sd, 'decoder.bn1', 48)
+    _conv_w(sd, 'decoder.last_conv.0', 256, 304, 3, gen)
+    _bn(sd, 'decoder.last_conv.1', 256)
+    _conv_w(sd, 'decoder.last_conv.4', 256, 256, 3, gen)
+    _bn(sd, 'decoder.last_conv.5', 256)
+    _conv_w(sd, 'decoder.last_conv.8', num_classes, 256, 1, gen, bias=True)
+    return sd
+
+
+def init_discriminator(seed=2, num_classes=19, ndf=64):
+    """State dict of FCDiscriminator (discriminator.py:8-20) with nn.Conv2d's default initialisation."""
+    gen = torch.Generator().manual_seed(seed)
+    sd, cin = {}, num_classes
+    for name, cout in (('conv1', ndf), ('conv2', ndf * 2), ('conv3', ndf * 4), ('conv4', ndf * 8), ('classifier', 1)):
+        _conv_w(sd, name, cout, cin, 4, gen, bias=True, default_init=True)
+        cin = cout
+    return sd
+
+
 def adapt_step(g_sd, d_sd, opt_g, opt_d, src_image, src_label, tgt_image, cfg, drop=None, output_stride=16):
     """One iteration of Trainer.training in train_adapt.py:137-181 (device-agnostic): returns
     (loss_seg, loss_adv, loss_D_src, loss_D_tgt) as python floats.  g_sd/d_sd hold leaf tensors

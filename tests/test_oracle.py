@@ -72,6 +72,37 @@ def test_state_dict_layout():
     assert sum(p.numel() for p in dc.parameters()) == 9721858
 
 
+def test_oracle_init_matches_module_layout():
+    """oracle.init_deeplab / init_discriminator (what bench.py's CPU arm runs on, with nothing of the product package
+    on that path): same keys in the same order, shapes, dtypes and initial distributions as the module tree."""
+    torch.manual_seed(1)
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    D = sub("modeling.discriminator").FCDiscriminator(num_classes=19)
+    for want, got in ((G.state_dict(), O.init_deeplab()), (D.state_dict(), O.init_discriminator())):
+        want = {k: v for k, v in want.items() if '.low_level_features.' not in k and '.high_level_features.' not in k}
+        assert list(want.keys()) == list(got.keys())
+        for k, v in want.items():
+            assert v.shape == got[k].shape and v.dtype == got[k].dtype, k
+            if v.dim() == 4 and v.numel() >= 4096:              # conv weights: same distribution
+                assert abs(float(got[k].std()) / float(v.std()) - 1) < 0.1 and abs(float(got[k].mean())) < 0.1 * float(v.std()), k
+            elif v.dim() <= 1 and (bool((v == 0).all()) or bool((v == 1).all())):
+                assert torch.equal(v, got[k]), k                # BN parameters and buffers: ones / zeros
+    # and it runs: one adaptation step of the oracle on those weights
+    g_sd, d_sd = O.init_deeplab(), O.init_discriminator()
+    for sd in (g_sd, d_sd):
+        for v in O.leaf_params(sd).values():
+            v.requires_grad_(True)
+    one, ten = O.split_lr_groups(list(O.leaf_params(g_sd).keys()))
+    opt = torch.optim.SGD([{'params': [g_sd[k] for k in one], 'lr': 5e-4}, {'params': [g_sd[k] for k in ten], 'lr': 5e-3}],
+                          momentum=0.9, weight_decay=5e-4)
+    opt_d = torch.optim.Adam(list(O.leaf_params(d_sd).values()), lr=1e-4, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(0)
+    src, tgt = torch.randn(2, 3, 64, 96, generator=g), torch.randn(2, 3, 64, 96, generator=g)
+    lab = torch.randint(0, 19, (2, 64, 96), generator=g).float()
+    losses = O.adapt_step(g_sd, d_sd, opt, opt_d, src, lab, tgt, O.BNCfg(True))
+    assert all(np.isfinite(v) for v in losses) and 2.0 < losses[0] < 4.5 and 0.5 < losses[1] < 0.9
+
+
 def test_deeplab_train_forward_backward():
     fix = golden('deeplab_train_2x65x97')
     sd = grad_sd(seeded_state('deeplab'))
