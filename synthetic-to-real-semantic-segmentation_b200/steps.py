@@ -475,6 +475,11 @@ class ValStep(object):
                     st.copy_(t, non_blocking=True)
             graph.replay()
 
+    def all_reduce(self, group=None):
+        """Data-parallel validation: every rank has run its shard of the images (rank r takes images r, r + world,
+        ...); sums the confusion matrices over the ranks (Evaluator.all_reduce) and returns the evaluator."""
+        return self.evaluator.all_reduce(group)
+
     def finish(self):
         """Order every lane before the current stream (call before reading the evaluator)."""
         for static, graph, stream in getattr(self, "_lanes", []):

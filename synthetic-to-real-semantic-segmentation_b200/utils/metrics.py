@@ -95,6 +95,20 @@ class Evaluator(object):
             L.call("s2r_argmax_confusion_nchw", _vp(logits), _vp(gt), N, Cc, HW, self.num_class,
                    _vp(self._counts), None, st)
 
+    def all_reduce(self, group=None):
+        """Data-parallel validation (one process per GPU, every rank evaluates its shard of the images): ONE
+        all-reduce(sum) of the int64 [num_class, num_class] counts -- and of the bad-prediction flag -- turns every
+        rank's matrix into the matrix of the whole set.  Integer sums: exact and independent of the order, so the
+        metrics equal the reference's single-process Evaluator (utils/metrics.py:34-46) fed all images.  Call once,
+        after the last add_batch; a no-op in a single process."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+            return self
+        self._ensure(None)
+        dist.all_reduce(self._counts, group=group)
+        dist.all_reduce(self._bad, group=group)
+        return self
+
     def reset(self):
         if self._counts is not None:
             self._counts.zero_()

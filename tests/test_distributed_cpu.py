@@ -4,7 +4,9 @@ combined.  The product kernels need a GPU; here the per-rank pieces are restated
   * synchronised BatchNorm forward: all-reduce of the fp64 per-channel (sum, sum of squares) + element count x world
     -> modeling/sync_batchnorm/batchnorm.py:113-125 (clamp(var, eps)^-1/2, unbiased running variance);
   * synchronised BatchNorm backward: all-reduce of (sum dy, sum dy*xhat) -> the autograd of the same formula;
-  * gradient all-reduce: per-rank mean losses, gradients summed and divided by the world size (engine/optim.py)."""
+  * gradient all-reduce: per-rank mean losses, gradients summed and divided by the world size (engine/optim.py);
+  * data-parallel validation: utils.metrics.Evaluator.all_reduce (the product's method, on counts accumulated per rank
+    with the oracle's bincount) -> the reference's Evaluator metrics on the whole set, bit-exact."""
 import os
 import socket
 import sys
@@ -73,6 +75,25 @@ def _worker(rank, world, port, q):
         dist.all_reduce(g)
         g /= world
         assert torch.allclose(g, x_all.mean((0, 2, 3)), rtol=1e-10)
+        # ---- validation: per-rank confusion matrices summed by Evaluator.all_reduce == the matrix of the whole set
+        import importlib
+        import numpy as np
+        metrics = importlib.import_module("synthetic-to-real-semantic-segmentation_b200.utils.metrics")
+        rng = np.random.RandomState(11)
+        gt_all = rng.randint(0, 20, (6, 33, 47)).astype(np.float32)
+        gt_all[gt_all == 19] = 255
+        pred_all = rng.randint(0, 19, (6, 33, 47)).astype(np.int64)
+        ev = metrics.Evaluator(19)
+        mine = slice(rank, None, world)                                   # rank r evaluates images r, r + world, ...
+        ev._counts = torch.from_numpy(O.confusion_matrix(gt_all[mine], pred_all[mine], 19).astype(np.int64))
+        ev._bad = torch.zeros(1, dtype=torch.int64)
+        assert ev.all_reduce() is ev
+        want = O.confusion_matrix(gt_all, pred_all, 19)
+        assert np.array_equal(ev.confusion_matrix, want.astype(np.float64))
+        m = O.evaluator_metrics(want)
+        miou, iou = ev.Mean_Intersection_over_Union()
+        assert miou == m['mIoU'] and np.array_equal(iou, m['IoU']) and ev.Pixel_Accuracy() == m['PA']
+        assert ev.Pixel_Accuracy_Class() == m['mPA'] and ev.Frequency_Weighted_Intersection_over_Union() == m['fwIoU']
         q.put((rank, "ok"))
     except Exception as e:   # noqa: BLE001
         q.put((rank, "%s: %s" % (type(e).__name__, e)))
@@ -80,7 +101,7 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_sync_bn_and_grad_allreduce_protocol():
+def test_two_rank_sync_bn_grad_allreduce_and_evaluator_protocol():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
