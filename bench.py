@@ -308,9 +308,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries the ONE JSON line: NCCL's own banner / debug output ("NCCL version ..." when NCCL_DEBUG is
-        # set) goes to stderr unless the caller chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = sub("_lib")
     if not os.path.exists(L.LIB_PATH):
