@@ -265,6 +265,79 @@ def adapt_step_case():
     np.savez_compressed(os.path.join(HERE, 'adapt_step.npz'), **fix)
 
 
+def feature_step_case():
+    """Two iterations of train.py:173-204 (BASELINE config 4: FCN-in-the-wild feature adaptation) on the reference's
+    own modules -- MobileNetV2, ASPP, Decoder, DomainClassifer built as train.py:46-56 builds them, the three stepping
+    optimizers of :63-82 (both flavours: Adam, the script default, and SGD), DomainLosses -- vs the oracle's
+    feature_step.  The script body is restated device-agnostically (it calls .cuda() on its inputs)."""
+    import torch.nn.functional as F
+    nn = torch.nn
+    fix = {}
+    for flavour in ('Adam', 'SGD'):
+        torch.manual_seed(7)
+        bb = no_dropout(ref_mobilenet.MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d))
+        aspp = no_dropout(RefASPP(backbone='mobilenet', output_stride=16, BatchNorm=nn.BatchNorm2d))
+        dec = no_dropout(RefDecoder(num_classes=19, backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+        dc = no_dropout(RefDC(backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+        mods = (bb, aspp, dec, dc)
+        for m in mods:
+            m.train()
+        sds = [clone_sd(m) for m in mods]
+        lr = 5e-4
+        if flavour == 'Adam':
+            mk = lambda ps: torch.optim.Adam(ps, lr=lr)  # noqa: E731
+        else:
+            mk = lambda ps: torch.optim.SGD(ps, lr=lr, momentum=0.9, weight_decay=5e-4, nesterov=False)  # noqa: E731
+        f_params = list(bb.parameters()) + list(aspp.parameters())
+        opts = (mk(f_params + list(dec.parameters())), mk(list(dc.parameters())), mk(f_params))
+        c_opt = mk(f_params + list(dec.parameters()))              # train.py:73-75: scheduled and zeroed, never stepped
+        o_fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+        o_opts = (mk(o_fp + list(O.leaf_params(sds[2]).values())), mk(list(O.leaf_params(sds[3]).values())), mk(o_fp))
+        task_loss_fn = RefSegLoss().build_loss('ce')
+        domain_loss_fn = RefDomLoss().build_loss()
+        g = torch.Generator().manual_seed(11)
+        hist = []
+        for it in range(2):
+            src = torch.randn(2, 3, 64, 96, generator=g)
+            tgt = torch.randn(2, 3, 64, 96, generator=g)
+            lab = torch.randint(0, 19, (2, 64, 96), generator=g).float()
+            for o in opts + (c_opt,) + o_opts:
+                o.param_groups[0]['lr'] = O.poly_lr(lr, it, 10)          # lr_scheduler.py:63-70 (one group each)
+            for o in opts + (c_opt,):
+                o.zero_grad()
+            sh0, sl = bb(src)
+            sh = aspp(sh0)
+            so = F.interpolate(dec(sh, sl), src.size()[2:], mode='bilinear', align_corners=True)
+            sd_pred = dc(sh)
+            task = task_loss_fn(so, lab)
+            th0, tl = bb(tgt)
+            th = aspp(th0)
+            F.interpolate(dec(th, tl), tgt.size()[2:], mode='bilinear', align_corners=True)   # tgt_output: computed, unused
+            td_pred = dc(th)
+            d_loss, d_acc = domain_loss_fn(sd_pred, td_pred)
+            d_inv_loss, _ = domain_loss_fn(td_pred, sd_pred)
+            (task + d_loss + d_inv_loss).backward()
+            for o in opts:
+                o.step()
+            ref = (task.item(), d_loss.item(), d_inv_loss.item(), float(d_acc))
+            got = O.feature_step(sds[0], sds[1], sds[2], sds[3], o_opts, src, lab, tgt, O.BNCfg(True), drop=False)
+            print('feature', flavour, 'it', it, ref, got)
+            assert np.allclose(ref, got, rtol=2e-4, atol=1e-6), (ref, got)
+            hist.append(ref)
+        fix['losses_' + flavour] = np.array(hist, dtype=np.float64)
+        for sd, m, k in ((sds[0], bb, 'features.0.0.weight'), (sds[1], aspp, 'conv1.weight'),
+                         (sds[2], dec, 'last_conv.8.weight'), (sds[3], dc, 'DC_adnn3.weight')):
+            w = dict(m.named_parameters())[k].detach()
+            assert relerr(sd[k].detach(), w) < 2e-4, (flavour, k, relerr(sd[k].detach(), w))
+            fix['w_%s:%s' % (flavour, k)] = head(w)
+            fix['wnorm_%s:%s' % (flavour, k)] = np.float64(w.double().norm())
+        # running statistics saw both domains, source first
+        rm = dict(bb.named_buffers())['features.0.1.running_mean']
+        assert relerr(sds[0]['features.0.1.running_mean'], rm) < 1e-5
+        fix['rm_%s:features.0.1.running_mean' % flavour] = head(rm)
+    np.savez_compressed(os.path.join(HERE, 'feature_step.npz'), **fix)
+
+
 def shapes_case():
     """The output shapes of the reference's __main__ smoke blocks."""
     torch.manual_seed(0)
@@ -351,6 +424,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'policy':
         policy_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'feature':
+        feature_step_case()
+        sys.exit(0)
     shapes_case()
     evaluator_case()
     discriminator_case()
@@ -358,6 +434,7 @@ if __name__ == '__main__':
     deeplab_case('deeplab_train_2x65x97', 2, 65, 97, True)
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
+    feature_step_case()
     config1_case()
     policy_case()
     print('all golden fixtures written to', HERE)

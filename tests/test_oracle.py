@@ -219,6 +219,46 @@ def test_adapt_step_two_iterations():
     assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
 
 
+def test_feature_step_two_iterations():
+    """oracle.feature_step (train.py:173-204, BASELINE config 4) against the run of the reference's own MobileNetV2 /
+    ASPP / Decoder / DomainClassifer modules and torch optimizers recorded in tests/golden/feature_step.npz (Adam -- the
+    script default -- and SGD); the product's parameter containers, built under the same seed, start from the
+    reference's initial weights."""
+    fix = golden('feature_step')
+    nn = torch.nn
+    for flavour in ('Adam', 'SGD'):
+        torch.manual_seed(7)
+        mods = (sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d),
+                sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d),
+                sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d),
+                sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d))
+        sds = []
+        for mod in mods:
+            sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+            for v in O.leaf_params(sd).values():
+                v.requires_grad_(True)
+            sds.append(sd)
+        if flavour == 'Adam':
+            mk = lambda ps: torch.optim.Adam(ps, lr=5e-4)  # noqa: E731
+        else:
+            mk = lambda ps: torch.optim.SGD(ps, lr=5e-4, momentum=0.9, weight_decay=5e-4)  # noqa: E731
+        fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+        opts = (mk(fp + list(O.leaf_params(sds[2]).values())), mk(list(O.leaf_params(sds[3]).values())), mk(fp))
+        g = torch.Generator().manual_seed(11)
+        for it in range(2):
+            src = torch.randn(2, 3, 64, 96, generator=g)
+            tgt = torch.randn(2, 3, 64, 96, generator=g)
+            lab = torch.randint(0, 19, (2, 64, 96), generator=g).float()
+            for o in opts:
+                o.param_groups[0]['lr'] = O.poly_lr(5e-4, it, 10)
+            got = O.feature_step(sds[0], sds[1], sds[2], sds[3], opts, src, lab, tgt, O.BNCfg(True), drop=False)
+            assert np.allclose(got, fix['losses_' + flavour][it], rtol=2e-4, atol=1e-6), (flavour, it, got)
+        for sd, k in ((sds[0], 'features.0.0.weight'), (sds[1], 'conv1.weight'), (sds[2], 'last_conv.8.weight'),
+                      (sds[3], 'DC_adnn3.weight')):
+            assert rel(sd[k].detach().reshape(-1)[:4096], fix['w_%s:%s' % (flavour, k)]) < 2e-4, (flavour, k)
+        assert rel(sds[0]['features.0.1.running_mean'].reshape(-1)[:4096], fix['rm_%s:features.0.1.running_mean' % flavour]) < 1e-5
+
+
 def test_input_stage_oracle_and_host_tables_against_reference_fixture():
     """oracle/input_stage.py (and the host-side resampling tables of the device input stage) against the outputs of
     the reference's own TrainSet/ValSet pipeline stored by tests/golden/make_golden_input.py."""
