@@ -1,6 +1,7 @@
 """CPU restatement (numpy; test infrastructure only) of the reference's prediction export, test_adapt.py:118-157
 (`imgsaver`) after the host argmax of test_adapt.py:170-171; PIL's NEAREST resize is oracle.input_stage.resize_nearest
-(pinned against Pillow by tests/golden/make_golden_input.py)."""
+(pinned against Pillow by tests/golden/make_golden_input.py).  Pinned against the reference's own `imgsaver`, compiled
+unmodified out of test_adapt.py, by tests/golden/make_golden_report.py (tests/golden/report.npz)."""
 import numpy as np
 
 from .input_stage import nearest_table

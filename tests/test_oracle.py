@@ -366,6 +366,22 @@ def test_prediction_export_oracle_against_pillow():
     assert np.array_equal(ids, want_ids) and np.array_equal(rgb, want_rgb)
 
 
+def test_prediction_export_oracle_against_reference_fixture():
+    """oracle/report.py against the PNG files the reference's own `imgsaver` (test_adapt.py:118-157, compiled unmodified
+    out of the script by tests/golden/make_golden_report.py) wrote for the same predictions."""
+    import importlib.util
+    from oracle import report as OR
+    spec = importlib.util.spec_from_file_location("make_golden_report", os.path.join(ROOT, "tests", "golden", "make_golden_report.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fix = golden("report")
+    for seed in fix["seeds"]:
+        ids, rgb = OR.imgsaver_arrays(gen.logits(int(seed)))
+        assert np.array_equal(ids, fix["ids%d" % seed]) and np.array_equal(rgb, fix["rgb%d" % seed]), seed
+        assert len(np.unique(ids)) >= 15                       # a real mix of classes, labelIds of the valid classes only
+        assert set(np.unique(ids)) <= set(OR.VALID_CLASSES)
+
+
 def test_batched_input_stage_host_planning_with_emulated_kernels():
     """The REAL host planning of the batched device input stage (window of the scaled image per sample, job tables for
     the column / row / nearest / blur / crop launches) driven through a pure-Python emulation of the kernels reproduces
