@@ -338,6 +338,82 @@ def feature_step_case():
     np.savez_compressed(os.path.join(HERE, 'feature_step.npz'), **fix)
 
 
+def sync_bn_case():
+    """The reference's synchronised BatchNorm protocol (row a11: batchnorm.py:48-125, comm.py:18-129, replicate.py:27-44)
+    EXECUTED on the CPU: two replicas of one SynchronizedBatchNorm2d registered through the reference's own
+    execute_replication_callbacks, their forwards run in two threads so that the replica statistics really travel
+    through SlavePipe / SyncMaster.run_master / _data_parallel_master / _compute_mean_std.  Only the two torch-internal
+    CUDA collectives that function calls (torch.nn.parallel._functions.ReduceAddCoalesced / Broadcast) are replaced
+    by their CPU meaning (sum of the replica tensors / the same tensors for every replica).  Compared with the
+    oracle's sync_clamp branch on the concatenated batch: outputs, running statistics, all gradients."""
+    import copy
+    import threading
+    from modeling.sync_batchnorm import batchnorm as ref_bn
+    from modeling.sync_batchnorm import replicate as ref_rep
+
+    class _Reduce:
+        @staticmethod
+        def apply(dev, n, *ts):
+            return tuple(sum(ts[i::n][1:], ts[i::n][0]) for i in range(n))
+
+    class _Bcast:
+        @staticmethod
+        def apply(devs, *ts):
+            return tuple(ts) * len(devs)
+
+    ref_bn.ReduceAddCoalesced, ref_bn.Broadcast = _Reduce, _Bcast
+    Cc = 6
+    g = torch.Generator().manual_seed(21)
+    x_all = torch.randn(5, Cc, 7, 9, generator=g) * 2 + 0.5
+    x_all[:, 2] = 0.75                                     # a constant channel: variance 0 -> clamp(eps), not var + eps
+    dy_all = torch.randn(5, Cc, 7, 9, generator=g)
+    shards = (slice(0, 2), slice(2, 5))                    # unequal replica batches
+    bn = ref_bn.SynchronizedBatchNorm2d(Cc)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(Cc, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(Cc, generator=g))
+    bn.train()
+    sd = {'bn.weight': bn.weight.detach().clone().requires_grad_(True), 'bn.bias': bn.bias.detach().clone().requires_grad_(True),
+          'bn.running_mean': bn.running_mean.clone(), 'bn.running_var': bn.running_var.clone()}
+    replicas = []
+    for _ in shards:
+        r = copy.copy(bn)
+        r._parameters, r._buffers = bn._parameters.copy(), bn._buffers.copy()
+        replicas.append(r)
+    ref_rep.execute_replication_callbacks(replicas)
+    xs = [x_all[s].clone().requires_grad_(True) for s in shards]
+    outs = [None, None]
+
+    def work(i):
+        outs[i] = replicas[i](xs[i])
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert all(o is not None for o in outs)
+    sum((o * dy_all[s]).sum() for o, s in zip(outs, shards)).backward()
+    y_ref = torch.cat([o.detach() for o in outs])
+    xr = x_all.clone().requires_grad_(True)
+    y = O.batch_norm(sd, 'bn', xr, O.BNCfg(True, 0.1, 1e-5, sync_clamp=True))
+    (y * dy_all).sum().backward()
+    # the updated running statistics land on the ORIGINAL module: the replicas share its SyncMaster, whose callback is
+    # the original's bound _data_parallel_master (batchnorm.py:44, :122-123 assign them on that `self`)
+    rm, rv = bn.running_mean, bn.running_var
+    assert relerr(y.detach(), y_ref) < 1e-6
+    assert relerr(sd['bn.running_mean'], rm) < 1e-6 and relerr(sd['bn.running_var'], rv) < 1e-6
+    dx_ref = torch.cat([x.grad for x in xs])
+    assert relerr(xr.grad, dx_ref) < 1e-5, relerr(xr.grad, dx_ref)
+    assert relerr(sd['bn.weight'].grad, bn.weight.grad) < 1e-5 and relerr(sd['bn.bias'].grad, bn.bias.grad) < 1e-5
+    # F.batch_norm (the non-parallel branch) differs on the constant channel: 1/sqrt(var + eps) vs clamp(var, eps)^-1/2
+    print('sync-bn: y', relerr(y.detach(), y_ref), 'dx', relerr(xr.grad, dx_ref), 'running_var', rv.tolist())
+    np.savez_compressed(os.path.join(HERE, 'sync_bn.npz'), x=x_all.numpy(), dy=dy_all.numpy(),
+                        weight=bn.weight.detach().numpy(), bias=bn.bias.detach().numpy(), y=y_ref.numpy(),
+                        dx=dx_ref.numpy(), dweight=bn.weight.grad.numpy(), dbias=bn.bias.grad.numpy(),
+                        running_mean=rm.numpy(), running_var=rv.numpy())
+
+
 def shapes_case():
     """The output shapes of the reference's __main__ smoke blocks."""
     torch.manual_seed(0)
@@ -424,6 +500,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'policy':
         policy_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'syncbn':
+        sync_bn_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'feature':
         feature_step_case()
         sys.exit(0)
@@ -434,6 +513,7 @@ if __name__ == '__main__':
     deeplab_case('deeplab_train_2x65x97', 2, 65, 97, True)
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
+    sync_bn_case()
     feature_step_case()
     config1_case()
     policy_case()

@@ -219,6 +219,26 @@ def test_adapt_step_two_iterations():
     assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
 
 
+def test_sync_batchnorm_against_reference_protocol_fixture():
+    """The oracle's synchronised-BatchNorm branch (batchnorm.py:55-78,113-125 over the whole batch) against the
+    reference's protocol executed with two replicas through its own SyncMaster / SlavePipe (tests/golden/
+    make_golden.py sync_bn_case): outputs, running statistics, gradients -- including a zero-variance channel, where
+    clamp(var, eps)^-1/2 and F.batch_norm's 1/sqrt(var + eps) differ."""
+    fix = golden('sync_bn')
+    sd = {'bn.weight': torch.from_numpy(fix['weight']).clone().requires_grad_(True),
+          'bn.bias': torch.from_numpy(fix['bias']).clone().requires_grad_(True),
+          'bn.running_mean': torch.zeros(6), 'bn.running_var': torch.ones(6)}
+    x = torch.from_numpy(fix['x']).clone().requires_grad_(True)
+    y = O.batch_norm(sd, 'bn', x, O.BNCfg(True, 0.1, 1e-5, sync_clamp=True))
+    (y * torch.from_numpy(fix['dy'])).sum().backward()
+    assert rel(y.detach(), fix['y']) < 1e-6 and rel(x.grad, fix['dx']) < 1e-5
+    assert rel(sd['bn.weight'].grad, fix['dweight']) < 1e-5 and rel(sd['bn.bias'].grad, fix['dbias']) < 1e-5
+    assert rel(sd['bn.running_mean'], fix['running_mean']) < 1e-6 and rel(sd['bn.running_var'], fix['running_var']) < 1e-6
+    assert abs(float(sd['bn.running_var'][2]) - 0.9) < 1e-6           # the constant channel
+    plain = O.batch_norm({k: v.detach().clone() for k, v in sd.items()}, 'bn', x.detach(), O.BNCfg(True, 0.1, 1e-5))
+    assert rel(plain[:, [0, 1, 3, 4, 5]], fix['y'][:, [0, 1, 3, 4, 5]]) < 1e-5   # same normalisation elsewhere
+
+
 def test_feature_step_two_iterations():
     """oracle.feature_step (train.py:173-204, BASELINE config 4) against the run of the reference's own MobileNetV2 /
     ASPP / Decoder / DomainClassifer modules and torch optimizers recorded in tests/golden/feature_step.npz (Adam -- the
