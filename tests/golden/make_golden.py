@@ -414,6 +414,74 @@ def sync_bn_case():
                         running_mean=rm.numpy(), running_var=rv.numpy())
 
 
+def reference_method(script, name, ns):
+    """A method of one of the reference's top-level scripts, compiled UNMODIFIED from its source segment (the scripts
+    themselves cannot be imported: tensorboardX is missing and they parse argv / build CUDA loaders at import)."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, script)).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), script, 'exec'), ns)
+            return ns[name]
+    raise RuntimeError('%s not found in %s' % (name, script))
+
+
+def validation_case():
+    """BASELINE config 5: the reference's own `Trainer.validation` (val_adapt.py:117-175, unmodified) run on the CPU
+    over three batches (2 + 2 + 1 images) with the reference's DeepLab, criterion and Evaluator; it appends its report
+    to val_info.txt.  Checked against it: the oracle's eval forward + argmax + confusion matrix + metrics and summed
+    loss, and the product's report text (utils.report.validation_report) character for character."""
+    import importlib
+    import tempfile
+    import types
+
+    class Bar(list):
+        def set_description(self, text):
+            pass
+
+    validation = reference_method('val_adapt.py', 'validation', {'np': np, 'torch': torch, 'tqdm': lambda it, desc='': Bar(it)})
+    torch.manual_seed(1)
+    ref = RefDeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    # give the BatchNorms non-trivial running statistics, as after training
+    g = torch.Generator().manual_seed(5)
+    for m in ref.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    sd = clone_sd(ref, grad=False)
+    batches = []
+    for k, n in enumerate((2, 2, 1)):
+        x, lab = make_inputs(300 + k, n, 65, 97)
+        batches.append({'image': x, 'label': lab})
+    trainer = types.SimpleNamespace(model=ref, evaluator=RefEvaluator(19), val_loader=batches,
+                                    criterion=RefSegLoss().build_loss('ce'), args=types.SimpleNamespace(cuda=False, batch_size=2))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            validation(trainer, 3)
+            text = open('val_info.txt').read()
+        finally:
+            os.chdir(cwd)
+    # oracle: val_adapt.py:122-135 restated
+    cm = np.zeros((19, 19), np.int64)
+    test_loss = 0.0
+    with torch.no_grad():
+        for b in batches:
+            out = O.deeplab_forward(sd, b['image'], O.BNCfg(False), 16)
+            test_loss += O.seg_cross_entropy(out, b['label']).item()
+            cm += O.confusion_matrix(b['label'].numpy(), np.argmax(out.numpy(), axis=1), 19)
+    assert np.array_equal(cm, trainer.evaluator.confusion_matrix)
+    m = O.evaluator_metrics(cm)
+    assert m['mIoU'] == trainer.evaluator.Mean_Intersection_over_Union()[0]
+    rep = importlib.import_module('synthetic-to-real-semantic-segmentation_b200.utils.report')
+    mine = rep.validation_report(trainer.evaluator, 3, 5, test_loss)
+    assert mine == text, (mine, text)
+    print(text)
+    np.savez_compressed(os.path.join(HERE, 'validation.npz'), text=np.array(text), confusion_matrix=cm,
+                        test_loss=np.float64(test_loss), epoch=np.int64(3), num_images=np.int64(5))
+
+
 def shapes_case():
     """The output shapes of the reference's __main__ smoke blocks."""
     torch.manual_seed(0)
@@ -500,6 +568,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'policy':
         policy_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'validation':
+        validation_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'syncbn':
         sync_bn_case()
         sys.exit(0)
@@ -514,6 +585,7 @@ if __name__ == '__main__':
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
     sync_bn_case()
+    validation_case()
     feature_step_case()
     config1_case()
     policy_case()

@@ -219,6 +219,22 @@ def test_adapt_step_two_iterations():
     assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
 
 
+def test_validation_report_against_reference_run():
+    """BASELINE config 5: the report the reference's own `Trainer.validation` (val_adapt.py:117-175, run unmodified on
+    the CPU by tests/golden/make_golden.py validation_case) appended to val_info.txt, against the product's metric
+    formulas (utils.metrics.Evaluator on the recorded counts) and report text (utils.report.validation_report),
+    character for character; the oracle's metrics on the same matrix."""
+    fix = golden('validation')
+    ev = sub("utils.metrics").Evaluator(19)
+    ev._counts = torch.from_numpy(fix['confusion_matrix'].astype(np.int64))       # as accumulated by the kernels
+    ev._bad = torch.zeros(1, dtype=torch.int64)
+    text = sub("utils.report").validation_report(ev, int(fix['epoch']), int(fix['num_images']), float(fix['test_loss']))
+    assert text == str(fix['text'])
+    m = O.evaluator_metrics(fix['confusion_matrix'])
+    assert "mIoU:{}, fwIoU: {}".format(m['mIoU'], m['fwIoU']) in text and "Acc:{}, Acc_class:{},".format(m['PA'], m['mPA']) in text
+    assert 0.9 * 5 * 65 * 97 < int(fix['confusion_matrix'].sum()) < 5 * 65 * 97      # valid pixels: all but the ~5 % ignored
+
+
 def test_sync_batchnorm_against_reference_protocol_fixture():
     """The oracle's synchronised-BatchNorm branch (batchnorm.py:55-78,113-125 over the whole batch) against the
     reference's protocol executed with two replicas through its own SyncMaster / SlavePipe (tests/golden/
