@@ -11,9 +11,12 @@ reference's key names.  Each function cites the reference lines it follows.
 
 Pinning: the reference ships no golden vectors or tests for this path.  tests/golden/make_golden.py
 imports the real reference modules from /root/reference, checks this port against them (forward,
-loss, parameter gradients, one full adaptation step) and writes the fixtures under tests/golden/
-that tests/test_oracle.py re-checks on every run -- parity is pinned on reference outputs
-generated in the build container, not on reference-owned vectors.
+loss, parameter gradients; the reference's own Trainer.training of train_adapt.py and
+Trainer.validation of val_adapt.py compiled unmodified out of the scripts and run on the CPU; the
+feature-adaptation step of train.py on the reference's modules; the synchronised-BatchNorm protocol
+executed through the reference's SyncMaster) and writes the fixtures under tests/golden/ that
+tests/test_oracle.py re-checks on every run -- parity is pinned on reference outputs generated in
+the build container, not on reference-owned vectors.
 """
 import math
 

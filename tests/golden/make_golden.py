@@ -426,6 +426,83 @@ def reference_method(script, name, ns):
     raise RuntimeError('%s not found in %s' % (name, script))
 
 
+def adapt_loop_case():
+    """BASELINE configs 2/3: the reference's own `Trainer.training` (train_adapt.py:115-196, unmodified source
+    segment) run for one epoch of ten iterations on the CPU -- reference DeepLab / FCDiscriminator / criterion /
+    LR_Scheduler / torch optimizers; the only concession is `Tensor.cuda()` made the identity while it runs (the body
+    calls it unconditionally on its BCE targets).  Per-iteration losses are recorded by wrapping the two loss
+    callables.  Compared with ten oracle adapt_step iterations under the oracle's poly schedule."""
+    import types
+    import torch.nn.functional as F
+    from torch.autograd import Variable
+    from utils.lr_scheduler import LR_Scheduler as RefSched
+
+    class Bar(list):
+        def set_description(self, text):
+            pass
+
+    training = reference_method('train_adapt.py', 'training', {'np': np, 'torch': torch, 'F': F, 'Variable': Variable,
+                                                               'tqdm': lambda it: Bar(it)})
+    torch.manual_seed(1)
+    G = no_dropout(RefDeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False))
+    D = RefD(num_classes=19)
+    D.train()
+    g_sd, d_sd = clone_sd(G), clone_sd(D)
+    lr, n_it = 5e-4, 10
+    opt = torch.optim.SGD([{'params': G.get_1x_lr_params(), 'lr': lr}, {'params': G.get_10x_lr_params(), 'lr': lr * 10}],
+                          momentum=0.9, weight_decay=5e-4, nesterov=False)                      # train_adapt.py:54-58
+    opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.9, 0.99))                         # :59-60
+    one, ten = O.split_lr_groups(list(O.leaf_params(g_sd).keys()))
+    o_opt = torch.optim.SGD([{'params': [g_sd[k] for k in one], 'lr': lr}, {'params': [g_sd[k] for k in ten], 'lr': lr * 10}],
+                            momentum=0.9, weight_decay=5e-4, nesterov=False)
+    o_opt_d = torch.optim.Adam(list(O.leaf_params(d_sd).values()), lr=1e-4, betas=(0.9, 0.99))
+    loader = []
+    for it in range(n_it):
+        src, lab = make_inputs(400 + it, 2, 49, 65)
+        tgt, _ = make_inputs(500 + it, 2, 49, 65)
+        loader.append({'src_image': src, 'src_label': lab, 'tgt_image': tgt})
+    seen = []
+
+    def recorded(fn):
+        def wrapper(*a):
+            out = fn(*a)
+            seen.append(out.item())
+            return out
+        return wrapper
+
+    quiet = types.SimpleNamespace(add_scalar=lambda *a: None, visualize_image=lambda *a: None)
+    trainer = types.SimpleNamespace(model=G, model_D=D, optimizer=opt, optimizer_D=opt_d, train_loader=loader,
+                                    scheduler=RefSched('poly', lr, 1, n_it), best_pred=0.0,
+                                    criterion=recorded(RefSegLoss().build_loss('ce')),
+                                    bce_loss=recorded(torch.nn.BCEWithLogitsLoss()), writer=quiet, summary=quiet,
+                                    args=types.SimpleNamespace(cuda=False, batch_size=2, dataset='gtav2cityscapes', no_val=False))
+    old_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        training(trainer, 0)
+    finally:
+        torch.Tensor.cuda = old_cuda
+    ref_hist = np.array(seen, dtype=np.float64).reshape(n_it, 4)     # loss_seg, loss_adv, loss_D(src), loss_D(tgt)
+    cfg = O.BNCfg(True)
+    o_hist = []
+    for it, b in enumerate(loader):
+        for o in (o_opt, o_opt_d):
+            for gi, grp in enumerate(o.param_groups):
+                grp['lr'] = O.poly_lr(lr, it, n_it) * (10 if gi > 0 else 1)
+        o_hist.append(O.adapt_step(g_sd, d_sd, o_opt, o_opt_d, b['src_image'], b['src_label'], b['tgt_image'], cfg, drop=False))
+    o_hist = np.array(o_hist, dtype=np.float64)
+    print('adapt loop: reference', ref_hist[[0, 1, n_it - 1]].tolist(), 'oracle', o_hist[[0, 1, n_it - 1]].tolist())
+    assert np.allclose(ref_hist, o_hist, rtol=1e-3, atol=1e-5), np.abs(ref_hist / o_hist - 1).max()
+    fix = dict(losses=ref_hist)
+    for k in ['backbone.features.0.0.weight', 'decoder.last_conv.8.weight']:
+        w = dict(G.named_parameters())[k].detach()
+        assert relerr(g_sd[k].detach(), w) < 1e-3, (k, relerr(g_sd[k].detach(), w))
+        fix['w:' + k] = head(w)
+    assert relerr(d_sd['conv1.weight'].detach(), D.conv1.weight.detach()) < 1e-3
+    fix['wd:conv1.weight'] = head(D.conv1.weight)
+    np.savez_compressed(os.path.join(HERE, 'adapt_loop.npz'), **fix)
+
+
 def validation_case():
     """BASELINE config 5: the reference's own `Trainer.validation` (val_adapt.py:117-175, unmodified) run on the CPU
     over three batches (2 + 2 + 1 images) with the reference's DeepLab, criterion and Evaluator; it appends its report
@@ -568,6 +645,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'policy':
         policy_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'adaptloop':
+        adapt_loop_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'validation':
         validation_case()
         sys.exit(0)
@@ -584,6 +664,7 @@ if __name__ == '__main__':
     deeplab_case('deeplab_train_2x65x97', 2, 65, 97, True)
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
+    adapt_loop_case()
     sync_bn_case()
     validation_case()
     feature_step_case()

@@ -219,6 +219,42 @@ def test_adapt_step_two_iterations():
     assert rel(d_sd['conv1.weight'].detach().reshape(-1)[:4096], fix['wd:conv1.weight']) < 1e-4
 
 
+def test_adapt_loop_against_reference_training_run():
+    """BASELINE configs 2/3: the loss history of the reference's own `Trainer.training` (train_adapt.py:115-196, run
+    unmodified for ten iterations on the CPU by tests/golden/make_golden.py adapt_loop_case, where all ten are checked)
+    against the oracle's adapt_step from the same seed -- the first three iterations here, to keep the suite short."""
+    fix = golden('adapt_loop')
+    assert fix['losses'].shape == (10, 4)
+    torch.manual_seed(1)
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    D = sub("modeling.discriminator").FCDiscriminator(num_classes=19)
+    g_sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    for sd in (g_sd, d_sd):
+        for v in O.leaf_params(sd).values():
+            v.requires_grad_(True)
+    one, ten = O.split_lr_groups(list(O.leaf_params(g_sd).keys()))
+    opt = torch.optim.SGD([{'params': [g_sd[k] for k in one], 'lr': 5e-4}, {'params': [g_sd[k] for k in ten], 'lr': 5e-3}],
+                          momentum=0.9, weight_decay=5e-4)
+    opt_d = torch.optim.Adam(list(O.leaf_params(d_sd).values()), lr=1e-4, betas=(0.9, 0.99))
+
+    def inputs(seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(2, 3, 49, 65, generator=g)
+        lab = torch.randint(0, 20, (2, 49, 65), generator=g).float()
+        lab[lab == 19] = 255
+        return x, lab
+
+    for it in range(3):
+        src, lab = inputs(400 + it)
+        tgt, _ = inputs(500 + it)
+        for o in (opt, opt_d):
+            for gi, grp in enumerate(o.param_groups):
+                grp['lr'] = O.poly_lr(5e-4, it, 10) * (10 if gi > 0 else 1)
+        got = O.adapt_step(g_sd, d_sd, opt, opt_d, src, lab, tgt, O.BNCfg(True), drop=False)
+        assert np.allclose(got, fix['losses'][it], rtol=1e-3, atol=1e-5), (it, got, fix['losses'][it])
+
+
 def test_validation_report_against_reference_run():
     """BASELINE config 5: the report the reference's own `Trainer.validation` (val_adapt.py:117-175, run unmodified on
     the CPU by tests/golden/make_golden.py validation_case) appended to val_info.txt, against the product's metric
