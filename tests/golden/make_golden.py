@@ -503,6 +503,71 @@ def adapt_loop_case():
     np.savez_compressed(os.path.join(HERE, 'adapt_loop.npz'), **fix)
 
 
+def feature_loop_case():
+    """BASELINE config 4 on the reference's own code: `Trainer.training` of train.py (:152-232, unmodified source
+    segment) for one epoch of ten iterations on the CPU with the reference's modules, DomainLosses, LR_Scheduler and
+    the script's default Adam optimizers (train.py:76-80), against ten oracle feature_step iterations."""
+    import types
+    import torch.nn.functional as F
+    from utils.lr_scheduler import LR_Scheduler as RefSched
+    nn = torch.nn
+
+    class Bar(list):
+        def set_description(self, text):
+            pass
+
+    training = reference_method('train.py', 'training', {'np': np, 'torch': torch, 'F': F, 'tqdm': lambda it: Bar(it)})
+    torch.manual_seed(7)
+    bb = no_dropout(ref_mobilenet.MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d))
+    aspp = no_dropout(RefASPP(backbone='mobilenet', output_stride=16, BatchNorm=nn.BatchNorm2d))
+    dec = no_dropout(RefDecoder(num_classes=19, backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+    dc = no_dropout(RefDC(backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+    sds = [clone_sd(m) for m in (bb, aspp, dec, dc)]
+    lr, n_it = 5e-4, 10
+    f_params = list(bb.parameters()) + list(aspp.parameters())
+    mk = lambda ps: torch.optim.Adam(ps, lr=lr)  # noqa: E731
+    o_fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+    o_opts = (mk(o_fp + list(O.leaf_params(sds[2]).values())), mk(list(O.leaf_params(sds[3]).values())), mk(o_fp))
+    loader = []
+    g = torch.Generator().manual_seed(13)
+    for it in range(n_it):
+        loader.append({'src_image': torch.randn(2, 3, 48, 64, generator=g), 'tgt_image': torch.randn(2, 3, 48, 64, generator=g),
+                       'src_label': torch.randint(0, 19, (2, 48, 64), generator=g).float()})
+    seen = []
+
+    def recorded(fn):
+        def wrapper(*a):
+            out = fn(*a)
+            seen.append(out.item() if torch.is_tensor(out) else (out[0].item(), out[1]))
+            return out
+        return wrapper
+
+    quiet = types.SimpleNamespace(add_scalar=lambda *a: None, visualize_image=lambda *a: None)
+    trainer = types.SimpleNamespace(
+        backbone_model=bb, assp_model=aspp, y_model=dec, d_model=dc,
+        task_optimizer=mk(f_params + list(dec.parameters())), d_optimizer=mk(list(dc.parameters())),
+        d_inv_optimizer=mk(f_params), c_optimizer=mk(f_params + list(dec.parameters())),
+        scheduler=RefSched('poly', lr, 1, n_it), best_pred=0.0, train_loader=loader,
+        task_loss=recorded(RefSegLoss().build_loss('ce')), domain_loss=recorded(RefDomLoss().build_loss()),
+        writer=quiet, summary=quiet, args=types.SimpleNamespace(cuda=False, batch_size=2, dataset='gtav2cityscapes', no_val=False))
+    training(trainer, 0)
+    # per iteration the body calls task_loss, domain_loss(src, tgt), domain_loss(tgt, src)
+    ref_hist = np.array([[seen[3 * i], seen[3 * i + 1][0], seen[3 * i + 2][0], seen[3 * i + 1][1]] for i in range(n_it)])
+    o_hist = []
+    for it, b in enumerate(loader):
+        for o in o_opts:
+            o.param_groups[0]['lr'] = O.poly_lr(lr, it, n_it)
+        o_hist.append(O.feature_step(sds[0], sds[1], sds[2], sds[3], o_opts, b['src_image'], b['src_label'], b['tgt_image'],
+                                     O.BNCfg(True), drop=False))
+    o_hist = np.array(o_hist, dtype=np.float64)
+    print('feature loop: reference', ref_hist[[0, n_it - 1]].tolist(), 'oracle', o_hist[[0, n_it - 1]].tolist())
+    assert np.allclose(ref_hist, o_hist, rtol=2e-3, atol=1e-5), np.abs(ref_hist / o_hist - 1).max()
+    for sd, m, k in ((sds[0], bb, 'features.0.0.weight'), (sds[2], dec, 'last_conv.8.weight'), (sds[3], dc, 'DC_adnn3.weight')):
+        w = dict(m.named_parameters())[k].detach()
+        assert relerr(sd[k].detach(), w) < 2e-3, (k, relerr(sd[k].detach(), w))
+    np.savez_compressed(os.path.join(HERE, 'feature_loop.npz'), losses=ref_hist)
+
+
 def validation_case():
     """BASELINE config 5: the reference's own `Trainer.validation` (val_adapt.py:117-175, unmodified) run on the CPU
     over three batches (2 + 2 + 1 images) with the reference's DeepLab, criterion and Evaluator; it appends its report
@@ -645,6 +710,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'policy':
         policy_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'featureloop':
+        feature_loop_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'adaptloop':
         adapt_loop_case()
         sys.exit(0)
@@ -665,6 +733,7 @@ if __name__ == '__main__':
     deeplab_case('deeplab_eval_1x97x65', 1, 97, 65, False)
     adapt_step_case()
     adapt_loop_case()
+    feature_loop_case()
     sync_bn_case()
     validation_case()
     feature_step_case()

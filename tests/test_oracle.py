@@ -255,6 +255,37 @@ def test_adapt_loop_against_reference_training_run():
         assert np.allclose(got, fix['losses'][it], rtol=1e-3, atol=1e-5), (it, got, fix['losses'][it])
 
 
+def test_feature_loop_against_reference_training_run():
+    """BASELINE config 4: the loss / domain-accuracy history of the reference's own `Trainer.training` of train.py (run
+    unmodified for ten iterations on the CPU by tests/golden/make_golden.py feature_loop_case, where all ten are
+    checked) against the oracle's feature_step -- the first two iterations here."""
+    fix = golden('feature_loop')
+    assert fix['losses'].shape == (10, 4)
+    nn = torch.nn
+    torch.manual_seed(7)
+    mods = (sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d),
+            sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d),
+            sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d),
+            sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d))
+    sds = []
+    for mod in mods:
+        sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+        for v in O.leaf_params(sd).values():
+            v.requires_grad_(True)
+        sds.append(sd)
+    fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+    opts = (torch.optim.Adam(fp + list(O.leaf_params(sds[2]).values()), lr=5e-4),
+            torch.optim.Adam(list(O.leaf_params(sds[3]).values()), lr=5e-4), torch.optim.Adam(fp, lr=5e-4))
+    g = torch.Generator().manual_seed(13)
+    for it in range(2):
+        src, tgt = torch.randn(2, 3, 48, 64, generator=g), torch.randn(2, 3, 48, 64, generator=g)
+        lab = torch.randint(0, 19, (2, 48, 64), generator=g).float()
+        for o in opts:
+            o.param_groups[0]['lr'] = O.poly_lr(5e-4, it, 10)
+        got = O.feature_step(sds[0], sds[1], sds[2], sds[3], opts, src, lab, tgt, O.BNCfg(True), drop=False)
+        assert np.allclose(got, fix['losses'][it], rtol=2e-3, atol=1e-5), (it, got, fix['losses'][it])
+
+
 def test_validation_report_against_reference_run():
     """BASELINE config 5: the report the reference's own `Trainer.validation` (val_adapt.py:117-175, run unmodified on
     the CPU by tests/golden/make_golden.py validation_case) appended to val_info.txt, against the product's metric
