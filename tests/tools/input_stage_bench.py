@@ -68,3 +68,32 @@ for n in range(N):
     ok &= np.array_equal(m, out['src_label'][n].cpu().numpy())
 cpu_ms = (time.time() - t0) * 1e3
 print("Pillow + numpy on 1 host core: %.1f ms per batch (includes the comparison); device output bit-identical: %s" % (cpu_ms, ok))
+
+# RandomGaussianBlur on every sample of the batch (the reference fires it on half of them), own radius per image,
+# against Pillow's GaussianBlur on the host
+from PIL import ImageFilter
+bdraws = [tuple(d) + (True, random.random(), random.random()) for d in draws]
+for _ in range(2):
+    outb = tr(d_src, d_tgt, d_lab, draws=bdraws)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(5):
+    outb = tr(d_src, d_tgt, d_lab, draws=bdraws)
+e1.record(); torch.cuda.synchronize()
+ms_b = e0.elapsed_time(e1) / 5
+ok = True
+for n in range(N):
+    flip, short, x1, y1, _, r_src, r_tgt = bdraws[n]
+    for key, t, r in (('src_image', src, r_src), ('tgt_image', tgt, r_tgt)):
+        im = Image.fromarray(t[n].numpy())
+        if flip:
+            im = im.transpose(Image.FLIP_LEFT_RIGHT)
+        ow, oh = dt._scale_size(W, H, short)
+        im = im.resize((ow, oh), Image.BILINEAR)
+        if short < CROP:
+            im = ImageOps.expand(im, border=(0, 0, CROP - ow if ow < CROP else 0, CROP - oh if oh < CROP else 0), fill=0)
+        im = im.crop((x1, y1, x1 + CROP, y1 + CROP)).filter(ImageFilter.GaussianBlur(radius=r))
+        a = np.array(im).astype(np.float32); a /= 255.0; a -= mean; a /= std
+        ok &= np.array_equal(a.transpose((2, 0, 1)), outb[key][n].cpu().numpy())
+print("with RandomGaussianBlur on all %d pairs: %.2f ms per batch (+%.2f ms for the two blur launches); identical to Pillow: %s"
+      % (N, ms_b, ms_b - ms, ok))
