@@ -4,12 +4,11 @@ Four parallel conv(+BN+ReLU) branches (1x1 and three dilated 3x3) and the image-
 write straight into channel slices of one NHWC concat buffer (no torch.cat copy), followed by the
 1x1 1280->256 projection, BN, ReLU and Dropout(0.5).
 """
-import torch
 import torch.nn as nn
 
 from .. import _lib as L
 from ..engine import ConvBNAct
-from ..runtime import RunBase, call_module
+from ..runtime import RunBase, call_module, init_reference_weights
 
 
 class _ASPPModule(nn.Module):
@@ -19,19 +18,10 @@ class _ASPPModule(nn.Module):
                                      dilation=dilation, bias=False)
         self.bn = BatchNorm(planes)
         self.relu = nn.ReLU()
-        _init_weight(self)
+        init_reference_weights(self)
 
     def forward(self, x):
         raise L.S2RError("_ASPPModule is executed by its ASPP parent on the fused kernels")
-
-
-def _init_weight(module):
-    for m in module.modules():
-        if isinstance(m, nn.Conv2d):
-            torch.nn.init.kaiming_normal_(m.weight)
-        elif isinstance(m, nn.modules.batchnorm._BatchNorm):
-            m.weight.data.fill_(1)
-            m.bias.data.zero_()
 
 
 class ASPPRun(RunBase):
@@ -98,7 +88,7 @@ class ASPP(nn.Module):
         self.bn1 = BatchNorm(256)
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(0.5)
-        _init_weight(self)
+        init_reference_weights(self)
         self._s2r_has_sync_bn = bool(getattr(BatchNorm, "_s2r_sync", False))
 
     def forward(self, x):

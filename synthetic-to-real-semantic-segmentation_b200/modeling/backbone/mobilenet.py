@@ -12,8 +12,8 @@ import torch.nn as nn
 
 from .. import sync_batchnorm  # noqa: F401
 from ... import _lib as L
-from ...engine import ConvBNAct, InvertedResidual as BlockRun, bn_backward, _vp
-from ...runtime import RunBase, call_module
+from ...engine import ConvBNAct, InvertedResidual as BlockRun, bn_backward
+from ...runtime import RunBase, call_module, init_reference_weights
 
 # expansion t, channels c, repeats n, stride s  (mobilenet.py:78-87 of the reference)
 _BLOCK_TABLE = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
@@ -114,7 +114,7 @@ class MobileNetV2(nn.Module):
                 feats.append(InvertedResidual(input_channel, oup, stride if i == 0 else 1, dilation, t, BatchNorm))
                 input_channel = oup
         self.features = nn.Sequential(*feats)
-        self._initialize_weights()
+        init_reference_weights(self)
         if pretrained:
             self._load_pretrained_model()
         self.low_level_features = self.features[0:4]
@@ -133,11 +133,3 @@ class MobileNetV2(nn.Module):
         state_dict = self.state_dict()
         state_dict.update({k: v for k, v in pretrain_dict.items() if k in state_dict})
         self.load_state_dict(state_dict)
-
-    def _initialize_weights(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                torch.nn.init.kaiming_normal_(m.weight)
-            elif isinstance(m, nn.modules.batchnorm._BatchNorm):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()

@@ -4,12 +4,11 @@ low-level 1x1 (24->48)+BN+ReLU and the x4 bilinear up-sampling of the ASPP outpu
 two channel slices of one NHWC concat buffer; then 3x3 304->256, 3x3 256->256 (each BN, ReLU,
 Dropout) and the biased 1x1 classifier.
 """
-import torch
 import torch.nn as nn
 
 from .. import _lib as L
 from ..engine import ConvBNAct, conv_fwd, conv_dgrad, conv_wgrad, bias_grad, round_up
-from ..runtime import RunBase, call_module
+from ..runtime import RunBase, call_module, init_reference_weights
 
 
 class DecoderRun(RunBase):
@@ -76,19 +75,11 @@ class Decoder(nn.Module):
                                        nn.ReLU(),
                                        nn.Dropout(0.1),
                                        nn.Conv2d(256, num_classes, kernel_size=1, stride=1))
-        self._init_weight()
+        init_reference_weights(self)
         self._s2r_has_sync_bn = bool(getattr(BatchNorm, "_s2r_sync", False))
 
     def forward(self, x, low_level_feat):
         return call_module(self, lambda: DecoderRun(self), (x, low_level_feat))
-
-    def _init_weight(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                torch.nn.init.kaiming_normal_(m.weight)
-            elif isinstance(m, nn.modules.batchnorm._BatchNorm):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
 
 
 def build_decoder(num_classes, backbone, BatchNorm):

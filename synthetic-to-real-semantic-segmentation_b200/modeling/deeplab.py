@@ -8,7 +8,7 @@ up-sampling (deeplab.py:31) writes the NCHW fp32 logits the callers expect.
 import torch.nn as nn
 
 from .. import _lib as L
-from ..engine import _vp, round_up
+from ..engine import _vp
 from ..functional import pop_pending_scale
 from ..runtime import RunBase, call_module
 from .sync_batchnorm import SynchronizedBatchNorm2d

@@ -1,11 +1,10 @@
 """Domain classifier of the FCN-in-the-wild feature adaptation, with the reference's (misspelt)
 module/class names and state_dict keys (modeling/domian.py:7-47)."""
-import torch
 import torch.nn as nn
 
 from .. import _lib as L
 from ..engine import ConvBNAct, conv_fwd, conv_dgrad, conv_wgrad, bias_grad, round_up
-from ..runtime import RunBase, call_module
+from ..runtime import RunBase, call_module, init_reference_weights
 
 
 class DomainClassiferRun(RunBase):
@@ -53,19 +52,11 @@ class DomainClassifer(nn.Module):
                                       nn.ReLU(),
                                       nn.Dropout(0.5))
         self.DC_adnn3 = nn.Conv2d(1024, 2, kernel_size=3, stride=1, padding=1, bias=True)
-        self._init_weight()
+        init_reference_weights(self)
         self._s2r_has_sync_bn = bool(getattr(BatchNorm, "_s2r_sync", False))
 
     def forward(self, input):
         return call_module(self, lambda: DomainClassiferRun(self), (input,))
-
-    def _init_weight(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                torch.nn.init.kaiming_normal_(m.weight)
-            elif isinstance(m, nn.modules.batchnorm._BatchNorm):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
 
 
 def build_domaincls(backbone, BatchNorm):

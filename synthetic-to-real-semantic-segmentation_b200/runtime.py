@@ -6,12 +6,24 @@ activations, so a module can be called several times before backward, as train.p
 and executes it on the C-ABI kernels; its backward executes the run's hand-written backward and
 accumulates parameter gradients straight into `.grad`.
 """
-import ctypes as C
 
 import torch
 
 from . import _lib as L
-from .engine import Act, Ctx, BF16, RawNCHW, round_up, _vp
+from .engine import Ctx, RawNCHW, round_up, _vp
+
+
+def init_reference_weights(module):
+    """The initialisation every constructor of the reference ends with (mobilenet.py:134-145, assp.py:22-32,80-91,
+    decoder.py:45-54, domian.py:35-44): kaiming-normal Conv2d weights, BatchNorm weights one and biases zero, visited
+    in `module.modules()` order -- the same order, hence the same draws from the random stream, as the reference;
+    biases of Conv2d keep nn.Conv2d's own initialisation."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.kaiming_normal_(m.weight)
+        elif isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
 
 
 def sync_group_for(module):

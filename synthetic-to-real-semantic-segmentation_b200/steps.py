@@ -18,7 +18,7 @@ import torch
 
 from .engine import seed_counter, prepack_weights, PEER, COMM_CHANNEL
 from . import functional as _fn
-from .functional import softmax_dim0, bce_with_logits, cross_entropy
+from .functional import softmax_dim0, bce_with_logits
 from .optim import FusedSGD, FusedAdam
 from .utils.loss import SegmentationLosses, DomainLosses
 from .utils.lr_scheduler import LR_Scheduler
