@@ -64,22 +64,15 @@ class ASPPRun(RunBase):
 class ASPP(nn.Module):
     def __init__(self, backbone, output_stride, BatchNorm):
         super().__init__()
-        if backbone == 'drn':
-            inplanes = 512
-        elif backbone == 'mobilenet':
-            inplanes = 320
-        else:
-            inplanes = 2048
-        if output_stride == 16:
-            dilations = [1, 6, 12, 18]
-        elif output_stride == 8:
-            dilations = [1, 12, 24, 36]
-        else:
+        inplanes = {'drn': 512, 'mobilenet': 320}.get(backbone, 2048)                 # assp.py:37-42
+        dilations = {16: (1, 6, 12, 18), 8: (1, 12, 24, 36)}.get(output_stride)       # assp.py:43-48
+        if dilations is None:
             raise NotImplementedError
-        self.aspp1 = _ASPPModule(inplanes, 256, 1, padding=0, dilation=dilations[0], BatchNorm=BatchNorm)
-        self.aspp2 = _ASPPModule(inplanes, 256, 3, padding=dilations[1], dilation=dilations[1], BatchNorm=BatchNorm)
-        self.aspp3 = _ASPPModule(inplanes, 256, 3, padding=dilations[2], dilation=dilations[2], BatchNorm=BatchNorm)
-        self.aspp4 = _ASPPModule(inplanes, 256, 3, padding=dilations[3], dilation=dilations[3], BatchNorm=BatchNorm)
+        # aspp1 (1x1) and aspp2..4 (3x3, padding = dilation), registered -- and initialised -- in this order
+        for k, d in enumerate(dilations, start=1):
+            ksize = 1 if k == 1 else 3
+            setattr(self, 'aspp%d' % k, _ASPPModule(inplanes, 256, ksize, padding=0 if k == 1 else d, dilation=d,
+                                                    BatchNorm=BatchNorm))
         self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)),
                                              nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
                                              BatchNorm(256),

@@ -13,24 +13,25 @@ class SegmentationLosses(object):
 
     def build_loss(self, mode='ce'):
         """Choices: ['ce' or 'focal']"""
-        if mode == 'ce':
-            return self.CrossEntropyLoss
-        elif mode == 'focal':
-            return self.FocalLoss
-        else:
+        losses = {'ce': self.CrossEntropyLoss, 'focal': self.FocalLoss}
+        if mode not in losses:
             raise NotImplementedError
+        return losses[mode]
 
-    def CrossEntropyLoss(self, logit, target):
-        # loss.py:21-30: nn.CrossEntropyLoss(weight, ignore_index, reduction='mean')(logit, target.long())
+    def _mean_ce(self, logit, target):
+        # nn.CrossEntropyLoss(weight, ignore_index, reduction='mean')(logit, target.long()), loss.py:21-30
         return cross_entropy(logit, target, weight=self.weight, ignore_index=self.ignore_index)
 
+    def CrossEntropyLoss(self, logit, target):
+        return self._mean_ce(logit, target)
+
     def FocalLoss(self, logit, target, gamma=2, alpha=0.5):
-        # loss.py:32-46: a scalar transform of the MEAN cross entropy
-        logpt = -cross_entropy(logit, target, weight=self.weight, ignore_index=self.ignore_index)
-        pt = torch.exp(logpt)
+        # loss.py:32-46: a scalar transform of the MEAN cross entropy, -(1 - e^-CE)^gamma * alpha * CE
+        log_pt = -self._mean_ce(logit, target)
+        modulation = (1 - torch.exp(log_pt)) ** gamma
         if alpha is not None:
-            logpt = logpt * alpha
-        return -((1 - pt) ** gamma) * logpt
+            log_pt = log_pt * alpha
+        return -modulation * log_pt
 
 
 class DomainLosses(object):

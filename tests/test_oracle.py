@@ -424,6 +424,31 @@ def test_gaussian_blur_oracle_against_reference_fixture_and_pillow():
         dt._gaussian_blur_weights(1.5)
 
 
+def test_loss_module_host_logic_against_reference_fixture(monkeypatch):
+    """utils.loss host logic on the CPU -- the focal transform of the mean cross entropy (loss.py:32-46), the loss
+    table of build_loss and its NotImplementedError -- with the one device call (functional.cross_entropy) replaced by
+    its torch equivalent; values and gradients against the reference's FocalLoss recorded in tests/golden/policy.npz."""
+    import torch.nn.functional as F
+    loss_mod = sub("utils.loss")
+
+    def ce(logit, target, weight=None, ignore_index=255, **kw):
+        return F.cross_entropy(logit, target.long(), weight=weight, ignore_index=ignore_index, reduction='mean')
+
+    monkeypatch.setattr(loss_mod, "cross_entropy", ce)
+    fix = golden("policy")
+    lab = torch.from_numpy(fix["focal_label"])
+    for tag, wgt in (("", None), ("_w", torch.from_numpy(fix["focal_weight"]))):
+        x = torch.from_numpy(fix["focal_logit"]).clone().requires_grad_(True)
+        losses = loss_mod.SegmentationLosses(weight=wgt)
+        loss = losses.build_loss('focal')(x, lab)
+        loss.backward()
+        assert abs(loss.item() - float(fix["focal_loss" + tag])) <= 1e-6 * abs(float(fix["focal_loss" + tag]))
+        assert rel(x.grad, fix["focal_grad" + tag]) < 1e-6
+        assert torch.equal(losses.build_loss('ce')(x.detach(), lab), ce(x.detach(), lab, weight=wgt))
+    with pytest.raises(NotImplementedError):
+        loss_mod.SegmentationLosses().build_loss('dice')
+
+
 def test_lr_policy_against_reference_fixture():
     """utils.lr_scheduler.LR_Scheduler (poly / cos / step, warm-up, lr to group 0 and 10*lr to the others --
     utils/lr_scheduler.py:43-70, incl. the overwrite of the discriminator's lr at train_adapt.py:133) against the
