@@ -9,6 +9,8 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2>gpurun_out/b
 cat gpurun_out/bench_$TAG.log
 python tests/tools/step_profile.py 400 > gpurun_out/step_profile_$TAG.log 2>&1; echo "profile rc=$?"
 head -16 gpurun_out/step_profile_$TAG.log
+python tests/tools/input_stage_bench.py > gpurun_out/input_stage_$TAG.log 2>&1; echo "input stage rc=$?"
+tail -4 gpurun_out/input_stage_$TAG.log
 if [ -z "$2" ]; then
   CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph"
   $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
