@@ -405,12 +405,29 @@ class DeviceTrainTransform(object):
         return keep
 
 
-class DeviceValTransform(object):
-    """transform_val of the reference's ValSet (FixedResize((size, size)), Normalize, ToTensor) + encode_segmap on a
-    batch: images u8 [N,H,W,3], labelId maps u8 [N,H,W] -> {'image': f32 [N,3,size,size], 'label': f32 [N,size,size]}."""
+def _fix_scale_crop_geometry(w, h, crop_size):
+    """custom_transforms_eval.py:132-145 (FixScaleCrop): short edge -> crop_size, then the centre window; python's
+    round() (half to even) as the reference calls it."""
+    if w > h:
+        oh = crop_size
+        ow = int(1.0 * w * oh / h)
+    else:
+        ow = crop_size
+        oh = int(1.0 * h * ow / w)
+    return ow, oh, int(round((ow - crop_size) / 2.)), int(round((oh - crop_size) / 2.))
 
-    def __init__(self, crop_size, mean=MEAN, std=STD):
-        self.size = crop_size
+
+class DeviceValTransform(object):
+    """The reference's evaluation pipelines + encode_segmap on a batch: images u8 [N,H,W,3], labelId maps u8 [N,H,W] ->
+    {'image': f32 [N,3,size,size], 'label': f32 [N,size,size]}.
+    mode='fixed_resize': FixedResize((size, size)), Normalize, ToTensor -- ValSet / TestSet.transform_val of
+    gtav2cityscapes.py:139-146,213-219 and gta5.py's transform_ts;
+    mode='fix_scale_crop': FixScaleCrop(size), Normalize, ToTensor -- gta5.py:81-88 (short edge to `size`, centre crop)."""
+
+    def __init__(self, crop_size, mean=MEAN, std=STD, mode='fixed_resize'):
+        if mode not in ('fixed_resize', 'fix_scale_crop'):
+            raise NotImplementedError(mode)
+        self.size, self.mode = crop_size, mode
         self.stage = _Stage(mean, std)
 
     def __call__(self, image, label):
@@ -419,12 +436,13 @@ class DeviceValTransform(object):
         N, H, W, _ = image.shape
         assert tuple(label.shape) == (N, H, W)                               # custom_transforms_eval.py:159
         dev, s = image.device, self.size
+        ow, oh, x1, y1 = (s, s, 0, 0) if self.mode == 'fixed_resize' else _fix_scale_crop_geometry(W, H, s)
         out = {'image': torch.empty((N, 3, s, s), dtype=torch.float32, device=dev),
                'label': torch.empty((N, s, s), dtype=torch.float32, device=dev)}
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            im, _ = st_.resize_image(image, s, s, False, st)
+            im, _ = st_.resize_image(image, ow, oh, False, st)
             # the reference relabels BEFORE the nearest resize; a per-pixel table commutes with a nearest-neighbour copy
-            lb, _ = st_.resize_label(label, s, s, False, st)
-            st_.finish(im, lb, False, False, 0, 0, out['image'], out['label'], s, s, st)
+            lb, _ = st_.resize_label(label, ow, oh, False, st)
+            st_.finish(im, lb, False, False, x1, y1, out['image'], out['label'], s, s, st)
         return out

@@ -125,6 +125,21 @@ def main():
         assert np.array_equal(vs['image'].numpy(), want_img) and np.array_equal(vs['label'].numpy(), want_lab)
         out["val_img"], out["val_lab"], out["val_size"] = img, lab, np.array([36], np.int32)
         out["val_out_img"], out["val_out_lab"] = vs['image'].numpy(), vs['label'].numpy()
+        # gta5.py:81-88 transform_val: FixScaleCrop + Normalize + ToTensor -- the reference's own transform classes on
+        # a landscape and a portrait image (the label is relabelled first, as ValSet.__getitem__ does)
+        from torchvision import transforms as tv_transforms
+        from dataloders import custom_transforms_eval as tr_e
+        fsc = tv_transforms.Compose([tr_e.FixScaleCrop(crop_size=36), tr_e.Normalize(mean=OI.MEAN, std=OI.STD), tr_e.ToTensor()])
+        for tag, (a, m) in (("land", (img, lab)), ("port", (np.ascontiguousarray(img.transpose(1, 0, 2)), np.ascontiguousarray(lab.T)))):
+            res = fsc({'image': Image.fromarray(a), 'label': Image.fromarray(OI.encode_segmap(m))})
+            h, w = m.shape
+            ow, oh = (int(1.0 * w * 36 / h), 36) if w > h else (36, int(1.0 * h * 36 / w))
+            x1, y1 = int(round((ow - 36) / 2.)), int(round((oh - 36) / 2.))
+            want_img = OI.normalize_to_tensor(OI.resize_bilinear(a, ow, oh)[y1:y1 + 36, x1:x1 + 36])
+            want_lab = OI.resize_nearest(OI.encode_segmap(m), ow, oh)[y1:y1 + 36, x1:x1 + 36].astype(np.float32)
+            assert np.array_equal(res['image'].numpy(), want_img) and np.array_equal(res['label'].numpy(), want_lab), tag
+            out["fsc_%s_img" % tag], out["fsc_%s_lab" % tag] = a, m
+            out["fsc_%s_out_img" % tag], out["fsc_%s_out_lab" % tag] = res['image'].numpy(), res['label'].numpy()
         out["cases"] = np.array(cases)
         out["blur_cases"] = np.array(blur_cases)
     # the label table against the reference's own relabelling of every byte value

@@ -97,3 +97,19 @@ def test_blur_random_stream_and_full_size_against_oracle(dt):
         assert np.array_equal(out['tgt_image'][n].cpu().numpy(), OI.normalize_to_tensor(OI.gaussian_blur(crop, r_tgt))), n
     with pytest.raises(NotImplementedError):
         tr(img.cuda(), img.cuda(), big.cuda(), draws=[(False, 1024, 0, 0, True, 2.0, 0.1)] * 2)
+
+
+def test_fix_scale_crop_validation_pipeline_against_reference_fixture(dt):
+    """DeviceValTransform(mode='fix_scale_crop') = FixScaleCrop + Normalize + ToTensor (gta5.py:81-88,
+    custom_transforms_eval.py:125-149) against the reference's own transform classes on a landscape and a portrait
+    image: bit-exact."""
+    fix = golden("input_stage")
+    for tag in ("land", "port"):
+        img = torch.from_numpy(np.stack([fix["fsc_%s_img" % tag]] * 2)).cuda()
+        lab = torch.from_numpy(np.stack([fix["fsc_%s_lab" % tag]] * 2)).cuda()
+        out = dt.DeviceValTransform(36, mode='fix_scale_crop')(img, lab)
+        for n in range(2):
+            assert np.array_equal(out['image'][n].cpu().numpy(), fix["fsc_%s_out_img" % tag]), tag
+            assert np.array_equal(out['label'][n].cpu().numpy(), fix["fsc_%s_out_lab" % tag]), tag
+    with pytest.raises(NotImplementedError):
+        dt.DeviceValTransform(36, mode='random')

@@ -124,7 +124,63 @@ def gaussian_blur3_multi(tab, n, H, W, stream):
             out[i] = three_passes(lambda yy: int(tmp[xb + yy * pitch]), y, H - 1, j.ww, j.fw)
 
 
-KERNELS = {"s2r_resize_bilinear_u8_multi": resize_bilinear_multi, "s2r_resize_nearest_u8_multi": resize_nearest_multi,
+def view(ptr, shape, dtype=np.uint8):
+    return arr(ptr, int(np.prod(shape)), dtype).reshape(shape)
+
+
+def resize_bilinear(inp, N, H, W, Cc, axis, out_size, bounds, kk, ksize, flip, out, stream):
+    """resize_h_kernel (axis 1, mirrored source columns when flip) / resize_v_kernel (axis 0), vectorised over the lines"""
+    x = view(inp, (N, H, W, Cc)).astype(np.int64)
+    bnd, k = view(bounds, (out_size, 2), np.int32), view(kk, (out_size, ksize), np.int32)
+    if axis == 1:
+        x = x[:, :, ::-1] if flip else x
+        o = view(out, (N, H, out_size, Cc))
+        for xx in range(out_size):
+            acc = np.full((N, H, Cc), 1 << (PB - 1), np.int64)
+            for t in range(bnd[xx, 1]):
+                acc += x[:, :, bnd[xx, 0] + t] * int(k[xx, t])
+            o[:, :, xx] = np.clip(acc >> PB, 0, 255)
+    else:
+        o = view(out, (N, out_size, W, Cc))
+        for yy in range(out_size):
+            acc = np.full((N, W, Cc), 1 << (PB - 1), np.int64)
+            for t in range(bnd[yy, 1]):
+                acc += x[:, bnd[yy, 0] + t] * int(k[yy, t])
+            o[:, yy] = np.clip(acc >> PB, 0, 255)
+
+
+def resize_nearest(inp, N, H, W, xtab, ytab, OH, OW, flip, out, stream):
+    """resize_nearest_kernel"""
+    x, o = view(inp, (N, H, W)), view(out, (N, OH, OW))
+    xt, yt = view(xtab, (OW,), np.int32), view(ytab, (OH,), np.int32)
+    o[:] = 0
+    for y in range(OH):
+        for xx in range(OW):
+            if xt[xx] >= 0 and yt[y] >= 0:
+                o[:, y, xx] = x[:, yt[y], (W - 1 - xt[xx]) if flip else xt[xx]]
+
+
+def input_stage(img, label, N, Hs, Ws, flip, x1, y1, mean, std, lut, fill, out_img, out_label, H, W, stream):
+    """input_stage_kernel: window (x1, y1) of the mirrored image, zero / fill padded on the right and bottom"""
+    for n in range(N):
+        if img:
+            x = view(img, (N, Hs, Ws, 3))[n]
+            x = x[:, ::-1] if flip else x
+            pad = np.zeros((max(Hs, y1 + H), max(Ws, x1 + W), 3), np.uint8)
+            pad[:Hs, :Ws] = x
+            view(out_img, (N, 3, H, W), np.float32)[n] = OI.normalize_to_tensor(pad[y1:y1 + H, x1:x1 + W])
+        if label:
+            x = view(label, (N, Hs, Ws))[n]
+            x = x[:, ::-1] if flip else x
+            if lut:
+                x = view(lut, (256,))[x]
+            pad = np.full((max(Hs, y1 + H), max(Ws, x1 + W)), fill, np.uint8)
+            pad[:Hs, :Ws] = x
+            view(out_label, (N, H, W), np.float32)[n] = pad[y1:y1 + H, x1:x1 + W].astype(np.float32)
+
+
+KERNELS = {"s2r_resize_bilinear_u8": resize_bilinear, "s2r_resize_nearest_u8": resize_nearest, "s2r_input_stage_u8": input_stage,
+           "s2r_resize_bilinear_u8_multi": resize_bilinear_multi, "s2r_resize_nearest_u8_multi": resize_nearest_multi,
            "s2r_input_stage_u8_multi": input_stage_multi, "s2r_gaussian_blur3_u8_multi": gaussian_blur3_multi}
 
 
@@ -135,6 +191,53 @@ def emu(name, *args):
 
 L.call = emu
 dt.L.call = emu
+
+
+class on_cpu(object):
+    """Lets DeviceTrainTransform / DeviceValTransform .__call__ run on CPU tensors: the device checks and the stream
+    lookup are the only CUDA touches on the host side (the kernels are the emulations above)."""
+
+    def __enter__(self):
+        import contextlib
+        import types
+        self.saved = (dt._Stage._check, torch.cuda.device, torch.cuda.current_stream)
+        dt._Stage._check = staticmethod(lambda t, n, what: None)
+        torch.cuda.device = lambda d: contextlib.nullcontext()
+        torch.cuda.current_stream = lambda d=None: types.SimpleNamespace(cuda_stream=0)
+
+    def __exit__(self, *exc):
+        dt._Stage._check, torch.cuda.device, torch.cuda.current_stream = self.saved
+
+
+def run_calls(fix):
+    """The public __call__ paths: validation pipelines (FixedResize; FixScaleCrop landscape / portrait) and the
+    per-sample (batched=False) training path with and without RandomGaussianBlur."""
+    ok = True
+    with on_cpu():
+        s = int(fix['val_size'][0])
+        out = dt.DeviceValTransform(s)(torch.from_numpy(fix['val_img'])[None], torch.from_numpy(fix['val_lab'])[None])
+        e = [np.array_equal(out['image'][0].numpy(), fix['val_out_img']), np.array_equal(out['label'][0].numpy(), fix['val_out_lab'])]
+        print('val fixed_resize', e)
+        ok &= all(e)
+        for tag in ('land', 'port'):
+            out = dt.DeviceValTransform(36, mode='fix_scale_crop')(torch.from_numpy(fix['fsc_%s_img' % tag])[None],
+                                                                   torch.from_numpy(fix['fsc_%s_lab' % tag])[None])
+            e = [np.array_equal(out['image'][0].numpy(), fix['fsc_%s_out_img' % tag]),
+                 np.array_equal(out['label'][0].numpy(), fix['fsc_%s_out_lab' % tag])]
+            print('val fix_scale_crop', tag, e)
+            ok &= all(e)
+        for k in (str(fix['cases'][0]), str(fix['cases'][3]), str(fix['blur_cases'][1]), str(fix['blur_cases'][2])):
+            flip, short, crop, x1, y1 = (int(v) for v in fix[k + '_draw'])
+            r = fix[k + '_radii'] if (k + '_radii') in fix.files else None
+            d = (bool(flip), short, x1, y1) + ((True, float(r[0]), float(r[1])) if r is not None else ())
+            out = dt.DeviceTrainTransform(1, crop)(torch.from_numpy(fix[k + '_src'])[None], torch.from_numpy(fix[k + '_tgt'])[None],
+                                                   torch.from_numpy(fix[k + '_lab'])[None], draws=[d], batched=False)
+            e = [np.array_equal(out['src_image'][0].numpy(), fix[k + '_out_src']),
+                 np.array_equal(out['tgt_image'][0].numpy(), fix[k + '_out_tgt']),
+                 np.array_equal(out['src_label'][0].numpy(), fix[k + '_out_lab'])]
+            print('per-sample path', k, e)
+            ok &= all(e)
+    return ok
 
 
 def run_pair(fix, a, b):
@@ -179,6 +282,7 @@ def main():
         ok &= run_pair(fix, a, b)
     ok &= run_pair(fix, blurred[0], plain[1])               # mixed batches: one sample blurred, one not
     ok &= run_pair(fix, plain[4], blurred[5])
+    ok &= run_calls(fix)
     print("ALL OK" if ok else "MISMATCH")
     return 0 if ok else 1
 
