@@ -424,6 +424,37 @@ def test_gaussian_blur_oracle_against_reference_fixture_and_pillow():
         dt._gaussian_blur_weights(1.5)
 
 
+def test_box_blur_c_oracle_against_pillow_and_numpy_oracle():
+    """oracle/box_blur.c (the byte path restated in C) against Pillow's GaussianBlur and the numpy restatement, over the
+    reference's range of radii and beyond, degenerate sizes included, and on a full 512 x 512 crop."""
+    from PIL import Image, ImageFilter
+    from oracle import input_stage as OI
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "liboracle_blur.so"))
+    lib.gaussian_blur_u8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                     ctypes.c_uint32, ctypes.c_int]
+
+    def c_blur(a, r):
+        out = a.copy()
+        fr = OI.gaussian_blur_radius(r) if r != 0 else 0
+        if fr != 0:
+            radius, ww, fw = OI.box_blur_weights(fr)
+            assert lib.gaussian_blur_u8(out.ctypes.data, a.shape[0], a.shape[1], a.shape[2], radius, ww, fw, 3) == 0
+        return out
+
+    rng = np.random.RandomState(3)
+    for trial in range(160):
+        h, w = int(rng.randint(1, 40)), int(rng.randint(1, 40))
+        a = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        r = float(rng.rand()) * (1.0, 1.0, 6.0, 40.0)[trial % 4]
+        got = c_blur(a, r)
+        assert np.array_equal(got, np.array(Image.fromarray(a).filter(ImageFilter.GaussianBlur(radius=r)))), (h, w, r)
+        assert np.array_equal(got, OI.gaussian_blur(a, r)), (h, w, r)
+    a = rng.randint(0, 256, (512, 512, 3)).astype(np.uint8)
+    for r in (0.0, 1e-3, 0.5, 0.999999):
+        assert np.array_equal(c_blur(a, r), np.array(Image.fromarray(a).filter(ImageFilter.GaussianBlur(radius=r)))), r
+
+
 def test_loss_module_host_logic_against_reference_fixture(monkeypatch):
     """utils.loss host logic on the CPU -- the focal transform of the mean cross entropy (loss.py:32-46), the loss
     table of build_loss and its NotImplementedError -- with the one device call (functional.cross_entropy) replaced by
