@@ -455,6 +455,35 @@ def test_box_blur_c_oracle_against_pillow_and_numpy_oracle():
         assert np.array_equal(c_blur(a, r), np.array(Image.fromarray(a).filter(ImageFilter.GaussianBlur(radius=r)))), r
 
 
+def test_resample_c_oracle_against_pillow_and_numpy_oracle():
+    """oracle/resample.c (Pillow's BILINEAR / NEAREST resize restated in C) against Pillow itself and the numpy
+    restatement over a sweep of shapes (1-pixel axes included) and on a GTA5-sized image."""
+    from PIL import Image
+    from oracle import input_stage as OI
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "liboracle_resample.so"))
+    lib.resize_bilinear_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    lib.resize_nearest_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    rng = np.random.RandomState(5)
+    for (h, w) in [(17, 23), (31, 90), (1, 7), (9, 1)]:
+        a = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        m = rng.randint(0, 256, (h, w)).astype(np.uint8)
+        for ow in (1, 5, 23, 36, 97):
+            for oh in (1, 7, 17, 40):
+                o = np.empty((oh, ow, 3), np.uint8)
+                assert lib.resize_bilinear_u8(a.ctypes.data, h, w, 3, oh, ow, o.ctypes.data) == 0
+                assert np.array_equal(o, np.array(Image.fromarray(a).resize((ow, oh), Image.BILINEAR))), (h, w, ow, oh)
+                assert np.array_equal(o, OI.resize_bilinear(a, ow, oh)), (h, w, ow, oh)
+                o2 = np.empty((oh, ow), np.uint8)
+                lib.resize_nearest_u8(m.ctypes.data, h, w, oh, ow, o2.ctypes.data)
+                assert np.array_equal(o2, np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST))), (h, w, ow, oh)
+                assert np.array_equal(o2, OI.resize_nearest(m, ow, oh)), (h, w, ow, oh)
+    a = rng.randint(0, 256, (1052, 1914, 3)).astype(np.uint8)
+    o = np.empty((700, 1273, 3), np.uint8)
+    assert lib.resize_bilinear_u8(a.ctypes.data, 1052, 1914, 3, 700, 1273, o.ctypes.data) == 0
+    assert np.array_equal(o, np.array(Image.fromarray(a).resize((1273, 700), Image.BILINEAR)))
+
+
 def test_loss_module_host_logic_against_reference_fixture(monkeypatch):
     """utils.loss host logic on the CPU -- the focal transform of the mean cross entropy (loss.py:32-46), the loss
     table of build_loss and its NotImplementedError -- with the one device call (functional.cross_entropy) replaced by
