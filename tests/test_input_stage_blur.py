@@ -1,6 +1,8 @@
-"""RandomGaussianBlur of the device input stage (dataloders/custom_transforms.py:92-105 of the reference; SURVEY.md
-section 8(f) row 3): bit-exact against the tensors the reference's unmodified TrainSet produced on draws where the blur
-fires (tests/golden/input_stage.npz, trainb* cases) and against the numpy restatement of Pillow's GaussianBlur."""
+"""Device input stage, the transforms added last:
+* RandomGaussianBlur (dataloders/custom_transforms.py:92-105 of the reference): bit-exact against the tensors the
+  reference's unmodified TrainSet produced on draws where the blur fires (tests/golden/input_stage.npz, trainb* cases)
+  and against the numpy restatement of Pillow's GaussianBlur;
+* FixScaleCrop evaluation pipeline (gta5.py:81-88): bit-exact against the reference's own transform classes."""
 import random
 
 import numpy as np
