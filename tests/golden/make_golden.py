@@ -426,6 +426,24 @@ def reference_method(script, name, ns):
     raise RuntimeError('%s not found in %s' % (name, script))
 
 
+def checkpoint_layout(ck):
+    """JSON description of a checkpoint dict the reference wrote: every tensor replaced by [dtype, shape], everything
+    else (keys, order, parameter-group index lists, hyper-parameters, scalars) kept."""
+    import json
+
+    def conv(v):
+        if torch.is_tensor(v):
+            return {'__tensor__': [str(v.dtype).replace('torch.', ''), list(v.shape)]}
+        if isinstance(v, dict):
+            return {'__items__': [[k if isinstance(k, str) else {'__int__': int(k)}, conv(x)] for k, x in v.items()]}
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        if isinstance(v, (bool, int, float, str)) or v is None:
+            return v
+        return float(v)
+    return json.dumps(conv(ck))
+
+
 def adapt_loop_case():
     """BASELINE configs 2/3: the reference's own `Trainer.training` (train_adapt.py:115-196, unmodified source
     segment) run for one epoch of ten iterations on the CPU -- reference DeepLab / FCDiscriminator / criterion /
@@ -471,11 +489,15 @@ def adapt_loop_case():
         return wrapper
 
     quiet = types.SimpleNamespace(add_scalar=lambda *a: None, visualize_image=lambda *a: None)
-    trainer = types.SimpleNamespace(model=G, model_D=D, optimizer=opt, optimizer_D=opt_d, train_loader=loader,
+    saved = []
+    # train_adapt.py:87-88 wraps the model in nn.DataParallel, which on a host without GPUs calls the module directly;
+    # with no_val the epoch ends by handing the checkpoint dict of :202-209 to Saver.save_checkpoint
+    trainer = types.SimpleNamespace(model=torch.nn.DataParallel(G), saver=types.SimpleNamespace(save_checkpoint=lambda st, best: saved.append(st)),
+                                    model_D=D, optimizer=opt, optimizer_D=opt_d, train_loader=loader,
                                     scheduler=RefSched('poly', lr, 1, n_it), best_pred=0.0,
                                     criterion=recorded(RefSegLoss().build_loss('ce')),
                                     bce_loss=recorded(torch.nn.BCEWithLogitsLoss()), writer=quiet, summary=quiet,
-                                    args=types.SimpleNamespace(cuda=False, batch_size=2, dataset='gtav2cityscapes', no_val=False))
+                                    args=types.SimpleNamespace(cuda=False, batch_size=2, dataset='gtav2cityscapes', no_val=True))
     old_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
@@ -500,6 +522,8 @@ def adapt_loop_case():
         fix['w:' + k] = head(w)
     assert relerr(d_sd['conv1.weight'].detach(), D.conv1.weight.detach()) < 1e-3
     fix['wd:conv1.weight'] = head(D.conv1.weight)
+    assert len(saved) == 1
+    fix['checkpoint_layout'] = np.array(checkpoint_layout(saved[0]))
     np.savez_compressed(os.path.join(HERE, 'adapt_loop.npz'), **fix)
 
 
@@ -565,7 +589,34 @@ def feature_loop_case():
     for sd, m, k in ((sds[0], bb, 'features.0.0.weight'), (sds[2], dec, 'last_conv.8.weight'), (sds[3], dc, 'DC_adnn3.weight')):
         w = dict(m.named_parameters())[k].detach()
         assert relerr(sd[k].detach(), w) < 2e-3, (k, relerr(sd[k].detach(), w))
-    np.savez_compressed(os.path.join(HERE, 'feature_loop.npz'), losses=ref_hist)
+    # train.py:254-314, unmodified: validation over two batches; the first epoch beats best_pred = 0, so it ends by
+    # handing the four-model checkpoint dict of :300-313 to Saver.save_checkpoint (models wrapped in nn.DataParallel
+    # as train.py:107-110 does -- a pass-through on a host without GPUs)
+    class VBar(list):
+        def set_description(self, text):
+            pass
+
+    validation = reference_method('train.py', 'validation', {'np': np, 'torch': torch, 'F': F, 'tqdm': lambda it, desc='': VBar(it)})
+    saved = []
+    for name in ('backbone_model', 'assp_model', 'y_model', 'd_model'):
+        setattr(trainer, name, torch.nn.DataParallel(getattr(trainer, name)))
+    trainer.saver = types.SimpleNamespace(save_checkpoint=lambda st, best: saved.append((st, best)))
+    trainer.evaluator = RefEvaluator(19)
+    trainer.val_loader = [{'image': x, 'label': lab} for x, lab in (make_inputs(600, 2, 48, 64), make_inputs(601, 1, 48, 64))]
+    trainer.task_loss = RefSegLoss().build_loss('ce')
+    validation(trainer, 0)
+    assert len(saved) == 1 and saved[0][1] is True
+    cm = np.zeros((19, 19), np.int64)
+    with torch.no_grad():
+        for b in trainer.val_loader:
+            hi, lo = O.mobilenet_forward(sds[0], b['image'], O.BNCfg(False))
+            out = torch.nn.functional.interpolate(O.decoder_forward(sds[2], O.aspp_forward(sds[1], hi, O.BNCfg(False)), lo, O.BNCfg(False)),
+                                                  b['image'].shape[2:], mode='bilinear', align_corners=True)
+            cm += O.confusion_matrix(b['label'].numpy(), np.argmax(out.numpy(), axis=1), 19)
+    assert np.array_equal(cm, trainer.evaluator.confusion_matrix)
+    assert saved[0][0]['best_pred'] == O.evaluator_metrics(cm)['mIoU']
+    np.savez_compressed(os.path.join(HERE, 'feature_loop.npz'), losses=ref_hist, val_confusion_matrix=cm,
+                        checkpoint_layout=np.array(checkpoint_layout(saved[0][0])))
 
 
 def validation_case():

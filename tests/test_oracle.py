@@ -286,6 +286,76 @@ def test_feature_loop_against_reference_training_run():
         assert np.allclose(got, fix['losses'][it], rtol=2e-3, atol=1e-5), (it, got, fix['losses'][it])
 
 
+def _layout_to_state(node):
+    """Inverse of make_golden.checkpoint_layout with zero tensors of the recorded dtype / shape."""
+    if isinstance(node, dict) and '__tensor__' in node:
+        dtype, shape = node['__tensor__']
+        return torch.zeros(shape, dtype=getattr(torch, dtype))
+    if isinstance(node, dict) and '__items__' in node:
+        return {(k['__int__'] if isinstance(k, dict) else k): _layout_to_state(v) for k, v in node['__items__']}
+    if isinstance(node, list):
+        return [_layout_to_state(v) for v in node]
+    return node
+
+
+def _skeleton(v):
+    """Structure of a checkpoint dict: keys in order, tensor dtypes / shapes, integers, booleans and strings; floats
+    (learning rates, best_pred, Adam's step counters) reduced to their type."""
+    if torch.is_tensor(v):
+        return ('tensor', str(v.dtype), tuple(v.shape)) if v.dim() else ('scalar-tensor',)
+    if isinstance(v, dict):
+        return [(k, _skeleton(x)) for k, x in v.items()]
+    if isinstance(v, (list, tuple)):
+        return [_skeleton(x) for x in v]
+    return 'float' if isinstance(v, float) else v
+
+
+def _fake_step(opt):
+    for g in opt.param_groups:
+        for p in g['params']:
+            p.grad = torch.zeros_like(p)
+    opt.step()
+
+
+def test_checkpoint_layouts_against_the_reference_scripts():
+    """SURVEY.md 8(f) row 2 on the reference's own code: the checkpoint dicts its unmodified `Trainer.training`
+    (train_adapt.py:202-209) and `Trainer.validation` (train.py:300-313) handed to Saver.save_checkpoint, recorded as
+    layouts (keys, order, tensor dtypes / shapes, parameter-group index lists) by tests/golden/make_golden.py.
+    utils.checkpoint.adapt_state / feature_state on the product's modules produce the same structure, and load_adapt /
+    load_feature accept the reference's (DataParallel-unwrapped) dicts.  CPU: torch optimizers stand in for the fused
+    ones, whose torch.optim-format state is a GPU test."""
+    import json
+    ck_mod = sub("utils.checkpoint")
+    nn = torch.nn
+    # ---- train_adapt.py layout
+    ref = _layout_to_state(json.loads(str(golden('adapt_loop')['checkpoint_layout'])))
+    assert list(ref.keys()) == ['epoch', 'state_dict', 'optimizer', 'best_pred']
+    G = sub("modeling.deeplab").DeepLab(backbone='mobilenet', output_stride=16, num_classes=19, sync_bn=False)
+    opt = torch.optim.SGD([{'params': list(G.get_1x_lr_params()), 'lr': 5e-4}, {'params': list(G.get_10x_lr_params()), 'lr': 5e-3}],
+                          momentum=0.9, weight_decay=5e-4, nesterov=False)
+    _fake_step(opt)
+    mine = ck_mod.adapt_state(G, opt, 0, 0.0)
+    assert _skeleton(mine) == _skeleton(ref)
+    assert ck_mod.load_adapt(ref, G, opt) == (1, 0.0)
+    assert float(G.decoder.last_conv[8].weight.detach().abs().sum()) == 0.0             # the (zero-filled) reference tensors are in
+    assert ck_mod.load_adapt({**ref, 'state_dict': {'module.' + k: v for k, v in ref['state_dict'].items()}}, G, ft=True)[0] == 0
+    # ---- train.py layout
+    ref = _layout_to_state(json.loads(str(golden('feature_loop')['checkpoint_layout'])))
+    mods = (sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d),
+            sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d), sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d),
+            sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d))
+    f_params = list(mods[0].parameters()) + list(mods[1].parameters())
+    opts = [torch.optim.Adam(f_params + list(mods[2].parameters()), lr=5e-4), torch.optim.Adam(list(mods[3].parameters()), lr=5e-4),
+            torch.optim.Adam(f_params, lr=5e-4)]
+    for o in opts:
+        _fake_step(o)
+    c_opt = torch.optim.Adam(f_params + list(mods[2].parameters()), lr=5e-4)      # exists, never steps (train.py:73-75)
+    mine = ck_mod.feature_state(*mods, *opts, 0, 0.5, c_optimizer=c_opt)
+    assert _skeleton(mine) == _skeleton(ref)
+    epoch, best = ck_mod.load_feature(ref, *mods, *opts)
+    assert epoch == 1 and best == ref['best_pred'] and float(mods[3].DC_adnn3.weight.detach().abs().sum()) == 0.0
+
+
 def test_validation_report_against_reference_run():
     """BASELINE config 5: the report the reference's own `Trainer.validation` (val_adapt.py:117-175, run unmodified on
     the CPU by tests/golden/make_golden.py validation_case) appended to val_info.txt, against the product's metric
