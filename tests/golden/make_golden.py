@@ -345,7 +345,9 @@ def sync_bn_case():
     through SlavePipe / SyncMaster.run_master / _data_parallel_master / _compute_mean_std.  Only the two torch-internal
     CUDA collectives that function calls (torch.nn.parallel._functions.ReduceAddCoalesced / Broadcast) are replaced
     by their CPU meaning (sum of the replica tensors / the same tensors for every replica).  Compared with the
-    oracle's sync_clamp branch on the concatenated batch: outputs, running statistics, all gradients."""
+    oracle's sync_clamp branch on the concatenated batch: outputs, running statistics, all gradients.  (Regenerating
+    the fixture can change `dx` in the last bit: the replicas' contributions to the shared statistics' gradients are
+    accumulated in thread-arrival order.  The tests compare with 1e-5.)"""
     import copy
     import threading
     from modeling.sync_batchnorm import batchnorm as ref_bn
