@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import ROOT, sub
+from conftest import PKG, ROOT, sub
 
 
 def header_symbols():
@@ -303,3 +303,49 @@ def test_rowtap_views_and_pack_maps_reproduce_conv4x4_s2(H, W, Cin, Cout):
                     e = (outp - base) // 2 + n * on + i * oh_s + j * ow_s
                     dxmem.reshape(-1)[e:e + 2 * Cp] += acc
     assert np.allclose(dxmem[:, 1:-1, 1:-1, :Cin], xt.grad.permute(0, 2, 3, 1).numpy(), atol=1e-8)
+
+
+def test_blur_kernel_text_compiled_for_the_host(tmp_path):
+    """The RandomGaussianBlur kernels (csrc/input_stage.cu: blur_tap, blur_three_passes, blur_rows_kernel,
+    blur_cols_kernel) taken as TEXT out of the .cu, stripped of their CUDA qualifiers, with the grid-stride loop reduced
+    to a plain loop, compiled with g++ and run on random windows / mirrors / paddings / radii against the oracle's
+    restatement of Pillow's GaussianBlur: the arithmetic and the addressing of the kernels without a GPU."""
+    import subprocess
+    from oracle import input_stage as OI
+    src = open(os.path.join(ROOT, PKG, "csrc", "input_stage.cu")).read()
+    core = src[src.index("__device__ __forceinline__ uint32_t blur_tap"):src.index("// grid = (blocks over H*W*3 bytes of the crop, njobs)")]
+    kernels = src[src.index("__global__ void __launch_bounds__(kThreads)\nblur_rows_kernel"):
+                  src.index('}  // namespace\n\nextern "C" int s2r_gaussian_blur3_u8_multi')]
+    core = core.replace("__device__ __forceinline__", "static inline")
+    kernels = (kernels.replace("__global__ void __launch_bounds__(kThreads)\n", "void ").replace("__restrict__", "")
+               .replace("jobs[blockIdx.y]", "jobs[block_y]").replace("blockIdx.x * kThreads + threadIdx.x", "0")
+               .replace("gridDim.x * kThreads", "1"))
+    assert "blockIdx" not in kernels and "threadIdx" not in kernels
+    header = open(os.path.join(ROOT, "include", "s2r_b200.h")).read()
+    job = header[header.index("typedef struct s2r_blur_job {"):header.index("} s2r_blur_job;") + len("} s2r_blur_job;")]
+    cpp = tmp_path / "blur_host.cpp"
+    cpp.write_text("#include <cstdint>\nconstexpr int kThreads = 256;\nstatic int block_y = 0;\n" + job + "\n" + core + kernels +
+                   'extern "C" void run(const s2r_blur_job* jobs, int n, int H, int W) {\n'
+                   "  for (block_y = 0; block_y < n; ++block_y) blur_rows_kernel(jobs, H, W);\n"
+                   "  for (block_y = 0; block_y < n; ++block_y) blur_cols_kernel(jobs, H, W);\n}\n")
+    so = tmp_path / "blur_host.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(cpp)])
+    lib = ctypes.CDLL(str(so))
+    L = sub("_lib")
+    dt = sub("dataloders.device_transforms")
+    rng = np.random.default_rng(1)
+    for t in range(120):
+        Hs, Ws, cs = int(rng.integers(1, 50)), int(rng.integers(1, 50)), int(rng.integers(2, 40))
+        flip = int(rng.integers(0, 2))
+        x1 = int(rng.integers(0, max(1, max(Ws, cs) - cs + 1)))
+        y1 = int(rng.integers(0, max(1, max(Hs, cs) - cs + 1)))
+        img = rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8)
+        r = float(rng.random()) * (1.0 if t % 4 else 1.41)
+        ww, fw = dt._gaussian_blur_weights(r)
+        tmp, out = np.zeros((cs, cs, 3), np.uint8), np.zeros((cs, cs, 3), np.uint8)
+        job_s = L.BlurJob(img.ctypes.data, tmp.ctypes.data, out.ctypes.data, Hs, Ws, flip, x1, y1, ww, fw, 0)
+        lib.run(ctypes.byref(job_s), 1, cs, cs)
+        a = img[:, ::-1] if flip else img
+        pad = np.zeros((max(Hs, y1 + cs), max(Ws, x1 + cs), 3), np.uint8)
+        pad[:Hs, :Ws] = a
+        assert np.array_equal(out, OI.gaussian_blur(pad[y1:y1 + cs, x1:x1 + cs], r)), (t, Hs, Ws, cs, flip, x1, y1, r)
