@@ -326,6 +326,9 @@ int s2r_softmax0_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, in
                                   s2r_stream_t stream);
 int s2r_softmax0_nhwc_pad_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, int softmax,
                               float* dx, s2r_stream_t stream);
+/* sums (fp64, zeroed by the caller) += {sum_valid w_t (lse - x_t), sum_valid w_t, #(argmax == t)}; grad_unscaled
+ * (optional) = w_t (softmax - onehot).  A target that is neither ignore_index nor in [0, C) makes sums[0] NaN (the
+ * reference's nn.CrossEntropyLoss stops with a device assert there, utils/loss.py:27-28). */
 int s2r_cross_entropy_nchw(const float* logits, const float* target, int const_target,
                            const float* weight, int N, int C, int64_t HW, int ignore_index,
                            double* sums, float* grad_unscaled, s2r_stream_t stream);
@@ -366,6 +369,11 @@ int s2r_sgd_step(const s2r_param_slot* slots, int nslots, const float* hyper, fl
                  s2r_stream_t stream);
 int s2r_adam_step(const s2r_param_slot* slots, int nslots, const float* hyper, float beta1,
                   float beta2, float eps, float weight_decay, float gscale, s2r_stream_t stream);
+/* dst[0..n) (device) = host_vals[0..n), n <= 8, stream-ordered.  The values travel as kernel arguments, i.e. they are
+ * read from host memory before the call returns: this is how the learning rate (utils/lr_scheduler.py:63-70 writes
+ * param_groups[i]['lr'] before every step, train_adapt.py:131-134) and Adam's bias corrections reach `hyper` ahead of
+ * a CUDA-graph replay without a host buffer the GPU would read later. */
+int s2r_store_f32(float* dst, int n, const float* host_vals, s2r_stream_t stream);
 
 /* ------------------------------------------------------------------ NVLink peer-memory exchange
  * Replaces the master/slave reduce + broadcast of modeling/sync_batchnorm/comm.py:18-129 and
@@ -381,7 +389,7 @@ int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream);
 /* The same on exchange channel 0 or 1: every rank issues the same sequence of calls PER CHANNEL, and calls on
  * different channels may be in flight together (the two streams of the training step). */
 int s2r_allreduce_small_f64_ch(double* buf, int n, int channel, s2r_stream_t stream);
-int s2r_comm_error(void);   /* non-zero: a bounded wait expired (synchronises the device) */
+int s2r_comm_error(void);   /* non-zero: a bounded wait expired; a host read of a mapped flag (no synchronisation) */
 int s2r_comm_destroy(void);
 
 #ifdef __cplusplus

@@ -351,7 +351,10 @@ def adapt_step(g_sd, d_sd, opt_g, opt_d, src_image, src_label, tgt_image, cfg, d
 
 def feature_step(f_sd, a_sd, y_sd, dc_sd, opts, src_image, src_label, tgt_image, cfg, drop=None, output_stride=16):
     """One iteration of Trainer.training in train.py:173-204: the summed loss reaches every
-    parameter; task, d and d_inv optimizers step (c_optimizer never does).  opts = (task, d, d_inv)."""
+    parameter; task, d and d_inv optimizers step (c_optimizer never does).  opts = (task, d, d_inv).
+    tgt_image=None is the single-domain branch (args.dataset == 'gtav', train.py:205-210): the domain classifier
+    still runs on the source features (:187, its BatchNorm running statistics move) but only the task loss is
+    back-propagated and only task_optimizer steps."""
     for o in opts:
         o.zero_grad()
 
@@ -364,6 +367,10 @@ def feature_step(f_sd, a_sd, y_sd, dc_sd, opts, src_image, src_label, tgt_image,
 
     src_out, src_d = fwd(src_image)
     task = seg_cross_entropy(src_out, src_label)
+    if tgt_image is None:
+        task.backward()
+        opts[0].step()
+        return task.item(), 0.0, 0.0, 0
     _, tgt_d = fwd(tgt_image)
     d_loss, d_acc = domain_loss(src_d, tgt_d)
     d_inv_loss, _ = domain_loss(tgt_d, src_d)

@@ -130,6 +130,7 @@ PROTOTYPES = {
     "s2r_allreduce_small_f64_ch": [vp, i32, i32, vp],
     "s2r_sgd_step": [vp, i32, vp, f32, f32, f32, i32, f32, vp],
     "s2r_adam_step": [vp, i32, vp, f32, f32, f32, f32, f32, vp],
+    "s2r_store_f32": [vp, i32, C.POINTER(f32), vp],
 }
 PLAIN = {"s2r_version": (i32, []), "s2r_last_error": (C.c_char_p, []), "s2r_device_ok": (i32, []),
          "s2r_comm_ready": (i32, []), "s2r_comm_error": (i32, []), "s2r_comm_destroy": (i32, [])}

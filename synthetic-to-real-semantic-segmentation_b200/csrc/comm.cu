@@ -13,7 +13,14 @@
 // seq lives in device memory and is advanced by the kernel itself, so captured CUDA graphs replay correctly.
 // A slot is reused only DEPTH exchanges later; a rank can be at most one exchange ahead of any peer (it cannot
 // finish exchange k before every peer has contributed to k), so DEPTH = 4 is ample.  Waits are bounded: after
-// ~20 s without progress the kernel records an error code and returns instead of hanging the GPU.
+// ~20 s without progress the kernel records an error code (in mapped host memory: steps.check_peer_exchange polls it
+// once per training step and raises) and returns instead of hanging the GPU.
+// Co-residency: the two exchange channels are used by the two streams of the training step, and a rank may reach
+// them in either order.  Each exchange kernel is ONE CTA that only waits for peers' stores, so two of them in
+// flight need two free CTA slots out of 148 SMs x several -- but CUDA does not GUARANTEE that independent graph
+// branches run concurrently: a rank that serialised channel 0 before channel 1 while a peer serialised them the
+// other way round would cross-wait.  That case ends in the bounded wait + the error above (never a hang or silently
+// partial sums); S2R_OVERLAP=0 runs the step on one stream and one channel.
 //
 // Set-up: each process allocates its inbox with cudaMalloc, exports a CUDA IPC handle, and opens the handles
 // of its peers (exchanged by the host through torch.distributed -- plumbing, not the data path).
@@ -32,14 +39,15 @@ struct CommDev {
   double* inbox[CM_MAX_WORLD];                 // base of every rank's inbox region (peer-mapped)
   unsigned long long* flags[CM_MAX_WORLD];     // base of every rank's flag array [DEPTH][world]
   unsigned long long* seq;                     // local: exchange counter
-  int* err;                                    // local: sticky error flag
+  int* err;                                    // sticky error flag in MAPPED HOST memory (the host polls it without a sync)
   int rank, world, slot;                       // slot: doubles per (depth, rank) entry
 };
 
 struct CommHost {
   bool ready = false;
   int rank = 0, world = 1, slot = 0;
-  void* local = nullptr;                       // cudaMalloc'ed region: inbox | flags | seq | err
+  void* local = nullptr;                       // cudaMalloc'ed region: inbox | flags | seq
+  int* err_host = nullptr;                     // cudaHostAlloc'ed (mapped) sticky error flag
   void* peers[CM_MAX_WORLD] = {nullptr};
   size_t inbox_bytes = 0, flags_bytes = 0;
   CommDev dev;
@@ -140,7 +148,10 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
     }
     buf[i] = acc;
   }
-  if (timed_out) atomicExch(c.err, 1);
+  if (timed_out) {
+    *reinterpret_cast<volatile int*>(c.err) = 1;
+    __threadfence_system();
+  }
   __syncthreads();
   if (threadIdx.x == 0) *seqp = seq;
 }
@@ -159,6 +170,8 @@ extern "C" int s2r_comm_create(int rank, int world, int slot_doubles, void* hand
   const size_t total = h.inbox_bytes + h.flags_bytes + 256;
   S2R_CUDA_OK(cudaMalloc(&h.local, total));
   S2R_CUDA_OK(cudaMemset(h.local, 0, total));
+  S2R_CUDA_OK(cudaHostAlloc((void**)&h.err_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  *h.err_host = 0;
   S2R_CUDA_OK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t ih;
   S2R_CUDA_OK(cudaIpcGetMemHandle(&ih, h.local));
@@ -185,7 +198,7 @@ extern "C" int s2r_comm_open(const void* handles) {
     h.dev.flags[r] = (unsigned long long*)((char*)h.peers[r] + h.inbox_bytes);
   }
   h.dev.seq = (unsigned long long*)((char*)h.local + h.inbox_bytes + h.flags_bytes);
-  h.dev.err = (int*)((char*)h.local + h.inbox_bytes + h.flags_bytes + 64);
+  S2R_CUDA_OK(cudaHostGetDevicePointer((void**)&h.dev.err, h.err_host, 0));
   h.dev.rank = h.rank; h.dev.world = h.world; h.dev.slot = h.slot;
   h.ready = true;
   return S2R_OK;
@@ -213,13 +226,13 @@ extern "C" int s2r_allreduce_small_f64(double* buf, int n, s2r_stream_t stream) 
   return s2r_allreduce_small_f64_ch(buf, n, 0, stream);
 }
 
-/* Non-zero after a bounded wait expired (a peer died); reading it synchronises the device. */
+/* Non-zero after a bounded wait expired (a peer died, or two exchange kernels that needed to be co-resident were
+ * serialised on some rank and cross-waited).  The flag is in mapped host memory: a plain read, no synchronisation --
+ * cheap enough to poll once per training step. */
 extern "C" int s2r_comm_error() {
   const CommHost& h = g_comm;
-  if (!h.ready) return 0;
-  int e = 0;
-  if (cudaMemcpy(&e, h.dev.err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  return e;
+  if (!h.ready || h.err_host == nullptr) return 0;
+  return *reinterpret_cast<volatile int*>(h.err_host);
 }
 
 extern "C" int s2r_comm_destroy() {
@@ -229,6 +242,7 @@ extern "C" int s2r_comm_destroy() {
   for (int r = 0; r < h.world; ++r)
     if (r != h.rank && h.peers[r]) cudaIpcCloseMemHandle(h.peers[r]);
   cudaFree(h.local);
+  if (h.err_host) cudaFreeHost(h.err_host);
   h = CommHost();
   return S2R_OK;
 }

@@ -117,6 +117,10 @@ ce_kernel(const float* __restrict__ logits, const float* __restrict__ target, in
       long long t = target ? (long long)__ldg(target + i + v) : (long long)const_target;
       valid[v] = (t != ignore_index) && t >= 0 && t < C;
       tcls[v] = valid[v] ? (int)t : 0;
+      // a class id outside [0, C) that is not ignore_index: nn.CrossEntropyLoss raises a device assert for it
+      // (utils/loss.py:27-28 of the reference would stop); here the LOSS becomes NaN -- a mislabelled data set (raw
+      // GTA ids 19..254) must not train quietly on the remaining pixels
+      if (!valid[v] && t != ignore_index) loss_acc = __int_as_float(0x7fc00000);
     }
     float mx[V], s[V], xt[V];
     int arg[V];

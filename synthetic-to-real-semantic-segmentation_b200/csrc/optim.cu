@@ -57,7 +57,27 @@ adam_kernel(const s2r_param_slot* __restrict__ slots, const float* __restrict__ 
   }
 }
 
+// Up to 8 floats passed BY VALUE as kernel arguments and stored to device memory: the values are snapshotted when
+// the launch is enqueued, so the host may overwrite its copy immediately (a pinned-host -> device copy node would
+// read the host buffer when the GPU executes it, i.e. possibly after the host has advanced by several steps).
+struct F32x8 {
+  float v[8];
+};
+
+__global__ void store_f32_kernel(float* __restrict__ dst, int n, F32x8 vals) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
 }  // namespace
+
+extern "C" int s2r_store_f32(float* dst, int n, const float* host_vals, s2r_stream_t stream) {
+  S2R_REQUIRE(dst && host_vals && n >= 1 && n <= 8, S2R_ERR_SHAPE, "store_f32: n=%d (1..8)", n);
+  F32x8 v = {};
+  for (int i = 0; i < n; ++i) v.v[i] = host_vals[i];
+  store_f32_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, n, v);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
 
 extern "C" int s2r_sgd_step(const s2r_param_slot* slots, int nslots, const float* hyper, float momentum,
                             float dampening, float weight_decay, int nesterov, float gscale,

@@ -96,6 +96,29 @@ def init_peer_exchange(group=None, slot=4096):
     return True
 
 
+def dp_world():
+    """Number of data-parallel ranks (1 without an initialised torch.distributed)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def allreduce_small_f64(t, group=None):
+    """Sum of a small contiguous fp64 vector over the ranks on the current stream: the NVLink peer-memory kernel
+    (current exchange channel) once the exchange is set up, NCCL otherwise.  Every rank must call it in the same
+    order per stream."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world <= 1:
+        return
+    if PEER["world"] == world and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= PEER["slot"]:
+        L.call("s2r_allreduce_small_f64_ch", _vp(t), t.numel(), COMM_CHANNEL[0],
+               C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream))
+        return
+    dist.all_reduce(t, group=group)
+
+
 _SIDE_STREAMS = {}
 WGRAD_STREAM = os.environ.get("S2R_WGRAD_STREAM", "1") != "0"
 
@@ -214,11 +237,7 @@ class Ctx:
         """Sum of a small statistics vector over the ranks: the NVLink peer-memory kernel when the exchange has
         been set up (init_peer_exchange), NCCL otherwise."""
         if self.world > 1:
-            if PEER["world"] == self.world and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= PEER["slot"]:
-                L.call("s2r_allreduce_small_f64_ch", _vp(t), t.numel(), COMM_CHANNEL[0], self.stream)
-                return
-            import torch.distributed as dist
-            dist.all_reduce(t, group=self.group)
+            allreduce_small_f64(t, self.group)
 
 
 # --------------------------------------------------------------------------- weights
@@ -271,7 +290,9 @@ def packed_weight(cx, w, mode):
 def prepack_weights(stream, build_only=False):
     """Re-pack, in ONE launch, every filter copy whose parameter changed since it was packed (call after the
     optimizer kernels / at the start of a step).  Later packed_weight() calls then hit the cache.
-    build_only: only upload the job table (a host->device copy, which must happen outside CUDA-graph capture)."""
+    build_only: only upload the job table (a host->device copy, which must happen outside CUDA-graph capture) and
+    return it: a CUDA graph that captures the launch holds raw pointers into the table, so whoever captures keeps the
+    returned object alive with the graph."""
     stale = []
     for k, (ref, transpose) in list(_PACK_REGISTRY.items()):
         w = ref()
@@ -305,10 +326,11 @@ def prepack_weights(stream, build_only=False):
             dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(stale[0][0].device)
             chunks.append((dev, len(part)))
         tab = chunks
-        _PACK_TABLES.clear()          # one live signature is enough (the set of filters of a training job is fixed)
+        while len(_PACK_TABLES) >= 8:            # a handful of live signatures (train / val / second model set)
+            _PACK_TABLES.pop(next(iter(_PACK_TABLES)))
         _PACK_TABLES[sig] = tab
     if build_only:
-        return len(stale)
+        return tab
     for dev, n in tab:
         L.call("s2r_pack_weights_multi", _vp(dev), n, stream)
     for w, transpose, ent, stamp in stale:
@@ -317,6 +339,12 @@ def prepack_weights(stream, build_only=False):
 
 
 _PACK_TABLES = {}
+
+
+def invalidate_packs():
+    """Mark every cached bf16 filter copy stale (call after parameters were rewritten behind torch's version counters,
+    e.g. through raw pointers); the next packed_weight() / prepack_weights() refreshes them."""
+    WEIGHT_EPOCH[0] += 1
 
 
 def grad_of(p):
@@ -680,6 +708,16 @@ def bn_backward(cx, bn, dy, z, st, act, dx, drop_p=0.0, seed=0, presummed=None, 
     return dx
 
 
+# When a dict {id(bn module): list}: the forward pass appends the raw conv output (Act) every training-mode BatchNorm in
+# the dict normalises -- bench.py's multi-rank parity record gathers them to check the synchronised statistics.
+BN_PROBE = None
+
+
+def _probe(bn, z):
+    if BN_PROBE is not None and id(bn) in BN_PROBE:
+        BN_PROBE[id(bn)].append(z)
+
+
 # --------------------------------------------------------------------------- composite layers
 class ConvBNAct:
     """conv -> BatchNorm -> activation [-> dropout], the BN output materialised in bf16.
@@ -697,6 +735,7 @@ class ConvBNAct:
         train = cx.training and self.bn.training
         sums = cx.f64(2 * Cout) if train else None
         conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
+        _probe(self.bn, z)
         # count_pad: the reference ran this conv on an input padded by count_pad pixels per side
         # (mobilenet.py:62-67): the extra border outputs are exact zeros but count in the statistics
         count = x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad)
@@ -801,6 +840,7 @@ class InvertedResidual:
         train = cx.training and self.bn2.training
         sums2 = cx.f64(2 * dw_in.C) if train else None
         z2 = dw_fwd(cx, dw_in, st_in, L.ACT_RELU6, halo, self.dw.weight, self.stride, d, d, sums2)
+        _probe(self.bn2, z2)
         st2 = bn_state(cx, self.bn2, sums2, z2.P)
         y2 = cx.new(z2.N, z2.H, z2.W, z2.C)
         bn_apply(cx, z2, st2, L.ACT_RELU6, y2)

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .engine import _vp
+from .engine import _vp, dp_world, allreduce_small_f64
 
 
 def _stream(t):
@@ -61,6 +61,16 @@ def pop_pending_scale(t):
     return PENDING_SCALE.pop(t.data_ptr(), None) if PENDING_SCALE else None
 
 
+# Data-parallel runs (one process per GPU, torch.distributed initialised with more than one rank): the reference
+# evaluates its criterion on the batch GATHERED by nn.DataParallel (train_adapt.py:87-88,144-145), i.e. the mean runs
+# over the valid pixels of the global batch.  With this switch on (default) the cross entropy all-reduces its three
+# sums -- 24 bytes -- so that every rank returns that global mean, and scales its local gradient by world / sum_global(w):
+# after the gradient all-reduce + 1/world of the fused optimizers this is exactly the gradient of the global-mean loss,
+# also when the ranks hold different numbers of valid (non-ignored) pixels.  Constant-target calls without class
+# weights (the domain loss, utils/loss.py:57-69) have equal counts on every rank and skip the exchange.
+GLOBAL_BATCH_MEAN = [True]
+
+
 class _CrossEntropy(torch.autograd.Function):
     """mean_{valid}(w_t * (lse - x_t)) with ignore_index (nn.CrossEntropyLoss, reduction='mean')."""
 
@@ -84,9 +94,13 @@ class _CrossEntropy(torch.autograd.Function):
             st = _stream(logit)
             L.call("s2r_cross_entropy_nchw", _vp(logit), _vp(target), int(const_target), _vp(weight), N, Cc, HW,
                    int(ignore_index), _vp(sums), _vp(grad), st)
+            world = dp_world() if (GLOBAL_BATCH_MEAN[0] and (target is not None or weight is not None)) else 1
+            if world > 1:
+                allreduce_small_f64(sums)
             L.call("s2r_ratio", _vp(sums), 0.0, _vp(out), st)
         ctx.grad = grad
         ctx.sums = sums
+        ctx.world = world
         if stats_out is not None:
             stats_out.append(sums)
         return out
@@ -96,6 +110,8 @@ class _CrossEntropy(torch.autograd.Function):
         grad, sums = ctx.grad, ctx.sums
         ctx.grad = None
         gout = gout.contiguous().float()
+        if ctx.world > 1:
+            gout = gout * float(ctx.world)      # see GLOBAL_BATCH_MEAN
         if DEFER_CE_SCALE[0]:
             PENDING_SCALE.clear()          # at most one pending gradient: a stale entry must never meet a recycled address
             PENDING_SCALE[grad.data_ptr()] = (gout.double() / sums[1]).float().reshape(1)

@@ -7,20 +7,19 @@ up-sampling (deeplab.py:31) writes the NCHW fp32 logits the callers expect.
 """
 import torch.nn as nn
 
-from .. import _lib as L
-from ..engine import _vp
-from ..functional import pop_pending_scale
 from ..runtime import RunBase, call_module
 from .sync_batchnorm import SynchronizedBatchNorm2d
 from .assp import build_aspp, ASPPRun
-from .decoder import build_decoder, DecoderRun
+from .decoder import build_decoder, DecoderRun, UpsampledLogits
 from .backbone import build_backbone
 from .backbone.mobilenet import MobileNetV2Run
 
 import torch
 
 
-class DeepLabRun(RunBase):
+class DeepLabRun(UpsampledLogits, RunBase):
+    """F.interpolate(x, size=input.size()[2:], mode='bilinear', align_corners=True) (deeplab.py:31) is fused with the
+    NHWC bf16 -> NCHW fp32 boundary conversion (decoder.UpsampledLogits)."""
     raw_inputs = True   # see MobileNetV2Run
 
     def __init__(self, mod):
@@ -29,30 +28,9 @@ class DeepLabRun(RunBase):
         self.decoder = DecoderRun(mod.decoder)
 
     def forward(self, cx, x):
-        self.in_hw = (x.H, x.W)
+        self.out_hw = (x.H, x.W)
         high, low = self.backbone.forward(cx, x)
         return self.decoder.forward(cx, self.aspp.forward(cx, high), low)
-
-    def export(self, cx, i, a):
-        # F.interpolate(x, size=input.size()[2:], mode='bilinear', align_corners=True) fused with
-        # the NHWC bf16 -> NCHW fp32 boundary conversion
-        H, W = self.in_hw
-        self.small = (a.N, a.H, a.W, a.C, a.pitch)
-        y = torch.empty((a.N, a.C, H, W), dtype=torch.float32, device=cx.device)
-        L.call("s2r_upsample_bilinear_nhwc_to_nchw", a.vp(), a.pitch, a.N, a.H, a.W, a.C, _vp(y), H, W, cx.stream)
-        return y
-
-    def import_grad(self, cx, i, d):
-        if d is None:
-            return None
-        N, h, w, Cc, pitch = self.small
-        scale = pop_pending_scale(d)       # a loss that left its mean-reduction factor to this kernel (functional.py)
-        d = d.contiguous()
-        g = cx.new(N, h, w, pitch)
-        g.C = Cc
-        L.call("s2r_upsample_bilinear_nchw_bwd_to_nhwc_scaled", _vp(d), N, Cc, d.shape[2], d.shape[3], g.vp(), pitch, h, w,
-               _vp(scale), cx.stream)
-        return g
 
     def backward(self, cx, douts, need=None):
         dx, dlow = self.decoder.backward(cx, douts)

@@ -4,8 +4,10 @@ torch.optim surface the reference's scripts use: param_groups with a mutable 'lr
 
 Gradients of all parameters live in ONE flat fp32 buffer (p.grad are views): zero_grad is a single
 memset, the data-parallel gradient all-reduce is a single NCCL call, and the slot table the
-kernels walk is built once.  Learning rate / bias corrections travel through a pinned host buffer
-and a device copy so that a captured CUDA graph replays with the current schedule value.
+kernels walk is built once.  Learning rate / bias corrections live in a small device buffer that
+advance() rewrites before every step with a stream-ordered store whose values travel as kernel
+arguments (s2r_store_f32): they are snapshotted when advance() is called, so a captured CUDA graph
+replays with the schedule value of ITS step even when the host runs several steps ahead of the GPU.
 """
 import ctypes as C
 import math
@@ -63,7 +65,7 @@ class _FusedBase(object):
             self._views.append((p, off, n))
             off += n
         self._tables = None
-        self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in self.param_groups]
+        self._hyper_host = [[0.0, 1.0, 1.0, 0.0] for _ in self.param_groups]
         self._hyper_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in self.param_groups]
         self.steps = 0
         self.grad_scale = 1.0
@@ -112,6 +114,17 @@ class _FusedBase(object):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _publish(self):
+        """Stream-ordered store of the hyper-parameters computed by advance() (values passed by value: no host
+        buffer is read after this returns).  Must not run inside a CUDA-graph capture: the captured step holds only
+        launch(); advance() runs on the replay stream ahead of every replay."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("optimizer.advance() inside a CUDA-graph capture: capture launch() only")
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            for h, d in zip(self._hyper_host, self._hyper_dev):
+                L.call("s2r_store_f32", _vp(d), 4, (C.c_float * 4)(*h), st)
 
     # state names in torch.optim's state_dict (torch.optim.SGD: 'momentum_buffer'; Adam: 'exp_avg', 'exp_avg_sq')
     state_names = ('momentum_buffer',)
@@ -182,17 +195,16 @@ class FusedSGD(_FusedBase):
                                       nesterov=nesterov))
 
     def advance(self):
-        """Host half of a step: publish the current learning rates in the pinned buffers the device
-        copy reads (also at CUDA-graph replay)."""
+        """Host half of a step: the current learning rates go to the device buffer the kernels read (stream-ordered
+        ahead of the eager launch() or of the CUDA-graph replay that follows)."""
         for gi, g in enumerate(self.param_groups):
             self._hyper_host[gi][0] = float(g['lr'])
         self.steps += 1
-        WEIGHT_EPOCH[0] += 1
+        self._publish()
 
     @torch.no_grad()
     def launch(self):
-        """Device half of a step (graph-capturable): pinned->device copy of the hyper-parameters and
-        one multi-tensor kernel per parameter group."""
+        """Device half of a step (graph-capturable): one multi-tensor kernel per parameter group."""
         if self._tables is None:
             self._build_tables()
         with torch.cuda.device(self.device):
@@ -200,10 +212,10 @@ class FusedSGD(_FusedBase):
                 tab, n = self._tables[gi]
                 if n == 0:
                     continue
-                self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
                 L.call("s2r_sgd_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(g['momentum']),
                        float(g['dampening']), float(g['weight_decay']), 1 if g['nesterov'] else 0,
                        float(self.grad_scale), self._stream())
+        WEIGHT_EPOCH[0] += 1     # the parameters change behind torch's version counters: bf16 filter copies are stale
 
     def step(self):
         self.advance()
@@ -226,7 +238,7 @@ class FusedAdam(_FusedBase):
             h[0] = float(g['lr'])
             h[1] = 1.0 - math.pow(b1, self.steps)
             h[2] = 1.0 - math.pow(b2, self.steps)
-        WEIGHT_EPOCH[0] += 1
+        self._publish()
 
     @torch.no_grad()
     def launch(self):
@@ -238,9 +250,9 @@ class FusedAdam(_FusedBase):
                 if n == 0:
                     continue
                 b1, b2 = g['betas']
-                self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
                 L.call("s2r_adam_step", _vp(tab), n, _vp(self._hyper_dev[gi]), float(b1), float(b2), float(g['eps']),
                        float(g['weight_decay']), float(self.grad_scale), self._stream())
+        WEIGHT_EPOCH[0] += 1
 
     def step(self):
         self.advance()

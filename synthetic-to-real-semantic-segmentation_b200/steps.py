@@ -16,7 +16,8 @@ import os
 
 import torch
 
-from .engine import seed_counter, prepack_weights, PEER, COMM_CHANNEL
+from . import _lib as _L
+from .engine import seed_counter, prepack_weights, PEER, COMM_CHANNEL, WEIGHT_EPOCH
 from . import functional as _fn
 from .functional import softmax_dim0, bce_with_logits
 from .optim import FusedSGD, FusedAdam
@@ -42,6 +43,19 @@ def _backward_ce_deferred(loss, model):
         raise RuntimeError("deferred cross-entropy scale was not consumed by the model's backward")
 
 
+def check_peer_exchange():
+    """Raise if the NVLink peer exchange of the BN statistics (csrc/comm.cu) hit its bounded wait -- a peer died, or
+    the exchange kernels of the step's two streams were not co-resident on some rank and cross-waited.  The flag
+    lives in mapped host memory, so this is a plain host read (no device synchronisation): the training steps poll
+    it once per iteration, i.e. an error surfaces one step late at most instead of training on on partial sums."""
+    if PEER["world"] > 1:
+        e = _L.lib().s2r_comm_error()
+        if e != 0:
+            raise _L.S2RError("BN-statistics peer exchange timed out (code %d): a rank is gone, or the two exchange "
+                              "channels of the two-stream step cross-waited -- rerun with S2R_OVERLAP=0 (one stream, "
+                              "one channel) or S2R_COMM=nccl" % e)
+
+
 def _disc_on_softmax0(model_D, logits):
     """model_D(F.softmax(logits, dim=0)) (train_adapt.py:151,166,174); the discriminator's fused input stage
     when it covers the shape, the two separate calls otherwise."""
@@ -52,66 +66,12 @@ def _disc_on_softmax0(model_D, logits):
     return model_D(softmax_dim0(logits))
 
 
-class AdaptStep(object):
-    def __init__(self, model, model_D, lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False,
-                 lr_scheduler='poly', epochs=200, iters_per_epoch=1000, class_weight=None, loss_type='ce'):
-        self.model, self.model_D = model, model_D
-        train_params = [{'params': list(model.get_1x_lr_params()), 'lr': lr},
-                        {'params': list(model.get_10x_lr_params()), 'lr': lr * 10}]
-        self.optimizer = FusedSGD(train_params, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov)
-        self.optimizer_D = FusedAdam(model_D.parameters(), lr=1e-4, betas=(0.9, 0.99))
-        self.criterion = SegmentationLosses(weight=class_weight).build_loss(mode=loss_type)
-        self.scheduler = LR_Scheduler(lr_scheduler, lr, epochs, iters_per_epoch)
-        self.source_label, self.target_label = 0, 1
+class _StagedInputs(object):
+    """Input pipelining for a captured step (AdaptStep / FeatureStep): the next step's host tensors are copied into
+    device staging buffers on a copy stream while the current graph replay runs; the replay then starts with a
+    device-to-device copy into the graph's static inputs (what a prefetching data loader does around
+    train_adapt.py:126-129 / train.py:163-172)."""
 
-    def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
-        """One eager step.  With capture() done, use replay() instead."""
-        self.scheduler(self.optimizer, i, epoch)
-        self.scheduler(self.optimizer_D, i, epoch)
-        self.optimizer.advance()
-        self.optimizer_D.advance()
-        return self._device_step(src_image, src_label, tgt_image)
-
-    def capture(self, src_image, src_label, tgt_image, warmup=2):
-        """Capture the whole step (both generator passes, three discriminator passes, all backward
-        passes, gradient all-reduce and both optimizer kernels) into one CUDA graph.  Inputs are copied
-        into static buffers before each replay; learning rates and Adam bias corrections reach the
-        device through pinned buffers, dropout masks through the device seed counter."""
-        dev = src_image.device
-        self._static = tuple(torch.empty_like(t) for t in (src_image, src_label, tgt_image))
-        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
-            st.copy_(t)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for k in range(warmup):
-                self(*self._static, i=0, epoch=0)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.scheduler(self.optimizer, 0, 0)
-        self.scheduler(self.optimizer_D, 0, 0)
-        self.optimizer.advance()
-        self.optimizer_D.advance()
-        prepack_weights(None, build_only=True)   # the job table is uploaded here, its launch is captured below
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_out = self._device_step(*self._static)
-        return self
-
-    def replay(self, src_image, src_label, tgt_image, i=0, epoch=0):
-        self.scheduler(self.optimizer, i, epoch)
-        self.scheduler(self.optimizer_D, i, epoch)
-        self.optimizer.advance()
-        self.optimizer_D.advance()
-        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
-            if st.data_ptr() != t.data_ptr():
-                st.copy_(t, non_blocking=True)
-        self._graph.replay()
-        return self._static_out
-
-    # ---- input pipelining for the captured step: the next step's host tensors are copied into device staging
-    # buffers on a copy stream while the current graph replay runs; the replay then starts with a device-to-device
-    # copy into the graph's static inputs (what a prefetching data loader does around train_adapt.py:126-129).
     def stage(self, src_image, src_label, tgt_image):
         """Start the asynchronous host->device copy of one step's inputs (pinned host tensors)."""
         dev = self._static[0].device
@@ -141,6 +101,68 @@ class AdaptStep(object):
         self._d2d_done = torch.cuda.Event()
         self._d2d_done.record(cur)
         return self.replay(*self._static, i=i, epoch=epoch)
+
+
+class AdaptStep(_StagedInputs):
+    def __init__(self, model, model_D, lr=5e-4, momentum=0.9, weight_decay=5e-4, nesterov=False,
+                 lr_scheduler='poly', epochs=200, iters_per_epoch=1000, class_weight=None, loss_type='ce'):
+        self.model, self.model_D = model, model_D
+        train_params = [{'params': list(model.get_1x_lr_params()), 'lr': lr},
+                        {'params': list(model.get_10x_lr_params()), 'lr': lr * 10}]
+        self.optimizer = FusedSGD(train_params, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov)
+        self.optimizer_D = FusedAdam(model_D.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        self.criterion = SegmentationLosses(weight=class_weight).build_loss(mode=loss_type)
+        self.scheduler = LR_Scheduler(lr_scheduler, lr, epochs, iters_per_epoch)
+        self.source_label, self.target_label = 0, 1
+
+    def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        """One eager step.  With capture() done, use replay() instead."""
+        check_peer_exchange()
+        self.scheduler(self.optimizer, i, epoch)
+        self.scheduler(self.optimizer_D, i, epoch)
+        self.optimizer.advance()
+        self.optimizer_D.advance()
+        return self._device_step(src_image, src_label, tgt_image)
+
+    def capture(self, src_image, src_label, tgt_image, warmup=2):
+        """Capture the whole step (both generator passes, three discriminator passes, all backward
+        passes, gradient all-reduce and both optimizer kernels) into one CUDA graph.  Inputs are copied
+        into static buffers before each replay; learning rates and Adam bias corrections reach the
+        device through optimizer.advance() ahead of every replay (values snapshotted at call time, optim.py),
+        dropout masks through the device seed counter."""
+        dev = src_image.device
+        self._static = tuple(torch.empty_like(t) for t in (src_image, src_label, tgt_image))
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            st.copy_(t)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for k in range(warmup):
+                self(*self._static, i=0, epoch=0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # the captured step holds launch() only: the host half (scheduler + advance(): step count, learning rates
+        # and bias corrections into the device buffers) runs ahead of every replay, not here -- the capture itself
+        # executes nothing and must not count as a step
+        # the job table is uploaded here and stays alive with the graph; its launch is captured below
+        self._pack_tables = prepack_weights(None, build_only=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._device_step(*self._static)
+        return self
+
+    def replay(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        check_peer_exchange()
+        self.scheduler(self.optimizer, i, epoch)
+        self.scheduler(self.optimizer_D, i, epoch)
+        self.optimizer.advance()
+        self.optimizer_D.advance()
+        for st, t in zip(self._static, (src_image, src_label, tgt_image)):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self._graph.replay()
+        WEIGHT_EPOCH[0] += 1     # the captured optimizer kernels changed the parameters (engine.packed_weight stamps)
+        return self._static_out
 
     def _device_step(self, src_image, src_label, tgt_image):
         model, model_D = self.model, self.model_D
@@ -247,7 +269,7 @@ AdaptStep._two_streams = _adapt_two_streams
 AdaptStep._passes_two_streams = _adapt_passes_two_streams
 
 
-class FeatureStep(object):
+class FeatureStep(_StagedInputs):
     def __init__(self, backbone_model, assp_model, y_model, d_model, lr=5e-4, optimizer='Adam', momentum=0.9,
                  weight_decay=5e-4, nesterov=False, lr_scheduler='poly', epochs=200, iters_per_epoch=1000):
         self.f, self.a, self.y, self.d = backbone_model, assp_model, y_model, d_model
@@ -272,13 +294,18 @@ class FeatureStep(object):
     def _forward(self, image):
         high0, low = self.f(image)
         high = self.a(high0)
-        out = torch.nn.functional.interpolate(self.y(high, low), image.size()[2:], mode='bilinear', align_corners=True)
+        # F.interpolate(self.y_model(high, low), image.size()[2:], mode='bilinear', align_corners=True)
+        # (train.py:184,194): the up-sampling is fused into the decoder's output conversion (resize.cu)
+        out = self.y(high, low, size=image.size()[2:])
         return out, self.d(high)
 
     def _optimizers(self):
         return (self.task_optimizer, self.d_optimizer, self.d_inv_optimizer)
 
-    def __call__(self, src_image, src_label, tgt_image, i=0, epoch=0):
+    def __call__(self, src_image, src_label, tgt_image=None, i=0, epoch=0):
+        """One eager step.  tgt_image=None: the single-domain branch of the loop (args.dataset == 'gtav',
+        train.py:164-165,205-210) -- task loss only, only task_optimizer steps."""
+        check_peer_exchange()
         for o in self._optimizers():
             self.scheduler(o, i, epoch)
         return self._device_step(src_image, src_label, tgt_image)
@@ -307,19 +334,20 @@ class FeatureStep(object):
                 self(*self._static, i=0, epoch=0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self._advance(0, 0)
-        prepack_weights(None, build_only=True)
+        self._pack_tables = prepack_weights(None, build_only=True)    # see AdaptStep.capture
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_out = self._device_step(*self._static, launch_only=True)
         return self
 
     def replay(self, src_image, src_label, tgt_image, i=0, epoch=0):
+        check_peer_exchange()
         self._advance(i, epoch)
         for st, t in zip(self._static, (src_image, src_label, tgt_image)):
             if st.data_ptr() != t.data_ptr():
                 st.copy_(t, non_blocking=True)
         self._graph.replay()
+        WEIGHT_EPOCH[0] += 1
         return self._static_out
 
     def _device_step(self, src_image, src_label, tgt_image, launch_only=False):
@@ -329,6 +357,18 @@ class FeatureStep(object):
         prepack_weights(torch.cuda.current_stream(src_image.device).cuda_stream)
         src_output, src_d_pred = self._forward(src_image)
         task_loss = self.task_loss(src_output, src_label)
+        if tgt_image is None:
+            # train.py:205-210: the domain classifier ran on the source features (:187, its BatchNorm statistics
+            # moved) but only the task loss is back-propagated and only task_optimizer steps
+            del src_d_pred
+            task_loss.backward()
+            self.task_optimizer.all_reduce_grads()
+            if launch_only:
+                self.task_optimizer.launch()
+            else:
+                self.task_optimizer.step()
+            zero = torch.zeros((), device=src_image.device)
+            return {'task_loss': task_loss.detach(), 'd_loss': zero, 'd_inv_loss': zero, 'd_acc': 0}
         _, tgt_d_pred = self._forward(tgt_image)
         d_loss, d_acc = self.domain_loss(src_d_pred, tgt_d_pred)
         d_inv_loss, _ = self.domain_loss(tgt_d_pred, src_d_pred)
@@ -460,20 +500,28 @@ class ValStep(object):
 
     @torch.no_grad()
     def replay(self, image, target):
+        # the graph holds no pack kernels (capture() packed the filters in its eager warm-up): bf16 filter copies
+        # made stale since then -- by an optimizer step of a training graph, a checkpoint load, any in-place update
+        # -- are refreshed here, in one launch on the current stream, which every lane waits for below
+        prepack_weights(torch.cuda.current_stream(image.device).cuda_stream)
         static, graph, stream = self._lanes[self._next]
         self._next = (self._next + 1) % len(self._lanes)
+        consumed = torch.cuda.Event()
         if stream is None:
             for st, t in zip(static, (image, target)):
                 if st.data_ptr() != t.data_ptr():
                     st.copy_(t, non_blocking=True)
+            consumed.record(torch.cuda.current_stream(image.device))
             graph.replay()
-            return
+            return consumed
         stream.wait_stream(torch.cuda.current_stream(image.device))     # the caller's tensors are ready
         with torch.cuda.stream(stream):
             for st, t in zip(static, (image, target)):
                 if st.data_ptr() != t.data_ptr():
                     st.copy_(t, non_blocking=True)
+            consumed.record(stream)
             graph.replay()
+        return consumed     # the caller may overwrite image / target once this event has completed (input pipelining)
 
     def all_reduce(self, group=None):
         """Data-parallel validation: every rank has run its shard of the images (rank r takes images r, r + world,

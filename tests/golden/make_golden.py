@@ -621,6 +621,81 @@ def feature_loop_case():
                         checkpoint_layout=np.array(checkpoint_layout(saved[0][0])))
 
 
+def feature_single_loop_case():
+    """train.py's single-domain branch (args.dataset == 'gtav', train.py:164-165,205-210) on the reference's own code:
+    the unmodified `Trainer.training` for ten iterations on {'image', 'label'} samples -- task loss only, only
+    task_optimizer steps, the domain classifier still runs forward on the source features (:187) -- against ten oracle
+    feature_step(..., tgt_image=None) iterations: losses, updated weights, the (moved) domain-classifier BN statistics
+    and its (unmoved) weights."""
+    import types
+    import torch.nn.functional as F
+    from utils.lr_scheduler import LR_Scheduler as RefSched
+    nn = torch.nn
+
+    class Bar(list):
+        def set_description(self, text):
+            pass
+
+    training = reference_method('train.py', 'training', {'np': np, 'torch': torch, 'F': F, 'tqdm': lambda it: Bar(it)})
+    torch.manual_seed(17)
+    bb = no_dropout(ref_mobilenet.MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d))
+    aspp = no_dropout(RefASPP(backbone='mobilenet', output_stride=16, BatchNorm=nn.BatchNorm2d))
+    dec = no_dropout(RefDecoder(num_classes=19, backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+    dc = no_dropout(RefDC(backbone='mobilenet', BatchNorm=nn.BatchNorm2d))
+    sds = [clone_sd(m) for m in (bb, aspp, dec, dc)]
+    dc_w0 = dc.DC_adnn3.weight.detach().clone()
+    lr, n_it = 5e-4, 10
+    f_params = list(bb.parameters()) + list(aspp.parameters())
+    mk = lambda ps: torch.optim.Adam(ps, lr=lr)  # noqa: E731
+    o_fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+    o_opts = (mk(o_fp + list(O.leaf_params(sds[2]).values())), mk(list(O.leaf_params(sds[3]).values())), mk(o_fp))
+    loader = []
+    g = torch.Generator().manual_seed(19)
+    for it in range(n_it):
+        loader.append({'image': torch.randn(2, 3, 48, 64, generator=g),
+                       'label': torch.randint(0, 19, (2, 48, 64), generator=g).float()})
+    seen = []
+
+    def recorded(fn):
+        def wrapper(*a):
+            out = fn(*a)
+            seen.append(out.item())
+            return out
+        return wrapper
+
+    def no_domain_loss(*a):
+        raise AssertionError('the single-domain branch must not evaluate the domain loss')
+
+    quiet = types.SimpleNamespace(add_scalar=lambda *a: None, visualize_image=lambda *a: None)
+    trainer = types.SimpleNamespace(
+        backbone_model=bb, assp_model=aspp, y_model=dec, d_model=dc,
+        task_optimizer=mk(f_params + list(dec.parameters())), d_optimizer=mk(list(dc.parameters())),
+        d_inv_optimizer=mk(f_params), c_optimizer=mk(f_params + list(dec.parameters())),
+        scheduler=RefSched('poly', lr, 1, n_it), best_pred=0.0, train_loader=loader,
+        task_loss=recorded(RefSegLoss().build_loss('ce')), domain_loss=no_domain_loss,
+        writer=quiet, summary=quiet, args=types.SimpleNamespace(cuda=False, batch_size=2, dataset='gtav', no_val=False))
+    training(trainer, 0)
+    ref_hist = np.array(seen)
+    o_hist = []
+    for it, b in enumerate(loader):
+        for o in o_opts:
+            o.param_groups[0]['lr'] = O.poly_lr(lr, it, n_it)
+        o_hist.append(O.feature_step(sds[0], sds[1], sds[2], sds[3], o_opts, b['image'], b['label'], None, O.BNCfg(True),
+                                     drop=False)[0])
+    o_hist = np.array(o_hist, dtype=np.float64)
+    print('single-domain feature loop: reference', ref_hist.tolist(), 'oracle', o_hist.tolist())
+    assert np.allclose(ref_hist, o_hist, rtol=2e-3, atol=1e-5), np.abs(ref_hist / o_hist - 1).max()
+    fix = {'losses': ref_hist}
+    for sd, m, k in ((sds[0], bb, 'features.0.0.weight'), (sds[1], aspp, 'conv1.weight'), (sds[2], dec, 'last_conv.8.weight'),
+                     (sds[3], dc, 'DC_adnn1.1.running_mean'), (sds[3], dc, 'DC_adnn3.weight')):
+        w = m.state_dict()[k].detach()
+        assert relerr(sd[k].detach(), w) < 2e-3, (k, relerr(sd[k].detach(), w))
+        fix['w:' + k] = head(w)
+    assert torch.equal(dc.DC_adnn3.weight.detach(), dc_w0)                  # d_optimizer never stepped
+    assert float(dc.DC_adnn1[1].running_mean.abs().sum()) > 0               # ... but its forward ran (train.py:187)
+    np.savez_compressed(os.path.join(HERE, 'feature_single_loop.npz'), **fix)
+
+
 def validation_case():
     """BASELINE config 5: the reference's own `Trainer.validation` (val_adapt.py:117-175, unmodified) run on the CPU
     over three batches (2 + 2 + 1 images) with the reference's DeepLab, criterion and Evaluator; it appends its report
@@ -766,6 +841,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'featureloop':
         feature_loop_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'featuresingle':
+        feature_single_loop_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'adaptloop':
         adapt_loop_case()
         sys.exit(0)
@@ -787,6 +865,7 @@ if __name__ == '__main__':
     adapt_step_case()
     adapt_loop_case()
     feature_loop_case()
+    feature_single_loop_case()
     sync_bn_case()
     validation_case()
     feature_step_case()

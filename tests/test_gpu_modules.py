@@ -278,6 +278,8 @@ def test_adapt_step_two_iterations_vs_reference_fixture(built_lib):
     G.cuda().train()
     D.cuda().train()
     step = sub("steps").AdaptStep(G, D, lr=5e-4, epochs=1, iters_per_epoch=10)
+    init = {k: p.detach().clone() for k, p in G.named_parameters()}
+    init_d = D.conv1.weight.detach().clone()
 
     def inputs(seed):
         g = torch.Generator().manual_seed(seed)
@@ -295,13 +297,40 @@ def test_adapt_step_two_iterations_vs_reference_fixture(built_lib):
         # iteration 0 starts from identical weights; iteration 1 sees the (chaotically different) logits of
         # updated weights through the discriminator, hence the wider band
         assert np.allclose(got, fix['losses'][it], rtol=1e-2 if it == 0 else 5e-2, atol=2e-3), (got, fix['losses'][it])
+    # What the optimizers did: the weight DELTAS w_after - w_init against the reference run's (the initial weights are
+    # the reference's, bit for bit: same seed, same constructor order -- tests/test_oracle.py).  After two SGD steps at
+    # lr ~5e-4 the weights themselves move by 1e-4..1e-3 relative, so comparing the weights would pass with a no-op
+    # optimizer; the deltas do not: a missing step gives rel = 1, a wrong sign rel = 2, the 1x / 10x learning-rate
+    # groups swapped a factor 10.  The classifier's gradient is well posed (pinned to 15 % above) -> tight bound on the
+    # 10x group; ASPP and the stem carry the chaotic common factor of the backbone gradient (module docstring) ->
+    # direction and order of magnitude.
     params = dict(G.named_parameters())
-    for k in fix.files:
-        if k.startswith('w:'):
-            assert rel(params[k[2:]].detach().reshape(-1)[:4096], fix[k]) <= 1e-2, k
-    # Adam normalises the gradient: after two steps of lr ~5e-4 a differing gradient sign moves a weight of
-    # magnitude ~3e-2 by up to 1e-3
-    assert rel(D.conv1.weight.detach().reshape(-1)[:4096], fix['wd:conv1.weight']) <= 6e-2
+
+    def delta(k, fixed, w0):
+        w0 = w0.detach().reshape(-1)[:fixed.shape[0]].double().cpu()
+        got_ = params[k].detach().reshape(-1)[:fixed.shape[0]].double().cpu() - w0 if k in params else None
+        return got_, torch.from_numpy(fixed).double() - w0
+
+    report = {}
+    for k in ('decoder.last_conv.8.weight', 'aspp.conv1.weight', 'backbone.features.0.0.weight'):
+        got_d, want_d = delta(k, fix['w:' + k], init[k])
+        cos = float((got_d * want_d).sum() / (got_d.norm() * want_d.norm() + 1e-30))
+        ratio = float(got_d.norm() / (want_d.norm() + 1e-30))
+        report[k] = (round(rel(got_d, want_d), 3), round(cos, 3), round(ratio, 3))
+    got_dd = D.conv1.weight.detach().reshape(-1)[:4096].double().cpu() - init_d.reshape(-1)[:4096].double().cpu()
+    want_dd = torch.from_numpy(fix['wd:conv1.weight']).double() - init_d.reshape(-1)[:4096].double().cpu()
+    cos_d = float((got_dd * want_dd).sum() / (got_dd.norm() * want_dd.norm() + 1e-30))
+    ratio_d = float(got_dd.norm() / (want_dd.norm() + 1e-30))
+    print("weight deltas vs reference run (rel, cosine, norm ratio):", report, "D.conv1 (Adam): cos %.3f ratio %.3f" % (cos_d, ratio_d))
+    r, c, q = report['decoder.last_conv.8.weight']
+    assert r <= 0.2 and c >= 0.98, report
+    r, c, q = report['aspp.conv1.weight']
+    assert c >= 0.5 and 0.3 <= q <= 3.0, report
+    r, c, q = report['backbone.features.0.0.weight']
+    assert c >= 0.2 and 0.2 <= q <= 5.0, report
+    # Adam normalises the gradient: every element moves by ~lr per step whatever the gradient's size, so the norm of
+    # the delta is pinned (a wrong bias correction or a stale lr shows here) while signs of tiny gradients may differ
+    assert 0.8 <= ratio_d <= 1.25 and cos_d >= 0.5, (cos_d, ratio_d)
 
 
 def test_feature_step_runs_and_matches_oracle_losses(built_lib):

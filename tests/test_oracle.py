@@ -286,6 +286,38 @@ def test_feature_loop_against_reference_training_run():
         assert np.allclose(got, fix['losses'][it], rtol=2e-3, atol=1e-5), (it, got, fix['losses'][it])
 
 
+def test_feature_single_domain_loop_against_reference_training_run():
+    """train.py's single-domain branch (args.dataset == 'gtav', train.py:164-165,205-210): the task-loss history of the
+    reference's own unmodified `Trainer.training` (ten iterations, tests/golden/make_golden.py
+    feature_single_loop_case, which checks all ten and the final weights) against the oracle's
+    feature_step(..., tgt_image=None) -- the first three iterations here, plus the branch's defining properties: the
+    domain classifier's weights do not move, its BatchNorm statistics do (its forward still runs, train.py:187)."""
+    fix = golden('feature_single_loop')
+    assert fix['losses'].shape == (10,)
+    nn = torch.nn
+    torch.manual_seed(17)
+    mods = (sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d),
+            sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d),
+            sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d),
+            sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d))
+    sds = [grad_sd(mod) for mod in mods]
+    dc_w0 = sds[3]['DC_adnn3.weight'].detach().clone()
+    fp = list(O.leaf_params(sds[0]).values()) + list(O.leaf_params(sds[1]).values())
+    opts = (torch.optim.Adam(fp + list(O.leaf_params(sds[2]).values()), lr=5e-4),
+            torch.optim.Adam(list(O.leaf_params(sds[3]).values()), lr=5e-4), torch.optim.Adam(fp, lr=5e-4))
+    g = torch.Generator().manual_seed(19)
+    for it in range(3):
+        img = torch.randn(2, 3, 48, 64, generator=g)
+        lab = torch.randint(0, 19, (2, 48, 64), generator=g).float()
+        for o in opts:
+            o.param_groups[0]['lr'] = O.poly_lr(5e-4, it, 10)
+        got = O.feature_step(sds[0], sds[1], sds[2], sds[3], opts, img, lab, None, O.BNCfg(True), drop=False)
+        assert got[1:] == (0.0, 0.0, 0)
+        assert abs(got[0] - fix['losses'][it]) <= 2e-3 * fix['losses'][it], (it, got, fix['losses'][it])
+    assert torch.equal(sds[3]['DC_adnn3.weight'].detach(), dc_w0)
+    assert float(sds[3]['DC_adnn1.1.running_mean'].abs().sum()) > 0
+
+
 def _layout_to_state(node):
     """Inverse of make_golden.checkpoint_layout with zero tensors of the recorded dtype / shape."""
     if isinstance(node, dict) and '__tensor__' in node:
