@@ -65,6 +65,7 @@ class Act:
 
 
 POISON = bool(os.environ.get("S2R_POISON"))   # fill uninitialised activation buffers with NaN (tests/debug)
+KEEP_ALL = [] if os.environ.get("S2R_KEEP_ALL") else None   # debug: never free engine buffers (lifetime-race bisection)
 
 
 PEER = {"world": 0, "slot": 0}
@@ -120,6 +121,8 @@ def allreduce_small_f64(t, group=None):
 
 
 _SIDE_STREAMS = {}
+FORK_ONLY = [k for k in os.environ.get("S2R_FORK_ONLY", "").split(",") if k]   # debug: fork only these wgrad kinds
+FORK_JOIN = bool(os.environ.get("S2R_FORK_JOIN"))                             # debug: join right after every fork
 WGRAD_STREAM = os.environ.get("S2R_WGRAD_STREAM", "1") != "0"
 
 
@@ -142,6 +145,8 @@ class _Fork(object):
 
     def __exit__(self, *a):
         self._ctx.__exit__(*a)
+        if FORK_JOIN:
+            self.cx.join()
 
 
 class _NoFork(object):
@@ -189,9 +194,11 @@ class Ctx:
         # looked up per call: the current stream changes under torch.cuda.graph / torch.cuda.stream
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def fork(self, *keep):
+    def fork(self, *keep, kind=""):
         """`with cx.fork(tensors...):` -- launches inside go to the side stream (no-op without async_wgrad)."""
-        return _Fork(self, keep) if self.side is not None else _NoFork()
+        if self.side is None or (FORK_ONLY and kind not in FORK_ONLY):
+            return _NoFork()
+        return _Fork(self, keep)
 
     def join(self):
         if self.side is not None and self._forked:
@@ -208,12 +215,16 @@ class Ctx:
         t = f((N, H, W, Cc), dtype=BF16, device=self.device)
         if POISON and not zero:
             t.fill_(float('nan'))   # debug: an element that is read before it is written poisons the result
+        if KEEP_ALL is not None:
+            KEEP_ALL.append(t)
         return Act(t)
 
     def f32(self, n, zero=True):
         t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.device)
         if POISON and not zero:
             t.fill_(float('nan'))
+        if KEEP_ALL is not None:
+            KEEP_ALL.append(t)
         return t
 
     def f64(self, n):
@@ -224,6 +235,8 @@ class Ctx:
         if a is None or self._f64_used + n2 > a.numel():
             a = torch.zeros(max(65536, n2), dtype=torch.float64, device=self.device)
             self._f64_arena, self._f64_used = a, 0
+            if KEEP_ALL is not None:
+                KEEP_ALL.append(a)
         out = a[self._f64_used:self._f64_used + n]
         self._f64_used += n2
         return out
@@ -504,7 +517,7 @@ def conv_wgrad(cx, x, dy, w, stride=1, pad=0, dil=1, grad_param=None):
     a.Cin, a.Cout = Cin, Cout
     a.dy = dy.ptr
     a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
-    with cx.fork(x.t, dy.t):
+    with cx.fork(x.t, dy.t, kind="kxk" if R * S > 1 else "1x1"):
         if R * S > 1 and WGRAD_TAP_MAJOR:
             # tap-major fp32 scratch [R*S][Cout][Cp]: the kernel's atomics hit 32 consecutive input channels (one
             # 128-byte line) per instruction instead of 32 elements R*S floats apart; one small pass adds it into the
@@ -589,7 +602,7 @@ def rowtap_wgrad(cx, xp, dy, w):
     a.Cin, a.Cout = 4 * Cp, Cout
     a.dy = dy.ptr
     a.dn, a.dh, a.dw = dy.H * dy.W * dy.pitch, dy.W * dy.pitch, dy.pitch
-    with cx.fork(xp.t, dy.t):
+    with cx.fork(xp.t, dy.t, kind="rowtap"):
         G = cx.f32(Cout * 16 * Cp)
         a.dweight = G.data_ptr()
         a.s_co, a.s_ci = 16 * Cp, 1

