@@ -63,6 +63,29 @@ typedef struct {
   int64_t wofs;       /* wgrad: element offset of this tap inside the weight-gradient tensor */
 } s2r_tap;
 
+/* A PENDING BatchNorm: the per-channel statistics a producer kernel has accumulated (sums = [2][C] fp64: sum and sum
+ * of squares) together with everything needed to turn them into mean / inv-std, scale / shift and the running-statistics
+ * update of modeling/sync_batchnorm/batchnorm.py:113-125 (or of the F.batch_norm fallback at :50-53).  There is no
+ * finalize launch: the kernel that CONSUMES the normalised tensor (s2r_dwconv3x3_fwd_bn, s2r_bn_apply_act_bn) derives
+ * scale / shift from the sums in its prologue -- the kernel boundary after the producer is all the ordering it needs --
+ * and its first CTA publishes mean_invstd / scale_shift (for the backward pass) and updates the running statistics.
+ * channel >= 0: synchronised BatchNorm on several ranks (batchnorm.py:55-78,90-111): the sums must first be summed over
+ * the ranks on that exchange channel (see s2r_comm_*), which waits for the peers and therefore runs as one small kernel
+ * of its own: s2r_bn_tail_run (exchange + finalize in one launch), after which the BatchNorm is no longer pending. */
+typedef struct s2r_bn_tail {
+  double count;        /* elements per channel over all ranks */
+  const double* sums;  /* [2][C] */
+  const float* gamma;  /* [C] or NULL */
+  const float* beta;   /* [C] or NULL */
+  float* running_mean; /* [C] or NULL: updated with `momentum` */
+  float* running_var;
+  float* mean_invstd;  /* out [2][C] */
+  float* scale_shift;  /* out [2][C]: gamma*invstd, beta - mean*gamma*invstd */
+  float eps, momentum;
+  int32_t clamp_mode;  /* 0: (var+eps)^-1/2 (F.batch_norm); 1: max(var,eps)^-1/2 (batchnorm.py:125) */
+  int32_t channel;     /* -1: no cross-rank exchange */
+} s2r_bn_tail;
+
 #define S2R_AUX_NONE 0
 #define S2R_AUX_ADD 1        /* out = act(acc + bias) + aux */
 #define S2R_AUX_LEAKY_MASK 2 /* out = (acc + bias) * (aux > 0 ? 1 : slope) */
@@ -143,6 +166,11 @@ int s2r_pack_weights_multi(const s2r_pack_job* jobs, int njobs, s2r_stream_t str
 int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
                       const float* w, void* y, double* stats, int N, int H, int W, int C,
                       int stride, int dil, int pad, s2r_stream_t stream);
+/* The same with the input's BatchNorm still pending (in_bn: host pointer; NULL = s2r_dwconv3x3_fwd): scale / shift of
+ * the prologue are derived from in_bn->sums inside the kernel, which also publishes them (see s2r_bn_tail). */
+int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, const float* in_scale_shift, int in_act,
+                         int halo_const, const float* w, void* y, double* stats, int N, int H, int W, int C,
+                         int stride, int dil, int pad, s2r_stream_t stream);
 /* Data gradient w.r.t. the PRE-prologue tensor's BN output, masked by act':
  *   g = dgrad(dy) * act'(x*scale + shift), written on the domain extended by `ext` pixels on
  *   every side (ext = pad when halo_const, where x counts as 0; else 0):  g[N][H+2ext][W+2ext][C].
@@ -179,6 +207,9 @@ int s2r_bn_finalize(const double* sums, double count, const float* gamma, const 
                     float eps, int clamp_mode, float momentum, float* running_mean,
                     float* running_var, float* mean_invstd, float* scale_shift, int C,
                     s2r_stream_t stream);
+/* [exchange of tail->sums on tail->channel] + finalize as ONE launch of one CTA (what the consumers otherwise do in
+ * their prologue): for synchronised BatchNorm and for consumers without a fused prologue. */
+int s2r_bn_tail_run(const s2r_bn_tail* tail, int C, s2r_stream_t stream);
 int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* mean_invstd,
                             float* scale_shift, int C, s2r_stream_t stream);
@@ -189,6 +220,10 @@ int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
                      const float* scale_shift, int act, const void* residual, float drop_p,
                      uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch, int yoff,
                      s2r_stream_t stream);
+/* The same for a pending BatchNorm (bn: host pointer; NULL = s2r_bn_apply_act with scale_shift). */
+int s2r_bn_apply_act_bn(const void* x, int64_t P, int C, int xpitch, int xoff, const s2r_bn_tail* bn,
+                        const float* scale_shift, int act, const void* residual, float drop_p, uint64_t seed,
+                        const uint64_t* seed_dev, void* y, int ypitch, int yoff, s2r_stream_t stream);
 int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch, int xoff,
                       const float* mean_invstd, const float* scale_shift, int act, float drop_p,
                       uint64_t seed, const uint64_t* seed_dev, int64_t P, int C, double* dsums,

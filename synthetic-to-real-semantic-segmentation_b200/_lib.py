@@ -26,6 +26,12 @@ class Tap(C.Structure):
                 ("dh", i32), ("dw", i32), ("wslice", i32), ("_pad", i32), ("wofs", i64)]
 
 
+class BnTail(C.Structure):
+    _fields_ = [("count", f64), ("sums", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("mean_invstd", vp), ("scale_shift", vp), ("eps", f32), ("momentum", f32),
+                ("clamp_mode", i32), ("channel", i32)]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("ntaps", i32), ("taps", Tap * S2R_MAX_TAPS),
                 ("N", i32), ("OH", i32), ("OW", i32), ("Cin", i32), ("Cout", i32),
@@ -92,14 +98,17 @@ PROTOTYPES = {
     "s2r_softmax0_nchw_to_nhwc_pad": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_softmax0_nhwc_pad_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_dwconv3x3_fwd_bn": [vp, C.POINTER(BnTail), vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_im2col_nchw_f32": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_channel_sums_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "s2r_bn_finalize": [vp, f64, vp, vp, f32, i32, f32, vp, vp, vp, vp, i32, vp],
+    "s2r_bn_tail_run": [C.POINTER(BnTail), i32, vp],
     "s2r_bn_eval_scale_shift": [vp, vp, vp, vp, f32, vp, vp, i32, vp],
     "s2r_bn_apply_act": [vp, i64, i32, i32, i32, vp, i32, vp, f32, u64, vp, vp, i32, i32, vp],
+    "s2r_bn_apply_act_bn": [vp, i64, i32, i32, i32, C.POINTER(BnTail), vp, i32, vp, f32, u64, vp, vp, i32, i32, vp],
     "s2r_bn_bwd_reduce": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, i64, i32, vp, vp],
     "s2r_bn_bwd_apply": [vp, i32, i32, vp, i32, i32, vp, vp, i32, f32, u64, vp, vp, f64, i64, i32, vp,
                          i32, i32, vp, vp, i32, i32, i32, vp],

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "dw_common.cuh"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(256)
 bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int xpitch, int xoff,
                      const float* __restrict__ scale_shift, const __nv_bfloat16* __restrict__ residual,
                      __nv_bfloat16* __restrict__ y, int ypitch, int yoff, int rows, float drop_p,
-                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev, const BnTail bn) {
   pdl_wait();
   pdl_trigger();
   if (DROP && seed_dev) seed += *seed_dev;
@@ -407,8 +408,30 @@ bn_apply_lean_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, in
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
   const float k = ACT == S2R_ACT_RELU6 ? (1.f / 6.f) : 1.f;
   float2 sc[4], sh[4];
-  load_pairs(scale_shift + g * 8, k, sc);
-  load_pairs(scale_shift + C + g * 8, k, sh);
+  if (bn.enabled) {
+    // pending BatchNorm: scale / shift from the producer's sums (bn_tail.cuh), computed ONCE per CTA by the threads
+    // of row slot 0 and handed to the other row slots through shared memory; block 0 publishes them
+    extern __shared__ float s_fin[];   // [2][C], pre-multiplied by k
+    if (r == 0) {
+      float fsc[8], fsh[8];
+      const bool pub = blockIdx.x == 0;
+      bn_fin4(bn, C, g * 8, pub, fsc, fsh);
+      bn_fin4(bn, C, g * 8 + 4, pub, fsc + 4, fsh + 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s_fin[g * 8 + i] = fsc[i] * k;
+        s_fin[C + g * 8 + i] = fsh[i] * k;
+      }
+    }
+    __syncthreads();
+    const float4 a0 = *reinterpret_cast<const float4*>(s_fin + g * 8), a1 = *reinterpret_cast<const float4*>(s_fin + g * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s_fin + C + g * 8), b1 = *reinterpret_cast<const float4*>(s_fin + C + g * 8 + 4);
+    sc[0] = make_float2(a0.x, a0.y); sc[1] = make_float2(a0.z, a0.w); sc[2] = make_float2(a1.x, a1.y); sc[3] = make_float2(a1.z, a1.w);
+    sh[0] = make_float2(b0.x, b0.y); sh[1] = make_float2(b0.z, b0.w); sh[2] = make_float2(b1.x, b1.y); sh[3] = make_float2(b1.z, b1.w);
+  } else {
+    load_pairs(scale_shift + g * 8, k, sc);
+    load_pairs(scale_shift + C + g * 8, k, sh);
+  }
   const long long step = (long long)gridDim.x * rows;
   long long p0 = (long long)blockIdx.x * rows + r;
   const __nv_bfloat16* xp = x + p0 * xpitch + xoff + g * 8;
@@ -603,8 +626,8 @@ inline ElemCfg elem_cfg(long long P, int C) {
   c.rows = 256 / cg;
   if (c.rows < 1) c.rows = 1;
   c.threads = c.rows * cg;
-  long long blocks = (P + (long long)c.rows * 4 - 1) / ((long long)c.rows * 4);  // >= 4 rows per thread
-  const long long cap = (long long)s2r_sm_count() * 16;
+  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);  // >= 8 rows per thread (two full batches)
+  const long long cap = (long long)s2r_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   c.grid = (int)blocks;
@@ -653,26 +676,43 @@ extern "C" int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, co
   return S2R_OK;
 }
 
-extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
-                                const float* scale_shift, int act, const void* residual,
-                                float drop_p, uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch,
-                                int yoff, s2r_stream_t stream) {
+extern "C" int s2r_bn_apply_act_bn(const void* x, int64_t P, int C, int xpitch, int xoff, const s2r_bn_tail* pending,
+                                   const float* scale_shift, int act, const void* residual,
+                                   float drop_p, uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch,
+                                   int yoff, s2r_stream_t stream) {
+  if (pending) {
+    S2R_REQUIRE(pending->count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+    S2R_REQUIRE(pending->sums && pending->scale_shift && pending->mean_invstd && (uintptr_t)pending->sums % 16 == 0,
+                S2R_ERR_SHAPE, "bn_apply: pending BatchNorm without sums / outputs");
+    scale_shift = pending->scale_shift;
+  }
   S2R_REQUIRE(C >= 8 && C % 8 == 0 && C <= 2048, S2R_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8 in [8,2048]", C);
   S2R_REQUIRE(vec_ok(x, xpitch, xoff) && vec_ok(y, ypitch, yoff) && vec_ok(residual, 8, 0) &&
                   ((uintptr_t)scale_shift % 16 == 0),
               S2R_ERR_SHAPE, "bn_apply: bad pitch/offset/alignment");
   S2R_REQUIRE(drop_p >= 0.f && drop_p < 1.f, S2R_ERR_SHAPE, "bn_apply: dropout p=%f", drop_p);
+  const bool lean = getenv("S2R_BN_GENERIC") == nullptr && (drop_p == 0.f || (act == S2R_ACT_RELU && !residual)) &&
+                    (act == S2R_ACT_NONE || act == S2R_ACT_RELU || act == S2R_ACT_RELU6);
+  // pending BatchNorm: the lean kernels finalise it in their prologue; otherwise (cross-rank exchange, generic kernel,
+  // empty tensor) one small launch does
+  const bool fused = pending && lean && P > 0 && bn_tail_fusable(pending);
+  if (pending && !fused) {
+    const int rt = s2r_bn_tail_launch(pending, C, (cudaStream_t)stream);
+    if (rt) return rt;
+  }
+  const BnTail bt = bn_tail_from(fused ? pending : nullptr);
   if (P == 0) return S2R_OK;
   const ElemCfg cfg = elem_cfg(P, C);
-  if (getenv("S2R_BN_GENERIC") == nullptr && (drop_p == 0.f || (act == S2R_ACT_RELU && !residual))) {
+  if (lean) {
     const __nv_bfloat16 *xb = (const __nv_bfloat16*)x, *rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long* sd = (const unsigned long long*)seed_dev;
 #define S2R_APPLY(ACT_, RES_, DROP_)                                                                                     \
-  S2R_CUDA_OK(s2r_launch(bn_apply_lean_kernel<ACT_, RES_, DROP_>, dim3(cfg.grid), dim3(cfg.threads), 0, st, xb,          \
+  S2R_CUDA_OK(s2r_launch(bn_apply_lean_kernel<ACT_, RES_, DROP_>, dim3(cfg.grid), dim3(cfg.threads),                     \
+                         fused ? (size_t)2 * C * sizeof(float) : (size_t)0, st, xb,                                        \
                          (long long)P, C, xpitch, xoff, scale_shift, rb, yb, ypitch, yoff, cfg.rows, drop_p,               \
-                         (unsigned long long)seed, sd))
+                         (unsigned long long)seed, sd, bt))
     bool done = true;
     if (drop_p > 0.f) S2R_APPLY(S2R_ACT_RELU, false, true);
     else if (act == S2R_ACT_NONE) { if (residual) S2R_APPLY(S2R_ACT_NONE, true, false); else S2R_APPLY(S2R_ACT_NONE, false, false); }
@@ -691,6 +731,14 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
       yoff, cfg.rows));
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int xoff,
+                                const float* scale_shift, int act, const void* residual,
+                                float drop_p, uint64_t seed, const uint64_t* seed_dev, void* y, int ypitch,
+                                int yoff, s2r_stream_t stream) {
+  return s2r_bn_apply_act_bn(x, P, C, xpitch, xoff, nullptr, scale_shift, act, residual, drop_p, seed, seed_dev, y, ypitch,
+                             yoff, stream);
 }
 
 extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,

@@ -26,22 +26,11 @@
 // of its peers (exchanged by the host through torch.distributed -- plumbing, not the data path).
 #include <string.h>
 
-#include "common.cuh"
+#include "bn_tail.cuh"
 
 namespace {
 
-constexpr int CM_DEPTH = 4;
-constexpr int CM_CHANNELS = 2;   // independent exchange sequences (one per stream of the two-stream training step)
-constexpr int CM_MAX_WORLD = 16;
 constexpr int CM_THREADS = 1024;
-
-struct CommDev {
-  double* inbox[CM_MAX_WORLD];                 // base of every rank's inbox region (peer-mapped)
-  unsigned long long* flags[CM_MAX_WORLD];     // base of every rank's flag array [DEPTH][world]
-  unsigned long long* seq;                     // local: exchange counter
-  int* err;                                    // sticky error flag in MAPPED HOST memory (the host polls it without a sync)
-  int rank, world, slot;                       // slot: doubles per (depth, rank) entry
-};
 
 struct CommHost {
   bool ready = false;
@@ -51,22 +40,10 @@ struct CommHost {
   void* peers[CM_MAX_WORLD] = {nullptr};
   size_t inbox_bytes = 0, flags_bytes = 0;
   CommDev dev;
+  CommDev* dev_copy = nullptr;               // the descriptor in device memory (kernels that take a pointer)
 };
 
 CommHost g_comm;
-
-// Low-latency ("LL") wire format: every 8-byte word carries 32 payload bits and the 32-bit sequence number of
-// the exchange, so data and flag arrive in ONE atomic store -- no fence, no separate flag write, no second
-// NVLink round trip.  A double travels as two such words.  The reader polls each word until its sequence field
-// matches; a slot still holding the words of exchange seq - DEPTH can never match.
-__device__ __forceinline__ void st_word(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // WORLD > 0: the rank count is a compile-time constant, so the polls of all peers are issued together (their L2
 // latencies overlap) instead of one peer after the other; WORLD == 0: generic loop.
@@ -75,6 +52,8 @@ __global__ void __launch_bounds__(CM_THREADS)
 allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
   // channel ch has its own sequence counter and its own region of every inbox: two streams can run their exchange
   // sequences concurrently as long as every rank issues the same sequence PER CHANNEL
+  pdl_wait();      // programmatic dependent launch (common.cuh): resident early, global memory only from here on
+  pdl_trigger();
   unsigned long long* seqp = c.seq + ch;
   const unsigned long long seq = *seqp + 1;       // every thread reads it; thread 0 advances it at the end
   const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -88,8 +67,8 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
     for (int r = 0; r < c.world; ++r) {
       if (r == c.rank) continue;
       unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.inbox[r]) + ch_words + ((size_t)d * c.world + c.rank) * slot_words;
-      st_word(dst + 2 * i, w0);
-      st_word(dst + 2 * i + 1, w1);
+      cm_st_word(dst + 2 * i, w0);
+      cm_st_word(dst + 2 * i + 1, w1);
     }
   }
   // 2. + 3. poll every rank's words and sum in rank order (own value taken from buf)
@@ -105,8 +84,8 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
 #pragma unroll
       for (int r = 0; r < WORLD; ++r) {
         const unsigned long long* src = in + (size_t)r * slot_words + 2 * i;
-        w0[r] = ld_word(src);
-        w1[r] = ld_word(src + 1);
+        w0[r] = cm_ld_word(src);
+        w1[r] = cm_ld_word(src + 1);
       }
 #pragma unroll
       for (int r = 0; r < WORLD; ++r)
@@ -131,12 +110,12 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
         continue;
       }
       const unsigned long long* src = in + (size_t)r * slot_words + 2 * i;
-      unsigned long long w0 = ld_word(src), w1 = ld_word(src + 1);
+      unsigned long long w0 = cm_ld_word(src), w1 = cm_ld_word(src + 1);
       if (((w0 ^ tag) >> 32) != 0 || ((w1 ^ tag) >> 32) != 0) {
         const long long t0 = clock64();
         while (true) {
-          w0 = ld_word(src);
-          w1 = ld_word(src + 1);
+          w0 = cm_ld_word(src);
+          w1 = cm_ld_word(src + 1);
           if (((w0 ^ tag) >> 32) == 0 && ((w1 ^ tag) >> 32) == 0) break;
           if (timed_out || clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone; do not hang the GPU
             timed_out = true;
@@ -156,7 +135,45 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
   if (threadIdx.x == 0) *seqp = seq;
 }
 
+// [exchange] + finalize of one BatchNorm layer in ONE launch of one CTA (bn_tail.cuh): what used to be the exchange
+// kernel followed by bn_finalize.  Launched with programmatic dependent launch like every other kernel of the step.
+__global__ void __launch_bounds__(CM_THREADS)
+bn_tail_kernel(int C, BnTail t) {
+  pdl_wait();
+  pdl_trigger();
+  double* stats = const_cast<double*>(t.sums);
+  if (t.comm) cm_exchange_cta(*t.comm, t.channel, stats, 2 * C);
+  for (int c = threadIdx.x; c < C; c += CM_THREADS) {
+    float sc, sh;
+    bn_fin1(t, C, c, cm_ld_f64(stats + c), cm_ld_f64(stats + C + c), t.gamma ? t.gamma[c] : 1.f, t.beta ? t.beta[c] : 0.f,
+            true, sc, sh);
+  }
+}
+
 }  // namespace
+
+const CommDev* s2r_comm_dev_ptr() { return g_comm.ready ? g_comm.dev_copy : nullptr; }
+
+int s2r_bn_tail_launch(const s2r_bn_tail* t, int C, cudaStream_t stream) {
+  S2R_REQUIRE(t && t->sums && C >= 1, S2R_ERR_SHAPE, "bn_tail: null statistics / tail or C=%d", C);
+  // batchnorm.py:116 -- the statistics need more than one value per channel
+  S2R_REQUIRE(t->count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+  S2R_REQUIRE(t->mean_invstd && t->scale_shift, S2R_ERR_SHAPE, "bn_tail: null outputs");
+  BnTail b = bn_tail_from(t);
+  if (t->channel >= 0) {
+    const CommHost& h = g_comm;
+    S2R_REQUIRE(h.ready && h.world > 1, S2R_ERR_SHAPE, "bn_tail: exchange channel %d without an initialised peer exchange", t->channel);
+    S2R_REQUIRE(t->channel < CM_CHANNELS && 2 * C <= h.slot, S2R_ERR_SHAPE, "bn_tail: channel %d / %d doubles exceed the slot of %d", t->channel, 2 * C, h.slot);
+    b.comm = h.dev_copy;
+  }
+  S2R_CUDA_OK(s2r_launch(bn_tail_kernel, dim3(1), dim3(CM_THREADS), 0, stream, C, b));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_tail_run(const s2r_bn_tail* tail, int C, s2r_stream_t stream) {
+  return s2r_bn_tail_launch(tail, C, (cudaStream_t)stream);
+}
 
 /* Allocates this rank's inbox (slot_doubles per contribution) and writes its 64-byte CUDA IPC handle. */
 extern "C" int s2r_comm_create(int rank, int world, int slot_doubles, void* handle_out) {
@@ -200,6 +217,8 @@ extern "C" int s2r_comm_open(const void* handles) {
   h.dev.seq = (unsigned long long*)((char*)h.local + h.inbox_bytes + h.flags_bytes);
   S2R_CUDA_OK(cudaHostGetDevicePointer((void**)&h.dev.err, h.err_host, 0));
   h.dev.rank = h.rank; h.dev.world = h.world; h.dev.slot = h.slot;
+  S2R_CUDA_OK(cudaMalloc((void**)&h.dev_copy, sizeof(CommDev)));
+  S2R_CUDA_OK(cudaMemcpy(h.dev_copy, &h.dev, sizeof(CommDev), cudaMemcpyHostToDevice));
   h.ready = true;
   return S2R_OK;
 }
@@ -214,10 +233,11 @@ extern "C" int s2r_allreduce_small_f64_ch(double* buf, int n, int channel, s2r_s
   S2R_REQUIRE(buf && n >= 1 && n <= h.slot, S2R_ERR_SHAPE, "allreduce_small: n=%d exceeds the slot of %d doubles", n, h.slot);
   S2R_REQUIRE(channel >= 0 && channel < CM_CHANNELS, S2R_ERR_SHAPE, "allreduce_small: channel %d", channel);
   if (h.world == 1) return S2R_OK;
-  if (h.world == 2) allreduce_small_kernel<2><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
-  else if (h.world == 4) allreduce_small_kernel<4><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
-  else if (h.world == 8) allreduce_small_kernel<8><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
-  else allreduce_small_kernel<0><<<1, CM_THREADS, 0, (cudaStream_t)stream>>>(buf, n, h.dev, channel);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h.world == 2) S2R_CUDA_OK(s2r_launch(allreduce_small_kernel<2>, dim3(1), dim3(CM_THREADS), 0, st, buf, n, h.dev, channel));
+  else if (h.world == 4) S2R_CUDA_OK(s2r_launch(allreduce_small_kernel<4>, dim3(1), dim3(CM_THREADS), 0, st, buf, n, h.dev, channel));
+  else if (h.world == 8) S2R_CUDA_OK(s2r_launch(allreduce_small_kernel<8>, dim3(1), dim3(CM_THREADS), 0, st, buf, n, h.dev, channel));
+  else S2R_CUDA_OK(s2r_launch(allreduce_small_kernel<0>, dim3(1), dim3(CM_THREADS), 0, st, buf, n, h.dev, channel));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -242,6 +262,7 @@ extern "C" int s2r_comm_destroy() {
   for (int r = 0; r < h.world; ++r)
     if (r != h.rank && h.peers[r]) cudaIpcCloseMemHandle(h.peers[r]);
   cudaFree(h.local);
+  if (h.dev_copy) cudaFree(h.dev_copy);
   if (h.err_host) cudaFreeHost(h.err_host);
   h = CommHost();
   return S2R_OK;

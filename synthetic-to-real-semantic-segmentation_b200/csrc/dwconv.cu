@@ -21,7 +21,7 @@
 // registers per thread (its channel group is fixed) and leave the CTA as one fp64 atomic per channel.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "bn_tail.cuh"
 
 namespace {
 
@@ -365,13 +365,13 @@ inline int dw_smem_attr(K kernel, size_t smem) {
 }  // namespace
 
 // streaming stride-1 kernels (dwconv_s1.cu)
-int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, int dil, cudaStream_t stream);
+int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int halo_const, const float* w, void* y,
+                  double* stats, int N, int H, int W, int C, int dil, cudaStream_t stream);
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
                   int interior, void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream);
 
-int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, double* stats, int N, int H, int W, int C,
-                  cudaStream_t stream);
+int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, const float* w, void* y, double* stats,
+                  int N, int H, int W, int C, cudaStream_t stream);
 int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int interior,
                   void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
 
@@ -385,19 +385,40 @@ static bool s1_eligible(const float* ss, int in_act, int stride, int dil, int pa
          getenv("S2R_DW_GENERIC") == nullptr;
 }
 
-extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
-                                 const float* w, void* y, double* stats, int N, int H, int W, int C,
-                                 int stride, int dil, int pad, s2r_stream_t stream) {
+// in_bn: the input's BatchNorm is still pending (s2r_bn_tail): the streaming kernels derive scale / shift from its
+// sums in their prologue; with a cross-rank exchange, or on the generic kernel, it is finalised by one small launch first.
+extern "C" int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, const float* in_scale_shift, int in_act,
+                                    int halo_const, const float* w, void* y, double* stats, int N, int H, int W, int C,
+                                    int stride, int dil, int pad, s2r_stream_t stream) {
   DwGeom G;
   int rc = dw_check(x, y, N, H, W, C, stride, dil, pad, &G);
   if (rc) return rc;
-  if (s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && ((uintptr_t)in_scale_shift % 16 == 0)) {
-    rc = s2r_dw_s1_fwd(x, in_scale_shift, halo_const, w, y, stats, N, H, W, C, dil, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_bn) {
+    S2R_REQUIRE(in_bn->count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+    S2R_REQUIRE(in_bn->sums && in_bn->scale_shift && in_bn->mean_invstd && (uintptr_t)in_bn->sums % 16 == 0, S2R_ERR_SHAPE,
+                "dwconv3x3_fwd: pending BatchNorm without sums / outputs");
+    in_scale_shift = in_bn->scale_shift;
+  }
+  const bool vec = in_scale_shift && ((uintptr_t)in_scale_shift % 16 == 0);
+  const bool s1 = s1_eligible(in_scale_shift, in_act, stride, dil, pad, C) && vec;
+  const bool s2 = s2_eligible(in_scale_shift, in_act, halo_const, stride, dil, pad, C) && vec;
+  const s2r_bn_tail* fused = ((s1 || s2) && bn_tail_fusable(in_bn)) ? in_bn : nullptr;
+  if (in_bn && !fused) {
+    rc = s2r_bn_tail_launch(in_bn, C, st);
+    if (rc) return rc;
+  }
+  if (s1) {
+    rc = s2r_dw_s1_fwd(x, in_scale_shift, fused, halo_const, w, y, stats, N, H, W, C, dil, st);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
-  if (s2_eligible(in_scale_shift, in_act, halo_const, stride, dil, pad, C) && ((uintptr_t)in_scale_shift % 16 == 0)) {
-    rc = s2r_dw_s2_fwd(x, in_scale_shift, w, y, stats, N, H, W, C, (cudaStream_t)stream);
+  if (s2) {
+    rc = s2r_dw_s2_fwd(x, in_scale_shift, fused, w, y, stats, N, H, W, C, st);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
+  }
+  if (fused) {   // the streaming kernels declined the shape after all
+    rc = s2r_bn_tail_launch(in_bn, C, st);
+    if (rc) return rc;
   }
   const int cg = C / 8;
   const int tw = pick_tw(cg, G.Wo, 1);
@@ -407,16 +428,23 @@ extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int
   if (slide) {
     rc = dw_smem_attr(dw_fwd_kernel<true>, smem);
     if (rc) return rc;
-    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<true>, dim3(grid), dim3(tw * cg), (size_t)(smem), (cudaStream_t)stream, 
+    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<true>, dim3(grid), dim3(tw * cg), (size_t)(smem), st,
         (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw));
   } else {
     rc = dw_smem_attr(dw_fwd_kernel<false>, smem);
     if (rc) return rc;
-    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<false>, dim3(grid), dim3(tw * cg), (size_t)(smem), (cudaStream_t)stream, 
+    S2R_CUDA_OK(s2r_launch(dw_fwd_kernel<false>, dim3(grid), dim3(tw * cg), (size_t)(smem), st,
         (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw));
   }
   S2R_LAUNCH_OK();
   return S2R_OK;
+}
+
+extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
+                                 const float* w, void* y, double* stats, int N, int H, int W, int C,
+                                 int stride, int dil, int pad, s2r_stream_t stream) {
+  return s2r_dwconv3x3_fwd_bn(x, nullptr, in_scale_shift, in_act, halo_const, w, y, stats, N, H, W, C, stride, dil, pad,
+                              stream);
 }
 
 static int dw_dgrad_generic(const void* dy, const float* w, const void* x,

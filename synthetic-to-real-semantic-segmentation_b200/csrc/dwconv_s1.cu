@@ -20,6 +20,7 @@
 // thread = (column j, 4 consecutive channels); lane order is channel-fastest, so a warp stores
 // contiguous CG*8-byte pixel segments.
 #include "dw_common.cuh"
+#include "bn_tail.cuh"
 
 using namespace s2r_tma;
 using namespace s2r_dw;
@@ -46,6 +47,7 @@ struct S1Geom {
   // output (y / g) addressing in elements: the tensor may be a strided view (dilation = parity planes)
   long long os_pix, os_row, os_img;
   int interior;     // backward: g has the unextended layout, border positions are not stored
+  int publish;      // forward with a pending input BatchNorm: this launch publishes it (one launch of a dilated set)
 };
 
 // 8-byte shared-memory load at a 32-bit shared address plus a compile-time byte offset: the three neighbours of
@@ -63,7 +65,7 @@ __device__ __forceinline__ uint2 lds8(uint32_t addr) {
 template <bool HALO, int CG>
 __global__ void __launch_bounds__(FWD_CONS + 32, 2)
 dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G) {
+                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
@@ -117,10 +119,20 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     const int g = tid % CG, j = tid / CG;
     const int c = (blockIdx.x * CG + g) * 4;
 
-    float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+    float4 t4, u4;
+    if (in_bn.enabled) {
+      // the input's BatchNorm is still pending: scale / shift from the producer's sums; the first CTA of every
+      // channel chunk publishes them (and mean / inv-std, running statistics) for the backward pass
+      float fsc[4], fsh[4];
+      bn_fin4(in_bn, G.C, c, blockIdx.y == 0 && G.publish && live && j == 0, fsc, fsh);
+      t4 = make_float4(fsc[0], fsc[1], fsc[2], fsc[3]);
+      u4 = make_float4(fsh[0], fsh[1], fsh[2], fsh[3]);
+    } else {
+      t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+      u4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
+    }
     const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-    t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
-    const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
     float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
     load_filter(w, c, 6.f, wA, wB);
 
@@ -431,6 +443,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
   if (per_chunk > nunits) per_chunk = (int)nunits;
   G->tiles = tiles; G->nunits = (int)nunits;
   G->N = N; G->H = H; G->W = W; G->C = C; G->CG = CG; G->TW = TW; G->rs = rs; G->nseg = nseg; G->ext = ext;
+  G->publish = 0;
   const int dy_bytes = RB * (TW + 2) * CG * 8, x_bytes = bwd ? RB * TW * CG * 8 : 0;
   G->xoff = (dy_bytes + 127) / 128 * 128;
   G->stage_bytes = (G->xoff + x_bytes + 127) / 128 * 128;
@@ -461,8 +474,12 @@ inline int s1_smem_attr(K kernel, size_t smem, int which) {
 // Internal entry points (called from dwconv.cu); return S2R_ERR_UNSUPPORTED when the shape is not covered.
 // Dilation d (padding d) is d*d independent dilation-1 problems on the parity planes of the tensor: plane (p, q)
 // holds the pixels (d*i + p, d*j + q) and is addressed through a TMA map with d-fold strides.
-int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, int dil, cudaStream_t stream) {
+int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int halo_const, const float* w, void* y,
+                  double* stats, int N, int H, int W, int C, int dil, cudaStream_t stream) {
+  // in_bn: the input's BatchNorm is pending -- every launch derives scale / shift from its sums, the first one of a
+  // dilated set (dil*dil parity-plane launches) publishes them and updates the running statistics
+  const BnTail bt = bn_tail_from(in_bn);
+  bool published = false;
   for (int p = 0; p < dil; ++p)
     for (int q = 0; q < dil; ++q) {
       const int Hp = (H - p + dil - 1) / dil, Wp = (W - q + dil - 1) / dil;
@@ -475,6 +492,8 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
       const long long poff = ((long long)p * W + q) * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
       G.interior = 0;
+      G.publish = published ? 0 : 1;
+      published = true;
       CUtensorMap xmap;
       if (!encode_nhwc_view(&xmap, (const __nv_bfloat16*)x + poff, N, Hp, Wp, C, G.os_pix, G.os_row, G.os_img,
                             G.CG * 4, G.TW + 2, RB))
@@ -484,7 +503,7 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, int halo_const, const float* w
   do {                                                                                      \
     int rc = s1_smem_attr(dw_s1_fwd_kernel<HALO_, CG_>, smem, SLOT_);                       \
     if (rc) return rc;                                                                      \
-    S2R_CUDA_OK(s2r_launch(dw_s1_fwd_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G)); \
+    S2R_CUDA_OK(s2r_launch(dw_s1_fwd_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt)); \
   } while (0)
       if (halo_const) {
         if (G.CG == 8) S2R_DW_FWD(true, 8, 0);

@@ -11,6 +11,7 @@
 // Backward (fused data + weight gradient): a thread owns one dy position (i, j) and the four input positions
 // (2i+p, 2j+q); it needs dy(i..i+1, j..j+1) -- dy row i is carried in registers.
 #include "dw_common.cuh"
+#include "bn_tail.cuh"
 
 using namespace s2r_tma;
 using namespace s2r_dw;
@@ -37,7 +38,7 @@ struct S2Maps {
 // ------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(F_CONS + 32, 2)
 dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S2Geom G) {
+                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S2Geom G, const BnTail in_bn) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[F_STAGES], bar_empty[F_STAGES];
@@ -87,10 +88,20 @@ dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
     const int ow = j0 + j;
     const bool active = live && ow < G.Wo;
 
-    float4 t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+    float4 t4, u4;
+    if (in_bn.enabled) {
+      // pending input BatchNorm: scale / shift from the producer's sums; the first CTA of every channel chunk
+      // publishes them (bn_tail.cuh)
+      float fsc[4], fsh[4];
+      bn_fin4(in_bn, G.C, c, blockIdx.y == 0 && blockIdx.z == 0 && live && j == 0, fsc, fsh);
+      t4 = make_float4(fsc[0], fsc[1], fsc[2], fsc[3]);
+      u4 = make_float4(fsh[0], fsh[1], fsh[2], fsh[3]);
+    } else {
+      t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+      u4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
+    }
     const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
-    t4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
-    const float2 shA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), shB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
     float2 wA[9], wB[9];
     load_filter(w, c, 6.f, wA, wB);
 
@@ -400,8 +411,8 @@ inline void s2_offsets(S2Geom* G, const int bw[5], int ntiles) {
 
 }  // namespace
 
-int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, double* stats, int N, int H, int W, int C,
-                  cudaStream_t stream) {
+int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, const float* w, void* y, double* stats,
+                  int N, int H, int W, int C, cudaStream_t stream) {
   S2Geom G;
   G.N = N; G.H = H; G.W = W; G.C = C;
   G.Ho = (H - 1) / 2 + 1; G.Wo = (W - 1) / 2 + 1;
@@ -432,7 +443,8 @@ int s2r_dw_s2_fwd(const void* x, const float* ss, const float* w, void* y, doubl
   }
   int threads = (TW * G.CG + 31) / 32 * 32 + 32;
   if (threads < (G.CG * 12 + 31) / 32 * 32) threads = (G.CG * 12 + 31) / 32 * 32;
-  S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w, (__nv_bfloat16*)y, stats, G));
+  S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w, (__nv_bfloat16*)y, stats, G,
+                         bn_tail_from(in_bn)));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -649,11 +649,27 @@ def bias_grad(cx, dy, b):
 
 # --------------------------------------------------------------------------- batch norm
 class BNState:
-    """Per-forward BN results: scale/shift and mean/invstd ([2][C] fp32 each) + element count."""
-    __slots__ = ("ss", "mi", "count", "frozen")
+    """Per-forward BN results: scale/shift and mean/invstd ([2][C] fp32 each) + element count.
+    pending: the s2r_bn_tail of a training-mode BatchNorm whose sums have been produced but not yet turned into
+    ss / mi -- the first kernel that consumes the normalised tensor (depthwise prologue, bn_apply) does that in its
+    own prologue and publishes ss / mi (csrc/bn_tail.cuh); take() hands the descriptor to that launch, ready() forces
+    it with one small launch for any other consumer."""
+    __slots__ = ("ss", "mi", "count", "frozen", "pending", "C", "keep")
 
-    def __init__(self, ss, mi, count, frozen):
-        self.ss, self.mi, self.count, self.frozen = ss, mi, count, frozen
+    def __init__(self, ss, mi, count, frozen, pending=None, C=0, keep=None):
+        self.ss, self.mi, self.count, self.frozen, self.pending, self.C = ss, mi, count, frozen, pending, C
+        self.keep = keep   # the fp64 sums the pending descriptor points at (raw pointer): alive as long as the state
+
+    def take(self):
+        """The pending descriptor (or None), for a launch that finalises it; afterwards ss / mi are valid in stream order."""
+        p, self.pending = self.pending, None
+        return p
+
+    def ready(self, cx):
+        p = self.take()
+        if p is not None:
+            L.call("s2r_bn_tail_run", C.byref(p), self.C, cx.stream)
+        return self
 
 
 def bn_finalize(cx, bn, sums, count_local):
@@ -684,14 +700,50 @@ def bn_eval(cx, bn):
     return BNState(ss, mi, 0.0, True)
 
 
-def bn_state(cx, bn, sums, count_local):
-    if cx.training and bn.training:
-        return bn_finalize(cx, bn, sums, count_local)
-    return bn_eval(cx, bn)
+def bn_plan(cx, bn, count_local):
+    """(sums, finish) for the BatchNorm `bn` that normalises the output of the next statistics-producing launch:
+    hand `sums` (fp64 [2][C], None in eval mode) to the producer, then call finish() -> BNState.
+    Training mode on one rank: the state is PENDING (no finalize launch; BNState).  Synchronised across ranks: the sums
+    are exchanged and finalised by one small launch (csrc/comm.cu), or all-reduced over NCCL (S2R_COMM=nccl) first.
+    Mirrors _SynchronizedBatchNorm._compute_mean_std (batchnorm.py:113-125) when synchronised across ranks and
+    F.batch_norm (batchnorm.py:50-53) otherwise."""
+    if not (cx.training and bn.training):
+        st = bn_eval(cx, bn)
+        return None, (lambda: st)
+    Cc = bn.num_features
+    sync = cx.world > 1 and getattr(bn, "_s2r_sync", False)
+    count = float(count_local) * (cx.world if sync else 1)
+    if count <= 1:
+        raise ValueError("BatchNorm computes unbiased standard-deviation, which requires size > 1.")
+    sums = cx.f64(2 * Cc)
+    ss = cx.f32(2 * Cc, zero=False)
+    mi = cx.f32(2 * Cc, zero=False)
+    t = L.BnTail()
+    t.count = count
+    t.sums = sums.data_ptr()
+    t.gamma, t.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+    t.running_mean, t.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+    t.mean_invstd, t.scale_shift = mi.data_ptr(), ss.data_ptr()
+    t.eps = float(bn.eps)
+    t.momentum = float(bn.momentum if bn.momentum is not None else 0.1)
+    t.clamp_mode = 1 if sync else 0
+    t.channel = -1
+    st = BNState(ss, mi, count, False, pending=t, C=Cc, keep=sums)
+
+    def finish():
+        if sync:
+            if PEER["world"] == cx.world:
+                t.channel = COMM_CHANNEL[0]   # exchange over NVLink peer memory + finalize: one small launch
+            else:
+                cx.allreduce(sums)            # NCCL
+            st.ready(cx)
+        return st
+    return sums, finish
 
 
 def bn_apply(cx, z, st, act, out, residual=None, drop_p=0.0, seed=0):
-    L.call("s2r_bn_apply_act", z.vp(), z.P, z.C, z.pitch, 0, _vp(st.ss), act,
+    p = st.take()
+    L.call("s2r_bn_apply_act_bn", z.vp(), z.P, z.C, z.pitch, 0, C.byref(p) if p is not None else None, _vp(st.ss), act,
            residual.vp() if residual is not None else None, float(drop_p), seed, _vp(cx.seed_dev), out.vp(),
            out.pitch, 0,
            cx.stream)
@@ -702,6 +754,7 @@ def bn_backward(cx, bn, dy, z, st, act, dx, drop_p=0.0, seed=0, presummed=None, 
     """dz of a training-mode BN (+act, +dropout) given dy; accumulates gamma/beta grads.
     presummed: fp64 [2][C] sums already produced by the kernel that wrote dy (dw dgrad)."""
     Cc = z.C
+    st.ready(cx)
     if presummed is None:
         sums = cx.f64(2 * Cc)
         L.call("s2r_bn_bwd_reduce", dy.vp(), dy.pitch, 0, z.vp(), z.pitch, 0, _vp(st.mi), _vp(st.ss), act,
@@ -745,14 +798,12 @@ class ConvBNAct:
         Cout = w.shape[0]
         OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
         z = cx.new(x.N, OH, OW, Cout)
-        train = cx.training and self.bn.training
-        sums = cx.f64(2 * Cout) if train else None
-        conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
-        _probe(self.bn, z)
         # count_pad: the reference ran this conv on an input padded by count_pad pixels per side
         # (mobilenet.py:62-67): the extra border outputs are exact zeros but count in the statistics
-        count = x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad)
-        st = bn_state(cx, self.bn, sums, count)
+        sums, finish = bn_plan(cx, self.bn, x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad))
+        conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
+        _probe(self.bn, z)
+        st = finish()
         p = self.drop_p if (cx.training and cx.dropout) else 0.0
         seed = cx.next_seed() if p > 0 else 0
         y = out if out is not None else cx.new(x.N, OH, OW, Cout)
@@ -767,19 +818,19 @@ class ConvBNAct:
         Cout = w.shape[0]
         OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
         z = cx.new(x.N, OH, OW, Cout)
-        train = cx.training and self.bn.training
-        sums = cx.f64(2 * Cout) if train else None
         if isinstance(x, RawNCHW):
             assert self.dil == 1
             x = im2col(cx, x, w.shape[2], w.shape[3], self.stride, self.pad)
+            sums, finish = bn_plan(cx, self.bn, x.N * OH * OW)
             conv_fwd(cx, x, patch_weight(w), z, stats=sums)
-            st = bn_state(cx, self.bn, sums, x.N * OH * OW)
+            st = finish()
             self.saved = (x, z, st, 0.0, 0)
             self.patch = True
             return z, st
         self.patch = False
+        sums, finish = bn_plan(cx, self.bn, x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad))
         conv_fwd(cx, x, w, z, self.stride, self.pad, self.dil, stats=sums)
-        st = bn_state(cx, self.bn, sums, x.N * (OH + 2 * count_pad) * (OW + 2 * count_pad))
+        st = finish()
         self.saved = (x, z, st, 0.0, 0)
         return z, st
 
@@ -812,11 +863,13 @@ class ConvBNAct:
 
 
 def dw_fwd(cx, x, st_in, in_act, halo_const, w, stride, dil, pad, stats):
+    """Depthwise 3x3 on act(BN(x)); st_in may still be pending: the kernel then finalises it in its prologue."""
     Ho, Wo = conv_out_hw(x.H, x.W, 3, 3, stride, pad, dil)
     y = cx.new(x.N, Ho, Wo, x.C)
-    L.call("s2r_dwconv3x3_fwd", x.vp(), _vp(st_in.ss) if st_in is not None else None, in_act,
-           1 if halo_const else 0, _vp(w), y.vp(), _vp(stats) if stats is not None else None, x.N, x.H, x.W,
-           x.C, stride, dil, pad, cx.stream)
+    p = st_in.take() if st_in is not None else None
+    L.call("s2r_dwconv3x3_fwd_bn", x.vp(), C.byref(p) if p is not None else None,
+           _vp(st_in.ss) if st_in is not None else None, in_act, 1 if halo_const else 0, _vp(w), y.vp(),
+           _vp(stats) if stats is not None else None, x.N, x.H, x.W, x.C, stride, dil, pad, cx.stream)
     return y
 
 
@@ -850,11 +903,11 @@ class InvertedResidual:
             dw_in, st_in, halo = z1, st1, True
         else:
             dw_in, st_in, halo = x, lazy, False
-        train = cx.training and self.bn2.training
-        sums2 = cx.f64(2 * dw_in.C) if train else None
+        Ho, Wo = conv_out_hw(dw_in.H, dw_in.W, 3, 3, self.stride, d, d)
+        sums2, finish2 = bn_plan(cx, self.bn2, dw_in.N * Ho * Wo)
         z2 = dw_fwd(cx, dw_in, st_in, L.ACT_RELU6, halo, self.dw.weight, self.stride, d, d, sums2)
         _probe(self.bn2, z2)
-        st2 = bn_state(cx, self.bn2, sums2, z2.P)
+        st2 = finish2()
         y2 = cx.new(z2.N, z2.H, z2.W, z2.C)
         bn_apply(cx, z2, st2, L.ACT_RELU6, y2)
         out = self.pw2.forward(cx, y2, residual=x if self.res else None)

@@ -34,14 +34,14 @@ def test_struct_layout_matches_c(built_lib, tmp_path):
     """sizeof() of the ctypes mirrors == sizeof() in C (compiled from the header with gcc)."""
     L = sub("_lib")
     c = tmp_path / "sz.c"
-    c.write_text('#include <stdio.h>\n#include "s2r_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(s2r_tap),'
-                 ' sizeof(s2r_conv_args), sizeof(s2r_wgrad_args), sizeof(s2r_param_slot));return 0;}\n')
+    c.write_text('#include <stdio.h>\n#include "s2r_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(s2r_tap),'
+                 ' sizeof(s2r_conv_args), sizeof(s2r_wgrad_args), sizeof(s2r_param_slot), sizeof(s2r_bn_tail));return 0;}\n')
     exe = tmp_path / "sz"
     import subprocess
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [ctypes.sizeof(L.Tap), ctypes.sizeof(L.ConvArgs), ctypes.sizeof(L.WgradArgs),
-                     ctypes.sizeof(L.ParamSlot)]
+                     ctypes.sizeof(L.ParamSlot), ctypes.sizeof(L.BnTail)]
 
 
 def test_struct_size_is_checked(built_lib):

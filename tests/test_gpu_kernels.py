@@ -282,6 +282,64 @@ def test_batchnorm_forward_backward(eng, cx, Cc, P, clamp):
     assert rel(to_nchw(out), ref(x).detach()) < 4e-3
 
 
+@pytest.mark.parametrize("kind,Cc,H,W", [("apply", 64, 32, 64), ("apply_res", 24, 33, 17), ("apply_relu", 256, 9, 13),
+                                          ("dw1", 96, 40, 56), ("dw2", 144, 34, 30), ("dwd2", 64, 18, 22), ("dwgen", 40, 12, 20)])
+def test_pending_batchnorm_finalised_by_its_consumer(eng, cx, kind, Cc, H, W):
+    """A pending BatchNorm (sums left by the producer, no finalize launch) finalised in the prologue of the kernel that
+    consumes the normalised tensor -- bn_apply / the streaming depthwise kernels, csrc/bn_tail.cuh -- against the
+    separate bn_finalize launch on the same sums: same output, same published scale / shift / mean / inv-std, same
+    running statistics (batchnorm.py:113-125 / F.batch_norm)."""
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(Cc + H)
+    N = 3
+    bn_a, bn_b = torch.nn.BatchNorm2d(Cc).cuda(), torch.nn.BatchNorm2d(Cc).cuda()
+    bn_a.weight.data = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    bn_a.bias.data = torch.randn(Cc, device="cuda", generator=g)
+    bn_a.running_mean.data = torch.randn(Cc, device="cuda", generator=g)
+    bn_b.load_state_dict(bn_a.state_dict())
+    bn_a.train(); bn_b.train()
+    x = nhwc_act(eng, bf(torch.randn(N, Cc, H, W, device="cuda", generator=g) * 1.3 + 0.4))
+    res = nhwc_act(eng, bf(torch.randn(N, Cc, H, W, device="cuda", generator=g)))
+    w = torch.randn(Cc, 1, 3, 3, device="cuda", generator=g) * 0.3
+
+    def consume(st):
+        if kind.startswith("apply"):
+            out = cx.new(N, H, W, Cc)
+            act = L.ACT_RELU if kind == "apply_relu" else L.ACT_RELU6 if kind == "apply" else L.ACT_NONE
+            eng.bn_apply(cx, x, st, act, out, residual=res if kind == "apply_res" else None)
+            return out
+        stride, dil = (2, 1) if kind == "dw2" else (1, 2) if kind == "dwd2" else (1, 1)
+        return eng.dw_fwd(cx, x, st, L.ACT_RELU6, True, w, stride, dil, dil, None)
+
+    # A: pending, finalised by the consumer
+    sums_a, finish = eng.bn_plan(cx, bn_a, x.P)
+    L.call("s2r_channel_sums_bf16", x.vp(), x.P, Cc, x.pitch, 0, C.c_void_p(sums_a.data_ptr()), cx.stream)
+    st_a = finish()
+    assert st_a.pending is not None
+    out_a = consume(st_a)
+    assert st_a.pending is None
+    # B: the separate launch
+    sums_b = cx.f64(2 * Cc)
+    L.call("s2r_channel_sums_bf16", x.vp(), x.P, Cc, x.pitch, 0, C.c_void_p(sums_b.data_ptr()), cx.stream)
+    st_b = eng.bn_finalize(cx, bn_b, sums_b, x.P)
+    out_b = consume(st_b)
+    torch.cuda.synchronize()
+    for a, b in ((st_a.ss, st_b.ss), (st_a.mi, st_b.mi), (bn_a.running_mean, bn_b.running_mean), (bn_a.running_var, bn_b.running_var)):
+        assert rel(a, b) < 2e-6, (kind, rel(a, b))
+    assert rel(out_a.t, out_b.t) < 1e-3
+    assert st_a.count == st_b.count
+    # a second consumer of the same state reads the published scale / shift
+    out_c = consume(st_a)
+    torch.cuda.synchronize()
+    assert torch.equal(out_c.t, out_a.t)
+    # any other consumer forces the finalisation with one small launch
+    sums_d, finish_d = eng.bn_plan(cx, bn_a, x.P)
+    L.call("s2r_channel_sums_bf16", x.vp(), x.P, Cc, x.pitch, 0, C.c_void_p(sums_d.data_ptr()), cx.stream)
+    st_d = finish_d().ready(cx)
+    torch.cuda.synchronize()
+    assert st_d.pending is None and rel(st_d.ss, st_a.ss) < 2e-6
+
+
 def test_bn_dropout_is_regenerated_in_backward(eng, cx):
     L = sub("_lib")
     Cc, P = 64, 4096
