@@ -29,7 +29,8 @@ namespace {
 
 constexpr int RB = 3;            // rows per TMA stage (= accumulator rotation period)
 constexpr int FWD_CONS = 256;    // forward: consumer threads (+ one producer warp)
-constexpr int FWD_STAGES = 4;
+constexpr int FWD_STAGES = 8;
+constexpr int FWD2_CONS = 224;   // two-column forward: 7 consumer warps + the producer = 256 threads -> 128 registers at 2 CTAs / SM
 constexpr int BWD_CONS = 352;    // backward: consumer threads (+ one producer warp)
 constexpr int BWD_STAGES = 4;
 
@@ -205,6 +206,166 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
       const float* p = red + k * (FWD_CONS + 1) + gg;
       float tot = 0.f;
       for (int jj = 0; jj < G.TW; ++jj) tot += p[jj * CG];
+      atomicAdd(&stats[(k >> 2) * G.C + (blockIdx.x * CG + gg) * 4 + (k & 3)], (double)tot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ forward, two columns per thread
+// The same computation with thread = (column pair 2j, 2j+1; 4 channels).  The activation a = relu6(x*sc+sh) is what the
+// one-column kernel spends most of its non-FMA issue slots on -- every element is unpacked and activated three times, as
+// the left, centre and right neighbour of three threads (3 x 8 of ~58 instructions per output vector).  A column pair
+// needs four activated vectors for two outputs (2 x 8 per output), one shared-memory load per output less, and the row
+// loop's fixed cost (barrier wait, pointer updates) is spread over twice the work: ~43 instead of ~58 instructions per
+// output vector, with twelve independent accumulator chains per thread instead of six.
+template <bool HALO, int CG>
+__global__ void __launch_bounds__(FWD2_CONS + 32, 2)
+dw_s1_fwd2_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
+                  __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+  __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
+  __shared__ float red[8 * (FWD2_CONS + 1)];
+  const int TWL = G.TW + 2;
+  const int npair = G.TW >> 1;                       // G.TW is even
+  const int ncons = npair * CG;                      // active consumer threads
+  const int ncw = (ncons + 31) / 32;                 // consumer warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FWD_STAGES; ++s) {
+      mbar_init(smem_addr(&bar_full[s]), 1);
+      mbar_init(smem_addr(&bar_empty[s]), ncw);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == ncw) {
+    // ---------------- producer warp
+    if (lane == 0) {
+      prefetch_tmap(&xmap);
+      int it = 0;
+      for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+        S1_UNIT(unit)
+        for (int k = 0; k < nst; ++k, ++it) {
+          const int s = it % FWD_STAGES;
+          if (it >= FWD_STAGES) mbar_wait(smem_addr(&bar_empty[s]), ((it / FWD_STAGES) - 1) & 1);
+          const uint32_t full = smem_addr(&bar_full[s]);
+          mbar_expect_tx(full, (uint32_t)(RB * TWL * CG * 8));
+          tma_load_4d(smem_addr(smem + (size_t)s * G.stage_bytes), &xmap, full, blockIdx.x * CG * 4, ow0 - 1,
+                      oh0 - 1 + k * RB, n);
+        }
+      }
+    }
+  } else if (warp < ncw) {
+    // ---------------- consumers
+    const bool live = threadIdx.x < ncons;
+    const int tid = live ? threadIdx.x : 0;
+    const int g = tid % CG, j = tid / CG;
+    const int c = (blockIdx.x * CG + g) * 4;
+
+    float4 t4, u4;
+    if (in_bn.enabled) {
+      float fsc[4], fsh[4];
+      bn_fin4(in_bn, G.C, c, blockIdx.y == 0 && G.publish && live && j == 0, fsc, fsh);
+      t4 = make_float4(fsc[0], fsc[1], fsc[2], fsc[3]);
+      u4 = make_float4(fsh[0], fsh[1], fsh[2], fsh[3]);
+    } else {
+      t4 = __ldg(reinterpret_cast<const float4*>(ss + c));
+      u4 = __ldg(reinterpret_cast<const float4*>(ss + G.C + c));
+    }
+    const float2 scA = make_float2(t4.x * (1.f / 6.f), t4.y * (1.f / 6.f)), scB = make_float2(t4.z * (1.f / 6.f), t4.w * (1.f / 6.f));
+    const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
+    float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
+    load_filter(w, c, 6.f, wA, wB);
+
+    const long long rowp = G.os_row;
+    const uint32_t tile0 = smem_addr(smem) + (uint32_t)(2 * j * CG + g) * 8u;   // left neighbour of column 2j, row 0, stage 0
+    const uint32_t rowstride = (uint32_t)(TWL * CG) * 8u;
+    float2 sA = make_float2(0.f, 0.f), sB = sA, qA = sA, qB = sA;
+    int it = 0;
+    for (int unit = blockIdx.y; unit < G.nunits; unit += gridDim.y) {
+    S1_UNIT(unit)
+    const int ow = ow0 + 2 * j;
+    const bool act0 = live && ow < G.W, act1 = live && ow + 1 < G.W;
+    // running output pointers: row o = r - 2 of step r
+    __nv_bfloat16* yrow0 = y + (long long)n * G.os_img + (long long)(oh0 - 2) * G.os_row + (long long)min(ow, G.W - 1) * G.os_pix + c;
+    __nv_bfloat16* yrow1 = y + (long long)n * G.os_img + (long long)(oh0 - 2) * G.os_row + (long long)min(ow + 1, G.W - 1) * G.os_pix + c;
+    // !HALO: zero (not relu6(shift)) outside the image
+    const bool ok0 = ow - 1 >= 0 && ow - 1 < G.W, ok1 = ow < G.W, ok2 = ow + 1 < G.W, ok3 = ow + 2 < G.W;
+    float2 accA[2][3], accB[2][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) accA[0][i] = accB[0][i] = accA[1][i] = accB[1][i] = make_float2(0.f, 0.f);
+
+    for (int k = 0; k < nst; ++k, ++it) {
+      const int s = it % FWD_STAGES;
+      mbar_wait(smem_addr(&bar_full[s]), (it / FWD_STAGES) & 1);
+      const uint32_t tile = tile0 + (uint32_t)s * (uint32_t)G.stage_bytes;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int r = k * RB + u;            // input row oh0 - 1 + r
+        const uint32_t rowt = tile + (uint32_t)u * rowstride;
+        float2 aA[4], aB[4];                 // activated columns 2j-1 .. 2j+2
+        act4(lds8<0>(rowt), scA, scB, shA, shB, aA[0], aB[0]);
+        act4(lds8<CG * 8>(rowt), scA, scB, shA, shB, aA[1], aB[1]);
+        act4(lds8<CG * 16>(rowt), scA, scB, shA, shB, aA[2], aB[2]);
+        act4(lds8<CG * 24>(rowt), scA, scB, shA, shB, aA[3], aB[3]);
+        if (!HALO) {
+          const bool row_ok = (unsigned)(oh0 - 1 + r) < (unsigned)G.H;
+          if (!(row_ok && ok0)) aA[0] = aB[0] = make_float2(0.f, 0.f);
+          if (!(row_ok && ok1)) aA[1] = aB[1] = make_float2(0.f, 0.f);
+          if (!(row_ok && ok2)) aA[2] = aB[2] = make_float2(0.f, 0.f);
+          if (!(row_ok && ok3)) aA[3] = aB[3] = make_float2(0.f, 0.f);
+        }
+        // output row o = r - ky gets ky's filter row; slot of o is o % 3 (u == r % 3)
+        const int s0 = u, s1 = (u + 2) % 3, s2 = (u + 1) % 3;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          accA[q][s0] = ffma2(aA[q + 2], wA[2], ffma2(aA[q + 1], wA[1], fmul2(aA[q], wA[0])));
+          accB[q][s0] = ffma2(aB[q + 2], wB[2], ffma2(aB[q + 1], wB[1], fmul2(aB[q], wB[0])));
+          accA[q][s1] = ffma2(aA[q + 2], wA[5], ffma2(aA[q + 1], wA[4], ffma2(aA[q], wA[3], accA[q][s1])));
+          accB[q][s1] = ffma2(aB[q + 2], wB[5], ffma2(aB[q + 1], wB[4], ffma2(aB[q], wB[3], accB[q][s1])));
+          accA[q][s2] = ffma2(aA[q + 2], wA[8], ffma2(aA[q + 1], wA[7], ffma2(aA[q], wA[6], accA[q][s2])));
+          accB[q][s2] = ffma2(aB[q + 2], wB[8], ffma2(aB[q + 1], wB[7], ffma2(aB[q], wB[6], accB[q][s2])));
+        }
+        if ((unsigned)(r - 2) < (unsigned)rows && act0) {
+          *reinterpret_cast<uint2*>(yrow0) = pack4(accA[0][s2], accB[0][s2]);
+          sA = fadd2(sA, accA[0][s2]);
+          sB = fadd2(sB, accB[0][s2]);
+          qA = ffma2(accA[0][s2], accA[0][s2], qA);
+          qB = ffma2(accB[0][s2], accB[0][s2], qB);
+          if (act1) {
+            *reinterpret_cast<uint2*>(yrow1) = pack4(accA[1][s2], accB[1][s2]);
+            sA = fadd2(sA, accA[1][s2]);
+            sB = fadd2(sB, accB[1][s2]);
+            qA = ffma2(accA[1][s2], accA[1][s2], qA);
+            qB = ffma2(accB[1][s2], accB[1][s2], qB);
+          }
+        }
+        yrow0 += rowp;
+        yrow1 += rowp;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&bar_empty[s]));
+    }
+    }   // units
+    if (stats) {
+      const float v[8] = {sA.x, sA.y, sB.x, sB.y, qA.x, qA.y, qB.x, qB.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[k * (FWD2_CONS + 1) + threadIdx.x] = live ? v[k] : 0.f;
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < CG * 8) {
+      const int gg = t / 8, k = t % 8;
+      const float* p = red + k * (FWD2_CONS + 1) + gg;
+      float tot = 0.f;
+      for (int jj = 0; jj < npair; ++jj) tot += p[jj * CG];
       atomicAdd(&stats[(k >> 2) * G.C + (blockIdx.x * CG + gg) * 4 + (k & 3)], (double)tot);
     }
   }
@@ -415,17 +576,18 @@ dw_s1_bwd_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constan
 
 // chunking: CG 4-channel groups per CTA, TW columns, TW*CG <= ncons_max consumer threads
 inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stages, bool bwd, int ctas_per_sm, S1Geom* G, dim3* grid,
-                    int* threads, size_t* smem) {
+                    int* threads, size_t* smem, int cols = 1) {
   int CG;
   if (C % 32 == 0) CG = 8;
   else if (C % 48 == 0) CG = 12;
   else if (C % 16 == 0) CG = 4;
   else return false;
   const int He = H + 2 * ext, We = W + 2 * ext;
-  int TW = ncons_max / CG;
+  int TW = cols * (ncons_max / CG);        // cols columns per consumer thread
+  if (TW + 2 > 256) TW = 254 / cols * cols;   // TMA box limit
   const int tiles = s2r_div_up(We, TW);
-  TW = s2r_div_up(We, tiles);              // balance the column tiles
-  if (TW + 2 > 256) return false;           // TMA box limit
+  TW = s2r_div_up(s2r_div_up(We, tiles), cols) * cols;   // balance the column tiles
+  if (TW + 2 > 256) return false;
   const int chunks = C / (CG * 4);
   // persistent CTAs: `per_chunk` of them per channel chunk (ctas_per_sm resident CTAs on every SM in total), each
   // taking work units (image, row segment, column tile) round-robin.  Rows per unit: as long as possible (vertical
@@ -448,7 +610,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
   G->xoff = (dy_bytes + 127) / 128 * 128;
   G->stage_bytes = (G->xoff + x_bytes + 127) / 128 * 128;
   *grid = dim3(chunks, per_chunk, 1);
-  *threads = (TW * CG + 31) / 32 * 32 + 32;
+  *threads = (TW / cols * CG + 31) / 32 * 32 + 32;
   if (*threads < (CG * 12 + 31) / 32 * 32) *threads = (CG * 12 + 31) / 32 * 32;   // the final reductions use CG*12 threads
   *smem = (size_t)stages * G->stage_bytes + 128;
   return true;
@@ -459,7 +621,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
 constexpr int S1_SMEM_CAP = 160 * 1024;
 template <typename K>
 inline int s1_smem_attr(K kernel, size_t smem, int which) {
-  static bool flags[9] = {false, false, false, false, false, false, false, false, false};   // per kernel instance
+  static bool flags[15] = {};   // per kernel instance
   bool& done = flags[which];
   S2R_REQUIRE(smem <= (size_t)S1_SMEM_CAP, S2R_ERR_UNSUPPORTED, "dwconv3x3: ring of %zu bytes exceeds the cap", smem);
   if (!done) {
@@ -488,7 +650,8 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int 
       dim3 grid;
       int threads;
       size_t smem;
-      if (!s1_plan(N, Hp, Wp, C, 0, FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem)) return S2R_ERR_UNSUPPORTED;
+      static const int cols = (getenv("S2R_DW_COLS") && getenv("S2R_DW_COLS")[0] == '1') ? 1 : 2;   // A/B switch
+      if (!s1_plan(N, Hp, Wp, C, 0, cols == 2 ? FWD2_CONS : FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem, cols)) return S2R_ERR_UNSUPPORTED;
       const long long poff = ((long long)p * W + q) * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
       G.interior = 0;
@@ -505,7 +668,23 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int 
     if (rc) return rc;                                                                      \
     S2R_CUDA_OK(s2r_launch(dw_s1_fwd_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt)); \
   } while (0)
-      if (halo_const) {
+#define S2R_DW_FWD2(HALO_, CG_, SLOT_)                                                      \
+  do {                                                                                      \
+    int rc = s1_smem_attr(dw_s1_fwd2_kernel<HALO_, CG_>, smem, SLOT_);                      \
+    if (rc) return rc;                                                                      \
+    S2R_CUDA_OK(s2r_launch(dw_s1_fwd2_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt)); \
+  } while (0)
+      if (cols == 2) {
+        if (halo_const) {
+          if (G.CG == 8) S2R_DW_FWD2(true, 8, 9);
+          else if (G.CG == 12) S2R_DW_FWD2(true, 12, 10);
+          else S2R_DW_FWD2(true, 4, 11);
+        } else {
+          if (G.CG == 8) S2R_DW_FWD2(false, 8, 12);
+          else if (G.CG == 12) S2R_DW_FWD2(false, 12, 13);
+          else S2R_DW_FWD2(false, 4, 14);
+        }
+      } else if (halo_const) {
         if (G.CG == 8) S2R_DW_FWD(true, 8, 0);
         else if (G.CG == 12) S2R_DW_FWD(true, 12, 1);
         else S2R_DW_FWD(true, 4, 2);
@@ -515,6 +694,7 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int 
         else S2R_DW_FWD(false, 4, 5);
       }
 #undef S2R_DW_FWD
+#undef S2R_DW_FWD2
       S2R_LAUNCH_OK();
     }
   return S2R_OK;

@@ -242,6 +242,25 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
             fwd_B.record(B)
     finally:
         COMM_CHANNEL[0] = 0
+    three = os.environ.get("S2R_STREAMS", "2") == "3"   # measured: 17.59 ms with, 17.45 ms without (profiles/r2_notes.md)
+    if three:
+        # third chain C: the discriminator's training pass on the (detached) source prediction needs nothing but
+        # G(src)'s forward and D's weights, so it runs beside G(src)'s backward and G(tgt)'s forward instead of after
+        # them; likewise its pass on the target prediction runs beside the adversarial backward.  D's parameter
+        # gradients come only from these two passes (requires_grad is off while the adversarial pass is issued,
+        # train_adapt.py:140-141,158-159), both on C, in the reference's order.
+        if getattr(self, "_stream_C", None) is None:
+            self._stream_C = torch.cuda.Stream(device=dev)
+        Cs = self._stream_C
+        Cs.wait_stream(A)                  # G(src) forward (and the zeroed gradient buffers) are ready
+        for p in model_D.parameters():
+            p.requires_grad = True
+        with torch.cuda.stream(Cs):
+            src_det = src_output.detach()
+            loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_det), self.source_label)
+            loss_D_src.backward()
+        for p in model_D.parameters():
+            p.requires_grad = False
     _backward_ce_deferred(loss_seg, model)  # on A, beside B's forward
     # the two generator backward passes run one after the other: overlapping them as well (all gradient accumulation
     # is atomic, so it would be legal) measured no gain -- 17.8 ms either way, the GPU is full by then
@@ -254,6 +273,15 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
         COMM_CHANNEL[0] = 0
     for p in model_D.parameters():
         p.requires_grad = True             # train D (train_adapt.py:158-159)
+    if three:
+        Cs.wait_event(fwd_B)
+        with torch.cuda.stream(Cs):
+            tgt_det = tgt_output.detach()
+            loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_det), self.target_label)
+            loss_D_tgt.backward()
+        A.wait_stream(Cs)
+        A.wait_stream(B)
+        return loss_seg, loss_adv, loss_D_src, loss_D_tgt
     src_output = src_output.detach()
     loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
     loss_D_src.backward()

@@ -2,8 +2,9 @@
 enough): two processes -- on two GPUs when the box has them, otherwise time-sliced on the same one -- meet through
 torch.distributed (gloo: plumbing only) and run
 
-  * the synchronised-BatchNorm exchange of csrc/comm.cu (CUDA-IPC mapped peer memory; works between two processes
-    on one device exactly as over NVLink) inside engine.bn_finalize / engine.bn_backward, against
+  * the synchronised-BatchNorm exchange -- csrc/comm.cu (CUDA-IPC mapped peer memory) when every rank has its own
+    GPU, the torch.distributed collective path of the same engine code on a single GPU (see _worker) -- inside
+    engine.bn_plan / engine.bn_backward, against
     modeling/sync_batchnorm/batchnorm.py:90-125 of the reference evaluated by the oracle on the GATHERED batch
     (O.batch_norm(..., sync_clamp=True): clamp(var, eps)^-1/2, unbiased running variance, global element count);
   * the global-batch mean of the cross entropy (functional.GLOBAL_BATCH_MEAN: train_adapt.py:87-88,144-145 evaluates
@@ -51,7 +52,15 @@ def _worker(rank, world, port, q):
     import importlib
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    os.environ.pop("S2R_COMM", None)
+    # Two GPUs: the NVLink peer-memory exchange of csrc/comm.cu (the product path).  ONE GPU: the two ranks are
+    # time-sliced on it, and kernels that spin on a flag the OTHER process writes must not be launched there (nothing
+    # guarantees that both run at the same time; the B200 profiling notes report context-switch timeouts, Xid 109, for
+    # exactly this) -- the statistics then travel through torch.distributed (S2R_COMM=nccl selects the collective
+    # path; the process group here is gloo), which waits on the host, never on the device.
+    if torch.cuda.device_count() >= world:
+        os.environ.pop("S2R_COMM", None)
+    else:
+        os.environ["S2R_COMM"] = "nccl"
     res = {}
     try:
         dev = torch.device("cuda", rank % torch.cuda.device_count())
@@ -71,7 +80,9 @@ def _worker(rank, world, port, q):
                                      {'params': list(G.get_10x_lr_params()), 'lr': 5e-3}], lr=5e-4, momentum=0.9,
                                     weight_decay=5e-4)
         out = G(xl)
-        assert eng.PEER["world"] == world, "the NVLink/IPC peer exchange was not set up: %r" % (eng.PEER,)
+        if os.environ.get("S2R_COMM") != "nccl":
+            assert eng.PEER["world"] == world, "the NVLink/IPC peer exchange was not set up: %r" % (eng.PEER,)
+        res["exchange"] = "peer memory (csrc/comm.cu)" if eng.PEER["world"] == world else "torch.distributed collectives (one GPU)"
         loss = sub("utils.loss").SegmentationLosses().build_loss('ce')(out, ll)
         loss.backward()
         opt.all_reduce_grads()
@@ -151,6 +162,7 @@ def test_two_ranks_sync_bn_global_ce_and_identical_weights(built_lib):
     res = {r: (status, info) for r, status, info in got}
     assert res[0][0] == "ok" and res[1][0] == "ok", res
     r0 = res[0][1]
+    print("BN-statistics exchange:", r0.get("exchange"))
     print("two ranks on %d GPU(s): loss %.5f (oracle fp32 %.5f, bf16-emulated %.5f); classifier gradient err %.4f; "
           "early BN vs fp32 %s mean %.2e" % (min(2, torch.cuda.device_count()), r0["loss"], r0["oracle_loss"][0],
                                              r0["oracle_loss"][1], r0["cls_grad_err"], r0["bn_early_vs_fp32"],

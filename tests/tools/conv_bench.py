@@ -66,7 +66,7 @@ for name, N, H, W, Cin, Cout, R, s, p, d in SHAPES:
     for op in ("fwd", "dgrad", "wgrad"):
         res = []
         for force in (False, True):
-            if op == "fwd": fn = lambda: eng.conv_fwd(cx, x, w, out, s, p, d, stats=stats, force_mma=force)
+            if op == "fwd": fn = lambda: eng.conv_fwd(cx, x, w, out, s, p, d, stats=None if os.environ.get("S2R_BENCH_NOSTATS") else stats, force_mma=force)
             elif op == "dgrad":
                 if Cin < 8: res.append(float('nan')); continue
                 fn = lambda: eng.conv_dgrad(cx, dy, w, dx, s, p, d, force_mma=force)
