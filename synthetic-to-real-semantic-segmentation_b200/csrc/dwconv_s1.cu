@@ -29,7 +29,7 @@ namespace {
 
 constexpr int RB = 3;            // rows per TMA stage (= accumulator rotation period)
 constexpr int FWD_CONS = 256;    // forward: consumer threads (+ one producer warp)
-constexpr int FWD_STAGES = 8;
+constexpr int FWD_STAGES = 4;
 constexpr int FWD2_CONS = 224;   // two-column forward: 7 consumer warps + the producer = 256 threads -> 128 registers at 2 CTAs / SM
 constexpr int BWD_CONS = 352;    // backward: consumer threads (+ one producer warp)
 constexpr int BWD_STAGES = 4;
@@ -583,23 +583,37 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
   else if (C % 16 == 0) CG = 4;
   else return false;
   const int He = H + 2 * ext, We = W + 2 * ext;
-  int TW = cols * (ncons_max / CG);        // cols columns per consumer thread
-  if (TW + 2 > 256) TW = 254 / cols * cols;   // TMA box limit
-  const int tiles = s2r_div_up(We, TW);
-  TW = s2r_div_up(s2r_div_up(We, tiles), cols) * cols;   // balance the column tiles
-  if (TW + 2 > 256) return false;
+  int TWmax = cols * (ncons_max / CG);   // cols columns per consumer thread
+  if (TWmax + 2 > 256) TWmax = 254 / cols * cols;   // TMA box limit
   const int chunks = C / (CG * 4);
-  // persistent CTAs: `per_chunk` of them per channel chunk (ctas_per_sm resident CTAs on every SM in total), each
-  // taking work units (image, row segment, column tile) round-robin.  Rows per unit: as long as possible (vertical
-  // halo = 2 rows per segment) but at least ~6 units per CTA for balance; rs + 2 is a multiple of the stage depth
-  // RB so no loaded row is wasted.
+  // persistent CTAs: `per_chunk` of them per channel chunk (ctas_per_sm resident CTAs of this kernel on every SM in
+  // total), each taking work units (image, row segment, column tile) round-robin.  The unit shape decides the balance:
+  // a CTA's time is (units it takes) x (rows per unit + 2 halo rows), the kernel's time that of the busiest CTA, so
+  // the split is searched -- column tilings near the widest one x segment heights with rs + 2 a multiple of the stage
+  // depth RB (no loaded row is wasted) -- for the smallest rounds x (rs + 3) (one row of slack per unit boundary).
+  // [The first version grew the segment count by doubling until every CTA had ~6 units; 96 units on 74 CTAs, two
+  // rounds for 1.3 rounds of work, is what that gave on the 192-channel 64x128 layer.]
   int per_chunk = (ctas_per_sm * s2r_sm_count()) / chunks;
   if (per_chunk < 1) per_chunk = 1;
-  int nseg = s2r_div_up(He, 64);
-  while ((long)tiles * N * nseg < 6L * per_chunk && He / (nseg * 2) >= 13) nseg *= 2;
-  int rs = s2r_div_up(He, nseg);
-  rs = (rs + 2 + RB - 1) / RB * RB - 2;
-  nseg = s2r_div_up(He, rs);
+  const int tmin = s2r_div_up(We, TWmax);
+  long best_cost = -1;
+  int tiles = tmin, rs = 0;
+  for (int t = tmin; t <= tmin + 2; ++t) {
+    if (t > tmin && s2r_div_up(We, t) < cols) break;
+    for (int r = RB + RB - 2; ; r += RB) {          // 4, 7, 10, ...: r + 2 is a multiple of RB
+      const int nsg = s2r_div_up(He, r);
+      const long units = (long)t * N * nsg;
+      const long rounds = (units + per_chunk - 1) / per_chunk;
+      const long cost = rounds * (r + 3);
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && t == tiles && r > rs)) {
+        best_cost = cost; tiles = t; rs = r;
+      }
+      if (r >= He) break;
+    }
+  }
+  const int TW = s2r_div_up(s2r_div_up(We, tiles), cols) * cols;   // balance the column tiles
+  if (TW + 2 > 256) return false;
+  const int nseg = s2r_div_up(He, rs);
   const long nunits = (long)tiles * N * nseg;
   if (nunits > 0x7fffffffL) return false;
   if (per_chunk > nunits) per_chunk = (int)nunits;
@@ -621,7 +635,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
 constexpr int S1_SMEM_CAP = 160 * 1024;
 template <typename K>
 inline int s1_smem_attr(K kernel, size_t smem, int which) {
-  static bool flags[15] = {};   // per kernel instance
+  static bool flags[21] = {};   // per kernel instance
   bool& done = flags[which];
   S2R_REQUIRE(smem <= (size_t)S1_SMEM_CAP, S2R_ERR_UNSUPPORTED, "dwconv3x3: ring of %zu bytes exceeds the cap", smem);
   if (!done) {
@@ -650,8 +664,12 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int 
       dim3 grid;
       int threads;
       size_t smem;
-      static const int cols = (getenv("S2R_DW_COLS") && getenv("S2R_DW_COLS")[0] == '1') ? 1 : 2;   // A/B switch
-      if (!s1_plan(N, Hp, Wp, C, 0, cols == 2 ? FWD2_CONS : FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem, cols)) return S2R_ERR_UNSUPPORTED;
+      // variant: two columns per thread on the large images, one on the small ones (measured per layer,
+      // tests/tools/dw_bench.py; S2R_DW_COLS=1|2 forces one)
+      static const int force_cols = getenv("S2R_DW_COLS") ? atoi(getenv("S2R_DW_COLS")) : 0;
+      const int cols = force_cols == 1 || force_cols == 2 ? force_cols : ((long)Hp * Wp >= 128L * 256 ? 2 : 1);
+      if (!s1_plan(N, Hp, Wp, C, 0, cols == 2 ? FWD2_CONS : FWD_CONS, FWD_STAGES, false, 2, &G, &grid, &threads, &smem, cols))
+        return S2R_ERR_UNSUPPORTED;
       const long long poff = ((long long)p * W + q) * C;
       G.os_pix = (long long)dil * C; G.os_row = (long long)dil * W * C; G.os_img = (long long)H * W * C;
       G.interior = 0;
