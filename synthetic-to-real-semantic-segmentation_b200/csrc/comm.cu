@@ -52,8 +52,12 @@ __global__ void __launch_bounds__(CM_THREADS)
 allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
   // channel ch has its own sequence counter and its own region of every inbox: two streams can run their exchange
   // sequences concurrently as long as every rank issues the same sequence PER CHANNEL
-  pdl_wait();      // programmatic dependent launch (common.cuh): resident early, global memory only from here on
-  pdl_trigger();
+  // Programmatic dependent launch (common.cuh): this one-CTA kernel may become resident early, but it must NOT release
+  // its own dependents before the exchange is over -- they would become resident on every SM (a bn_apply grid takes
+  // all thread slots) and sit there while this kernel waits for the peers, starving the other stream's kernels that
+  // the PEER's exchange on the other channel is waiting for: a cross-rank cycle (seen as the bounded-wait error on
+  // 2 GPUs).  No launch_dependents here: the dependents start when this kernel completes.
+  pdl_wait();
   unsigned long long* seqp = c.seq + ch;
   const unsigned long long seq = *seqp + 1;       // every thread reads it; thread 0 advances it at the end
   const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -140,7 +144,7 @@ allreduce_small_kernel(double* __restrict__ buf, int n, CommDev c, int ch) {
 __global__ void __launch_bounds__(CM_THREADS)
 bn_tail_kernel(int C, BnTail t) {
   pdl_wait();
-  pdl_trigger();
+  if (!t.comm) pdl_trigger();   // with an exchange: dependents only after it (see allreduce_small_kernel)
   double* stats = const_cast<double*>(t.sums);
   if (t.comm) cm_exchange_cta(*t.comm, t.channel, stats, 2 * C);
   for (int c = threadIdx.x; c < C; c += CM_THREADS) {
