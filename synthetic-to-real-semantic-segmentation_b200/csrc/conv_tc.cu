@@ -68,7 +68,11 @@ struct TcMaps {
 };
 
 constexpr int TC_STG_BYTES = 128 * 64;                 // one epilogue unit: 128 pixel rows x 32 bf16 channels
-constexpr int TC_STG_TOTAL = 3 * TC_STG_BYTES;         // one staging buffer per epilogue warp group
+// NSTG staging buffers per epilogue warp group.  Two: a unit is staged while the TMA store of the previous one is still
+// reading its buffer, and the per-unit chain has ONE named barrier instead of two and no wait for the store's read
+// (the shallow pointwise convolutions are bound by exactly that chain).  One where the shared memory is needed for the
+// operand pipeline of the tensor-bound shapes (MT = 2 with wide tiles).
+constexpr int tc_stg_total(int nstg) { return 3 * nstg * TC_STG_BYTES; }
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,7 +184,7 @@ constexpr int TC_MAX_COUT = 1024;  // per-CTA statistics staging (channels)
 // running side by side share the A boxes in L2).  The TMA producer runs ahead across tile boundaries, the
 // MMA issuer alternates between NACC TMEM accumulators, the epilogue warps drain one accumulator while the
 // next tile is being multiplied.
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, int NSTG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * 128;
@@ -310,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool one_n = n_tiles_n == 1;                            // Cout <= BN: tile index = pixel tile
     const bool one_row = p.tiles_h == 1 && p.N == 1;              // flattened pointwise problem: one long pixel row
     int lt = 0, rot = grp;                                        // rot = (grp + 3 - lt % 3) % 3, kept incrementally
+    int cnt = 0;                                                  // units this warp group has staged (buffer parity)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt, rot = rot == 0 ? 2 : rot - 1) {
       const int mt = one_n ? tile : tile / n_tiles_n, n0 = one_n ? 0 : (tile - mt * n_tiles_n) * BN;
       const int ab = lt % NACC;
@@ -419,9 +424,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // stage the 128 x 32 unit in shared memory (64-byte rows, 16-byte chunks XOR-swizzled with (row >> 1) & 3:
         // the layout of CU_TENSOR_MAP_SWIZZLE_64B, conflict-free for these stores) and write it out with one TMA
         // store: full 64-byte segments per pixel instead of 32 scattered 16-byte stores per instruction
-        uint8_t* stg = smem_stg + grp * TC_STG_BYTES;
-        if (row == 0) bulk_wait_read0();          // the previous store of this group has finished reading the buffer
-        named_bar_sync(1 + grp, 128);
+        uint8_t* stg = smem_stg + (grp * NSTG + (NSTG == 2 ? (cnt & 1) : 0)) * TC_STG_BYTES;
+        ++cnt;
+        if (NSTG == 1) {
+          if (row == 0) bulk_wait_read0();        // the previous store of this group has finished reading the buffer
+          named_bar_sync(1 + grp, 128);
+        }
+        // NSTG == 2: this buffer was last used two units ago; row 0 waited for that unit's store before the barrier of
+        // the unit in between (below), and every thread finished reading its statistics before arriving there
         {
           uint8_t* rp = stg + row * 64;
           const int sw = (row >> 1) & 3;
@@ -429,6 +439,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int qq = 0; qq < 4; ++qq) *reinterpret_cast<uint4*>(rp + ((qq ^ sw) << 4)) = pk[qq];
         }
         fence_proxy_async();
+        if (NSTG == 2 && row == 0) bulk_wait_read0();   // the previous unit's store (the other buffer) has been read
         named_bar_sync(1 + grp, 128);
         if (row == 0 && tok) {
           tma_store_4d(&maps.out, smem_addr(stg), n0 + c0, tw_, th_, tn_);
@@ -442,11 +453,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           // segment) they ran 8-way contended and dominated the epilogue's latency chain.  Rows 8*rr + cls of one
           // load instruction sit in 32 distinct banks (64-byte rows, chunk XOR (row >> 1) & 3).
           const int pr = ew * 4 + (lane & 3), cls = lane >> 2;
+          const uint32_t stg_s = smem_addr(stg);
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
             const int r2 = rr * 8 + cls;
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + r2 * 64 + ((((pr >> 2) ^ ((r2 >> 1) & 3))) << 4) + (pr & 3) * 4);
+            uint32_t wv;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(stg_s + (uint32_t)(r2 * 64 + ((((pr >> 2) ^ ((r2 >> 1) & 3))) << 4) + (pr & 3) * 4)));
             const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
             s0 += f0; s1 += f1;
             q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
@@ -540,17 +553,18 @@ bool encode_weights(EncodeTiledFn enc, CUtensorMap* m, const void* w, int Kpad, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, int NSTG>
 int launch_tc(const TcMaps& maps, const TcParams& p, int n_tiles_n, cudaStream_t st) {
-  constexpr int smem = STAGES * (MT * TC_A_BYTES + BN * 128) + TC_STG_TOTAL + 1024;
+  constexpr int smem = STAGES * (MT * TC_A_BYTES + BN * 128) + tc_stg_total(NSTG) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    S2R_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2R_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, MT, STAGES, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const long long tiles = (long long)s2r_div_up(p.n_subtiles, MT) * n_tiles_n;
   const int grid = (int)(tiles < s2r_sm_count() ? tiles : s2r_sm_count());  // persistent: one CTA per SM
-  S2R_CUDA_OK(s2r_launch(conv_tc_kernel<BN, MT, STAGES>, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, maps, p));
+  S2R_CUDA_OK(s2r_launch(conv_tc_kernel<BN, MT, STAGES, NSTG>, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, maps, p));
   S2R_LAUNCH_OK();
   return 1;
 }
@@ -693,10 +707,12 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
   const bool deep = (long long)p.ntaps * p.kchunks >= 8;
   const bool big = deep && nsub * ntn >= 2ll * s2r_sm_count() * 2;
   switch (BN) {
-    case 256: return big ? launch_tc<256, 2, 3>(maps, p, ntn, st) : launch_tc<256, 1, 4>(maps, p, ntn, st);
-    case 160: return big ? launch_tc<160, 2, 3>(maps, p, ntn, st) : launch_tc<160, 1, 5>(maps, p, ntn, st);
-    case 128: return big ? launch_tc<128, 2, 4>(maps, p, ntn, st) : launch_tc<128, 1, 6>(maps, p, ntn, st);
-    case 64: return big ? launch_tc<64, 2, 4>(maps, p, ntn, st) : launch_tc<64, 1, 8>(maps, p, ntn, st);
-    default: return launch_tc<32, 1, 8>(maps, p, ntn, st);
+    // stages x staging buffers within the 227 KB of shared memory: the shallow (MT = 1) shapes, whose epilogue is the
+    // bottleneck, give up one or two operand stages for the second staging buffer
+    case 256: return big ? launch_tc<256, 2, 3, 1>(maps, p, ntn, st) : launch_tc<256, 1, 3, 2>(maps, p, ntn, st);
+    case 160: return big ? launch_tc<160, 2, 3, 2>(maps, p, ntn, st) : launch_tc<160, 1, 4, 2>(maps, p, ntn, st);
+    case 128: return big ? launch_tc<128, 2, 4, 1>(maps, p, ntn, st) : launch_tc<128, 1, 5, 2>(maps, p, ntn, st);
+    case 64: return big ? launch_tc<64, 2, 4, 2>(maps, p, ntn, st) : launch_tc<64, 1, 6, 2>(maps, p, ntn, st);
+    default: return launch_tc<32, 1, 8, 2>(maps, p, ntn, st);
   }
 }
