@@ -108,6 +108,8 @@ typedef struct {
   const void* aux; /* bf16 view, same pixel grid as out */
   int64_t an, ah, aw;
   double* stats; /* [2][Cout]: += sum and sum of squares of (acc + bias), or NULL */
+  const float* oscale; /* [Cout] or NULL: out = act(acc*oscale[co] + bias[co]) -- an eval-mode BatchNorm
+                          (running statistics; batchnorm.py:50-53) folded into the producing convolution */
 } s2r_conv_args;
 
 int s2r_conv_fwd(const s2r_conv_args* a, s2r_stream_t stream);
@@ -167,10 +169,12 @@ int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, in
                       const float* w, void* y, double* stats, int N, int H, int W, int C,
                       int stride, int dil, int pad, s2r_stream_t stream);
 /* The same with the input's BatchNorm still pending (in_bn: host pointer; NULL = s2r_dwconv3x3_fwd): scale / shift of
- * the prologue are derived from in_bn->sums inside the kernel, which also publishes them (see s2r_bn_tail). */
+ * the prologue are derived from in_bn->sums inside the kernel, which also publishes them (see s2r_bn_tail).
+ * out_scale_shift ([2][C] or NULL; inference, excludes stats): y = relu6(conv*scale + shift) -- the BatchNorm + ReLU6
+ * that FOLLOWS the convolution (mobilenet.py:41-42,55-56) with its running statistics, applied before the store. */
 int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, const float* in_scale_shift, int in_act,
-                         int halo_const, const float* w, void* y, double* stats, int N, int H, int W, int C,
-                         int stride, int dil, int pad, s2r_stream_t stream);
+                         int halo_const, const float* w, void* y, double* stats, const float* out_scale_shift,
+                         int N, int H, int W, int C, int stride, int dil, int pad, s2r_stream_t stream);
 /* Data gradient w.r.t. the PRE-prologue tensor's BN output, masked by act':
  *   g = dgrad(dy) * act'(x*scale + shift), written on the domain extended by `ext` pixels on
  *   every side (ext = pad when halo_const, where x counts as 0; else 0):  g[N][H+2ext][W+2ext][C].

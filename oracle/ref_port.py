@@ -35,6 +35,17 @@ def _q(t):
     return t if Q is None else Q(t)
 
 
+# bf16-storage emulation (tests/emul.py) of the B200 INFERENCE path: in eval mode under torch.no_grad() the BatchNorm
+# (+ activation, + residual) is the epilogue of the producing convolution, so the pre-BatchNorm output of the
+# depthwise / project / ASPP / decoder / domain-classifier convolutions is never stored (hence never rounded).
+Q_FOLD_EVAL = False
+
+
+def _qz(t, cfg):
+    """Rounding point of a pre-BatchNorm convolution output."""
+    return t if (Q_FOLD_EVAL and not cfg.training) else _q(t)
+
+
 def _tr(name, t):
     if TRACE is not None:
         TRACE.append((name, t.detach()))
@@ -104,9 +115,9 @@ def inverted_residual(sd, pre, x, inp, oup, stride, dil, expand, cfg):
         h = F.relu6(batch_norm(sd, pre + '.conv.1', h, cfg))       # consumed by the dw prologue: not stored
         i = 3
     hidden = h.shape[1]
-    h = _q(F.conv2d(h, sd['%s.conv.%d.weight' % (pre, i)], None, stride, 0, dil, hidden))
+    h = _qz(F.conv2d(h, sd['%s.conv.%d.weight' % (pre, i)], None, stride, 0, dil, hidden), cfg)
     h = _q(F.relu6(batch_norm(sd, '%s.conv.%d' % (pre, i + 1), h, cfg)))
-    h = _q(F.conv2d(h, _q(sd['%s.conv.%d.weight' % (pre, i + 3)])))
+    h = _qz(F.conv2d(h, _q(sd['%s.conv.%d.weight' % (pre, i + 3)])), cfg)
     h = batch_norm(sd, '%s.conv.%d' % (pre, i + 4), h, cfg)
     return _q(x + h) if (stride == 1 and inp == oup) else _q(h)
 
@@ -129,13 +140,13 @@ def aspp_forward(sd, x, cfg, output_stride=16, pre='', drop=None):
     outs = []
     for k, d in enumerate(dils, start=1):
         w = sd['%saspp%d.atrous_conv.weight' % (pre, k)]
-        h = _q(F.conv2d(x, _q(w), None, 1, 0 if k == 1 else d, d))
+        h = _qz(F.conv2d(x, _q(w), None, 1, 0 if k == 1 else d, d), cfg)
         outs.append(_q(F.relu(batch_norm(sd, '%saspp%d.bn' % (pre, k), h, cfg))))
     g = _q(F.adaptive_avg_pool2d(x, 1))
-    g = _q(F.conv2d(g, _q(sd[pre + 'global_avg_pool.1.weight'])))
+    g = _qz(F.conv2d(g, _q(sd[pre + 'global_avg_pool.1.weight'])), cfg)
     g = _q(F.relu(batch_norm(sd, pre + 'global_avg_pool.2', g, cfg)))
     outs.append(F.interpolate(g, size=x.shape[2:], mode='bilinear', align_corners=True))
-    h = _q(F.conv2d(_tr('aspp_cat', torch.cat(outs, 1)), _q(sd[pre + 'conv1.weight'])))
+    h = _qz(F.conv2d(_tr('aspp_cat', torch.cat(outs, 1)), _q(sd[pre + 'conv1.weight'])), cfg)
     h = F.relu(batch_norm(sd, pre + 'bn1', h, cfg))
     return _tr('aspp_out', _q(_dropout(h, 0.5, cfg, drop)))
 
@@ -148,13 +159,13 @@ def _dropout(x, p, cfg, drop):
 
 def decoder_forward(sd, x, low, cfg, pre='', drop=None):
     """modeling/decoder.py:34-43."""
-    l = _q(F.conv2d(low, _q(sd[pre + 'conv1.weight'])))
+    l = _qz(F.conv2d(low, _q(sd[pre + 'conv1.weight'])), cfg)
     l = _q(F.relu(batch_norm(sd, pre + 'bn1', l, cfg)))
     x = _q(F.interpolate(x, size=l.shape[2:], mode='bilinear', align_corners=True))
     h = _tr('dec_cat', torch.cat((x, l), 1))
-    h = _q(F.conv2d(h, _q(sd[pre + 'last_conv.0.weight']), None, 1, 1))
+    h = _qz(F.conv2d(h, _q(sd[pre + 'last_conv.0.weight']), None, 1, 1), cfg)
     h = _tr('dec_y1', _q(_dropout(F.relu(batch_norm(sd, pre + 'last_conv.1', h, cfg)), 0.5, cfg, drop)))
-    h = _q(F.conv2d(h, _q(sd[pre + 'last_conv.4.weight']), None, 1, 1))
+    h = _qz(F.conv2d(h, _q(sd[pre + 'last_conv.4.weight']), None, 1, 1), cfg)
     h = _tr('dec_y2', _q(_dropout(F.relu(batch_norm(sd, pre + 'last_conv.5', h, cfg)), 0.1, cfg, drop)))
     return _tr('dec_logits', _q(F.conv2d(h, _q(sd[pre + 'last_conv.8.weight']), sd[pre + 'last_conv.8.bias'])))
 
@@ -177,9 +188,9 @@ def discriminator_forward(sd, x):
 
 def domain_classifier_forward(sd, x, cfg, drop=None):
     """modeling/domian.py:27-32."""
-    h = _q(F.conv2d(_q(x), _q(sd['DC_adnn1.0.weight'])))
+    h = _qz(F.conv2d(_q(x), _q(sd['DC_adnn1.0.weight'])), cfg)
     h = _q(_dropout(F.relu(batch_norm(sd, 'DC_adnn1.1', h, cfg)), 0.5, cfg, drop))
-    h = _q(F.conv2d(h, _q(sd['DC_adnn2.0.weight']), None, 1, 1))
+    h = _qz(F.conv2d(h, _q(sd['DC_adnn2.0.weight']), None, 1, 1), cfg)
     h = _q(_dropout(F.relu(batch_norm(sd, 'DC_adnn2.1', h, cfg)), 0.5, cfg, drop))
     return _q(F.conv2d(h, _q(sd['DC_adnn3.weight']), sd['DC_adnn3.bias'], 1, 1))
 

@@ -38,7 +38,7 @@ class ConvArgs(C.Structure):
                 ("w", vp), ("Cout_pad", i32), ("Kpad", i32),
                 ("out", vp), ("on", i64), ("oh", i64), ("ow", i64),
                 ("bias", vp), ("act", i32), ("slope", f32), ("aux_mode", i32), ("_pad", i32),
-                ("aux", vp), ("an", i64), ("ah", i64), ("aw", i64), ("stats", vp)]
+                ("aux", vp), ("an", i64), ("ah", i64), ("aw", i64), ("stats", vp), ("oscale", vp)]
 
 
 class WgradArgs(C.Structure):
@@ -98,7 +98,7 @@ PROTOTYPES = {
     "s2r_softmax0_nchw_to_nhwc_pad": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_softmax0_nhwc_pad_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
-    "s2r_dwconv3x3_fwd_bn": [vp, C.POINTER(BnTail), vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "s2r_dwconv3x3_fwd_bn": [vp, C.POINTER(BnTail), vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_wgrad": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

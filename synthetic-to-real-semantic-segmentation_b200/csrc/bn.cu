@@ -741,6 +741,11 @@ extern "C" int s2r_bn_apply_act(const void* x, int64_t P, int C, int xpitch, int
                              yoff, stream);
 }
 
+// y = relu6(y*scale + shift) in place (the generic depthwise kernel's inference epilogue, dwconv.cu)
+int s2r_bn_apply_inplace_relu6(void* y, int64_t P, int C, const float* scale_shift, cudaStream_t st) {
+  return s2r_bn_apply_act_bn(y, P, C, C, 0, nullptr, scale_shift, S2R_ACT_RELU6, nullptr, 0.f, 0, nullptr, y, C, 0, (s2r_stream_t)st);
+}
+
 extern "C" int s2r_bn_bwd_reduce(const void* dy, int dypitch, int dyoff, const void* x, int xpitch,
                                  int xoff, const float* mean_invstd, const float* scale_shift, int act,
                                  float drop_p, uint64_t seed, const uint64_t* seed_dev, int64_t P, int C,

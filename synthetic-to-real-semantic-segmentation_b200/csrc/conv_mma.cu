@@ -40,6 +40,7 @@ struct FwdParams {
   __nv_bfloat16* out;
   long long on, oh, ow;
   const float* bias;
+  const float* oscale;
   int act;
   float slope;
   int aux_mode;
@@ -238,6 +239,10 @@ tap_fwd_kernel(const __grid_constant__ FwdParams p) {
         const int co = n0 + warp_n * 32 + ni * 8 + tq * 2;
         float v0 = acc[mi][ni][h * 2], v1 = acc[mi][ni][h * 2 + 1];
         const bool c0 = co < p.Cout, c1 = co + 1 < p.Cout;
+        if (p.oscale) {
+          if (c0) v0 *= __ldg(p.oscale + co);
+          if (c1) v1 *= __ldg(p.oscale + co + 1);
+        }
         if (p.bias) {
           if (c0) v0 += __ldg(p.bias + co);
           if (c1) v1 += __ldg(p.bias + co + 1);
@@ -613,6 +618,7 @@ extern "C" int s2r_conv_fwd_mma(const s2r_conv_args* a, s2r_stream_t stream) {
   p.out = (__nv_bfloat16*)a->out;
   p.on = a->on; p.oh = a->oh; p.ow = a->ow;
   p.bias = a->bias; p.act = a->act; p.slope = a->slope;
+  p.oscale = a->oscale;
   p.aux_mode = a->aux_mode;
   p.aux = a->aux_mode == S2R_AUX_NONE ? nullptr : (const __nv_bfloat16*)a->aux;
   p.an = a->an; p.ah = a->ah; p.aw = a->aw;

@@ -53,6 +53,7 @@ struct TcParams {
   __nv_bfloat16* out;
   long long on, oh, ow;
   const float* bias;
+  const float* oscale;
   int act;
   float slope;
   int aux_mode;
@@ -367,6 +368,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         const bool full = n0 + c0 + 32 <= p.Cout;   // warp-uniform
+        if (p.oscale) {   // eval-mode BatchNorm folded into the convolution: acc * scale[co] (+ bias below = shift)
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.oscale + n0 + c0 + i));
+              v[i] *= s4.x; v[i + 1] *= s4.y; v[i + 2] *= s4.z; v[i + 3] *= s4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) v[i] *= __ldg(p.oscale + n0 + c0 + i);
+          }
+        }
         if (p.bias) {
           if (full) {
 #pragma unroll
@@ -661,6 +675,8 @@ int s2r_conv_fwd_tc(const s2r_conv_args* a, cudaStream_t st) {
   p.out = (__nv_bfloat16*)a->out;
   p.on = on; p.oh = oh; p.ow = ow;
   p.bias = a->bias; p.act = a->act; p.slope = a->slope;
+  p.oscale = a->oscale;
+  if ((a->bias && (uintptr_t)a->bias % 16) || (a->oscale && (uintptr_t)a->oscale % 16)) return 0;   // float4 loads
   p.aux_mode = a->aux_mode;
   p.aux = a->aux_mode == S2R_AUX_NONE ? nullptr : (const __nv_bfloat16*)a->aux;
   p.an = an; p.ah = ah; p.aw = aw;

@@ -366,12 +366,12 @@ inline int dw_smem_attr(K kernel, size_t smem) {
 
 // streaming stride-1 kernels (dwconv_s1.cu)
 int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int halo_const, const float* w, void* y,
-                  double* stats, int N, int H, int W, int C, int dil, cudaStream_t stream);
+                  double* stats, const float* oss, int N, int H, int W, int C, int dil, cudaStream_t stream);
 int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int ext,
                   int interior, void* g, double* bsums, float* dw, int N, int H, int W, int C, int dil, cudaStream_t stream);
 
 int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, cudaStream_t stream);
+                  const float* oss, int N, int H, int W, int C, cudaStream_t stream);
 int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* mi, const float* w, int interior,
                   void* g, double* bsums, float* dw, int N, int H, int W, int C, cudaStream_t stream);
 
@@ -387,13 +387,18 @@ static bool s1_eligible(const float* ss, int in_act, int stride, int dil, int pa
 
 // in_bn: the input's BatchNorm is still pending (s2r_bn_tail): the streaming kernels derive scale / shift from its
 // sums in their prologue; with a cross-rank exchange, or on the generic kernel, it is finalised by one small launch first.
+// out_scale_shift (inference, [2][C] or NULL): y = relu6(conv*scale + shift), the BatchNorm + ReLU6 that follows the
+// convolution with its running statistics, applied in the kernel's store (the generic kernel: one bn_apply pass after it).
+int s2r_bn_apply_inplace_relu6(void* y, int64_t P, int C, const float* scale_shift, cudaStream_t st);
+
 extern "C" int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, const float* in_scale_shift, int in_act,
-                                    int halo_const, const float* w, void* y, double* stats, int N, int H, int W, int C,
-                                    int stride, int dil, int pad, s2r_stream_t stream) {
+                                    int halo_const, const float* w, void* y, double* stats, const float* out_scale_shift,
+                                    int N, int H, int W, int C, int stride, int dil, int pad, s2r_stream_t stream) {
   DwGeom G;
   int rc = dw_check(x, y, N, H, W, C, stride, dil, pad, &G);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  S2R_REQUIRE(!(out_scale_shift && stats), S2R_ERR_SHAPE, "dwconv3x3_fwd: an output BatchNorm (inference) and statistics (training) exclude each other");
   if (in_bn) {
     S2R_REQUIRE(in_bn->count > 1, S2R_ERR_SHAPE, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
     S2R_REQUIRE(in_bn->sums && in_bn->scale_shift && in_bn->mean_invstd && (uintptr_t)in_bn->sums % 16 == 0, S2R_ERR_SHAPE,
@@ -409,11 +414,11 @@ extern "C" int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, con
     if (rc) return rc;
   }
   if (s1) {
-    rc = s2r_dw_s1_fwd(x, in_scale_shift, fused, halo_const, w, y, stats, N, H, W, C, dil, st);
+    rc = s2r_dw_s1_fwd(x, in_scale_shift, fused, halo_const, w, y, stats, out_scale_shift, N, H, W, C, dil, st);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
   if (s2) {
-    rc = s2r_dw_s2_fwd(x, in_scale_shift, fused, w, y, stats, N, H, W, C, st);
+    rc = s2r_dw_s2_fwd(x, in_scale_shift, fused, w, y, stats, out_scale_shift, N, H, W, C, st);
     if (rc != S2R_ERR_UNSUPPORTED) return rc;
   }
   if (fused) {   // the streaming kernels declined the shape after all
@@ -437,14 +442,15 @@ extern "C" int s2r_dwconv3x3_fwd_bn(const void* x, const s2r_bn_tail* in_bn, con
         (const __nv_bfloat16*)x, in_scale_shift, in_act, halo_const, w, (__nv_bfloat16*)y, stats, G, tw));
   }
   S2R_LAUNCH_OK();
+  if (out_scale_shift) return s2r_bn_apply_inplace_relu6(y, (int64_t)N * G.Ho * G.Wo, C, out_scale_shift, st);
   return S2R_OK;
 }
 
 extern "C" int s2r_dwconv3x3_fwd(const void* x, const float* in_scale_shift, int in_act, int halo_const,
                                  const float* w, void* y, double* stats, int N, int H, int W, int C,
                                  int stride, int dil, int pad, s2r_stream_t stream) {
-  return s2r_dwconv3x3_fwd_bn(x, nullptr, in_scale_shift, in_act, halo_const, w, y, stats, N, H, W, C, stride, dil, pad,
-                              stream);
+  return s2r_dwconv3x3_fwd_bn(x, nullptr, in_scale_shift, in_act, halo_const, w, y, stats, nullptr, N, H, W, C, stride, dil,
+                              pad, stream);
 }
 
 static int dw_dgrad_generic(const void* dy, const float* w, const void* x,

@@ -60,13 +60,22 @@ __device__ __forceinline__ uint2 lds8(uint32_t addr) {
   return v;
 }
 
+// relu6(v*sc + sh) with sc6 = sc/6, sh6 = sh/6: 6 * sat(v*sc6 + sh6)
+__device__ __forceinline__ float2 oaff2(float2 v, float2 sc6, float2 sh6) {
+  return make_float2(6.f * __saturatef(fmaf(v.x, sc6.x, sh6.x)), 6.f * __saturatef(fmaf(v.y, sc6.y, sh6.y)));
+}
+
 // ------------------------------------------------------------------------------------ forward
 // y[oh][ow] = sum_{ky,kx} a(oh+ky-1, ow+kx-1) w[ky][kx],  a = relu6(x*sc+sh) inside the image and
 // HALO ? relu6(sh) : 0 outside.  stats += per-channel sum / sum of squares of y.
-template <bool HALO, int CG>
+// OAFF (inference): the BatchNorm + ReLU6 that FOLLOWS the convolution (mobilenet.py:41-42,55-56) with its running
+// statistics is applied to the accumulators before the store, y = relu6(acc*oss[c] + oss[C+c]) -- no bn_apply pass
+// over the output; no statistics in that mode.
+template <bool HALO, int CG, bool OAFF>
 __global__ void __launch_bounds__(FWD_CONS + 32, 2)
 dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn) {
+                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn,
+                 const float* __restrict__ oss) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
@@ -136,6 +145,12 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
     const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
     float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
     load_filter(w, c, 6.f, wA, wB);
+    float2 oscA = make_float2(0.f, 0.f), oscB = oscA, oshA = oscA, oshB = oscA;   // OAFF: scale / 6, shift / 6
+    if (OAFF) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(oss + c)), p4 = __ldg(reinterpret_cast<const float4*>(oss + G.C + c));
+      oscA = make_float2(o4.x * (1.f / 6.f), o4.y * (1.f / 6.f)); oscB = make_float2(o4.z * (1.f / 6.f), o4.w * (1.f / 6.f));
+      oshA = make_float2(p4.x * (1.f / 6.f), p4.y * (1.f / 6.f)); oshB = make_float2(p4.z * (1.f / 6.f), p4.w * (1.f / 6.f));
+    }
 
     const long long rowp = G.os_row;
     const uint32_t tile0 = smem_addr(smem) + (uint32_t)(j * CG + g) * 8u;   // this thread's left neighbour in row 0 of stage 0
@@ -180,11 +195,15 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
         accA[s2] = ffma2(rA, wA[8], ffma2(cA, wA[7], ffma2(lA, wA[6], accA[s2])));
         accB[s2] = ffma2(rB, wB[8], ffma2(cB, wB[7], ffma2(lB, wB[6], accB[s2])));
         if ((unsigned)(r - 2) < (unsigned)rows && active) {
-          *reinterpret_cast<uint2*>(yrow) = pack4(accA[s2], accB[s2]);
-          sA = fadd2(sA, accA[s2]);
-          sB = fadd2(sB, accB[s2]);
-          qA = ffma2(accA[s2], accA[s2], qA);
-          qB = ffma2(accB[s2], accB[s2], qB);
+          if (OAFF) {
+            *reinterpret_cast<uint2*>(yrow) = pack4(oaff2(accA[s2], oscA, oshA), oaff2(accB[s2], oscB, oshB));
+          } else {
+            *reinterpret_cast<uint2*>(yrow) = pack4(accA[s2], accB[s2]);
+            sA = fadd2(sA, accA[s2]);
+            sB = fadd2(sB, accB[s2]);
+            qA = ffma2(accA[s2], accA[s2], qA);
+            qB = ffma2(accB[s2], accB[s2], qB);
+          }
         }
         yrow += rowp;
       }
@@ -218,10 +237,11 @@ dw_s1_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restri
 // needs four activated vectors for two outputs (2 x 8 per output), one shared-memory load per output less, and the row
 // loop's fixed cost (barrier wait, pointer updates) is spread over twice the work: ~43 instead of ~58 instructions per
 // output vector, with twelve independent accumulator chains per thread instead of six.
-template <bool HALO, int CG>
+template <bool HALO, int CG, bool OAFF>
 __global__ void __launch_bounds__(FWD2_CONS + 32, 2)
 dw_s1_fwd2_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ ss, const float* __restrict__ w,
-                  __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn) {
+                  __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S1Geom G, const BnTail in_bn,
+                  const float* __restrict__ oss) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[FWD_STAGES], bar_empty[FWD_STAGES];
@@ -281,6 +301,12 @@ dw_s1_fwd2_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restr
     const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
     float2 wA[9], wB[9];   // 6 * filter, channels (0,1) and (2,3)
     load_filter(w, c, 6.f, wA, wB);
+    float2 oscA = make_float2(0.f, 0.f), oscB = oscA, oshA = oscA, oshB = oscA;   // OAFF: scale / 6, shift / 6
+    if (OAFF) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(oss + c)), p4 = __ldg(reinterpret_cast<const float4*>(oss + G.C + c));
+      oscA = make_float2(o4.x * (1.f / 6.f), o4.y * (1.f / 6.f)); oscB = make_float2(o4.z * (1.f / 6.f), o4.w * (1.f / 6.f));
+      oshA = make_float2(p4.x * (1.f / 6.f), p4.y * (1.f / 6.f)); oshB = make_float2(p4.z * (1.f / 6.f), p4.w * (1.f / 6.f));
+    }
 
     const long long rowp = G.os_row;
     const uint32_t tile0 = smem_addr(smem) + (uint32_t)(2 * j * CG + g) * 8u;   // left neighbour of column 2j, row 0, stage 0
@@ -332,17 +358,22 @@ dw_s1_fwd2_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restr
           accB[q][s2] = ffma2(aB[q + 2], wB[8], ffma2(aB[q + 1], wB[7], ffma2(aB[q], wB[6], accB[q][s2])));
         }
         if ((unsigned)(r - 2) < (unsigned)rows && act0) {
-          *reinterpret_cast<uint2*>(yrow0) = pack4(accA[0][s2], accB[0][s2]);
-          sA = fadd2(sA, accA[0][s2]);
-          sB = fadd2(sB, accB[0][s2]);
-          qA = ffma2(accA[0][s2], accA[0][s2], qA);
-          qB = ffma2(accB[0][s2], accB[0][s2], qB);
-          if (act1) {
-            *reinterpret_cast<uint2*>(yrow1) = pack4(accA[1][s2], accB[1][s2]);
-            sA = fadd2(sA, accA[1][s2]);
-            sB = fadd2(sB, accB[1][s2]);
-            qA = ffma2(accA[1][s2], accA[1][s2], qA);
-            qB = ffma2(accB[1][s2], accB[1][s2], qB);
+          if (OAFF) {
+            *reinterpret_cast<uint2*>(yrow0) = pack4(oaff2(accA[0][s2], oscA, oshA), oaff2(accB[0][s2], oscB, oshB));
+            if (act1) *reinterpret_cast<uint2*>(yrow1) = pack4(oaff2(accA[1][s2], oscA, oshA), oaff2(accB[1][s2], oscB, oshB));
+          } else {
+            *reinterpret_cast<uint2*>(yrow0) = pack4(accA[0][s2], accB[0][s2]);
+            sA = fadd2(sA, accA[0][s2]);
+            sB = fadd2(sB, accB[0][s2]);
+            qA = ffma2(accA[0][s2], accA[0][s2], qA);
+            qB = ffma2(accB[0][s2], accB[0][s2], qB);
+            if (act1) {
+              *reinterpret_cast<uint2*>(yrow1) = pack4(accA[1][s2], accB[1][s2]);
+              sA = fadd2(sA, accA[1][s2]);
+              sB = fadd2(sB, accB[1][s2]);
+              qA = ffma2(accA[1][s2], accA[1][s2], qA);
+              qB = ffma2(accB[1][s2], accB[1][s2], qB);
+            }
           }
         }
         yrow0 += rowp;
@@ -635,7 +666,7 @@ inline bool s1_plan(int N, int H, int W, int C, int ext, int ncons_max, int stag
 constexpr int S1_SMEM_CAP = 160 * 1024;
 template <typename K>
 inline int s1_smem_attr(K kernel, size_t smem, int which) {
-  static bool flags[21] = {};   // per kernel instance
+  static bool flags[32] = {};   // per kernel instance
   bool& done = flags[which];
   S2R_REQUIRE(smem <= (size_t)S1_SMEM_CAP, S2R_ERR_UNSUPPORTED, "dwconv3x3: ring of %zu bytes exceeds the cap", smem);
   if (!done) {
@@ -651,7 +682,8 @@ inline int s1_smem_attr(K kernel, size_t smem, int which) {
 // Dilation d (padding d) is d*d independent dilation-1 problems on the parity planes of the tensor: plane (p, q)
 // holds the pixels (d*i + p, d*j + q) and is addressed through a TMA map with d-fold strides.
 int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int halo_const, const float* w, void* y,
-                  double* stats, int N, int H, int W, int C, int dil, cudaStream_t stream) {
+                  double* stats, const float* oss, int N, int H, int W, int C, int dil, cudaStream_t stream) {
+  if (oss && (stats || (uintptr_t)oss % 16)) return S2R_ERR_UNSUPPORTED;   // output affine: inference only
   // in_bn: the input's BatchNorm is pending -- every launch derives scale / shift from its sums, the first one of a
   // dilated set (dil*dil parity-plane launches) publishes them and updates the running statistics
   const BnTail bt = bn_tail_from(in_bn);
@@ -680,39 +712,27 @@ int s2r_dw_s1_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, int 
                             G.CG * 4, G.TW + 2, RB))
         return S2R_ERR_UNSUPPORTED;
       __nv_bfloat16* yv = (__nv_bfloat16*)y + poff;
-#define S2R_DW_FWD(HALO_, CG_, SLOT_)                                                       \
+#define S2R_DW_FWD(K_, HALO_, CG_, OAFF_, SLOT_)                                              \
   do {                                                                                      \
-    int rc = s1_smem_attr(dw_s1_fwd_kernel<HALO_, CG_>, smem, SLOT_);                       \
+    int rc = s1_smem_attr(K_<HALO_, CG_, OAFF_>, smem, SLOT_);                              \
     if (rc) return rc;                                                                      \
-    S2R_CUDA_OK(s2r_launch(dw_s1_fwd_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt)); \
+    S2R_CUDA_OK(s2r_launch(K_<HALO_, CG_, OAFF_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt, oss)); \
   } while (0)
-#define S2R_DW_FWD2(HALO_, CG_, SLOT_)                                                      \
+#define S2R_DW_FWD_CG(K_, HALO_, OAFF_, SLOT_)                                              \
   do {                                                                                      \
-    int rc = s1_smem_attr(dw_s1_fwd2_kernel<HALO_, CG_>, smem, SLOT_);                      \
-    if (rc) return rc;                                                                      \
-    S2R_CUDA_OK(s2r_launch(dw_s1_fwd2_kernel<HALO_, CG_>, grid, dim3(threads), smem, stream, xmap, ss, w, yv, stats, G, bt)); \
+    if (G.CG == 8) S2R_DW_FWD(K_, HALO_, 8, OAFF_, SLOT_);                                  \
+    else if (G.CG == 12) S2R_DW_FWD(K_, HALO_, 12, OAFF_, SLOT_ + 1);                       \
+    else S2R_DW_FWD(K_, HALO_, 4, OAFF_, SLOT_ + 2);                                        \
   } while (0)
       if (cols == 2) {
-        if (halo_const) {
-          if (G.CG == 8) S2R_DW_FWD2(true, 8, 9);
-          else if (G.CG == 12) S2R_DW_FWD2(true, 12, 10);
-          else S2R_DW_FWD2(true, 4, 11);
-        } else {
-          if (G.CG == 8) S2R_DW_FWD2(false, 8, 12);
-          else if (G.CG == 12) S2R_DW_FWD2(false, 12, 13);
-          else S2R_DW_FWD2(false, 4, 14);
-        }
-      } else if (halo_const) {
-        if (G.CG == 8) S2R_DW_FWD(true, 8, 0);
-        else if (G.CG == 12) S2R_DW_FWD(true, 12, 1);
-        else S2R_DW_FWD(true, 4, 2);
+        if (halo_const) { if (oss) S2R_DW_FWD_CG(dw_s1_fwd2_kernel, true, true, 0); else S2R_DW_FWD_CG(dw_s1_fwd2_kernel, true, false, 3); }
+        else { if (oss) S2R_DW_FWD_CG(dw_s1_fwd2_kernel, false, true, 6); else S2R_DW_FWD_CG(dw_s1_fwd2_kernel, false, false, 9); }
       } else {
-        if (G.CG == 8) S2R_DW_FWD(false, 8, 3);
-        else if (G.CG == 12) S2R_DW_FWD(false, 12, 4);
-        else S2R_DW_FWD(false, 4, 5);
+        if (halo_const) { if (oss) S2R_DW_FWD_CG(dw_s1_fwd_kernel, true, true, 12); else S2R_DW_FWD_CG(dw_s1_fwd_kernel, true, false, 15); }
+        else { if (oss) S2R_DW_FWD_CG(dw_s1_fwd_kernel, false, true, 18); else S2R_DW_FWD_CG(dw_s1_fwd_kernel, false, false, 21); }
       }
+#undef S2R_DW_FWD_CG
 #undef S2R_DW_FWD
-#undef S2R_DW_FWD2
       S2R_LAUNCH_OK();
     }
   return S2R_OK;
@@ -747,9 +767,9 @@ int s2r_dw_s1_bwd(const void* dy, const void* x, const float* ss, const float* m
     if (rc) return rc;                                                                                               \
     S2R_CUDA_OK(s2r_launch(dw_s1_bwd_kernel<CG_>, grid, dim3(threads), smem, stream, dymap, xmap, ss, mi, w, (__nv_bfloat16*)g + goff, bsums, dw, G)); \
   } while (0)
-      if (G.CG == 8) S2R_DW_BWD(8, 6);
-      else if (G.CG == 12) S2R_DW_BWD(12, 7);
-      else S2R_DW_BWD(4, 8);
+      if (G.CG == 8) S2R_DW_BWD(8, 24);
+      else if (G.CG == 12) S2R_DW_BWD(12, 25);
+      else S2R_DW_BWD(4, 26);
 #undef S2R_DW_BWD
       S2R_LAUNCH_OK();
     }

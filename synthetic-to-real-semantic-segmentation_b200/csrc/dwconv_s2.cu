@@ -36,9 +36,13 @@ struct S2Maps {
 };
 
 // ------------------------------------------------------------------------------------ forward
+// OAFF (inference): y = relu6(acc*oss[c] + oss[C+c]), the BatchNorm + ReLU6 that follows the convolution with its
+// running statistics (mobilenet.py:55-56), applied before the store; no statistics in that mode.
+template <bool OAFF>
 __global__ void __launch_bounds__(F_CONS + 32, 2)
 dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss, const float* __restrict__ w,
-                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S2Geom G, const BnTail in_bn) {
+                 __nv_bfloat16* __restrict__ y, double* __restrict__ stats, const S2Geom G, const BnTail in_bn,
+                 const float* __restrict__ oss) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t bar_full[F_STAGES], bar_empty[F_STAGES];
@@ -104,6 +108,12 @@ dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
     const float2 shA = make_float2(u4.x * (1.f / 6.f), u4.y * (1.f / 6.f)), shB = make_float2(u4.z * (1.f / 6.f), u4.w * (1.f / 6.f));
     float2 wA[9], wB[9];
     load_filter(w, c, 6.f, wA, wB);
+    float2 oscA = make_float2(0.f, 0.f), oscB = oscA, oshA = oscA, oshB = oscA;   // OAFF: scale / 6, shift / 6
+    if (OAFF) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(oss + c)), p4 = __ldg(reinterpret_cast<const float4*>(oss + G.C + c));
+      oscA = make_float2(o4.x * (1.f / 6.f), o4.y * (1.f / 6.f)); oscB = make_float2(o4.z * (1.f / 6.f), o4.w * (1.f / 6.f));
+      oshA = make_float2(p4.x * (1.f / 6.f), p4.y * (1.f / 6.f)); oshB = make_float2(p4.z * (1.f / 6.f), p4.w * (1.f / 6.f));
+    }
 
     const size_t rowp = (size_t)G.Wo * G.C;
     __nv_bfloat16* yp = y + (((size_t)n * G.Ho + o0) * G.Wo + min(ow, G.Wo - 1)) * G.C + c - rowp;   // row o0-1+r at + r*rowp
@@ -135,11 +145,18 @@ dw_s2_fwd_kernel(const __grid_constant__ S2Maps M, const float* __restrict__ ss,
         curA = ffma2(rA, wA[8], ffma2(eA, wA[7], ffma2(lA, wA[6], curA)));
         curB = ffma2(rB, wB[8], ffma2(eB, wB[7], ffma2(lB, wB[6], curB)));
         if (r >= 1 && r <= rows && active) {
-          *reinterpret_cast<uint2*>(yp + (size_t)r * rowp) = pack4(curA, curB);
-          sA = fadd2(sA, curA);
-          sB = fadd2(sB, curB);
-          qA = ffma2(curA, curA, qA);
-          qB = ffma2(curB, curB, qB);
+          if (OAFF) {
+            float2 oA, oB;
+            oA.x = 6.f * __saturatef(fmaf(curA.x, oscA.x, oshA.x)); oA.y = 6.f * __saturatef(fmaf(curA.y, oscA.y, oshA.y));
+            oB.x = 6.f * __saturatef(fmaf(curB.x, oscB.x, oshB.x)); oB.y = 6.f * __saturatef(fmaf(curB.y, oscB.y, oshB.y));
+            *reinterpret_cast<uint2*>(yp + (size_t)r * rowp) = pack4(oA, oB);
+          } else {
+            *reinterpret_cast<uint2*>(yp + (size_t)r * rowp) = pack4(curA, curB);
+            sA = fadd2(sA, curA);
+            sB = fadd2(sB, curB);
+            qA = ffma2(curA, curA, qA);
+            qB = ffma2(curB, curB, qB);
+          }
         }
         curA = ffma2(rA, wA[2], ffma2(eA, wA[1], fmul2(lA, wA[0])));
         curB = ffma2(rB, wB[2], ffma2(eB, wB[1], fmul2(lB, wB[0])));
@@ -412,7 +429,8 @@ inline void s2_offsets(S2Geom* G, const int bw[5], int ntiles) {
 }  // namespace
 
 int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, const float* w, void* y, double* stats,
-                  int N, int H, int W, int C, cudaStream_t stream) {
+                  const float* oss, int N, int H, int W, int C, cudaStream_t stream) {
+  if (oss && (stats || (uintptr_t)oss % 16)) return S2R_ERR_UNSUPPORTED;   // output affine: inference only
   S2Geom G;
   G.N = N; G.H = H; G.W = W; G.C = C;
   G.Ho = (H - 1) / 2 + 1; G.Wo = (W - 1) / 2 + 1;
@@ -438,13 +456,19 @@ int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, cons
   if (smem > (size_t)S2_SMEM_CAP) return S2R_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr) {
-    S2R_CUDA_OK(cudaFuncSetAttribute(dw_s2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_CAP));
+    S2R_CUDA_OK(cudaFuncSetAttribute(dw_s2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_CAP));
+    S2R_CUDA_OK(cudaFuncSetAttribute(dw_s2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_CAP));
     attr = true;
   }
   int threads = (TW * G.CG + 31) / 32 * 32 + 32;
   if (threads < (G.CG * 12 + 31) / 32 * 32) threads = (G.CG * 12 + 31) / 32 * 32;
-  S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w, (__nv_bfloat16*)y, stats, G,
-                         bn_tail_from(in_bn)));
+  const BnTail bt = bn_tail_from(in_bn);
+  if (oss)
+    S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel<true>, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w,
+                           (__nv_bfloat16*)y, stats, G, bt, oss));
+  else
+    S2R_CUDA_OK(s2r_launch(dw_s2_fwd_kernel<false>, dim3(chunks, tiles, N * G.nseg), dim3(threads), smem, stream, M, ss, w,
+                           (__nv_bfloat16*)y, stats, G, bt, oss));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -164,6 +164,9 @@ class Ctx:
         L.require_cuda()
         self.device = device
         self.training = training
+        # inference: eval mode AND no backward pass will follow (set by runtime.ModuleFn under torch.no_grad()):
+        # BatchNorm folds into the producing kernels' epilogues and nothing is saved for a backward
+        self.inference = False
         # weight gradients are leaves of the backward pass (nothing downstream reads them before the optimizer): with
         # async_wgrad they are issued on a side stream and overlap the data-gradient chain, whose many small kernels
         # leave most SMs idle; join() orders them before whatever follows the module's backward
@@ -434,8 +437,9 @@ def conv_out_hw(H, W, R, S, stride, pad, dil):
 
 
 def conv_fwd(cx, x, w, out, stride=1, pad=0, dil=1, bias=None, act=L.ACT_NONE, slope=0.0, stats=None,
-             aux=None, aux_mode=L.AUX_NONE, force_mma=False):
-    """out = epi(conv(x, w)); x/out are Act views, w an OIHW fp32 parameter."""
+             aux=None, aux_mode=L.AUX_NONE, force_mma=False, oscale=None):
+    """out = epi(conv(x, w)); x/out are Act views, w an OIHW fp32 parameter.
+    oscale: per-output-channel fp32 scale applied to the accumulator before the bias (a folded eval-mode BatchNorm)."""
     Cout, Cin, R, S = w.shape
     assert x.C >= Cin and out.C >= Cout, (x.C, Cin, out.C, Cout)
     OH, OW = conv_out_hw(x.H, x.W, R, S, stride, pad, dil)
@@ -457,6 +461,7 @@ def conv_fwd(cx, x, w, out, stride=1, pad=0, dil=1, bias=None, act=L.ACT_NONE, s
         a.aux = aux.ptr
         a.an, a.ah, a.aw = aux.H * aux.W * aux.pitch, aux.W * aux.pitch, aux.pitch
     a.stats = stats.data_ptr() if stats is not None else None
+    a.oscale = oscale.data_ptr() if oscale is not None else None
     L.call("s2r_conv_fwd_mma" if force_mma else "s2r_conv_fwd", C.byref(a), cx.stream)
     return out
 
@@ -797,6 +802,15 @@ class ConvBNAct:
         w = self.conv.weight
         Cout = w.shape[0]
         OH, OW = conv_out_hw(x.H, x.W, w.shape[2], w.shape[3], self.stride, self.pad, self.dil)
+        if cx.inference:
+            # inference: BatchNorm with its running statistics (batchnorm.py:50-53) + activation (+ residual) are the
+            # convolution's epilogue, act(acc*scale + shift) + residual -- no pre-BN tensor, no bn_apply pass
+            st = bn_eval(cx, self.bn)
+            y = out if out is not None else cx.new(x.N, OH, OW, Cout)
+            conv_fwd(cx, x, w, y, self.stride, self.pad, self.dil, bias=st.ss[Cout:], oscale=st.ss[:Cout], act=self.act,
+                     aux=residual, aux_mode=L.AUX_ADD if residual is not None else L.AUX_NONE)
+            self.saved = None
+            return y
         z = cx.new(x.N, OH, OW, Cout)
         # count_pad: the reference ran this conv on an input padded by count_pad pixels per side
         # (mobilenet.py:62-67): the extra border outputs are exact zeros but count in the statistics
@@ -862,14 +876,16 @@ class ConvBNAct:
         return dx
 
 
-def dw_fwd(cx, x, st_in, in_act, halo_const, w, stride, dil, pad, stats):
-    """Depthwise 3x3 on act(BN(x)); st_in may still be pending: the kernel then finalises it in its prologue."""
+def dw_fwd(cx, x, st_in, in_act, halo_const, w, stride, dil, pad, stats, out_ss=None):
+    """Depthwise 3x3 on act(BN(x)); st_in may still be pending: the kernel then finalises it in its prologue.
+    out_ss (inference): scale / shift of the BatchNorm that follows; the kernel stores relu6(conv*scale + shift)."""
     Ho, Wo = conv_out_hw(x.H, x.W, 3, 3, stride, pad, dil)
     y = cx.new(x.N, Ho, Wo, x.C)
     p = st_in.take() if st_in is not None else None
     L.call("s2r_dwconv3x3_fwd_bn", x.vp(), C.byref(p) if p is not None else None,
            _vp(st_in.ss) if st_in is not None else None, in_act, 1 if halo_const else 0, _vp(w), y.vp(),
-           _vp(stats) if stats is not None else None, x.N, x.H, x.W, x.C, stride, dil, pad, cx.stream)
+           _vp(stats) if stats is not None else None, _vp(out_ss) if out_ss is not None else None,
+           x.N, x.H, x.W, x.C, stride, dil, pad, cx.stream)
     return y
 
 
@@ -903,6 +919,12 @@ class InvertedResidual:
             dw_in, st_in, halo = z1, st1, True
         else:
             dw_in, st_in, halo = x, lazy, False
+        if cx.inference:
+            # inference: BN2 + ReLU6 in the depthwise kernel's store, BN3 (+ residual) in the project conv's epilogue
+            st2 = bn_eval(cx, self.bn2)
+            y2 = dw_fwd(cx, dw_in, st_in, L.ACT_RELU6, halo, self.dw.weight, self.stride, d, d, None, out_ss=st2.ss)
+            self.saved = None
+            return self.pw2.forward(cx, y2, residual=x if self.res else None)
         Ho, Wo = conv_out_hw(dw_in.H, dw_in.W, 3, 3, self.stride, d, d)
         sums2, finish2 = bn_plan(cx, self.bn2, dw_in.N * Ho * Wo)
         z2 = dw_fwd(cx, dw_in, st_in, L.ACT_RELU6, halo, self.dw.weight, self.stride, d, d, sums2)

@@ -69,6 +69,9 @@ class ModuleFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             cx = Ctx(dev, module.training, sync_group_for(module) if module.training else None,
                      dropout=not getattr(module, "_s2r_no_dropout", False))
+            # (grad mode is always off inside Function.forward and needs_input_grad ignores it: call_module records
+            # whether the CALLER had it on)
+            cx.inference = (not module.training) and not _CALLER_GRAD[0]
             run = make_run()
             raw = getattr(run, "raw_inputs", False)
             acts = [RawNCHW(x) if raw else to_nhwc(cx, x) for x in inputs]
@@ -119,6 +122,13 @@ class RunBase:
         return to_nhwc(cx, d)
 
 
+_CALLER_GRAD = [True]
+
+
 def call_module(module, make_run, inputs):
     params = [p for p in module.parameters()]
-    return ModuleFn.apply(module, make_run, len(inputs), *inputs, *params)
+    _CALLER_GRAD[0] = torch.is_grad_enabled()
+    try:
+        return ModuleFn.apply(module, make_run, len(inputs), *inputs, *params)
+    finally:
+        _CALLER_GRAD[0] = True

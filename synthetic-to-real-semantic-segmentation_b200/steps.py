@@ -193,7 +193,9 @@ class AdaptStep(_StagedInputs):
             tgt_output = tgt_output.detach()
             loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
             loss_D_tgt.backward()
-        self.optimizer.all_reduce_grads()
+        if not getattr(self, "_g_reduced", False):
+            self.optimizer.all_reduce_grads()
+        self._g_reduced = False
         self.optimizer_D.all_reduce_grads()
         self.optimizer.launch()
         self.optimizer_D.launch()
@@ -269,6 +271,12 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
     try:
         with torch.cuda.stream(B):
             loss_adv.backward()
+            # data parallel: the generator's gradient is complete here (A's backward was waited for above), the
+            # discriminator's training passes on A do not touch it -- its all-reduce runs on B beside them instead of
+            # after them.  The discriminator's all-reduce follows on A after A has waited for B (end of this function):
+            # the two collectives of the one communicator stay in a fixed order on every rank.
+            self.optimizer.all_reduce_grads()
+            self._g_reduced = True
     finally:
         COMM_CHANNEL[0] = 0
     for p in model_D.parameters():

@@ -24,13 +24,15 @@ class _RoundBF16(torch.autograd.Function):
 
 
 @contextlib.contextmanager
-def emulate_bf16(trace=None):
-    old = (O.Q, O.TRACE)
-    O.Q, O.TRACE = _RoundBF16.apply, trace
+def emulate_bf16(trace=None, fold_eval=True):
+    """fold_eval: eval-mode BatchNorm layers are epilogues of their convolutions (the B200 inference path under
+    torch.no_grad(); oracle/ref_port.py Q_FOLD_EVAL) -- the pre-BatchNorm tensors are not rounding points."""
+    old = (O.Q, O.TRACE, O.Q_FOLD_EVAL)
+    O.Q, O.TRACE, O.Q_FOLD_EVAL = _RoundBF16.apply, trace, fold_eval
     try:
         yield
     finally:
-        O.Q, O.TRACE = old
+        O.Q, O.TRACE, O.Q_FOLD_EVAL = old
 
 
 @contextlib.contextmanager
