@@ -217,6 +217,19 @@ int s2r_bn_tail_run(const s2r_bn_tail* tail, int C, s2r_stream_t stream);
 int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* mean_invstd,
                             float* scale_shift, int C, s2r_stream_t stream);
+/* The same for many BatchNorm layers in one launch (the table lives in device memory): the inference path runs this
+ * once per forward pass and folds the scale / shift pairs into the producing kernels' epilogues. */
+typedef struct s2r_bn_eval_job {
+  const float* gamma;  /* [C] or NULL */
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float* mean_invstd;  /* out [2][C] */
+  float* scale_shift;  /* out [2][C] */
+  int32_t C;
+  float eps;
+} s2r_bn_eval_job;
+int s2r_bn_eval_multi(const s2r_bn_eval_job* jobs, int njobs, s2r_stream_t stream);
 /* y = dropout(act(x*scale + shift)) + residual.  The dropout mask is a pure function of
  * (seed + *seed_dev, element index); seed_dev (device, may be NULL) lets a captured CUDA graph
  * draw a fresh mask on every replay. */

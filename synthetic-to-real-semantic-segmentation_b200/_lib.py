@@ -32,6 +32,11 @@ class BnTail(C.Structure):
                 ("clamp_mode", i32), ("channel", i32)]
 
 
+class BnEvalJob(C.Structure):
+    _fields_ = [("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp), ("mean_invstd", vp),
+                ("scale_shift", vp), ("C", i32), ("eps", f32)]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("ntaps", i32), ("taps", Tap * S2R_MAX_TAPS),
                 ("N", i32), ("OH", i32), ("OW", i32), ("Cin", i32), ("Cout", i32),
@@ -106,6 +111,7 @@ PROTOTYPES = {
     "s2r_channel_sums_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "s2r_bn_finalize": [vp, f64, vp, vp, f32, i32, f32, vp, vp, vp, vp, i32, vp],
     "s2r_bn_tail_run": [C.POINTER(BnTail), i32, vp],
+    "s2r_bn_eval_multi": [vp, i32, vp],
     "s2r_bn_eval_scale_shift": [vp, vp, vp, vp, f32, vp, vp, i32, vp],
     "s2r_bn_apply_act": [vp, i64, i32, i32, i32, vp, i32, vp, f32, u64, vp, vp, i32, i32, vp],
     "s2r_bn_apply_act_bn": [vp, i64, i32, i32, i32, C.POINTER(BnTail), vp, i32, vp, f32, u64, vp, vp, i32, i32, vp],

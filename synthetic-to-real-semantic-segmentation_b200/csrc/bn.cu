@@ -146,6 +146,23 @@ __global__ void bn_eval_kernel(const float* __restrict__ gamma, const float* __r
   scale_shift[C + c] = b - rm[c] * sc;
 }
 
+// eval mode, every BatchNorm layer of a model in ONE launch (blockIdx.y = layer): the inference path folds these
+// scale / shift pairs into the producing kernels' epilogues, so this is the only BatchNorm launch of a forward pass
+__global__ void bn_eval_multi_kernel(const s2r_bn_eval_job* __restrict__ jobs) {
+  pdl_wait();
+  pdl_trigger();
+  const s2r_bn_eval_job j = jobs[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.C; c += gridDim.x * blockDim.x) {
+    const float invstd = rsqrtf(j.running_var[c] + j.eps);
+    const float g = j.gamma ? j.gamma[c] : 1.f, b = j.beta ? j.beta[c] : 0.f;
+    const float sc = g * invstd;
+    j.mean_invstd[c] = j.running_mean[c];
+    j.mean_invstd[j.C + c] = invstd;
+    j.scale_shift[c] = sc;
+    j.scale_shift[j.C + c] = b - j.running_mean[c] * sc;
+  }
+}
+
 // Per-thread channel constants: a thread owns one group of 8 channels for its whole lifetime, so the
 // per-channel parameters are loaded once into registers (no per-element division or parameter loads).
 struct ChanConst {
@@ -672,6 +689,15 @@ extern "C" int s2r_bn_eval_scale_shift(const float* gamma, const float* beta, co
   S2R_REQUIRE(C >= 1, S2R_ERR_SHAPE, "bn_eval: C=%d", C);
   S2R_CUDA_OK(s2r_launch(bn_eval_kernel, dim3(s2r_div_up(C, 128)), dim3(128), (size_t)0, (cudaStream_t)stream, 
       gamma, beta, running_mean, running_var, eps, mean_invstd, scale_shift, C));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_bn_eval_multi(const s2r_bn_eval_job* jobs, int njobs, s2r_stream_t stream) {
+  S2R_REQUIRE(njobs >= 0 && njobs <= 65535, S2R_ERR_SHAPE, "bn_eval_multi: %d jobs", njobs);
+  if (njobs == 0) return S2R_OK;
+  S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "bn_eval_multi: null table");
+  S2R_CUDA_OK(s2r_launch(bn_eval_multi_kernel, dim3(2, njobs), dim3(256), (size_t)0, (cudaStream_t)stream, jobs));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

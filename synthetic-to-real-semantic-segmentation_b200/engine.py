@@ -167,6 +167,7 @@ class Ctx:
         # inference: eval mode AND no backward pass will follow (set by runtime.ModuleFn under torch.no_grad()):
         # BatchNorm folds into the producing kernels' epilogues and nothing is saved for a backward
         self.inference = False
+        self.eval_states = None   # inference: {id(bn): BNState} filled by bn_eval_all (one launch for all layers)
         # weight gradients are leaves of the backward pass (nothing downstream reads them before the optimizer): with
         # async_wgrad they are issued on a side stream and overlap the data-gradient chain, whose many small kernels
         # leave most SMs idle; join() orders them before whatever follows the module's backward
@@ -696,7 +697,44 @@ def bn_finalize(cx, bn, sums, count_local):
     return BNState(ss, mi, count, False)
 
 
+def bn_eval_all(cx, module):
+    """Inference: scale / shift of EVERY BatchNorm layer of `module` from its running statistics in one launch
+    (s2r_bn_eval_multi); bn_eval() then hands out the per-layer states.  The job table and the output buffers are
+    built once per module (they hold raw pointers to the parameters / buffers: rebuilt when those move) and live on the
+    module; the launch is repeated on every forward pass, so a captured graph always sees the current statistics.
+    Several streams may run it at once on the same buffers (validation graph lanes): they write identical values."""
+    bns = [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    if not bns:
+        return
+    sig = tuple(t.data_ptr() for m in bns for t in (m.weight, m.bias, m.running_mean, m.running_var))
+    ent = getattr(module, "_s2r_eval_tab", None)
+    if ent is None or ent[0] != sig:
+        if torch.cuda.is_current_stream_capturing():
+            return          # table upload is a host->device copy: per-layer bn_eval launches in this capture
+        total = sum(2 * m.num_features for m in bns)
+        buf = torch.empty(2 * total, dtype=torch.float32, device=cx.device)
+        arr = (L.BnEvalJob * len(bns))()
+        states, off = {}, 0
+        for i, m in enumerate(bns):
+            Cc = m.num_features
+            mi, ss = buf[off:off + 2 * Cc], buf[total + off:total + off + 2 * Cc]
+            off += 2 * Cc
+            j = arr[i]
+            j.gamma, j.beta = m.weight.data_ptr(), m.bias.data_ptr()
+            j.running_mean, j.running_var = m.running_mean.data_ptr(), m.running_var.data_ptr()
+            j.mean_invstd, j.scale_shift, j.C, j.eps = mi.data_ptr(), ss.data_ptr(), Cc, float(m.eps)
+            states[id(m)] = BNState(ss, mi, 0.0, True)
+        tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(cx.device)
+        ent = (sig, tab, len(bns), states, buf)
+        module._s2r_eval_tab = ent
+    L.call("s2r_bn_eval_multi", _vp(ent[1]), ent[2], cx.stream)
+    cx.eval_states = ent[3]
+
+
 def bn_eval(cx, bn):
+    pre = cx.eval_states.get(id(bn)) if cx.eval_states is not None else None
+    if pre is not None:
+        return pre
     Cc = bn.num_features
     ss = cx.f32(2 * Cc, zero=False)
     mi = cx.f32(2 * Cc, zero=False)

@@ -10,7 +10,7 @@ accumulates parameter gradients straight into `.grad`.
 import torch
 
 from . import _lib as L
-from .engine import Ctx, RawNCHW, round_up, _vp
+from .engine import Ctx, RawNCHW, round_up, _vp, bn_eval_all
 
 
 def init_reference_weights(module):
@@ -72,6 +72,8 @@ class ModuleFn(torch.autograd.Function):
             # (grad mode is always off inside Function.forward and needs_input_grad ignores it: call_module records
             # whether the CALLER had it on)
             cx.inference = (not module.training) and not _CALLER_GRAD[0]
+            if cx.inference:
+                bn_eval_all(cx, module)
             run = make_run()
             raw = getattr(run, "raw_inputs", False)
             acts = [RawNCHW(x) if raw else to_nhwc(cx, x) for x in inputs]
