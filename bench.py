@@ -322,9 +322,9 @@ def dominant_kernel_roofline(torch, batch, h, w, peaks):
     """decoder.last_conv.0: 3x3 304->256 on [B, H/4, W/4] (45.9 GF/img forward), the
     largest single kernel of the step; timed alone with CUDA events, L2 flushed between launches."""
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 8, 512x1024 from the committed
-    # ncu --set full capture (profiles/r1s_conv_tc_decoder_ncu.txt: 161.1 MB read + 95.2 MB written -- part of the
+    # ncu --set full capture (profiles/r2_conv_tc_decoder_ncu.txt: 161.2 MB read + 94.3 MB written -- part of the
     # 134 MB output is still in the 126 MB L2 when the kernel ends; algorithmic 159 + 134 = 293 MB)
-    traffic = 256.3e6 if (batch, h, w) == (8, 512, 1024) else None
+    traffic = 255.5e6 if (batch, h, w) == (8, 512, 1024) else None
     return conv_roofline(torch, peaks, "tap-GEMM conv fwd 3x3 304->256 (decoder.last_conv.0)", batch, h // 4, w // 4, 304,
                          256, 3, 1, traffic)
 
