@@ -428,6 +428,23 @@ inline void s2_offsets(S2Geom* G, const int bw[5], int ntiles) {
 
 }  // namespace
 
+// Rows per CTA for a grid of `per_row_seg` CTAs per row segment on `slots` resident CTA slots: the kernel runs in
+// ceil(CTAs / slots) waves of (rs + 1 halo + ~3 rows of prologue / reduction) row steps each; rs + 1 is a multiple of
+// the stage depth RB so that no loaded row is wasted.  (The first version doubled the segment count until the grid had
+// four CTAs per SM, which leaves e.g. 1.3 waves of work on 2 waves of time.)
+static int s2_pick_rows(int rows_total, long per_row_seg, long slots) {
+  long best = -1;
+  int best_rs = RB - 1;
+  for (int rs = RB + RB - 1; ; rs += RB) {       // 5, 8, 11, ...
+    const long nsg = (rows_total + rs - 1) / rs;
+    const long waves = (per_row_seg * nsg + slots - 1) / slots;
+    const long cost = waves * (rs + 4);
+    if (best < 0 || cost < best || (cost == best && rs > best_rs)) { best = cost; best_rs = rs; }
+    if (rs >= rows_total) break;
+  }
+  return best_rs;
+}
+
 int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, const float* w, void* y, double* stats,
                   const float* oss, int N, int H, int W, int C, cudaStream_t stream) {
   if (oss && (stats || (uintptr_t)oss % 16)) return S2R_ERR_UNSUPPORTED;   // output affine: inference only
@@ -441,10 +458,7 @@ int s2r_dw_s2_fwd(const void* x, const float* ss, const s2r_bn_tail* in_bn, cons
   TW = s2r_div_up(G.Wo, tiles);
   G.TW = TW;
   const int chunks = C / (G.CG * 4);
-  int nseg = s2r_div_up(G.Ho, 64);
-  while ((long)chunks * tiles * N * nseg < 4L * s2r_sm_count() && G.Ho / (nseg * 2) >= 16) nseg *= 2;
-  int rs = s2r_div_up(G.Ho, nseg);
-  rs = (rs + 1 + RB - 1) / RB * RB - 1;
+  const int rs = s2_pick_rows(G.Ho, (long)chunks * tiles * N, 2L * s2r_sm_count());
   G.rs = rs; G.nseg = s2r_div_up(G.Ho, rs);
   if ((long)N * G.nseg > 65535) return S2R_ERR_UNSUPPORTED;
   const int bw[5] = {TW, TW + 1, TW, TW + 1, 0};
@@ -487,10 +501,7 @@ int s2r_dw_s2_bwd(const void* dy, const void* x, const float* ss, const float* m
   TW = s2r_div_up(nJ, tiles);
   G.TW = TW;
   const int chunks = C / (G.CG * 4);
-  int nseg = s2r_div_up(nI, 64);
-  while ((long)chunks * tiles * N * nseg < 4L * s2r_sm_count() && nI / (nseg * 2) >= 16) nseg *= 2;
-  int rs = s2r_div_up(nI, nseg);
-  rs = (rs + 1 + RB - 1) / RB * RB - 1;
+  const int rs = s2_pick_rows(nI, (long)chunks * tiles * N, 1L * s2r_sm_count());
   G.rs = rs; G.nseg = s2r_div_up(nI, rs);
   if ((long)N * G.nseg > 65535) return S2R_ERR_UNSUPPORTED;
   const int bw[5] = {TW, TW, TW, TW, TW + 1};
