@@ -30,8 +30,12 @@ inline RowReduceCfg row_reduce_cfg(long long P, int C) {
   c.rows = 256 / c.cg;
   if (c.rows < 1) c.rows = 1;
   c.threads = c.cg * c.rows;
-  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);  // >= 8 rows per thread
-  long long cap = (long long)s2r_sm_count() * 4;
+  // >= 8 rows per thread; one wave of CTAs: three per SM (the kernels' launch bound) on the large tensors, ONE per SM
+  // on the small ones, where the fp64 atomics of the final reduction -- every CTA adds into the same 2*C addresses --
+  // are the tail (measured, tests/tools/bn_bench.py: 16384x384 10.5 -> 7.4 us, 65536x192 15.0 -> 10.3 us,
+  // 1048576x96 80.4 -> 65.4 us = 0.94 of the copy peak)
+  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);
+  long long cap = (long long)s2r_sm_count() * (P * (long long)C >= 24LL * 1024 * 1024 ? 3 : 1);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   c.grid = (int)blocks;
@@ -643,8 +647,10 @@ inline ElemCfg elem_cfg(long long P, int C) {
   c.rows = 256 / cg;
   if (c.rows < 1) c.rows = 1;
   c.threads = c.rows * cg;
-  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);  // >= 8 rows per thread (two full batches)
-  const long long cap = (long long)s2r_sm_count() * 8;
+  // >= 8 rows per thread (two full batches); 16 CTAs per SM on the large tensors, 8 on the small ones, where every
+  // CTA's prologue (channel constants, a pending BatchNorm's finalize) weighs more (tests/tools/bn_bench.py)
+  long long blocks = (P + (long long)c.rows * 8 - 1) / ((long long)c.rows * 8);
+  const long long cap = (long long)s2r_sm_count() * (P * (long long)C >= 24LL * 1024 * 1024 ? 16 : 8);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   c.grid = (int)blocks;
