@@ -624,6 +624,10 @@ def run_adapt(args):
                    "streams": "two pass chains (G(src) fwd/bwd + D training | G(tgt) fwd + adversarial bwd) and one "
                               "weight-gradient side stream per chain, all inside the one graph"
                               if os.environ.get("S2R_OVERLAP", "1") != "0" else "one",
+                   "discriminator_forward_on_target": ("evaluated once per step and shared by the adversarial pass "
+                                                       "(train_adapt.py:151) and the discriminator's training pass (:174): same "
+                                                       "tensor, same weights, identical values and gradients"
+                                                       if os.environ.get("S2R_SHARE_D_FWD", "1") != "0" else "evaluated twice"),
                    "bn_exchange": ("nvlink peer memory (csrc/comm.cu)" if sub("engine").PEER["world"] == world else "nccl")
                    if world > 1 else "none",
                    "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush",

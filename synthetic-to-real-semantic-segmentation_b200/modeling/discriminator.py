@@ -60,22 +60,25 @@ class FCDiscriminatorRun(RunBase):
         self.acts = acts
         return h
 
-    def backward(self, cx, douts, need=None):
+    def backward(self, cx, douts, need=None, wgrad=True, keep=False):
+        """wgrad=False: data gradients only (the discriminator frozen); keep=True: the saved activations stay for a
+        second backward pass over the same forward (FCDiscriminator.forward_softmax0_shared)."""
         d = douts[0] if isinstance(douts, tuple) else douts
         acts = self.acts
-        self.acts = None
+        if not keep:
+            self.acts = None
         need_dx = True if need is None else bool(need[0])
         for i in range(len(self.convs) - 1, -1, -1):
             c = self.convs[i]
             xin = acts[i]
-            if c.weight.requires_grad:
+            if wgrad and c.weight.requires_grad:
                 if i == 0 and self.rowtap:
                     rowtap_wgrad(cx, xin, d, c.weight)
                 elif i == 0:
                     conv_wgrad(cx, xin, d, patch_weight(c.weight), grad_param=c.weight)
                 else:
                     conv_wgrad(cx, xin, d, c.weight, stride=2, pad=1)
-            if c.bias is not None and c.bias.requires_grad:
+            if wgrad and c.bias is not None and c.bias.requires_grad:
                 bias_grad(cx, d, c.bias)
             if i == 0 and not need_dx:
                 return None
@@ -86,7 +89,8 @@ class FCDiscriminatorRun(RunBase):
                 dx = torch.empty((N, Cc, H, W), dtype=torch.float32, device=cx.device)
                 L.call("s2r_softmax0_nhwc_pad_bwd", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
                        1 if self.softmax0 else 0, _vp(dx), cx.stream)
-                self.logits = None
+                if not keep:
+                    self.logits = None
                 return dx
             if i == 0:
                 N, H, W, Cc = self.in_shape   # gradient w.r.t. the input pixels: the ordinary 4x4 data gradient
@@ -100,6 +104,78 @@ class FCDiscriminatorRun(RunBase):
                        aux_mode=L.AUX_LEAKY_MASK if i > 0 else L.AUX_NONE, slope=self.slope)
             d = dx
         return d
+
+
+class _SharedForward(object):
+    """One evaluation of the discriminator whose saved activations serve two backward passes."""
+
+    def __init__(self):
+        self.run, self.out, self.pending = None, None, 2
+
+    def done(self):
+        self.pending -= 1
+        if self.pending <= 0 and self.run is not None:
+            self.run.acts = None
+            self.run.logits = None
+            self.run = None
+
+
+class _SharedInputFn(torch.autograd.Function):
+    """out = D(softmax0(logits)) with the discriminator FROZEN: the gradient goes to the logits only."""
+
+    @staticmethod
+    def forward(ctx, module, holder, logits):
+        from ..engine import Ctx, RawNCHW
+        from ..runtime import to_nchw
+        dev = logits.device
+        if dev.type != "cuda":
+            raise L.S2RError("s2r_b200 modules run on CUDA tensors only (got %s); there is no CPU path" % dev)
+        with torch.cuda.device(dev):
+            cx = Ctx(dev, module.training, None)
+            run = FCDiscriminatorRun(module, softmax0=True)
+            out = run.export(cx, 0, run.forward(cx, RawNCHW(logits)))
+        # (a detached alias: `out` itself gets this node as its grad_fn, and holder -> out -> grad_fn -> ctx -> holder
+        # would be a reference cycle that only the garbage collector frees)
+        holder.run, holder.out = run, out.detach()
+        ctx.holder, ctx.module, ctx.dev = holder, module, dev
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..engine import Ctx
+        h = ctx.holder
+        res = None
+        if dout is not None and ctx.needs_input_grad[2]:
+            with torch.cuda.device(ctx.dev):
+                cx = Ctx(ctx.dev, True, None, dropout=False, async_wgrad=True)
+                res = h.run.backward(cx, (h.run.import_grad(cx, 0, dout),), (True,), wgrad=False, keep=True)
+                cx.join()
+        h.done()
+        return None, None, res
+
+
+class _SharedParamFn(torch.autograd.Function):
+    """The same output values as a function of the discriminator's PARAMETERS only (the input detached): the backward
+    pass accumulates the parameter gradients from the activations the shared forward saved."""
+
+    @staticmethod
+    def forward(ctx, module, holder, *params):
+        ctx.holder, ctx.module, ctx.dev = holder, module, holder.out.device
+        ctx.set_materialize_grads(False)
+        return holder.out.detach().clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..engine import Ctx
+        h = ctx.holder
+        if dout is not None:
+            with torch.cuda.device(ctx.dev):
+                cx = Ctx(ctx.dev, True, None, dropout=False, async_wgrad=True)
+                h.run.backward(cx, (h.run.import_grad(cx, 0, dout),), (False,), wgrad=True, keep=True)
+                cx.join()
+        h.done()
+        return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
 class FCDiscriminator(nn.Module):
@@ -119,3 +195,18 @@ class FCDiscriminator(nn.Module):
         """`self(F.softmax(logits, dim=0))` -- the call train_adapt.py:151,166,174 makes -- with the batch-axis
         softmax (and its backward) fused into the input stage: the fp32 softmax tensor is never materialised."""
         return call_module(self, lambda: FCDiscriminatorRun(self, softmax0=True), (logits,))
+
+    def forward_softmax0_shared(self, logits):
+        """The adversarial pass and the discriminator's training pass on the target prediction evaluate
+        `self(F.softmax(x, dim=0))` on the SAME tensor with the SAME weights (train_adapt.py:151 and :174; the
+        discriminator is only updated at :181): one evaluation serves both.  Returns (frozen, attach):
+          frozen  -- the output as a function of `logits` with the discriminator frozen (train_adapt.py:140-141,151-155:
+                     its backward is the data-gradient chain down to the logits, no parameter gradients);
+          attach  -- a callable returning the same values as a function of the discriminator's parameters with the
+                     input detached (train_adapt.py:159,173-178: its backward accumulates the parameter gradients).
+                     Call it on the stream the training pass should run on.
+        Values and gradients are those of the two separate calls (the forward kernels are deterministic)."""
+        holder = _SharedForward()
+        frozen = _SharedInputFn.apply(self, holder, logits)
+        params = [p for p in self.parameters()]
+        return frozen, (lambda: _SharedParamFn.apply(self, holder, *params))

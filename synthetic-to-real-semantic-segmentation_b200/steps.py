@@ -56,6 +56,15 @@ def check_peer_exchange():
                               "one channel) or S2R_COMM=nccl" % e)
 
 
+def _shared_d_forward(model_D, logits):
+    """model_D.forward_softmax0_shared when the fused input stage covers the shape (and S2R_SHARE_D_FWD != 0), else None."""
+    fn = getattr(model_D, "forward_softmax0_shared", None)
+    if (fn is None or os.environ.get("S2R_SHARE_D_FWD", "1") == "0" or logits.dim() != 4 or logits.shape[0] > 8
+            or logits.shape[1] > 64 or logits.shape[2] % 2 or logits.shape[3] % 2):
+        return None
+    return fn
+
+
 def _disc_on_softmax0(model_D, logits):
     """model_D(F.softmax(logits, dim=0)) (train_adapt.py:151,166,174); the discriminator's fused input stage
     when it covers the shape, the two separate calls otherwise."""
@@ -181,7 +190,13 @@ class AdaptStep(_StagedInputs):
             loss_seg = self.criterion(src_output, src_label)
             _backward_ce_deferred(loss_seg, model)
             tgt_output = model(tgt_image)
-            D_out = _disc_on_softmax0(model_D, tgt_output)
+            shared = _shared_d_forward(model_D, tgt_output)
+            if shared is not None:
+                # D(softmax(tgt_output)) is evaluated ONCE for the adversarial pass (:151) and the discriminator's
+                # training pass (:174): same tensor, same weights (FCDiscriminator.forward_softmax0_shared)
+                D_out, attach_tgt = shared(tgt_output)
+            else:
+                D_out, attach_tgt = _disc_on_softmax0(model_D, tgt_output), None
             loss_adv = bce_with_logits(D_out, self.source_label)
             loss_adv.backward()
             # ---- train D (train_adapt.py:160-178)
@@ -191,7 +206,8 @@ class AdaptStep(_StagedInputs):
             loss_D_src = bce_with_logits(_disc_on_softmax0(model_D, src_output), self.source_label)
             loss_D_src.backward()
             tgt_output = tgt_output.detach()
-            loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
+            D_tgt = attach_tgt() if attach_tgt is not None else _disc_on_softmax0(model_D, tgt_output)
+            loss_D_tgt = bce_with_logits(D_tgt, self.target_label)
             loss_D_tgt.backward()
         if not getattr(self, "_g_reduced", False):
             self.optimizer.all_reduce_grads()
@@ -238,7 +254,11 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
     try:
         with torch.cuda.stream(B):
             tgt_output = model(tgt_image)
-            D_out = _disc_on_softmax0(model_D, tgt_output)
+            shared = _shared_d_forward(model_D, tgt_output)
+            if shared is not None:
+                D_out, attach_tgt = shared(tgt_output)     # one evaluation for the adversarial AND the training pass
+            else:
+                D_out, attach_tgt = _disc_on_softmax0(model_D, tgt_output), None
             loss_adv = bce_with_logits(D_out, self.source_label)
             fwd_B = torch.cuda.Event()
             fwd_B.record(B)
@@ -285,7 +305,8 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
         Cs.wait_event(fwd_B)
         with torch.cuda.stream(Cs):
             tgt_det = tgt_output.detach()
-            loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_det), self.target_label)
+            D_tgt = attach_tgt() if attach_tgt is not None else _disc_on_softmax0(model_D, tgt_det)
+            loss_D_tgt = bce_with_logits(D_tgt, self.target_label)
             loss_D_tgt.backward()
         A.wait_stream(Cs)
         A.wait_stream(B)
@@ -295,7 +316,8 @@ def _adapt_passes_two_streams(self, src_image, src_label, tgt_image):
     loss_D_src.backward()
     A.wait_event(fwd_B)
     tgt_output = tgt_output.detach()
-    loss_D_tgt = bce_with_logits(_disc_on_softmax0(model_D, tgt_output), self.target_label)
+    D_tgt = attach_tgt() if attach_tgt is not None else _disc_on_softmax0(model_D, tgt_output)
+    loss_D_tgt = bce_with_logits(D_tgt, self.target_label)
     loss_D_tgt.backward()
     A.wait_stream(B)
     return loss_seg, loss_adv, loss_D_src, loss_D_tgt

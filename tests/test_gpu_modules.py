@@ -248,6 +248,48 @@ def test_discriminator_vs_fixture(built_lib):
     assert all(p.grad is None or float(p.grad.abs().sum()) == 0.0 for p in D.parameters())
 
 
+def test_discriminator_shared_forward_equals_the_two_separate_calls(built_lib):
+    """train_adapt.py:151 (adversarial pass, discriminator frozen) and :174 (training pass, input detached) evaluate
+    model_D(F.softmax(tgt_output, dim=0)) on the same tensor with the same weights; forward_softmax0_shared evaluates
+    it once.  Values bit-identical, gradient w.r.t. the logits bit-identical (no atomics on that chain), parameter
+    gradients equal to the separate call up to the order of the weight-gradient atomics."""
+    fn = sub("functional")
+    torch.manual_seed(5)
+    D = sub("modeling.discriminator").FCDiscriminator(num_classes=19).cuda().train()
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(4, 19, 64, 96, generator=g).cuda()
+    # the two separate calls
+    for p in D.parameters():
+        p.requires_grad = False
+    la = logits.clone().requires_grad_(True)
+    out_a = D.forward_softmax0(la)
+    fn.bce_with_logits(out_a, 0).backward()
+    for p in D.parameters():
+        p.requires_grad = True
+    out_b = D.forward_softmax0(logits.clone())
+    fn.bce_with_logits(out_b, 1).backward()
+    torch.cuda.synchronize()
+    ref_dlogits = la.grad.clone()
+    ref_grads = {k: p.grad.clone() for k, p in D.named_parameters()}
+    D.zero_grad(set_to_none=True)
+    # one shared evaluation
+    for p in D.parameters():
+        p.requires_grad = False
+    ls = logits.clone().requires_grad_(True)
+    frozen, attach = D.forward_softmax0_shared(ls)
+    fn.bce_with_logits(frozen, 0).backward()
+    assert all(p.grad is None for p in D.parameters())           # the frozen pass leaves the parameters alone
+    for p in D.parameters():
+        p.requires_grad = True
+    out_d = attach()
+    fn.bce_with_logits(out_d, 1).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(frozen.detach(), out_a.detach()) and torch.equal(out_d.detach(), out_b.detach())
+    assert torch.equal(ls.grad, ref_dlogits)
+    for k, p in D.named_parameters():
+        assert rel(p.grad, ref_grads[k]) <= 1e-5, (k, rel(p.grad, ref_grads[k]))
+
+
 def test_domain_classifier_vs_fixture(built_lib):
     fix = golden('domain_classifier')
     torch.manual_seed(4)
