@@ -247,12 +247,6 @@ tap_fwd_kernel(const __grid_constant__ FwdParams p) {
           if (c0) v0 += __ldg(p.bias + co);
           if (c1) v1 += __ldg(p.bias + co + 1);
         }
-        if (mok) {
-          csum[ni][0] += v0;
-          csum[ni][1] += v1;
-          csq[ni][0] += v0 * v0;
-          csq[ni][1] += v1 * v1;
-        }
         if (!mok || !c0) continue;
         if (p.aux_mode == S2R_AUX_LEAKY_MASK) {
           const float a0 = __bfloat162float(arow[co]);
@@ -266,6 +260,13 @@ tap_fwd_kernel(const __grid_constant__ FwdParams p) {
             if (c1) v1 += __bfloat162float(arow[co + 1]);
           }
         }
+        // statistics of the STORED values (after activation / auxiliary operand, rounded to bf16), like conv_tc.cu
+        v0 = __bfloat162float(__float2bfloat16(v0));
+        v1 = c1 ? __bfloat162float(__float2bfloat16(v1)) : 0.f;
+        csum[ni][0] += v0;
+        csum[ni][1] += v1;
+        csq[ni][0] += v0 * v0;
+        csq[ni][1] += v1 * v1;
         if (c1 && ((reinterpret_cast<uintptr_t>(orow + co) & 3) == 0)) {
           *reinterpret_cast<__nv_bfloat162*>(orow + co) = __floats2bfloat162_rn(v0, v1);
         } else {

@@ -468,8 +468,10 @@ def conv_fwd(cx, x, w, out, stride=1, pad=0, dil=1, bias=None, act=L.ACT_NONE, s
 
 
 def conv_dgrad(cx, dy, w, dx, stride=1, pad=0, dil=1, aux=None, aux_mode=L.AUX_NONE, slope=0.0,
-               force_mma=False):
-    """dx = conv_transpose(dy, w) written per input-parity class; dx is an Act [N,H,W,>=Cin]."""
+               force_mma=False, stats=None):
+    """dx = conv_transpose(dy, w) written per input-parity class; dx is an Act [N,H,W,>=Cin].
+    stats (fp64 [2][Cin], zeroed): += per-channel sum / sum of squares of the stored dx (all parity classes add into
+    it) -- the bias gradient of the layer below without a pass of its own."""
     Cout, Cin, R, S = w.shape
     assert dy.pitch - dy.off >= round_up(Cout, 8) and dx.C >= Cin
     wp, Cin_pad, Kpad = packed_weight(cx, w, True)
@@ -503,7 +505,7 @@ def conv_dgrad(cx, dy, w, dx, stride=1, pad=0, dil=1, aux=None, aux_mode=L.AUX_N
             if aux is not None:
                 a.aux = aux.ptr + 2 * (ph * W + pw) * aux.pitch
                 a.an, a.ah, a.aw = H * W * aux.pitch, stride * W * aux.pitch, stride * aux.pitch
-            a.stats = None
+            a.stats = stats.data_ptr() if stats is not None else None
             L.call("s2r_conv_fwd_mma" if force_mma else "s2r_conv_fwd", C.byref(a), cx.stream)
     return dx
 
@@ -645,12 +647,14 @@ def rowtap_dgrad(cx, dy, w, H, W):
     return dxp
 
 
-def bias_grad(cx, dy, b):
-    """b.grad += per-channel sum of dy."""
-    Cc = round_up(b.numel(), 8)
-    sums = cx.f64(2 * Cc)
-    L.call("s2r_channel_sums_bf16", dy.vp(), dy.P, Cc, dy.pitch, 0, _vp(sums), cx.stream)
-    L.call("s2r_add_f64_to_f32", _vp(sums), _vp(grad_of(b)), b.numel(), cx.stream)
+def bias_grad(cx, dy, b, presummed=None):
+    """b.grad += per-channel sum of dy.  presummed: fp64 sums the kernel that produced dy has already left
+    (conv_dgrad(stats=...)): no pass over dy."""
+    if presummed is None:
+        Cc = round_up(b.numel(), 8)
+        presummed = cx.f64(2 * Cc)
+        L.call("s2r_channel_sums_bf16", dy.vp(), dy.P, Cc, dy.pitch, 0, _vp(presummed), cx.stream)
+    L.call("s2r_add_f64_to_f32", _vp(presummed), _vp(grad_of(b)), b.numel(), cx.stream)
 
 
 # --------------------------------------------------------------------------- batch norm

@@ -68,6 +68,7 @@ class FCDiscriminatorRun(RunBase):
         if not keep:
             self.acts = None
         need_dx = True if need is None else bool(need[0])
+        dsums = None    # per-channel sums of d left by the data-gradient launch that produced it (bias gradient)
         for i in range(len(self.convs) - 1, -1, -1):
             c = self.convs[i]
             xin = acts[i]
@@ -79,7 +80,7 @@ class FCDiscriminatorRun(RunBase):
                 else:
                     conv_wgrad(cx, xin, d, c.weight, stride=2, pad=1)
             if wgrad and c.bias is not None and c.bias.requires_grad:
-                bias_grad(cx, d, c.bias)
+                bias_grad(cx, d, c.bias, presummed=dsums)
             if i == 0 and not need_dx:
                 return None
             if i == 0 and self.rowtap:
@@ -99,9 +100,13 @@ class FCDiscriminatorRun(RunBase):
             else:
                 dx = cx.new(xin.N, xin.H, xin.W, xin.pitch)
                 dx.C = xin.C
-            # dz_{i-1} = dgrad * leaky'(y_{i-1}); the first layer's input has no activation
+            # dz_{i-1} = dgrad * leaky'(y_{i-1}); the first layer's input has no activation.  When the layer below
+            # needs its bias gradient, the epilogue of this launch leaves the per-channel sums of dz_{i-1}
+            below = self.convs[i - 1] if i > 0 else None
+            want = wgrad and below is not None and below.bias is not None and below.bias.requires_grad
+            dsums = cx.f64(2 * dx.C) if (want and dx.C <= 1024 and dx.C % 8 == 0) else None
             conv_dgrad(cx, d, c.weight, dx, stride=2, pad=1, aux=xin if i > 0 else None,
-                       aux_mode=L.AUX_LEAKY_MASK if i > 0 else L.AUX_NONE, slope=self.slope)
+                       aux_mode=L.AUX_LEAKY_MASK if i > 0 else L.AUX_NONE, slope=self.slope, stats=dsums)
             d = dx
         return d
 
