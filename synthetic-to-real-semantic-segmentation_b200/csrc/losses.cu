@@ -178,6 +178,95 @@ ce_kernel(const float* __restrict__ logits, const float* __restrict__ target, in
   }
 }
 
+// The same for C <= CMAX classes (19 on this path) with the 4-pixel logit vectors of ALL classes held in registers:
+// the C loads of a pixel group are issued back to back (the generic kernel's runtime class loop serialises load ->
+// exp -> load), the maximum is taken first (no rescaling branch in the exp chain), and the gradient is computed from the
+// registers instead of a second read of the logits.
+template <int CMAX>
+__global__ void __launch_bounds__(kThreads)
+ce_regs_kernel(const float* __restrict__ logits, const float* __restrict__ target, int const_target,
+               const float* __restrict__ weight, int C, long long HW, long long npix, int ignore_index,
+               double* __restrict__ sums, float* __restrict__ grad) {
+  pdl_wait();
+  pdl_trigger();
+  float loss_acc = 0.f, w_acc = 0.f, hit_acc = 0.f;
+  const long long nvec = npix / 4;
+  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < nvec; q += (long long)gridDim.x * kThreads) {
+    const long long i = q * 4;
+    const long long img = i / HW, px = i - img * HW;
+    const float* base = logits + img * (long long)C * HW + px;
+    float4 x[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      x[c] = c < C ? __ldg(reinterpret_cast<const float4*>(base + (long long)c * HW)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float tv[4];
+    if (target) *reinterpret_cast<float4*>(tv) = __ldg(reinterpret_cast<const float4*>(target + i));
+    int tcls[4];
+    bool valid[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const long long t = target ? (long long)tv[v] : (long long)const_target;
+      valid[v] = (t != ignore_index) && t >= 0 && t < C;
+      tcls[v] = valid[v] ? (int)t : 0;
+      if (!valid[v] && t != ignore_index) loss_acc = __int_as_float(0x7fc00000);   // see ce_kernel
+    }
+    float mx[4], s[4] = {0.f, 0.f, 0.f, 0.f}, xt[4] = {0.f, 0.f, 0.f, 0.f};
+    int arg[4] = {0, 0, 0, 0};
+    mx[0] = x[0].x; mx[1] = x[0].y; mx[2] = x[0].z; mx[3] = x[0].w;
+#pragma unroll
+    for (int c = 1; c < CMAX; ++c) {
+      const float t[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (t[v] > mx[v]) { mx[v] = t[v]; arg[v] = c; }     // first maximum, like the generic kernel
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      float t[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (c == tcls[v]) xt[v] = t[v];
+        t[v] = __expf(t[v] - mx[v]);     // exp(-inf) = 0 for the classes past C
+        s[v] += t[v];
+      }
+      x[c] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    float wt[4], inv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float lse = mx[v] + __logf(s[v]);
+      wt[v] = valid[v] ? (weight ? __ldg(weight + tcls[v]) : 1.f) : 0.f;
+      loss_acc += wt[v] * (lse - xt[v]);
+      w_acc += wt[v];
+      hit_acc += (valid[v] && arg[v] == tcls[v]) ? 1.f : 0.f;
+      inv[v] = wt[v] / s[v];
+    }
+    if (grad) {
+      float* gbase = grad + img * (long long)C * HW + px;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          float4 g;
+          g.x = x[c].x * inv[0] - (c == tcls[0] ? wt[0] : 0.f);
+          g.y = x[c].y * inv[1] - (c == tcls[1] ? wt[1] : 0.f);
+          g.z = x[c].z * inv[2] - (c == tcls[2] ? wt[2] : 0.f);
+          g.w = x[c].w * inv[3] - (c == tcls[3] ? wt[3] : 0.f);
+          *reinterpret_cast<float4*>(gbase + (long long)c * HW) = g;
+        }
+    }
+  }
+  __shared__ double red[3][kThreads / 32];
+  double a = warp_sum_d((double)loss_acc), b = warp_sum_d((double)w_acc), h = warp_sum_d((double)hit_acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = a; red[1][wid] = b; red[2][wid] = h; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
 __global__ void ratio_kernel(const double* __restrict__ sums, float* __restrict__ out, double denom_override) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
@@ -420,7 +509,11 @@ extern "C" int s2r_cross_entropy_nchw(const float* logits, const float* target, 
   if (npix == 0) return S2R_OK;
   const bool vec = (HW % 4 == 0) &&
                    (((uintptr_t)logits | (uintptr_t)grad_unscaled) % 16 == 0);
-  if (vec)
+  const bool tvec = !target || (uintptr_t)target % 16 == 0;
+  if (vec && tvec && C >= 2 && C <= 19 && getenv("S2R_CE_GENERIC") == nullptr)
+    S2R_CUDA_OK(s2r_launch(ce_regs_kernel<19>, dim3(s2r_grid(npix / 4, kThreads, 8)), dim3(kThreads), (size_t)0, (cudaStream_t)stream,
+        logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled));
+  else if (vec)
     S2R_CUDA_OK(s2r_launch(ce_kernel<4>, dim3(s2r_grid(npix / 4, kThreads, 8)), dim3(kThreads), (size_t)0, (cudaStream_t)stream, 
         logits, target, const_target, weight, C, HW, npix, ignore_index, sums, grad_unscaled));
   else
