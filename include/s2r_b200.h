@@ -399,6 +399,13 @@ int s2r_confusion_matrix(const void* gt, int gt_is_i64, const int64_t* pred, int
 int s2r_argmax_confusion_nchw(const float* logits, const float* gt, int N, int C, int64_t HW,
                               int num_class, int64_t* counts, int64_t* pred_out,
                               s2r_stream_t stream);
+/* The same from the decoder's LOW-RESOLUTION logits x (NHWC bf16 [N][Hi][Wi][pitch], C <= 32 classes): the final
+ * F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) of modeling/deeplab.py:31, the argmax of
+ * val_adapt.py:133 and the histogram of utils/metrics.py:34-43 in ONE pass; the fp32 [N,C,Ho,Wo] logits are never
+ * materialised.  Interpolated values are those of s2r_upsample_bilinear_nhwc_to_nchw bit for bit, so the counts equal
+ * s2r_upsample_bilinear_nhwc_to_nchw + s2r_argmax_confusion_nchw exactly.  gt: fp32 [N][Ho][Wo]. */
+int s2r_upsample_argmax_confusion_nhwc(const void* x, int xpitch, int N, int Hi, int Wi, int C, const float* gt,
+                                       int Ho, int Wo, int num_class, int64_t* counts, s2r_stream_t stream);
 
 /* ------------------------------------------------------------------ optimizers
  * torch.optim.SGD / Adam steps at train_adapt.py:58-60,180-181 and train.py:63-82,202-204, as

@@ -139,6 +139,7 @@ PROTOTYPES = {
     "s2r_bce_logits_bwd": [vp, vp, f32, i64, vp, vp, vp],
     "s2r_confusion_matrix": [vp, i32, vp, i64, i32, vp, vp, vp],
     "s2r_argmax_confusion_nchw": [vp, vp, i32, i32, i64, i32, vp, vp, vp],
+    "s2r_upsample_argmax_confusion_nhwc": [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp],
     "s2r_comm_create": [i32, i32, i32, vp],
     "s2r_comm_open": [vp],
     "s2r_allreduce_small_f64": [vp, i32, vp],

@@ -9,7 +9,7 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ conv_common.cuh -nt "$o" ] || [ dw_common.cuh -nt "$o" ] || [ tma_util.cuh -nt "$o" ] || [ bn_tail.cuh -nt "$o" ] || [ ../../include/s2r_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ conv_common.cuh -nt "$o" ] || [ dw_common.cuh -nt "$o" ] || [ tma_util.cuh -nt "$o" ] || [ bn_tail.cuh -nt "$o" ] || [ lerp.cuh -nt "$o" ] || [ ../../include/s2r_b200.h -nt "$o" ]; then
     $NVCC $FLAGS "$@" -c "$f" -o "$o" &
     pids+=($!)
   fi

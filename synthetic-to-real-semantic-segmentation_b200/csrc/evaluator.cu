@@ -7,6 +7,7 @@
 // match.any so spatially coherent label maps do not serialise on one bank, then
 // one 64-bit global atomic per non-empty bin per CTA.
 #include "common.cuh"
+#include "lerp.cuh"
 
 namespace {
 
@@ -124,6 +125,74 @@ argmax_confusion_kernel(const float* __restrict__ logits, const float* __restric
 }
 
 
+// The same on the decoder's LOW-RESOLUTION logits (NHWC bf16 [N][Hi][Wi][pitch], C classes): the final
+// F.interpolate(x, size, mode='bilinear', align_corners=True) of deeplab.py:31, the argmax of val_adapt.py:133 and the
+// histogram of metrics.py:34-43 in one pass -- the fp32 [N,C,Ho,Wo] logits (159 MB per 1024x2048 image, written by
+// the up-sampling and read back by the argmax) never exist.  Every thread evaluates the C interpolated values of its
+// pixel with resize.cu's own arithmetic (lerp.cuh), so the predictions are those of the two-step path bit for bit.
+template <int CG>
+__global__ void __launch_bounds__(kThreads)
+up_argmax_confusion_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int Hi, int Wi, int C,
+                           const float* __restrict__ gt, int Ho, int Wo, long long npix, float sh, float sw, int nc,
+                           unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int hist[kMaxClass * kMaxClass];
+  const int bins = nc * nc;
+  for (int i = threadIdx.x; i < bins; i += kThreads) hist[i] = 0;
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long iters = (npix + stride - 1) / stride;   // block-uniform: match.any needs all 32 lanes
+  const long long first = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long plane = (long long)Ho * Wo;
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = first + it * stride;
+    int bin = -1;
+    if (i < npix) {
+      const int n = (int)(i / plane);
+      const int r = (int)(i - (long long)n * plane);
+      const int oh = r / Wo, ow = r - oh * Wo;
+      const Lerp ly = lerp_src(oh, sh, Hi), lx = lerp_src(ow, sw, Wi);
+      const __nv_bfloat16* b = x + (long long)n * Hi * Wi * xpitch;
+      const __nv_bfloat16* p00 = b + ((long long)ly.i0 * Wi + lx.i0) * xpitch;
+      const __nv_bfloat16* p01 = b + ((long long)ly.i0 * Wi + lx.i1) * xpitch;
+      const __nv_bfloat16* p10 = b + ((long long)ly.i1 * Wi + lx.i0) * xpitch;
+      const __nv_bfloat16* p11 = b + ((long long)ly.i1 * Wi + lx.i1) * xpitch;
+      float best = 0.f;
+      int arg = 0;
+#pragma unroll
+      for (int g = 0; g < CG; ++g) {
+        float v00[8], v01[8], v10[8], v11[8];
+        bf16x8_to_float(ldg16(p00 + g * 8), v00);
+        bf16x8_to_float(ldg16(p01 + g * 8), v01);
+        bf16x8_to_float(ldg16(p10 + g * 8), v10);
+        bf16x8_to_float(ldg16(p11 + g * 8), v11);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = g * 8 + k;
+          if (c < C) {
+            const float v = bilerp(ly, lx, v00[k], v01[k], v10[k], v11[k]);
+            // strict > keeps the first maximum; a NaN beats any non-NaN (numpy.argmax)
+            if (c == 0 || v > best || (v != v && best == best)) {
+              best = v;
+              arg = c;
+            }
+          }
+        }
+      }
+      int cls = 0;
+      if (gt_valid<float>(__ldg(gt + i), nc, &cls) && arg < nc) bin = cls * nc + arg;
+    }
+    hist_add(hist, bin);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kThreads) {
+    const unsigned int c = hist[i];
+    if (c) atomicAdd(&counts[i], (unsigned long long)c);
+  }
+}
+
+
 // Prediction export (test_adapt.py:118-157 / val_adapt.py:179-218 imgsaver + the host argmax at test_adapt.py:170-171):
 // argmax over the class planes at the source pixel PIL's NEAREST resize picks for every output position, then the two
 // byte tables (trainId -> labelId, trainId -> RGB).  ids u8 [N][OH][OW], rgb u8 [N][OH][OW][3]; ties -> lowest class
@@ -196,6 +265,36 @@ extern "C" int s2r_argmax_confusion_nchw(const float* logits, const float* gt, i
   argmax_confusion_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
       logits, gt, C, HW, npix, num_class > 0 ? num_class : 1, (unsigned long long*)counts,
       (long long*)pred_out);
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
+
+extern "C" int s2r_upsample_argmax_confusion_nhwc(const void* x, int xpitch, int N, int Hi, int Wi, int C,
+                                                  const float* gt, int Ho, int Wo, int num_class, int64_t* counts,
+                                                  s2r_stream_t stream) {
+  S2R_REQUIRE(N >= 0 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1, S2R_ERR_SHAPE, "upsample_argmax_confusion: bad shape");
+  const int cgs = (C + 7) / 8;
+  S2R_REQUIRE(x && xpitch % 8 == 0 && xpitch >= cgs * 8 && (uintptr_t)x % 16 == 0, S2R_ERR_SHAPE,
+              "upsample_argmax_confusion: pitch %d must be a multiple of 8 covering C=%d", xpitch, C);
+  S2R_REQUIRE(cgs <= 4, S2R_ERR_UNSUPPORTED, "upsample_argmax_confusion: C=%d > 32 not supported", C);
+  S2R_REQUIRE(num_class >= 1 && num_class <= kMaxClass, S2R_ERR_UNSUPPORTED,
+              "upsample_argmax_confusion: num_class %d outside [1,%d]", num_class, kMaxClass);
+  S2R_REQUIRE(gt && counts, S2R_ERR_SHAPE, "upsample_argmax_confusion: gt / counts is null");
+  S2R_REQUIRE((long long)Ho * Wo < (1ll << 31), S2R_ERR_UNSUPPORTED, "upsample_argmax_confusion: image too large");
+  const long long npix = (long long)N * Ho * Wo;
+  if (npix == 0) return S2R_OK;
+  const int grid = s2r_grid(npix, kThreads * 4, 8);
+  const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  cudaStream_t st = (cudaStream_t)stream;
+#define S2R_UAC(CG_) S2R_CUDA_OK(s2r_launch(up_argmax_confusion_kernel<CG_>, dim3(grid), dim3(kThreads), (size_t)0, st, xb, xpitch, Hi, Wi, C, gt, Ho, Wo, npix, sh, sw, num_class, (unsigned long long*)counts))
+  switch (cgs) {
+    case 1: S2R_UAC(1); break;
+    case 2: S2R_UAC(2); break;
+    case 3: S2R_UAC(3); break;
+    default: S2R_UAC(4); break;
+  }
+#undef S2R_UAC
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -7,31 +7,11 @@
 // (in-1)/(out-1) in fp32, src = scale*dst, i0 = int(src), i1 = i0 + (i0 < in-1).
 // Backward kernels are gather-formulated (no atomics, deterministic).
 #include "common.cuh"
+#include "lerp.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-
-struct Lerp {
-  int i0, i1;
-  float w0, w1;
-};
-
-__device__ __forceinline__ Lerp lerp_src(int o, float scale, int in) {
-  Lerp l;
-  const float t = scale * (float)o;
-  int i0 = (int)t;
-  if (i0 > in - 1) i0 = in - 1;
-  l.i0 = i0;
-  l.i1 = i0 + (i0 < in - 1 ? 1 : 0);
-  l.w1 = t - (float)i0;
-  l.w0 = 1.f - l.w1;
-  return l;
-}
-
-__host__ __device__ __forceinline__ float ac_scale(int in, int out) {
-  return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
-}
 
 // candidate output range that can reference input index i
 __device__ __forceinline__ void cand_range(int i, float scale, int out, int* lo, int* hi) {
@@ -159,8 +139,7 @@ up_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int xpitch, int N, int Hi
       for (int i = 0; i < 8; ++i) {
         const int c = g * 8 + i;
         if (c < C)
-          out[(long long)c * plane] = ly.w0 * (lx.w0 * v00[i] + lx.w1 * v01[i]) +
-                                      ly.w1 * (lx.w0 * v10[i] + lx.w1 * v11[i]);
+          out[(long long)c * plane] = bilerp(ly, lx, v00[i], v01[i], v10[i], v11[i]);
       }
     }
   }

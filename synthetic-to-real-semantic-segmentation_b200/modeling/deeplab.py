@@ -39,6 +39,21 @@ class DeepLabRun(UpsampledLogits, RunBase):
         return None
 
 
+class DeepLabConfusionRun(DeepLabRun):
+    """Validation: the up-sampling at the module boundary, the argmax and the Evaluator's histogram are one launch on
+    the decoder's low-resolution logits (utils.metrics.Evaluator.add_batch_lowres); the fp32 logits never exist."""
+
+    def __init__(self, mod, target, evaluator):
+        DeepLabRun.__init__(self, mod)
+        self.target, self.evaluator = target, evaluator
+
+    def export(self, cx, i, a):
+        if tuple(self.target.shape[-2:]) != tuple(self.out_hw):
+            raise ValueError("forward_confusion: label map %s, image %s" % (tuple(self.target.shape), self.out_hw))
+        self.evaluator.add_batch_lowres(self.target, a.ptr, a.pitch, a.N, a.H, a.W, a.C, cx.stream)
+        return torch.empty((a.N, 0), dtype=torch.float32, device=cx.device)
+
+
 class DeepLab(nn.Module):
     def __init__(self, backbone='resnet', output_stride=16, num_classes=19, sync_bn=True, freeze_bn=False):
         super().__init__()
@@ -53,6 +68,17 @@ class DeepLab(nn.Module):
 
     def forward(self, input):
         return call_module(self, lambda: DeepLabRun(self), (input,))
+
+    @torch.no_grad()
+    def forward_confusion(self, input, target, evaluator):
+        """val_adapt.py:126-135 in one call: `output = model(image)`, `pred = argmax(output, 1)`,
+        `evaluator.add_batch(target, pred)` -- with the final x4 up-sampling (deeplab.py:31), the argmax and the
+        histogram fused into one kernel on the decoder's low-resolution logits.  Counts are identical to
+        evaluator.add_batch_logits(target, self(input)); eval mode only."""
+        if self.training:
+            raise RuntimeError("forward_confusion is the validation path: call model.eval() first")
+        evaluator._ensure(input.device if input.device.type == "cuda" else None)
+        call_module(self, lambda: DeepLabConfusionRun(self, target, evaluator), (input,))
 
     def _lr_params(self, modules):
         # deeplab.py:42-72: Conv2d (+ BatchNorm unless freeze_bn) parameters of the given sub-modules

@@ -498,6 +498,9 @@ class _SharedGradOptimizer(object):
         pass
 
 
+FUSED_VAL = os.environ.get("S2R_FUSED_VAL", "1") != "0"   # ValStep: fused up-sampling + argmax + confusion matrix
+
+
 class ValStep(object):
     """val_adapt.py:122-135 with argmax + confusion matrix fused on the device."""
 
@@ -515,6 +518,11 @@ class ValStep(object):
 
     @torch.no_grad()
     def __call__(self, image, target, with_loss=False):
+        net = getattr(self.model, "module", self.model)     # nn.DataParallel wrapper of the reference's scripts
+        if not with_loss and FUSED_VAL and hasattr(net, "forward_confusion") and not net.training:
+            # up-sampling + argmax + histogram in one launch on the low-resolution logits (no fp32 logits tensor)
+            net.forward_confusion(image, target, self._evaluator)
+            return None
         output = self.model(image)
         loss = self.criterion(output, target) if with_loss else None
         self._evaluator.add_batch_logits(target, output)

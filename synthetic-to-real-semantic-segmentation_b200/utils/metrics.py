@@ -95,6 +95,18 @@ class Evaluator(object):
             L.call("s2r_argmax_confusion_nchw", _vp(logits), _vp(gt), N, Cc, HW, self.num_class,
                    _vp(self._counts), None, st)
 
+    def add_batch_lowres(self, gt_image, act_ptr, pitch, N, Hi, Wi, Cc, stream):
+        """The final bilinear up-sampling of deeplab.py:31 to the label map's size, the argmax and the histogram in
+        one launch, from the decoder's NHWC bf16 logits (raw device pointer; called by DeepLab.forward_confusion on
+        the engine's stream).  Same counts as forward() + add_batch_logits(), bit for bit."""
+        gt = self._as_cuda(gt_image, False)
+        if gt.dtype != torch.float32:
+            gt = gt.float()
+        if gt.dim() != 3 or gt.shape[0] != N:
+            raise ValueError("add_batch_lowres: label map %s does not match a batch of %d" % (tuple(gt.shape), N))
+        L.call("s2r_upsample_argmax_confusion_nhwc", C.c_void_p(act_ptr), pitch, N, Hi, Wi, Cc, _vp(gt),
+               gt.shape[1], gt.shape[2], self.num_class, _vp(self._counts), stream)
+
     def all_reduce(self, group=None):
         """Data-parallel validation (one process per GPU, every rank evaluates its shard of the images): ONE
         all-reduce(sum) of the int64 [num_class, num_class] counts -- and of the bad-prediction flag -- turns every

@@ -146,6 +146,41 @@ def test_conv_into_concat_slice_and_leaky_mask(eng, cx):
     assert rel(to_nchw(dx), ref) < 4e-3
 
 
+
+@pytest.mark.parametrize("shape", [(1, 256, 512, 19, 1024, 2048), (2, 33, 17, 19, 129, 65), (3, 8, 8, 5, 8, 8),
+                                   (1, 5, 7, 32, 1, 1), (2, 16, 16, 8, 61, 64)])
+def test_fused_upsample_argmax_confusion_bit_exact(eng, cx, shape):
+    """s2r_upsample_argmax_confusion_nhwc (deeplab.py:31 + val_adapt.py:133 + metrics.py:34-43 in one launch on the
+    low-resolution NHWC bf16 logits) against the two launches it replaces -- s2r_upsample_bilinear_nhwc_to_nchw, then
+    s2r_argmax_confusion_nchw on the fp32 logits -- and against numpy's argmax / the oracle's confusion matrix on those
+    logits: identical counts, including ties (bf16 inputs make exact ties common), NaN and ignored / out-of-range labels."""
+    L = sub("_lib")
+    N, Hi, Wi, Cc, Ho, Wo = shape
+    g = torch.Generator(device="cuda").manual_seed(Hi * Wi + Cc)
+    x = bf(torch.randn(N, Cc, Hi, Wi, device="cuda", generator=g))
+    x[:, :, ::3, ::2] = bf(torch.round(x[:, :, ::3, ::2]))          # many exact ties between classes
+    if Hi > 4:
+        x[0, Cc // 2, 2, 3] = float("nan")
+    xa = nhwc_act(eng, x)
+    nc = max(Cc, 2)
+    gt = torch.randint(-1, nc + 2, (N, Ho, Wo), device="cuda", generator=g).float()
+    gt[torch.rand(N, Ho, Wo, device="cuda", generator=g) < 0.1] = 255
+    logits = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device="cuda")
+    L.call("s2r_upsample_bilinear_nhwc_to_nchw", xa.vp(), xa.pitch, N, Hi, Wi, Cc, C.c_void_p(logits.data_ptr()), Ho, Wo, cx.stream)
+    two = torch.zeros((nc, nc), dtype=torch.int64, device="cuda")
+    L.call("s2r_argmax_confusion_nchw", C.c_void_p(logits.data_ptr()), C.c_void_p(gt.data_ptr()), N, Cc, Ho * Wo, nc,
+           C.c_void_p(two.data_ptr()), None, cx.stream)
+    one = torch.zeros((nc, nc), dtype=torch.int64, device="cuda")
+    L.call("s2r_upsample_argmax_confusion_nhwc", xa.vp(), xa.pitch, N, Hi, Wi, Cc, C.c_void_p(gt.data_ptr()), Ho, Wo, nc,
+           C.c_void_p(one.data_ptr()), cx.stream)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    pred = np.argmax(logits.cpu().numpy(), axis=1)
+    want = O.confusion_matrix(gt.cpu().numpy(), pred, nc)
+    assert np.array_equal(one.cpu().numpy(), want)
+    assert int(one.sum()) == int(((gt >= 0) & (gt < nc)).sum())
+
+
 DW_CASES = [(2, 18, 26, 32, 1, 1, False), (2, 17, 25, 96, 2, 1, True), (2, 16, 24, 144, 1, 1, True),
             (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True),
             # streaming stride-1 kernels: several column tiles / row segments, 32-, 48- and 16-channel chunks

@@ -472,6 +472,48 @@ def test_val_step_confusion_matrix_matches_oracle_on_same_predictions(built_lib)
     assert val.evaluator.Mean_Intersection_over_Union()[0] == m_['mIoU']
 
 
+
+def test_val_step_fused_path_equals_logits_path(built_lib):
+    """ValStep's one-launch up-sampling + argmax + histogram (DeepLab.forward_confusion) against the path through the
+    fp32 logits (model(image) + Evaluator.add_batch_logits): identical confusion matrices; with_loss=True keeps the
+    logits path and returns the cross entropy."""
+    steps = sub("steps")
+    m = make_deeplab().cuda().eval()
+    with torch.no_grad():
+        m(torch.randn(1, 3, 160, 224).cuda())       # warm-up: filter packing, lazy buffers (launch counts below)
+    cms = {}
+    for fused in (True, False):
+        steps.FUSED_VAL = fused
+        try:
+            val = steps.ValStep(m, 19)
+            L = sub("_lib")
+            n0 = L.launches
+            for k in range(2):
+                gg = torch.Generator().manual_seed(20 + k)
+                x = torch.randn(1, 3, 160, 224, generator=gg)
+                lab = torch.randint(0, 20, (1, 160, 224), generator=gg).float()
+                lab[lab == 19] = 255
+                val(x.cuda(), lab.cuda())
+            cms[fused] = (val.evaluator.confusion_matrix.copy(), L.launches - n0)
+        finally:
+            steps.FUSED_VAL = True
+    assert np.array_equal(cms[True][0], cms[False][0]) and cms[True][0].sum() > 0
+    assert cms[True][1] == cms[False][1] - 2          # one launch instead of two, per image
+    val = steps.ValStep(m, 19)
+    gg = torch.Generator().manual_seed(20)
+    x = torch.randn(1, 3, 160, 224, generator=gg)
+    lab = torch.randint(0, 20, (1, 160, 224), generator=gg).float()
+    lab[lab == 19] = 255
+    loss = val(x.cuda(), lab.cuda(), with_loss=True)
+    assert torch.isfinite(loss)
+    with pytest.raises(RuntimeError):
+        m.train()
+        try:
+            m.forward_confusion(x.cuda(), lab.cuda(), val.evaluator)
+        finally:
+            m.eval()
+
+
 def test_val_step_graph_lanes_accumulate_identical_counts(built_lib):
     """ValStep.capture(lanes=2): successive images replayed on two graph lanes give exactly the counts of the eager
     loop (integer atomics; order-independent)."""
