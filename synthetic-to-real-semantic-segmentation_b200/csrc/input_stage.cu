@@ -230,50 +230,80 @@ input_stage_multi_kernel(const s2r_stage_job* __restrict__ jobs, NormParams np, 
 
 // ---- RandomGaussianBlur: the crop (cut from the scaled image exactly as input_stage_multi_kernel cuts it: mirror,
 // zero padding on the right / bottom) goes through three 3-tap passes along x (blur_rows_kernel -> tmp) and three
-// along y (blur_cols_kernel -> out).  P_0 = the line, P_{k+1}(j) = tap(P_k(max(j-1, 0)), P_k(j), P_k(min(j+1, last)));
-// a thread evaluates P_3 at its position by recursion (27 L1-resident byte loads; the whole stage moves < 1 MB per
-// image), so there is no intermediate buffer between the passes of one axis.
+// along y (blur_cols_kernel -> out).  P_0 = the line, P_{k+1}(j) = tap(P_k(max(j-1, 0)), P_k(j), P_k(min(j+1, last))).
+// A thread produces K CONSECUTIVE positions of a line: it loads the K + 6 source bytes they depend on once and
+// evaluates the three passes on shrinking register windows (K + 4, K + 2, K values), so a byte costs (3K + 6) / K taps
+// and (K + 6) / K loads -- the first version evaluated P_3 at one position by recursion (13 taps, 27 loads per byte,
+// 0.46 ms for the sixteen 512x512 crops of a batch).  The replicated line ends enter through selects on the absolute
+// position: window entries that lie off the line are never read.  No intermediate buffer between the passes of an axis.
 __device__ __forceinline__ uint32_t blur_tap(uint32_t l, uint32_t c, uint32_t r, uint32_t ww, uint32_t fw) {
   return (c * ww + (l + r) * fw + (1u << 23)) >> 24;
 }
 
-template <class Line>
-__device__ __forceinline__ uint8_t blur_three_passes(Line p0, int x, int last, uint32_t ww, uint32_t fw) {
-  auto lo = [](int j) { return j < 0 ? 0 : j; };
-  auto hi = [last](int j) { return j > last ? last : j; };
-  auto p1 = [&](int j) { return blur_tap(p0(lo(j - 1)), p0(j), p0(hi(j + 1)), ww, fw); };
-  auto p2 = [&](int j) { return blur_tap(p1(lo(j - 1)), p1(j), p1(hi(j + 1)), ww, fw); };
-  return (uint8_t)blur_tap(p2(lo(x - 1)), p2(x), p2(hi(x + 1)), ww, fw);
+// o[u] = P_3(x0 + u), u < K (positions past `last` produce unused values)
+template <int K, class Line>
+__device__ __forceinline__ void blur_three_passes(Line p0, int x0, int last, uint32_t ww, uint32_t fw, uint8_t* o) {
+  uint32_t b0[K + 6], b1[K + 4], b2[K + 2];
+#pragma unroll
+  for (int i = 0; i < K + 6; ++i) {            // b0[i] = P_0(clamp(x0 - 3 + i))
+    const int j = x0 - 3 + i;
+    b0[i] = p0(j < 0 ? 0 : (j > last ? last : j));
+  }
+#pragma unroll
+  for (int s = 0; s < K + 4; ++s) b1[s] = blur_tap(b0[s], b0[s + 1], b0[s + 2], ww, fw);   // P_1(x0 - 2 + s) where on the line
+#pragma unroll
+  for (int t = 0; t < K + 2; ++t) {            // P_2(x0 - 1 + t) where on the line
+    const int j = x0 - 1 + t;
+    const uint32_t l = j <= 0 ? b1[t + 1] : b1[t], r = j >= last ? b1[t + 1] : b1[t + 2];
+    b2[t] = blur_tap(l, b1[t + 1], r, ww, fw);
+  }
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    const int x = x0 + u;
+    const uint32_t l = x <= 0 ? b2[u + 1] : b2[u], r = x >= last ? b2[u + 1] : b2[u + 2];
+    o[u] = (uint8_t)blur_tap(l, b2[u + 1], r, ww, fw);
+  }
 }
+
+constexpr int BLUR_KX = 4;   // pixels (x 3 channels) per thread of the row pass
+constexpr int BLUR_KY = 8;   // rows per thread of the column pass
 
 // grid = (blocks over H*W*3 bytes of the crop, njobs)
 __global__ void __launch_bounds__(kThreads)
 blur_rows_kernel(const s2r_blur_job* __restrict__ jobs, int H, int W) {
   const s2r_blur_job j = jobs[blockIdx.y];
-  const int total = H * W * 3;
+  const int G = (W + BLUR_KX - 1) / BLUR_KX, total = H * G;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-    const int c = i % 3, x = (i / 3) % W, y = i / (3 * W);
+    const int x0 = (i % G) * BLUR_KX, y = i / G;
     const int sy = j.y1 + y;
-    const uint8_t* row = j.img + (long long)sy * j.Ws * 3 + c;
     const bool row_inside = sy < j.Hs;
-    auto px = [&](int xx) -> uint32_t {
-      const int sx0 = j.x1 + xx;
-      if (!row_inside || sx0 >= j.Ws) return 0u;             // ImageOps.expand(border, fill = 0) before the crop
-      return row[(j.flip ? j.Ws - 1 - sx0 : sx0) * 3];
-    };
-    j.tmp[i] = blur_three_passes(px, x, W - 1, j.ww, j.fw);
+    for (int c = 0; c < 3; ++c) {
+      const uint8_t* row = j.img + (long long)sy * j.Ws * 3 + c;
+      auto px = [&](int xx) -> uint32_t {
+        const int sx0 = j.x1 + xx;
+        if (!row_inside || sx0 >= j.Ws) return 0u;             // ImageOps.expand(border, fill = 0) before the crop
+        return row[(j.flip ? j.Ws - 1 - sx0 : sx0) * 3];
+      };
+      uint8_t o[BLUR_KX];
+      blur_three_passes<BLUR_KX>(px, x0, W - 1, j.ww, j.fw, o);
+      for (int u = 0; u < BLUR_KX; ++u)
+        if (x0 + u < W) j.tmp[((long long)y * W + x0 + u) * 3 + c] = o[u];
+    }
   }
 }
 
 __global__ void __launch_bounds__(kThreads)
 blur_cols_kernel(const s2r_blur_job* __restrict__ jobs, int H, int W) {
   const s2r_blur_job j = jobs[blockIdx.y];
-  const int pitch = W * 3, total = H * pitch;
+  const int pitch = W * 3, total = ((H + BLUR_KY - 1) / BLUR_KY) * pitch;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-    const int xb = i % pitch, y = i / pitch;
+    const int xb = i % pitch, y0 = (i / pitch) * BLUR_KY;
     const uint8_t* col = j.tmp + xb;
-    auto px = [&](int yy) -> uint32_t { return col[yy * pitch]; };
-    j.out[i] = blur_three_passes(px, y, H - 1, j.ww, j.fw);
+    auto px = [&](int yy) -> uint32_t { return col[(long long)yy * pitch]; };
+    uint8_t o[BLUR_KY];
+    blur_three_passes<BLUR_KY>(px, y0, H - 1, j.ww, j.fw, o);
+    for (int u = 0; u < BLUR_KY; ++u)
+      if (y0 + u < H) j.out[(long long)(y0 + u) * pitch + xb] = o[u];
   }
 }
 
@@ -284,11 +314,12 @@ extern "C" int s2r_gaussian_blur3_u8_multi(const s2r_blur_job* jobs, int njobs, 
               "gaussian_blur3_u8_multi: bad shape");
   if (njobs == 0) return S2R_OK;
   S2R_REQUIRE(jobs != nullptr, S2R_ERR_SHAPE, "gaussian_blur3_u8_multi: null table");
-  int gx = s2r_div_up((long long)H * W * 3, kThreads);
-  if (gx > 4096) gx = 4096;
-  blur_rows_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
+  int gr = s2r_div_up((long long)H * s2r_div_up(W, BLUR_KX), kThreads), gc = s2r_div_up((long long)s2r_div_up(H, BLUR_KY) * W * 3, kThreads);
+  if (gr > 4096) gr = 4096;
+  if (gc > 4096) gc = 4096;
+  blur_rows_kernel<<<dim3(gr, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
   S2R_LAUNCH_OK();
-  blur_cols_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
+  blur_cols_kernel<<<dim3(gc, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs, H, W);
   S2R_LAUNCH_OK();
   return S2R_OK;
 }

@@ -97,3 +97,27 @@ for n in range(N):
         ok &= np.array_equal(a.transpose((2, 0, 1)), outb[key][n].cpu().numpy())
 print("with RandomGaussianBlur on all %d pairs: %.2f ms per batch (+%.2f ms for the two blur launches); identical to Pillow: %s"
       % (N, ms_b, ms_b - ms, ok))
+
+# device time of the two blur launches alone (job table resident, CUDA-graph replay of 10 calls): sixteen 512x512
+# crops cut out of 8 + 8 scaled images
+L = sub("_lib")
+scaled = [torch.randint(0, 256, (700, 1273, 3), dtype=torch.uint8, generator=g).to(dev) for _ in range(2 * N)]
+buf = torch.empty((2, 2 * N, CROP, CROP, 3), dtype=torch.uint8, device=dev)
+ww, fw = dt._gaussian_blur_weights(0.7)
+jobs = [L.BlurJob(scaled[k].data_ptr(), buf[0, k].data_ptr(), buf[1, k].data_ptr(), 700, 1273, k & 1, 37 + k, 11 + k,
+                  int(ww), int(fw), 0) for k in range(2 * N)]
+tab = dt._upload(jobs, dev)
+st = torch.cuda.current_stream().cuda_stream
+call = lambda: L.call("s2r_gaussian_blur3_u8_multi", tab.data_ptr(), 2 * N, CROP, CROP, st)
+call(); torch.cuda.synchronize()
+gr = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr):
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(10):
+        call()
+gr.replay(); torch.cuda.synchronize()
+e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / 10 * 1e3
+nbytes = 2 * N * CROP * CROP * 3
+print("blur launches alone (device time, 16 crops of %dx%d): %.1f us per batch = %.0f GB/s over the 4 x %.1f MB read + written"
+      % (CROP, CROP, us, 4 * nbytes / us / 1e3, nbytes / 1e6))
