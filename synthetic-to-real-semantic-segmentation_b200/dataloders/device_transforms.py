@@ -113,10 +113,42 @@ def _scale_size(w, h, short_size):
     return ow, oh
 
 
+class _PinnedRing(object):
+    """Staging slots in page-locked memory for the per-batch job tables.  A table that goes to the device from pageable
+    memory makes the host wait until the copy has run, i.e. until everything queued on the stream before it has
+    finished: with four or five tables per batch the stage ran at the pace of those waits (0.45 ms per batch for
+    ~0.1 ms of kernels).  From a pinned slot the copy is asynchronous; a slot is reused only after its copy is done."""
+    SLOTS, SIZE = 32, 1 << 16
+
+    def __init__(self):
+        self.buf, self.events, self.next = None, [None] * self.SLOTS, 0
+
+    def put(self, data, dev):
+        n = len(data)
+        if self.buf is None:
+            self.buf = torch.empty((self.SLOTS, self.SIZE), dtype=torch.uint8, pin_memory=True)
+        k, self.next = self.next, (self.next + 1) % self.SLOTS
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        self.buf[k, :n] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        t = torch.empty(n, dtype=torch.uint8, device=dev)
+        t.copy_(self.buf[k, :n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self.events[k] = ev
+        return t
+
+
+_RING = _PinnedRing()
+
+
 def _upload(jobs, dev):
-    """A ctypes job table -> device memory."""
-    arr = (type(jobs[0]) * len(jobs))(*jobs)
-    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    """A ctypes job table -> device memory (asynchronously, through a pinned staging slot)."""
+    data = bytes((type(jobs[0]) * len(jobs))(*jobs))
+    dev = torch.device(dev)
+    if dev.type != "cuda" or len(data) > _PinnedRing.SIZE:
+        return torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    return _RING.put(data, dev)
 
 
 class _Stage(object):

@@ -121,3 +121,16 @@ us = e0.elapsed_time(e1) / 10 * 1e3
 nbytes = 2 * N * CROP * CROP * 3
 print("blur launches alone (device time, 16 crops of %dx%d): %.1f us per batch = %.0f GB/s over the 4 x %.1f MB read + written"
       % (CROP, CROP, us, 4 * nbytes / us / 1e3, nbytes / 1e6))
+
+# device time of the whole batched stage: the launches of 5 calls are enqueued behind a 30 ms spin kernel, so the events
+# see the GPU run them back to back (the 0.45 ms above is what the Python call costs end to end: four launches plus the
+# job tables and their upload)
+for rnd, with_blur, d in ((0, False, draws), (0, True, bdraws), (1, False, draws), (1, True, bdraws)):   # round 0: warm-up
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(30e-3 * 1.9e9))
+    e0.record()
+    for _ in range(5):
+        tr(d_src, d_tgt, d_lab, draws=d)
+    e1.record(); torch.cuda.synchronize()
+    if rnd:
+        print("batched stage%s, device time: %.3f ms per batch" % (" with RandomGaussianBlur on all pairs" if with_blur else "", e0.elapsed_time(e1) / 5))
