@@ -543,7 +543,11 @@ def multi_rank_parity(job, G, run_step, d_src, it):
         rec["softmax_dim0_rank_local_over_global_mean_ratio"] = float(loc.double().mean() / glob.double().mean())
         del allx, glob, loc
     del parts
-    rec["softmax_dim0"] = "rank-local batch (stated deviation; north_star: only BN statistics and gradients are exchanged)"
+    if sub("functional").GLOBAL_SOFTMAX0[0]:
+        rec["softmax_dim0"] = ("global batch (S2R_GLOBAL_SOFTMAX0=1: batch maximum / sum of exponentials / sum of g*y all-reduced per "
+                               "discriminator evaluation; two-rank parity: tests/test_gpu_multirank.py)")
+    else:
+        rec["softmax_dim0"] = "rank-local batch (stated deviation; north_star: only BN statistics and gradients are exchanged)"
     rec["cross_entropy_mean"] = "global batch (valid-pixel counts all-reduced)"
     # one more full step, then compare the replicas
     run_step(it)

@@ -378,6 +378,18 @@ int s2r_softmax0_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, in
                                   s2r_stream_t stream);
 int s2r_softmax0_nhwc_pad_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, int softmax,
                               float* dx, s2r_stream_t stream);
+/* The same over the GLOBAL batch of a data-parallel run -- the reference's nn.DataParallel gathers the logits of all
+ * replicas on one device before F.softmax(x, dim=0) (train_adapt.py:87-88,151,166,174), so the softmax runs over the
+ * images of ALL ranks.  s2r_softmax0_batch_stats: out[i] = max_b x[b][i] (gmax NULL) or sum_b exp(x[b][i] - gmax[i]) over
+ * this rank's B images, i < M = C*H*W; the caller all-reduces the first with MAX, the second with SUM.  _global forward:
+ * y_b = exp(x_b - gmax) / gsum into the padded NHWC buffer.  _global backward, two launches around one all-reduce(SUM):
+ * tpart != NULL: tpart[i] = this rank's sum_b g_b y_b (dx untouched); tpart == NULL: dx_b = y_b (g_b - tglob). */
+int s2r_softmax0_batch_stats(const float* x, int B, int64_t M, const float* gmax, float* out, s2r_stream_t stream);
+int s2r_softmax0_nchw_to_nhwc_pad_global(const float* x, int B, int C, int H, int W, const float* gmax,
+                                         const float* gsum, void* yp, int Cp, s2r_stream_t stream);
+int s2r_softmax0_nhwc_pad_bwd_global(const float* x, const void* gp, int B, int C, int H, int W, int Cp,
+                                     const float* gmax, const float* gsum, float* tpart, const float* tglob,
+                                     float* dx, s2r_stream_t stream);
 /* sums (fp64, zeroed by the caller) += {sum_valid w_t (lse - x_t), sum_valid w_t, #(argmax == t)}; grad_unscaled
  * (optional) = w_t (softmax - onehot).  A target that is neither ignore_index nor in [0, C) makes sums[0] NaN (the
  * reference's nn.CrossEntropyLoss stops with a device assert there, utils/loss.py:27-28). */

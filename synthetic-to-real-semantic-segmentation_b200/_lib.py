@@ -102,6 +102,9 @@ PROTOTYPES = {
     "s2r_wgrad_scatter_taps": [vp, vp, i32, i32, i32, i32, vp],
     "s2r_softmax0_nchw_to_nhwc_pad": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "s2r_softmax0_nhwc_pad_bwd": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "s2r_softmax0_batch_stats": [vp, i32, i64, vp, vp, vp],
+    "s2r_softmax0_nchw_to_nhwc_pad_global": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp],
+    "s2r_softmax0_nhwc_pad_bwd_global": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "s2r_dwconv3x3_fwd": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_fwd_bn": [vp, C.POINTER(BnTail), vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "s2r_dwconv3x3_dgrad": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -347,9 +347,13 @@ constexpr int SP_TW = 128;
 constexpr int SP_THREADS = 256;
 constexpr int SP_MAXB = 8;
 
+// gmax / gsum (both or neither; [C][H][W] fp32): maximum and sum of exp(x - gmax) over the GLOBAL batch, i.e. over the
+// images of all ranks (s2r_softmax0_batch_stats + two all-reduces): F.softmax(x, dim=0) of the gathered batch, as the
+// reference's single-process DataParallel evaluates it (train_adapt.py:87-88,151), on a rank that holds B of the images.
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(SP_THREADS)
-softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, int W, __nv_bfloat16* __restrict__ y, int Cp) {
+softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, int W, __nv_bfloat16* __restrict__ y, int Cp,
+                            const float* __restrict__ gmax, const float* __restrict__ gsum) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t sp_smem[];
@@ -383,12 +387,21 @@ softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, in
       float m0 = -INFINITY, m1 = -INFINITY, s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) { m0 = fmaxf(m0, t0[b]); m1 = fmaxf(m1, t1[b]); }
+      const long long gi = (long long)c0 * plane + (long long)h * W + w0 + w;
+      if (gmax) {
+        m0 = __ldg(gmax + gi);
+        if (has1) m1 = __ldg(gmax + gi + plane);
+      }
       if (!has1) m1 = 0.f;
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) {
         t0[b] = b < bc ? __expf(t0[b] - m0) : 0.f;
         t1[b] = (b < bc && has1) ? __expf(t1[b] - m1) : 0.f;
         s0 += t0[b]; s1 += t1[b];
+      }
+      if (gsum) {
+        s0 = __ldg(gsum + gi);
+        if (has1) s1 = __ldg(gsum + gi + plane);
       }
       s0 = 1.f / s0; s1 = has1 ? 1.f / s1 : 0.f;
 #pragma unroll
@@ -429,7 +442,8 @@ softmax0_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, in
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(SP_THREADS)
 softmax0_nhwc_pad_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ gp, int B, int C, int H,
-                             int W, int Cp, float* __restrict__ dx) {
+                             int W, int Cp, float* __restrict__ dx, const float* __restrict__ gmax,
+                             const float* __restrict__ gsum, float* __restrict__ tpart, const float* __restrict__ tglob) {
   pdl_wait();      // programmatic dependent launch: see common.cuh
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t sp_smem[];
@@ -458,11 +472,21 @@ softmax0_nhwc_pad_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* _
       float m = -INFINITY, s = 0.f, dot = 0.f;
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) m = fmaxf(m, t[b]);
+      // global batch (see the forward kernel): statistics of all ranks' images; the sum over b' of g y then also runs
+      // over all ranks -- this launch leaves its part in tpart, a second one takes the all-reduced sum from tglob
+      const long long gi = (long long)c * plane + (long long)h * W + w0 + w;
+      if (gmax) m = __ldg(gmax + gi);
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) { t[b] = b < bc ? __expf(t[b] - m) : 0.f; s += t[b]; }
+      if (gsum) s = __ldg(gsum + gi);
       s = 1.f / s;
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) { t[b] *= s; dot = fmaf(t[b], g[b], dot); }
+      if (tpart) {
+        tpart[gi] = dot;
+        continue;
+      }
+      if (tglob) dot = __ldg(tglob + gi);
 #pragma unroll
       for (int b = 0; b < SP_MAXB; ++b) g[b] = t[b] * (g[b] - dot);
     }
@@ -472,7 +496,34 @@ softmax0_nhwc_pad_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* _
   }
 }
 
+// out[i] = max_b x[b][i] (gmax == NULL) or sum_b exp(x[b][i] - gmax[i]), i over the M = C*H*W positions of one image
+__global__ void __launch_bounds__(kThreads)
+softmax0_batch_stats_kernel(const float* __restrict__ x, int B, long long M, const float* __restrict__ gmax,
+                            float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < M; i += (long long)gridDim.x * kThreads) {
+    float a = gmax ? 0.f : -INFINITY;
+    const float m = gmax ? __ldg(gmax + i) : 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float v = __ldg(x + (long long)b * M + i);
+      a = gmax ? a + __expf(v - m) : fmaxf(a, v);
+    }
+    out[i] = a;
+  }
+}
+
 }  // namespace
+
+extern "C" int s2r_softmax0_batch_stats(const float* x, int B, int64_t M, const float* gmax, float* out,
+                                        s2r_stream_t stream) {
+  S2R_REQUIRE(x && out && B >= 1 && M >= 0, S2R_ERR_SHAPE, "softmax0_batch_stats: bad arguments");
+  if (M == 0) return S2R_OK;
+  S2R_CUDA_OK(s2r_launch(softmax0_batch_stats_kernel, dim3(s2r_grid(M, kThreads, 16)), dim3(kThreads), (size_t)0,
+                         (cudaStream_t)stream, x, B, (long long)M, gmax, out));
+  S2R_LAUNCH_OK();
+  return S2R_OK;
+}
 
 extern "C" int s2r_softmax_dim0_fwd(const float* x, float* y, int B, int64_t M, s2r_stream_t stream) {
   S2R_REQUIRE(B >= 1 && M >= 0, S2R_ERR_SHAPE, "softmax_dim0: bad shape B=%d M=%lld", B, (long long)M);
@@ -556,7 +607,8 @@ extern "C" int s2r_bce_logits_bwd(const float* x, const float* target, float con
 }
 
 template <bool SOFTMAX>
-static int launch_sp_fwd(const float* x, int B, int C, int H, int W, void* yp, int Cp, cudaStream_t st) {
+static int launch_sp_fwd(const float* x, int B, int C, int H, int W, void* yp, int Cp, cudaStream_t st,
+                         const float* gmax = nullptr, const float* gsum = nullptr) {
   const int smem = min(B, SP_MAXB) * SP_TW * Cp * 2;
   static bool attr = false;
   if (!attr) {
@@ -564,13 +616,15 @@ static int launch_sp_fwd(const float* x, int B, int C, int H, int W, void* yp, i
     attr = true;
   }
   dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
-  S2R_CUDA_OK(s2r_launch(softmax0_to_nhwc_pad_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, B, C, H, W, (__nv_bfloat16*)yp, Cp));
+  S2R_CUDA_OK(s2r_launch(softmax0_to_nhwc_pad_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, B, C, H, W, (__nv_bfloat16*)yp, Cp, gmax, gsum));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
 
 template <bool SOFTMAX>
-static int launch_sp_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, float* dx, cudaStream_t st) {
+static int launch_sp_bwd(const float* x, const void* gp, int B, int C, int H, int W, int Cp, float* dx, cudaStream_t st,
+                         const float* gmax = nullptr, const float* gsum = nullptr, float* tpart = nullptr,
+                         const float* tglob = nullptr) {
   const int smem = min(B, SP_MAXB) * SP_TW * Cp * 2;
   static bool attr = false;
   if (!attr) {
@@ -578,7 +632,7 @@ static int launch_sp_bwd(const float* x, const void* gp, int B, int C, int H, in
     attr = true;
   }
   dim3 grid(s2r_div_up(W, SP_TW), H, s2r_div_up(B, SP_MAXB));
-  S2R_CUDA_OK(s2r_launch(softmax0_nhwc_pad_bwd_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, (const __nv_bfloat16*)gp, B, C, H, W, Cp, dx));
+  S2R_CUDA_OK(s2r_launch(softmax0_nhwc_pad_bwd_kernel<SOFTMAX>, dim3(grid), dim3(SP_THREADS), (size_t)(smem), st, x, (const __nv_bfloat16*)gp, B, C, H, W, Cp, dx, gmax, gsum, tpart, tglob));
   S2R_LAUNCH_OK();
   return S2R_OK;
 }
@@ -602,4 +656,29 @@ extern "C" int s2r_softmax0_nhwc_pad_bwd(const float* x, const void* gp, int B, 
   S2R_REQUIRE(!softmax || B <= SP_MAXB, S2R_ERR_UNSUPPORTED, "softmax0_nhwc_pad_bwd: batch %d > %d", B, SP_MAXB);
   return softmax ? launch_sp_bwd<true>(x, gp, B, C, H, W, Cp, dx, (cudaStream_t)stream)
                  : launch_sp_bwd<false>(x, gp, B, C, H, W, Cp, dx, (cudaStream_t)stream);
+}
+
+// F.softmax(x, dim=0) over the GLOBAL batch of a data-parallel run (the reference's DataParallel gathers the logits on one
+// device before train_adapt.py:151,166,174): gmax / gsum = s2r_softmax0_batch_stats all-reduced (MAX, then SUM) over the ranks.
+extern "C" int s2r_softmax0_nchw_to_nhwc_pad_global(const float* x, int B, int C, int H, int W, const float* gmax,
+                                                    const float* gsum, void* yp, int Cp, s2r_stream_t stream) {
+  S2R_REQUIRE(x && yp && gmax && gsum && B >= 1 && C >= 1 && H >= 1 && W >= 1 && H <= 65535, S2R_ERR_SHAPE,
+              "softmax0_to_nhwc_pad_global: bad arguments");
+  S2R_REQUIRE(Cp % 8 == 0 && Cp >= C && Cp <= 64 && (uintptr_t)yp % 16 == 0, S2R_ERR_SHAPE,
+              "softmax0_to_nhwc_pad_global: channel pitch %d (need a multiple of 8 in [C, 64]) / alignment", Cp);
+  S2R_REQUIRE(B <= SP_MAXB, S2R_ERR_UNSUPPORTED, "softmax0_to_nhwc_pad_global: batch %d > %d per rank", B, SP_MAXB);
+  return launch_sp_fwd<true>(x, B, C, H, W, yp, Cp, (cudaStream_t)stream, gmax, gsum);
+}
+
+// Backward of the above in two launches around one all-reduce(SUM): tpart != NULL: tpart[c][h][w] = this rank's part of
+// sum_b' g_b' y_b' (dx untouched); tpart == NULL: dx_b = y_b * (g_b - tglob) with the all-reduced sum in tglob.
+extern "C" int s2r_softmax0_nhwc_pad_bwd_global(const float* x, const void* gp, int B, int C, int H, int W, int Cp,
+                                                const float* gmax, const float* gsum, float* tpart, const float* tglob,
+                                                float* dx, s2r_stream_t stream) {
+  S2R_REQUIRE(x && gp && gmax && gsum && (tpart || (tglob && dx)) && B >= 1 && C >= 1 && H >= 1 && W >= 1 && H <= 65535,
+              S2R_ERR_SHAPE, "softmax0_nhwc_pad_bwd_global: bad arguments");
+  S2R_REQUIRE(Cp % 8 == 0 && Cp >= C && Cp <= 64 && (uintptr_t)gp % 16 == 0, S2R_ERR_SHAPE,
+              "softmax0_nhwc_pad_bwd_global: channel pitch %d (need a multiple of 8 in [C, 64]) / alignment", Cp);
+  S2R_REQUIRE(B <= SP_MAXB, S2R_ERR_UNSUPPORTED, "softmax0_nhwc_pad_bwd_global: batch %d > %d per rank", B, SP_MAXB);
+  return launch_sp_bwd<true>(x, gp, B, C, H, W, Cp, dx, (cudaStream_t)stream, gmax, gsum, tpart, tglob);
 }

@@ -3,6 +3,8 @@ their logits in): batch-axis softmax, ignore-index cross entropy, BCE-with-logit
 autograd node whose forward and backward are single C-ABI kernel launches."""
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -69,6 +71,15 @@ def pop_pending_scale(t):
 # also when the ranks hold different numbers of valid (non-ignored) pixels.  Constant-target calls without class
 # weights (the domain loss, utils/loss.py:57-69) have equal counts on every rank and skip the exchange.
 GLOBAL_BATCH_MEAN = [True]
+
+# F.softmax(x, dim=0) in front of the discriminator (train_adapt.py:151,166,174) over the GLOBAL batch: the reference's
+# single-process nn.DataParallel gathers the logits of all replicas on one device first (train_adapt.py:87-88), so its
+# softmax runs over the images of every GPU.  Off by default -- the north star lists the BatchNorm sums and the gradients
+# as the only exchanges, and this one costs two all-reduces of a [19,H,W] fp32 map per discriminator evaluation plus one
+# per backward pass (5 x 40 MB per adaptation step at 512x1024); S2R_GLOBAL_SOFTMAX0=1 (or setting this flag) selects
+# the exact semantics: FCDiscriminator.forward_softmax0* then exchange the batch maximum, the sum of exponentials and,
+# in the backward pass, the sum of g*y over torch.distributed.
+GLOBAL_SOFTMAX0 = [os.environ.get("S2R_GLOBAL_SOFTMAX0", "0") == "1"]
 
 
 class _CrossEntropy(torch.autograd.Function):

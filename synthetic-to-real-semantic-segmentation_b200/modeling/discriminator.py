@@ -15,6 +15,15 @@ from ..engine import (conv_fwd, conv_dgrad, conv_wgrad, bias_grad, conv_out_hw, 
 from ..runtime import RunBase, call_module
 
 
+def _global_softmax0():
+    """functional.GLOBAL_SOFTMAX0 and more than one rank: the batch-axis softmax runs over the gathered batch."""
+    from .. import functional as _fn
+    if not _fn.GLOBAL_SOFTMAX0[0]:
+        return False
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 class FCDiscriminatorRun(RunBase):
     """conv1 reads its NCHW fp32 argument directly (raw_inputs): the argument -- optionally through the batch-axis
     softmax of train_adapt.py:151,166,174 (softmax0=True, the fused form of `model_D(F.softmax(x, dim=0))`) -- is
@@ -33,11 +42,28 @@ class FCDiscriminatorRun(RunBase):
         if self.rowtap:
             Cp = round_up(x.C, 8)
             xp = PadAct(torch.empty((x.N, x.H + 2, x.W + 2, Cp), dtype=BF16, device=cx.device), x.H, x.W, x.C)
-            L.call("s2r_softmax0_nchw_to_nhwc_pad", _vp(x.t), x.N, x.C, x.H, x.W, 1 if self.softmax0 else 0,
-                   C.c_void_p(xp.ptr), Cp, cx.stream)
+            self.gstat = None
+            if self.softmax0 and _global_softmax0():
+                # the softmax runs over the images of ALL ranks (functional.GLOBAL_SOFTMAX0): batch maximum and sum of
+                # exponentials per (class, pixel), all-reduced, then the normalised values into the padded buffer
+                import torch.distributed as dist
+                M = x.C * x.H * x.W
+                gmax = torch.empty(M, dtype=torch.float32, device=cx.device)
+                gsum = torch.empty(M, dtype=torch.float32, device=cx.device)
+                L.call("s2r_softmax0_batch_stats", _vp(x.t), x.N, M, None, _vp(gmax), cx.stream)
+                dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+                L.call("s2r_softmax0_batch_stats", _vp(x.t), x.N, M, _vp(gmax), _vp(gsum), cx.stream)
+                dist.all_reduce(gsum, op=dist.ReduceOp.SUM)
+                L.call("s2r_softmax0_nchw_to_nhwc_pad_global", _vp(x.t), x.N, x.C, x.H, x.W, _vp(gmax), _vp(gsum),
+                       C.c_void_p(xp.ptr), Cp, cx.stream)
+                self.gstat = (gmax, gsum)
+            else:
+                L.call("s2r_softmax0_nchw_to_nhwc_pad", _vp(x.t), x.N, x.C, x.H, x.W, 1 if self.softmax0 else 0,
+                       C.c_void_p(xp.ptr), Cp, cx.stream)
             self.logits = x.t if self.softmax0 else None
             acts = [xp]
         else:
+            self.gstat = None
             if self.softmax0:
                 raise NotImplementedError("fused softmax input needs even sizes, <= 64 channels and batch <= 8")
             acts = [im2col(cx, x, 4, 4, 2, 1)]   # conv1 as a pointwise GEMM over 4x4 patches
@@ -88,10 +114,21 @@ class FCDiscriminatorRun(RunBase):
                 N, H, W, Cc = self.in_shape
                 dxp = rowtap_dgrad(cx, d, c.weight, H, W)
                 dx = torch.empty((N, Cc, H, W), dtype=torch.float32, device=cx.device)
-                L.call("s2r_softmax0_nhwc_pad_bwd", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
-                       1 if self.softmax0 else 0, _vp(dx), cx.stream)
+                if self.softmax0 and self.gstat is not None:
+                    import torch.distributed as dist
+                    gmax, gsum = self.gstat
+                    tsum = torch.empty(Cc * H * W, dtype=torch.float32, device=cx.device)
+                    L.call("s2r_softmax0_nhwc_pad_bwd_global", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
+                           _vp(gmax), _vp(gsum), _vp(tsum), None, None, cx.stream)
+                    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                    L.call("s2r_softmax0_nhwc_pad_bwd_global", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
+                           _vp(gmax), _vp(gsum), None, _vp(tsum), _vp(dx), cx.stream)
+                else:
+                    L.call("s2r_softmax0_nhwc_pad_bwd", _vp(self.logits), C.c_void_p(dxp.ptr), N, Cc, H, W, dxp.Cp,
+                           1 if self.softmax0 else 0, _vp(dx), cx.stream)
                 if not keep:
                     self.logits = None
+                    self.gstat = None
                 return dx
             if i == 0:
                 N, H, W, Cc = self.in_shape   # gradient w.r.t. the input pixels: the ordinary 4x4 data gradient
@@ -122,6 +159,7 @@ class _SharedForward(object):
         if self.pending <= 0 and self.run is not None:
             self.run.acts = None
             self.run.logits = None
+            self.run.gstat = None
             self.run = None
 
 

@@ -8,9 +8,10 @@ reference; losses stay on the device (no per-step .item()).
 
 Data parallel (one process per GPU): each rank runs the step on its shard of the batch; BN
 statistics are all-reduced inside the engine when the model was built with sync_bn=True, and the
-flat gradient buffers are all-reduced (averaged) before the optimizer steps.  Deviation from the
-single-process DataParallel of the reference, stated in DESIGN.md: the cross-entropy mean and
-F.softmax(dim=0) are taken over the rank-local batch.
+flat gradient buffers are all-reduced (averaged) before the optimizer steps.  The cross-entropy mean is the
+global-batch one (functional.GLOBAL_BATCH_MEAN).  Deviation from the single-process DataParallel of the
+reference, stated in DESIGN.md: F.softmax(dim=0) is taken over the rank-local batch unless
+functional.GLOBAL_SOFTMAX0 (S2R_GLOBAL_SOFTMAX0=1) asks for the gathered-batch semantics.
 """
 import os
 

@@ -179,3 +179,99 @@ def test_two_ranks_sync_bn_global_ce_and_identical_weights(built_lib):
     assert len(errs) == 60 and errs[len(errs) // 2] <= 2e-2 and errs[-1] <= 2.5e-1, errs[-5:]
     # gradient of the global-mean loss (all-reduced and divided by the world size) at the classifier
     assert r0["cls_grad_err"] <= 0.2, r0["cls_grad_err"]
+
+
+def _softmax_worker(rank, world, port, q):
+    import importlib
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    res = {}
+    try:
+        dev = torch.device("cuda", rank % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sub = lambda n: importlib.import_module(PKG + "." + n)      # noqa: E731
+        fn = sub("functional")
+        torch.manual_seed(3)
+        D = sub("modeling.discriminator").FCDiscriminator(num_classes=19).to(dev).train()
+        g = torch.Generator().manual_seed(7)
+        x_all = (torch.randn(4, 19, 64, 96, generator=g) * 2.0).to(dev)
+        w_all = torch.randn(4, 1, 2, 3, generator=g).to(dev)          # loss_r = sum(out_r * w_r): a different g per image
+        per = 4 // world
+        sl = slice(rank * per, (rank + 1) * per)
+
+        def run(x, w, flag):
+            fn.GLOBAL_SOFTMAX0[0] = flag
+            try:
+                for p in D.parameters():
+                    p.grad = None
+                xr = x.clone().requires_grad_(True)
+                out = D.forward_softmax0(xr)
+                (out * w).sum().backward()
+                torch.cuda.synchronize(dev)
+                return out.detach().double().cpu(), xr.grad.detach().double().cpu(), D.conv1.weight.grad.detach().double().cpu()
+            finally:
+                fn.GLOBAL_SOFTMAX0[0] = False
+
+        out_g, dx_g, dw_g = run(x_all[sl], w_all[sl], True)            # sharded, global softmax (exchanged)
+        out_l, dx_l, _ = run(x_all[sl], w_all[sl], False)              # sharded, rank-local softmax (the default)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (out_g, dx_g, dw_g))
+        if rank == 0:
+            out_1, dx_1, dw_1 = run(x_all, w_all, False)               # one process, the whole batch: the reference semantics
+            rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))   # noqa: E731
+            res["out"] = rel(torch.cat([t[0] for t in gathered]), out_1)
+            res["dx"] = rel(torch.cat([t[1] for t in gathered]), dx_1)
+            res["dw"] = rel(sum(t[2] for t in gathered), dw_1)
+            res["local_vs_global_out"] = rel(out_l, out_1[sl])
+            # and against fp32 torch on the gathered batch
+            import torch.nn.functional as F
+            xr = x_all.detach().clone().requires_grad_(True)
+            h = F.softmax(xr, dim=0)
+            for i, c in enumerate([D.conv1, D.conv2, D.conv3, D.conv4, D.classifier]):
+                h = F.conv2d(h, c.weight.detach(), c.bias.detach(), stride=2, padding=1)
+                if i < 4:
+                    h = F.leaky_relu(h, 0.2)
+            (h * w_all).sum().backward()
+            res["out_fp32"] = rel(torch.cat([t[0] for t in gathered]), h.detach().double().cpu())
+            res["dx_fp32"] = rel(torch.cat([t[1] for t in gathered]), xr.grad.double().cpu())
+        q.put((rank, "ok", res))
+    except Exception as e:   # noqa: BLE001
+        import traceback
+        q.put((rank, "%s: %s\n%s" % (type(e).__name__, e, traceback.format_exc()), res))
+    finally:
+        try:
+            dist.destroy_process_group()
+        except Exception:   # noqa: BLE001
+            pass
+
+
+def test_two_ranks_global_batch_softmax_in_front_of_the_discriminator(built_lib):
+    """functional.GLOBAL_SOFTMAX0: `model_D(F.softmax(x, dim=0))` (train_adapt.py:151,166,174) with the softmax taken
+    over the batch of ALL ranks, as the reference's single-process DataParallel does on the gathered logits
+    (train_adapt.py:87-88).  Two ranks with two images each, statistics exchanged (max, sum of exponentials; sum of
+    g*y in the backward pass), against ONE process running the same kernels on the four images: output, gradient
+    w.r.t. the logits (which couples the ranks through the normalisation) and the summed weight gradient; and against
+    fp32 torch on the gathered batch.  The default (rank-local softmax) is measurably something else."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_softmax_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        got = [q.get(timeout=300) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    res = {r: (status, info) for r, status, info in got}
+    assert res[0][0] == "ok" and res[1][0] == "ok", res
+    r0 = res[0][1]
+    print("global batch softmax on two ranks vs one process: out %.2e dx %.2e dw %.2e | vs fp32 torch: out %.2e dx %.2e | "
+          "rank-local softmax vs the reference semantics: out %.2e" % (r0["out"], r0["dx"], r0["dw"], r0["out_fp32"],
+                                                                      r0["dx_fp32"], r0["local_vs_global_out"]))
+    assert r0["out"] <= 2e-3 and r0["dx"] <= 5e-3 and r0["dw"] <= 5e-3, r0
+    assert r0["out_fp32"] <= 1e-2 and r0["dx_fp32"] <= 1e-1, r0
+    assert r0["local_vs_global_out"] >= 1e-1, r0          # the stated deviation of the default is real
