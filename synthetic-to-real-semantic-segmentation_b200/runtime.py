@@ -7,10 +7,12 @@ and executes it on the C-ABI kernels; its backward executes the run's hand-writt
 accumulates parameter gradients straight into `.grad`.
 """
 
+import os
+
 import torch
 
 from . import _lib as L
-from .engine import Ctx, RawNCHW, round_up, _vp, bn_eval_all
+from .engine import Act, Ctx, RawNCHW, round_up, _vp, bn_eval_all
 
 
 def init_reference_weights(module):
@@ -36,10 +38,31 @@ def sync_group_for(module):
     return dist.group.WORLD
 
 
-def to_nhwc(cx, x):
+# Zero-copy hand-off between drop-in modules (train.py:182-196 chains four of them: backbone -> ASPP -> decoder, and the
+# domain classifier on the backbone's features).  to_nchw() remembers on the fp32 tensor it returns which NHWC bf16
+# buffer it was converted from; when that very tensor -- same object, same version counter -- comes back as the input
+# (or, in the backward pass, as the incoming gradient) of another module, to_nhwc() hands out the bf16 buffer instead of
+# converting the fp32 copy back.  bf16 -> fp32 -> bf16 is the identity, so the values are the same bit for bit.  An
+# incoming GRADIENT is taken only once (consume=True): a module's backward may accumulate into it in place.
+# S2R_ZERO_COPY=0 disables the hand-off.
+ZERO_COPY = [os.environ.get("S2R_ZERO_COPY", "1") != "0"]
+
+
+def to_nhwc(cx, x, consume=False):
     """NCHW fp32 -> NHWC bf16 (channels zero-padded to a multiple of 8)."""
     if x.dim() != 4:
         raise ValueError('expected 4D input (got {}D input)'.format(x.dim()))
+    src = getattr(x, "_s2r_act", None)
+    if src is not None and ZERO_COPY[0]:
+        a, version = src
+        if consume:
+            try:
+                del x._s2r_act
+            except AttributeError:
+                pass
+        if (version == x._version and x.dtype == torch.float32 and a.t.device == x.device
+                and (a.N, a.C, a.H, a.W) == tuple(x.shape)):
+            return Act(a.t, a.C, a.off)
     x = x.contiguous()
     if x.dtype != torch.float32:
         x = x.float()
@@ -54,6 +77,8 @@ def to_nchw(cx, a, Cc=None):
     Cc = a.C if Cc is None else Cc
     y = torch.empty((a.N, Cc, a.H, a.W), dtype=torch.float32, device=cx.device)
     L.call("s2r_nhwc_bf16_to_nchw_f32", a.vp(), a.pitch, a.N, Cc, a.H * a.W, _vp(y), cx.stream)
+    if Cc == a.C:
+        y._s2r_act = (a, y._version)      # see ZERO_COPY
     return y
 
 
@@ -121,7 +146,7 @@ class RunBase:
     def import_grad(self, cx, i, d):
         if d is None:
             return None
-        return to_nhwc(cx, d)
+        return to_nhwc(cx, d, consume=True)
 
 
 _CALLER_GRAD = [True]

@@ -218,6 +218,67 @@ def test_backbone_aspp_decoder_as_separate_modules(built_lib):
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
 
 
+
+def test_zero_copy_hand_off_between_modules_is_bit_identical(built_lib):
+    """runtime.ZERO_COPY: a module that receives the very fp32 tensor another drop-in module returned (train.py:182-196:
+    backbone -> ASPP -> decoder, domain classifier on the backbone's features) takes the producer's NHWC bf16 buffer
+    instead of converting the fp32 copy back -- in the forward pass and for the gradients in the backward pass.  Same
+    values bit for bit in the forward pass, same gradients up to the order of the weight-gradient atomics; fewer launches;
+    a tensor that was modified in place, detached or re-created is converted as before."""
+    nn = torch.nn
+    rt, L = sub("runtime"), sub("_lib")
+    torch.manual_seed(4)
+    bb = sub("modeling.backbone.mobilenet").MobileNetV2(output_stride=16, BatchNorm=nn.BatchNorm2d).cuda().train()
+    aspp = sub("modeling.assp").ASPP('mobilenet', 16, nn.BatchNorm2d).cuda().train()
+    dec = sub("modeling.decoder").Decoder(19, 'mobilenet', nn.BatchNorm2d).cuda().train()
+    dc = sub("modeling.domian").DomainClassifer('mobilenet', nn.BatchNorm2d).cuda().train()
+    mods = (bb, aspp, dec, dc)
+    for mod in mods:
+        mod._s2r_no_dropout = True
+    sd0 = [{k: v.detach().clone() for k, v in mod.state_dict().items()} for mod in mods]
+    x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
+    gy = torch.randn(2, 19, 32, 24, generator=torch.Generator().manual_seed(2)).cuda()
+    res = {}
+    for zc in (True, False):
+        rt.ZERO_COPY[0] = zc
+        try:
+            for mod, sd in zip(mods, sd0):
+                mod.load_state_dict(sd)
+                for p in mod.parameters():
+                    p.grad = None
+            n0 = L.launches
+            hi, lo = bb(x)
+            hi2 = aspp(hi)
+            y = dec(hi2, lo)
+            dom = dc(hi2)
+            ((y * gy).sum() + dom.sum()).backward()
+            torch.cuda.synchronize()
+            res[zc] = (L.launches - n0, [t.detach().clone() for t in (hi, lo, hi2, y, dom)],
+                       {(i, k): p.grad.detach().clone() for i, mod in enumerate(mods) for k, p in mod.named_parameters()})
+        finally:
+            rt.ZERO_COPY[0] = True
+    assert res[True][0] < res[False][0], (res[True][0], res[False][0])
+    for a, b in zip(res[True][1], res[False][1]):
+        assert torch.equal(a, b)
+    worst = max(rel(res[True][2][k], v) for k, v in res[False][2].items())
+    print("zero-copy hand-off: %d instead of %d launches; worst parameter-gradient difference %.2e" % (res[True][0], res[False][0], worst))
+    assert worst <= 1e-4
+    # an input that is not the producer's tensor any more is converted
+    hi, lo = bb(x)
+    assert getattr(hi, "_s2r_act", None) is not None
+    n0 = L.launches
+    aspp(hi)
+    with_copy = L.launches - n0
+    hi_mod = hi.detach().clone()
+    n0 = L.launches
+    out_a = aspp(hi_mod)
+    assert L.launches - n0 == with_copy + 1
+    hi.detach().mul_(1.0)                      # in-place write through an alias bumps the version: the hand-off is off
+    n0 = L.launches
+    out_b = aspp(hi)
+    assert L.launches - n0 == with_copy + 1
+
+
 def test_discriminator_vs_fixture(built_lib):
     fix = golden('discriminator')
     torch.manual_seed(2)
