@@ -57,6 +57,10 @@ def softmax_dim0(x):
 # Off by default: any other consumer (user code, hooks) sees the fully scaled gradient.
 DEFER_CE_SCALE = [False]
 PENDING_SCALE = {}
+# The same, decided when the loss is EVALUATED: a cross entropy computed while DEFER_NEXT is set defers its scale in
+# whatever backward pass it later takes part in (steps.FeatureStep sums the task loss with the domain losses and
+# calls backward once: only the task loss feeds an up-sampling backward kernel that can take the factor).
+DEFER_NEXT = [False]
 
 
 def pop_pending_scale(t):
@@ -112,6 +116,7 @@ class _CrossEntropy(torch.autograd.Function):
         ctx.grad = grad
         ctx.sums = sums
         ctx.world = world
+        ctx.defer = bool(DEFER_NEXT[0])
         if stats_out is not None:
             stats_out.append(sums)
         return out
@@ -123,7 +128,7 @@ class _CrossEntropy(torch.autograd.Function):
         gout = gout.contiguous().float()
         if ctx.world > 1:
             gout = gout * float(ctx.world)      # see GLOBAL_BATCH_MEAN
-        if DEFER_CE_SCALE[0]:
+        if DEFER_CE_SCALE[0] or ctx.defer:
             PENDING_SCALE.clear()          # at most one pending gradient: a stale entry must never meet a recycled address
             PENDING_SCALE[grad.data_ptr()] = (gout.double() / sums[1]).float().reshape(1)
             return grad, None, None, None, None, None

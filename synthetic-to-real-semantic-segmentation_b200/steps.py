@@ -415,7 +415,13 @@ class FeatureStep(_StagedInputs):
         self.d_optimizer.zero_grad()
         prepack_weights(torch.cuda.current_stream(src_image.device).cuda_stream)
         src_output, src_d_pred = self._forward(src_image)
-        task_loss = self.task_loss(src_output, src_label)
+        # the task loss's gradient goes straight into the decoder's fused up-sampling backward, which takes the mean
+        # reduction's factor along (functional.DEFER_NEXT): no scaling pass over the N x 19 x H x W gradient
+        _fn.DEFER_NEXT[0] = type(self.y).__name__ == 'Decoder'
+        try:
+            task_loss = self.task_loss(src_output, src_label)
+        finally:
+            _fn.DEFER_NEXT[0] = False
         if tgt_image is None:
             # train.py:205-210: the domain classifier ran on the source features (:187, its BatchNorm statistics
             # moved) but only the task loss is back-propagated and only task_optimizer steps
@@ -433,6 +439,9 @@ class FeatureStep(_StagedInputs):
         d_inv_loss, _ = self.domain_loss(tgt_d_pred, src_d_pred)
         loss = task_loss + d_loss + d_inv_loss
         loss.backward()
+        if _fn.PENDING_SCALE:
+            _fn.PENDING_SCALE.clear()
+            raise RuntimeError("deferred cross-entropy scale was not consumed by the decoder's backward")
         self.task_optimizer.all_reduce_grads()
         self.d_optimizer.all_reduce_grads()
         for o in self._optimizers():
