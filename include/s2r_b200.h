@@ -147,7 +147,8 @@ int s2r_rowtap_wgrad_scatter(const float* G, float* dw, int Cout, int Cin, s2r_s
  * s2r_conv_wgrad (s_ci = 1: coalesced atomics) added into the OIHW gradient. */
 int s2r_wgrad_scatter_taps(const float* G, float* dw, int Cout, int Cin, int RS, int Cp, s2r_stream_t stream);
 /* The same for many filters in one launch.  A job packs the elements [begin, end) of one packed filter
- * (flattened [R*S][A_pad][B_pad] index); the table lives in device memory. */
+ * (flattened [R*S][A_pad][B_pad] index); the table lives in device memory.  transpose = mode + 16 (modes 0 / 1 only):
+ * [begin, end) counts (a, b) pairs of the [A_pad][B_pad] plane instead and the job writes all R*S taps of each pair. */
 typedef struct s2r_pack_job {
   const float* w;
   void* packed;

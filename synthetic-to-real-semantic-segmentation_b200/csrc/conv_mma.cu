@@ -489,6 +489,23 @@ __global__ void pack_weights_multi_kernel(const s2r_pack_job* __restrict__ jobs)
   const s2r_pack_job j = jobs[blockIdx.y];
   const float* __restrict__ w = j.w;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.packed);
+  if (j.transpose & 16) {
+    // modes 0 / 1, several taps: [begin, end) counts (a, b) PAIRS and a thread writes all RS taps of its pair -- the RS
+    // source floats of a pair are contiguous in the OIHW filter (36 bytes of a 3x3 filter), so a warp of consecutive b
+    // (mode 0: consecutive input channels) reads one contiguous run once instead of RS strided passes over it, and the
+    // index arithmetic is paid once per pair
+    const int mode = j.transpose & 15;
+    const unsigned B = (unsigned)j.B_pad, end = (unsigned)j.end;
+    const size_t slice = (size_t)j.A_pad * j.B_pad;
+    for (unsigned i = (unsigned)j.begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+      const unsigned a = i / B, b = i - a * B;
+      const int co = mode ? (int)b : (int)a, ci = mode ? (int)a : (int)b;
+      const bool in = co < j.Cout && ci < j.Cin;
+      const float* src = w + ((size_t)co * j.Cin + ci) * j.RS;
+      for (int t = 0; t < j.RS; ++t) out[(size_t)t * slice + i] = __float2bfloat16(in ? __ldg(src + t) : 0.f);
+    }
+    return;
+  }
   if (j.end <= 0x7fffffffLL) {
     // 32-bit index arithmetic: the three div / mod pairs per element are ~10 instructions each in 32 bits and ~40 in
     // 64 bits, and they were most of this kernel (149 us per feature-adaptation step for 19 M elements)

@@ -329,10 +329,13 @@ def prepack_weights(stream, build_only=False):
         jobs = []
         for w, transpose, ent, _ in stale:
             Cout, Cin, RS, ns, A_pad, B_pad = _pack_dims(w, transpose)
-            total = ns * A_pad * B_pad
-            for b in range(0, total, _PACK_JOB_ELEMS):
-                jobs.append((w.data_ptr(), ent[1].data_ptr(), Cout, Cin, RS, int(transpose), A_pad, B_pad, b,
-                             min(total, b + _PACK_JOB_ELEMS)))
+            if int(transpose) <= 1 and RS > 1:
+                # several taps: a job covers (a, b) pairs and writes all taps of each (contiguous in the OIHW source)
+                total, mode, per = A_pad * B_pad, int(transpose) + 16, max(256, _PACK_JOB_ELEMS // RS)
+            else:
+                total, mode, per = ns * A_pad * B_pad, int(transpose), _PACK_JOB_ELEMS
+            for b in range(0, total, per):
+                jobs.append((w.data_ptr(), ent[1].data_ptr(), Cout, Cin, RS, mode, A_pad, B_pad, b, min(total, b + per)))
         chunks = []
         for s0 in range(0, len(jobs), 65535):
             part = jobs[s0:s0 + 65535]

@@ -181,6 +181,39 @@ def test_fused_upsample_argmax_confusion_bit_exact(eng, cx, shape):
     assert int(one.sum()) == int(((gt >= 0) & (gt < nc)).sum())
 
 
+
+def test_prepack_weights_multi_equals_single_pack(eng, cx):
+    """prepack_weights (ONE launch re-packing every stale bf16 filter copy; several-tap filters through the
+    tap-loop jobs of s2r_pack_weights_multi) against s2r_pack_weight filter by filter: bit-identical buffers for
+    3x3 / 4x4 / 1x1 filters, ragged channel counts, forward and data-gradient orientation."""
+    L = sub("_lib")
+    g = torch.Generator(device="cuda").manual_seed(12)
+    shapes = [(24, 19, 3, 3), (320, 257, 3, 3), (64, 24, 4, 4), (96, 16, 1, 1), (33, 70, 3, 3)]
+    ws = [torch.nn.Parameter(torch.randn(*sh, device="cuda", generator=g)) for sh in shapes]
+    for w in ws:
+        for mode in (0, 1):
+            eng.packed_weight(cx, w, mode)
+    with torch.no_grad():
+        for w in ws:
+            w.mul_(1.5).add_(0.25)              # bumps the version: every copy is stale
+    n = eng.prepack_weights(cx.stream)
+    assert n == 2 * len(ws)
+    torch.cuda.synchronize()
+    for w in ws:
+        for mode in (0, 1):
+            buf, A_pad, B_pad = eng.packed_weight(cx, w, mode)      # cache hit: the multi launch's result
+            Cout, Cin, RS, ns, A2, B2 = eng._pack_dims(w, mode)
+            ref = torch.empty((ns, A2, B2), dtype=torch.bfloat16, device="cuda")
+            L.call("s2r_pack_weight", C.c_void_p(w.data_ptr()), Cout, Cin, w.shape[2], w.shape[3], mode,
+                   C.c_void_p(ref.data_ptr()), A2, B2, cx.stream)
+            torch.cuda.synchronize()
+            assert (A_pad, B_pad) == (A2, B2) and torch.equal(buf.view(torch.int16), ref.view(torch.int16)), (tuple(w.shape), mode)
+            want = w.detach().permute(2, 3, 1, 0) if mode else w.detach().permute(2, 3, 0, 1)
+            want = want.reshape(RS, *want.shape[2:]).to(torch.bfloat16)
+            assert torch.equal(buf[:, :want.shape[1], :want.shape[2]], want)
+            assert float(buf[:, want.shape[1]:, :].float().abs().sum()) == 0 and float(buf[:, :, want.shape[2]:].float().abs().sum()) == 0
+
+
 DW_CASES = [(2, 18, 26, 32, 1, 1, False), (2, 17, 25, 96, 2, 1, True), (2, 16, 24, 144, 1, 1, True),
             (1, 9, 13, 960, 1, 2, True), (2, 12, 12, 192, 2, 1, True), (1, 10, 10, 384, 1, 1, True),
             # streaming stride-1 kernels: several column tiles / row segments, 32-, 48- and 16-channel chunks
